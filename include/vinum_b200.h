@@ -1,0 +1,266 @@
+/*
+ * vinum_b200 -- C ABI of the B200-native (sm_100a) physical operators that replace
+ * Vinum's CPU operators on its one data-parallel hot path:
+ *   comparison/filter -> projection/arithmetic -> hash group-by aggregate -> sort
+ * over Arrow column chunks resident in HBM.
+ *
+ * This header is the drop-in boundary.  Everything is `extern "C"`, plain pointers
+ * and sizes; no C++/torch/Arrow types cross it.  Every entry point cites the
+ * reference interface (path:line under the reference checkout) it replaces.
+ *
+ * Conventions
+ *   - every function returns VK_OK (0) or a negative VK_ERR_* code; the message is
+ *     available from vk_last_error() (thread-local).  Nothing aborts or throws
+ *     (reference: `.ValueOrDie()` aborts at vinum/core/vinum_lib.cpp:62-63 and
+ *     RAISE_ON_ARROW_FAILURE throws at vinum_cpp/src/common/util.h:4-11).
+ *   - all `data` / `validity` / `mask` / output pointers are DEVICE pointers owned by
+ *     the caller unless a parameter is explicitly named `host_*`.
+ *   - a column is described exactly like an Arrow primitive array: values buffer,
+ *     optional validity bitmap (LSB-first, 1 = valid), element offset, length.
+ *   - one CUDA stream per call (`VkStream` is a cudaStream_t; NULL = legacy default
+ *     stream).  Calls are asynchronous with respect to the host unless documented
+ *     otherwise.  Objects are thread-compatible, not thread-safe (same as the
+ *     reference's operators, which run under the GIL).
+ */
+#ifndef VINUM_B200_H
+#define VINUM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VK_ABI_VERSION 1
+
+#define VK_OK 0
+#define VK_ERR_CUDA (-1)        /* a CUDA runtime call or kernel failed             */
+#define VK_ERR_ARG (-2)         /* invalid argument                                  */
+#define VK_ERR_UNSUPPORTED (-3) /* dtype / op combination not implemented on device  */
+#define VK_ERR_OOM (-4)         /* device or pinned-host allocation failed           */
+#define VK_ERR_STATE (-5)       /* object used in the wrong state                    */
+
+typedef void* VkStream; /* cudaStream_t */
+typedef void* VkEvent;  /* cudaEvent_t  */
+
+/* Physical element types.  Arrow date32/time32 map to VK_I32; date64/time64/
+ * timestamp/duration map to VK_I64 (the reference treats them the same way through
+ * NumericArrayIter<T>, vinum_cpp/src/common/array_iterators.cpp:7-46). */
+typedef enum VkDType {
+    VK_I8 = 1, VK_I16 = 2, VK_I32 = 3, VK_I64 = 4,
+    VK_U8 = 5, VK_U16 = 6, VK_U32 = 7, VK_U64 = 8,
+    VK_F32 = 9, VK_F64 = 10,
+    VK_BOOL8 = 11 /* one byte per row, 0/1: a NumPy `bool_` mask (expressions.py:30-36) */
+} VkDType;
+
+/* Device view of one Arrow primitive array (replaces arrow::NumericArray<T> as seen
+ * by NumericArrayIter::SetArray, vinum_cpp/src/common/array_iterators.h:180-187). */
+typedef struct VkColumn {
+    const void* data;        /* values buffer (element 0 of the buffer, NOT of the slice) */
+    const uint8_t* validity; /* Arrow validity bitmap or NULL when there are no nulls      */
+    int64_t offset;          /* slice offset in elements (applies to data and validity)    */
+    int64_t length;          /* number of rows                                             */
+    int32_t dtype;           /* VkDType                                                    */
+    int32_t nulls_as_nan;    /* 1: load through the reference's NumPy view semantics:
+                                NULL -> NaN and the column is read as float64
+                                (vinum/arrow/record_batch.py:100-125)                      */
+} VkColumn;
+
+typedef struct VkScalar {
+    int32_t dtype; /* VK_I64, VK_U64 or VK_F64 */
+    int32_t _pad;
+    union { int64_t i; uint64_t u; double f; } v;
+} VkScalar;
+
+/* ---------------------------------------------------------------- runtime -- */
+int vk_abi_version(void);
+const char* vk_last_error(void);
+int vk_device_count(int* out_n);
+int vk_set_device(int device);
+int vk_get_device(int* out_device);
+int vk_device_info(int device, int* out_sm_count, int* out_cc_major, int* out_cc_minor,
+                   uint64_t* out_total_bytes, uint64_t* out_free_bytes);
+int vk_malloc(void** out_ptr, uint64_t bytes, VkStream stream);   /* stream-ordered pool */
+int vk_free(void* ptr, VkStream stream);
+int vk_host_alloc(void** out_ptr, uint64_t bytes);                /* pinned host memory  */
+int vk_host_free(void* ptr);
+int vk_host_register(void* ptr, uint64_t bytes);                  /* pin an Arrow buffer */
+int vk_host_unregister(void* ptr);
+int vk_memcpy_h2d(void* dst, const void* host_src, uint64_t bytes, VkStream stream);
+int vk_memcpy_d2h(void* host_dst, const void* src, uint64_t bytes, VkStream stream);
+int vk_memcpy_d2d(void* dst, const void* src, uint64_t bytes, VkStream stream);
+int vk_memset(void* dst, int byte, uint64_t bytes, VkStream stream);
+int vk_stream_create(VkStream* out_stream);
+int vk_stream_destroy(VkStream stream);
+int vk_stream_sync(VkStream stream);
+int vk_device_sync(void);
+int vk_event_create(VkEvent* out_event);
+int vk_event_destroy(VkEvent event);
+int vk_event_record(VkEvent event, VkStream stream);
+int vk_event_sync(VkEvent event);
+int vk_event_elapsed_ms(VkEvent start, VkEvent stop, float* out_ms);
+/* number of kernels this library has launched since load (bench.py `gpu_launches`) */
+uint64_t vk_launch_count(void);
+
+/* ------------------------------------------------- synthetic table (8d) ---- */
+/* Deterministic, shard-regenerable columns: value(row r, column c) is a pure
+ * function of splitmix64(r*16 + c + seed*0x9E3779B97F4A7C15); the same formulas
+ * are restated in NumPy in vinum_b200/datagen.py, so any row range is bit-identical
+ * on host and device.  `kind` is a VkGenKind. */
+typedef enum VkGenKind {
+    VK_GEN_I0 = 0,  /* int64  u % 1000                       */
+    VK_GEN_I1 = 1,  /* int64  uniform in [-2^40, 2^40)       */
+    VK_GEN_I2 = 2,  /* int64  global row id                  */
+    VK_GEN_I3 = 3,  /* int64  u % 1000000                    */
+    VK_GEN_F0 = 4,  /* f64    uniform [0,1)                  */
+    VK_GEN_F1 = 5,  /* f64    uniform [-1000,1000)           */
+    VK_GEN_F2 = 6,  /* f64    sum of 4 uniforms - 2          */
+    VK_GEN_F3 = 7,  /* f64    uniform [0,1e6)                */
+    VK_GEN_K32 = 8  /* int32  u % 1000                       */
+} VkGenKind;
+int vk_datagen(int kind, uint64_t seed, int64_t row0, int64_t nrows, void* out, VkStream stream);
+
+/* ------------------------------------------------ comparison -> mask (a1) -- */
+/* Replaces the NumPy comparison lambdas of vinum/core/expressions.py:30-36.
+ * out_mask: one byte per row (NumPy bool_).  NULL rows (when nulls_as_nan) compare
+ * as NaN: every op is false except NE (record_batch.py:112-118 + IEEE). */
+typedef enum VkCmpOp { VK_EQ = 0, VK_NE = 1, VK_GT = 2, VK_GE = 3, VK_LT = 4, VK_LE = 5 } VkCmpOp;
+int vk_compare_scalar(const VkColumn* lhs, int op, const VkScalar* rhs, uint8_t* out_mask,
+                      VkStream stream);
+int vk_compare_columns(const VkColumn* lhs, int op, const VkColumn* rhs, uint8_t* out_mask,
+                       VkStream stream);
+/* BETWEEN / NOT BETWEEN, expressions.py:43-48: (x >= lo) & (x <= hi) / (x < lo) | (x > hi) */
+int vk_between_scalar(const VkColumn* x, const VkScalar* lo, const VkScalar* hi, int negate,
+                      uint8_t* out_mask, VkStream stream);
+/* IN / NOT IN over a literal list, expressions.py:39-40 (np.isin).  `host_values`
+ * are n_values scalars of one dtype, read on the host during the call. */
+int vk_isin_scalars(const VkColumn* x, const VkScalar* host_values, int n_values, int negate,
+                    uint8_t* out_mask, VkStream stream);
+
+/* ------------------------------------------- boolean mask combine (a2) ----- */
+/* Replaces pc.and_/or_/invert and pc.is_null/is_valid, expressions.py:27-29,37-38.
+ * Masks are null-free byte masks on the numeric path. */
+typedef enum VkMaskOp { VK_MASK_AND = 0, VK_MASK_OR = 1, VK_MASK_NOT = 2 } VkMaskOp;
+int vk_mask_combine(int op, const uint8_t* a, const uint8_t* b /* NULL for NOT */, int64_t n,
+                    uint8_t* out_mask, VkStream stream);
+int vk_is_null(const VkColumn* x, int want_valid, uint8_t* out_mask, VkStream stream);
+/* byte mask <-> Arrow bit-packed boolean (pa.array(np_bool), record_batch.py:86-87) */
+int vk_mask_to_bits(const uint8_t* mask, int64_t n, uint8_t* out_bits, VkStream stream);
+int vk_bits_to_mask(const uint8_t* bits, int64_t bit_offset, int64_t n, uint8_t* out_mask,
+                    VkStream stream);
+
+/* --------------------------------------------- filter / compaction (a4) ---- */
+/* Replaces RecordBatch.filter -> pa.RecordBatch.filter(mask) (vinum/arrow/
+ * record_batch.py:85-90, called from FilterOperator._kernel, vinum/core/
+ * algebra.py:119-123): order-preserving stream compaction of EVERY column.
+ *
+ * The predicate is either a byte mask (pred_kind = VK_PRED_MASK) or a fused
+ * `column <op> scalar` comparison evaluated in registers (VK_PRED_CMP), so the
+ * mask is never materialised.  out_cols[i].data must have room for cols[i].length
+ * elements; out_valid_bytes[i] (may be NULL when cols[i].validity is NULL)
+ * receives one validity byte per selected row.  *out_rows (device int64) receives
+ * the number of selected rows.  `scratch` is vk_filter_scratch_bytes(n) bytes. */
+typedef enum VkPredKind { VK_PRED_NONE = 0, VK_PRED_MASK = 1, VK_PRED_CMP = 2 } VkPredKind;
+typedef struct VkPredicate {
+    int32_t kind;          /* VkPredKind                                   */
+    int32_t op;            /* VkCmpOp (VK_PRED_CMP)                        */
+    const uint8_t* mask;   /* VK_PRED_MASK: one byte per row               */
+    VkColumn column;       /* VK_PRED_CMP: left-hand side                  */
+    VkScalar scalar;       /* VK_PRED_CMP: right-hand side                 */
+} VkPredicate;
+uint64_t vk_filter_scratch_bytes(int64_t n_rows);
+int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int n_cols,
+              void* const* out_data, uint8_t* const* out_valid_bytes, int64_t* out_rows,
+              void* scratch, VkStream stream);
+
+/* ------------------------------------------ arithmetic projection (a5) ----- */
+/* Replaces the NumPy ufuncs of vinum/core/expressions.py:13-24.  NumPy semantics:
+ * `/` is true division (float64 out), `%` is floor-mod, integers wrap.  The caller
+ * passes the NumPy result dtype as out_dtype.  Compiled with -fmad=false so float
+ * results are bit-identical to NumPy's single IEEE operations. */
+typedef enum VkArithOp {
+    VK_ADD = 0, VK_SUB = 1, VK_MUL = 2, VK_DIV = 3, VK_MOD = 4,
+    VK_BITAND = 5, VK_BITOR = 6, VK_BITXOR = 7,
+    VK_NEG = 8, VK_BITNOT = 9
+} VkArithOp;
+/* lhs/rhs: exactly one of (column, scalar) is non-NULL per side; for unary ops rhs
+ * side is entirely NULL. */
+int vk_arith(int op, const VkColumn* lhs_col, const VkScalar* lhs_scalar, const VkColumn* rhs_col,
+             const VkScalar* rhs_scalar, int64_t n_rows, int out_dtype, void* out, VkStream stream);
+
+/* ------------------------------------------------ hash aggregate (a8-a14) -- */
+/* Replaces BaseAggregate / SingleNumericalHashAggregate / MultiNumericalHashAggregate
+ * / OneGroupAggregate (vinum_cpp/src/operators/aggregate/*.cpp) and the aggregate
+ * functions of agg_funcs.h.  A VkAgg is the streaming state of ONE operator: created
+ * once, fed every batch with vk_agg_update (== BaseAggregate::Next,
+ * base_aggregate.cpp:23-45), asked once for the result (== Result, :47-68).
+ *
+ * Keys are normalised exactly like NextAsUInt64 (array_iterators.h:215-217,239-248):
+ * integers sign-extend to u64, floats bit-cast; a NULL key is its own group. */
+typedef enum VkAggFunc {
+    VK_AGG_COUNT_STAR = 0, VK_AGG_COUNT = 1, VK_AGG_MIN = 2, VK_AGG_MAX = 3,
+    VK_AGG_SUM = 4, VK_AGG_AVG = 5
+} VkAggFunc;
+typedef struct VkAgg VkAgg;
+#define VK_AGG_MAX_KEYS 8
+#define VK_AGG_MAX_FUNCS 16
+/* key_dtypes[n_keys]; funcs[n_funcs] with func_in_dtypes[i] the input column dtype
+ * (ignored for COUNT_STAR).  n_keys == 0 is the un-grouped OneGroupAggregate. */
+int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_funcs,
+                  const int32_t* funcs, const int32_t* func_in_dtypes, int64_t expected_groups);
+int vk_agg_destroy(VkAgg* agg);
+/* One batch.  keys[n_keys], values[n_funcs] (values[i] ignored for COUNT_STAR; may
+ * alias).  `pred` may be NULL (no filter) -- a non-NULL predicate fuses the WHERE
+ * clause into the aggregation pass (north-star filter->hash-agg pipeline). */
+int vk_agg_update(VkAgg* agg, const VkPredicate* pred, int64_t n_rows, const VkColumn* keys,
+                  const VkColumn* values, VkStream stream);
+/* Number of groups so far (synchronises the stream). */
+int vk_agg_num_groups(VkAgg* agg, int64_t* out_groups, VkStream stream);
+/* Finalised, dense result (device buffers, each with room for num_groups rows):
+ *   out_keys[k]        : u64 normalised key values
+ *   out_key_valid[k]   : one byte per group, 0 for the NULL key
+ *   out_count_star     : u64 rows per group
+ *   out_vals_lo/hi[f]  : raw 64-bit result lanes per function:
+ *       COUNT*          lo = count (u64)
+ *       MIN/MAX         lo = value in its input type widened to 64 bits / f64 bits
+ *       SUM int8-32     lo = int64/uint64 wrap sum        SUM float  lo = f64 bits
+ *       SUM (u)int64    lo,hi = 128-bit two's complement sum
+ *       AVG             lo = f64 bits of the average computed with the reference's
+ *                       formulas (agg_funcs.h:519-540), or f32 value widened to f64
+ *                       for (u)int8/16 inputs (agg_func_factory.cpp:179-196)
+ *   out_vals_valid[f]  : one byte per group, 0 when the group had no valid input
+ * Group order is unspecified (as in the reference) except that the NULL
+ * single-key group is last (single_numerical_hash_aggregate.cpp:54-60). */
+int vk_agg_result(VkAgg* agg, int64_t num_groups, uint64_t* const* out_keys,
+                  uint8_t* const* out_key_valid, uint64_t* out_count_star,
+                  uint64_t* const* out_vals_lo, uint64_t* const* out_vals_hi,
+                  uint8_t* const* out_vals_valid, VkStream stream);
+/* Multi-GPU exchange: export this rank's partial groups destined to
+ * rank `dest` of `n_ranks` (hash(key) mod n_ranks) as a flat u64 record stream and
+ * merge a received stream into the local table.  Record layout: vk_agg_record_words. */
+int vk_agg_record_words(VkAgg* agg, int* out_words);
+int vk_agg_partition_counts(VkAgg* agg, int n_ranks, int64_t* out_counts_dev, VkStream stream);
+int vk_agg_export_partials(VkAgg* agg, int n_ranks, const int64_t* offsets_dev /* n_ranks */,
+                           uint64_t* out_records, VkStream stream);
+int vk_agg_merge_partials(VkAgg* agg, const uint64_t* records, int64_t n_records, VkStream stream);
+/* introspection for tests/bench: which kernel path the last update used
+ * (0 = none, 1 = shared-memory table, 2 = global table, 3 = one-group reduction) */
+int vk_agg_last_path(VkAgg* agg);
+
+/* --------------------------------------------------------- sort (a15-a16) -- */
+/* Replaces Sort::Sorted (vinum_cpp/src/operators/sort/sort.cpp:15-63):
+ * arrow::compute::SortIndices (stable; NaN then NULL last in both directions;
+ * -0.0 == +0.0) followed by Take of every column. */
+typedef enum VkSortOrder { VK_ASC = 0, VK_DESC = 1 } VkSortOrder;
+uint64_t vk_sort_scratch_bytes(int64_t n_rows);
+/* out_indices: n_rows int64 row ids (the permutation SortIndices returns). */
+int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int64_t n_rows,
+                    int64_t* out_indices, void* scratch, VkStream stream);
+/* Take: out[i] = col[indices[i]]; out_valid_bytes may be NULL when no validity. */
+int vk_take(const VkColumn* col, const int64_t* indices, int64_t n_indices, void* out,
+            uint8_t* out_valid_bytes, VkStream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VINUM_B200_H */

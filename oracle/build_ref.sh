@@ -1,0 +1,51 @@
+#!/usr/bin/env bash
+# Compiles the reference's OWN C++ operators, from the sources where they lie
+# under /root/reference/vinum_cpp/src, into oracle/_ref/ref_vinum_lib*.so.
+# The reference's CMake build is not used (it needs network for gtest and pins
+# Arrow 3.0); this is a direct g++ recipe.
+# Outputs ONLY under oracle/_ref/ (git-ignored; travels to the GPU box).
+# No reference source is copied into the repo.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+SRC="${VINUM_REF_SRC:-/root/reference/vinum_cpp/src}"
+OUT="$HERE/_ref"
+if [ ! -d "$SRC" ]; then
+  echo "build_ref.sh: $SRC absent (GPU box?) - keeping prebuilt $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT/obj"
+PY="${PYTHON:-python}"
+PA=$($PY -c "import pyarrow as pa;print(pa.get_library_dirs()[0])")
+PAINC=$($PY -c "import pyarrow as pa;print(pa.get_include())")
+PYINC=$($PY -c "import sysconfig;print(sysconfig.get_paths()['include'])")
+PBINC=$($PY -c "import pybind11;print(pybind11.get_include())")
+NPINC=$($PY -c "import numpy;print(numpy.get_include())")
+EXT=$($PY -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))")
+TARGET="$OUT/ref_vinum_lib$EXT"
+FLAGS="-O2 -std=c++20 -fPIC -fvisibility=hidden -w -include $HERE/compat.h \
+  -I$PAINC -I$SRC -I$SRC/operators -I$SRC/operators/aggregate -I$SRC/operators/sort \
+  -I$PYINC -I$PBINC -I$NPINC"
+FILES="$HERE/ref_wrapper.cpp \
+  $SRC/common/huge_int.cpp $SRC/common/array_iterators.cpp \
+  $SRC/operators/aggregate/agg_func_factory.cpp $SRC/operators/aggregate/base_aggregate.cpp \
+  $SRC/operators/aggregate/one_group_aggregate.cpp \
+  $SRC/operators/aggregate/single_numerical_hash_aggregate.cpp \
+  $SRC/operators/aggregate/multi_numerical_hash_aggregate.cpp \
+  $SRC/operators/sort/sort.cpp $SRC/operators/table_batch_reader.cpp"
+newest_src=$(stat -c %Y $FILES "$HERE/compat.h" | sort -n | tail -1)
+if [ -f "$TARGET" ] && [ "$(stat -c %Y "$TARGET")" -ge "$newest_src" ]; then
+  echo "build_ref.sh: $TARGET up to date"; exit 0
+fi
+pids=()
+objs=()
+for f in $FILES; do
+  o="$OUT/obj/$(basename "${f%.cpp}").o"
+  objs+=("$o")
+  g++ $FLAGS -c "$f" -o "$o" &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+g++ -shared "${objs[@]}" -L"$PA" -l:libarrow_python.so.2400 -l:libarrow_compute.so.2400 \
+    -l:libarrow.so.2400 -Wl,-rpath,"$PA" -o "$TARGET"
+rm -rf "$OUT/obj"
+echo "build_ref.sh: built $TARGET"

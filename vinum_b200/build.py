@@ -1,0 +1,93 @@
+"""In-tree build of libvinum_b200.so (the C-ABI library, include/vinum_b200.h).
+
+nvcc cross-compiles for sm_100a without a GPU.  The shared object is written next
+to this file (vinum_b200/_C/libvinum_b200.so): it is git-ignored but travels to the
+GPU box with the repo snapshot.
+
+    python -m vinum_b200.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+OUT_DIR = HERE / "_C"
+LIB_PATH = OUT_DIR / "libvinum_b200.so"
+
+SOURCES = [
+    "vk_runtime.cu",
+    "vk_filter.cu",
+    "vk_arith.cu",
+    "vk_hashagg.cu",
+    "vk_sort.cu",
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    # NumPy parity: every float result is one correctly rounded IEEE op (no FMA contraction)
+    "-fmad=false",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: vinum_b200 needs the CUDA toolkit to build its sm_100a kernels")
+
+
+def _newest_source_mtime() -> float:
+    files = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "vinum_b200.h",
+                                                                   Path(__file__)]
+    return max(f.stat().st_mtime for f in files)
+
+
+def needs_build() -> bool:
+    return not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < _newest_source_mtime()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = _nvcc()
+    OUT_DIR.mkdir(exist_ok=True)
+    obj_dir = OUT_DIR / "obj"
+    obj_dir.mkdir(exist_ok=True)
+
+    def compile_one(src: str) -> Path:
+        obj = obj_dir / (Path(src).stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr, flush=True)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    tmp = LIB_PATH.with_suffix(".so.tmp")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *map(str, objs)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
+    shutil.rmtree(obj_dir, ignore_errors=True)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(p)

@@ -1,0 +1,182 @@
+// Arithmetic projection kernels: NumPy ufunc semantics of
+// vinum/core/expressions.py:13-24 evaluated in one coalesced pass.  Compiled with
+// -fmad=false: each result is a single correctly-rounded IEEE operation, as in NumPy.
+#include "vk_common.cuh"
+#include "vk_pred.cuh"
+
+namespace vk {
+
+struct Operand {
+    Col col;
+    int is_col;
+    uint64_t bits;  // scalar converted to the compute class
+};
+
+struct ArithParams {
+    int op;
+    int out_dtype;
+    Operand a, b;
+};
+
+enum ComputeClass { CC_I64 = 0, CC_U64 = 1, CC_F64 = 2, CC_F32 = 3 };
+
+template <int CC> struct CCT;
+template <> struct CCT<CC_I64> { using type = int64_t; };
+template <> struct CCT<CC_U64> { using type = uint64_t; };
+template <> struct CCT<CC_F64> { using type = double; };
+template <> struct CCT<CC_F32> { using type = float; };
+
+template <int CC>
+__device__ __forceinline__ typename CCT<CC>::type load_operand(const Operand& o, int64_t i) {
+    if constexpr (CC == CC_I64) return o.is_col ? (int64_t) load_as_u64(o.col, i) : (int64_t) o.bits;
+    else if constexpr (CC == CC_U64) return o.is_col ? load_as_u64(o.col, i) : o.bits;
+    else if constexpr (CC == CC_F64) return o.is_col ? load_as_f64(o.col, i) : __longlong_as_double((long long) o.bits);
+    else return o.is_col ? load_dom<DOM_F32>(o.col, i) : __uint_as_float((uint32_t) o.bits);
+}
+
+// np.mod for floats (npy_divmod): C fmod, then move the result to the divisor's sign.
+template <typename F>
+__device__ __forceinline__ F np_fmod(F a, F b) {
+    F m = fmod(a, b);
+    if (b == (F) 0) return m;  // NaN
+    if (m != (F) 0) {
+        if ((b < (F) 0) != (m < (F) 0)) m += b;
+    } else {
+        m = copysign((F) 0, b);
+    }
+    return m;
+}
+
+template <int CC>
+__device__ __forceinline__ typename CCT<CC>::type arith_apply(int op, typename CCT<CC>::type x,
+                                                              typename CCT<CC>::type y) {
+    using T = typename CCT<CC>::type;
+    if constexpr (CC == CC_F64 || CC == CC_F32) {
+        switch (op) {
+            case VK_ADD: return x + y;
+            case VK_SUB: return x - y;
+            case VK_MUL: return x * y;
+            case VK_DIV: return x / y;
+            case VK_MOD: return np_fmod<T>(x, y);
+            case VK_NEG: return -x;
+            default: return x;
+        }
+    } else {
+        switch (op) {
+            case VK_ADD: return (T) ((uint64_t) x + (uint64_t) y);
+            case VK_SUB: return (T) ((uint64_t) x - (uint64_t) y);
+            case VK_MUL: return (T) ((uint64_t) x * (uint64_t) y);
+            case VK_MOD: {
+                if (y == 0) return 0;  // NumPy: integer x % 0 == 0 (with a warning)
+                if constexpr (CC == CC_I64) {
+                    if (y == -1) return 0;  // avoids INT64_MIN % -1 trap
+                    int64_t m = x % y;
+                    if (m != 0 && ((m < 0) != (y < 0))) m += y;  // floor-mod: sign of the divisor
+                    return m;
+                } else {
+                    return x % y;
+                }
+            }
+            case VK_BITAND: return x & y;
+            case VK_BITOR: return x | y;
+            case VK_BITXOR: return x ^ y;
+            case VK_NEG: return (T) (0 - (uint64_t) x);
+            case VK_BITNOT: return ~x;
+            default: return x;
+        }
+    }
+}
+
+template <int CC>
+__global__ void __launch_bounds__(256) arith_kernel(ArithParams p, int64_t n, void* __restrict__ out) {
+    using T = typename CCT<CC>::type;
+    int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T x = load_operand<CC>(p.a, i);
+        T y = (p.op >= VK_NEG) ? x : load_operand<CC>(p.b, i);
+        T r = arith_apply<CC>(p.op, x, y);
+        if constexpr (CC == CC_F64) reinterpret_cast<double*>(out)[i] = r;
+        else if constexpr (CC == CC_F32) reinterpret_cast<float*>(out)[i] = r;
+        else {
+            if (p.out_dtype == VK_BOOL8 && p.op == VK_BITNOT) r = (T) (((uint64_t) x) ^ 1ULL);
+            store_from_u64(out, p.out_dtype, i, (uint64_t) r);
+        }
+    }
+}
+
+static int make_operand(const VkColumn* col, const VkScalar* sc, int cc, int64_t n, Operand* o, const char* side) {
+    if (col) {
+        if (!dtype_valid(col->dtype)) return fail(VK_ERR_ARG, std::string("vk_arith: bad dtype on ") + side);
+        if (col->length != n) return fail(VK_ERR_ARG, std::string("vk_arith: length mismatch on ") + side);
+        if ((cc == CC_I64 || cc == CC_U64) && (dtype_is_float(col->dtype) || col->nulls_as_nan))
+            return fail(VK_ERR_ARG, "vk_arith: float operand with integer result dtype");
+        o->col = make_col(*col);
+        o->is_col = 1;
+        return VK_OK;
+    }
+    o->is_col = 0;
+    switch (cc) {
+        case CC_I64: case CC_U64:
+            if (sc->dtype == VK_F64) return fail(VK_ERR_ARG, "vk_arith: float scalar with integer result dtype");
+            o->bits = sc->v.u;
+            return VK_OK;
+        case CC_F64: {
+            double d = sc->dtype == VK_F64 ? sc->v.f : (sc->dtype == VK_I64 ? (double) sc->v.i : (double) sc->v.u);
+            memcpy(&o->bits, &d, 8);
+            return VK_OK;
+        }
+        default: {
+            double d = sc->dtype == VK_F64 ? sc->v.f : (sc->dtype == VK_I64 ? (double) sc->v.i : (double) sc->v.u);
+            float f = (float) d;
+            uint32_t b;
+            memcpy(&b, &f, 4);
+            o->bits = b;
+            return VK_OK;
+        }
+    }
+}
+
+}  // namespace vk
+
+using namespace vk;
+
+extern "C" int vk_arith(int op, const VkColumn* lhs_col, const VkScalar* lhs_scalar, const VkColumn* rhs_col,
+                        const VkScalar* rhs_scalar, int64_t n_rows, int out_dtype, void* out, VkStream stream) {
+    VK_REQUIRE(op >= VK_ADD && op <= VK_BITNOT, "vk_arith: bad op");
+    VK_REQUIRE((lhs_col != nullptr) != (lhs_scalar != nullptr), "vk_arith: lhs must be exactly one of column/scalar");
+    const bool unary = op >= VK_NEG;
+    if (unary) VK_REQUIRE(!rhs_col && !rhs_scalar, "vk_arith: unary op takes no rhs");
+    else VK_REQUIRE((rhs_col != nullptr) != (rhs_scalar != nullptr), "vk_arith: rhs must be exactly one of column/scalar");
+    VK_REQUIRE(dtype_valid(out_dtype), "vk_arith: bad out_dtype");
+    VK_REQUIRE(n_rows >= 0, "vk_arith: negative n_rows");
+    if (n_rows == 0) return VK_OK;
+    VK_REQUIRE(out, "vk_arith: out is NULL");
+    int cc;
+    if (out_dtype == VK_F64) cc = CC_F64;
+    else if (out_dtype == VK_F32) cc = CC_F32;
+    else if (out_dtype == VK_U64) cc = CC_U64;
+    else cc = CC_I64;
+    if (cc == CC_F64 || cc == CC_F32)
+        VK_REQUIRE(op <= VK_MOD || op == VK_NEG, "vk_arith: bitwise op with float result dtype");
+    if (cc == CC_I64 || cc == CC_U64) VK_REQUIRE(op != VK_DIV, "vk_arith: '/' is true division (float result)");
+    ArithParams p{};
+    p.op = op;
+    p.out_dtype = out_dtype;
+    int rc = make_operand(lhs_col, lhs_scalar, cc, n_rows, &p.a, "lhs");
+    if (rc != VK_OK) return rc;
+    if (!unary) {
+        rc = make_operand(rhs_col, rhs_scalar, cc, n_rows, &p.b, "rhs");
+        if (rc != VK_OK) return rc;
+    }
+    int64_t need = (n_rows + 255) / 256, cap = (int64_t) sm_count() * 8;
+    int g = (int) (need < cap ? need : cap);
+    cudaStream_t s = (cudaStream_t) stream;
+    switch (cc) {
+        case CC_I64: arith_kernel<CC_I64><<<g, 256, 0, s>>>(p, n_rows, out); break;
+        case CC_U64: arith_kernel<CC_U64><<<g, 256, 0, s>>>(p, n_rows, out); break;
+        case CC_F32: arith_kernel<CC_F32><<<g, 256, 0, s>>>(p, n_rows, out); break;
+        default: arith_kernel<CC_F64><<<g, 256, 0, s>>>(p, n_rows, out); break;
+    }
+    VK_CHECK_LAUNCH("arith_kernel");
+    return VK_OK;
+}

@@ -1,0 +1,1314 @@
+// Hash group-by aggregate for sm_100a.
+//
+// Replaces the row-at-a-time loop of BaseAggregate::Next
+// (vinum_cpp/src/operators/aggregate/base_aggregate.cpp:23-45) and its
+// SingleNumerical / MultiNumerical / OneGroup specialisations with three kernels:
+//
+//   agg_fast_kernel   low-cardinality single-key path (the north-star pipeline):
+//                     persistent CTAs stream row tiles with 16-byte loads, evaluate the
+//                     WHERE predicate in registers, resolve the key in a shared-memory
+//                     open-addressing table and accumulate COUNT / SUM(f64) there; one
+//                     flush per CTA into the global table.  No row is written back.
+//   agg_general_kernel any key arity / dtype / NULLs / function: straight to the global
+//                     (L2/HBM) table with native 64-bit atomics.
+//   agg_onegroup_kernel un-grouped reduction (OneGroupAggregate::Next,
+//                     one_group_aggregate.cpp:9-26): register accumulate, warp shuffle,
+//                     one atomic per CTA.
+//
+// Rows that cannot be inserted because the global table is at its load limit are
+// appended to a replay list; the host grows the table and replays them, so an update
+// never loses rows whatever the cardinality turns out to be.
+#include "vk_hashagg.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace vk {
+
+constexpr uint64_t LK_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
+constexpr int FA_THREADS = 256;
+constexpr int FA_ROWS = 4;                       // rows per thread per tile
+constexpr int FA_TILE = FA_THREADS * FA_ROWS;    // 1024 rows
+constexpr int FA_MAXPROBE = 16;
+constexpr int FA_MAX_VALS = 2;
+
+enum FastStrategy { FS_SHARED_CAS = 0, FS_WARP_PRIVATE = 1, FS_GLOBAL_RED = 2 };
+
+struct ReplayList {
+    uint32_t* rows;                 // row ids relative to the chunk start
+    unsigned long long* count;      // appended so far
+    unsigned long long* lost;       // rows that did not fit (must stay 0)
+    unsigned long long* spilled;    // rows the fast kernel sent to the global path (statistics)
+    uint64_t capacity;
+};
+
+__device__ __forceinline__ void replay_append(const ReplayList& l, int64_t row) {
+    unsigned long long pos = atomicAdd(l.count, 1ULL);
+    if (pos < l.capacity) l.rows[pos] = (uint32_t) row;
+    else atomicAdd(l.lost, 1ULL);
+}
+
+struct FastParams {
+    Pred pred;
+    Col key;
+    int key_mode;  // 0: 8-byte raw bits, 1: int32 sign-extend, 2: 4-byte zero-extend
+    int n_vals;
+    Col val[FA_MAX_VALS];
+    uint32_t val_funcs[FA_MAX_VALS];  // bitmask of function indices fed by val[v]
+    int64_t n;
+    int64_t num_tiles;
+    int log2s;
+    int64_t row_limit;  // row-level inserts stop here; the rest is reserved for the CTA flushes
+    GTable table;
+    ReplayList replay;
+};
+
+// ---- raw tile registers ---------------------------------------------------------
+template <int PK, int NV>
+struct TileRegs {
+    uint64_t key[FA_ROWS];
+    uint64_t pred[(PK == PK_F64_VEC || PK == PK_I64_VEC) ? FA_ROWS : 1];
+    uint64_t val[NV > 0 ? NV : 1][FA_ROWS];
+    uint32_t flags;  // bit r: row r is in range (and, for non-vector predicates, selected)
+};
+
+__device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t) hi << 32) | lo; }
+
+template <int PK, int NV>
+__device__ __forceinline__ void load_tile(const FastParams& p, int64_t tile, int tid, TileRegs<PK, NV>& t) {
+    t.flags = 0;
+    const int64_t base = tile * FA_TILE;
+#pragma unroll
+    for (int j = 0; j < FA_ROWS / 2; ++j) {
+        const int64_t r0 = base + j * (FA_THREADS * 2) + tid * 2;
+        const int a = 2 * j, b = 2 * j + 1;
+        if (r0 + 1 < p.n) {
+            // ---- full pair: vector loads ----
+            if (p.key_mode == 0) {
+                uint4 q = ldg_stream16(p.key.data + r0 * 8);
+                t.key[a] = u64_of(q.x, q.y);
+                t.key[b] = u64_of(q.z, q.w);
+            } else {
+                uint2 q = ldg_stream8(p.key.data + r0 * 4);
+                if (p.key_mode == 1) {
+                    t.key[a] = (uint64_t) (int64_t) (int32_t) q.x;
+                    t.key[b] = (uint64_t) (int64_t) (int32_t) q.y;
+                } else {
+                    t.key[a] = q.x;
+                    t.key[b] = q.y;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                uint4 q = ldg_stream16(p.val[v].data + r0 * 8);
+                t.val[v][a] = u64_of(q.x, q.y);
+                t.val[v][b] = u64_of(q.z, q.w);
+            }
+            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
+                uint4 q = ldg_stream16(p.pred.col.data + r0 * 8);
+                t.pred[a] = u64_of(q.x, q.y);
+                t.pred[b] = u64_of(q.z, q.w);
+                t.flags |= 3u << a;
+            } else {
+                bool f0, f1;
+                pred_pair<PK>(p.pred, r0, p.n, f0, f1);
+                t.flags |= ((uint32_t) f0 << a) | ((uint32_t) f1 << b);
+            }
+        } else if (r0 < p.n) {
+            // ---- last odd row of the chunk ----
+            t.key[a] = p.key_mode == 0 ? reinterpret_cast<const uint64_t*>(p.key.data)[r0]
+                     : p.key_mode == 1 ? (uint64_t) (int64_t) reinterpret_cast<const int32_t*>(p.key.data)[r0]
+                                       : (uint64_t) reinterpret_cast<const uint32_t*>(p.key.data)[r0];
+            t.key[b] = 0;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                t.val[v][a] = reinterpret_cast<const uint64_t*>(p.val[v].data)[r0];
+                t.val[v][b] = 0;
+            }
+            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
+                t.pred[a] = reinterpret_cast<const uint64_t*>(p.pred.col.data)[r0];
+                t.pred[b] = 0;
+                t.flags |= 1u << a;
+            } else {
+                bool f0, f1;
+                pred_pair<PK>(p.pred, r0, p.n, f0, f1);
+                t.flags |= (uint32_t) f0 << a;
+            }
+        }
+    }
+}
+
+template <int PK, int NV>
+__device__ __forceinline__ bool row_selected(const FastParams& p, const TileRegs<PK, NV>& t, int r) {
+    bool in = (t.flags >> r) & 1;
+    if constexpr (PK == PK_F64_VEC)
+        return in && apply_cmp(p.pred.op, __longlong_as_double((long long) t.pred[r]),
+                               __longlong_as_double((long long) p.pred.scalar.bits));
+    else if constexpr (PK == PK_I64_VEC)
+        return in && apply_cmp(p.pred.op, (int64_t) t.pred[r], (int64_t) p.pred.scalar.bits);
+    else
+        return in;
+}
+
+// Shared-memory key table: returns the slot or -1 (table region full -> spill).
+__device__ __forceinline__ int local_find_or_insert(volatile uint64_t* s_keys, uint64_t key, uint32_t h, uint32_t smask) {
+#pragma unroll 1
+    for (int probe = 0; probe < FA_MAXPROBE; ++probe) {
+        uint64_t k = s_keys[h];
+        if (k == key) return (int) h;
+        if (k == LK_EMPTY) {
+            uint64_t old = atomicCAS(const_cast<unsigned long long*>(reinterpret_cast<volatile unsigned long long*>(s_keys + h)),
+                                     (unsigned long long) LK_EMPTY, (unsigned long long) key);
+            if (old == LK_EMPTY || old == key) return (int) h;
+        }
+        h = (h + 1) & smask;
+    }
+    return -1;
+}
+
+// Row goes straight to the global table (local table full, or sentinel key).
+template <int NV>
+__device__ __forceinline__ void global_row_update(const FastParams& p, uint64_t key, const uint64_t* vals /*NV*/,
+                                                  int64_t row) {
+    int64_t g = gt_find_or_insert<1>(p.table, &key, 0u, hash_key1(key), p.row_limit);
+    if (g < 0) {
+        replay_append(p.replay, row);
+        return;
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), 1ULL);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        uint32_t fm = p.val_funcs[v];
+        while (fm) {
+            int fi = __ffs(fm) - 1;
+            fm &= fm - 1;
+            atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g), __longlong_as_double((long long) vals[v]));
+        }
+    }
+}
+
+// Shared memory layout (dynamic):
+//   FS_SHARED_CAS  : keys[S] u64 | sum[NV][S] f64 | cnt[S] u32
+//   FS_WARP_PRIVATE: keys[S] u64 | sum[W][NV][S] f64 | cnt[S] u32
+//   FS_GLOBAL_RED  : keys[S] u64 | gslot[S] u32 (global slot + 1, 0 = not published)
+template <int PK, int NV, int STRAT>
+__global__ void __launch_bounds__(FA_THREADS) agg_fast_kernel(const __grid_constant__ FastParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int S = 1 << p.log2s;
+    const uint32_t smask = S - 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int W = FA_THREADS / 32;
+
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem);
+    double* s_sum = reinterpret_cast<double*>(smem + (size_t) S * 8);
+    const int sum_copies = STRAT == FS_WARP_PRIVATE ? W : (STRAT == FS_SHARED_CAS ? 1 : 0);
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + (size_t) S * 8 + (size_t) sum_copies * NV * S * 8);
+
+    for (int i = tid; i < S; i += FA_THREADS) {
+        s_keys[i] = LK_EMPTY;
+        s_cnt[i] = 0;
+    }
+    for (int i = tid; i < sum_copies * NV * S; i += FA_THREADS) s_sum[i] = 0.0;
+    __syncthreads();
+
+    double* my_sum = STRAT == FS_WARP_PRIVATE ? s_sum + (size_t) warp * NV * S : s_sum;
+    const unsigned lt = lanemask_lt();
+
+    TileRegs<PK, NV> cur, nxt;
+    int64_t tile = blockIdx.x;
+    if (tile < p.num_tiles) load_tile<PK, NV>(p, tile, tid, cur);
+    for (; tile < p.num_tiles; tile += gridDim.x) {
+        const int64_t tnext = tile + gridDim.x;
+        if (tnext < p.num_tiles) load_tile<PK, NV>(p, tnext, tid, nxt);
+
+#pragma unroll
+        for (int r = 0; r < FA_ROWS; ++r) {
+            const bool sel = row_selected<PK, NV>(p, cur, r);
+            const uint64_t key = cur.key[r];
+            int slot = -1;
+            if (sel && key != LK_EMPTY)
+                slot = local_find_or_insert(s_keys, key, (uint32_t) (hash_key1(key) >> 40) & smask, smask);
+            const int64_t row = tile * FA_TILE + (r >> 1) * (FA_THREADS * 2) + tid * 2 + (r & 1);
+
+            if constexpr (STRAT == FS_GLOBAL_RED) {
+                // the local table only caches key -> global slot
+                if (sel) {
+                    int64_t g = -1;
+                    if (slot >= 0) {
+                        uint32_t gs = reinterpret_cast<volatile uint32_t*>(s_cnt)[slot];
+                        if (gs == 0) {
+                            g = gt_find_or_insert<1>(p.table, &key, 0u, hash_key1(key), p.row_limit);
+                            if (g >= 0 && g < 0xfffffffeLL) reinterpret_cast<volatile uint32_t*>(s_cnt)[slot] = (uint32_t) g + 1;
+                        } else {
+                            g = (int64_t) gs - 1;
+                        }
+                    } else {
+                        g = gt_find_or_insert<1>(p.table, &key, 0u, hash_key1(key), p.row_limit);
+                    }
+                    if (g < 0) {
+                        replay_append(p.replay, row);
+                    } else {
+                        atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), 1ULL);
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            uint32_t fm = p.val_funcs[v];
+                            while (fm) {
+                                int fi = __ffs(fm) - 1;
+                                fm &= fm - 1;
+                                atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g),
+                                          __longlong_as_double((long long) cur.val[v][r]));
+                            }
+                        }
+                    }
+                }
+            } else {
+                if (sel && slot < 0) {
+                    uint64_t vals[NV > 0 ? NV : 1];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) vals[v] = cur.val[v][r];
+                    atomicAdd(p.replay.spilled, 1ULL);
+                    global_row_update<NV>(p, key, vals, row);
+                }
+                const bool upd = sel && slot >= 0;
+                if (upd) atomicAdd(&s_cnt[slot], 1u);
+                if constexpr (NV > 0) {
+                    if constexpr (STRAT == FS_SHARED_CAS) {
+                        if (upd) {
+#pragma unroll
+                            for (int v = 0; v < NV; ++v)
+                                atomicAdd(&my_sum[(size_t) v * S + slot], __longlong_as_double((long long) cur.val[v][r]));
+                        }
+                    } else {
+                        // warp-private accumulators: plain read-modify-write, lanes that hit
+                        // the same slot take turns (rank order)
+                        unsigned peers = __match_any_sync(0xffffffffu, upd ? (unsigned) slot : (0x80000000u | lane));
+                        int mult = upd ? __popc(peers) : 0;
+                        int maxm = __reduce_max_sync(0xffffffffu, mult);
+                        if (maxm <= 1) {
+                            if (upd) {
+#pragma unroll
+                                for (int v = 0; v < NV; ++v)
+                                    my_sum[(size_t) v * S + slot] += __longlong_as_double((long long) cur.val[v][r]);
+                            }
+                        } else {
+                            int rank = __popc(peers & lt);
+                            for (int round = 0; round < maxm; ++round) {
+                                if (upd && rank == round) {
+#pragma unroll
+                                    for (int v = 0; v < NV; ++v)
+                                        my_sum[(size_t) v * S + slot] += __longlong_as_double((long long) cur.val[v][r]);
+                                }
+                                __syncwarp();
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cur = nxt;
+    }
+
+    if constexpr (STRAT != FS_GLOBAL_RED) {
+        // ---- flush the CTA's partial groups into the global table ----
+        __syncthreads();
+        for (int s = tid; s < S; s += FA_THREADS) {
+            uint64_t key = s_keys[s];
+            if (key == LK_EMPTY) continue;
+            uint32_t c = s_cnt[s];
+            if (c == 0) continue;
+            int64_t g = gt_find_or_insert<1>(p.table, &key, 0u, hash_key1(key), p.table.max_groups);
+            if (g < 0) {  // cannot happen: the host reserves gridDim.x * S free slots
+                atomicAdd(p.replay.lost, (unsigned long long) c);
+                continue;
+            }
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), (unsigned long long) c);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double total = 0.0;
+                for (int w = 0; w < sum_copies; ++w) total += s_sum[((size_t) w * NV + v) * S + s];
+                uint32_t fm = p.val_funcs[v];
+                while (fm) {
+                    int fi = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g), total);
+                }
+            }
+        }
+    }
+}
+
+// ============================================================ general kernel
+struct GenParams {
+    Pred pred;
+    int pk;                          // PredKernelKind (evaluated row-wise)
+    int n_keys;
+    Col keys[VK_AGG_MAX_KEYS];
+    int n_funcs;
+    FuncSpec specs[VK_AGG_MAX_FUNCS];
+    Col vals[VK_AGG_MAX_FUNCS];
+    int64_t n;
+    const uint32_t* row_list;        // replay: process these rows only
+    const unsigned long long* row_list_count;
+    GTable table;
+    ReplayList replay;
+};
+
+__device__ __forceinline__ bool pred_row(const Pred& p, int64_t i) {
+    if (p.kind == VK_PRED_NONE) return true;
+    if (p.kind == VK_PRED_MASK) return p.mask[i] != 0;
+    return pred_row_generic(p, i);
+}
+
+__global__ void __launch_bounds__(256) agg_general_kernel(const __grid_constant__ GenParams p) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const bool replaying = p.row_list != nullptr;
+    const int64_t total = replaying ? (int64_t) *p.row_list_count : p.n;
+    for (int64_t it = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
+        const int64_t i = replaying ? (int64_t) p.row_list[it] : it;
+        if (!replaying && !pred_row(p.pred, i)) continue;  // listed rows already passed the predicate
+        uint64_t kv[VK_AGG_MAX_KEYS];
+        uint32_t nullmask = 0;
+        for (int k = 0; k < p.n_keys; ++k) {
+            bool valid = col_valid(p.keys[k], i);
+            kv[k] = valid ? load_as_u64(p.keys[k], i) : 0;
+            nullmask |= (uint32_t) (!valid) << k;
+        }
+        int64_t slot = gt_find_or_insert<0>(p.table, kv, nullmask, hash_keys(kv, nullmask, p.n_keys), p.table.max_groups);
+        if (slot < 0) {
+            replay_append(p.replay, i);
+            continue;
+        }
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + slot), 1ULL);
+        for (int f = 0; f < p.n_funcs; ++f) {
+            const FuncSpec spec = p.specs[f];
+            if (spec.acc == ACC_NONE) continue;
+            if (!col_valid(p.vals[f], i)) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.table.nnull[f] + slot), 1ULL);
+                continue;
+            }
+            if (spec.acc == ACC_COUNT) continue;
+            acc_update_global(p.table, f, spec, slot, acc_load(spec, p.vals[f], i));
+        }
+    }
+}
+
+// ============================================================ one-group kernel
+// One launch per aggregate function; slot 0 of the table is the single group.
+struct OneParams {
+    Pred pred;
+    FuncSpec spec;
+    Col val;
+    int fi;            // function index, -1: count rows only (COUNT(*) / the row counter)
+    int64_t n;
+    GTable table;
+};
+
+__global__ void __launch_bounds__(256) agg_onegroup_kernel(const __grid_constant__ OneParams p) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    uint64_t lo = 0, hi = 0, nn = 0, rows = 0;
+    double fsum = 0.0;
+    const int acc = p.fi < 0 ? ACC_NONE : p.spec.acc;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        if (!pred_row(p.pred, i)) continue;
+        ++rows;
+        if (acc == ACC_NONE) continue;
+        if (!col_valid(p.val, i)) { ++nn; continue; }
+        if (acc == ACC_COUNT) continue;
+        uint64_t v = acc_load(p.spec, p.val, i);
+        switch (acc) {
+            case ACC_SUM_F64: fsum += __longlong_as_double((long long) v); break;
+            case ACC_SUM_I64: lo += v; break;
+            case ACC_SUM_I128: {
+                uint64_t nl = lo + v;
+                hi += ((!p.spec.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL) + (nl < lo ? 1ULL : 0ULL);
+                lo = nl;
+                break;
+            }
+            default: {
+                uint64_t o = ord_transform(p.spec.ord, p.spec.is_min, v);
+                lo = o > lo ? o : lo;
+                break;
+            }
+        }
+    }
+    // warp reduction
+    for (int d = 16; d > 0; d >>= 1) {
+        rows += __shfl_xor_sync(0xffffffffu, rows, d);
+        nn += __shfl_xor_sync(0xffffffffu, nn, d);
+        if (acc == ACC_SUM_F64) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+        else if (acc == ACC_SUM_I64) lo += __shfl_xor_sync(0xffffffffu, lo, d);
+        else if (acc == ACC_SUM_I128) {
+            uint64_t ol = __shfl_xor_sync(0xffffffffu, lo, d), oh = __shfl_xor_sync(0xffffffffu, hi, d);
+            uint64_t nl = lo + ol;
+            hi += oh + (nl < lo ? 1ULL : 0ULL);
+            lo = nl;
+        } else if (acc == ACC_MAXORD) {
+            uint64_t o = __shfl_xor_sync(0xffffffffu, lo, d);
+            lo = o > lo ? o : lo;
+        }
+    }
+    if ((threadIdx.x & 31) != 0) return;
+    if (p.fi < 0) {
+        if (rows) atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star), (unsigned long long) rows);
+        return;
+    }
+    if (nn) atomicAdd(reinterpret_cast<unsigned long long*>(p.table.nnull[p.fi]), (unsigned long long) nn);
+    switch (acc) {
+        case ACC_SUM_F64:
+            if (rows - nn) atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[p.fi]), fsum);
+            break;
+        case ACC_SUM_I64:
+            if (lo) atomicAdd(reinterpret_cast<unsigned long long*>(p.table.acc_lo[p.fi]), (unsigned long long) lo);
+            break;
+        case ACC_SUM_I128:
+            if (lo | hi) acc_add_i128(p.table.acc_lo[p.fi], p.table.acc_hi[p.fi], lo, hi);
+            break;
+        case ACC_MAXORD:
+            if (rows - nn) atomicMax(reinterpret_cast<unsigned long long*>(p.table.acc_lo[p.fi]), (unsigned long long) lo);
+            break;
+        default: break;
+    }
+}
+
+// ================================================================== finalize
+struct FinalParams {
+    GTable table;
+    FuncSpec specs[VK_AGG_MAX_FUNCS];
+    int64_t num_groups;
+    int null_last;                      // single key: NULL group goes to row num_groups-1
+    unsigned long long* cursor;         // output row allocator
+    uint64_t* out_keys[VK_AGG_MAX_KEYS];
+    uint8_t* out_key_valid[VK_AGG_MAX_KEYS];
+    uint64_t* out_count_star;
+    uint64_t* out_lo[VK_AGG_MAX_FUNCS];
+    uint64_t* out_hi[VK_AGG_MAX_FUNCS];
+    uint8_t* out_valid[VK_AGG_MAX_FUNCS];
+};
+
+// Hugeint::TryCast<double>, vinum_cpp/src/common/huge_int.cpp:394-406
+__device__ __forceinline__ double hugeint_to_double(__int128 v) {
+    uint64_t lower = (uint64_t) v;
+    int64_t upper = (int64_t) (v >> 64);
+    if (upper == -1) return -(double) (0xFFFFFFFFFFFFFFFFULL - lower) - 1.0;
+    return (double) lower + (double) upper * 18446744073709551616.0;  // double(UINT64_MAX) rounds to 2^64
+}
+
+__global__ void __launch_bounds__(256) agg_finalize_kernel(const __grid_constant__ FinalParams p) {
+    const GTable& t = p.table;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
+        if (t.state[s] != 2) continue;
+        const uint32_t nullmask = t.n_keys ? t.knull[s] : 0;
+        int64_t row;
+        if (p.null_last && nullmask) row = p.num_groups - 1;
+        else row = (int64_t) atomicAdd(p.cursor, 1ULL);
+        if (row >= p.num_groups) continue;  // defensive
+        for (int k = 0; k < t.n_keys; ++k) {
+            p.out_keys[k][row] = t.keys[(int64_t) k * t.capacity + s];
+            p.out_key_valid[k][row] = !((nullmask >> k) & 1);
+        }
+        const uint64_t rows = t.count_star[s];
+        p.out_count_star[row] = rows;
+        for (int f = 0; f < t.n_funcs; ++f) {
+            const FuncSpec spec = p.specs[f];
+            const uint64_t nn = t.nnull[f] ? t.nnull[f][s] : 0;
+            const uint64_t nvalid = rows - nn;
+            uint64_t lo = 0, hi = 0;
+            bool valid = nvalid > 0;
+            const uint64_t alo = t.acc_lo[f] ? t.acc_lo[f][s] : 0;
+            const uint64_t ahi = t.acc_hi[f] ? t.acc_hi[f][s] : 0;
+            switch (spec.func) {
+                case VK_AGG_COUNT_STAR: lo = rows; valid = true; break;
+                case VK_AGG_COUNT: lo = nvalid; valid = true; break;
+                case VK_AGG_MIN: case VK_AGG_MAX: lo = valid ? ord_inverse(spec.ord, spec.is_min, alo) : 0; break;
+                case VK_AGG_SUM: lo = alo; hi = ahi; break;
+                case VK_AGG_AVG: {
+                    if (!valid) break;
+                    double avg;
+                    if (spec.acc == ACC_SUM_F64) {
+                        avg = __longlong_as_double((long long) alo) / (double) nvalid;  // agg_funcs.h:519-522
+                    } else if (spec.acc == ACC_SUM_I64) {
+                        double sum = spec.in_unsigned ? (double) alo : (double) (int64_t) alo;
+                        avg = sum / (double) nvalid;
+                        if (dtype_size(spec.in_dtype) <= 2) avg = (double) (float) avg;  // T_OUT = float_t
+                    } else {
+                        // hugeint quotient + remainder, agg_funcs.h:524-540
+                        __int128 sum = (__int128) (((unsigned __int128) ahi << 64) | alo);
+                        __int128 cnt = (__int128) (int64_t) nvalid;
+                        __int128 q = sum / cnt, rem = sum % cnt;
+                        avg = hugeint_to_double(q);
+                        avg += hugeint_to_double(rem) / (double) nvalid;
+                    }
+                    lo = (uint64_t) __double_as_longlong(avg);
+                    break;
+                }
+                default: break;
+            }
+            p.out_lo[f][row] = lo;
+            if (p.out_hi[f]) p.out_hi[f][row] = hi;
+            p.out_valid[f][row] = valid;
+        }
+    }
+}
+
+// ==================================================================== rehash
+struct RehashParams {
+    GTable src, dst;
+};
+__global__ void __launch_bounds__(256) agg_rehash_kernel(const __grid_constant__ RehashParams p) {
+    const GTable& a = p.src;
+    const GTable& b = p.dst;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < a.capacity; s += stride) {
+        if (a.state[s] != 2) continue;
+        uint64_t kv[VK_AGG_MAX_KEYS];
+        const uint32_t nullmask = a.n_keys ? a.knull[s] : 0;
+        for (int k = 0; k < a.n_keys; ++k) kv[k] = a.keys[(int64_t) k * a.capacity + s];
+        int64_t d = gt_find_or_insert<0>(b, kv, nullmask, hash_keys(kv, nullmask, a.n_keys), b.max_groups);
+        if (d < 0) continue;  // cannot happen: dst is larger
+        b.count_star[d] = a.count_star[s];
+        for (int f = 0; f < a.n_funcs; ++f) {
+            if (a.acc_lo[f]) b.acc_lo[f][d] = a.acc_lo[f][s];
+            if (a.acc_hi[f]) b.acc_hi[f][d] = a.acc_hi[f][s];
+            if (a.nnull[f]) b.nnull[f][d] = a.nnull[f][s];
+        }
+    }
+}
+
+// ============================================================ partial exchange
+// Record (u64 words): keys[n_keys] | nullmask | count_star | per func: lo, hi, nnull
+struct ExchParams {
+    GTable table;
+    FuncSpec specs[VK_AGG_MAX_FUNCS];
+    int n_ranks;
+    int words;
+    long long* counts;             // [n_ranks]
+    const long long* offsets;      // [n_ranks] record offsets
+    unsigned long long* cursors;   // [n_ranks]
+    uint64_t* out;
+    const uint64_t* in;
+    int64_t n_in;
+    ReplayList replay;
+};
+__device__ __forceinline__ int dest_rank(uint64_t hash, int n_ranks) { return (int) ((hash >> 33) % (uint64_t) n_ranks); }
+
+__global__ void __launch_bounds__(256) agg_partition_count_kernel(const __grid_constant__ ExchParams p) {
+    const GTable& t = p.table;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
+        if (t.state[s] != 2) continue;
+        uint64_t kv[VK_AGG_MAX_KEYS];
+        const uint32_t nullmask = t.n_keys ? t.knull[s] : 0;
+        for (int k = 0; k < t.n_keys; ++k) kv[k] = t.keys[(int64_t) k * t.capacity + s];
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.counts) + dest_rank(hash_keys(kv, nullmask, t.n_keys), p.n_ranks), 1ULL);
+    }
+}
+__global__ void __launch_bounds__(256) agg_export_kernel(const __grid_constant__ ExchParams p) {
+    const GTable& t = p.table;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
+        if (t.state[s] != 2) continue;
+        uint64_t kv[VK_AGG_MAX_KEYS];
+        const uint32_t nullmask = t.n_keys ? t.knull[s] : 0;
+        for (int k = 0; k < t.n_keys; ++k) kv[k] = t.keys[(int64_t) k * t.capacity + s];
+        int d = dest_rank(hash_keys(kv, nullmask, t.n_keys), p.n_ranks);
+        int64_t rec = p.offsets[d] + (int64_t) atomicAdd(p.cursors + d, 1ULL);
+        uint64_t* o = p.out + rec * p.words;
+        int w = 0;
+        for (int k = 0; k < t.n_keys; ++k) o[w++] = kv[k];
+        o[w++] = nullmask;
+        o[w++] = t.count_star[s];
+        for (int f = 0; f < t.n_funcs; ++f) {
+            o[w++] = t.acc_lo[f] ? t.acc_lo[f][s] : 0;
+            o[w++] = t.acc_hi[f] ? t.acc_hi[f][s] : 0;
+            o[w++] = t.nnull[f] ? t.nnull[f][s] : 0;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) agg_merge_kernel(const __grid_constant__ ExchParams p) {
+    const GTable& t = p.table;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < p.n_in; r += stride) {
+        const uint64_t* o = p.in + r * p.words;
+        uint64_t kv[VK_AGG_MAX_KEYS];
+        int w = 0;
+        for (int k = 0; k < t.n_keys; ++k) kv[k] = o[w++];
+        const uint32_t nullmask = (uint32_t) o[w++];
+        int64_t slot = gt_find_or_insert<0>(t, kv, nullmask, hash_keys(kv, nullmask, t.n_keys), t.max_groups);
+        if (slot < 0) {
+            replay_append(p.replay, r);
+            continue;
+        }
+        atomicAdd(reinterpret_cast<unsigned long long*>(t.count_star + slot), (unsigned long long) o[w++]);
+        for (int f = 0; f < t.n_funcs; ++f) {
+            const FuncSpec spec = p.specs[f];
+            uint64_t lo = o[w++], hi = o[w++], nn = o[w++];
+            if (nn && t.nnull[f]) atomicAdd(reinterpret_cast<unsigned long long*>(t.nnull[f] + slot), (unsigned long long) nn);
+            switch (spec.acc) {
+                case ACC_SUM_F64:
+                    atomicAdd(reinterpret_cast<double*>(t.acc_lo[f] + slot), __longlong_as_double((long long) lo));
+                    break;
+                case ACC_SUM_I64:
+                    atomicAdd(reinterpret_cast<unsigned long long*>(t.acc_lo[f] + slot), (unsigned long long) lo);
+                    break;
+                case ACC_SUM_I128: acc_add_i128(t.acc_lo[f] + slot, t.acc_hi[f] + slot, lo, hi); break;
+                case ACC_MAXORD:
+                    atomicMax(reinterpret_cast<unsigned long long*>(t.acc_lo[f] + slot), (unsigned long long) lo);
+                    break;
+                default: break;
+            }
+        }
+    }
+}
+
+}  // namespace vk
+
+using namespace vk;
+
+// =================================================================== host side
+struct VkAgg {
+    int n_keys = 0;
+    int key_dtypes[VK_AGG_MAX_KEYS] = {0};
+    int n_funcs = 0;
+    FuncSpec specs[VK_AGG_MAX_FUNCS];
+    GTable t{};
+    bool table_ready = false;
+    int64_t expected_groups = 0;
+    int64_t groups_ub = 0;            // upper bound on groups in the table
+    unsigned long long* d_ctr = nullptr;  // [0] num_groups [1] list count [2] lost [3] spilled [4] finalize cursor [5..] scratch
+    unsigned long long* h_ctr = nullptr;  // pinned mirror
+    uint32_t* list = nullptr;
+    uint64_t list_cap = 0;
+    int last_path = 0;
+    int strategy = FS_SHARED_CAS;
+    int log2s = 11;
+    bool fast_disabled = false;       // cardinality turned out too high for the shared-memory table
+    uint64_t fast_rows = 0, fast_spilled = 0;
+};
+
+namespace {
+
+constexpr double kMaxLoad = 0.5;
+constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_WORDS = 16;
+
+int64_t pow2_ceil(int64_t x) {
+    int64_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+int alloc_table(VkAgg* a, GTable* t, int64_t capacity, cudaStream_t s) {
+    memset(t, 0, sizeof(GTable));
+    t->capacity = capacity;
+    t->max_groups = (int64_t) (capacity * kMaxLoad);
+    t->n_keys = a->n_keys;
+    t->n_funcs = a->n_funcs;
+    t->num_groups = a->d_ctr + CTR_GROUPS;
+    auto zalloc = [&](void** p, size_t bytes) -> int {
+        VK_CUDA(cudaMallocAsync(p, bytes, s));
+        VK_CUDA(cudaMemsetAsync(*p, 0, bytes, s));
+        return VK_OK;
+    };
+    int rc;
+    if ((rc = zalloc((void**) &t->state, capacity * sizeof(uint32_t)))) return rc;
+    if (a->n_keys) {
+        if ((rc = zalloc((void**) &t->keys, (size_t) a->n_keys * capacity * sizeof(uint64_t)))) return rc;
+        if ((rc = zalloc((void**) &t->knull, capacity * sizeof(uint32_t)))) return rc;
+    }
+    if ((rc = zalloc((void**) &t->count_star, capacity * sizeof(uint64_t)))) return rc;
+    for (int f = 0; f < a->n_funcs; ++f) {
+        int acc = a->specs[f].acc;
+        if (acc >= ACC_SUM_F64)
+            if ((rc = zalloc((void**) &t->acc_lo[f], capacity * sizeof(uint64_t)))) return rc;
+        if (acc == ACC_SUM_I128)
+            if ((rc = zalloc((void**) &t->acc_hi[f], capacity * sizeof(uint64_t)))) return rc;
+        if (acc != ACC_NONE)
+            if ((rc = zalloc((void**) &t->nnull[f], capacity * sizeof(uint64_t)))) return rc;
+    }
+    return VK_OK;
+}
+
+void free_table(GTable* t, cudaStream_t s) {
+    if (t->state) cudaFreeAsync(t->state, s);
+    if (t->keys) cudaFreeAsync(t->keys, s);
+    if (t->knull) cudaFreeAsync(t->knull, s);
+    if (t->count_star) cudaFreeAsync(t->count_star, s);
+    for (int f = 0; f < VK_AGG_MAX_FUNCS; ++f) {
+        if (t->acc_lo[f]) cudaFreeAsync(t->acc_lo[f], s);
+        if (t->acc_hi[f]) cudaFreeAsync(t->acc_hi[f], s);
+        if (t->nnull[f]) cudaFreeAsync(t->nnull[f], s);
+    }
+    memset(t, 0, sizeof(GTable));
+}
+
+int read_counters(VkAgg* a, cudaStream_t s) {
+    VK_CUDA(cudaMemcpyAsync(a->h_ctr, a->d_ctr, CTR_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    VK_CUDA(cudaStreamSynchronize(s));
+    return VK_OK;
+}
+
+// Grow (rehash) so that at least `need_free` more groups fit.
+int grow_table(VkAgg* a, int64_t groups_now, int64_t need_free, cudaStream_t s) {
+    int64_t cap = a->t.capacity;
+    while ((int64_t) (cap * kMaxLoad) - groups_now < need_free) cap <<= 1;
+    if (cap == a->t.capacity) return VK_OK;
+    GTable nt;
+    // the group counter is shared: reset it, the rehash re-counts
+    int rc = alloc_table(a, &nt, cap, s);
+    if (rc != VK_OK) return rc;
+    VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_GROUPS, 0, sizeof(unsigned long long), s));
+    RehashParams rp{a->t, nt};
+    int64_t need = (a->t.capacity + 255) / 256, capb = (int64_t) sm_count() * 8;
+    agg_rehash_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(rp);
+    VK_CHECK_LAUNCH("agg_rehash_kernel");
+    free_table(&a->t, s);
+    a->t = nt;
+    return VK_OK;
+}
+
+int ensure_list(VkAgg* a, uint64_t want, cudaStream_t s) {
+    if (a->list_cap >= want) return VK_OK;
+    if (a->list) VK_CUDA(cudaFreeAsync(a->list, s));
+    a->list = nullptr;
+    a->list_cap = 0;
+    VK_CUDA(cudaMallocAsync((void**) &a->list, want * sizeof(uint32_t), s));
+    a->list_cap = want;
+    return VK_OK;
+}
+
+ReplayList make_replay(VkAgg* a) {
+    ReplayList l;
+    l.rows = a->list;
+    l.count = a->d_ctr + CTR_LIST;
+    l.lost = a->d_ctr + CTR_LOST;
+    l.spilled = a->d_ctr + CTR_SPILL;
+    l.capacity = a->list_cap;
+    return l;
+}
+
+size_t fast_smem_bytes(int strat, int nv, int log2s) {
+    size_t S = (size_t) 1 << log2s;
+    int copies = strat == FS_WARP_PRIVATE ? FA_THREADS / 32 : (strat == FS_SHARED_CAS ? 1 : 0);
+    return S * 8 + (size_t) copies * nv * S * 8 + S * 4;
+}
+
+template <int PK, int NV>
+int launch_fast_strat(const FastParams& p, int strat, int grid, size_t smem, cudaStream_t s) {
+    auto go = [&](auto kernel) -> int {
+        VK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        kernel<<<grid, FA_THREADS, smem, s>>>(p);
+        VK_CHECK_LAUNCH("agg_fast_kernel");
+        return VK_OK;
+    };
+    switch (strat) {
+        case FS_WARP_PRIVATE: return go(agg_fast_kernel<PK, NV, FS_WARP_PRIVATE>);
+        case FS_GLOBAL_RED: return go(agg_fast_kernel<PK, NV, FS_GLOBAL_RED>);
+        default: return go(agg_fast_kernel<PK, NV, FS_SHARED_CAS>);
+    }
+}
+template <int PK>
+int launch_fast_nv(const FastParams& p, int strat, int grid, size_t smem, cudaStream_t s) {
+    switch (p.n_vals) {
+        case 0: return launch_fast_strat<PK, 0>(p, strat, grid, smem, s);
+        case 1: return launch_fast_strat<PK, 1>(p, strat, grid, smem, s);
+        default: return launch_fast_strat<PK, 2>(p, strat, grid, smem, s);
+    }
+}
+int launch_fast(const FastParams& p, int pk, int strat, int grid, size_t smem, cudaStream_t s) {
+    switch (pk) {
+        case PK_NONE: return launch_fast_nv<PK_NONE>(p, strat, grid, smem, s);
+        case PK_MASK: return launch_fast_nv<PK_MASK>(p, strat, grid, smem, s);
+        case PK_F64_VEC: return launch_fast_nv<PK_F64_VEC>(p, strat, grid, smem, s);
+        case PK_I64_VEC: return launch_fast_nv<PK_I64_VEC>(p, strat, grid, smem, s);
+        default: return launch_fast_nv<PK_GENERIC>(p, strat, grid, smem, s);
+    }
+}
+
+VkColumn slice_col(const VkColumn& c, int64_t off, int64_t len) {
+    VkColumn r = c;
+    r.offset += off;
+    r.length = len;
+    return r;
+}
+
+bool aligned_for_pairs(const VkColumn& c) {
+    const int es = dtype_size(c.dtype);
+    uintptr_t addr = reinterpret_cast<uintptr_t>(c.data) + (uintptr_t) c.offset * es;
+    return (addr % (2 * es)) == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_funcs, const int32_t* funcs,
+                  const int32_t* func_in_dtypes, int64_t expected_groups) {
+    VK_REQUIRE(out, "vk_agg_create: out is NULL");
+    *out = nullptr;
+    VK_REQUIRE(n_keys >= 0 && n_keys <= VK_AGG_MAX_KEYS, "vk_agg_create: 0..8 key columns supported");
+    VK_REQUIRE(n_funcs >= 0 && n_funcs <= VK_AGG_MAX_FUNCS, "vk_agg_create: 0..16 aggregate functions supported");
+    VK_REQUIRE(n_keys == 0 || key_dtypes, "vk_agg_create: key_dtypes is NULL");
+    VK_REQUIRE(n_funcs == 0 || (funcs && func_in_dtypes), "vk_agg_create: funcs is NULL");
+    VkAgg* a = new VkAgg();
+    a->n_keys = n_keys;
+    a->n_funcs = n_funcs;
+    a->expected_groups = expected_groups;
+    for (int k = 0; k < n_keys; ++k) {
+        if (!dtype_valid(key_dtypes[k])) { delete a; return fail(VK_ERR_ARG, "vk_agg_create: bad key dtype"); }
+        a->key_dtypes[k] = key_dtypes[k];
+    }
+    for (int f = 0; f < n_funcs; ++f) {
+        FuncSpec s{};
+        s.func = funcs[f];
+        s.in_dtype = func_in_dtypes[f];
+        const int dt = s.in_dtype;
+        if (s.func != VK_AGG_COUNT_STAR && !dtype_valid(dt)) { delete a; return fail(VK_ERR_ARG, "vk_agg_create: bad input dtype"); }
+        s.in_unsigned = dtype_is_unsigned(dt);
+        switch (s.func) {
+            case VK_AGG_COUNT_STAR: s.acc = ACC_NONE; break;
+            case VK_AGG_COUNT: s.acc = ACC_COUNT; break;
+            case VK_AGG_MIN: case VK_AGG_MAX:
+                s.acc = ACC_MAXORD;
+                s.is_min = s.func == VK_AGG_MIN;
+                s.ord = dtype_is_float(dt) ? ORD_F64 : (dtype_is_unsigned(dt) ? ORD_U64 : ORD_S64);
+                break;
+            case VK_AGG_SUM: case VK_AGG_AVG:
+                // agg_func_factory.cpp:107-131 (SUM) / :176-211 (AVG)
+                if (dt == VK_BOOL8) { delete a; return fail(VK_ERR_UNSUPPORTED, "Column data type is not supported by sum()/avg()."); }
+                if (dtype_is_float(dt)) s.acc = ACC_SUM_F64;
+                else if (dtype_size(dt) == 8) s.acc = ACC_SUM_I128;
+                else s.acc = ACC_SUM_I64;
+                break;
+            default:
+                delete a;
+                return fail(VK_ERR_ARG, "vk_agg_create: unknown aggregate function");
+        }
+        a->specs[f] = s;
+    }
+    const char* st = getenv("VINUM_B200_AGG_STRATEGY");
+    if (st) a->strategy = atoi(st);
+    const char* ls = getenv("VINUM_B200_AGG_LOG2S");
+    if (ls) a->log2s = atoi(ls);
+    if (a->log2s < 6) a->log2s = 6;
+    if (a->log2s > 13) a->log2s = 13;
+    cudaError_t e = cudaMalloc((void**) &a->d_ctr, CTR_WORDS * sizeof(unsigned long long));
+    if (e != cudaSuccess) { delete a; return cuda_fail(e, "cudaMalloc(counters)"); }
+    cudaMemset(a->d_ctr, 0, CTR_WORDS * sizeof(unsigned long long));
+    e = cudaHostAlloc((void**) &a->h_ctr, CTR_WORDS * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaFree(a->d_ctr); delete a; return cuda_fail(e, "cudaHostAlloc(counters)"); }
+    *out = a;
+    return VK_OK;
+}
+
+int vk_agg_destroy(VkAgg* a) {
+    if (!a) return VK_OK;
+    cudaDeviceSynchronize();
+    if (a->table_ready) free_table(&a->t, 0);
+    if (a->list) cudaFreeAsync(a->list, 0);
+    if (a->d_ctr) cudaFree(a->d_ctr);
+    if (a->h_ctr) cudaFreeHost(a->h_ctr);
+    delete a;
+    return VK_OK;
+}
+
+int vk_agg_last_path(VkAgg* a) { return a ? a->last_path : 0; }
+
+static int run_replay_until_empty(VkAgg* a, GenParams gp, int64_t chunk_rows, cudaStream_t s) {
+    // Precondition: counters read back in a->h_ctr after the chunk's kernel.
+    while (true) {
+        if (a->h_ctr[CTR_LOST] != 0)
+            return fail(VK_ERR_STATE, "vk_agg_update: internal error: replay list overflowed (rows lost)");
+        const int64_t groups = (int64_t) a->h_ctr[CTR_GROUPS];
+        const int64_t pending = (int64_t) a->h_ctr[CTR_LIST];
+        a->groups_ub = groups;
+        if (pending == 0) return VK_OK;
+        // grow so that every pending row can become a new group, then replay the list
+        int rc = grow_table(a, groups, pending + 1024, s);
+        if (rc != VK_OK) return rc;
+        // the list being replayed must not be appended to while it is read: with enough
+        // free slots no row can fail, so `count` is only read.
+        uint32_t* replay_rows = nullptr;
+        VK_CUDA(cudaMallocAsync((void**) &replay_rows, (size_t) pending * sizeof(uint32_t), s));
+        VK_CUDA(cudaMemcpyAsync(replay_rows, a->list, (size_t) pending * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        VK_CUDA(cudaMemcpyAsync(a->d_ctr + CTR_CURSOR + 1, a->d_ctr + CTR_LIST, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+        VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_LIST, 0, sizeof(unsigned long long), s));
+        gp.table = a->t;
+        gp.replay = make_replay(a);
+        gp.row_list = replay_rows;
+        gp.row_list_count = a->d_ctr + CTR_CURSOR + 1;
+        gp.n = chunk_rows;
+        int64_t need = (pending + 255) / 256, capb = (int64_t) sm_count() * 8;
+        agg_general_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(gp);
+        VK_CHECK_LAUNCH("agg_general_kernel(replay)");
+        VK_CUDA(cudaFreeAsync(replay_rows, s));
+        rc = read_counters(a, s);
+        if (rc != VK_OK) return rc;
+    }
+}
+
+int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkColumn* keys, const VkColumn* values,
+                  VkStream stream) {
+    VK_REQUIRE(a, "vk_agg_update: agg is NULL");
+    VK_REQUIRE(n_rows >= 0, "vk_agg_update: negative n_rows");
+    VK_REQUIRE(a->n_keys == 0 || keys, "vk_agg_update: keys is NULL");
+    VK_REQUIRE(a->n_funcs == 0 || values, "vk_agg_update: values is NULL");
+    cudaStream_t s = (cudaStream_t) stream;
+    for (int k = 0; k < a->n_keys; ++k) {
+        VK_REQUIRE(keys[k].dtype == a->key_dtypes[k], "vk_agg_update: key dtype changed between batches");
+        VK_REQUIRE(keys[k].length == n_rows, "vk_agg_update: key column length != n_rows");
+    }
+    for (int f = 0; f < a->n_funcs; ++f) {
+        if (a->specs[f].acc == ACC_NONE) continue;
+        VK_REQUIRE(values[f].dtype == a->specs[f].in_dtype, "vk_agg_update: value dtype changed between batches");
+        VK_REQUIRE(values[f].length == n_rows, "vk_agg_update: value column length != n_rows");
+    }
+    VkPredicate none{};
+    none.kind = VK_PRED_NONE;
+    if (!pred) pred = &none;
+
+    // ---- table on first use ----
+    if (!a->table_ready) {
+        int64_t cap;
+        if (a->n_keys == 0) cap = 1;
+        else {
+            int64_t guess = a->expected_groups > 0 ? a->expected_groups * 4 : (n_rows < (1 << 19) ? n_rows * 4 : (1 << 21));
+            cap = pow2_ceil(guess < 4096 ? 4096 : guess);
+        }
+        int rc = alloc_table(a, &a->t, cap, s);
+        if (rc != VK_OK) return rc;
+        a->table_ready = true;
+        a->groups_ub = 0;
+        if (a->n_keys == 0) {
+            // the single group exists even for empty input (COUNT(*) = 0, hash_agg_test.cpp:761-778)
+            uint32_t two = 2;
+            VK_CUDA(cudaMemcpyAsync(a->t.state, &two, sizeof(two), cudaMemcpyHostToDevice, s));
+            unsigned long long one = 1;
+            VK_CUDA(cudaMemcpyAsync(a->d_ctr + CTR_GROUPS, &one, sizeof(one), cudaMemcpyHostToDevice, s));
+            a->groups_ub = 1;
+            a->t.max_groups = 1;
+        }
+    }
+    if (n_rows == 0) return VK_OK;
+
+    // ---- un-grouped reduction ----
+    if (a->n_keys == 0) {
+        a->last_path = 3;
+        int64_t need = (n_rows + 255) / 256, capb = (int64_t) sm_count() * 8;
+        const unsigned grid = (unsigned) (need < capb ? need : capb);
+        for (int f = -1; f < a->n_funcs; ++f) {
+            if (f >= 0 && a->specs[f].acc == ACC_NONE) continue;
+            OneParams op{};
+            int pk;
+            int rc = make_pred(*pred, n_rows, &op.pred, &pk);
+            if (rc != VK_OK) return rc;
+            op.fi = f;
+            op.n = n_rows;
+            op.table = a->t;
+            if (f >= 0) {
+                op.spec = a->specs[f];
+                op.val = make_col(values[f]);
+            }
+            agg_onegroup_kernel<<<grid, 256, 0, s>>>(op);
+            VK_CHECK_LAUNCH("agg_onegroup_kernel");
+        }
+        return VK_OK;
+    }
+
+    // ---- path selection ----
+    bool fast = a->n_keys == 1 && !a->fast_disabled && keys[0].validity == nullptr && aligned_for_pairs(keys[0]);
+    int key_mode = 0;
+    if (fast) {
+        switch (keys[0].dtype) {
+            case VK_I64: case VK_U64: case VK_F64: key_mode = 0; break;
+            case VK_I32: key_mode = 1; break;
+            case VK_U32: case VK_F32: key_mode = 2; break;
+            default: fast = false;
+        }
+    }
+    VkColumn fast_vals[FA_MAX_VALS];
+    uint32_t fast_val_funcs[FA_MAX_VALS] = {0, 0};
+    int n_fast_vals = 0;
+    for (int f = 0; fast && f < a->n_funcs; ++f) {
+        const FuncSpec& sp = a->specs[f];
+        if (sp.acc == ACC_NONE) continue;
+        if (values[f].validity != nullptr) { fast = false; break; }
+        if (sp.acc == ACC_COUNT) continue;
+        if (sp.acc != ACC_SUM_F64 || sp.in_dtype != VK_F64 || !aligned_for_pairs(values[f])) { fast = false; break; }
+        int v = 0;
+        for (; v < n_fast_vals; ++v)
+            if (fast_vals[v].data == values[f].data && fast_vals[v].offset == values[f].offset) break;
+        if (v == n_fast_vals) {
+            if (n_fast_vals == FA_MAX_VALS) { fast = false; break; }
+            fast_vals[n_fast_vals++] = values[f];
+        }
+        fast_val_funcs[v] |= 1u << f;
+    }
+    Pred dpred;
+    int pk;
+    int rc = make_pred(*pred, n_rows, &dpred, &pk);
+    if (rc != VK_OK) return rc;
+
+    const int sms = sm_count();
+    int strat = a->strategy;
+    int log2s = a->log2s;
+    size_t smem = fast ? fast_smem_bytes(strat, n_fast_vals, log2s) : 0;
+    while (fast && smem > (size_t) max_smem_optin() && log2s > 6) smem = fast_smem_bytes(strat, n_fast_vals, --log2s);
+    if (fast && smem > (size_t) max_smem_optin()) fast = false;
+    int ctas_per_sm = 1;
+    if (fast) {
+        ctas_per_sm = (int) ((size_t) (max_smem_optin() + 1024) / (smem + 1024));
+        if (ctas_per_sm > 4) ctas_per_sm = 4;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const int fast_grid_max = sms * ctas_per_sm;
+    const int64_t S = (int64_t) 1 << log2s;
+
+    // ---- chunk loop: never more rows in flight than (free slots + replay capacity) ----
+    uint64_t list_max = (uint64_t) 1 << 28;
+    {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+            while (list_max * sizeof(uint32_t) > fr / 16 && list_max > (1u << 16)) list_max >>= 1;
+        }
+    }
+    int64_t pos = 0;
+    while (pos < n_rows) {
+        const int64_t remaining = n_rows - pos;
+        const int64_t flush_reserve = (fast && strat != FS_GLOBAL_RED) ? (int64_t) fast_grid_max * S : 0;
+        int64_t free_slots = a->t.max_groups - a->groups_ub - flush_reserve;
+        if (free_slots < 1024) {
+            // bound is pessimistic: refresh it, then grow if it is real
+            rc = read_counters(a, s);
+            if (rc != VK_OK) return rc;
+            a->groups_ub = (int64_t) a->h_ctr[CTR_GROUPS];
+            free_slots = a->t.max_groups - a->groups_ub - flush_reserve;
+            if (free_slots < 1024) {
+                rc = grow_table(a, a->groups_ub, a->groups_ub + flush_reserve + 4096, s);
+                if (rc != VK_OK) return rc;
+                free_slots = a->t.max_groups - a->groups_ub - flush_reserve;
+            }
+        }
+        int64_t chunk = remaining;
+        bool may_fail = false;
+        if (chunk > free_slots) {
+            uint64_t want = (uint64_t) (chunk - free_slots);
+            if (want > list_max) want = list_max;
+            rc = ensure_list(a, want, s);
+            if (rc != VK_OK) return rc;
+            if (chunk > free_slots + (int64_t) a->list_cap) chunk = free_slots + (int64_t) a->list_cap;
+            may_fail = true;
+        }
+        if (chunk > (int64_t) 0xfffff000LL) chunk = (int64_t) 0xfffff000LL;  // row ids in the list are 32-bit
+        if (chunk < remaining) chunk &= ~(int64_t) (FA_TILE - 1);            // keep chunk starts pair-aligned
+        if (chunk <= 0) return fail(VK_ERR_STATE, "vk_agg_update: internal error: empty chunk");
+        VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_LIST, 0, 3 * sizeof(unsigned long long), s));  // list, lost, spilled
+
+        VkPredicate cpred = *pred;
+        if (cpred.kind == VK_PRED_MASK) cpred.mask += pos;
+        if (cpred.kind == VK_PRED_CMP) cpred.column = slice_col(cpred.column, pos, chunk);
+        rc = make_pred(cpred, chunk, &dpred, &pk);
+        if (rc != VK_OK) return rc;
+
+        GenParams gp{};
+        gp.pred = dpred;
+        gp.pk = pk;
+        gp.n_keys = a->n_keys;
+        for (int k = 0; k < a->n_keys; ++k) gp.keys[k] = make_col(slice_col(keys[k], pos, chunk));
+        gp.n_funcs = a->n_funcs;
+        for (int f = 0; f < a->n_funcs; ++f) {
+            gp.specs[f] = a->specs[f];
+            if (a->specs[f].acc != ACC_NONE) gp.vals[f] = make_col(slice_col(values[f], pos, chunk));
+        }
+        gp.n = chunk;
+        gp.table = a->t;
+        gp.replay = make_replay(a);
+
+        if (fast) {
+            a->last_path = 1;
+            FastParams fp{};
+            fp.pred = dpred;
+            fp.key = gp.keys[0];
+            fp.key_mode = key_mode;
+            fp.n_vals = n_fast_vals;
+            for (int v = 0; v < n_fast_vals; ++v) {
+                fp.val[v] = make_col(slice_col(fast_vals[v], pos, chunk));
+                fp.val_funcs[v] = fast_val_funcs[v];
+            }
+            fp.n = chunk;
+            fp.num_tiles = (chunk + FA_TILE - 1) / FA_TILE;
+            fp.log2s = log2s;
+            fp.row_limit = strat == FS_GLOBAL_RED ? a->t.max_groups : a->t.max_groups - flush_reserve;
+            fp.table = a->t;
+            fp.replay = gp.replay;
+            int grid = fp.num_tiles < fast_grid_max ? (int) fp.num_tiles : fast_grid_max;
+            rc = launch_fast(fp, pk, strat, grid, smem, s);
+            if (rc != VK_OK) return rc;
+            a->groups_ub += chunk;
+        } else {
+            a->last_path = 2;
+            int64_t need = (chunk + 255) / 256, capb = (int64_t) sms * 8;
+            agg_general_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(gp);
+            VK_CHECK_LAUNCH("agg_general_kernel");
+            a->groups_ub += chunk;
+        }
+
+        if (may_fail || (fast && a->fast_rows < ((uint64_t) 1 << 22))) {
+            // rows may have been deferred (or we are still learning the cardinality)
+            rc = read_counters(a, s);
+            if (rc != VK_OK) return rc;
+            if (fast) {
+                a->fast_rows += (uint64_t) chunk;
+                a->fast_spilled += a->h_ctr[CTR_SPILL];
+                // shared-memory table thrashing: most rows fall through to the global path
+                if (a->fast_rows >= 65536 && a->fast_spilled * 4 > a->fast_rows) a->fast_disabled = true;
+            }
+            rc = run_replay_until_empty(a, gp, chunk, s);
+            if (rc != VK_OK) return rc;
+            if (a->fast_disabled) fast = false;
+        }
+        pos += chunk;
+    }
+    return VK_OK;
+}
+
+int vk_agg_num_groups(VkAgg* a, int64_t* out_groups, VkStream stream) {
+    VK_REQUIRE(a && out_groups, "vk_agg_num_groups: NULL argument");
+    if (!a->table_ready) {
+        *out_groups = a->n_keys == 0 ? 1 : 0;
+        return VK_OK;
+    }
+    int rc = read_counters(a, (cudaStream_t) stream);
+    if (rc != VK_OK) return rc;
+    a->groups_ub = (int64_t) a->h_ctr[CTR_GROUPS];
+    *out_groups = a->groups_ub;
+    return VK_OK;
+}
+
+int vk_agg_result(VkAgg* a, int64_t num_groups, uint64_t* const* out_keys, uint8_t* const* out_key_valid,
+                  uint64_t* out_count_star, uint64_t* const* out_vals_lo, uint64_t* const* out_vals_hi,
+                  uint8_t* const* out_vals_valid, VkStream stream) {
+    VK_REQUIRE(a, "vk_agg_result: agg is NULL");
+    cudaStream_t s = (cudaStream_t) stream;
+    if (num_groups == 0) return VK_OK;
+    VK_REQUIRE(out_count_star, "vk_agg_result: out_count_star is NULL");
+    if (!a->table_ready) {
+        // OneGroup result() without any batch: a single all-NULL / zero-count row
+        VK_REQUIRE(a->n_keys == 0 && num_groups == 1, "vk_agg_result: no batches were aggregated");
+        VK_CUDA(cudaMemsetAsync(out_count_star, 0, 8, s));
+        for (int f = 0; f < a->n_funcs; ++f) {
+            VK_CUDA(cudaMemsetAsync(out_vals_lo[f], 0, 8, s));
+            if (out_vals_hi && out_vals_hi[f]) VK_CUDA(cudaMemsetAsync(out_vals_hi[f], 0, 8, s));
+            int is_count = a->specs[f].func == VK_AGG_COUNT_STAR || a->specs[f].func == VK_AGG_COUNT;
+            VK_CUDA(cudaMemsetAsync(out_vals_valid[f], is_count ? 1 : 0, 1, s));
+        }
+        return VK_OK;
+    }
+    FinalParams fp{};
+    fp.table = a->t;
+    fp.num_groups = num_groups;
+    fp.null_last = a->n_keys == 1;
+    fp.cursor = a->d_ctr + CTR_CURSOR;
+    VK_CUDA(cudaMemsetAsync(fp.cursor, 0, sizeof(unsigned long long), s));
+    for (int k = 0; k < a->n_keys; ++k) {
+        VK_REQUIRE(out_keys && out_keys[k] && out_key_valid && out_key_valid[k], "vk_agg_result: NULL key output");
+        fp.out_keys[k] = out_keys[k];
+        fp.out_key_valid[k] = out_key_valid[k];
+    }
+    fp.out_count_star = out_count_star;
+    for (int f = 0; f < a->n_funcs; ++f) {
+        VK_REQUIRE(out_vals_lo && out_vals_lo[f] && out_vals_valid && out_vals_valid[f], "vk_agg_result: NULL value output");
+        fp.specs[f] = a->specs[f];
+        fp.out_lo[f] = out_vals_lo[f];
+        fp.out_hi[f] = out_vals_hi ? out_vals_hi[f] : nullptr;
+        fp.out_valid[f] = out_vals_valid[f];
+    }
+    int64_t need = (a->t.capacity + 255) / 256, capb = (int64_t) sm_count() * 8;
+    agg_finalize_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(fp);
+    VK_CHECK_LAUNCH("agg_finalize_kernel");
+    return VK_OK;
+}
+
+int vk_agg_record_words(VkAgg* a, int* out_words) {
+    VK_REQUIRE(a && out_words, "vk_agg_record_words: NULL argument");
+    *out_words = a->n_keys + 2 + 3 * a->n_funcs;
+    return VK_OK;
+}
+
+static int exch_params(VkAgg* a, ExchParams* p) {
+    memset(p, 0, sizeof(*p));
+    p->table = a->t;
+    for (int f = 0; f < a->n_funcs; ++f) p->specs[f] = a->specs[f];
+    p->words = a->n_keys + 2 + 3 * a->n_funcs;
+    return VK_OK;
+}
+
+int vk_agg_partition_counts(VkAgg* a, int n_ranks, int64_t* out_counts_dev, VkStream stream) {
+    VK_REQUIRE(a && out_counts_dev && n_ranks >= 1, "vk_agg_partition_counts: bad argument");
+    cudaStream_t s = (cudaStream_t) stream;
+    VK_CUDA(cudaMemsetAsync(out_counts_dev, 0, sizeof(int64_t) * n_ranks, s));
+    if (!a->table_ready) return VK_OK;
+    ExchParams p;
+    exch_params(a, &p);
+    p.n_ranks = n_ranks;
+    p.counts = reinterpret_cast<long long*>(out_counts_dev);
+    int64_t need = (a->t.capacity + 255) / 256, capb = (int64_t) sm_count() * 8;
+    agg_partition_count_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(p);
+    VK_CHECK_LAUNCH("agg_partition_count_kernel");
+    return VK_OK;
+}
+
+int vk_agg_export_partials(VkAgg* a, int n_ranks, const int64_t* offsets_dev, uint64_t* out_records, VkStream stream) {
+    VK_REQUIRE(a && offsets_dev && n_ranks >= 1, "vk_agg_export_partials: bad argument");
+    if (!a->table_ready) return VK_OK;
+    VK_REQUIRE(out_records, "vk_agg_export_partials: out_records is NULL");
+    cudaStream_t s = (cudaStream_t) stream;
+    ExchParams p;
+    exch_params(a, &p);
+    p.n_ranks = n_ranks;
+    p.offsets = reinterpret_cast<const long long*>(offsets_dev);
+    p.out = out_records;
+    unsigned long long* cursors = nullptr;
+    VK_CUDA(cudaMallocAsync((void**) &cursors, sizeof(unsigned long long) * n_ranks, s));
+    VK_CUDA(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * n_ranks, s));
+    p.cursors = cursors;
+    int64_t need = (a->t.capacity + 255) / 256, capb = (int64_t) sm_count() * 8;
+    agg_export_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(p);
+    VK_CHECK_LAUNCH("agg_export_kernel");
+    VK_CUDA(cudaFreeAsync(cursors, s));
+    return VK_OK;
+}
+
+int vk_agg_merge_partials(VkAgg* a, const uint64_t* records, int64_t n_records, VkStream stream) {
+    VK_REQUIRE(a && n_records >= 0, "vk_agg_merge_partials: bad argument");
+    VK_REQUIRE(a->n_keys > 0, "vk_agg_merge_partials: un-grouped aggregates merge on the host");
+    if (n_records == 0) return VK_OK;
+    VK_REQUIRE(records, "vk_agg_merge_partials: records is NULL");
+    cudaStream_t s = (cudaStream_t) stream;
+    if (!a->table_ready) {
+        int rc = alloc_table(a, &a->t, pow2_ceil(n_records * 4 < 4096 ? 4096 : n_records * 4), s);
+        if (rc != VK_OK) return rc;
+        a->table_ready = true;
+        a->groups_ub = 0;
+    }
+    // make room for every record becoming a new group: merging can then never fail
+    int rc = read_counters(a, s);
+    if (rc != VK_OK) return rc;
+    a->groups_ub = (int64_t) a->h_ctr[CTR_GROUPS];
+    rc = grow_table(a, a->groups_ub, n_records + 1024, s);
+    if (rc != VK_OK) return rc;
+    rc = ensure_list(a, 1024, s);
+    if (rc != VK_OK) return rc;
+    VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_LIST, 0, 3 * sizeof(unsigned long long), s));
+    ExchParams p;
+    exch_params(a, &p);
+    p.in = records;
+    p.n_in = n_records;
+    p.replay = make_replay(a);
+    int64_t need = (n_records + 255) / 256, capb = (int64_t) sm_count() * 8;
+    agg_merge_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(p);
+    VK_CHECK_LAUNCH("agg_merge_kernel");
+    a->groups_ub += n_records;
+    return VK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,427 @@
+// Device radix sort + gather.
+//
+// Replaces Sort::Sorted (vinum_cpp/src/operators/sort/sort.cpp:15-63), i.e. Arrow's
+// SortIndices (stable; NaN after every number, NULL after NaN, in BOTH directions;
+// -0.0 == +0.0) followed by Take.
+//
+// Each sort key is mapped to an order-preserving 64-bit integer (DESC = complement of
+// the numeric code, so ties keep their input order), then sorted with a stable LSD
+// radix sort over 8-bit digits: one histogram pass finds the digits that actually
+// vary (constant digits are skipped), and every remaining digit is ONE pass over the
+// data ("onesweep": per-tile digit counts are chained with a decoupled look-back, so a
+// pass reads and writes each (key, row-id) pair exactly once).  Multi-key sorts run
+// the keys from last to first on the running permutation.
+#include "vk_common.cuh"
+
+namespace vk {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr uint32_t RS_NULLBIT = 0x80000000u;
+
+constexpr uint64_t KEY_NAN = 0xFFFFFFFFFFFFFFFEULL;
+constexpr uint64_t KEY_NULL = 0xFFFFFFFFFFFFFFFFULL;
+
+// ---------------------------------------------------------------- prepare ----
+// key'[i] = code(col[perm[i]]), idx[i] = perm[i] (| NULLBIT for NULL integer keys),
+// plus the 8 x 256 digit histogram of the codes.
+struct PrepParams {
+    Col col;
+    int desc;
+    int int_nulls;            // integer column with a validity bitmap: NULLs ride in idx bit 31
+    const uint32_t* perm;     // nullptr: identity
+    int64_t n;
+    uint64_t* out_key;
+    uint32_t* out_idx;
+    unsigned long long* hist; // [9][256]; row 8 = NULL-bit digit (2 buckets used)
+};
+
+__device__ __forceinline__ uint64_t sort_code(const Col& c, int64_t i, int desc, bool* is_null) {
+    *is_null = !col_valid(c, i);
+    if (dtype_is_float(c.dtype)) {
+        if (*is_null) { *is_null = false; return KEY_NULL; }  // in-band for floats
+        double d = load_as_f64_raw(c, i);
+        if (d != d) return KEY_NAN;
+        if (d == 0.0) d = 0.0;  // -0.0 -> +0.0
+        uint64_t o = f64_to_ordered((uint64_t) __double_as_longlong(d));
+        return desc ? ~o : o;
+    }
+    if (*is_null) return 0;
+    uint64_t raw = load_as_u64(c, i);
+    uint64_t o = dtype_is_signed(c.dtype) ? (raw ^ 0x8000000000000000ULL) : raw;
+    return desc ? ~o : o;
+}
+
+__global__ void __launch_bounds__(256) sort_prepare_kernel(const __grid_constant__ PrepParams p) {
+    __shared__ uint32_t s_hist[9 * 256];
+    for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    // uniform trip count so the warp votes below are convergent
+    const int64_t iters = (p.n + stride - 1) / stride;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = it * stride + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+        const bool in = i < p.n;
+        uint64_t code = 0;
+        uint32_t idx = 0;
+        if (in) {
+            const int64_t src = p.perm ? (int64_t) (p.perm[i] & ~RS_NULLBIT) : i;
+            bool is_null;
+            code = sort_code(p.col, src, p.desc, &is_null);
+            idx = (uint32_t) src | ((p.int_nulls && is_null) ? RS_NULLBIT : 0u);
+            p.out_key[i] = code;
+            p.out_idx[i] = idx;
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, in);
+        if (!active) continue;
+        const int leader = __ffs(active) - 1;
+#pragma unroll
+        for (int d = 0; d < 9; ++d) {
+            const uint32_t digit = d < 8 ? (uint32_t) (code >> (8 * d)) & 0xffu : (idx >> 31);
+            const uint32_t first = __shfl_sync(0xffffffffu, digit, leader);
+            // constant digits are the common case (small integers): one add per warp
+            if (__all_sync(0xffffffffu, !in || digit == first)) {
+                if ((threadIdx.x & 31) == leader) atomicAdd(&s_hist[d * 256 + first], (uint32_t) __popc(active));
+            } else if (in) {
+                atomicAdd(&s_hist[d * 256 + digit], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(p.hist + i, (unsigned long long) s_hist[i]);
+}
+
+// exclusive scan of each digit's 256 buckets: hist -> bucket start offsets (in place)
+__global__ void __launch_bounds__(256) sort_scan_kernel(unsigned long long* hist) {
+    __shared__ unsigned long long s[256];
+    const int d = blockIdx.x, t = threadIdx.x;
+    unsigned long long v = hist[d * 256 + t];
+    s[t] = v;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        unsigned long long a = t >= off ? s[t - off] : 0;
+        __syncthreads();
+        s[t] += a;
+        __syncthreads();
+    }
+    hist[d * 256 + t] = s[t] - v;
+}
+
+// -------------------------------------------------------------- radix pass ----
+constexpr uint64_t RS_FLAG_SHIFT = 62;
+constexpr uint64_t RS_AGG = 1ULL << RS_FLAG_SHIFT;
+constexpr uint64_t RS_PREFIX = 2ULL << RS_FLAG_SHIFT;
+constexpr uint64_t RS_VALUE_MASK = (1ULL << RS_FLAG_SHIFT) - 1;
+
+struct PassParams {
+    const uint64_t* in_key;
+    const uint32_t* in_idx;
+    uint64_t* out_key;
+    uint32_t* out_idx;
+    int64_t n;
+    int shift;                          // 0..56, or 64 for the NULL-bit pass
+    const unsigned long long* bucket_start;  // [256] for this digit
+    unsigned long long* ticket;
+    unsigned long long* status;         // [tiles][256]
+};
+
+__device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int shift) {
+    return shift == 64 ? (idx >> 31) : (uint32_t) (key >> shift) & 0xffu;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) sort_pass_kernel(const __grid_constant__ PassParams p) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    uint64_t* s_key = reinterpret_cast<uint64_t*>(rs_smem);
+    uint32_t* s_idx = reinterpret_cast<uint32_t*>(rs_smem + (size_t) RS_TILE * 8);
+    __shared__ uint32_t s_wcnt[RS_WARPS][256];   // per-warp digit counters -> warp offsets
+    __shared__ uint32_t s_lb[256];               // tile-local bucket start
+    __shared__ unsigned long long s_gbase[256];  // global position of the bucket's first item of this tile
+    __shared__ int64_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (int64_t) atomicAdd(p.ticket, 1ULL);
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s_wcnt[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t base = tile * RS_TILE;
+    const int tile_n = (int) ((p.n - base) < RS_TILE ? (p.n - base) : RS_TILE);
+    const unsigned lt = lanemask_lt();
+
+    // ---- load (warp-striped: item k of lane l is element warp*512 + k*32 + l) ----
+    uint64_t key[RS_ITEMS];
+    uint32_t idx[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+        if (li < tile_n) {
+            key[k] = p.in_key[base + li];
+            idx[k] = p.in_idx[base + li];
+        } else {
+            key[k] = 0;
+            idx[k] = 0;
+        }
+    }
+    // ---- stable rank inside the warp's 512 items ----
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+        const bool in = li < tile_n;
+        const uint32_t d = pass_digit(key[k], idx[k], p.shift);
+        const unsigned peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
+        const int leader = __ffs(peers) - 1;
+        uint32_t c = 0;
+        if (in && lane == leader) {
+            c = s_wcnt[warp][d];
+            s_wcnt[warp][d] = c + __popc(peers);
+        }
+        c = __shfl_sync(0xffffffffu, c, leader);
+        rank[k] = c + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per bucket (thread b <-> bucket b): scan over warps, publish, look back ----
+    {
+        const int b = tid;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t c = s_wcnt[w][b];
+            s_wcnt[w][b] = run;
+            run += c;
+        }
+        const uint64_t total = run;
+        unsigned long long* st = p.status + tile * 256 + b;
+        uint64_t excl = 0;
+        if (tile == 0) {
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(st), "l"(RS_PREFIX | total) : "memory");
+        } else {
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(st), "l"(RS_AGG | total) : "memory");
+            int64_t look = tile - 1;
+            while (true) {
+                unsigned long long v;
+                const unsigned long long* q = p.status + look * 256 + b;
+                do {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+                } while ((v >> RS_FLAG_SHIFT) == 0);
+                excl += v & RS_VALUE_MASK;
+                if ((v >> RS_FLAG_SHIFT) == 2) break;
+                --look;
+            }
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(st), "l"(RS_PREFIX | (excl + total)) : "memory");
+        }
+        s_gbase[b] = p.bucket_start[b] + excl;
+        // tile-local exclusive scan over buckets
+        s_lb[b] = (uint32_t) total;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // 256 counts, 8 per lane
+        uint32_t v[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] = s_lb[lane * 8 + j]; sum += v[j]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, dlt);
+            if (lane >= dlt) inc += t;
+        }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s_lb[lane * 8 + j] = run; run += v[j]; }
+    }
+    __syncthreads();
+
+    // ---- reorder inside shared memory, then write bucket runs ----
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+        if (li < tile_n) {
+            const uint32_t d = pass_digit(key[k], idx[k], p.shift);
+            const uint32_t pos = s_lb[d] + s_wcnt[warp][d] + rank[k];
+            s_key[pos] = key[k];
+            s_idx[pos] = idx[k];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < tile_n; i += RS_THREADS) {
+        const uint64_t kx = s_key[i];
+        const uint32_t ix = s_idx[i];
+        const uint32_t d = pass_digit(kx, ix, p.shift);
+        const unsigned long long dst = s_gbase[d] + (uint32_t) (i - s_lb[d]);
+        p.out_key[dst] = kx;
+        p.out_idx[dst] = ix;
+    }
+}
+
+__global__ void __launch_bounds__(256) sort_iota_kernel(uint32_t* idx, int64_t n) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) idx[i] = (uint32_t) i;
+}
+__global__ void __launch_bounds__(256) sort_widen_kernel(const uint32_t* idx, int64_t n, int64_t* out) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (int64_t) (idx[i] & ~RS_NULLBIT);
+}
+
+// ------------------------------------------------------------------- take ----
+struct TakeParams {
+    Col col;
+    const int64_t* indices;
+    int64_t n;
+    void* out;
+    uint8_t* out_valid;
+};
+__global__ void __launch_bounds__(256) take_kernel(const __grid_constant__ TakeParams p) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int es = dtype_size(p.col.dtype);
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const int64_t src = p.indices[i];
+        if (es == 8) reinterpret_cast<uint64_t*>(p.out)[i] = reinterpret_cast<const uint64_t*>(p.col.data)[src];
+        else if (es == 4) reinterpret_cast<uint32_t*>(p.out)[i] = reinterpret_cast<const uint32_t*>(p.col.data)[src];
+        else if (es == 2) reinterpret_cast<uint16_t*>(p.out)[i] = reinterpret_cast<const uint16_t*>(p.col.data)[src];
+        else reinterpret_cast<uint8_t*>(p.out)[i] = p.col.data[src];
+        if (p.out_valid) p.out_valid[i] = col_valid(p.col, src);
+    }
+}
+
+static unsigned grid_rows(int64_t n, int per_sm = 8) {
+    int64_t need = (n + 255) / 256, cap = (int64_t) sm_count() * per_sm;
+    if (need < 1) need = 1;
+    return (unsigned) (need < cap ? need : cap);
+}
+
+struct SortScratch {
+    uint64_t* key[2];
+    uint32_t* idx[2];
+    unsigned long long* hist;    // [9][256]
+    unsigned long long* ticket;  // 1
+    unsigned long long* status;  // [tiles][256]
+    size_t status_bytes;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t carve(int64_t n, void* base, SortScratch* s) {
+    const int64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    uint64_t* k0 = (uint64_t*) take((size_t) n * 8);
+    uint64_t* k1 = (uint64_t*) take((size_t) n * 8);
+    uint32_t* i0 = (uint32_t*) take((size_t) n * 4);
+    uint32_t* i1 = (uint32_t*) take((size_t) n * 4);
+    unsigned long long* hist = (unsigned long long*) take(9 * 256 * 8);
+    unsigned long long* ticket = (unsigned long long*) take(256);
+    size_t sb = (size_t) (tiles > 0 ? tiles : 1) * 256 * 8;
+    unsigned long long* status = (unsigned long long*) take(sb);
+    if (s) {
+        s->key[0] = k0; s->key[1] = k1; s->idx[0] = i0; s->idx[1] = i1;
+        s->hist = hist; s->ticket = ticket; s->status = status; s->status_bytes = sb;
+    }
+    return off;
+}
+
+}  // namespace vk
+
+using namespace vk;
+
+extern "C" {
+
+uint64_t vk_sort_scratch_bytes(int64_t n_rows) {
+    if (n_rows < 1) n_rows = 1;
+    return carve(n_rows, nullptr, nullptr);
+}
+
+int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int64_t n_rows,
+                    int64_t* out_indices, void* scratch, VkStream stream) {
+    VK_REQUIRE(keys && orders && n_keys >= 1, "vk_sort_indices: at least one sort key is required");
+    VK_REQUIRE(n_rows >= 0, "vk_sort_indices: negative n_rows");
+    if (n_rows == 0) return VK_OK;
+    VK_REQUIRE(out_indices && scratch, "vk_sort_indices: NULL buffer");
+    VK_REQUIRE(n_rows < (int64_t) 0x7fffffffLL, "vk_sort_indices: at most 2^31-1 rows per call");
+    for (int k = 0; k < n_keys; ++k) {
+        VK_REQUIRE(dtype_valid(keys[k].dtype), "vk_sort_indices: bad key dtype");
+        VK_REQUIRE(keys[k].dtype != VK_BOOL8, "Sorting by boolean column is not supported yet.");  // algebra.py:191-201
+        VK_REQUIRE(keys[k].length == n_rows, "vk_sort_indices: key length != n_rows");
+        VK_REQUIRE(orders[k] == VK_ASC || orders[k] == VK_DESC, "vk_sort_indices: bad sort order");
+    }
+    cudaStream_t s = (cudaStream_t) stream;
+    SortScratch sc;
+    carve(n_rows, scratch, &sc);
+    const int64_t tiles = (n_rows + RS_TILE - 1) / RS_TILE;
+    VK_CUDA(cudaFuncSetAttribute(sort_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 12));
+    int cur = 0;            // buffers holding the running (key', idx)
+    bool have_perm = false;
+    unsigned long long h_hist[9 * 256];
+
+    for (int k = n_keys - 1; k >= 0; --k) {
+        // ---- codes of this key in the running order + digit histograms ----
+        PrepParams pp{};
+        pp.col = make_col(keys[k]);
+        pp.desc = orders[k] == VK_DESC;
+        pp.int_nulls = keys[k].validity != nullptr && !dtype_is_float(keys[k].dtype);
+        pp.perm = have_perm ? sc.idx[cur] : nullptr;
+        pp.n = n_rows;
+        const int nxt = cur ^ 1;
+        pp.out_key = sc.key[nxt];
+        pp.out_idx = sc.idx[nxt];
+        pp.hist = sc.hist;
+        VK_CUDA(cudaMemsetAsync(sc.hist, 0, 9 * 256 * 8, s));
+        sort_prepare_kernel<<<grid_rows(n_rows, 4), 256, 0, s>>>(pp);
+        VK_CHECK_LAUNCH("sort_prepare_kernel");
+        cur = nxt;
+        have_perm = true;
+        VK_CUDA(cudaMemcpyAsync(h_hist, sc.hist, sizeof(h_hist), cudaMemcpyDeviceToHost, s));
+        VK_CUDA(cudaStreamSynchronize(s));
+        sort_scan_kernel<<<9, 256, 0, s>>>(sc.hist);
+        VK_CHECK_LAUNCH("sort_scan_kernel");
+        // ---- one pass per digit that actually varies ----
+        for (int d = 0; d < 9; ++d) {
+            bool varies = true;
+            for (int b = 0; b < 256; ++b)
+                if (h_hist[d * 256 + b] == (unsigned long long) n_rows) { varies = false; break; }
+            if (!varies) continue;
+            PassParams ps{};
+            ps.in_key = sc.key[cur];
+            ps.in_idx = sc.idx[cur];
+            ps.out_key = sc.key[cur ^ 1];
+            ps.out_idx = sc.idx[cur ^ 1];
+            ps.n = n_rows;
+            ps.shift = d < 8 ? 8 * d : 64;
+            ps.bucket_start = sc.hist + d * 256;
+            ps.ticket = sc.ticket;
+            ps.status = sc.status;
+            VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
+            VK_CUDA(cudaMemsetAsync(sc.status, 0, sc.status_bytes, s));
+            sort_pass_kernel<<<(unsigned) tiles, RS_THREADS, RS_TILE * 12, s>>>(ps);
+            VK_CHECK_LAUNCH("sort_pass_kernel");
+            cur ^= 1;
+        }
+    }
+    sort_widen_kernel<<<grid_rows(n_rows), 256, 0, s>>>(sc.idx[cur], n_rows, out_indices);
+    VK_CHECK_LAUNCH("sort_widen_kernel");
+    return VK_OK;
+}
+
+int vk_take(const VkColumn* col, const int64_t* indices, int64_t n_indices, void* out, uint8_t* out_valid_bytes,
+            VkStream stream) {
+    VK_REQUIRE(col && n_indices >= 0, "vk_take: bad argument");
+    if (n_indices == 0) return VK_OK;
+    VK_REQUIRE(indices && out, "vk_take: NULL buffer");
+    VK_REQUIRE(dtype_valid(col->dtype), "vk_take: bad dtype");
+    VK_REQUIRE(col->validity == nullptr || out_valid_bytes, "vk_take: column has validity but no out_valid_bytes");
+    TakeParams p{make_col(*col), indices, n_indices, out, col->validity ? out_valid_bytes : nullptr};
+    take_kernel<<<grid_rows(n_indices), 256, 0, (cudaStream_t) stream>>>(p);
+    VK_CHECK_LAUNCH("take_kernel");
+    return VK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+"""Drop-in replacement of the reference's `vinum_lib` extension module.
+
+Same Python-visible names, constructor signatures, method names and error behaviour
+as the pybind11 module of vinum/core/vinum_lib.cpp:20-167, but every operator runs on
+the GPU through the C ABI (include/vinum_b200.h):
+
+    AggFuncType, SortOrder, AggFuncDef,
+    SingleNumericalHashAggregate, MultiNumericalHashAggregate, OneGroupAggregate,
+    GenericHashAggregate (string / any-type keys: not on the device path yet),
+    Sort, TableBatchReader, import_pyarrow
+
+`next(batch)` takes a host `pyarrow.RecordBatch` (as the reference does), copies only
+the referenced columns to the device asynchronously and launches the update kernel;
+`result()` / `sorted()` return a host `pyarrow.RecordBatch`.  A `DeviceBatch`
+(vinum_b200.device) is accepted wherever a RecordBatch is, which skips the copy.
+
+To use it in the reference: `sys.modules['vinum_lib'] = vinum_b200.vinum_lib` before
+`import vinum`.
+"""
+from __future__ import annotations
+
+import enum
+from typing import List, Optional, Sequence
+
+import pyarrow as pa
+
+from . import _lib as L
+from .aggregate import Aggregator
+from .device import DeviceBatch, DeviceColumn, Stream, default_stream
+from . import ops
+
+
+def import_pyarrow() -> int:
+    """vinum_lib.cpp:22-23.  The shim has no libarrow_python dependency; 0 == success."""
+    return 0
+
+
+class AggFuncType(enum.IntEnum):
+    """vinum_lib.cpp:25-32 (values are the C ABI's VkAggFunc codes)."""
+    COUNT_STAR = L.AGG_COUNT_STAR
+    COUNT = L.AGG_COUNT
+    MIN = L.AGG_MIN
+    MAX = L.AGG_MAX
+    SUM = L.AGG_SUM
+    AVG = L.AGG_AVG
+
+
+class SortOrder(enum.IntEnum):
+    """vinum_lib.cpp:34-37."""
+    ASC = L.ASC
+    DESC = L.DESC
+
+
+# pybind11's export_values()
+COUNT_STAR, COUNT, MIN, MAX, SUM, AVG = (AggFuncType.COUNT_STAR, AggFuncType.COUNT, AggFuncType.MIN,
+                                         AggFuncType.MAX, AggFuncType.SUM, AggFuncType.AVG)
+ASC, DESC = SortOrder.ASC, SortOrder.DESC
+
+
+class AggFuncDef:
+    """vinum_lib.cpp:39-51 / agg_funcs.h:20-24.  `column_name == ''` for COUNT(*)."""
+
+    def __init__(self, func: AggFuncType, column_name: str, out_col_name: str):
+        self.func = AggFuncType(func)
+        self._column_name = str(column_name)
+        self._out_col_name = str(out_col_name)
+
+    @property
+    def column_name(self) -> str:
+        return self._column_name
+
+    @property
+    def out_col_name(self) -> str:
+        return self._out_col_name
+
+    def __repr__(self) -> str:
+        return f"<AggFuncDef col_name: {self._column_name}, out_col_name: {self._out_col_name}>"
+
+
+def _as_batch_like(batch):
+    if isinstance(batch, (pa.RecordBatch, pa.Table, DeviceBatch)):
+        return batch
+    # the reference aborts the process here (`.ValueOrDie()`, vinum_lib.cpp:62-63)
+    raise TypeError(f"expected pyarrow.RecordBatch, got {type(batch).__name__}")
+
+
+def _schema_of(batch) -> pa.Schema:
+    return batch.schema() if isinstance(batch, DeviceBatch) else batch.schema
+
+
+def _column_to_device(batch, name: str, stream: Stream) -> DeviceColumn:
+    if isinstance(batch, DeviceBatch):
+        return batch.column(name)
+    idx = batch.schema.get_field_index(name)
+    return DeviceColumn.from_arrow(batch.column(idx), stream)
+
+
+class _BaseAggregate:
+    """BaseAggregate (base_aggregate.h:15-45): streaming state of one aggregate operator."""
+
+    _min_keys = 1
+    _max_keys = L.AGG_MAX_KEYS
+
+    def __init__(self, groupby_cols: Sequence[str], agg_cols: Sequence[str], agg_funcs: Sequence[AggFuncDef]):
+        self._groupby_cols = [str(c) for c in groupby_cols]
+        self._agg_cols = [str(c) for c in agg_cols]
+        self._funcs = list(agg_funcs)
+        for f in self._funcs:
+            if not isinstance(f, AggFuncDef):
+                raise TypeError("agg_funcs must be a list of AggFuncDef")
+        if not (self._min_keys <= len(self._groupby_cols) <= self._max_keys):
+            raise RuntimeError(f"{type(self).__name__}: unsupported number of group-by columns "
+                               f"({len(self._groupby_cols)})")
+        self._agg: Optional[Aggregator] = None
+        self._key_types: List[pa.DataType] = []
+        self._stream = default_stream()
+
+    # -- BaseAggregate::EnsureInitAggFuncs, base_aggregate.cpp:91-119
+    def _ensure_init(self, schema: pa.Schema) -> None:
+        if self._agg is not None:
+            return
+        for name in self._groupby_cols + self._agg_cols:
+            if schema.get_field_index(name) == -1:
+                raise RuntimeError("Column not found: " + name)  # base_aggregate.cpp:121-131
+        self._key_types = [schema.field(n).type for n in self._groupby_cols]
+        specs = []
+        for f in self._funcs:
+            if f.column_name:
+                if schema.get_field_index(f.column_name) == -1:
+                    raise RuntimeError("Column not found: " + f.column_name)
+                specs.append((int(f.func), schema.field(f.column_name).type))
+            else:
+                specs.append((int(f.func), None))
+        self._check_key_types(self._key_types)
+        self._agg = Aggregator(self._key_types, specs)
+
+    def _check_key_types(self, types) -> None:
+        for t in types:
+            if not (pa.types.is_integer(t) or pa.types.is_floating(t) or pa.types.is_temporal(t)):
+                raise RuntimeError("Unsupported data type for aggregation column.")  # array_iterators.cpp:79
+
+    def next(self, batch) -> None:
+        batch = _as_batch_like(batch)
+        self._ensure_init(_schema_of(batch))
+        st = self._stream
+        cache = {}
+
+        def col(name):
+            if name not in cache:
+                cache[name] = _column_to_device(batch, name, st)
+            return cache[name]
+
+        keys = [col(n) for n in self._groupby_cols]
+        values = [col(f.column_name) if f.column_name else None for f in self._funcs]
+        if not keys and all(v is None for v in values):
+            self._agg.update_count_rows(batch.num_rows, None, st)
+        else:
+            self._agg.update(keys, values, None, st)
+        if not isinstance(batch, DeviceBatch):
+            st.sync()  # the async copies read the caller's Arrow buffers
+
+    def result(self) -> pa.RecordBatch:
+        if self._agg is None:
+            # result() before any batch: the reference builds an empty batch with no
+            # schema information (base_aggregate.cpp:47-68)
+            return pa.RecordBatch.from_arrays([], names=[])
+        key_arrays, agg_arrays = self._agg.result_arrays(self._stream)
+        arrays, names = [], []
+        for name in self._agg_cols:  # GROUP_BUILDER columns first, base_aggregate.cpp:100-108
+            arrays.append(key_arrays[self._groupby_cols.index(name)])
+            names.append(name)
+        for f, arr in zip(self._funcs, agg_arrays):
+            arrays.append(arr)
+            names.append(f.out_col_name)
+        return pa.RecordBatch.from_arrays(arrays, names=names)
+
+
+class SingleNumericalHashAggregate(_BaseAggregate):
+    """vinum_lib.cpp:54-71; single_numerical_hash_aggregate.cpp:15-68."""
+    _min_keys = 1
+    _max_keys = 1
+
+
+class MultiNumericalHashAggregate(_BaseAggregate):
+    """vinum_lib.cpp:73-90; multi_numerical_hash_aggregate.cpp:17-58."""
+    _min_keys = 1
+
+
+class GenericHashAggregate(_BaseAggregate):
+    """vinum_lib.cpp:92-109.  Numeric keys run on the device; string / bool / nested
+    keys (generic_hash_aggregate.h:9-43) are a SURVEY 8f 'next' row."""
+    _min_keys = 1
+
+    def _check_key_types(self, types) -> None:
+        for t in types:
+            if not (pa.types.is_integer(t) or pa.types.is_floating(t) or pa.types.is_temporal(t)):
+                raise NotImplementedError(
+                    f"GenericHashAggregate over key type {t} is not implemented on the device path")
+
+
+class OneGroupAggregate(_BaseAggregate):
+    """vinum_lib.cpp:111-124; one_group_aggregate.cpp:9-37."""
+    _min_keys = 0
+    _max_keys = 0
+
+    def __init__(self, agg_funcs: Sequence[AggFuncDef]):
+        super().__init__([], [], agg_funcs)
+
+
+class Sort:
+    """vinum_lib.cpp:126-142; Sort::Next buffers (sort.cpp:11-13), Sort::Sorted sorts
+    everything at once (sort.cpp:15-63)."""
+
+    def __init__(self, sort_cols: Sequence[str], sort_order: Sequence[SortOrder]):
+        self._cols = [str(c) for c in sort_cols]
+        self._order = [int(SortOrder(o)) for o in sort_order]
+        if len(self._cols) != len(self._order):
+            raise RuntimeError("Sort: sort_cols and sort_order differ in length")
+        self._batches: List = []
+        self._stream = default_stream()
+
+    def next(self, batch) -> None:
+        self._batches.append(_as_batch_like(batch))
+
+    def sorted(self) -> pa.RecordBatch:
+        if not self._batches:
+            raise RuntimeError("Failed to create table from record batches.")  # sort.cpp:17-19
+        st = self._stream
+        if all(isinstance(b, DeviceBatch) for b in self._batches) and len(self._batches) == 1:
+            dev = self._batches[0]
+            schema = dev.schema()
+        else:
+            host = [b.to_arrow(st) if isinstance(b, DeviceBatch) else b for b in self._batches]
+            table = pa.Table.from_batches([b for b in host]) if not isinstance(host[0], pa.Table) else pa.concat_tables(host)
+            table = table.combine_chunks()
+            schema = table.schema
+            for name in self._cols:
+                if schema.get_field_index(name) == -1:
+                    raise RuntimeError("Failed to sort table.")  # sort.cpp:34-36
+            dev = DeviceBatch.from_arrow(table, st)
+        for name in self._cols:
+            if name not in dev.column_names:
+                raise RuntimeError("Failed to sort table.")
+            if pa.types.is_boolean(dev.column(name).arrow_type):
+                raise RuntimeError("Failed to sort table.")  # Arrow 3.0 could not sort booleans (algebra.py:191-201)
+        out = ops.sort_batch(dev, self._cols, self._order, st)
+        return out.to_arrow(st)
+
+
+class TableBatchReader:
+    """vinum_lib.cpp:144-165; table_batch_reader.cpp:5-16 -- zero-copy row-range slices
+    of the table, one RecordBatch per call, None at the end."""
+
+    def __init__(self, table: pa.Table):
+        if not isinstance(table, pa.Table):
+            raise TypeError(f"expected pyarrow.Table, got {type(table).__name__}")
+        self._table = table
+        self._batch_size: Optional[int] = None
+        self._iter = None
+
+    def set_batch_size(self, batch_size: int) -> None:
+        self._batch_size = int(batch_size)
+
+    def next(self) -> Optional[pa.RecordBatch]:
+        if self._iter is None:
+            self._iter = iter(self._table.to_batches(max_chunksize=self._batch_size))
+        return next(self._iter, None)
