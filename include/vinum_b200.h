@@ -98,6 +98,7 @@ int vk_event_create(VkEvent* out_event);
 int vk_event_destroy(VkEvent event);
 int vk_event_record(VkEvent event, VkStream stream);
 int vk_event_sync(VkEvent event);
+int vk_stream_wait_event(VkStream stream, VkEvent event);  /* cudaStreamWaitEvent */
 int vk_event_elapsed_ms(VkEvent start, VkEvent stop, float* out_ms);
 /* number of kernels this library has launched since load (bench.py `gpu_launches`) */
 uint64_t vk_launch_count(void);
@@ -246,6 +247,12 @@ int vk_agg_merge_partials(VkAgg* agg, const uint64_t* records, int64_t n_records
 /* introspection for tests/bench: which kernel path the last update used
  * (0 = none, 1 = shared-memory table, 2 = global table, 3 = one-group reduction) */
 int vk_agg_last_path(VkAgg* agg);
+/* Optional per-launch kernel timing (CUDA events recorded on the launch stream, resolved
+ * lazily: no extra synchronisation).  vk_agg_profile_read returns, for `path` (1/2 as
+ * above), the summed kernel milliseconds, the number of launches and the rows they
+ * processed since profiling was enabled; it waits for the recorded events. */
+int vk_agg_profile(VkAgg* agg, int enable);
+int vk_agg_profile_read(VkAgg* agg, int path, double* out_ms, int64_t* out_launches, int64_t* out_rows);
 
 /* --------------------------------------------------------- sort (a15-a16) -- */
 /* Replaces Sort::Sorted (vinum_cpp/src/operators/sort/sort.cpp:15-63):

@@ -1,0 +1,248 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol the header
+declares, the host-side logic (type tables, result assembly, scalar conversion,
+exchange planning) is right, and the multi-rank repartition plan works over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_functions():
+    text = (ROOT / "include" / "vinum_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from vinum_b200 import _lib
+    names = _declared_functions()
+    assert len(names) >= 50
+    raw = ctypes.CDLL(str(_lib.LIB_PATH))
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/vinum_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in vinum_b200/_lib.py"
+    assert set(_lib.SIGNATURES) <= set(names), set(_lib.SIGNATURES) - set(names)
+    assert raw.vk_abi_version() == 1
+
+
+def test_library_is_sm100a_only():
+    from vinum_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+
+
+def test_no_gpu_call_fails_loudly_not_silently():
+    """Without a device every compute entry point raises; nothing falls back to the CPU."""
+    import vinum_b200 as vb
+    try:
+        n = vb.device_count()
+    except vb.VinumB200Error:
+        n = 0
+    if n > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(vb.VinumB200Error):
+        vb.DeviceColumn.from_numpy(np.arange(10))
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "vinum_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "oracle" not in re.sub(r'"""(.|\n)*?"""', "", src), f"{p} references the oracle"
+    for p in (ROOT / "vinum_b200" / "csrc").glob("*"):
+        assert "oracle" not in p.read_text()
+
+
+def test_make_scalar():
+    from vinum_b200 import _lib as L
+    s = L.make_scalar(5)
+    assert s.dtype == L.I64 and s.v.i == 5
+    s = L.make_scalar(-(2**63))
+    assert s.dtype == L.I64 and s.v.i == -(2**63)
+    s = L.make_scalar(2**64 - 1)
+    assert s.dtype == L.U64 and s.v.u == 2**64 - 1
+    s = L.make_scalar(0.5)
+    assert s.dtype == L.F64 and s.v.f == 0.5
+    s = L.make_scalar(np.float32(0.25))
+    assert s.dtype == L.F64 and s.v.f == 0.25
+    with pytest.raises(OverflowError):
+        L.make_scalar(2**64)
+    with pytest.raises(TypeError):
+        L.make_scalar("x")
+
+
+def test_output_type_table_matches_reference_factory():
+    """SURVEY A.2 / agg_func_factory.cpp: the type of every aggregate output."""
+    from vinum_b200 import _lib as L
+    from vinum_b200.aggregate import check_supported, output_type
+    ints = [pa.int8(), pa.int16(), pa.int32(), pa.int64()]
+    uints = [pa.uint8(), pa.uint16(), pa.uint32(), pa.uint64()]
+    for t in ints + uints + [pa.float32(), pa.float64(), pa.timestamp("ms")]:
+        assert output_type(L.AGG_COUNT, t) == pa.uint64()
+        assert output_type(L.AGG_MIN, t) == t and output_type(L.AGG_MAX, t) == t
+    assert output_type(L.AGG_COUNT_STAR, None) == pa.uint64()
+    for t in ints:
+        assert output_type(L.AGG_SUM, t) == pa.int64()
+    for t in uints:
+        assert output_type(L.AGG_SUM, t) == pa.uint64()
+    assert output_type(L.AGG_SUM, pa.float32()) == pa.float64()
+    assert output_type(L.AGG_SUM, pa.time32("ms")) == pa.time32("ms")
+    for t in (pa.int8(), pa.int16(), pa.uint8(), pa.uint16()):
+        assert output_type(L.AGG_AVG, t) == pa.float32()
+    for t in (pa.int32(), pa.int64(), pa.uint32(), pa.uint64(), pa.float32(), pa.float64(), pa.time64("us")):
+        assert output_type(L.AGG_AVG, t) == pa.float64()
+    for t in (pa.bool_(), pa.date32(), pa.date64(), pa.timestamp("s")):
+        with pytest.raises(RuntimeError, match=r"not supported by sum\(\)"):
+            check_supported(L.AGG_SUM, t)
+        with pytest.raises(RuntimeError, match=r"not supported by avg\(\)"):
+            check_supported(L.AGG_AVG, t)
+
+
+def test_sum_int64_result_assembly_decimal_switch():
+    """128-bit (lo, hi) lanes -> int64 unless any group overflows -> whole column decimal128(38,0)."""
+    import decimal
+    from vinum_b200 import _lib as L
+    from vinum_b200.aggregate import _agg_array
+
+    def lanes(vals):
+        lo = np.array([v & (2**64 - 1) for v in vals], dtype=np.uint64)
+        hi = np.array([(v >> 64) & (2**64 - 1) for v in vals], dtype=np.uint64)
+        return lo, hi
+
+    valid = np.array([True, True, False])
+    lo, hi = lanes([5, -7, 0])
+    arr = _agg_array(L.AGG_SUM, pa.int64(), L.I64, lo, hi, valid)
+    assert arr.type == pa.int64() and arr.to_pylist() == [5, -7, None]
+    lo, hi = lanes([2**63, -7, 0])
+    arr = _agg_array(L.AGG_SUM, pa.int64(), L.I64, lo, hi, valid)
+    assert arr.type == pa.decimal128(38, 0)
+    assert arr.to_pylist() == [decimal.Decimal(2**63), decimal.Decimal(-7), None]
+    # -2^63 exactly fails the reference's int64 cast (huge_int.cpp:341-361)
+    lo, hi = lanes([-(2**63), 1, 0])
+    assert _agg_array(L.AGG_SUM, pa.int64(), L.I64, lo, hi, valid).type == pa.decimal128(38, 0)
+    lo, hi = lanes([2**64 - 1, 3, 0])
+    arr = _agg_array(L.AGG_SUM, pa.uint64(), L.U64, lo, hi, valid)
+    assert arr.type == pa.uint64() and arr.to_pylist() == [2**64 - 1, 3, None]
+    lo, hi = lanes([2**64, 3, 0])
+    assert _agg_array(L.AGG_SUM, pa.uint64(), L.U64, lo, hi, valid).type == pa.decimal128(38, 0)
+    # an overflowing lane in an INVALID group does not switch the column
+    lo, hi = lanes([1, 2, 2**70])
+    assert _agg_array(L.AGG_SUM, pa.int64(), L.I64, lo, hi, valid).type == pa.int64()
+
+
+def test_narrowing_and_temporal_result_arrays():
+    from vinum_b200 import _lib as L
+    from vinum_b200.aggregate import _agg_array, _key_array
+    valid = np.array([True, False])
+    lo = np.array([np.int64(-5).astype(np.uint64), 0], dtype=np.uint64)
+    arr = _agg_array(L.AGG_MIN, pa.int8(), L.I8, lo, np.zeros(2, np.uint64), valid)
+    assert arr.type == pa.int8() and arr.to_pylist() == [-5, None]
+    arr = _agg_array(L.AGG_MAX, pa.timestamp("ms"), L.I64, np.array([1611664420588, 0], np.uint64),
+                     np.zeros(2, np.uint64), valid)
+    assert arr.type == pa.timestamp("ms") and arr.cast(pa.int64()).to_pylist() == [1611664420588, None]
+    f = np.array([np.float64(1.5)]).view(np.uint64)
+    arr = _agg_array(L.AGG_AVG, pa.int8(), L.I8, f, np.zeros(1, np.uint64), np.array([True]))
+    assert arr.type == pa.float32() and arr.to_pylist() == [1.5]
+    k = _key_array(np.array([np.float32(0.5).view(np.uint32)], dtype=np.uint64), np.array([True]), pa.float32(), L.F32)
+    assert k.type == pa.float32() and k.to_pylist() == [0.5]
+
+
+def test_arith_result_dtype_follows_numpy():
+    from vinum_b200 import _lib as L
+    from vinum_b200.ops import result_dtype
+    from vinum_b200.device import DeviceColumn
+
+    def col(dt, nulls=False):
+        c = DeviceColumn(None, object() if nulls else None, 0, 4, dt, None, 1 if nulls else 0, data_ptr=0)
+        return c
+
+    assert result_dtype(L.ADD, col(L.I64), 3) == np.int64
+    assert result_dtype(L.ADD, col(L.I32), col(L.I8)) == np.int32
+    assert result_dtype(L.DIV, col(L.I64), col(L.I64)) == np.float64
+    assert result_dtype(L.MUL, col(L.F32), 0.1) == np.float32
+    assert result_dtype(L.MUL, col(L.I16), 2.5) == np.float64
+    assert result_dtype(L.ADD, col(L.I64, nulls=True), 1) == np.float64  # NULL -> NaN view
+    assert result_dtype(L.NEG, col(L.I8), None) == np.int8
+    assert result_dtype(L.ADD, col(L.U8), col(L.U32)) == np.uint32
+
+
+def test_shard_ranges_cover_rows_exactly():
+    from vinum_b200.dist import shard_range
+    for n in (0, 1, 7, 1000, 10**9 + 7):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+
+
+def test_exchange_plan():
+    from vinum_b200.dist import exchange_plan
+    counts = np.array([[1, 2, 3], [4, 0, 6], [7, 8, 9]])
+    so, ss, ro, rs = exchange_plan(counts)
+    assert so.tolist() == [[0, 1, 3], [0, 4, 4], [0, 7, 15]]
+    assert ss.tolist() == counts.tolist()
+    assert rs.tolist() == counts.T.tolist()
+    assert ro.tolist() == [[0, 1, 5], [0, 2, 2], [0, 3, 9]]
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from vinum_b200.dist import exchange_plan, all_to_all_records, shard_range
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+words = 3
+# rank r sends (r+1)*(d+1) records to rank d; record = [src, dst, seq]
+counts_local = torch.tensor([(rank + 1) * (d + 1) for d in range(world)], dtype=torch.int64)
+allc = [torch.empty_like(counts_local) for _ in range(world)]
+dist.all_gather(allc, counts_local)
+counts = torch.stack(allc).numpy()
+so, ss, ro, rs = exchange_plan(counts)
+recs = []
+for d in range(world):
+    for s in range(int(ss[rank][d])):
+        recs += [rank, d, s]
+send = torch.tensor(recs, dtype=torch.int64)
+recv = all_to_all_records(send, ss[rank], rs[rank], words).view(-1, words).numpy()
+assert recv.shape[0] == int(rs[rank].sum())
+assert (recv[:, 1] == rank).all()
+for src in range(world):
+    part = recv[int(ro[rank][src]): int(ro[rank][src]) + int(rs[rank][src])]
+    assert (part[:, 0] == src).all() and (part[:, 2] == np.arange(len(part))).all()
+lo, hi = shard_range(1001, rank, world)
+tot = torch.tensor([hi - lo]); dist.all_reduce(tot); assert int(tot) == 1001
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_partial_group_exchange_over_gloo_world2(tmp_path):
+    """The all-to-all-v of partial-aggregate records with 2 CPU ranks."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=str(ROOT), port=port))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

@@ -109,7 +109,7 @@ def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(
             f"{LIB_PATH} is missing: the vinum_b200 CUDA library has not been built. "
-            "Run `python -m vinum_b200.build` (needs nvcc); there is no CPU fallback."
+            "Run `python vinum_b200/build.py` (needs nvcc); there is no CPU fallback."
         )
     lib = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_LOCAL", 0) | getattr(os, "RTLD_NOW", 2))
     return lib
@@ -149,6 +149,7 @@ SIGNATURES = {
     "vk_event_destroy": (_int, [_p]),
     "vk_event_record": (_int, [_p, _p]),
     "vk_event_sync": (_int, [_p]),
+    "vk_stream_wait_event": (_int, [_p, _p]),
     "vk_event_elapsed_ms": (_int, [_p, _p, C.POINTER(C.c_float)]),
     "vk_launch_count": (_u64, []),
     "vk_datagen": (_int, [_int, _u64, _i64, _i64, _p, _p]),
@@ -174,6 +175,8 @@ SIGNATURES = {
     "vk_agg_export_partials": (_int, [_p, _int, _p, _p, _p]),
     "vk_agg_merge_partials": (_int, [_p, _p, _i64, _p]),
     "vk_agg_last_path": (_int, [_p]),
+    "vk_agg_profile": (_int, [_p, _int]),
+    "vk_agg_profile_read": (_int, [_p, _int, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "vk_sort_scratch_bytes": (_u64, [_i64]),
     "vk_sort_indices": (_int, [C.POINTER(VkColumn), C.POINTER(C.c_int32), _int, _i64, _p, _p, _p]),
     "vk_take": (_int, [C.POINTER(VkColumn), _p, _i64, _p, _p, _p]),
@@ -219,4 +222,4 @@ class _Checked:
 lib = _Checked(_lib)
 
 if _lib.vk_abi_version() != 1:
-    raise ImportError("libvinum_b200.so ABI version mismatch; rebuild with `python -m vinum_b200.build --force`")
+    raise ImportError("libvinum_b200.so ABI version mismatch; rebuild with `python vinum_b200/build.py --force`")

@@ -136,6 +136,16 @@ class Aggregator:
     def last_path(self) -> int:
         return int(L._lib.vk_agg_last_path(self._h))
 
+    def profile(self, enable: bool = True) -> None:
+        """Per-launch CUDA-event timing of the update kernels (no extra syncs)."""
+        lib.vk_agg_profile(self._h, int(enable))
+
+    def profile_read(self, path: int = 1):
+        """(kernel ms, launches, rows) of kernel path 1 (shared-memory) or 2 (global)."""
+        ms, ln, rows = C.c_double(), C.c_int64(), C.c_int64()
+        lib.vk_agg_profile_read(self._h, path, C.byref(ms), C.byref(ln), C.byref(rows))
+        return ms.value, ln.value, rows.value
+
     def num_groups(self, stream: Optional[Stream] = None) -> int:
         st = stream or default_stream()
         g = C.c_int64()

@@ -4,7 +4,7 @@ nvcc cross-compiles for sm_100a without a GPU.  The shared object is written nex
 to this file (vinum_b200/_C/libvinum_b200.so): it is git-ignored but travels to the
 GPU box with the repo snapshot.
 
-    python -m vinum_b200.build [--force] [--verbose]
+    python vinum_b200/build.py [--force] [--verbose]
 """
 from __future__ import annotations
 

@@ -684,6 +684,15 @@ struct VkAgg {
     int log2s = 11;
     bool fast_disabled = false;       // cardinality turned out too high for the shared-memory table
     uint64_t fast_rows = 0, fast_spilled = 0;
+    // optional per-launch timing of the update kernels (bench.py roofline): events are
+    // recorded on the launch stream and resolved lazily, so profiling adds no sync
+    bool profile = false;
+    struct ProfSpan { cudaEvent_t e0, e1; int64_t rows; int path; };
+    std::vector<ProfSpan> prof_pending;
+    std::vector<ProfSpan> prof_free;
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_launches[4] = {0, 0, 0, 0};
+    int64_t prof_rows[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -831,6 +840,38 @@ VkColumn slice_col(const VkColumn& c, int64_t off, int64_t len) {
     return r;
 }
 
+// profiling spans ----------------------------------------------------------------
+int prof_begin(VkAgg* a, cudaStream_t s, int64_t rows, int path) {
+    if (!a->profile) return -1;
+    VkAgg::ProfSpan sp;
+    if (!a->prof_free.empty()) {
+        sp = a->prof_free.back();
+        a->prof_free.pop_back();
+    } else {
+        if (cudaEventCreate(&sp.e0) != cudaSuccess || cudaEventCreate(&sp.e1) != cudaSuccess) return -1;
+    }
+    sp.rows = rows;
+    sp.path = path;
+    cudaEventRecord(sp.e0, s);
+    a->prof_pending.push_back(sp);
+    return (int) a->prof_pending.size() - 1;
+}
+void prof_end(VkAgg* a, cudaStream_t s, int idx) {
+    if (idx >= 0) cudaEventRecord(a->prof_pending[idx].e1, s);
+}
+void prof_resolve(VkAgg* a) {
+    for (auto& sp : a->prof_pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(sp.e1) == cudaSuccess && cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) {
+            a->prof_ms[sp.path] += ms;
+            a->prof_launches[sp.path] += 1;
+            a->prof_rows[sp.path] += sp.rows;
+        }
+        a->prof_free.push_back(sp);
+    }
+    a->prof_pending.clear();
+}
+
 bool aligned_for_pairs(const VkColumn& c) {
     const int es = dtype_size(c.dtype);
     uintptr_t addr = reinterpret_cast<uintptr_t>(c.data) + (uintptr_t) c.offset * es;
@@ -903,6 +944,8 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
 int vk_agg_destroy(VkAgg* a) {
     if (!a) return VK_OK;
     cudaDeviceSynchronize();
+    prof_resolve(a);
+    for (auto& sp : a->prof_free) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     if (a->table_ready) free_table(&a->t, 0);
     if (a->list) cudaFreeAsync(a->list, 0);
     if (a->d_ctr) cudaFree(a->d_ctr);
@@ -912,6 +955,20 @@ int vk_agg_destroy(VkAgg* a) {
 }
 
 int vk_agg_last_path(VkAgg* a) { return a ? a->last_path : 0; }
+
+int vk_agg_profile(VkAgg* a, int enable) {
+    VK_REQUIRE(a, "vk_agg_profile: agg is NULL");
+    a->profile = enable != 0;
+    return VK_OK;
+}
+int vk_agg_profile_read(VkAgg* a, int path, double* out_ms, int64_t* out_launches, int64_t* out_rows) {
+    VK_REQUIRE(a && path >= 1 && path <= 3, "vk_agg_profile_read: bad argument");
+    prof_resolve(a);
+    if (out_ms) *out_ms = a->prof_ms[path];
+    if (out_launches) *out_launches = a->prof_launches[path];
+    if (out_rows) *out_rows = a->prof_rows[path];
+    return VK_OK;
+}
 
 static int run_replay_until_empty(VkAgg* a, GenParams gp, int64_t chunk_rows, cudaStream_t s) {
     // Precondition: counters read back in a->h_ctr after the chunk's kernel.
@@ -1141,13 +1198,17 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             fp.table = a->t;
             fp.replay = gp.replay;
             int grid = fp.num_tiles < fast_grid_max ? (int) fp.num_tiles : fast_grid_max;
+            const int span = prof_begin(a, s, chunk, 1);
             rc = launch_fast(fp, pk, strat, grid, smem, s);
+            prof_end(a, s, span);
             if (rc != VK_OK) return rc;
             a->groups_ub += chunk;
         } else {
             a->last_path = 2;
             int64_t need = (chunk + 255) / 256, capb = (int64_t) sms * 8;
+            const int span = prof_begin(a, s, chunk, 2);
             agg_general_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(gp);
+            prof_end(a, s, span);
             VK_CHECK_LAUNCH("agg_general_kernel");
             a->groups_ub += chunk;
         }

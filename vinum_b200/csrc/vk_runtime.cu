@@ -231,6 +231,10 @@ int vk_event_sync(VkEvent event) {
     VK_CUDA(cudaEventSynchronize((cudaEvent_t) event));
     return VK_OK;
 }
+int vk_stream_wait_event(VkStream stream, VkEvent event) {
+    VK_CUDA(cudaStreamWaitEvent((cudaStream_t) stream, (cudaEvent_t) event, 0));
+    return VK_OK;
+}
 int vk_event_elapsed_ms(VkEvent start, VkEvent stop, float* out_ms) {
     VK_REQUIRE(out_ms, "vk_event_elapsed_ms: out_ms is NULL");
     VK_CUDA(cudaEventElapsedTime(out_ms, (cudaEvent_t) start, (cudaEvent_t) stop));

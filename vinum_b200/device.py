@@ -81,7 +81,7 @@ class Stream:
         return C.c_void_p(self.handle)
 
     def __del__(self):
-        if getattr(self, "_owned", False) and self.handle:
+        if getattr(self, "_owned", False) and getattr(self, "handle", 0):
             try:
                 L._lib.vk_stream_destroy(C.c_void_p(self.handle))
             except Exception:
