@@ -21,6 +21,10 @@ lib = vb.lib
 OUT = {}
 
 
+def mark(msg):
+    print('#', msg, flush=True)
+
+
 def timed(fn, st, reps=5, warm=2):
     e0, e1 = C.c_void_p(), C.c_void_p()
     lib.vk_event_create(C.byref(e0)); lib.vk_event_create(C.byref(e1))
@@ -76,18 +80,22 @@ def s_filter():
     names = ["i1", "i2", "f0", "f1"]
     batch = datagen.device_table(names, 0, n, stream=st)
     host = {k: datagen.host_column(k, 0, n) for k in names}
+    mark("filter small cmp")
     out = ops.filter_batch(batch, ops.Predicate.compare(batch.column("f0"), ">", 0.5), st)
+    mark("filter small done")
     m = host["f0"] > 0.5
     ok = out.num_rows == int(m.sum())
     for k in names:
         ok = ok and np.array_equal(out.column(k).to_numpy(st), host[k][m])
     res["cmp_parity"] = bool(ok)
+    mark("compare")
     mask = ops.compare(batch.column("f0"), ">", 0.5, st)
     res["mask_parity"] = bool(np.array_equal(mask.to_numpy(st).astype(bool), m))
     out2 = ops.filter_batch(batch, ops.Predicate.from_mask(mask), st)
     res["mask_filter_parity"] = bool(out2.num_rows == int(m.sum()) and
                                      np.array_equal(out2.column("i2").to_numpy(st), host["i2"][m]))
     # timing at C2 size
+    mark("filter c2")
     n = 100_000_000
     batch = datagen.device_table(names, 0, n, stream=st)
     vp = ops.Predicate.compare(batch.column("f0"), ">", 0.5).vk()
@@ -170,6 +178,7 @@ def s_agg_parity():
         uk, cnt, sm = np_groupby(h[keyname], h["f1"], m)
         for strat in (0, 1, 2):
             for log2s in (11,) if keyname != "i3" else (11,):
+                mark(f"agg parity {keyname} strat {strat}")
                 k, c, s, path, ms = run_agg(cols.column(keyname), cols.column("f1"), cols.column("f0"), n, st, strat, log2s, reps=1)
                 kk = k.view(np.int64)
                 order = np.argsort(kk)
@@ -178,6 +187,7 @@ def s_agg_parity():
                       np.allclose(s[order], sm, rtol=1e-9, atol=1e-6))
                 res[f"{keyname}_s{strat}"] = {"ok": bool(ok), "groups": int(len(kk)), "path": path, "ms": ms}
     # no predicate, general path via nulls-free int64 key but MIN/MAX funcs
+    mark("agg general")
     agg = Aggregator([pa.int64()], [(L.AGG_COUNT_STAR, None), (L.AGG_MIN, pa.float64()), (L.AGG_MAX, pa.int64()),
                                     (L.AGG_SUM, pa.int64()), (L.AGG_AVG, pa.int64())])
     agg.update([cols.column("i0")], [None, cols.column("f1"), cols.column("i3"), cols.column("i3"), cols.column("i3")], None, st)
@@ -262,7 +272,9 @@ def s_sort():
     i0 = datagen.device_column("i0", 0, n, stream=st)
     hf3 = datagen.host_column("f3", 0, n)
     hi0 = datagen.host_column("i0", 0, n)
+    mark("sort f3 desc")
     idx = ops.sort_indices([f3], [L.DESC], st).to_numpy(st)
+    mark("sort f3 done")
     ref = np.argsort(-hf3, kind="stable")
     res["f3_desc"] = bool(np.array_equal(idx, ref))
     idx = ops.sort_indices([i0], [L.ASC], st).to_numpy(st)
