@@ -215,7 +215,7 @@ def s_agg_highcard():
     st = vb.default_stream()
     res = {}
     os.environ["VINUM_B200_AGG_STRATEGY"] = "0"
-    n = 20_000_000
+    n = int(os.environ.get("VK_HC_ROWS", 20_000_000))
     cols = datagen.device_table(["i1", "f1", "f0"], 0, n, stream=st)
     h = {k: datagen.host_column(k, 0, n) for k in ["i1", "f1", "f0"]}
     # ~n distinct keys: exercises replay list + table growth

@@ -19,6 +19,7 @@
 // appended to a replay list; the host grows the table and replays them, so an update
 // never loses rows whatever the cardinality turns out to be.
 #include "vk_hashagg.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -496,15 +497,18 @@ __device__ __forceinline__ double hugeint_to_double(__int128 v) {
 __global__ void __launch_bounds__(256) agg_finalize_kernel(const __grid_constant__ FinalParams p) {
     const GTable& t = p.table;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
-        if (t.state[s] != 2) continue;
-        const uint32_t nullmask = t.n_keys ? t.knull[s] : 0;
+    const int64_t slots = gt_total_slots(t);
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
+        if (!gt_slot_occupied(t, s)) continue;
+        uint64_t kv[VK_AGG_MAX_KEYS];
+        uint32_t nullmask;
+        gt_slot_key(t, s, kv, &nullmask);
         int64_t row;
         if (p.null_last && nullmask) row = p.num_groups - 1;
         else row = (int64_t) atomicAdd(p.cursor, 1ULL);
         if (row >= p.num_groups) continue;  // defensive
         for (int k = 0; k < t.n_keys; ++k) {
-            p.out_keys[k][row] = t.keys[(int64_t) k * t.capacity + s];
+            p.out_keys[k][row] = kv[k];
             p.out_key_valid[k][row] = !((nullmask >> k) & 1);
         }
         const uint64_t rows = t.count_star[s];
@@ -559,11 +563,12 @@ __global__ void __launch_bounds__(256) agg_rehash_kernel(const __grid_constant__
     const GTable& a = p.src;
     const GTable& b = p.dst;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < a.capacity; s += stride) {
-        if (a.state[s] != 2) continue;
+    const int64_t slots = gt_total_slots(a);
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
+        if (!gt_slot_occupied(a, s)) continue;
         uint64_t kv[VK_AGG_MAX_KEYS];
-        const uint32_t nullmask = a.n_keys ? a.knull[s] : 0;
-        for (int k = 0; k < a.n_keys; ++k) kv[k] = a.keys[(int64_t) k * a.capacity + s];
+        uint32_t nullmask;
+        gt_slot_key(a, s, kv, &nullmask);
         int64_t d = gt_find_or_insert<0>(b, kv, nullmask, hash_keys(kv, nullmask, a.n_keys), b.max_groups);
         if (d < 0) continue;  // cannot happen: dst is larger
         b.count_star[d] = a.count_star[s];
@@ -595,22 +600,24 @@ __device__ __forceinline__ int dest_rank(uint64_t hash, int n_ranks) { return (i
 __global__ void __launch_bounds__(256) agg_partition_count_kernel(const __grid_constant__ ExchParams p) {
     const GTable& t = p.table;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
-        if (t.state[s] != 2) continue;
+    const int64_t slots = gt_total_slots(t);
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
+        if (!gt_slot_occupied(t, s)) continue;
         uint64_t kv[VK_AGG_MAX_KEYS];
-        const uint32_t nullmask = t.n_keys ? t.knull[s] : 0;
-        for (int k = 0; k < t.n_keys; ++k) kv[k] = t.keys[(int64_t) k * t.capacity + s];
+        uint32_t nullmask;
+        gt_slot_key(t, s, kv, &nullmask);
         atomicAdd(reinterpret_cast<unsigned long long*>(p.counts) + dest_rank(hash_keys(kv, nullmask, t.n_keys), p.n_ranks), 1ULL);
     }
 }
 __global__ void __launch_bounds__(256) agg_export_kernel(const __grid_constant__ ExchParams p) {
     const GTable& t = p.table;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
-        if (t.state[s] != 2) continue;
+    const int64_t slots = gt_total_slots(t);
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
+        if (!gt_slot_occupied(t, s)) continue;
         uint64_t kv[VK_AGG_MAX_KEYS];
-        const uint32_t nullmask = t.n_keys ? t.knull[s] : 0;
-        for (int k = 0; k < t.n_keys; ++k) kv[k] = t.keys[(int64_t) k * t.capacity + s];
+        uint32_t nullmask;
+        gt_slot_key(t, s, kv, &nullmask);
         int d = dest_rank(hash_keys(kv, nullmask, t.n_keys), p.n_ranks);
         int64_t rec = p.offsets[d] + (int64_t) atomicAdd(p.cursors + d, 1ULL);
         uint64_t* o = p.out + rec * p.words;
@@ -697,6 +704,13 @@ struct VkAgg {
 
 namespace {
 
+bool debug_on() {
+    static int v = -1;
+    if (v < 0) v = getenv("VINUM_B200_DEBUG") ? 1 : 0;
+    return v == 1;
+}
+#define VK_DBG(...) do { if (debug_on()) { fprintf(stderr, "[vk_agg] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
+
 constexpr double kMaxLoad = 0.5;
 constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_WORDS = 16;
 
@@ -712,27 +726,36 @@ int alloc_table(VkAgg* a, GTable* t, int64_t capacity, cudaStream_t s) {
     t->max_groups = (int64_t) (capacity * kMaxLoad);
     t->n_keys = a->n_keys;
     t->n_funcs = a->n_funcs;
+    t->single = a->n_keys == 1;
     t->num_groups = a->d_ctr + CTR_GROUPS;
+    const int64_t slots = capacity + (t->single ? 2 : 0);
     auto zalloc = [&](void** p, size_t bytes) -> int {
         VK_CUDA(cudaMallocAsync(p, bytes, s));
         VK_CUDA(cudaMemsetAsync(*p, 0, bytes, s));
         return VK_OK;
     };
     int rc;
-    if ((rc = zalloc((void**) &t->state, capacity * sizeof(uint32_t)))) return rc;
-    if (a->n_keys) {
-        if ((rc = zalloc((void**) &t->keys, (size_t) a->n_keys * capacity * sizeof(uint64_t)))) return rc;
-        if ((rc = zalloc((void**) &t->knull, capacity * sizeof(uint32_t)))) return rc;
+    if (t->single) {
+        // key array doubles as the slot tag: all-ones == free
+        if ((rc = zalloc((void**) &t->state, 2 * sizeof(uint32_t)))) return rc;
+        VK_CUDA(cudaMallocAsync((void**) &t->keys, (size_t) slots * sizeof(uint64_t), s));
+        VK_CUDA(cudaMemsetAsync(t->keys, 0xFF, (size_t) slots * sizeof(uint64_t), s));
+    } else {
+        if ((rc = zalloc((void**) &t->state, capacity * sizeof(uint32_t)))) return rc;
+        if (a->n_keys) {
+            if ((rc = zalloc((void**) &t->keys, (size_t) a->n_keys * capacity * sizeof(uint64_t)))) return rc;
+            if ((rc = zalloc((void**) &t->knull, capacity * sizeof(uint32_t)))) return rc;
+        }
     }
-    if ((rc = zalloc((void**) &t->count_star, capacity * sizeof(uint64_t)))) return rc;
+    if ((rc = zalloc((void**) &t->count_star, slots * sizeof(uint64_t)))) return rc;
     for (int f = 0; f < a->n_funcs; ++f) {
         int acc = a->specs[f].acc;
         if (acc >= ACC_SUM_F64)
-            if ((rc = zalloc((void**) &t->acc_lo[f], capacity * sizeof(uint64_t)))) return rc;
+            if ((rc = zalloc((void**) &t->acc_lo[f], slots * sizeof(uint64_t)))) return rc;
         if (acc == ACC_SUM_I128)
-            if ((rc = zalloc((void**) &t->acc_hi[f], capacity * sizeof(uint64_t)))) return rc;
+            if ((rc = zalloc((void**) &t->acc_hi[f], slots * sizeof(uint64_t)))) return rc;
         if (acc != ACC_NONE)
-            if ((rc = zalloc((void**) &t->nnull[f], capacity * sizeof(uint64_t)))) return rc;
+            if ((rc = zalloc((void**) &t->nnull[f], slots * sizeof(uint64_t)))) return rc;
     }
     return VK_OK;
 }
@@ -767,7 +790,7 @@ int grow_table(VkAgg* a, int64_t groups_now, int64_t need_free, cudaStream_t s) 
     if (rc != VK_OK) return rc;
     VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_GROUPS, 0, sizeof(unsigned long long), s));
     RehashParams rp{a->t, nt};
-    int64_t need = (a->t.capacity + 255) / 256, capb = (int64_t) sm_count() * 8;
+    int64_t need = (gt_total_slots(a->t) + 255) / 256, capb = (int64_t) sm_count() * 8;
     agg_rehash_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(rp);
     VK_CHECK_LAUNCH("agg_rehash_kernel");
     free_table(&a->t, s);
@@ -978,6 +1001,8 @@ static int run_replay_until_empty(VkAgg* a, GenParams gp, int64_t chunk_rows, cu
         const int64_t groups = (int64_t) a->h_ctr[CTR_GROUPS];
         const int64_t pending = (int64_t) a->h_ctr[CTR_LIST];
         a->groups_ub = groups;
+        VK_DBG("replay: groups=%lld pending=%lld capacity=%lld", (long long) groups, (long long) pending,
+               (long long) a->t.capacity);
         if (pending == 0) return VK_OK;
         // grow so that every pending row can become a new group, then replay the list
         int rc = grow_table(a, groups, pending + 1024, s);
@@ -1159,6 +1184,9 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         if (chunk < remaining) chunk &= ~(int64_t) (FA_TILE - 1);            // keep chunk starts pair-aligned
         if (chunk <= 0) return fail(VK_ERR_STATE, "vk_agg_update: internal error: empty chunk");
         VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_LIST, 0, 3 * sizeof(unsigned long long), s));  // list, lost, spilled
+        VK_DBG("chunk pos=%lld rows=%lld fast=%d may_fail=%d free_slots=%lld capacity=%lld groups_ub=%lld list_cap=%llu",
+               (long long) pos, (long long) chunk, (int) fast, (int) may_fail, (long long) free_slots,
+               (long long) a->t.capacity, (long long) a->groups_ub, (unsigned long long) a->list_cap);
 
         VkPredicate cpred = *pred;
         if (cpred.kind == VK_PRED_MASK) cpred.mask += pos;
@@ -1283,7 +1311,7 @@ int vk_agg_result(VkAgg* a, int64_t num_groups, uint64_t* const* out_keys, uint8
         fp.out_hi[f] = out_vals_hi ? out_vals_hi[f] : nullptr;
         fp.out_valid[f] = out_vals_valid[f];
     }
-    int64_t need = (a->t.capacity + 255) / 256, capb = (int64_t) sm_count() * 8;
+    int64_t need = (gt_total_slots(a->t) + 255) / 256, capb = (int64_t) sm_count() * 8;
     agg_finalize_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(fp);
     VK_CHECK_LAUNCH("agg_finalize_kernel");
     return VK_OK;
@@ -1312,7 +1340,7 @@ int vk_agg_partition_counts(VkAgg* a, int n_ranks, int64_t* out_counts_dev, VkSt
     exch_params(a, &p);
     p.n_ranks = n_ranks;
     p.counts = reinterpret_cast<long long*>(out_counts_dev);
-    int64_t need = (a->t.capacity + 255) / 256, capb = (int64_t) sm_count() * 8;
+    int64_t need = (gt_total_slots(a->t) + 255) / 256, capb = (int64_t) sm_count() * 8;
     agg_partition_count_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(p);
     VK_CHECK_LAUNCH("agg_partition_count_kernel");
     return VK_OK;
@@ -1332,7 +1360,7 @@ int vk_agg_export_partials(VkAgg* a, int n_ranks, const int64_t* offsets_dev, ui
     VK_CUDA(cudaMallocAsync((void**) &cursors, sizeof(unsigned long long) * n_ranks, s));
     VK_CUDA(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * n_ranks, s));
     p.cursors = cursors;
-    int64_t need = (a->t.capacity + 255) / 256, capb = (int64_t) sm_count() * 8;
+    int64_t need = (gt_total_slots(a->t) + 255) / 256, capb = (int64_t) sm_count() * 8;
     agg_export_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(p);
     VK_CHECK_LAUNCH("agg_export_kernel");
     VK_CUDA(cudaFreeAsync(cursors, s));

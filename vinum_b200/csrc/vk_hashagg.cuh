@@ -34,20 +34,37 @@ struct FuncSpec {
 };
 
 // Global (HBM/L2-resident) open-addressing table, structure-of-arrays.
+//
+// Two slot protocols:
+//  * single-key tables (`single` = 1, the SingleNumericalHashAggregate case): the 64-bit
+//    normalised key IS the slot tag.  A slot is claimed AND published by one 64-bit CAS
+//    from GT_EMPTY to the key, so lookups never wait on another thread (wait-free
+//    readers, lock-free inserts).  The key value GT_EMPTY itself and the NULL key live in
+//    two dedicated slots behind the table (indices capacity and capacity+1), flagged in
+//    `state[0..1]`.
+//  * multi-key tables: a per-slot state word (0 empty, 1 being written, 2 ready) guards
+//    the key tuple; a reader that meets a slot in state 1 backs off with __nanosleep so
+//    the writer (possibly a lane of the same warp) is scheduled.
+constexpr uint64_t GT_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
+
 struct GTable {
-    int64_t capacity;      // power of two
+    int64_t capacity;      // power of two (hashed slots)
     int64_t max_groups;    // insertion limit (load factor bound)
     int32_t n_keys;
     int32_t n_funcs;
-    uint32_t* state;       // 0 empty, 1 being written, 2 ready
-    uint64_t* keys;        // [n_keys][capacity] normalised key values
-    uint32_t* knull;       // [capacity] bit k set when key k is NULL
-    uint64_t* count_star;  // [capacity]
+    int32_t single;        // 1: single-key protocol
+    int32_t _pad;
+    uint32_t* state;       // multi: [capacity] slot states; single: [2] flags of the special slots
+    uint64_t* keys;        // multi: [n_keys][capacity]; single: [capacity + 2], GT_EMPTY = free
+    uint32_t* knull;       // multi: [capacity] bit k set when key k is NULL; single: unused
+    uint64_t* count_star;  // [slots]
     uint64_t* acc_lo[VK_AGG_MAX_FUNCS];
     uint64_t* acc_hi[VK_AGG_MAX_FUNCS];  // only for SUM_I128
-    uint64_t* nnull[VK_AGG_MAX_FUNCS];   // NULL inputs seen per group (allocated on demand)
+    uint64_t* nnull[VK_AGG_MAX_FUNCS];   // NULL inputs seen per group
     unsigned long long* num_groups;      // device counter
 };
+
+__host__ __device__ __forceinline__ int64_t gt_total_slots(const GTable& t) { return t.capacity + (t.single ? 2 : 0); }
 
 __device__ __forceinline__ uint64_t hash_keys(const uint64_t* kv, uint32_t nullmask, int n_keys) {
     uint64_t h = 0x243F6A8885A308D3ULL ^ nullmask;
@@ -64,17 +81,75 @@ __device__ __forceinline__ uint32_t ld_state(const uint32_t* p) {
 __device__ __forceinline__ void st_state_release(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint64_t ld_key_relaxed(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Occupancy / key of slot s (finalize, rehash, export walk every slot).
+__device__ __forceinline__ bool gt_slot_occupied(const GTable& t, int64_t s) {
+    if (!t.single) return t.state[s] == 2;
+    if (s < t.capacity) return t.keys[s] != GT_EMPTY;
+    return t.state[s - t.capacity] != 0;
+}
+__device__ __forceinline__ void gt_slot_key(const GTable& t, int64_t s, uint64_t* kv, uint32_t* nullmask) {
+    if (!t.single) {
+        *nullmask = t.n_keys ? t.knull[s] : 0;
+        for (int k = 0; k < t.n_keys; ++k) kv[k] = t.keys[(int64_t) k * t.capacity + s];
+    } else if (s < t.capacity) {
+        kv[0] = t.keys[s];
+        *nullmask = 0;
+    } else if (s == t.capacity) {
+        kv[0] = GT_EMPTY;
+        *nullmask = 0;
+    } else {
+        kv[0] = 0;
+        *nullmask = 1;
+    }
+}
+
+// Single-key protocol.  Returns the slot, or -1 when the table holds `limit` groups.
+__device__ __forceinline__ int64_t gt1_find_or_insert(const GTable& t, uint64_t key, bool is_null, uint64_t hash,
+                                                      int64_t limit) {
+    if (is_null || key == GT_EMPTY) {
+        const int which = is_null ? 1 : 0;
+        if (ld_state(t.state + which) == 0u) {
+            if (*reinterpret_cast<volatile unsigned long long*>(t.num_groups) >= (unsigned long long) limit) return -1;
+            if (atomicCAS(t.state + which, 0u, 2u) == 0u) atomicAdd(t.num_groups, 1ULL);
+        }
+        return t.capacity + which;
+    }
+    const uint64_t mask = (uint64_t) t.capacity - 1;
+    uint64_t slot = hash & mask;
+    for (int64_t probes = 0; probes < t.capacity; ++probes) {
+        uint64_t k = ld_key_relaxed(t.keys + slot);
+        if (k == key) return (int64_t) slot;
+        if (k == GT_EMPTY) {
+            if (*reinterpret_cast<volatile unsigned long long*>(t.num_groups) >= (unsigned long long) limit) return -1;
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(t.keys + slot),
+                                               (unsigned long long) GT_EMPTY, (unsigned long long) key);
+            if (old == GT_EMPTY) {
+                atomicAdd(t.num_groups, 1ULL);
+                return (int64_t) slot;
+            }
+            if (old == key) return (int64_t) slot;
+        }
+        slot = (slot + 1) & mask;
+    }
+    return -1;
+}
 
 // Find the slot of (kv, nullmask) or claim a new one.  Returns -1 when the table has
 // reached `limit` groups (the caller records the row for replay after a grow).
-// Every loop iteration is self-contained (claim + publish happen in one iteration), so
-// lanes of one warp spinning on each other's slots cannot deadlock.
 template <int NK>
 __device__ __forceinline__ int64_t gt_find_or_insert(const GTable& t, const uint64_t* kv, uint32_t nullmask,
                                                      uint64_t hash, int64_t limit) {
-    const int n_keys = NK > 0 ? NK : t.n_keys;
+    if (NK == 1 || t.single) return gt1_find_or_insert(t, kv[0], nullmask & 1u, hash, limit);
+    const int n_keys = t.n_keys;
     const uint64_t mask = (uint64_t) t.capacity - 1;
     uint64_t slot = hash & mask;
+    unsigned backoff = 8;
     for (int64_t probes = 0; probes < t.capacity;) {
         uint32_t s = ld_state(t.state + slot);
         if (s == 2) {
@@ -94,8 +169,12 @@ __device__ __forceinline__ int64_t gt_find_or_insert(const GTable& t, const uint
                 atomicAdd(t.num_groups, 1ULL);
                 return (int64_t) slot;
             }
+        } else {
+            // being written by another thread: yield so that the writer (possibly a lane of
+            // this warp) runs, then re-read the same slot
+            __nanosleep(backoff);
+            if (backoff < 256) backoff <<= 1;
         }
-        // s == 1 (or lost the claim): re-read the same slot
     }
     return -1;
 }
