@@ -31,6 +31,15 @@ def canonical(batch, key_cols):
     # subset of the group-by columns (planner.py:452-469), so they need not be unique
     extra = [f.name for f in batch.schema if f.name not in key_cols and not pa.types.is_floating(f.type)
              and not pa.types.is_decimal(f.type)]
+    # last resort: NULL-ness of the floating columns (their values may differ in the last bits)
+    float_cols = [f.name for f in batch.schema if f.name not in key_cols and pa.types.is_floating(f.type)]
+    for name in float_cols:
+        col = batch.column(name).combine_chunks()
+        sort_keys_tail = ~np.asarray(col.is_valid().to_numpy(zero_copy_only=False), dtype=bool)
+        sort_keys.append(sort_keys_tail)
+    sort_keys = sort_keys[::-1]  # lowest priority first; the loop below appends higher-priority keys
+    tail = list(sort_keys)
+    sort_keys = []
     for name in list(key_cols) + extra:
         col = batch.column(name).combine_chunks()
         valid = np.asarray(col.is_valid().to_numpy(zero_copy_only=False), dtype=bool)
@@ -47,6 +56,7 @@ def canonical(batch, key_cols):
             code = v.astype(np.int64).view(np.uint64) ^ np.uint64(1 << 63) if v.dtype.kind == "i" else v.astype(np.uint64)
         sort_keys.append(code)
         sort_keys.append(~valid)
+    sort_keys = sort_keys + tail[::-1]
     order = np.lexsort(tuple(reversed(sort_keys))) if n else np.empty(0, dtype=np.int64)
     return batch.take(pa.array(order, type=pa.int64()))
 
