@@ -125,6 +125,9 @@ def s_filter():
     return res
 
 
+CFGS = [(1, 0), (0, 0), (1, 4), (0, 4)]
+
+
 def np_groupby(keys, vals, mask):
     k = keys[mask]
     v = vals[mask]
@@ -134,9 +137,14 @@ def np_groupby(keys, vals, mask):
     return uk, cnt, sm
 
 
-def run_agg(keycol, valcol, predcol, n, st, strategy, log2s, reps=3):
-    os.environ["VINUM_B200_AGG_STRATEGY"] = str(strategy)
-    os.environ["VINUM_B200_AGG_LOG2S"] = str(log2s)
+def run_agg(keycol, valcol, predcol, n, st, cfg, reps=3):
+    """cfg = (direct policy, warps or 0) -> env knobs read by vk_agg_create."""
+    direct, warps = cfg
+    os.environ["VINUM_B200_AGG_DIRECT"] = str(direct)
+    if warps:
+        os.environ["VINUM_B200_AGG_WARPS"] = str(warps)
+    else:
+        os.environ.pop("VINUM_B200_AGG_WARPS", None)
     pred = ops.Predicate.compare(predcol, ">", 0.5) if predcol is not None else None
 
     def once():
@@ -176,16 +184,17 @@ def s_agg_parity():
     m = h["f0"] > 0.5
     for keyname in ["i0", "k32", "i3"]:
         uk, cnt, sm = np_groupby(h[keyname], h["f1"], m)
-        for strat in (0, 1, 2):
-            for log2s in (11,) if keyname != "i3" else (11,):
-                mark(f"agg parity {keyname} strat {strat}")
-                k, c, s, path, ms = run_agg(cols.column(keyname), cols.column("f1"), cols.column("f0"), n, st, strat, log2s, reps=1)
+        for cfg in CFGS:
+            for _once in (0,):
+                strat = "d%d_w%d" % cfg
+                mark(f"agg parity {keyname} cfg {strat}")
+                k, c, s, path, ms = run_agg(cols.column(keyname), cols.column("f1"), cols.column("f0"), n, st, cfg, reps=1)
                 kk = k.view(np.int64)
                 order = np.argsort(kk)
                 ok = (len(kk) == len(uk) and np.array_equal(kk[order], uk.astype(np.int64)) and
                       np.array_equal(c[order], cnt.astype(np.uint64)) and
                       np.allclose(s[order], sm, rtol=1e-9, atol=1e-6))
-                res[f"{keyname}_s{strat}"] = {"ok": bool(ok), "groups": int(len(kk)), "path": path, "ms": ms}
+                res[f"{keyname}_{strat}"] = {"ok": bool(ok), "groups": int(len(kk)), "path": path, "ms": ms}
     # no predicate, general path via nulls-free int64 key but MIN/MAX funcs
     mark("agg general")
     agg = Aggregator([pa.int64()], [(L.AGG_COUNT_STAR, None), (L.AGG_MIN, pa.float64()), (L.AGG_MAX, pa.int64()),
@@ -214,7 +223,6 @@ def s_agg_parity():
 def s_agg_highcard():
     st = vb.default_stream()
     res = {}
-    os.environ["VINUM_B200_AGG_STRATEGY"] = "0"
     n = int(os.environ.get("VK_HC_ROWS", 20_000_000))
     cols = datagen.device_table(["i1", "f1", "f0"], 0, n, stream=st)
     h = {k: datagen.host_column(k, 0, n) for k in ["i1", "f1", "f0"]}
@@ -246,20 +254,20 @@ def s_agg_bench():
     cols = datagen.device_table(["i0", "f0", "f1"], 0, n, stream=st)
     k32 = datagen.device_column("k32", 0, n, stream=st)
     st.sync()
-    for strat in (0, 1, 2):
-        for log2s in (10, 11, 12):
-            if strat == 2 and log2s != 11:
-                continue
-            try:
-                k, c, s, path, ms = run_agg(cols.column("i0"), cols.column("f1"), cols.column("f0"), n, st, strat, log2s)
-                res[f"northstar_s{strat}_l{log2s}"] = {"ms": ms, "GBps": n * 24 / ms / 1e6, "Grows": n / ms / 1e6,
-                                                      "groups": int(len(k)), "path": path, "cnt": int(c.sum())}
-                print(json.dumps({f"northstar_s{strat}_l{log2s}": res[f"northstar_s{strat}_l{log2s}"]}), flush=True)
-            except Exception as e:  # noqa: BLE001
-                res[f"northstar_s{strat}_l{log2s}"] = {"error": repr(e)}
-    for strat in (0, 1):
-        k, c, s, path, ms = run_agg(k32, cols.column("f1"), None, n, st, strat, 11)
-        res[f"c3_s{strat}"] = {"ms": ms, "GBps": n * 12 / ms / 1e6, "Grows": n / ms / 1e6, "groups": int(len(k)), "path": path}
+    for cfg in CFGS:
+        name = "northstar_d%d_w%d" % cfg
+        try:
+            k, c, s, path, ms = run_agg(cols.column("i0"), cols.column("f1"), cols.column("f0"), n, st, cfg)
+            res[name] = {"ms": ms, "GBps": n * 24 / ms / 1e6, "Grows": n / ms / 1e6,
+                         "groups": int(len(k)), "path": path, "cnt": int(c.sum())}
+        except Exception as e:  # noqa: BLE001
+            res[name] = {"error": repr(e)}
+        print(json.dumps({name: res[name]}), flush=True)
+    for cfg in CFGS:
+        name = "c3_d%d_w%d" % cfg
+        k, c, s, path, ms = run_agg(k32, cols.column("f1"), None, n, st, cfg)
+        res[name] = {"ms": ms, "GBps": n * 12 / ms / 1e6, "Grows": n / ms / 1e6, "groups": int(len(k)), "path": path}
+        print(json.dumps({name: res[name]}), flush=True)
     return res
 
 

@@ -1,9 +1,8 @@
-"""Tiny driver for ncu: one fused filter->aggregate update. usage: prof_agg.py STRATEGY LOG2S [ROWS]"""
+"""Tiny driver for ncu: one fused filter->aggregate update. usage: prof_agg.py DIRECT [N_ROWS]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["VINUM_B200_AGG_STRATEGY"] = sys.argv[1]
-os.environ["VINUM_B200_AGG_LOG2S"] = sys.argv[2]
-n = int(sys.argv[3]) if len(sys.argv) > 3 else 200_000_000
+os.environ["VINUM_B200_AGG_DIRECT"] = sys.argv[1]
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 200_000_000
 import pyarrow as pa
 import vinum_b200 as vb
 from vinum_b200 import _lib as L, datagen, ops

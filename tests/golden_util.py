@@ -20,44 +20,47 @@ def manifest():
 
 def canonical(batch, key_cols):
     """Group-by output order is unspecified: sort rows by the key columns
-    (NULLs last, NaN before NULL, -0.0 distinguished from 0.0 through its bits)."""
+    (NULLs last, NaN before NULL, -0.0 distinguished from 0.0 through its bits).
+
+    The emitted key columns may be a strict subset of the group-by columns
+    (planner.py:452-469), so they need not be unique: ties are broken by every exact
+    (non-floating) column, then by the NULL-ness and finally the value of the floating
+    aggregate columns (two rows whose floats are that close compare equal within the
+    tolerance whichever way they are ordered)."""
     if isinstance(batch, pa.RecordBatch):
         batch = pa.Table.from_batches([batch])
     if batch.num_rows == 0 or not key_cols:
         return batch
-    n = batch.num_rows
-    sort_keys = []
-    # tie-break on every exact (non-floating) column: the emitted key columns may be a strict
-    # subset of the group-by columns (planner.py:452-469), so they need not be unique
-    extra = [f.name for f in batch.schema if f.name not in key_cols and not pa.types.is_floating(f.type)
+    exact = [f.name for f in batch.schema if f.name not in key_cols and not pa.types.is_floating(f.type)
              and not pa.types.is_decimal(f.type)]
-    # last resort: NULL-ness of the floating columns (their values may differ in the last bits)
-    float_cols = [f.name for f in batch.schema if f.name not in key_cols and pa.types.is_floating(f.type)]
-    for name in float_cols:
-        col = batch.column(name).combine_chunks()
-        sort_keys_tail = ~np.asarray(col.is_valid().to_numpy(zero_copy_only=False), dtype=bool)
-        sort_keys.append(sort_keys_tail)
-    sort_keys = sort_keys[::-1]  # lowest priority first; the loop below appends higher-priority keys
-    tail = list(sort_keys)
-    sort_keys = []
-    for name in list(key_cols) + extra:
+    floats = [f.name for f in batch.schema if f.name not in key_cols and pa.types.is_floating(f.type)]
+    sort_keys = []  # highest priority first
+
+    def add(name, by_bits):
         col = batch.column(name).combine_chunks()
         valid = np.asarray(col.is_valid().to_numpy(zero_copy_only=False), dtype=bool)
         t = col.type
         if pa.types.is_floating(t):
             v = np.asarray(col.fill_null(0).to_numpy(zero_copy_only=False), dtype=np.float64)
-            bits = v.view(np.uint64)
-            # total order on the bit patterns (distinct groups for -0.0 / 0.0 / NaN payloads)
-            code = np.where(bits >> np.uint64(63), ~bits, bits | np.uint64(1 << 63))
+            if by_bits:
+                bits = v.view(np.uint64)
+                # total order on the bit patterns (distinct groups for -0.0 / 0.0 / NaN payloads)
+                code = np.where(bits >> np.uint64(63), ~bits, bits | np.uint64(1 << 63))
+            else:
+                code = np.where(np.isnan(v), np.inf, v)
         else:
             phys = pa.int32() if (pa.types.is_date32(t) or pa.types.is_time32(t)) else (
                 pa.int64() if pa.types.is_temporal(t) else t)
             v = np.asarray(col.view(phys).fill_null(0).to_numpy(zero_copy_only=False))
             code = v.astype(np.int64).view(np.uint64) ^ np.uint64(1 << 63) if v.dtype.kind == "i" else v.astype(np.uint64)
-        sort_keys.append(code)
         sort_keys.append(~valid)
-    sort_keys = sort_keys + tail[::-1]
-    order = np.lexsort(tuple(reversed(sort_keys))) if n else np.empty(0, dtype=np.int64)
+        sort_keys.append(code)
+
+    for name in list(key_cols) + exact:
+        add(name, True)
+    for name in floats:
+        add(name, False)
+    order = np.lexsort(tuple(reversed(sort_keys)))
     return batch.take(pa.array(order, type=pa.int64()))
 
 

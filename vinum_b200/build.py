@@ -20,12 +20,16 @@ CSRC = HERE / "csrc"
 OUT_DIR = HERE / "_C"
 LIB_PATH = OUT_DIR / "libvinum_b200.so"
 
+# (source, object stem, extra defines): vk_agg_fast_inst.cu is compiled once per slice of
+# the fused-aggregate kernel variants so that they build in parallel
 SOURCES = [
-    "vk_runtime.cu",
-    "vk_filter.cu",
-    "vk_arith.cu",
-    "vk_hashagg.cu",
-    "vk_sort.cu",
+    ("vk_agg_fast_inst.cu", f"vk_agg_fast_inst{part}", [f"-DVK_FAST_PART={part}"]) for part in range(5)
+] + [
+    ("vk_hashagg.cu", "vk_hashagg", []),
+    ("vk_sort.cu", "vk_sort", []),
+    ("vk_filter.cu", "vk_filter", []),
+    ("vk_runtime.cu", "vk_runtime", []),
+    ("vk_arith.cu", "vk_arith", []),
 ]
 
 NVCC_FLAGS = [
@@ -63,9 +67,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     obj_dir = OUT_DIR / "obj"
     obj_dir.mkdir(exist_ok=True)
 
-    def compile_one(src: str) -> Path:
-        obj = obj_dir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+    hdr_mtime = max(f.stat().st_mtime for f in list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "vinum_b200.h",
+                                                                            Path(__file__)])
+
+    def compile_one(item) -> Path:
+        src, stem, defines = item
+        obj = obj_dir / (stem + ".o")
+        if not force and obj.exists() and obj.stat().st_mtime >= max(hdr_mtime, (CSRC / src).stat().st_mtime):
+            return obj  # up to date
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
             print(" ".join(cmd), flush=True)
@@ -84,7 +94,6 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB_PATH)
-    shutil.rmtree(obj_dir, ignore_errors=True)
     return LIB_PATH
 
 

@@ -1,25 +1,39 @@
 // agg_fast_kernel -- fused filter -> hash aggregate for low-cardinality single-key
-// group-bys (the north-star pipeline).  See DESIGN.md 3.1.
+// group-bys (the north-star pipeline).
 //
-// One persistent CTA per SM.  Rows stream through registers (16-byte loads, next tile
-// prefetched while the current one is processed); the WHERE predicate is evaluated in
-// registers; the key is resolved in a CTA-shared open-addressing table to a DENSE group
-// id; COUNT and up to three 64-bit accumulator cells per group live in WARP-PRIVATE
-// shared-memory arrays that are updated with plain read-modify-write (shared-memory
-// 64-bit atomics are CAS loops on sm_100a and far too slow for a per-row path).  Lanes
-// of a warp that hit the same group in the same step are serialised in
-// __match_any_sync rank order.  The whole per-row path is warp-convergent: the probe
-// loop runs until __any_sync says no lane is searching, so the warp never splits into
-// sub-warps that would replay the loads and the table code.
+// Measured on B200 (scripts/ubench/smem_prims.cu, profiles/): MATCH.ANY costs 64 issue
+// cycles per warp, a shared 64-bit CAS ~11, a shared f64 atomicAdd (CAS loop) ~20, while a
+// random LDS.128 + STS.128 pair costs ~12-19 and a one-byte STS + LDS pair ~6.  The per-row
+// path below therefore contains no atomic and no MATCH:
+//
+//  * one persistent CTA per SM; rows stream through registers with 16-byte loads that stay
+//    RAW (no instruction touches a loaded register until the tile is processed, so the loads
+//    of tile k+1 are in flight during all of tile k); the WHERE predicate is evaluated in
+//    registers and never materialised;
+//  * the key is mapped to a dense group id either DIRECTLY (key - base < G: dense integer
+//    domains such as dictionary codes, learned by the host from the first chunk) or through
+//    a CTA-shared open-addressing table that is only READ on the per-row path (an 8-byte CAS
+//    runs once per distinct key per CTA);
+//  * COUNT and the accumulator cells of a group live in WARP-PRIVATE 16/32-byte entries
+//    updated with plain LDS.128 / STS.128.  Lanes of a warp that hit the same group in the
+//    same step are serialised by tag arbitration: every lane stores its lane id in a byte
+//    array indexed by group, the warp syncs, the lane that reads its own id back owns the
+//    group for this round, the others retry;
+//  * every loop on the path is warp-convergent (runs until __any_sync says no lane is
+//    pending), so a warp never splits into sub-warps.
+//
+// At the end every CTA folds its warps' entries and flushes one update per group into the
+// global table.  Keys that do not fit the CTA's table go to the global table row by row.
 #pragma once
 #include "vk_hashagg.cuh"
 
 namespace vk {
 
-constexpr int FA_ROWS = 4;        // rows per thread per tile (two lane-contiguous pairs)
-constexpr int FA_MAX_COLS = 3;    // distinct value columns
-constexpr int FA_MAX_CELLS = 3;   // 64-bit accumulator cells per group
-constexpr int FA_MAX_WARPS = 16;
+constexpr int FA_MAX_THREADS = 256;
+constexpr int FA_R = 8;            // rows per thread per tile (four lane-contiguous pairs)
+constexpr int FA_MAX_COLS = 3;     // distinct value columns
+constexpr int FA_MAX_CELLS = 3;    // 64-bit accumulator cells per group (besides COUNT)
+constexpr int FA_MAXPROBE = 64;
 constexpr uint32_t GID_PENDING = 0xFFFFu;  // key claimed, dense id not published yet
 constexpr uint32_t GID_SPILL = 0xFFFEu;    // more groups than the CTA holds: rows go to the global table
 constexpr uint64_t LK_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
@@ -27,13 +41,20 @@ constexpr uint64_t LK_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
 enum CellOp { CELL_ADD_F64 = 0, CELL_ADD_I64 = 1, CELL_ADD_I128 = 2 /* this cell = lo, next = hi */,
               CELL_I128_HI = 3, CELL_MAXORD = 4 };
 
+// Column layout specialisations (compile time): what a loaded register pair means.
+enum FastMode {
+    FM_ALL8 = 0,     // key and every value column are 8-byte raw
+    FM_KEY4 = 1,     // 4-byte key (int32 sign- or uint32/float32 zero-extended), 8-byte values
+    FM_RUNTIME = 2   // per-column modes decided at run time (key_mode / col_mode)
+};
+
 struct FastCell {
-    int32_t op;          // CellOp
-    int32_t col;         // index into FastParams::col
-    uint32_t func_mask;  // aggregate functions this cell is flushed into
-    int32_t ord;         // MAXORD: OrdKind
-    int32_t is_min;      // MAXORD
-    int32_t in_unsigned; // ADD_I128: zero- instead of sign-extend
+    int32_t op;           // CellOp
+    int32_t col;          // index into FastParams::col
+    uint32_t func_mask;   // aggregate functions this cell is flushed into
+    int32_t ord;          // MAXORD: OrdKind
+    int32_t is_min;       // MAXORD
+    int32_t in_unsigned;  // ADD_I128: zero- instead of sign-extend
 };
 
 struct FastParams {
@@ -47,104 +68,197 @@ struct FastParams {
     FastCell cell[FA_MAX_CELLS];
     int64_t n;
     int64_t num_tiles;
-    int log2s;                    // shared key table slots = 1 << log2s
+    int log2s;                    // shared key table slots = 1 << log2s (hash mode)
     int gmax;                     // dense group ids per CTA
+    uint64_t direct_base;         // direct mode: gid = key - direct_base
     int64_t row_limit;            // row-level global inserts stop here (flush reserve above it)
     GTable table;
     ReplayList replay;
 };
 
-__host__ __device__ inline size_t fast_smem_bytes(int log2s, int gmax, int n_cells, int warps) {
-    size_t S = (size_t) 1 << log2s;
-    size_t table = S * 8 + S * 2;
-    table = (table + 15) & ~(size_t) 15;
-    size_t per_warp = (size_t) gmax * 4 + (size_t) n_cells * gmax * 8;
-    return table + per_warp * warps;
+// Dynamic shared memory: [hash mode: keys[S] u64 | gid[S] u16] | per warp { entries[G][NW] u64 | tags[G] u8 }.
+__host__ __device__ inline size_t fast_table_bytes(int log2s, bool direct) { return direct ? 0 : ((size_t) 10 << log2s); }
+__host__ __device__ inline size_t fast_warp_bytes(int gmax, int nw) {
+    return (size_t) gmax * nw * 8 + (((size_t) gmax + 15) & ~(size_t) 15);
+}
+__host__ __device__ inline size_t fast_smem_bytes(int log2s, bool direct, int gmax, int nw, int warps) {
+    return fast_table_bytes(log2s, direct) + fast_warp_bytes(gmax, nw) * warps;
 }
 
-template <int PK, int NV>
-struct TileRegs {
-    uint64_t key[FA_ROWS];
-    uint64_t pred[(PK == PK_F64_VEC || PK == PK_I64_VEC) ? FA_ROWS : 1];
-    uint64_t val[NV > 0 ? NV : 1][FA_ROWS];
-    uint32_t flags;  // bit r: row r in range (and, for non-vector predicates, already selected)
-};
+// ---- shared-memory accessors (explicit so that nothing is cached in registers) ---------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t lds64(uint32_t a) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t a, uint32_t (&e)[4]) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint32_t (&e)[4]) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]) : "memory");
+}
+__device__ __forceinline__ uint32_t ldg_stream2(const void* p) {
+    uint16_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return r;
+}
 
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t) hi << 32) | lo; }
 
+// ---- tile registers: RAW load results, decoded only when the tile is processed ----------
+template <int PK, int NV>
+struct RawTile {
+    uint4 kq[FA_R / 2];
+    uint4 pq[(PK == PK_F64_VEC || PK == PK_I64_VEC || PK == PK_MASK) ? FA_R / 2 : 1];
+    uint4 vq[NV > 0 ? NV : 1][FA_R / 2];
+    uint32_t flags;  // bit r: row r exists (and, for PK_GENERIC, is already selected)
+};
+
+// Row pairs are lane-contiguous: pair j of thread t covers rows base + j*2*threads + 2t, +1,
+// so every 8-byte column is read with one 16-byte load per lane per pair.
+template <int PK, int NV, int MODE>
+__device__ __forceinline__ void load_tile_full(const FastParams& p, int64_t tile, int tid, int nthreads, RawTile<PK, NV>& t) {
+    const int64_t r0 = tile * (int64_t) (nthreads * FA_R) + tid * 2;
+    const int64_t jstride = (int64_t) nthreads * 2;
+    t.flags = (1u << FA_R) - 1u;
+#pragma unroll
+    for (int j = 0; j < FA_R / 2; ++j) {
+        const int64_t r = r0 + j * jstride;
+        if (MODE == FM_ALL8 || (MODE == FM_RUNTIME && p.key_mode == 0)) {
+            t.kq[j] = ldg_stream16(p.key.data + r * 8);
+        } else {
+            const uint2 q = ldg_stream8(p.key.data + r * 4);
+            t.kq[j].x = q.x;
+            t.kq[j].y = q.y;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            if (MODE != FM_RUNTIME || p.col_mode[v] == 0) {
+                t.vq[v][j] = ldg_stream16(p.col[v].data + r * 8);
+            } else {
+                const uint2 q = ldg_stream8(p.col[v].data + r * 4);
+                t.vq[v][j].x = q.x;
+                t.vq[v][j].y = q.y;
+            }
+        }
+        if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
+            t.pq[j] = ldg_stream16(p.pred.col.data + r * 8);
+        } else if constexpr (PK == PK_MASK) {
+            t.pq[j].x = ldg_stream2(p.pred.mask + r);  // two mask bytes; r is even, the base 2-byte aligned
+        } else if constexpr (PK == PK_GENERIC) {
+            bool f0, f1;
+            pred_pair<PK>(p.pred, r, p.n, f0, f1);
+            if (!f0) t.flags &= ~(1u << (2 * j));
+            if (!f1) t.flags &= ~(2u << (2 * j));
+        }
+    }
+}
+
+// The last, partial tile of a chunk: row-wise loads, out-of-range rows flagged off.
+template <int PK, int NV, int MODE>
+__device__ __forceinline__ void load_tile_tail(const FastParams& p, int64_t tile, int tid, int nthreads, RawTile<PK, NV>& t) {
+    const int64_t r0 = tile * (int64_t) (nthreads * FA_R) + tid * 2;
+    const int64_t jstride = (int64_t) nthreads * 2;
+    t.flags = 0;
+    auto ld_elem = [](const Col& c, bool eight, int64_t i, uint32_t& lo, uint32_t& hi) {
+        if (eight) {
+            const uint64_t v = reinterpret_cast<const uint64_t*>(c.data)[i];
+            lo = (uint32_t) v;
+            hi = (uint32_t) (v >> 32);
+        } else {
+            lo = reinterpret_cast<const uint32_t*>(c.data)[i];
+            hi = 0;
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < FA_R / 2; ++j) {
+        t.kq[j] = make_uint4(0, 0, 0, 0);
+        if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC || PK == PK_MASK) t.pq[j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) t.vq[v][j] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int64_t r = r0 + j * jstride + hf;
+            if (r >= p.n) continue;
+            uint32_t lo, hi;
+            const bool k8 = MODE == FM_ALL8 || (MODE == FM_RUNTIME && p.key_mode == 0);
+            ld_elem(p.key, k8, r, lo, hi);
+            if (k8) { if (hf) { t.kq[j].z = lo; t.kq[j].w = hi; } else { t.kq[j].x = lo; t.kq[j].y = hi; } }
+            else { if (hf) t.kq[j].y = lo; else t.kq[j].x = lo; }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const bool v8 = MODE != FM_RUNTIME || p.col_mode[v] == 0;
+                ld_elem(p.col[v], v8, r, lo, hi);
+                if (v8) { if (hf) { t.vq[v][j].z = lo; t.vq[v][j].w = hi; } else { t.vq[v][j].x = lo; t.vq[v][j].y = hi; } }
+                else { if (hf) t.vq[v][j].y = lo; else t.vq[v][j].x = lo; }
+            }
+            bool on = true;
+            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
+                ld_elem(p.pred.col, true, r, lo, hi);
+                if (hf) { t.pq[j].z = lo; t.pq[j].w = hi; } else { t.pq[j].x = lo; t.pq[j].y = hi; }
+            } else if constexpr (PK == PK_MASK) {
+                t.pq[j].x |= (uint32_t) p.pred.mask[r] << (8 * hf);
+            } else if constexpr (PK == PK_GENERIC) {
+                on = pred_row_generic(p.pred, r);
+            }
+            if (on) t.flags |= 1u << (2 * j + hf);
+        }
+    }
+}
+
+// ---- decoding a row of a raw tile ---------------------------------------------------------
 __device__ __forceinline__ uint64_t widen4(uint32_t raw, int mode) {
     if (mode == 1) return (uint64_t) (int64_t) (int32_t) raw;
     if (mode == 3) return (uint64_t) __double_as_longlong((double) __uint_as_float(raw));
     return raw;
 }
-
-template <int PK, int NV>
-__device__ __forceinline__ void load_tile(const FastParams& p, int64_t tile, int tid, int nthreads,
-                                          TileRegs<PK, NV>& t) {
-    t.flags = 0;
-    const int64_t base = tile * (int64_t) (nthreads * FA_ROWS);
-#pragma unroll
-    for (int j = 0; j < FA_ROWS / 2; ++j) {
-        const int64_t r0 = base + (int64_t) j * (nthreads * 2) + tid * 2;
-        const int a = 2 * j, b = 2 * j + 1;
-        if (r0 + 1 < p.n) {
-            if (p.key_mode == 0) {
-                uint4 q = ldg_stream16(p.key.data + r0 * 8);
-                t.key[a] = u64_of(q.x, q.y);
-                t.key[b] = u64_of(q.z, q.w);
-            } else {
-                uint2 q = ldg_stream8(p.key.data + r0 * 4);
-                t.key[a] = p.key_mode == 1 ? (uint64_t) (int64_t) (int32_t) q.x : (uint64_t) q.x;
-                t.key[b] = p.key_mode == 1 ? (uint64_t) (int64_t) (int32_t) q.y : (uint64_t) q.y;
-            }
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                if (p.col_mode[v] == 0) {
-                    uint4 q = ldg_stream16(p.col[v].data + r0 * 8);
-                    t.val[v][a] = u64_of(q.x, q.y);
-                    t.val[v][b] = u64_of(q.z, q.w);
-                } else {
-                    uint2 q = ldg_stream8(p.col[v].data + r0 * 4);
-                    t.val[v][a] = widen4(q.x, p.col_mode[v]);
-                    t.val[v][b] = widen4(q.y, p.col_mode[v]);
-                }
-            }
-            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
-                uint4 q = ldg_stream16(p.pred.col.data + r0 * 8);
-                t.pred[a] = u64_of(q.x, q.y);
-                t.pred[b] = u64_of(q.z, q.w);
-                t.flags |= 3u << a;
-            } else {
-                bool f0, f1;
-                pred_pair<PK>(p.pred, r0, p.n, f0, f1);
-                t.flags |= ((uint32_t) f0 << a) | ((uint32_t) f1 << b);
-            }
-        } else if (r0 < p.n) {
-            // last odd row of the chunk
-            t.key[a] = p.key_mode == 0 ? reinterpret_cast<const uint64_t*>(p.key.data)[r0]
-                     : p.key_mode == 1 ? (uint64_t) (int64_t) reinterpret_cast<const int32_t*>(p.key.data)[r0]
-                                       : (uint64_t) reinterpret_cast<const uint32_t*>(p.key.data)[r0];
-            t.key[b] = 0;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                t.val[v][a] = p.col_mode[v] == 0 ? reinterpret_cast<const uint64_t*>(p.col[v].data)[r0]
-                                                 : widen4(reinterpret_cast<const uint32_t*>(p.col[v].data)[r0], p.col_mode[v]);
-                t.val[v][b] = 0;
-            }
-            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
-                t.pred[a] = reinterpret_cast<const uint64_t*>(p.pred.col.data)[r0];
-                t.pred[b] = 0;
-                t.flags |= 1u << a;
-            } else {
-                bool f0, f1;
-                pred_pair<PK>(p.pred, r0, p.n, f0, f1);
-                t.flags |= (uint32_t) f0 << a;
-            }
-        }
+template <int R>
+__device__ __forceinline__ uint64_t q8(const uint4 (&q)[FA_R / 2]) {  // 8-byte element of row R
+    return (R & 1) ? u64_of(q[R >> 1].z, q[R >> 1].w) : u64_of(q[R >> 1].x, q[R >> 1].y);
+}
+template <int R>
+__device__ __forceinline__ uint32_t q4(const uint4 (&q)[FA_R / 2]) {  // 4-byte element of row R
+    return (R & 1) ? q[R >> 1].y : q[R >> 1].x;
+}
+template <int MODE, int R>
+__device__ __forceinline__ uint64_t row_key(const FastParams& p, const uint4 (&kq)[FA_R / 2]) {
+    if constexpr (MODE == FM_ALL8) return q8<R>(kq);
+    else if constexpr (MODE == FM_KEY4) {
+        const uint32_t raw = q4<R>(kq);
+        const uint32_t hi = p.key_mode == 1 ? (uint32_t) ((int32_t) raw >> 31) : 0u;
+        return u64_of(raw, hi);
+    } else {
+        if (p.key_mode == 0) return q8<R>(kq);
+        return widen4(q4<R>(kq), p.key_mode == 1 ? 1 : 2);
+    }
+}
+template <int MODE, int R>
+__device__ __forceinline__ uint64_t row_val(const FastParams& p, int v, const uint4 (&vq)[FA_R / 2]) {
+    if constexpr (MODE != FM_RUNTIME) return q8<R>(vq);
+    else {
+        if (p.col_mode[v] == 0) return q8<R>(vq);
+        return widen4(q4<R>(vq), p.col_mode[v]);
     }
 }
 
-// Branch-free comparison: `sel_mask` has one bit per outcome {less, equal, greater, unordered}.
+// Branch-free comparison: `mask` has one bit per outcome {less, equal, greater, unordered}.
 __host__ __device__ inline uint32_t cmp_outcome_mask(int op) {
     switch (op) {
         case VK_EQ: return 0b0010u;
@@ -167,245 +281,392 @@ __device__ __forceinline__ uint64_t cell_apply(const FastCell& c, uint64_t cur, 
             return (uint64_t) __double_as_longlong(__longlong_as_double((long long) cur) +
                                                    __longlong_as_double((long long) v));
         case CELL_MAXORD: {
-            uint64_t o = ord_transform(c.ord, c.is_min, v);
+            const uint64_t o = ord_transform(c.ord, c.is_min, v);
             return o > cur ? o : cur;
         }
         default: return cur + v;  // ADD_I64 and the low limb of ADD_I128
     }
 }
 
-// A row that does not go through the CTA-local table: straight to the global one.
-template <int NV>
-__device__ __forceinline__ void fast_global_row(const FastParams& p, uint64_t key, const uint64_t* vals, int64_t row) {
-    int64_t g = gt1_find_or_insert(p.table, key, false, hash_key1(key), p.row_limit);
-    if (g < 0) {
-        replay_append(p.replay, row);
-        return;
-    }
-    atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), 1ULL);
+__device__ __forceinline__ uint32_t fast_hash32(uint64_t key) {
+    uint32_t x = (uint32_t) key ^ ((uint32_t) (key >> 32) * 0x85EBCA77u);
+    x ^= x >> 16;
+    return x * 0x9E3779B1u;  // Fibonacci hashing: the TOP bits index the table
+}
+
+// One folded group of a CTA (or one spilled row) into the global table.
+__device__ __forceinline__ void fast_global_update(const FastParams& p, int64_t g, uint64_t cnt, const uint64_t* w /*cells*/) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), (unsigned long long) cnt);
     for (int c = 0; c < p.n_cells; ++c) {
         const FastCell cell = p.cell[c];
         if (cell.op == CELL_I128_HI) continue;
-        uint64_t v = 0;
-#pragma unroll
-        for (int k = 0; k < NV; ++k)
-            if (cell.col == k) v = vals[k];
         uint32_t fm = cell.func_mask;
         while (fm) {
             const int fi = __ffs(fm) - 1;
             fm &= fm - 1;
             switch (cell.op) {
                 case CELL_ADD_F64:
-                    atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g), __longlong_as_double((long long) v));
+                    atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g), __longlong_as_double((long long) w[c]));
                     break;
                 case CELL_ADD_I64:
-                    atomicAdd(reinterpret_cast<unsigned long long*>(p.table.acc_lo[fi] + g), (unsigned long long) v);
+                    atomicAdd(reinterpret_cast<unsigned long long*>(p.table.acc_lo[fi] + g), (unsigned long long) w[c]);
                     break;
                 case CELL_ADD_I128:
-                    acc_add_i128(p.table.acc_lo[fi] + g, p.table.acc_hi[fi] + g, v,
-                                 (!cell.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL);
+                    acc_add_i128(p.table.acc_lo[fi] + g, p.table.acc_hi[fi] + g, w[c], w[c + 1 < FA_MAX_CELLS ? c + 1 : c]);
                     break;
                 default:
-                    atomicMax(reinterpret_cast<unsigned long long*>(p.table.acc_lo[fi] + g),
-                              (unsigned long long) ord_transform(cell.ord, cell.is_min, v));
+                    atomicMax(reinterpret_cast<unsigned long long*>(p.table.acc_lo[fi] + g), (unsigned long long) w[c]);
                     break;
             }
         }
     }
 }
 
-template <int PK, int NV>
-__global__ void __launch_bounds__(FA_MAX_WARPS * 32, 1) agg_fast_kernel(const __grid_constant__ FastParams p) {
+// A row that does not go through the CTA-local table: straight to the global one.
+static __device__ __noinline__ void fast_global_row(const FastParams& p, uint64_t key, uint64_t v0, uint64_t v1, uint64_t v2,
+                                             int64_t row) {
+    const int64_t g = gt1_find_or_insert(p.table, key, false, hash_key1(key), p.row_limit);
+    if (g < 0) {
+        replay_append(p.replay, row);
+        return;
+    }
+    const uint64_t vals[FA_MAX_COLS] = {v0, v1, v2};
+    uint64_t w[FA_MAX_CELLS] = {0, 0, 0};
+    for (int c = 0; c < p.n_cells; ++c) {
+        const FastCell cell = p.cell[c];
+        if (cell.op == CELL_I128_HI) {
+            const FastCell lo = p.cell[c - 1];
+            w[c] = (!lo.in_unsigned && (int64_t) vals[lo.col] < 0) ? ~0ULL : 0ULL;
+        } else if (cell.op == CELL_MAXORD) {
+            w[c] = ord_transform(cell.ord, cell.is_min, vals[cell.col]);
+        } else {
+            w[c] = vals[cell.col];
+        }
+    }
+    fast_global_update(p, g, 1, w);
+}
+
+// Kernel context shared by the per-row steps.
+struct FastCtx {
+    uint32_t a_keys, a_gid;  // shared key table (hash mode)
+    uint32_t a_ent, a_tag;   // this warp's entries / tags
+    uint32_t smask, hshift;
+    uint32_t opmask;
+    uint64_t pscalar;
+    int lane;
+};
+
+// NW = 64-bit words per entry (word 0 = COUNT, words 1.. = cells): 2 or 4.
+// SUMF64: the entry's single cell is a float64 SUM (no run-time cell dispatch).
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, int R>
+__device__ __forceinline__ void fast_row(const FastParams& p, const FastCtx& cx, const RawTile<PK, NV>& t, uint8_t* smem,
+                                         uint32_t* s_ngroups, int64_t row, uint32_t& spilled) {
+    constexpr int NCMAX = NW - 1;
+    // ---- predicate (registers only) ----
+    bool act = (t.flags >> R) & 1u;
+    if constexpr (PK == PK_F64_VEC)
+        act = act && cmp_by_mask(cx.opmask, __longlong_as_double((long long) q8<R>(t.pq)), __longlong_as_double((long long) cx.pscalar));
+    else if constexpr (PK == PK_I64_VEC)
+        act = act && cmp_by_mask(cx.opmask, (int64_t) q8<R>(t.pq), (int64_t) cx.pscalar);
+    else if constexpr (PK == PK_MASK)
+        act = act && ((t.pq[R >> 1].x >> (8 * (R & 1))) & 0xffu);
+    const uint64_t key = row_key<MODE, R>(p, t.kq);
+
+    // ---- key -> dense group id ----
+    uint32_t gid = GID_SPILL;
+    bool todo;
+    if constexpr (DIRECT) {
+        const uint64_t d = key - p.direct_base;
+        todo = act && d < (uint64_t) (uint32_t) p.gmax;
+        gid = (uint32_t) d;
+    } else {
+        uint32_t h = fast_hash32(key) >> cx.hshift;
+        bool pend = act && key != LK_EMPTY;  // the sentinel itself cannot live in the table
+        for (int it = 0; __any_sync(0xffffffffu, pend); ++it) {
+            if (it >= FA_MAXPROBE) break;     // table region exhausted: leave these rows to the global table
+            if (pend) {
+                const uint64_t k = lds64(cx.a_keys + h * 8);
+                const uint32_t g = lds16(cx.a_gid + h * 2);
+                if (k == key) {
+                    if (g != GID_PENDING) {
+                        gid = g;
+                        pend = false;
+                    }
+                } else if (k == LK_EMPTY) {
+                    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(smem) + h,
+                                                             (unsigned long long) LK_EMPTY, (unsigned long long) key);
+                    if (old == LK_EMPTY) {
+                        uint32_t ng = atomicAdd(s_ngroups, 1u);
+                        if (ng >= (uint32_t) p.gmax) ng = GID_SPILL;
+                        sts16(cx.a_gid + h * 2, ng);
+                        gid = ng;
+                        pend = false;
+                    } else if (old != key) {
+                        h = (h + 1) & cx.smask;
+                    }  // old == key: another lane just claimed it; read its id next round
+                } else {
+                    h = (h + 1) & cx.smask;
+                }
+            }
+        }
+        todo = act && gid < (uint32_t) p.gmax;
+    }
+    const bool spill = act && !todo;
+
+    // ---- accumulate into the warp-private entry; same-group lanes arbitrate by tag ----
+    while (__any_sync(0xffffffffu, todo)) {
+        if (todo) sts8(cx.a_tag + gid, (uint32_t) cx.lane);
+        __syncwarp();
+        if (todo && lds8(cx.a_tag + gid) == (uint32_t) cx.lane) {
+            todo = false;
+            const uint32_t ea = cx.a_ent + gid * (NW * 8);
+            uint32_t e[4];
+            lds128(ea, e);
+            e[0] += 1;  // COUNT: 32 bits are enough for one warp in one launch
+            if constexpr (SUMF64) {
+                const double s = __hiloint2double((int) e[3], (int) e[2]) +
+                                 __longlong_as_double((long long) row_val<MODE, R>(p, 0, t.vq[0]));
+                e[2] = (uint32_t) __double2loint(s);
+                e[3] = (uint32_t) __double2hiint(s);
+                sts128(ea, e);
+            } else {
+                uint32_t f[4] = {0, 0, 0, 0};
+                if constexpr (NW == 4) lds128(ea + 16, f);
+                uint64_t w[3] = {u64_of(e[2], e[3]), u64_of(f[0], f[1]), u64_of(f[2], f[3])};
+#pragma unroll
+                for (int c = 0; c < NCMAX; ++c) {
+                    if (c < p.n_cells) {
+                        const FastCell cell = p.cell[c];
+                        if (cell.op != CELL_I128_HI) {
+                            uint64_t v = 0;
+#pragma unroll
+                            for (int k = 0; k < NV; ++k)
+                                if (cell.col == k) v = row_val<MODE, R>(p, k, t.vq[k]);
+                            const uint64_t old = w[c];
+                            const uint64_t nv = cell_apply(cell, old, v);
+                            w[c] = nv;
+                            if (NW == 4 && cell.op == CELL_ADD_I128 && c + 1 < NCMAX) {
+                                const uint64_t ext = (!cell.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL;
+                                w[c + 1 < 3 ? c + 1 : 2] += ext + (nv < old ? 1ULL : 0ULL);
+                            }
+                        }
+                    }
+                }
+                e[2] = (uint32_t) w[0];
+                e[3] = (uint32_t) (w[0] >> 32);
+                sts128(ea, e);
+                if constexpr (NW == 4) {
+                    f[0] = (uint32_t) w[1]; f[1] = (uint32_t) (w[1] >> 32);
+                    f[2] = (uint32_t) w[2]; f[3] = (uint32_t) (w[2] >> 32);
+                    sts128(ea + 16, f);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- rows the CTA table could not take: global table, off the hot path ----
+    if (__any_sync(0xffffffffu, spill)) {
+        if (spill) {
+            uint64_t v[FA_MAX_COLS] = {0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = row_val<MODE, R>(p, k, t.vq[k]);
+            ++spilled;
+            fast_global_row(p, key, v[0], v[1], v[2], row);
+        }
+        __syncwarp();
+    }
+}
+
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64>
+__global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_ngroups;
-    const int S = 1 << p.log2s;
-    const uint32_t smask = S - 1;
+    const int S = DIRECT ? 0 : (1 << p.log2s);
     const int G = p.gmax;
     const int nthreads = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    const int ncells = p.n_cells;
+    constexpr int NCMAX = NW - 1;  // cells an entry can hold
 
-    uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem);
-    uint16_t* s_gid = reinterpret_cast<uint16_t*>(smem + (size_t) S * 8);
-    const size_t table_bytes = ((size_t) S * 10 + 15) & ~(size_t) 15;
-    const size_t per_warp = (size_t) G * 4 + (size_t) ncells * G * 8;
-    uint8_t* acc_base = smem + table_bytes;
-    uint64_t* my_cells = reinterpret_cast<uint64_t*>(acc_base + (size_t) warp * per_warp);  // [ncells][G]
-    uint32_t* my_cnt = reinterpret_cast<uint32_t*>(acc_base + (size_t) warp * per_warp + (size_t) ncells * G * 8);
+    const uint32_t a_base = smem_addr(smem);
+    const uint32_t a_warp0 = a_base + (uint32_t) fast_table_bytes(p.log2s, DIRECT);
+    const uint32_t warp_bytes = (uint32_t) fast_warp_bytes(G, NW);
+    FastCtx cx;
+    cx.a_keys = a_base;
+    cx.a_gid = a_base + (uint32_t) S * 8;
+    cx.a_ent = a_warp0 + (uint32_t) warp * warp_bytes;
+    cx.a_tag = cx.a_ent + (uint32_t) G * NW * 8;
+    cx.smask = (uint32_t) S - 1u;
+    cx.hshift = 32 - p.log2s;
+    cx.opmask = cmp_outcome_mask(p.pred.op);
+    cx.pscalar = p.pred.scalar.bits;
+    cx.lane = lane;
 
-    for (int i = tid; i < S; i += nthreads) {
-        s_keys[i] = LK_EMPTY;
-        s_gid[i] = (uint16_t) GID_PENDING;
-    }
     {
-        uint32_t* z = reinterpret_cast<uint32_t*>(acc_base);
-        const size_t words = per_warp * nwarps / 4;
-        for (size_t i = tid; i < words; i += nthreads) z[i] = 0;
-    }
-    if (tid == 0) s_ngroups = 0;
-    __syncthreads();
-
-    const unsigned lt = lanemask_lt();
-    const uint32_t opmask = cmp_outcome_mask(p.pred.op);
-    const uint64_t pscalar = p.pred.scalar.bits;
-    uint32_t spilled = 0;
-
-    TileRegs<PK, NV> cur, nxt;
-    int64_t tile = blockIdx.x;
-    if (tile < p.num_tiles) load_tile<PK, NV>(p, tile, tid, nthreads, cur);
-    for (; tile < p.num_tiles; tile += gridDim.x) {
-        __syncwarp();
-        const int64_t tnext = tile + gridDim.x;
-        if (tnext < p.num_tiles) load_tile<PK, NV>(p, tnext, tid, nthreads, nxt);
-
-#pragma unroll
-        for (int r = 0; r < FA_ROWS; ++r) {
-            // ---- predicate (registers only) ----
-            bool act = (cur.flags >> r) & 1;
-            if constexpr (PK == PK_F64_VEC)
-                act = act && cmp_by_mask(opmask, __longlong_as_double((long long) cur.pred[r]),
-                                         __longlong_as_double((long long) pscalar));
-            else if constexpr (PK == PK_I64_VEC)
-                act = act && cmp_by_mask(opmask, (int64_t) cur.pred[r], (int64_t) pscalar);
-            const uint64_t key = cur.key[r];
-
-            // ---- key -> dense group id: warp-convergent probe loop ----
-            uint64_t x = key ^ (key >> 29);
-            x *= 0x9E3779B97F4A7C15ULL;
-            const uint32_t hh = (uint32_t) (x >> 32);
-            uint32_t h = hh >> (32 - p.log2s);
-            const uint32_t step = ((hh << 1) | 1u) & smask;
-            uint32_t gid = GID_SPILL;
-            bool searching = act && key != LK_EMPTY;
-            for (int it = 0; it < 4 * 64; ++it) {
-                if (!__any_sync(0xffffffffu, searching)) break;
-                if (searching) {
-                    const uint64_t k = reinterpret_cast<volatile uint64_t*>(s_keys)[h];
-                    if (k == key) {
-                        const uint32_t g = reinterpret_cast<volatile uint16_t*>(s_gid)[h];
-                        if (g != GID_PENDING) {
-                            gid = g;
-                            searching = false;
-                        }
-                    } else if (k == LK_EMPTY) {
-                        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(s_keys + h),
-                                                                 (unsigned long long) LK_EMPTY, (unsigned long long) key);
-                        if (old == LK_EMPTY) {
-                            uint32_t g = atomicAdd(&s_ngroups, 1u);
-                            if (g >= (uint32_t) G) g = GID_SPILL;
-                            reinterpret_cast<volatile uint16_t*>(s_gid)[h] = (uint16_t) g;
-                            gid = g;
-                            searching = false;
-                        } else if (old != key) {
-                            h = (h + step) & smask;
-                        }  // old == key: another lane just inserted it; re-read its id next round
-                    } else {
-                        h = (h + step) & smask;
-                    }
-                }
-                __syncwarp();
-            }
-            const bool upd = act && !searching && gid < (uint32_t) G;
-            const bool spill = act && !upd;
-
-            // ---- accumulate into the warp-private arrays; same-group lanes take turns ----
-            const unsigned peers = __match_any_sync(0xffffffffu, upd ? gid : (0x10000u | (unsigned) lane));
-            const int mult = upd ? __popc(peers) : 0;
-            const int rank = __popc(peers & lt);
-            const int maxm = __reduce_max_sync(0xffffffffu, mult);
-            if (upd && rank == 0) my_cnt[gid] += (uint32_t) mult;
-            for (int round = 0; round < maxm; ++round) {
-                if (upd && rank == round) {
-                    for (int c = 0; c < ncells; ++c) {
-                        const FastCell cell = p.cell[c];
-                        if (cell.op == CELL_I128_HI) continue;
-                        uint64_t v = 0;
-#pragma unroll
-                        for (int k = 0; k < NV; ++k)
-                            if (cell.col == k) v = cur.val[k][r];
-                        uint64_t* slot = my_cells + (size_t) c * G + gid;
-                        const uint64_t old = *slot;
-                        const uint64_t nw = cell_apply(cell, old, v);
-                        *slot = nw;
-                        if (cell.op == CELL_ADD_I128) {
-                            const uint64_t ext = (!cell.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL;
-                            slot[G] += ext + (nw < old ? 1ULL : 0ULL);
-                        }
-                    }
-                }
-                if (maxm > 1) __syncwarp();
-            }
-
-            // ---- rows the CTA table could not take: global table, off the hot path ----
-            if (__any_sync(0xffffffffu, spill)) {
-                if (spill) {
-                    uint64_t vals[NV > 0 ? NV : 1];
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) vals[k] = cur.val[k][r];
-                    const int64_t row = tile * (int64_t) (nthreads * FA_ROWS) + (int64_t) (r >> 1) * (nthreads * 2) +
-                                        tid * 2 + (r & 1);
-                    ++spilled;
-                    fast_global_row<NV>(p, key, vals, row);
-                }
-                __syncwarp();
+        if constexpr (!DIRECT) {
+            uint64_t* k = reinterpret_cast<uint64_t*>(smem);
+            uint16_t* g = reinterpret_cast<uint16_t*>(smem + (size_t) S * 8);
+            for (int i = tid; i < S; i += nthreads) {
+                k[i] = LK_EMPTY;
+                g[i] = (uint16_t) GID_PENDING;
             }
         }
-        cur = nxt;
+        uint32_t* z = reinterpret_cast<uint32_t*>(smem + fast_table_bytes(p.log2s, DIRECT));
+        const size_t words = (size_t) warp_bytes * nwarps / 4;
+        for (size_t i = tid; i < words; i += nthreads) z[i] = 0;
+        if (tid == 0) s_ngroups = 0;
+    }
+    __syncthreads();
+
+    uint32_t spilled = 0;
+    const int64_t tile_rows = (int64_t) nthreads * FA_R;
+    const int64_t full_tiles = p.n / tile_rows;  // tiles [0, full_tiles) are complete
+
+    auto load = [&](int64_t tile, RawTile<PK, NV>& t) {
+        if (tile < full_tiles) load_tile_full<PK, NV, MODE>(p, tile, tid, nthreads, t);
+        else load_tile_tail<PK, NV, MODE>(p, tile, tid, nthreads, t);
+    };
+    auto process = [&](int64_t tile, const RawTile<PK, NV>& t) {
+        const int64_t row0 = tile * tile_rows + tid * 2;
+#define VK_FAST_ROW(RR)                                                                                         \
+        fast_row<PK, NV, NW, MODE, DIRECT, SUMF64, RR>(p, cx, t, smem, &s_ngroups,                               \
+                                                       row0 + (int64_t) (RR >> 1) * (nthreads * 2) + (RR & 1), spilled);
+        VK_FAST_ROW(0) VK_FAST_ROW(1) VK_FAST_ROW(2) VK_FAST_ROW(3)
+        VK_FAST_ROW(4) VK_FAST_ROW(5) VK_FAST_ROW(6) VK_FAST_ROW(7)
+#undef VK_FAST_ROW
+    };
+
+    // two register tiles, explicitly alternated: no copy ever waits on a load
+    RawTile<PK, NV> ta, tb;
+    int64_t tile = blockIdx.x;
+    const int64_t stride = gridDim.x;
+    if (tile < p.num_tiles) load(tile, ta);
+    while (tile < p.num_tiles) {
+        if (tile + stride < p.num_tiles) load(tile + stride, tb);
+        process(tile, ta);
+        tile += stride;
+        if (tile >= p.num_tiles) break;
+        if (tile + stride < p.num_tiles) load(tile + stride, ta);
+        process(tile, tb);
+        tile += stride;
     }
 
-    // ---- flush: combine the warps' private accumulators, one global update per group ----
+    // ---- flush: fold the warps' private entries, one global update per group ----
     __syncthreads();
     for (int d = 16; d > 0; d >>= 1) spilled += __shfl_xor_sync(0xffffffffu, spilled, d);
     if (lane == 0 && spilled) atomicAdd(p.replay.spilled, (unsigned long long) spilled);
-    for (int s = tid; s < S; s += nthreads) {
-        const uint64_t key = s_keys[s];
-        if (key == LK_EMPTY) continue;
-        const uint32_t gid = s_gid[s];
-        if (gid >= (uint32_t) G) continue;
+    const int n_iter = DIRECT ? G : S;
+    for (int s = tid; s < n_iter; s += nthreads) {
+        uint64_t key;
+        uint32_t g16;
+        if constexpr (DIRECT) {
+            key = p.direct_base + (uint64_t) s;
+            g16 = (uint32_t) s;
+        } else {
+            key = lds64(cx.a_keys + s * 8);
+            if (key == LK_EMPTY) continue;
+            g16 = lds16(cx.a_gid + s * 2);
+            if (g16 >= (uint32_t) G) continue;
+        }
         uint64_t cnt = 0;
-        for (int w = 0; w < nwarps; ++w)
-            cnt += reinterpret_cast<const uint32_t*>(acc_base + (size_t) w * per_warp + (size_t) ncells * G * 8)[gid];
+        uint64_t acc[FA_MAX_CELLS] = {0, 0, 0};
+        double facc[FA_MAX_CELLS] = {0.0, 0.0, 0.0};
+        for (int w = 0; w < nwarps; ++w) {
+            const uint32_t ea = a_warp0 + (uint32_t) w * warp_bytes + g16 * (NW * 8);
+            uint32_t e[4], f[4] = {0, 0, 0, 0};
+            lds128(ea, e);
+            if constexpr (NW == 4) lds128(ea + 16, f);
+            cnt += e[0];
+            const uint64_t ev[3] = {u64_of(e[2], e[3]), u64_of(f[0], f[1]), u64_of(f[2], f[3])};
+#pragma unroll
+            for (int c = 0; c < NCMAX; ++c) {
+                if (c < p.n_cells) {
+                    const int op = p.cell[c].op;
+                    const uint64_t v = ev[c];
+                    if (op == CELL_ADD_F64) facc[c] += __longlong_as_double((long long) v);
+                    else if (op == CELL_MAXORD) acc[c] = v > acc[c] ? v : acc[c];
+                    else if (op == CELL_ADD_I128) {
+                        const uint64_t nl = acc[c] + v;
+                        if (c + 1 < NCMAX) acc[c + 1] += (nl < acc[c] ? 1ULL : 0ULL);
+                        acc[c] = nl;
+                    } else acc[c] += v;  // ADD_I64, I128_HI
+                }
+            }
+        }
         if (cnt == 0) continue;
+#pragma unroll
+        for (int c = 0; c < NCMAX; ++c)
+            if (c < p.n_cells && p.cell[c].op == CELL_ADD_F64) acc[c] = (uint64_t) __double_as_longlong(facc[c]);
         // the host reserves capacity for every CTA's groups: this insert cannot fail
         const int64_t g = gt1_find_or_insert(p.table, key, false, hash_key1(key), INT64_MAX);
         if (g < 0) {
             atomicAdd(p.replay.lost, (unsigned long long) cnt);
             continue;
         }
-        atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), (unsigned long long) cnt);
-        for (int c = 0; c < ncells; ++c) {
-            const FastCell cell = p.cell[c];
-            if (cell.op == CELL_I128_HI) continue;
-            uint64_t lo = 0, hi = 0;
-            double fsum = 0.0;
-            for (int w = 0; w < nwarps; ++w) {
-                const uint64_t* cells = reinterpret_cast<const uint64_t*>(acc_base + (size_t) w * per_warp);
-                const uint64_t v = cells[(size_t) c * G + gid];
-                if (cell.op == CELL_ADD_F64) fsum += __longlong_as_double((long long) v);
-                else if (cell.op == CELL_MAXORD) lo = v > lo ? v : lo;
-                else {
-                    const uint64_t nl = lo + v;
-                    if (cell.op == CELL_ADD_I128) hi += cells[(size_t) (c + 1) * G + gid] + (nl < lo ? 1ULL : 0ULL);
-                    lo = nl;
-                }
-            }
-            uint32_t fm = cell.func_mask;
-            while (fm) {
-                const int fi = __ffs(fm) - 1;
-                fm &= fm - 1;
-                switch (cell.op) {
-                    case CELL_ADD_F64: atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g), fsum); break;
-                    case CELL_ADD_I64:
-                        atomicAdd(reinterpret_cast<unsigned long long*>(p.table.acc_lo[fi] + g), (unsigned long long) lo);
-                        break;
-                    case CELL_ADD_I128: acc_add_i128(p.table.acc_lo[fi] + g, p.table.acc_hi[fi] + g, lo, hi); break;
-                    default:
-                        atomicMax(reinterpret_cast<unsigned long long*>(p.table.acc_lo[fi] + g), (unsigned long long) lo);
-                        break;
-                }
-            }
-        }
+        fast_global_update(p, g, cnt, acc);
     }
 }
+
+// ---- launch plumbing (instantiated per predicate kind in vk_agg_fast_pk*.cu) -------------
+struct FastLaunch {
+    int pk;        // PredKernelKind
+    int nw;        // 2 or 4
+    int mode;      // FastMode
+    bool direct;
+    bool sumf64;
+    int grid, threads;
+    size_t smem;
+};
+
+
+#define VK_FAST_GO(PK, NV, NW, MODE, DIRECT, SUMF64)                                                             \
+    do {                                                                                                       \
+        auto kernel = agg_fast_kernel<PK, NV, NW, MODE, DIRECT, SUMF64>;                                        \
+        VK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) l.smem));      \
+        kernel<<<l.grid, l.threads, l.smem, s>>>(p);                                                           \
+        VK_CHECK_LAUNCH("agg_fast_kernel");                                                                    \
+        return VK_OK;                                                                                          \
+    } while (0)
+
+// Lean set: compile-time layout, optional direct mode (predicate kinds NONE / F64_VEC).
+template <int PK, int MODE, bool DIRECT>
+int launch_fast_lean(const FastParams& p, const FastLaunch& l, cudaStream_t s) {
+    switch (p.n_cols) {
+        case 0: VK_FAST_GO(PK, 0, 2, MODE, DIRECT, false);
+        case 1:
+            if (l.nw == 2 && l.sumf64) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true);
+            if (l.nw == 2) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, false);
+            VK_FAST_GO(PK, 1, 4, MODE, DIRECT, false);
+        case 2: VK_FAST_GO(PK, 2, 4, MODE, DIRECT, false);
+        default: VK_FAST_GO(PK, 3, 4, MODE, DIRECT, false);
+    }
+}
+// Generic set: run-time column modes, hash mode only (every predicate kind).
+template <int PK>
+int launch_fast_generic(const FastParams& p, const FastLaunch& l, cudaStream_t s) {
+    switch (p.n_cols) {
+        case 0: VK_FAST_GO(PK, 0, 2, FM_RUNTIME, false, false);
+        case 1:
+            if (l.nw == 2) VK_FAST_GO(PK, 1, 2, FM_RUNTIME, false, false);
+            VK_FAST_GO(PK, 1, 4, FM_RUNTIME, false, false);
+        case 2: VK_FAST_GO(PK, 2, 4, FM_RUNTIME, false, false);
+        default: VK_FAST_GO(PK, 3, 4, FM_RUNTIME, false, false);
+    }
+}
+// The instantiations are spread over several translation units (vk_agg_fast_inst.cu is
+// compiled once per VK_FAST_PART) so that they build in parallel.
+#define VK_FAST_DECL(name) int name(const FastParams& p, const FastLaunch& l, cudaStream_t s)
+VK_FAST_DECL(launch_fast_none_all8);
+VK_FAST_DECL(launch_fast_none_key4);
+VK_FAST_DECL(launch_fast_none_rt);
+VK_FAST_DECL(launch_fast_f64_all8);
+VK_FAST_DECL(launch_fast_f64_key4);
+VK_FAST_DECL(launch_fast_f64_rt);
+VK_FAST_DECL(launch_fast_mask_rt);
+VK_FAST_DECL(launch_fast_i64_rt);
+VK_FAST_DECL(launch_fast_gen_rt);
+
+// Which predicate kinds have the lean set (the host only asks for direct / compile-time modes there).
+__host__ inline bool fast_pk_is_lean(int pk) { return pk == PK_NONE || pk == PK_F64_VEC; }
 
 }  // namespace vk

@@ -19,6 +19,7 @@
 // appended to a replay list; the host grows the table and replays them, so an update
 // never loses rows whatever the cardinality turns out to be.
 #include "vk_hashagg.cuh"
+#include "vk_agg_fast.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,315 +27,25 @@
 
 namespace vk {
 
-constexpr uint64_t LK_EMPTY = 0xFFFFFFFFFFFFFFFFULL;
-constexpr int FA_THREADS = 256;
-constexpr int FA_ROWS = 4;                       // rows per thread per tile
-constexpr int FA_TILE = FA_THREADS * FA_ROWS;    // 1024 rows
-constexpr int FA_MAXPROBE = 16;
-constexpr int FA_MAX_VALS = 2;
-
-enum FastStrategy { FS_SHARED_CAS = 0, FS_WARP_PRIVATE = 1, FS_GLOBAL_RED = 2 };
-
-struct ReplayList {
-    uint32_t* rows;                 // row ids relative to the chunk start
-    unsigned long long* count;      // appended so far
-    unsigned long long* lost;       // rows that did not fit (must stay 0)
-    unsigned long long* spilled;    // rows the fast kernel sent to the global path (statistics)
-    uint64_t capacity;
-};
-
-__device__ __forceinline__ void replay_append(const ReplayList& l, int64_t row) {
-    unsigned long long pos = atomicAdd(l.count, 1ULL);
-    if (pos < l.capacity) l.rows[pos] = (uint32_t) row;
-    else atomicAdd(l.lost, 1ULL);
-}
-
-struct FastParams {
-    Pred pred;
-    Col key;
-    int key_mode;  // 0: 8-byte raw bits, 1: int32 sign-extend, 2: 4-byte zero-extend
-    int n_vals;
-    Col val[FA_MAX_VALS];
-    uint32_t val_funcs[FA_MAX_VALS];  // bitmask of function indices fed by val[v]
-    int64_t n;
-    int64_t num_tiles;
-    int log2s;
-    int64_t row_limit;  // row-level inserts stop here; the rest is reserved for the CTA flushes
-    GTable table;
-    ReplayList replay;
-};
-
-// ---- raw tile registers ---------------------------------------------------------
-template <int PK, int NV>
-struct TileRegs {
-    uint64_t key[FA_ROWS];
-    uint64_t pred[(PK == PK_F64_VEC || PK == PK_I64_VEC) ? FA_ROWS : 1];
-    uint64_t val[NV > 0 ? NV : 1][FA_ROWS];
-    uint32_t flags;  // bit r: row r is in range (and, for non-vector predicates, selected)
-};
-
-__device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t) hi << 32) | lo; }
-
-template <int PK, int NV>
-__device__ __forceinline__ void load_tile(const FastParams& p, int64_t tile, int tid, TileRegs<PK, NV>& t) {
-    t.flags = 0;
-    const int64_t base = tile * FA_TILE;
-#pragma unroll
-    for (int j = 0; j < FA_ROWS / 2; ++j) {
-        const int64_t r0 = base + j * (FA_THREADS * 2) + tid * 2;
-        const int a = 2 * j, b = 2 * j + 1;
-        if (r0 + 1 < p.n) {
-            // ---- full pair: vector loads ----
-            if (p.key_mode == 0) {
-                uint4 q = ldg_stream16(p.key.data + r0 * 8);
-                t.key[a] = u64_of(q.x, q.y);
-                t.key[b] = u64_of(q.z, q.w);
-            } else {
-                uint2 q = ldg_stream8(p.key.data + r0 * 4);
-                if (p.key_mode == 1) {
-                    t.key[a] = (uint64_t) (int64_t) (int32_t) q.x;
-                    t.key[b] = (uint64_t) (int64_t) (int32_t) q.y;
-                } else {
-                    t.key[a] = q.x;
-                    t.key[b] = q.y;
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                uint4 q = ldg_stream16(p.val[v].data + r0 * 8);
-                t.val[v][a] = u64_of(q.x, q.y);
-                t.val[v][b] = u64_of(q.z, q.w);
-            }
-            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
-                uint4 q = ldg_stream16(p.pred.col.data + r0 * 8);
-                t.pred[a] = u64_of(q.x, q.y);
-                t.pred[b] = u64_of(q.z, q.w);
-                t.flags |= 3u << a;
-            } else {
-                bool f0, f1;
-                pred_pair<PK>(p.pred, r0, p.n, f0, f1);
-                t.flags |= ((uint32_t) f0 << a) | ((uint32_t) f1 << b);
-            }
-        } else if (r0 < p.n) {
-            // ---- last odd row of the chunk ----
-            t.key[a] = p.key_mode == 0 ? reinterpret_cast<const uint64_t*>(p.key.data)[r0]
-                     : p.key_mode == 1 ? (uint64_t) (int64_t) reinterpret_cast<const int32_t*>(p.key.data)[r0]
-                                       : (uint64_t) reinterpret_cast<const uint32_t*>(p.key.data)[r0];
-            t.key[b] = 0;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                t.val[v][a] = reinterpret_cast<const uint64_t*>(p.val[v].data)[r0];
-                t.val[v][b] = 0;
-            }
-            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
-                t.pred[a] = reinterpret_cast<const uint64_t*>(p.pred.col.data)[r0];
-                t.pred[b] = 0;
-                t.flags |= 1u << a;
-            } else {
-                bool f0, f1;
-                pred_pair<PK>(p.pred, r0, p.n, f0, f1);
-                t.flags |= (uint32_t) f0 << a;
-            }
-        }
+// ============================================================ key range (direct mode)
+// Smallest / largest key of a single-key table in SIGNED 64-bit order; out[0] = min, out[1] = max.
+__global__ void __launch_bounds__(256) agg_key_range_kernel(GTable t, long long* out) {
+    long long mn = INT64_MAX, mx = INT64_MIN;
+    const int64_t slots = t.capacity + 1;  // + the slot of the all-ones key; the NULL group has no key
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (int64_t) gridDim.x * blockDim.x) {
+        if (!gt_slot_occupied(t, s)) continue;
+        const long long k = s < t.capacity ? (long long) t.keys[s] : -1LL;
+        mn = k < mn ? k : mn;
+        mx = k > mx ? k : mx;
     }
-}
-
-template <int PK, int NV>
-__device__ __forceinline__ bool row_selected(const FastParams& p, const TileRegs<PK, NV>& t, int r) {
-    bool in = (t.flags >> r) & 1;
-    if constexpr (PK == PK_F64_VEC)
-        return in && apply_cmp(p.pred.op, __longlong_as_double((long long) t.pred[r]),
-                               __longlong_as_double((long long) p.pred.scalar.bits));
-    else if constexpr (PK == PK_I64_VEC)
-        return in && apply_cmp(p.pred.op, (int64_t) t.pred[r], (int64_t) p.pred.scalar.bits);
-    else
-        return in;
-}
-
-// Shared-memory key table: returns the slot or -1 (table region full -> spill).
-__device__ __forceinline__ int local_find_or_insert(volatile uint64_t* s_keys, uint64_t key, uint32_t h, uint32_t smask) {
-#pragma unroll 1
-    for (int probe = 0; probe < FA_MAXPROBE; ++probe) {
-        uint64_t k = s_keys[h];
-        if (k == key) return (int) h;
-        if (k == LK_EMPTY) {
-            uint64_t old = atomicCAS(const_cast<unsigned long long*>(reinterpret_cast<volatile unsigned long long*>(s_keys + h)),
-                                     (unsigned long long) LK_EMPTY, (unsigned long long) key);
-            if (old == LK_EMPTY || old == key) return (int) h;
-        }
-        h = (h + 1) & smask;
+    for (int d = 16; d > 0; d >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
     }
-    return -1;
-}
-
-// Row goes straight to the global table (local table full, or sentinel key).
-template <int NV>
-__device__ __forceinline__ void global_row_update(const FastParams& p, uint64_t key, const uint64_t* vals /*NV*/,
-                                                  int64_t row) {
-    int64_t g = gt_find_or_insert<1>(p.table, &key, 0u, hash_key1(key), p.row_limit);
-    if (g < 0) {
-        replay_append(p.replay, row);
-        return;
-    }
-    atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), 1ULL);
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        uint32_t fm = p.val_funcs[v];
-        while (fm) {
-            int fi = __ffs(fm) - 1;
-            fm &= fm - 1;
-            atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g), __longlong_as_double((long long) vals[v]));
-        }
-    }
-}
-
-// Shared memory layout (dynamic):
-//   FS_SHARED_CAS  : keys[S] u64 | sum[NV][S] f64 | cnt[S] u32
-//   FS_WARP_PRIVATE: keys[S] u64 | sum[W][NV][S] f64 | cnt[S] u32
-//   FS_GLOBAL_RED  : keys[S] u64 | gslot[S] u32 (global slot + 1, 0 = not published)
-template <int PK, int NV, int STRAT>
-__global__ void __launch_bounds__(FA_THREADS) agg_fast_kernel(const __grid_constant__ FastParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int S = 1 << p.log2s;
-    const uint32_t smask = S - 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int W = FA_THREADS / 32;
-
-    uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem);
-    double* s_sum = reinterpret_cast<double*>(smem + (size_t) S * 8);
-    const int sum_copies = STRAT == FS_WARP_PRIVATE ? W : (STRAT == FS_SHARED_CAS ? 1 : 0);
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + (size_t) S * 8 + (size_t) sum_copies * NV * S * 8);
-
-    for (int i = tid; i < S; i += FA_THREADS) {
-        s_keys[i] = LK_EMPTY;
-        s_cnt[i] = 0;
-    }
-    for (int i = tid; i < sum_copies * NV * S; i += FA_THREADS) s_sum[i] = 0.0;
-    __syncthreads();
-
-    double* my_sum = STRAT == FS_WARP_PRIVATE ? s_sum + (size_t) warp * NV * S : s_sum;
-    const unsigned lt = lanemask_lt();
-
-    TileRegs<PK, NV> cur, nxt;
-    int64_t tile = blockIdx.x;
-    if (tile < p.num_tiles) load_tile<PK, NV>(p, tile, tid, cur);
-    for (; tile < p.num_tiles; tile += gridDim.x) {
-        const int64_t tnext = tile + gridDim.x;
-        if (tnext < p.num_tiles) load_tile<PK, NV>(p, tnext, tid, nxt);
-
-#pragma unroll
-        for (int r = 0; r < FA_ROWS; ++r) {
-            const bool sel = row_selected<PK, NV>(p, cur, r);
-            const uint64_t key = cur.key[r];
-            int slot = -1;
-            if (sel && key != LK_EMPTY)
-                slot = local_find_or_insert(s_keys, key, (uint32_t) (hash_key1(key) >> 40) & smask, smask);
-            const int64_t row = tile * FA_TILE + (r >> 1) * (FA_THREADS * 2) + tid * 2 + (r & 1);
-
-            if constexpr (STRAT == FS_GLOBAL_RED) {
-                // the local table only caches key -> global slot
-                if (sel) {
-                    int64_t g = -1;
-                    if (slot >= 0) {
-                        uint32_t gs = reinterpret_cast<volatile uint32_t*>(s_cnt)[slot];
-                        if (gs == 0) {
-                            g = gt_find_or_insert<1>(p.table, &key, 0u, hash_key1(key), p.row_limit);
-                            if (g >= 0 && g < 0xfffffffeLL) reinterpret_cast<volatile uint32_t*>(s_cnt)[slot] = (uint32_t) g + 1;
-                        } else {
-                            g = (int64_t) gs - 1;
-                        }
-                    } else {
-                        g = gt_find_or_insert<1>(p.table, &key, 0u, hash_key1(key), p.row_limit);
-                    }
-                    if (g < 0) {
-                        replay_append(p.replay, row);
-                    } else {
-                        atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), 1ULL);
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            uint32_t fm = p.val_funcs[v];
-                            while (fm) {
-                                int fi = __ffs(fm) - 1;
-                                fm &= fm - 1;
-                                atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g),
-                                          __longlong_as_double((long long) cur.val[v][r]));
-                            }
-                        }
-                    }
-                }
-            } else {
-                if (sel && slot < 0) {
-                    uint64_t vals[NV > 0 ? NV : 1];
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) vals[v] = cur.val[v][r];
-                    atomicAdd(p.replay.spilled, 1ULL);
-                    global_row_update<NV>(p, key, vals, row);
-                }
-                const bool upd = sel && slot >= 0;
-                if (upd) atomicAdd(&s_cnt[slot], 1u);
-                if constexpr (NV > 0) {
-                    if constexpr (STRAT == FS_SHARED_CAS) {
-                        if (upd) {
-#pragma unroll
-                            for (int v = 0; v < NV; ++v)
-                                atomicAdd(&my_sum[(size_t) v * S + slot], __longlong_as_double((long long) cur.val[v][r]));
-                        }
-                    } else {
-                        // warp-private accumulators: plain read-modify-write, lanes that hit
-                        // the same slot take turns (rank order)
-                        unsigned peers = __match_any_sync(0xffffffffu, upd ? (unsigned) slot : (0x80000000u | lane));
-                        int mult = upd ? __popc(peers) : 0;
-                        int maxm = __reduce_max_sync(0xffffffffu, mult);
-                        if (maxm <= 1) {
-                            if (upd) {
-#pragma unroll
-                                for (int v = 0; v < NV; ++v)
-                                    my_sum[(size_t) v * S + slot] += __longlong_as_double((long long) cur.val[v][r]);
-                            }
-                        } else {
-                            int rank = __popc(peers & lt);
-                            for (int round = 0; round < maxm; ++round) {
-                                if (upd && rank == round) {
-#pragma unroll
-                                    for (int v = 0; v < NV; ++v)
-                                        my_sum[(size_t) v * S + slot] += __longlong_as_double((long long) cur.val[v][r]);
-                                }
-                                __syncwarp();
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        cur = nxt;
-    }
-
-    if constexpr (STRAT != FS_GLOBAL_RED) {
-        // ---- flush the CTA's partial groups into the global table ----
-        __syncthreads();
-        for (int s = tid; s < S; s += FA_THREADS) {
-            uint64_t key = s_keys[s];
-            if (key == LK_EMPTY) continue;
-            uint32_t c = s_cnt[s];
-            if (c == 0) continue;
-            int64_t g = gt_find_or_insert<1>(p.table, &key, 0u, hash_key1(key), p.table.max_groups);
-            if (g < 0) {  // cannot happen: the host reserves gridDim.x * S free slots
-                atomicAdd(p.replay.lost, (unsigned long long) c);
-                continue;
-            }
-            atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + g), (unsigned long long) c);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                double total = 0.0;
-                for (int w = 0; w < sum_copies; ++w) total += s_sum[((size_t) w * NV + v) * S + s];
-                uint32_t fm = p.val_funcs[v];
-                while (fm) {
-                    int fi = __ffs(fm) - 1;
-                    fm &= fm - 1;
-                    atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[fi] + g), total);
-                }
-            }
-        }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+        atomicMin(out, mn);
+        atomicMax(out + 1, mx);
     }
 }
 
@@ -687,10 +398,17 @@ struct VkAgg {
     uint32_t* list = nullptr;
     uint64_t list_cap = 0;
     int last_path = 0;
-    int strategy = FS_SHARED_CAS;
-    int log2s = 11;
+    // fast (shared-memory) path configuration; env overrides are for tuning runs
+    int fast_log2s = 12;              // CTA key table slots
+    int fast_warps = 8;               // warps per CTA (fewer warps = more groups per warp-private table)
+    bool fast_warps_fixed = false;
+    int fast_direct_policy = 1;       // 1: use direct (key - base) group ids when the key range allows, 0: always hash
+    bool direct_known = false;        // key range of the table measured
+    bool direct_ok = false;
+    uint64_t direct_min = 0, direct_span = 0;  // smallest key (signed order) and max - min
     bool fast_disabled = false;       // cardinality turned out too high for the shared-memory table
-    uint64_t fast_rows = 0, fast_spilled = 0;
+    uint64_t fast_rows_seen = 0, fast_spilled = 0;
+    int64_t fast_groups_seen = 0;
     // optional per-launch timing of the update kernels (bench.py roofline): events are
     // recorded on the launch stream and resolved lazily, so profiling adds no sync
     bool profile = false;
@@ -712,7 +430,7 @@ bool debug_on() {
 #define VK_DBG(...) do { if (debug_on()) { fprintf(stderr, "[vk_agg] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
 constexpr double kMaxLoad = 0.5;
-constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_WORDS = 16;
+constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_RANGE = 8, CTR_WORDS = 16;
 
 int64_t pow2_ceil(int64_t x) {
     int64_t p = 1;
@@ -818,41 +536,47 @@ ReplayList make_replay(VkAgg* a) {
     return l;
 }
 
-size_t fast_smem_bytes(int strat, int nv, int log2s) {
-    size_t S = (size_t) 1 << log2s;
-    int copies = strat == FS_WARP_PRIVATE ? FA_THREADS / 32 : (strat == FS_SHARED_CAS ? 1 : 0);
-    return S * 8 + (size_t) copies * nv * S * 8 + S * 4;
+// Fast-path plan for one update call: which columns are streamed and which accumulator
+// cells a group entry holds.
+struct FastPlan {
+    int key_mode = 0;
+    int n_cols = 0;
+    VkColumn cols[FA_MAX_COLS];
+    int col_mode[FA_MAX_COLS] = {0, 0, 0};
+    int n_cells = 0;
+    FastCell cells[FA_MAX_CELLS];
+    int nw = 2;  // 64-bit words per entry
+    int mode = FM_RUNTIME;
+    bool sumf64 = false;
+};
+
+// Largest number of dense group ids a CTA of `warps` warps can hold.
+int fast_gmax(int log2s, bool direct, int nw, int warps) {
+    const int64_t budget = (int64_t) max_smem_optin() - 256;
+    const int64_t avail = budget - (int64_t) fast_table_bytes(log2s, direct);
+    if (avail <= 0) return 0;
+    int64_t g = avail / ((int64_t) warps * (nw * 8 + 1));
+    g &= ~(int64_t) 15;
+    while (g > 0 && (int64_t) fast_smem_bytes(log2s, direct, (int) g, nw, warps) > budget) g -= 16;
+    if (!direct) {
+        const int64_t cap = ((int64_t) 1 << log2s) / 2;  // keep the key table at most half full
+        if (g > cap) g = cap;
+    }
+    if (g > 0xFFF0) g = 0xFFF0;
+    return (int) g;
 }
 
-template <int PK, int NV>
-int launch_fast_strat(const FastParams& p, int strat, int grid, size_t smem, cudaStream_t s) {
-    auto go = [&](auto kernel) -> int {
-        VK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        kernel<<<grid, FA_THREADS, smem, s>>>(p);
-        VK_CHECK_LAUNCH("agg_fast_kernel");
-        return VK_OK;
-    };
-    switch (strat) {
-        case FS_WARP_PRIVATE: return go(agg_fast_kernel<PK, NV, FS_WARP_PRIVATE>);
-        case FS_GLOBAL_RED: return go(agg_fast_kernel<PK, NV, FS_GLOBAL_RED>);
-        default: return go(agg_fast_kernel<PK, NV, FS_SHARED_CAS>);
-    }
-}
-template <int PK>
-int launch_fast_nv(const FastParams& p, int strat, int grid, size_t smem, cudaStream_t s) {
-    switch (p.n_vals) {
-        case 0: return launch_fast_strat<PK, 0>(p, strat, grid, smem, s);
-        case 1: return launch_fast_strat<PK, 1>(p, strat, grid, smem, s);
-        default: return launch_fast_strat<PK, 2>(p, strat, grid, smem, s);
-    }
-}
-int launch_fast(const FastParams& p, int pk, int strat, int grid, size_t smem, cudaStream_t s) {
-    switch (pk) {
-        case PK_NONE: return launch_fast_nv<PK_NONE>(p, strat, grid, smem, s);
-        case PK_MASK: return launch_fast_nv<PK_MASK>(p, strat, grid, smem, s);
-        case PK_F64_VEC: return launch_fast_nv<PK_F64_VEC>(p, strat, grid, smem, s);
-        case PK_I64_VEC: return launch_fast_nv<PK_I64_VEC>(p, strat, grid, smem, s);
-        default: return launch_fast_nv<PK_GENERIC>(p, strat, grid, smem, s);
+int launch_fast(const FastParams& p, const FastLaunch& l, cudaStream_t s) {
+    switch (l.pk) {
+        case PK_NONE:
+            return l.mode == FM_ALL8 ? launch_fast_none_all8(p, l, s)
+                 : l.mode == FM_KEY4 ? launch_fast_none_key4(p, l, s) : launch_fast_none_rt(p, l, s);
+        case PK_F64_VEC:
+            return l.mode == FM_ALL8 ? launch_fast_f64_all8(p, l, s)
+                 : l.mode == FM_KEY4 ? launch_fast_f64_key4(p, l, s) : launch_fast_f64_rt(p, l, s);
+        case PK_MASK: return launch_fast_mask_rt(p, l, s);
+        case PK_I64_VEC: return launch_fast_i64_rt(p, l, s);
+        default: return launch_fast_gen_rt(p, l, s);
     }
 }
 
@@ -895,10 +619,117 @@ void prof_resolve(VkAgg* a) {
     a->prof_pending.clear();
 }
 
+// Key range of the (single-key) table -> a->direct_*; decides whether later chunks may use
+// direct group ids.  One small scan of the table plus a counter read-back.
+int measure_key_range(VkAgg* a, cudaStream_t s) {
+    const long long init[2] = {INT64_MAX, INT64_MIN};
+    VK_CUDA(cudaMemcpyAsync(a->d_ctr + CTR_RANGE, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    int64_t need = (a->t.capacity + 1 + 255) / 256, capb = (int64_t) sm_count() * 8;
+    agg_key_range_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(a->t, reinterpret_cast<long long*>(a->d_ctr + CTR_RANGE));
+    VK_CHECK_LAUNCH("agg_key_range_kernel");
+    int rc = read_counters(a, s);
+    if (rc != VK_OK) return rc;
+    const long long mn = (long long) a->h_ctr[CTR_RANGE], mx = (long long) a->h_ctr[CTR_RANGE + 1];
+    a->direct_known = true;
+    a->direct_ok = mn <= mx && (uint64_t) mx - (uint64_t) mn < 0xFFF0ULL;
+    a->direct_min = (uint64_t) mn;
+    a->direct_span = (uint64_t) mx - (uint64_t) mn;
+    VK_DBG("key range: min=%lld max=%lld direct_ok=%d", mn, mx, (int) a->direct_ok);
+    return VK_OK;
+}
+
 bool aligned_for_pairs(const VkColumn& c) {
     const int es = dtype_size(c.dtype);
     uintptr_t addr = reinterpret_cast<uintptr_t>(c.data) + (uintptr_t) c.offset * es;
     return (addr % (2 * es)) == 0;
+}
+
+// Can this update run on the shared-memory path?  Single fixed-width key without NULLs,
+// value columns without NULLs, at most FA_MAX_COLS distinct columns / FA_MAX_CELLS cells.
+bool build_fast_plan(const VkAgg* a, const VkColumn* keys, const VkColumn* values, FastPlan* out) {
+    FastPlan pl;
+    if (keys[0].validity != nullptr || !aligned_for_pairs(keys[0])) return false;
+    switch (keys[0].dtype) {
+        case VK_I64: case VK_U64: case VK_F64: pl.key_mode = 0; break;
+        case VK_I32: pl.key_mode = 1; break;
+        case VK_U32: case VK_F32: pl.key_mode = 2; break;
+        default: return false;
+    }
+    for (int f = 0; f < a->n_funcs; ++f) {
+        const FuncSpec& sp = a->specs[f];
+        if (sp.acc == ACC_NONE) continue;
+        const VkColumn& vc = values[f];
+        if (vc.validity != nullptr) return false;
+        if (sp.acc == ACC_COUNT) continue;  // no NULLs: COUNT(col) == COUNT(*)
+        int mode;
+        switch (vc.dtype) {
+            case VK_I64: case VK_U64: case VK_F64: mode = 0; break;
+            case VK_I32: mode = 1; break;
+            case VK_U32: mode = 2; break;
+            case VK_F32: mode = 3; break;
+            default: return false;
+        }
+        if (!aligned_for_pairs(vc)) return false;
+        FastCell cell{};
+        switch (sp.acc) {
+            case ACC_SUM_F64:
+                if (!dtype_is_float(vc.dtype)) return false;
+                cell.op = CELL_ADD_F64;
+                break;
+            case ACC_SUM_I64:
+                if (mode != 1 && mode != 2) return false;
+                cell.op = CELL_ADD_I64;
+                break;
+            case ACC_SUM_I128:
+                if (mode != 0 || dtype_is_float(vc.dtype)) return false;
+                cell.op = CELL_ADD_I128;
+                cell.in_unsigned = sp.in_unsigned;
+                break;
+            case ACC_MAXORD:
+                cell.op = CELL_MAXORD;
+                cell.ord = sp.ord;
+                cell.is_min = sp.is_min;
+                break;
+            default: return false;
+        }
+        int ci = 0;
+        for (; ci < pl.n_cols; ++ci)
+            if (pl.cols[ci].data == vc.data && pl.cols[ci].offset == vc.offset && pl.cols[ci].dtype == vc.dtype) break;
+        if (ci == pl.n_cols) {
+            if (pl.n_cols == FA_MAX_COLS) return false;
+            pl.cols[pl.n_cols] = vc;
+            pl.col_mode[pl.n_cols] = mode;
+            ++pl.n_cols;
+        }
+        cell.col = ci;
+        int k = 0;
+        for (; k < pl.n_cells; ++k) {
+            const FastCell& e = pl.cells[k];
+            if (e.op == cell.op && e.col == cell.col && e.ord == cell.ord && e.is_min == cell.is_min &&
+                e.in_unsigned == cell.in_unsigned) break;
+        }
+        if (k == pl.n_cells) {
+            const int need = cell.op == CELL_ADD_I128 ? 2 : 1;
+            if (pl.n_cells + need > FA_MAX_CELLS) return false;
+            pl.cells[pl.n_cells] = cell;
+            pl.cells[pl.n_cells].func_mask = 0;
+            ++pl.n_cells;
+            if (need == 2) {
+                FastCell hi{};
+                hi.op = CELL_I128_HI;
+                hi.col = ci;
+                pl.cells[pl.n_cells++] = hi;
+            }
+        }
+        pl.cells[k].func_mask |= 1u << f;
+    }
+    pl.nw = pl.n_cells <= 1 ? 2 : 4;
+    bool vals8 = true;
+    for (int v = 0; v < pl.n_cols; ++v) vals8 = vals8 && pl.col_mode[v] == 0;
+    pl.mode = !vals8 ? FM_RUNTIME : (pl.key_mode == 0 ? FM_ALL8 : FM_KEY4);
+    pl.sumf64 = pl.n_cells == 1 && pl.cells[0].op == CELL_ADD_F64 && pl.n_cols == 1;
+    *out = pl;
+    return true;
 }
 
 }  // namespace
@@ -949,12 +780,17 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
         }
         a->specs[f] = s;
     }
-    const char* st = getenv("VINUM_B200_AGG_STRATEGY");
-    if (st) a->strategy = atoi(st);
-    const char* ls = getenv("VINUM_B200_AGG_LOG2S");
-    if (ls) a->log2s = atoi(ls);
-    if (a->log2s < 6) a->log2s = 6;
-    if (a->log2s > 13) a->log2s = 13;
+    if (const char* v = getenv("VINUM_B200_AGG_LOG2S")) a->fast_log2s = atoi(v);
+    if (a->fast_log2s < 8) a->fast_log2s = 8;
+    if (a->fast_log2s > 13) a->fast_log2s = 13;
+    if (const char* v = getenv("VINUM_B200_AGG_WARPS")) {
+        a->fast_warps = atoi(v);
+        a->fast_warps_fixed = true;
+    }
+    if (a->fast_warps < 1) a->fast_warps = 1;
+    if (a->fast_warps > FA_MAX_THREADS / 32) a->fast_warps = FA_MAX_THREADS / 32;
+    if (const char* v = getenv("VINUM_B200_AGG_DIRECT")) a->fast_direct_policy = atoi(v);
+    if (getenv("VINUM_B200_AGG_NOFAST")) a->fast_disabled = true;
     cudaError_t e = cudaMalloc((void**) &a->d_ctr, CTR_WORDS * sizeof(unsigned long long));
     if (e != cudaSuccess) { delete a; return cuda_fail(e, "cudaMalloc(counters)"); }
     cudaMemset(a->d_ctr, 0, CTR_WORDS * sizeof(unsigned long long));
@@ -1097,53 +933,49 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
     }
 
     // ---- path selection ----
-    bool fast = a->n_keys == 1 && !a->fast_disabled && keys[0].validity == nullptr && aligned_for_pairs(keys[0]);
-    int key_mode = 0;
-    if (fast) {
-        switch (keys[0].dtype) {
-            case VK_I64: case VK_U64: case VK_F64: key_mode = 0; break;
-            case VK_I32: key_mode = 1; break;
-            case VK_U32: case VK_F32: key_mode = 2; break;
-            default: fast = false;
-        }
-    }
-    VkColumn fast_vals[FA_MAX_VALS];
-    uint32_t fast_val_funcs[FA_MAX_VALS] = {0, 0};
-    int n_fast_vals = 0;
-    for (int f = 0; fast && f < a->n_funcs; ++f) {
-        const FuncSpec& sp = a->specs[f];
-        if (sp.acc == ACC_NONE) continue;
-        if (values[f].validity != nullptr) { fast = false; break; }
-        if (sp.acc == ACC_COUNT) continue;
-        if (sp.acc != ACC_SUM_F64 || sp.in_dtype != VK_F64 || !aligned_for_pairs(values[f])) { fast = false; break; }
-        int v = 0;
-        for (; v < n_fast_vals; ++v)
-            if (fast_vals[v].data == values[f].data && fast_vals[v].offset == values[f].offset) break;
-        if (v == n_fast_vals) {
-            if (n_fast_vals == FA_MAX_VALS) { fast = false; break; }
-            fast_vals[n_fast_vals++] = values[f];
-        }
-        fast_val_funcs[v] |= 1u << f;
-    }
+    FastPlan plan;
+    bool fast = a->n_keys == 1 && !a->fast_disabled && build_fast_plan(a, keys, values, &plan);
     Pred dpred;
     int pk;
     int rc = make_pred(*pred, n_rows, &dpred, &pk);
     if (rc != VK_OK) return rc;
 
     const int sms = sm_count();
-    int strat = a->strategy;
-    int log2s = a->log2s;
-    size_t smem = fast ? fast_smem_bytes(strat, n_fast_vals, log2s) : 0;
-    while (fast && smem > (size_t) max_smem_optin() && log2s > 6) smem = fast_smem_bytes(strat, n_fast_vals, --log2s);
-    if (fast && smem > (size_t) max_smem_optin()) fast = false;
-    int ctas_per_sm = 1;
-    if (fast) {
-        ctas_per_sm = (int) ((size_t) (max_smem_optin() + 1024) / (smem + 1024));
-        if (ctas_per_sm > 4) ctas_per_sm = 4;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
-    const int fast_grid_max = sms * ctas_per_sm;
-    const int64_t S = (int64_t) 1 << log2s;
+    const int log2s = a->fast_log2s;
+    const bool lean = fast && fast_pk_is_lean(pk) && plan.mode != FM_RUNTIME;
+    int warps = a->fast_warps, gmax = 0;
+    bool direct = false;
+    uint64_t direct_base = 0;
+    size_t smem = 0;
+    auto configure_fast = [&](int64_t groups_hint) {
+        direct = false;
+        const int w_hi = a->fast_warps_fixed ? a->fast_warps : FA_MAX_THREADS / 32;
+        const int w_lo = a->fast_warps_fixed ? a->fast_warps : 2;
+        // direct group ids (key - base): the key range seen so far fits the warp-private tables
+        if (lean && a->fast_direct_policy && a->direct_known && a->direct_ok) {
+            for (int w = w_hi; w >= w_lo; w >>= 1) {
+                const int g = fast_gmax(log2s, true, plan.nw, w);
+                if (g >= 16 && a->direct_span < (uint64_t) g) {
+                    direct = true;
+                    warps = w;
+                    gmax = g;
+                    // centre the observed range in the window so that unseen neighbours still map
+                    direct_base = a->direct_min - ((uint64_t) g - 1 - a->direct_span) / 2;
+                    break;
+                }
+            }
+        }
+        if (!direct) {
+            // fewer warps per CTA leave more shared memory per warp-private table
+            warps = w_hi;
+            while (warps > w_lo && groups_hint + groups_hint / 32 + 8 > fast_gmax(log2s, false, plan.nw, warps)) warps >>= 1;
+            gmax = fast_gmax(log2s, false, plan.nw, warps);
+            if (gmax < 16 || groups_hint > gmax) fast = false;
+        }
+        smem = fast_smem_bytes(log2s, direct, gmax, plan.nw, warps);
+    };
+    if (fast) configure_fast(a->fast_groups_seen);
+    const int fast_grid_max = sms;  // one persistent CTA per SM
 
     // ---- chunk loop: never more rows in flight than (free slots + replay capacity) ----
     uint64_t list_max = (uint64_t) 1 << 28;
@@ -1156,7 +988,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
     int64_t pos = 0;
     while (pos < n_rows) {
         const int64_t remaining = n_rows - pos;
-        const int64_t flush_reserve = (fast && strat != FS_GLOBAL_RED) ? (int64_t) fast_grid_max * S : 0;
+        const int64_t flush_reserve = fast ? (int64_t) fast_grid_max * gmax : 0;
         int64_t free_slots = a->t.max_groups - a->groups_ub - flush_reserve;
         if (free_slots < 1024) {
             // bound is pessimistic: refresh it, then grow if it is real
@@ -1181,7 +1013,9 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             may_fail = true;
         }
         if (chunk > (int64_t) 0xfffff000LL) chunk = (int64_t) 0xfffff000LL;  // row ids in the list are 32-bit
-        if (chunk < remaining) chunk &= ~(int64_t) (FA_TILE - 1);            // keep chunk starts pair-aligned
+        // the first fast chunk is small: it tells the cardinality before the table geometry is fixed
+        if (fast && a->fast_rows_seen == 0 && chunk > ((int64_t) 1 << 22)) chunk = (int64_t) 1 << 22;
+        if (chunk < remaining) chunk &= ~(int64_t) 4095;                      // keep chunk starts pair-aligned
         if (chunk <= 0) return fail(VK_ERR_STATE, "vk_agg_update: internal error: empty chunk");
         VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_LIST, 0, 3 * sizeof(unsigned long long), s));  // list, lost, spilled
         VK_DBG("chunk pos=%lld rows=%lld fast=%d may_fail=%d free_slots=%lld capacity=%lld groups_ub=%lld list_cap=%llu",
@@ -1213,21 +1047,37 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             FastParams fp{};
             fp.pred = dpred;
             fp.key = gp.keys[0];
-            fp.key_mode = key_mode;
-            fp.n_vals = n_fast_vals;
-            for (int v = 0; v < n_fast_vals; ++v) {
-                fp.val[v] = make_col(slice_col(fast_vals[v], pos, chunk));
-                fp.val_funcs[v] = fast_val_funcs[v];
+            fp.key_mode = plan.key_mode;
+            fp.n_cols = plan.n_cols;
+            for (int v = 0; v < plan.n_cols; ++v) {
+                fp.col[v] = make_col(slice_col(plan.cols[v], pos, chunk));
+                fp.col_mode[v] = plan.col_mode[v];
             }
+            fp.n_cells = plan.n_cells;
+            for (int c = 0; c < plan.n_cells; ++c) fp.cell[c] = plan.cells[c];
+            const int threads = warps * 32;
+            const int64_t tile_rows = (int64_t) threads * FA_R;
             fp.n = chunk;
-            fp.num_tiles = (chunk + FA_TILE - 1) / FA_TILE;
+            fp.num_tiles = (chunk + tile_rows - 1) / tile_rows;
             fp.log2s = log2s;
-            fp.row_limit = strat == FS_GLOBAL_RED ? a->t.max_groups : a->t.max_groups - flush_reserve;
+            fp.gmax = gmax;
+            fp.direct_base = direct_base;
+            fp.row_limit = a->t.max_groups - flush_reserve;
             fp.table = a->t;
             fp.replay = gp.replay;
-            int grid = fp.num_tiles < fast_grid_max ? (int) fp.num_tiles : fast_grid_max;
+            FastLaunch fl;
+            fl.pk = pk;
+            fl.nw = plan.nw;
+            fl.mode = lean ? plan.mode : FM_RUNTIME;
+            fl.direct = direct;
+            fl.sumf64 = plan.sumf64;
+            fl.grid = fp.num_tiles < fast_grid_max ? (int) fp.num_tiles : fast_grid_max;
+            fl.threads = threads;
+            fl.smem = smem;
+            VK_DBG("fast launch: pk=%d mode=%d direct=%d base=%lld gmax=%d warps=%d nw=%d smem=%zu", pk, fl.mode, (int) direct,
+                   (long long) direct_base, gmax, warps, plan.nw, smem);
             const int span = prof_begin(a, s, chunk, 1);
-            rc = launch_fast(fp, pk, strat, grid, smem, s);
+            rc = launch_fast(fp, fl, s);
             prof_end(a, s, span);
             if (rc != VK_OK) return rc;
             a->groups_ub += chunk;
@@ -1241,19 +1091,29 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             a->groups_ub += chunk;
         }
 
-        if (may_fail || (fast && a->fast_rows < ((uint64_t) 1 << 22))) {
+        if (may_fail || (fast && a->fast_rows_seen < ((uint64_t) 1 << 22))) {
             // rows may have been deferred (or we are still learning the cardinality)
             rc = read_counters(a, s);
             if (rc != VK_OK) return rc;
             if (fast) {
-                a->fast_rows += (uint64_t) chunk;
-                a->fast_spilled += a->h_ctr[CTR_SPILL];
-                // shared-memory table thrashing: most rows fall through to the global path
-                if (a->fast_rows >= 65536 && a->fast_spilled * 4 > a->fast_rows) a->fast_disabled = true;
+                const uint64_t spill_now = a->h_ctr[CTR_SPILL];
+                a->fast_rows_seen += (uint64_t) chunk;
+                a->fast_spilled += spill_now;
+                a->fast_groups_seen = (int64_t) a->h_ctr[CTR_GROUPS];
+                if (chunk >= 65536 && spill_now * 4 > (uint64_t) chunk) {
+                    // this configuration thrashes: most rows fell through to the global path
+                    if (direct) a->direct_ok = false;   // the key range moved: back to hash mode
+                    else a->fast_disabled = true;       // cardinality too high for shared memory
+                } else if (lean && a->fast_direct_policy && !a->direct_known &&
+                           a->fast_groups_seen <= fast_gmax(log2s, true, plan.nw, 2)) {
+                    rc = measure_key_range(a, s);
+                    if (rc != VK_OK) return rc;
+                }
             }
             rc = run_replay_until_empty(a, gp, chunk, s);
             if (rc != VK_OK) return rc;
             if (a->fast_disabled) fast = false;
+            if (fast) configure_fast(a->fast_groups_seen);
         }
         pos += chunk;
     }

@@ -227,4 +227,20 @@ __device__ __forceinline__ void acc_update_global(const GTable& t, int fi, const
     }
 }
 
+// Rows that could not be inserted (table at its load limit) are appended here and replayed
+// by the host after a grow.
+struct ReplayList {
+    uint32_t* rows;                 // row ids relative to the chunk start
+    unsigned long long* count;      // appended so far
+    unsigned long long* lost;       // rows that did not fit (must stay 0)
+    unsigned long long* spilled;    // rows the fast kernel sent to the global path (statistics)
+    uint64_t capacity;
+};
+
+__device__ __forceinline__ void replay_append(const ReplayList& l, int64_t row) {
+    unsigned long long pos = atomicAdd(l.count, 1ULL);
+    if (pos < l.capacity) l.rows[pos] = (uint32_t) row;
+    else atomicAdd(l.lost, 1ULL);
+}
+
 }  // namespace vk
