@@ -125,7 +125,7 @@ def s_filter():
     return res
 
 
-CFGS = [(1, 0), (0, 0), (1, 4), (0, 4)]
+CFGS = [(1, 0), (0, 0), (1, 8), (0, 8), (1, 4)]
 
 
 def np_groupby(keys, vals, mask):

@@ -29,7 +29,7 @@
 
 namespace vk {
 
-constexpr int FA_MAX_THREADS = 256;
+constexpr int FA_MAX_THREADS = 384;
 constexpr int FA_R = 8;            // rows per thread per tile (four lane-contiguous pairs)
 constexpr int FA_MAX_COLS = 3;     // distinct value columns
 constexpr int FA_MAX_CELLS = 3;    // 64-bit accumulator cells per group (besides COUNT)
@@ -76,11 +76,9 @@ struct FastParams {
     ReplayList replay;
 };
 
-// Dynamic shared memory: [hash mode: keys[S] u64 | gid[S] u16] | per warp { entries[G][NW] u64 | tags[G] u8 }.
+// Dynamic shared memory: [hash mode: keys[S] u64 | gid[S] u16] | per warp entries[G][NW] u64.
 __host__ __device__ inline size_t fast_table_bytes(int log2s, bool direct) { return direct ? 0 : ((size_t) 10 << log2s); }
-__host__ __device__ inline size_t fast_warp_bytes(int gmax, int nw) {
-    return (size_t) gmax * nw * 8 + (((size_t) gmax + 15) & ~(size_t) 15);
-}
+__host__ __device__ inline size_t fast_warp_bytes(int gmax, int nw) { return (size_t) gmax * nw * 8; }
 __host__ __device__ inline size_t fast_smem_bytes(int log2s, bool direct, int gmax, int nw, int warps) {
     return fast_table_bytes(log2s, direct) + fast_warp_bytes(gmax, nw) * warps;
 }
@@ -100,13 +98,8 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ void lds128(uint32_t a, uint32_t (&e)[4]) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]) : "r"(a) : "memory");
@@ -229,50 +222,32 @@ __device__ __forceinline__ uint64_t widen4(uint32_t raw, int mode) {
     if (mode == 3) return (uint64_t) __double_as_longlong((double) __uint_as_float(raw));
     return raw;
 }
-template <int R>
-__device__ __forceinline__ uint64_t q8(const uint4 (&q)[FA_R / 2]) {  // 8-byte element of row R
-    return (R & 1) ? u64_of(q[R >> 1].z, q[R >> 1].w) : u64_of(q[R >> 1].x, q[R >> 1].y);
+// `r` is a compile-time constant after unrolling: these selects fold away.
+__device__ __forceinline__ uint64_t q8(const uint4 (&q)[FA_R / 2], int r) {  // 8-byte element of row r
+    return (r & 1) ? u64_of(q[r >> 1].z, q[r >> 1].w) : u64_of(q[r >> 1].x, q[r >> 1].y);
 }
-template <int R>
-__device__ __forceinline__ uint32_t q4(const uint4 (&q)[FA_R / 2]) {  // 4-byte element of row R
-    return (R & 1) ? q[R >> 1].y : q[R >> 1].x;
+__device__ __forceinline__ uint32_t q4(const uint4 (&q)[FA_R / 2], int r) {  // 4-byte element of row r
+    return (r & 1) ? q[r >> 1].y : q[r >> 1].x;
 }
-template <int MODE, int R>
-__device__ __forceinline__ uint64_t row_key(const FastParams& p, const uint4 (&kq)[FA_R / 2]) {
-    if constexpr (MODE == FM_ALL8) return q8<R>(kq);
+template <int MODE>
+__device__ __forceinline__ uint64_t row_key(const FastParams& p, const uint4 (&kq)[FA_R / 2], int r) {
+    if constexpr (MODE == FM_ALL8) return q8(kq, r);
     else if constexpr (MODE == FM_KEY4) {
-        const uint32_t raw = q4<R>(kq);
+        const uint32_t raw = q4(kq, r);
         const uint32_t hi = p.key_mode == 1 ? (uint32_t) ((int32_t) raw >> 31) : 0u;
         return u64_of(raw, hi);
     } else {
-        if (p.key_mode == 0) return q8<R>(kq);
-        return widen4(q4<R>(kq), p.key_mode == 1 ? 1 : 2);
+        if (p.key_mode == 0) return q8(kq, r);
+        return widen4(q4(kq, r), p.key_mode == 1 ? 1 : 2);
     }
 }
-template <int MODE, int R>
-__device__ __forceinline__ uint64_t row_val(const FastParams& p, int v, const uint4 (&vq)[FA_R / 2]) {
-    if constexpr (MODE != FM_RUNTIME) return q8<R>(vq);
+template <int MODE>
+__device__ __forceinline__ uint64_t row_val(const FastParams& p, int v, const uint4 (&vq)[FA_R / 2], int r) {
+    if constexpr (MODE != FM_RUNTIME) return q8(vq, r);
     else {
-        if (p.col_mode[v] == 0) return q8<R>(vq);
-        return widen4(q4<R>(vq), p.col_mode[v]);
+        if (p.col_mode[v] == 0) return q8(vq, r);
+        return widen4(q4(vq, r), p.col_mode[v]);
     }
-}
-
-// Branch-free comparison: `mask` has one bit per outcome {less, equal, greater, unordered}.
-__host__ __device__ inline uint32_t cmp_outcome_mask(int op) {
-    switch (op) {
-        case VK_EQ: return 0b0010u;
-        case VK_NE: return 0b1101u;
-        case VK_GT: return 0b0100u;
-        case VK_GE: return 0b0110u;
-        case VK_LT: return 0b0001u;
-        default: return 0b0011u;  // LE
-    }
-}
-template <typename T>
-__device__ __forceinline__ bool cmp_by_mask(uint32_t mask, T x, T c) {
-    const uint32_t code = x < c ? 0u : (x == c ? 1u : (x > c ? 2u : 3u));
-    return (mask >> code) & 1u;
 }
 
 __device__ __forceinline__ uint64_t cell_apply(const FastCell& c, uint64_t cur, uint64_t v) {
@@ -346,133 +321,213 @@ static __device__ __noinline__ void fast_global_row(const FastParams& p, uint64_
     fast_global_update(p, g, 1, w);
 }
 
-// Kernel context shared by the per-row steps.
+// Kernel context shared by the per-tile steps.
 struct FastCtx {
     uint32_t a_keys, a_gid;  // shared key table (hash mode)
-    uint32_t a_ent, a_tag;   // this warp's entries / tags
+    uint32_t a_ent;          // this warp's entries
     uint32_t smask, hshift;
-    uint32_t opmask;
+    int op;                  // VkCmpOp of the fused predicate
     uint64_t pscalar;
-    int lane;
+    uint32_t lane;
 };
 
-// NW = 64-bit words per entry (word 0 = COUNT, words 1.. = cells): 2 or 4.
+// Entry layout (NW 64-bit words, NW = 2 or 4):
+//   word 0 = COUNT (low 32 bits: one warp in one launch) | arbitration tag (high 32 bits)
+//   word 1.. = accumulator cells
 // SUMF64: the entry's single cell is a float64 SUM (no run-time cell dispatch).
-template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, int R>
-__device__ __forceinline__ void fast_row(const FastParams& p, const FastCtx& cx, const RawTile<PK, NV>& t, uint8_t* smem,
-                                         uint32_t* s_ngroups, int64_t row, uint32_t& spilled) {
+//
+// A tile is processed in two phases.  Phase 1 is pure register work for all FA_R rows
+// (decode, predicate, group id or first table probe) that the compiler interleaves freely.
+// Phase 2 is one short critical section per row: store the lane id as the entry's tag,
+// sync the warp, load the whole entry (tag + COUNT + cell in one LDS.128); the lane that
+// reads its own tag back applies the row and stores the entry, the others go round again.
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64>
+__device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx, const RawTile<PK, NV>& t, uint8_t* smem,
+                                          uint32_t* s_ngroups, int64_t row0, int nthreads, uint32_t& spilled) {
     constexpr int NCMAX = NW - 1;
-    // ---- predicate (registers only) ----
-    bool act = (t.flags >> R) & 1u;
-    if constexpr (PK == PK_F64_VEC)
-        act = act && cmp_by_mask(cx.opmask, __longlong_as_double((long long) q8<R>(t.pq)), __longlong_as_double((long long) cx.pscalar));
-    else if constexpr (PK == PK_I64_VEC)
-        act = act && cmp_by_mask(cx.opmask, (int64_t) q8<R>(t.pq), (int64_t) cx.pscalar);
-    else if constexpr (PK == PK_MASK)
-        act = act && ((t.pq[R >> 1].x >> (8 * (R & 1))) & 0xffu);
-    const uint64_t key = row_key<MODE, R>(p, t.kq);
+    uint64_t key[FA_R];
+    uint32_t ea[FA_R];       // shared address of the row's entry
+    uint32_t todo = 0, spill = 0;
 
-    // ---- key -> dense group id ----
-    uint32_t gid = GID_SPILL;
-    bool todo;
+    // ---- phase 1: predicate and group id ----
+    uint32_t okmask = (1u << FA_R) - 1u;
+    if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
+        // one compare per row: the operator is uniform, so branch on it once per tile
+        okmask = 0;
+#define VK_PRED_ROWS(OP)                                                                                  \
+        _Pragma("unroll") for (int r = 0; r < FA_R; ++r) {                                                \
+            bool ok;                                                                                      \
+            if constexpr (PK == PK_F64_VEC)                                                               \
+                ok = __longlong_as_double((long long) q8(t.pq, r)) OP __longlong_as_double((long long) cx.pscalar); \
+            else                                                                                          \
+                ok = (int64_t) q8(t.pq, r) OP (int64_t) cx.pscalar;                                       \
+            okmask |= (uint32_t) ok << r;                                                                 \
+        }
+        switch (cx.op) {
+            case VK_EQ: VK_PRED_ROWS(==) break;
+            case VK_NE: VK_PRED_ROWS(!=) break;
+            case VK_GT: VK_PRED_ROWS(>) break;
+            case VK_GE: VK_PRED_ROWS(>=) break;
+            case VK_LT: VK_PRED_ROWS(<) break;
+            default: VK_PRED_ROWS(<=) break;
+        }
+#undef VK_PRED_ROWS
+    } else if constexpr (PK == PK_MASK) {
+        okmask = 0;
+#pragma unroll
+        for (int r = 0; r < FA_R; ++r)
+            okmask |= (uint32_t) (((t.pq[r >> 1].x >> (8 * (r & 1))) & 0xffu) != 0) << r;
+    }
+    const uint32_t act = t.flags & okmask;
+#pragma unroll
+    for (int r = 0; r < FA_R; ++r) key[r] = row_key<MODE>(p, t.kq, r);
     if constexpr (DIRECT) {
-        const uint64_t d = key - p.direct_base;
-        todo = act && d < (uint64_t) (uint32_t) p.gmax;
-        gid = (uint32_t) d;
+        uint32_t inmask = 0;
+        const uint32_t g32 = (uint32_t) p.gmax;
+#pragma unroll
+        for (int r = 0; r < FA_R; ++r) {
+            const uint64_t d = key[r] - p.direct_base;
+            const uint32_t dl = (uint32_t) d, dh = (uint32_t) (d >> 32);
+            inmask |= (uint32_t) ((dh == 0u) & (dl < g32)) << r;
+            ea[r] = cx.a_ent + dl * (NW * 8);
+        }
+        todo = act & inmask;
+        spill = act & ~inmask;
     } else {
-        uint32_t h = fast_hash32(key) >> cx.hshift;
-        bool pend = act && key != LK_EMPTY;  // the sentinel itself cannot live in the table
-        for (int it = 0; __any_sync(0xffffffffu, pend); ++it) {
-            if (it >= FA_MAXPROBE) break;     // table region exhausted: leave these rows to the global table
-            if (pend) {
-                const uint64_t k = lds64(cx.a_keys + h * 8);
-                const uint32_t g = lds16(cx.a_gid + h * 2);
-                if (k == key) {
-                    if (g != GID_PENDING) {
-                        gid = g;
-                        pend = false;
-                    }
-                } else if (k == LK_EMPTY) {
-                    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(smem) + h,
-                                                             (unsigned long long) LK_EMPTY, (unsigned long long) key);
-                    if (old == LK_EMPTY) {
-                        uint32_t ng = atomicAdd(s_ngroups, 1u);
-                        if (ng >= (uint32_t) p.gmax) ng = GID_SPILL;
-                        sts16(cx.a_gid + h * 2, ng);
-                        gid = ng;
-                        pend = false;
-                    } else if (old != key) {
-                        h = (h + 1) & cx.smask;
-                    }  // old == key: another lane just claimed it; read its id next round
+        uint32_t h[FA_R], gid[FA_R];
+        uint32_t pend = 0;
+        // first probe of every row, all loads in flight together
+#pragma unroll
+        for (int r = 0; r < FA_R; ++r) {
+            h[r] = fast_hash32(key[r]) >> cx.hshift;
+            gid[r] = GID_SPILL;
+            if ((act >> r) & 1u) {
+                if (key[r] == LK_EMPTY) {
+                    spill |= 1u << r;  // the sentinel itself cannot live in the table
                 } else {
-                    h = (h + 1) & cx.smask;
+                    const uint64_t k = lds64(cx.a_keys + h[r] * 8);
+                    const uint32_t g = lds16(cx.a_gid + h[r] * 2);
+                    if (k == key[r] && g != GID_PENDING) gid[r] = g;
+                    else pend |= 1u << r;
                 }
             }
         }
-        todo = act && gid < (uint32_t) p.gmax;
-    }
-    const bool spill = act && !todo;
-
-    // ---- accumulate into the warp-private entry; same-group lanes arbitrate by tag ----
-    while (__any_sync(0xffffffffu, todo)) {
-        if (todo) sts8(cx.a_tag + gid, (uint32_t) cx.lane);
-        __syncwarp();
-        if (todo && lds8(cx.a_tag + gid) == (uint32_t) cx.lane) {
-            todo = false;
-            const uint32_t ea = cx.a_ent + gid * (NW * 8);
-            uint32_t e[4];
-            lds128(ea, e);
-            e[0] += 1;  // COUNT: 32 bits are enough for one warp in one launch
-            if constexpr (SUMF64) {
-                const double s = __hiloint2double((int) e[3], (int) e[2]) +
-                                 __longlong_as_double((long long) row_val<MODE, R>(p, 0, t.vq[0]));
-                e[2] = (uint32_t) __double2loint(s);
-                e[3] = (uint32_t) __double2hiint(s);
-                sts128(ea, e);
-            } else {
-                uint32_t f[4] = {0, 0, 0, 0};
-                if constexpr (NW == 4) lds128(ea + 16, f);
-                uint64_t w[3] = {u64_of(e[2], e[3]), u64_of(f[0], f[1]), u64_of(f[2], f[3])};
+        // rows whose first probe did not hit: walk / insert, warp-convergent
+        for (int it = 0; __any_sync(0xffffffffu, pend != 0); ++it) {
+            if (it >= FA_MAXPROBE) {  // table region exhausted: leave these rows to the global table
+                spill |= pend;
+                pend = 0;
+                break;
+            }
 #pragma unroll
-                for (int c = 0; c < NCMAX; ++c) {
-                    if (c < p.n_cells) {
-                        const FastCell cell = p.cell[c];
-                        if (cell.op != CELL_I128_HI) {
-                            uint64_t v = 0;
-#pragma unroll
-                            for (int k = 0; k < NV; ++k)
-                                if (cell.col == k) v = row_val<MODE, R>(p, k, t.vq[k]);
-                            const uint64_t old = w[c];
-                            const uint64_t nv = cell_apply(cell, old, v);
-                            w[c] = nv;
-                            if (NW == 4 && cell.op == CELL_ADD_I128 && c + 1 < NCMAX) {
-                                const uint64_t ext = (!cell.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL;
-                                w[c + 1 < 3 ? c + 1 : 2] += ext + (nv < old ? 1ULL : 0ULL);
+            for (int r = 0; r < FA_R; ++r) {
+                if (__any_sync(0xffffffffu, (pend >> r) & 1u)) {
+                    if ((pend >> r) & 1u) {
+                        const uint64_t k = lds64(cx.a_keys + h[r] * 8);
+                        const uint32_t g = lds16(cx.a_gid + h[r] * 2);
+                        if (k == key[r]) {
+                            if (g != GID_PENDING) {
+                                gid[r] = g;
+                                pend &= ~(1u << r);
                             }
+                        } else if (k == LK_EMPTY) {
+                            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(smem) + h[r],
+                                                                     (unsigned long long) LK_EMPTY, (unsigned long long) key[r]);
+                            if (old == LK_EMPTY) {
+                                uint32_t ng = atomicAdd(s_ngroups, 1u);
+                                if (ng >= (uint32_t) p.gmax) ng = GID_SPILL;
+                                sts16(cx.a_gid + h[r] * 2, ng);
+                                gid[r] = ng;
+                                pend &= ~(1u << r);
+                            } else if (old != key[r]) {
+                                h[r] = (h[r] + 1) & cx.smask;
+                            }  // old == key: another lane just claimed it; read its id next round
+                        } else {
+                            h[r] = (h[r] + 1) & cx.smask;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < FA_R; ++r) {
+            ea[r] = cx.a_ent + gid[r] * (NW * 8);
+            if (((act & ~spill) >> r) & 1u) {
+                if (gid[r] < (uint32_t) p.gmax) todo |= 1u << r;
+                else spill |= 1u << r;
+            }
+        }
+    }
+
+    // ---- phase 2: accumulate into the warp-private entries, one row at a time ----
+#pragma unroll
+    for (int r = 0; r < FA_R; ++r) {
+        bool mine = (todo >> r) & 1u;
+        while (__any_sync(0xffffffffu, mine)) {
+            if (mine) sts32(ea[r] + 4, cx.lane);
+            __syncwarp();
+            if (mine) {
+                uint32_t e[4];
+                lds128(ea[r], e);
+                if (e[1] == cx.lane) {
+                    mine = false;
+                    e[0] += 1;
+                    if constexpr (SUMF64) {
+                        const double sum = __hiloint2double((int) e[3], (int) e[2]) +
+                                           __longlong_as_double((long long) row_val<MODE>(p, 0, t.vq[0], r));
+                        e[2] = (uint32_t) __double2loint(sum);
+                        e[3] = (uint32_t) __double2hiint(sum);
+                        sts128(ea[r], e);
+                    } else {
+                        uint32_t f[4] = {0, 0, 0, 0};
+                        if constexpr (NW == 4) lds128(ea[r] + 16, f);
+                        uint64_t w[3] = {u64_of(e[2], e[3]), u64_of(f[0], f[1]), u64_of(f[2], f[3])};
+#pragma unroll
+                        for (int c = 0; c < NCMAX; ++c) {
+                            if (c < p.n_cells) {
+                                const FastCell cell = p.cell[c];
+                                if (cell.op != CELL_I128_HI) {
+                                    uint64_t v = 0;
+#pragma unroll
+                                    for (int k = 0; k < NV; ++k)
+                                        if (cell.col == k) v = row_val<MODE>(p, k, t.vq[k], r);
+                                    const uint64_t old = w[c];
+                                    const uint64_t nv = cell_apply(cell, old, v);
+                                    w[c] = nv;
+                                    if (NW == 4 && cell.op == CELL_ADD_I128 && c + 1 < NCMAX) {
+                                        const uint64_t ext = (!cell.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL;
+                                        w[c + 1 < 3 ? c + 1 : 2] += ext + (nv < old ? 1ULL : 0ULL);
+                                    }
+                                }
+                            }
+                        }
+                        e[2] = (uint32_t) w[0];
+                        e[3] = (uint32_t) (w[0] >> 32);
+                        sts128(ea[r], e);
+                        if constexpr (NW == 4) {
+                            f[0] = (uint32_t) w[1]; f[1] = (uint32_t) (w[1] >> 32);
+                            f[2] = (uint32_t) w[2]; f[3] = (uint32_t) (w[2] >> 32);
+                            sts128(ea[r] + 16, f);
                         }
                     }
                 }
-                e[2] = (uint32_t) w[0];
-                e[3] = (uint32_t) (w[0] >> 32);
-                sts128(ea, e);
-                if constexpr (NW == 4) {
-                    f[0] = (uint32_t) w[1]; f[1] = (uint32_t) (w[1] >> 32);
-                    f[2] = (uint32_t) w[2]; f[3] = (uint32_t) (w[2] >> 32);
-                    sts128(ea + 16, f);
-                }
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 
     // ---- rows the CTA table could not take: global table, off the hot path ----
-    if (__any_sync(0xffffffffu, spill)) {
-        if (spill) {
-            uint64_t v[FA_MAX_COLS] = {0, 0, 0};
+    if (__any_sync(0xffffffffu, spill != 0)) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) v[k] = row_val<MODE, R>(p, k, t.vq[k]);
-            ++spilled;
-            fast_global_row(p, key, v[0], v[1], v[2], row);
+        for (int r = 0; r < FA_R; ++r) {
+            if ((spill >> r) & 1u) {
+                uint64_t v[FA_MAX_COLS] = {0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < NV; ++k) v[k] = row_val<MODE>(p, k, t.vq[k], r);
+                ++spilled;
+                fast_global_row(p, key[r], v[0], v[1], v[2], row0 + (int64_t) (r >> 1) * (nthreads * 2) + (r & 1));
+            }
         }
         __syncwarp();
     }
@@ -495,12 +550,11 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
     cx.a_keys = a_base;
     cx.a_gid = a_base + (uint32_t) S * 8;
     cx.a_ent = a_warp0 + (uint32_t) warp * warp_bytes;
-    cx.a_tag = cx.a_ent + (uint32_t) G * NW * 8;
     cx.smask = (uint32_t) S - 1u;
     cx.hshift = 32 - p.log2s;
-    cx.opmask = cmp_outcome_mask(p.pred.op);
+    cx.op = p.pred.op;
     cx.pscalar = p.pred.scalar.bits;
-    cx.lane = lane;
+    cx.lane = (uint32_t) lane;
 
     {
         if constexpr (!DIRECT) {
@@ -527,13 +581,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
         else load_tile_tail<PK, NV, MODE>(p, tile, tid, nthreads, t);
     };
     auto process = [&](int64_t tile, const RawTile<PK, NV>& t) {
-        const int64_t row0 = tile * tile_rows + tid * 2;
-#define VK_FAST_ROW(RR)                                                                                         \
-        fast_row<PK, NV, NW, MODE, DIRECT, SUMF64, RR>(p, cx, t, smem, &s_ngroups,                               \
-                                                       row0 + (int64_t) (RR >> 1) * (nthreads * 2) + (RR & 1), spilled);
-        VK_FAST_ROW(0) VK_FAST_ROW(1) VK_FAST_ROW(2) VK_FAST_ROW(3)
-        VK_FAST_ROW(4) VK_FAST_ROW(5) VK_FAST_ROW(6) VK_FAST_ROW(7)
-#undef VK_FAST_ROW
+        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64>(p, cx, t, smem, &s_ngroups, tile * tile_rows + tid * 2, nthreads, spilled);
     };
 
     // two register tiles, explicitly alternated: no copy ever waits on a load

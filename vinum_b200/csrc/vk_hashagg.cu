@@ -400,7 +400,7 @@ struct VkAgg {
     int last_path = 0;
     // fast (shared-memory) path configuration; env overrides are for tuning runs
     int fast_log2s = 12;              // CTA key table slots
-    int fast_warps = 8;               // warps per CTA (fewer warps = more groups per warp-private table)
+    int fast_warps = FA_MAX_THREADS / 32;  // warps per CTA (fewer warps = more groups per warp-private table)
     bool fast_warps_fixed = false;
     int fast_direct_policy = 1;       // 1: use direct (key - base) group ids when the key range allows, 0: always hash
     bool direct_known = false;        // key range of the table measured
@@ -555,7 +555,7 @@ int fast_gmax(int log2s, bool direct, int nw, int warps) {
     const int64_t budget = (int64_t) max_smem_optin() - 256;
     const int64_t avail = budget - (int64_t) fast_table_bytes(log2s, direct);
     if (avail <= 0) return 0;
-    int64_t g = avail / ((int64_t) warps * (nw * 8 + 1));
+    int64_t g = avail / ((int64_t) warps * (nw * 8));
     g &= ~(int64_t) 15;
     while (g > 0 && (int64_t) fast_smem_bytes(log2s, direct, (int) g, nw, warps) > budget) g -= 16;
     if (!direct) {
@@ -951,9 +951,10 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         direct = false;
         const int w_hi = a->fast_warps_fixed ? a->fast_warps : FA_MAX_THREADS / 32;
         const int w_lo = a->fast_warps_fixed ? a->fast_warps : 2;
+        auto next_w = [](int w) { return w > 8 ? w - 2 : w >> 1; };  // 12, 10, 8, 4, 2
         // direct group ids (key - base): the key range seen so far fits the warp-private tables
         if (lean && a->fast_direct_policy && a->direct_known && a->direct_ok) {
-            for (int w = w_hi; w >= w_lo; w >>= 1) {
+            for (int w = w_hi; w >= w_lo; w = next_w(w)) {
                 const int g = fast_gmax(log2s, true, plan.nw, w);
                 if (g >= 16 && a->direct_span < (uint64_t) g) {
                     direct = true;
@@ -968,7 +969,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         if (!direct) {
             // fewer warps per CTA leave more shared memory per warp-private table
             warps = w_hi;
-            while (warps > w_lo && groups_hint + groups_hint / 32 + 8 > fast_gmax(log2s, false, plan.nw, warps)) warps >>= 1;
+            while (warps > w_lo && groups_hint + groups_hint / 32 + 8 > fast_gmax(log2s, false, plan.nw, warps)) warps = next_w(warps);
             gmax = fast_gmax(log2s, false, plan.nw, warps);
             if (gmax < 16 || groups_hint > gmax) fast = false;
         }
