@@ -125,9 +125,14 @@ struct RawTile {
 };
 
 // Row pairs are lane-contiguous: pair j of thread t covers rows base + j*2*threads + 2t, +1,
-// so every 8-byte column is read with one 16-byte load per lane per pair.
+// so every 8-byte column is read with one 16-byte load per lane per pair.  Only complete
+// tiles are loaded here (the host sends the ragged tail of a chunk to agg_general_kernel).
+//
+// The key / predicate registers of a tile are dead after phase 1 and the value registers of
+// pair j after its two rows have been accumulated, so each is refilled with the tile after
+// next as soon as it dies: every load has almost two tile periods to land.
 template <int PK, int NV, int MODE>
-__device__ __forceinline__ void load_tile_full(const FastParams& p, int64_t tile, int tid, int nthreads, RawTile<PK, NV>& t) {
+__device__ __forceinline__ void load_tile_keys(const FastParams& p, int64_t tile, int tid, int nthreads, RawTile<PK, NV>& t) {
     const int64_t r0 = tile * (int64_t) (nthreads * FA_R) + tid * 2;
     const int64_t jstride = (int64_t) nthreads * 2;
     t.flags = (1u << FA_R) - 1u;
@@ -141,16 +146,6 @@ __device__ __forceinline__ void load_tile_full(const FastParams& p, int64_t tile
             t.kq[j].x = q.x;
             t.kq[j].y = q.y;
         }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            if (MODE != FM_RUNTIME || p.col_mode[v] == 0) {
-                t.vq[v][j] = ldg_stream16(p.col[v].data + r * 8);
-            } else {
-                const uint2 q = ldg_stream8(p.col[v].data + r * 4);
-                t.vq[v][j].x = q.x;
-                t.vq[v][j].y = q.y;
-            }
-        }
         if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
             t.pq[j] = ldg_stream16(p.pred.col.data + r * 8);
         } else if constexpr (PK == PK_MASK) {
@@ -163,55 +158,17 @@ __device__ __forceinline__ void load_tile_full(const FastParams& p, int64_t tile
         }
     }
 }
-
-// The last, partial tile of a chunk: row-wise loads, out-of-range rows flagged off.
 template <int PK, int NV, int MODE>
-__device__ __forceinline__ void load_tile_tail(const FastParams& p, int64_t tile, int tid, int nthreads, RawTile<PK, NV>& t) {
-    const int64_t r0 = tile * (int64_t) (nthreads * FA_R) + tid * 2;
-    const int64_t jstride = (int64_t) nthreads * 2;
-    t.flags = 0;
-    auto ld_elem = [](const Col& c, bool eight, int64_t i, uint32_t& lo, uint32_t& hi) {
-        if (eight) {
-            const uint64_t v = reinterpret_cast<const uint64_t*>(c.data)[i];
-            lo = (uint32_t) v;
-            hi = (uint32_t) (v >> 32);
+__device__ __forceinline__ void load_tile_vals(const FastParams& p, int64_t tile, int tid, int nthreads, RawTile<PK, NV>& t, int j) {
+    const int64_t r = tile * (int64_t) (nthreads * FA_R) + tid * 2 + (int64_t) j * (nthreads * 2);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        if (MODE != FM_RUNTIME || p.col_mode[v] == 0) {
+            t.vq[v][j] = ldg_stream16(p.col[v].data + r * 8);
         } else {
-            lo = reinterpret_cast<const uint32_t*>(c.data)[i];
-            hi = 0;
-        }
-    };
-#pragma unroll
-    for (int j = 0; j < FA_R / 2; ++j) {
-        t.kq[j] = make_uint4(0, 0, 0, 0);
-        if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC || PK == PK_MASK) t.pq[j] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) t.vq[v][j] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const int64_t r = r0 + j * jstride + hf;
-            if (r >= p.n) continue;
-            uint32_t lo, hi;
-            const bool k8 = MODE == FM_ALL8 || (MODE == FM_RUNTIME && p.key_mode == 0);
-            ld_elem(p.key, k8, r, lo, hi);
-            if (k8) { if (hf) { t.kq[j].z = lo; t.kq[j].w = hi; } else { t.kq[j].x = lo; t.kq[j].y = hi; } }
-            else { if (hf) t.kq[j].y = lo; else t.kq[j].x = lo; }
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const bool v8 = MODE != FM_RUNTIME || p.col_mode[v] == 0;
-                ld_elem(p.col[v], v8, r, lo, hi);
-                if (v8) { if (hf) { t.vq[v][j].z = lo; t.vq[v][j].w = hi; } else { t.vq[v][j].x = lo; t.vq[v][j].y = hi; } }
-                else { if (hf) t.vq[v][j].y = lo; else t.vq[v][j].x = lo; }
-            }
-            bool on = true;
-            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) {
-                ld_elem(p.pred.col, true, r, lo, hi);
-                if (hf) { t.pq[j].z = lo; t.pq[j].w = hi; } else { t.pq[j].x = lo; t.pq[j].y = hi; }
-            } else if constexpr (PK == PK_MASK) {
-                t.pq[j].x |= (uint32_t) p.pred.mask[r] << (8 * hf);
-            } else if constexpr (PK == PK_GENERIC) {
-                on = pred_row_generic(p.pred, r);
-            }
-            if (on) t.flags |= 1u << (2 * j + hf);
+            const uint2 q = ldg_stream8(p.col[v].data + r * 4);
+            t.vq[v][j].x = q.x;
+            t.vq[v][j].y = q.y;
         }
     }
 }
@@ -342,8 +299,9 @@ struct FastCtx {
 // sync the warp, load the whole entry (tag + COUNT + cell in one LDS.128); the lane that
 // reads its own tag back applies the row and stores the entry, the others go round again.
 template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64>
-__device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx, const RawTile<PK, NV>& t, uint8_t* smem,
-                                          uint32_t* s_ngroups, int64_t row0, int nthreads, uint32_t& spilled) {
+__device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx, RawTile<PK, NV>& t, uint8_t* smem,
+                                          uint32_t* s_ngroups, int64_t row0, int tid, int nthreads, int64_t refill_tile,
+                                          uint32_t& spilled) {
     constexpr int NCMAX = NW - 1;
     uint64_t key[FA_R];
     uint32_t ea[FA_R];       // shared address of the row's entry
@@ -460,6 +418,24 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
         }
     }
 
+    // ---- rows the CTA table could not take: global table, off the hot path ----
+    if (__any_sync(0xffffffffu, spill != 0)) {
+#pragma unroll
+        for (int r = 0; r < FA_R; ++r) {
+            if ((spill >> r) & 1u) {
+                uint64_t v[FA_MAX_COLS] = {0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < NV; ++k) v[k] = row_val<MODE>(p, k, t.vq[k], r);
+                ++spilled;
+                fast_global_row(p, key[r], v[0], v[1], v[2], row0 + (int64_t) (r >> 1) * (nthreads * 2) + (r & 1));
+            }
+        }
+        __syncwarp();
+    }
+
+    // the key / predicate registers are dead: refill them with the tile after next
+    if (refill_tile >= 0) load_tile_keys<PK, NV, MODE>(p, refill_tile, tid, nthreads, t);
+
     // ---- phase 2: accumulate into the warp-private entries, one row at a time ----
 #pragma unroll
     for (int r = 0; r < FA_R; ++r) {
@@ -515,21 +491,8 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
             }
             __syncwarp();
         }
-    }
-
-    // ---- rows the CTA table could not take: global table, off the hot path ----
-    if (__any_sync(0xffffffffu, spill != 0)) {
-#pragma unroll
-        for (int r = 0; r < FA_R; ++r) {
-            if ((spill >> r) & 1u) {
-                uint64_t v[FA_MAX_COLS] = {0, 0, 0};
-#pragma unroll
-                for (int k = 0; k < NV; ++k) v[k] = row_val<MODE>(p, k, t.vq[k], r);
-                ++spilled;
-                fast_global_row(p, key[r], v[0], v[1], v[2], row0 + (int64_t) (r >> 1) * (nthreads * 2) + (r & 1));
-            }
-        }
-        __syncwarp();
+        // both rows of a pair done: its value registers are dead, refill them
+        if ((r & 1) && refill_tile >= 0) load_tile_vals<PK, NV, MODE>(p, refill_tile, tid, nthreads, t, r >> 1);
     }
 }
 
@@ -574,27 +537,27 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
 
     uint32_t spilled = 0;
     const int64_t tile_rows = (int64_t) nthreads * FA_R;
-    const int64_t full_tiles = p.n / tile_rows;  // tiles [0, full_tiles) are complete
 
-    auto load = [&](int64_t tile, RawTile<PK, NV>& t) {
-        if (tile < full_tiles) load_tile_full<PK, NV, MODE>(p, tile, tid, nthreads, t);
-        else load_tile_tail<PK, NV, MODE>(p, tile, tid, nthreads, t);
-    };
-    auto process = [&](int64_t tile, const RawTile<PK, NV>& t) {
-        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64>(p, cx, t, smem, &s_ngroups, tile * tile_rows + tid * 2, nthreads, spilled);
-    };
-
-    // two register tiles, explicitly alternated: no copy ever waits on a load
+    // two register tiles, explicitly alternated, each refilled piecewise while it is processed
     RawTile<PK, NV> ta, tb;
     int64_t tile = blockIdx.x;
     const int64_t stride = gridDim.x;
-    if (tile < p.num_tiles) load(tile, ta);
+    auto load_all = [&](int64_t tl, RawTile<PK, NV>& t) {
+        load_tile_keys<PK, NV, MODE>(p, tl, tid, nthreads, t);
+#pragma unroll
+        for (int j = 0; j < FA_R / 2; ++j) load_tile_vals<PK, NV, MODE>(p, tl, tid, nthreads, t, j);
+    };
+    auto process = [&](int64_t tl, RawTile<PK, NV>& t) {
+        const int64_t nx = tl + 2 * stride;
+        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64>(p, cx, t, smem, &s_ngroups, tl * tile_rows + tid * 2, tid, nthreads,
+                                                    nx < p.num_tiles ? nx : (int64_t) -1, spilled);
+    };
+    if (tile < p.num_tiles) load_all(tile, ta);
+    if (tile + stride < p.num_tiles) load_all(tile + stride, tb);
     while (tile < p.num_tiles) {
-        if (tile + stride < p.num_tiles) load(tile + stride, tb);
         process(tile, ta);
         tile += stride;
         if (tile >= p.num_tiles) break;
-        if (tile + stride < p.num_tiles) load(tile + stride, ta);
         process(tile, tb);
         tile += stride;
     }

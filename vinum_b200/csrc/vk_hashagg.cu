@@ -59,6 +59,7 @@ struct GenParams {
     FuncSpec specs[VK_AGG_MAX_FUNCS];
     Col vals[VK_AGG_MAX_FUNCS];
     int64_t n;
+    int64_t row_begin;               // first row to process (the fast path leaves its ragged tail here)
     const uint32_t* row_list;        // replay: process these rows only
     const unsigned long long* row_list_count;
     GTable table;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) agg_general_kernel(const __grid_constant_
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     const bool replaying = p.row_list != nullptr;
     const int64_t total = replaying ? (int64_t) *p.row_list_count : p.n;
-    for (int64_t it = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
+    for (int64_t it = (replaying ? 0 : p.row_begin) + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
         const int64_t i = replaying ? (int64_t) p.row_list[it] : it;
         if (!replaying && !pred_row(p.pred, i)) continue;  // listed rows already passed the predicate
         uint64_t kv[VK_AGG_MAX_KEYS];
@@ -1016,7 +1017,12 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         if (chunk > (int64_t) 0xfffff000LL) chunk = (int64_t) 0xfffff000LL;  // row ids in the list are 32-bit
         // the first fast chunk is small: it tells the cardinality before the table geometry is fixed
         if (fast && a->fast_rows_seen == 0 && chunk > ((int64_t) 1 << 22)) chunk = (int64_t) 1 << 22;
-        if (chunk < remaining) chunk &= ~(int64_t) 4095;                      // keep chunk starts pair-aligned
+        if (chunk < remaining) {
+            // chunk starts stay pair-aligned, and fast chunks are whole tiles (only the last one has a tail)
+            const int64_t unit = fast ? (int64_t) warps * 32 * FA_R : 4096;
+            if (chunk >= unit) chunk -= chunk % unit;
+            else chunk &= ~(int64_t) 1;
+        }
         if (chunk <= 0) return fail(VK_ERR_STATE, "vk_agg_update: internal error: empty chunk");
         VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_LIST, 0, 3 * sizeof(unsigned long long), s));  // list, lost, spilled
         VK_DBG("chunk pos=%lld rows=%lld fast=%d may_fail=%d free_slots=%lld capacity=%lld groups_ub=%lld list_cap=%llu",
@@ -1059,7 +1065,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             const int threads = warps * 32;
             const int64_t tile_rows = (int64_t) threads * FA_R;
             fp.n = chunk;
-            fp.num_tiles = (chunk + tile_rows - 1) / tile_rows;
+            fp.num_tiles = chunk / tile_rows;  // complete tiles; the ragged tail goes to the general kernel below
             fp.log2s = log2s;
             fp.gmax = gmax;
             fp.direct_base = direct_base;
@@ -1077,10 +1083,20 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             fl.smem = smem;
             VK_DBG("fast launch: pk=%d mode=%d direct=%d base=%lld gmax=%d warps=%d nw=%d smem=%zu", pk, fl.mode, (int) direct,
                    (long long) direct_base, gmax, warps, plan.nw, smem);
-            const int span = prof_begin(a, s, chunk, 1);
-            rc = launch_fast(fp, fl, s);
-            prof_end(a, s, span);
-            if (rc != VK_OK) return rc;
+            const int64_t fast_rows = fp.num_tiles * tile_rows;
+            if (fp.num_tiles > 0) {
+                const int span = prof_begin(a, s, fast_rows, 1);
+                rc = launch_fast(fp, fl, s);
+                prof_end(a, s, span);
+                if (rc != VK_OK) return rc;
+            }
+            if (fast_rows < chunk) {
+                GenParams tp = gp;
+                tp.row_begin = fast_rows;
+                int64_t need = (chunk - fast_rows + 255) / 256;
+                agg_general_kernel<<<(unsigned) need, 256, 0, s>>>(tp);
+                VK_CHECK_LAUNCH("agg_general_kernel(tail)");
+            }
             a->groups_ub += chunk;
         } else {
             a->last_path = 2;
