@@ -436,63 +436,81 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
     // the key / predicate registers are dead: refill them with the tile after next
     if (refill_tile >= 0) load_tile_keys<PK, NV, MODE>(p, refill_tile, tid, nthreads, t);
 
-    // ---- phase 2: accumulate into the warp-private entries, one row at a time ----
+    // ---- phase 2: accumulate into the warp-private entries, one row PAIR per round ----
+    // The two rows of a pair arbitrate and update in the same round, so their shared-memory
+    // round trips overlap (the kernel is bound by this dependent chain, not by issue slots
+    // or by the shared-memory pipe: profiles/).  A lane whose two rows hit the same entry
+    // applies both to one loaded copy.
+    auto apply_row = [&](uint32_t (&e)[4], uint32_t (&f)[4], int r) {
+        e[0] += 1;
+        if constexpr (SUMF64) {
+            const double sum = __hiloint2double((int) e[3], (int) e[2]) +
+                               __longlong_as_double((long long) row_val<MODE>(p, 0, t.vq[0], r));
+            e[2] = (uint32_t) __double2loint(sum);
+            e[3] = (uint32_t) __double2hiint(sum);
+        } else {
+            uint64_t w[3] = {u64_of(e[2], e[3]), u64_of(f[0], f[1]), u64_of(f[2], f[3])};
 #pragma unroll
-    for (int r = 0; r < FA_R; ++r) {
-        bool mine = (todo >> r) & 1u;
-        while (__any_sync(0xffffffffu, mine)) {
-            if (mine) sts32(ea[r] + 4, cx.lane);
-            __syncwarp();
-            if (mine) {
-                uint32_t e[4];
-                lds128(ea[r], e);
-                if (e[1] == cx.lane) {
-                    mine = false;
-                    e[0] += 1;
-                    if constexpr (SUMF64) {
-                        const double sum = __hiloint2double((int) e[3], (int) e[2]) +
-                                           __longlong_as_double((long long) row_val<MODE>(p, 0, t.vq[0], r));
-                        e[2] = (uint32_t) __double2loint(sum);
-                        e[3] = (uint32_t) __double2hiint(sum);
-                        sts128(ea[r], e);
-                    } else {
-                        uint32_t f[4] = {0, 0, 0, 0};
-                        if constexpr (NW == 4) lds128(ea[r] + 16, f);
-                        uint64_t w[3] = {u64_of(e[2], e[3]), u64_of(f[0], f[1]), u64_of(f[2], f[3])};
+            for (int c = 0; c < NCMAX; ++c) {
+                if (c < p.n_cells) {
+                    const FastCell cell = p.cell[c];
+                    if (cell.op != CELL_I128_HI) {
+                        uint64_t v = 0;
 #pragma unroll
-                        for (int c = 0; c < NCMAX; ++c) {
-                            if (c < p.n_cells) {
-                                const FastCell cell = p.cell[c];
-                                if (cell.op != CELL_I128_HI) {
-                                    uint64_t v = 0;
-#pragma unroll
-                                    for (int k = 0; k < NV; ++k)
-                                        if (cell.col == k) v = row_val<MODE>(p, k, t.vq[k], r);
-                                    const uint64_t old = w[c];
-                                    const uint64_t nv = cell_apply(cell, old, v);
-                                    w[c] = nv;
-                                    if (NW == 4 && cell.op == CELL_ADD_I128 && c + 1 < NCMAX) {
-                                        const uint64_t ext = (!cell.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL;
-                                        w[c + 1 < 3 ? c + 1 : 2] += ext + (nv < old ? 1ULL : 0ULL);
-                                    }
-                                }
-                            }
-                        }
-                        e[2] = (uint32_t) w[0];
-                        e[3] = (uint32_t) (w[0] >> 32);
-                        sts128(ea[r], e);
-                        if constexpr (NW == 4) {
-                            f[0] = (uint32_t) w[1]; f[1] = (uint32_t) (w[1] >> 32);
-                            f[2] = (uint32_t) w[2]; f[3] = (uint32_t) (w[2] >> 32);
-                            sts128(ea[r] + 16, f);
+                        for (int k = 0; k < NV; ++k)
+                            if (cell.col == k) v = row_val<MODE>(p, k, t.vq[k], r);
+                        const uint64_t old = w[c];
+                        const uint64_t nv = cell_apply(cell, old, v);
+                        w[c] = nv;
+                        if (NW == 4 && cell.op == CELL_ADD_I128 && c + 1 < NCMAX) {
+                            const uint64_t ext = (!cell.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL;
+                            w[c + 1 < 3 ? c + 1 : 2] += ext + (nv < old ? 1ULL : 0ULL);
                         }
                     }
                 }
             }
+            e[2] = (uint32_t) w[0];
+            e[3] = (uint32_t) (w[0] >> 32);
+            if constexpr (NW == 4) {
+                f[0] = (uint32_t) w[1]; f[1] = (uint32_t) (w[1] >> 32);
+                f[2] = (uint32_t) w[2]; f[3] = (uint32_t) (w[2] >> 32);
+            }
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < FA_R / 2; ++j) {
+        const int r0 = 2 * j, r1 = 2 * j + 1;
+        bool m0 = (todo >> r0) & 1u, m1 = (todo >> r1) & 1u;
+        const bool dup = m0 && m1 && ea[r0] == ea[r1];
+        if (dup) m1 = false;
+        while (__any_sync(0xffffffffu, m0 | m1)) {
+            if (m0) sts32(ea[r0] + 4, cx.lane);
+            if (m1) sts32(ea[r1] + 4, cx.lane);
+            __syncwarp();
+            uint32_t e0[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0};
+            if (m0) lds128(ea[r0], e0);
+            if (m1) lds128(ea[r1], e1);
+            if (m0 && e0[1] == cx.lane) {
+                m0 = false;
+                uint32_t f[4] = {0, 0, 0, 0};
+                if constexpr (NW == 4) lds128(ea[r0] + 16, f);
+                apply_row(e0, f, r0);
+                if (dup) apply_row(e0, f, r1);
+                sts128(ea[r0], e0);
+                if constexpr (NW == 4) sts128(ea[r0] + 16, f);
+            }
+            if (m1 && e1[1] == cx.lane) {
+                m1 = false;
+                uint32_t f[4] = {0, 0, 0, 0};
+                if constexpr (NW == 4) lds128(ea[r1] + 16, f);
+                apply_row(e1, f, r1);
+                sts128(ea[r1], e1);
+                if constexpr (NW == 4) sts128(ea[r1] + 16, f);
+            }
             __syncwarp();
         }
-        // both rows of a pair done: its value registers are dead, refill them
-        if ((r & 1) && refill_tile >= 0) load_tile_vals<PK, NV, MODE>(p, refill_tile, tid, nthreads, t, r >> 1);
+        // both rows of the pair done: its value registers are dead, refill them
+        if (refill_tile >= 0) load_tile_vals<PK, NV, MODE>(p, refill_tile, tid, nthreads, t, j);
     }
 }
 

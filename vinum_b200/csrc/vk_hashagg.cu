@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 namespace vk {
@@ -396,6 +397,10 @@ struct VkAgg {
     int64_t groups_ub = 0;            // upper bound on groups in the table
     unsigned long long* d_ctr = nullptr;  // [0] num_groups [1] list count [2] lost [3] spilled [4] finalize cursor [5..] scratch
     unsigned long long* h_ctr = nullptr;  // pinned mirror
+    bool ctr_ready = false;           // d_ctr zeroed on the first stream this object is used on
+    cudaStream_t last_stream = nullptr;   // every call so far ran on this stream ...
+    bool stream_seen = false, multi_stream = false;  // ... unless multi_stream
+    uint64_t list_max = 0;            // replay list cap (entries), from free memory at first use
     uint32_t* list = nullptr;
     uint64_t list_cap = 0;
     int last_path = 0;
@@ -432,6 +437,57 @@ bool debug_on() {
 
 constexpr double kMaxLoad = 0.5;
 constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_RANGE = 8, CTR_WORDS = 16;
+
+// Counter blocks (16 device words + a pinned host mirror) are recycled across aggregate
+// objects: cudaMalloc / cudaHostAlloc / cudaFree cost far more than a whole 1e9-row scan.
+struct CtrBlock { int device; unsigned long long* d; unsigned long long* h; };
+std::mutex g_ctr_mu;
+std::vector<CtrBlock> g_ctr_free;
+
+int ctr_acquire(VkAgg* a) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_ctr_mu);
+        for (size_t i = 0; i < g_ctr_free.size(); ++i) {
+            if (g_ctr_free[i].device == dev) {
+                a->d_ctr = g_ctr_free[i].d;
+                a->h_ctr = g_ctr_free[i].h;
+                g_ctr_free.erase(g_ctr_free.begin() + i);
+                return VK_OK;
+            }
+        }
+    }
+    cudaError_t e = cudaMalloc((void**) &a->d_ctr, CTR_WORDS * sizeof(unsigned long long));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(counters)");
+    e = cudaHostAlloc((void**) &a->h_ctr, CTR_WORDS * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaFree(a->d_ctr);
+        a->d_ctr = nullptr;
+        return cuda_fail(e, "cudaHostAlloc(counters)");
+    }
+    return VK_OK;
+}
+void ctr_release(VkAgg* a) {
+    if (!a->d_ctr) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_ctr_mu);
+    g_ctr_free.push_back(CtrBlock{dev, a->d_ctr, a->h_ctr});
+    a->d_ctr = nullptr;
+    a->h_ctr = nullptr;
+}
+// Every entry point that touches the counters on a stream goes through here first.
+int ctr_init(VkAgg* a, cudaStream_t s) {
+    if (a->stream_seen && a->last_stream != s) a->multi_stream = true;
+    a->stream_seen = true;
+    a->last_stream = s;
+    if (!a->ctr_ready) {
+        VK_CUDA(cudaMemsetAsync(a->d_ctr, 0, CTR_WORDS * sizeof(unsigned long long), s));
+        a->ctr_ready = true;
+    }
+    return VK_OK;
+}
 
 int64_t pow2_ceil(int64_t x) {
     int64_t p = 1;
@@ -792,24 +848,28 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
     if (a->fast_warps > FA_MAX_THREADS / 32) a->fast_warps = FA_MAX_THREADS / 32;
     if (const char* v = getenv("VINUM_B200_AGG_DIRECT")) a->fast_direct_policy = atoi(v);
     if (getenv("VINUM_B200_AGG_NOFAST")) a->fast_disabled = true;
-    cudaError_t e = cudaMalloc((void**) &a->d_ctr, CTR_WORDS * sizeof(unsigned long long));
-    if (e != cudaSuccess) { delete a; return cuda_fail(e, "cudaMalloc(counters)"); }
-    cudaMemset(a->d_ctr, 0, CTR_WORDS * sizeof(unsigned long long));
-    e = cudaHostAlloc((void**) &a->h_ctr, CTR_WORDS * sizeof(unsigned long long), cudaHostAllocDefault);
-    if (e != cudaSuccess) { cudaFree(a->d_ctr); delete a; return cuda_fail(e, "cudaHostAlloc(counters)"); }
+    const int rc = ctr_acquire(a);
+    if (rc != VK_OK) { delete a; return rc; }
     *out = a;
     return VK_OK;
 }
 
 int vk_agg_destroy(VkAgg* a) {
     if (!a) return VK_OK;
-    cudaDeviceSynchronize();
+    // Stream-ordered teardown: the table and the list go back to the pool behind the work
+    // already queued on the object's stream.  The counter block is recycled by the next
+    // aggregate (possibly on another stream), so that stream is drained first.
+    cudaStream_t s = a->last_stream;
+    if (a->multi_stream) {
+        cudaDeviceSynchronize();
+    } else if (a->stream_seen) {
+        cudaStreamSynchronize(s);
+    }
     prof_resolve(a);
     for (auto& sp : a->prof_free) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
-    if (a->table_ready) free_table(&a->t, 0);
-    if (a->list) cudaFreeAsync(a->list, 0);
-    if (a->d_ctr) cudaFree(a->d_ctr);
-    if (a->h_ctr) cudaFreeHost(a->h_ctr);
+    if (a->table_ready) free_table(&a->t, s);
+    if (a->list) cudaFreeAsync(a->list, s);
+    ctr_release(a);
     delete a;
     return VK_OK;
 }
@@ -872,6 +932,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
     VK_REQUIRE(a->n_keys == 0 || keys, "vk_agg_update: keys is NULL");
     VK_REQUIRE(a->n_funcs == 0 || values, "vk_agg_update: values is NULL");
     cudaStream_t s = (cudaStream_t) stream;
+    { const int irc = ctr_init(a, s); if (irc != VK_OK) return irc; }
     for (int k = 0; k < a->n_keys; ++k) {
         VK_REQUIRE(keys[k].dtype == a->key_dtypes[k], "vk_agg_update: key dtype changed between batches");
         VK_REQUIRE(keys[k].length == n_rows, "vk_agg_update: key column length != n_rows");
@@ -980,13 +1041,14 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
     const int fast_grid_max = sms;  // one persistent CTA per SM
 
     // ---- chunk loop: never more rows in flight than (free slots + replay capacity) ----
-    uint64_t list_max = (uint64_t) 1 << 28;
-    {
+    if (a->list_max == 0) {
+        a->list_max = (uint64_t) 1 << 28;
         size_t fr = 0, tot = 0;
         if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
-            while (list_max * sizeof(uint32_t) > fr / 16 && list_max > (1u << 16)) list_max >>= 1;
+            while (a->list_max * sizeof(uint32_t) > fr / 16 && a->list_max > (1u << 16)) a->list_max >>= 1;
         }
     }
+    const uint64_t list_max = a->list_max;
     int64_t pos = 0;
     while (pos < n_rows) {
         const int64_t remaining = n_rows - pos;
@@ -1143,7 +1205,9 @@ int vk_agg_num_groups(VkAgg* a, int64_t* out_groups, VkStream stream) {
         *out_groups = a->n_keys == 0 ? 1 : 0;
         return VK_OK;
     }
-    int rc = read_counters(a, (cudaStream_t) stream);
+    int rc = ctr_init(a, (cudaStream_t) stream);
+    if (rc != VK_OK) return rc;
+    rc = read_counters(a, (cudaStream_t) stream);
     if (rc != VK_OK) return rc;
     a->groups_ub = (int64_t) a->h_ctr[CTR_GROUPS];
     *out_groups = a->groups_ub;
@@ -1155,6 +1219,7 @@ int vk_agg_result(VkAgg* a, int64_t num_groups, uint64_t* const* out_keys, uint8
                   uint8_t* const* out_vals_valid, VkStream stream) {
     VK_REQUIRE(a, "vk_agg_result: agg is NULL");
     cudaStream_t s = (cudaStream_t) stream;
+    { const int irc = ctr_init(a, s); if (irc != VK_OK) return irc; }
     if (num_groups == 0) return VK_OK;
     VK_REQUIRE(out_count_star, "vk_agg_result: out_count_star is NULL");
     if (!a->table_ready) {
@@ -1211,6 +1276,7 @@ static int exch_params(VkAgg* a, ExchParams* p) {
 int vk_agg_partition_counts(VkAgg* a, int n_ranks, int64_t* out_counts_dev, VkStream stream) {
     VK_REQUIRE(a && out_counts_dev && n_ranks >= 1, "vk_agg_partition_counts: bad argument");
     cudaStream_t s = (cudaStream_t) stream;
+    { const int irc = ctr_init(a, s); if (irc != VK_OK) return irc; }
     VK_CUDA(cudaMemsetAsync(out_counts_dev, 0, sizeof(int64_t) * n_ranks, s));
     if (!a->table_ready) return VK_OK;
     ExchParams p;
@@ -1228,6 +1294,7 @@ int vk_agg_export_partials(VkAgg* a, int n_ranks, const int64_t* offsets_dev, ui
     if (!a->table_ready) return VK_OK;
     VK_REQUIRE(out_records, "vk_agg_export_partials: out_records is NULL");
     cudaStream_t s = (cudaStream_t) stream;
+    { const int irc = ctr_init(a, s); if (irc != VK_OK) return irc; }
     ExchParams p;
     exch_params(a, &p);
     p.n_ranks = n_ranks;
@@ -1250,6 +1317,7 @@ int vk_agg_merge_partials(VkAgg* a, const uint64_t* records, int64_t n_records, 
     if (n_records == 0) return VK_OK;
     VK_REQUIRE(records, "vk_agg_merge_partials: records is NULL");
     cudaStream_t s = (cudaStream_t) stream;
+    { const int irc = ctr_init(a, s); if (irc != VK_OK) return irc; }
     if (!a->table_ready) {
         int rc = alloc_table(a, &a->t, pow2_ceil(n_records * 4 < 4096 ? 4096 : n_records * 4), s);
         if (rc != VK_OK) return rc;
