@@ -252,8 +252,11 @@ def run_ours(args) -> dict:
         sampler.start()
     launches0 = lib.vk_launch_count()
     lib.vk_event_record(e0, st.ptr)
+    step_wall_ms = []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         step(True)
+        step_wall_ms.append(round((time.perf_counter() - t_s) * 1e3, 3))
     lib.vk_event_record(e1, st.ptr)
     lib.vk_event_sync(e1)
     barrier()
@@ -306,6 +309,7 @@ def run_ours(args) -> dict:
                    "groups": last_result.get("groups"), "selected_rows": last_result.get("count"),
                    "agg_path": last_result.get("path"), "parallelism": f"row-range x{world}"},
         "gpu_launches": int(launches1 - launches0),
+        "step_wall_ms": step_wall_ms,  # host wall clock of each timed step (every step ends with a D2H read)
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rows/s", "rows_per_step": e2e_rows * world,
                 "h2d_bytes_per_step": int(stats.get("h2d_bytes", 0)) * world,

@@ -126,6 +126,8 @@ def s_filter():
 
 
 CFGS = [(1, 0), (0, 0), (1, 8), (0, 8), (1, 4)]
+if os.environ.get("VK_CFGS"):
+    CFGS = [tuple(int(x) for x in c.split(":")) for c in os.environ["VK_CFGS"].split(",")]
 
 
 def np_groupby(keys, vals, mask):

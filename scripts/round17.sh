@@ -1,0 +1,5 @@
+source scripts/gpu_round.sh true
+rm -f gpurun_out/round.log
+run pytest_gpu 900 python -m pytest tests -m gpu -x -q
+TAILN=40 run ab 900 python scripts/agg_ab.py "" "AGG_PF=6,AGG_WARPS=8" "AGG_PF=0,AGG_WARPS=12"
+TAILN=5 run bench 600 python bench.py

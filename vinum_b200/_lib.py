@@ -12,6 +12,8 @@ from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "_C" / "libvinum_b200.so"
+if os.environ.get("VINUM_B200_LIB"):  # tuning builds (build.py --variant=...), same C ABI
+    LIB_PATH = Path(os.environ["VINUM_B200_LIB"]).resolve()
 
 
 class VinumB200Error(RuntimeError):

@@ -98,6 +98,9 @@ class Aggregator:
             self._h = C.c_void_p()
 
     def __del__(self):
+        from .device import _shutting_down
+        if _shutting_down():
+            return
         try:
             self.close()
         except Exception:

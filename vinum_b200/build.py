@@ -59,23 +59,28 @@ def needs_build() -> bool:
     return not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < _newest_source_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> Path:
+    """`variant` / `defines` build a tuning variant (libvinum_b200_<variant>.so, selected at
+    run time with VINUM_B200_LIB) next to the product library."""
+    lib_path = OUT_DIR / f"libvinum_b200_{variant}.so" if variant else LIB_PATH
+    if not variant and not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
     OUT_DIR.mkdir(exist_ok=True)
-    obj_dir = OUT_DIR / "obj"
+    obj_dir = OUT_DIR / ("obj_" + variant if variant else "obj")
     obj_dir.mkdir(exist_ok=True)
 
     hdr_mtime = max(f.stat().st_mtime for f in list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "vinum_b200.h",
                                                                             Path(__file__)])
+
+    extra_defines = list(defines)
 
     def compile_one(item) -> Path:
         src, stem, defines = item
         obj = obj_dir / (stem + ".o")
         if not force and obj.exists() and obj.stat().st_mtime >= max(hdr_mtime, (CSRC / src).stat().st_mtime):
             return obj  # up to date
-        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *defines, *extra_defines, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
             print(" ".join(cmd), flush=True)
@@ -88,15 +93,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH.with_suffix(".so.tmp")
+    tmp = lib_path.with_suffix(".so.tmp")
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB_PATH)
-    return LIB_PATH
+    os.replace(tmp, lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    variant, defs = "", []
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):
+            variant = a.split("=", 1)[1]
+        elif a.startswith("-D"):
+            defs.append(a)
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=variant, defines=defs)
     print(p)

@@ -29,8 +29,15 @@
 
 namespace vk {
 
-constexpr int FA_MAX_THREADS = 384;
+#ifndef VK_FA_MAXT
+#define VK_FA_MAXT 384
+#endif
+constexpr int FA_MAX_THREADS = VK_FA_MAXT;
 constexpr int FA_R = 8;            // rows per thread per tile (four lane-contiguous pairs)
+#ifndef VK_FA_K
+#define VK_FA_K 2
+#endif
+constexpr int FA_K = VK_FA_K;      // rows per arbitration round in phase 2 (2, 4 or 8)
 constexpr int FA_MAX_COLS = 3;     // distinct value columns
 constexpr int FA_MAX_CELLS = 3;    // 64-bit accumulator cells per group (besides COUNT)
 constexpr int FA_MAXPROBE = 64;
@@ -72,6 +79,8 @@ struct FastParams {
     int gmax;                     // dense group ids per CTA
     uint64_t direct_base;         // direct mode: gid = key - direct_base
     int64_t row_limit;            // row-level global inserts stop here (flush reserve above it)
+    int pf_dist;                  // L2 bulk prefetch distance in tiles (0 = off)
+    long long* key_range;         // optional {min, max} (signed order) of the keys this launch flushes
     GTable table;
     ReplayList replay;
 };
@@ -114,6 +123,13 @@ __device__ __forceinline__ uint32_t ldg_stream2(const void* p) {
 }
 
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t) hi << 32) | lo; }
+
+// Asynchronous bulk prefetch of [p, p + bytes) into L2 (no register, no shared memory): it
+// keeps more bytes in flight than the register tiles alone can.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
+    const uint64_t a = reinterpret_cast<uint64_t>(ptr) & ~(uint64_t) 15;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(bytes) : "memory");
+}
 
 // ---- tile registers: RAW load results, decoded only when the tile is processed ----------
 template <int PK, int NV>
@@ -436,11 +452,11 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
     // the key / predicate registers are dead: refill them with the tile after next
     if (refill_tile >= 0) load_tile_keys<PK, NV, MODE>(p, refill_tile, tid, nthreads, t);
 
-    // ---- phase 2: accumulate into the warp-private entries, one row PAIR per round ----
-    // The two rows of a pair arbitrate and update in the same round, so their shared-memory
-    // round trips overlap (the kernel is bound by this dependent chain, not by issue slots
-    // or by the shared-memory pipe: profiles/).  A lane whose two rows hit the same entry
-    // applies both to one loaded copy.
+    // ---- phase 2: accumulate into the warp-private entries, FA_K rows per round ----
+    // The FA_K rows of a group arbitrate and update in the same round, so their
+    // shared-memory round trips overlap (the kernel is bound by this dependent chain, not by
+    // issue slots or by the shared-memory pipe: profiles/).  The tag is (lane, row slot), so
+    // two rows of ONE lane that hit the same entry arbitrate like rows of different lanes.
     auto apply_row = [&](uint32_t (&e)[4], uint32_t (&f)[4], int r) {
         e[0] += 1;
         if constexpr (SUMF64) {
@@ -478,39 +494,38 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
         }
     };
 #pragma unroll
-    for (int j = 0; j < FA_R / 2; ++j) {
-        const int r0 = 2 * j, r1 = 2 * j + 1;
-        bool m0 = (todo >> r0) & 1u, m1 = (todo >> r1) & 1u;
-        const bool dup = m0 && m1 && ea[r0] == ea[r1];
-        if (dup) m1 = false;
-        while (__any_sync(0xffffffffu, m0 | m1)) {
-            if (m0) sts32(ea[r0] + 4, cx.lane);
-            if (m1) sts32(ea[r1] + 4, cx.lane);
+    for (int q = 0; q < FA_R / FA_K; ++q) {
+        uint32_t pend = (todo >> (q * FA_K)) & ((1u << FA_K) - 1u);
+        while (__any_sync(0xffffffffu, pend != 0)) {
+#pragma unroll
+            for (int k = 0; k < FA_K; ++k)
+                if ((pend >> k) & 1u) sts32(ea[q * FA_K + k] + 4, cx.lane | ((uint32_t) k << 5));
             __syncwarp();
-            uint32_t e0[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0};
-            if (m0) lds128(ea[r0], e0);
-            if (m1) lds128(ea[r1], e1);
-            if (m0 && e0[1] == cx.lane) {
-                m0 = false;
-                uint32_t f[4] = {0, 0, 0, 0};
-                if constexpr (NW == 4) lds128(ea[r0] + 16, f);
-                apply_row(e0, f, r0);
-                if (dup) apply_row(e0, f, r1);
-                sts128(ea[r0], e0);
-                if constexpr (NW == 4) sts128(ea[r0] + 16, f);
+            uint32_t e[FA_K][4];
+#pragma unroll
+            for (int k = 0; k < FA_K; ++k) {
+                e[k][1] = 0xFFFFFFFFu;
+                if ((pend >> k) & 1u) lds128(ea[q * FA_K + k], e[k]);
             }
-            if (m1 && e1[1] == cx.lane) {
-                m1 = false;
-                uint32_t f[4] = {0, 0, 0, 0};
-                if constexpr (NW == 4) lds128(ea[r1] + 16, f);
-                apply_row(e1, f, r1);
-                sts128(ea[r1], e1);
-                if constexpr (NW == 4) sts128(ea[r1] + 16, f);
+#pragma unroll
+            for (int k = 0; k < FA_K; ++k) {
+                if (e[k][1] == (cx.lane | ((uint32_t) k << 5))) {
+                    const int r = q * FA_K + k;
+                    pend &= ~(1u << k);
+                    uint32_t f[4] = {0, 0, 0, 0};
+                    if constexpr (NW == 4) lds128(ea[r] + 16, f);
+                    apply_row(e[k], f, r);
+                    sts128(ea[r], e[k]);
+                    if constexpr (NW == 4) sts128(ea[r] + 16, f);
+                }
             }
-            __syncwarp();
+            __syncwarp();  // (measured: dropping this barrier buys nothing)
         }
-        // both rows of the pair done: its value registers are dead, refill them
-        if (refill_tile >= 0) load_tile_vals<PK, NV, MODE>(p, refill_tile, tid, nthreads, t, j);
+        // the rows of this group are done: their value registers are dead, refill them
+        if (refill_tile >= 0) {
+#pragma unroll
+            for (int j = q * FA_K / 2; j < (q + 1) * FA_K / 2; ++j) load_tile_vals<PK, NV, MODE>(p, refill_tile, tid, nthreads, t, j);
+        }
     }
 }
 
@@ -572,10 +587,32 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
     };
     if (tile < p.num_tiles) load_all(tile, ta);
     if (tile + stride < p.num_tiles) load_all(tile + stride, tb);
+    // one lane per column streams the tile `pf_dist` rounds ahead into L2
+    auto prefetch = [&](int64_t tl) {
+        if (p.pf_dist <= 0 || lane != 0 || warp > NV + 1) return;
+        const int64_t pt = tl + (int64_t) p.pf_dist * stride;
+        if (pt >= p.num_tiles) return;
+        const int64_t r = pt * tile_rows;
+        if (warp == 0) {
+            const bool k8 = MODE == FM_ALL8 || (MODE == FM_RUNTIME && p.key_mode == 0);
+            l2_prefetch_bulk(p.key.data + r * (k8 ? 8 : 4), (uint32_t) tile_rows * (k8 ? 8u : 4u));
+        } else if (warp == 1) {
+            if constexpr (PK == PK_F64_VEC || PK == PK_I64_VEC) l2_prefetch_bulk(p.pred.col.data + r * 8, (uint32_t) tile_rows * 8u);
+            else if constexpr (PK == PK_MASK) l2_prefetch_bulk(p.pred.mask + r, (uint32_t) tile_rows);
+        } else {
+            const int v = warp - 2;
+            if (v < NV) {
+                const bool v8 = MODE != FM_RUNTIME || p.col_mode[v] == 0;
+                l2_prefetch_bulk(p.col[v].data + r * (v8 ? 8 : 4), (uint32_t) tile_rows * (v8 ? 8u : 4u));
+            }
+        }
+    };
     while (tile < p.num_tiles) {
+        prefetch(tile);
         process(tile, ta);
         tile += stride;
         if (tile >= p.num_tiles) break;
+        prefetch(tile);
         process(tile, tb);
         tile += stride;
     }
@@ -585,6 +622,8 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
     for (int d = 16; d > 0; d >>= 1) spilled += __shfl_xor_sync(0xffffffffu, spilled, d);
     if (lane == 0 && spilled) atomicAdd(p.replay.spilled, (unsigned long long) spilled);
     const int n_iter = DIRECT ? G : S;
+    unsigned long long selected = 0;
+    long long kmin = INT64_MAX, kmax = INT64_MIN;
     for (int s = tid; s < n_iter; s += nthreads) {
         uint64_t key;
         uint32_t g16;
@@ -623,6 +662,9 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
             }
         }
         if (cnt == 0) continue;
+        selected += cnt;
+        kmin = (long long) key < kmin ? (long long) key : kmin;
+        kmax = (long long) key > kmax ? (long long) key : kmax;
 #pragma unroll
         for (int c = 0; c < NCMAX; ++c)
             if (c < p.n_cells && p.cell[c].op == CELL_ADD_F64) acc[c] = (uint64_t) __double_as_longlong(facc[c]);
@@ -633,6 +675,20 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
             continue;
         }
         fast_global_update(p, g, cnt, acc);
+    }
+    // selectivity statistic for the host's geometry choice (one atomic per warp)
+    for (int d = 16; d > 0; d >>= 1) selected += __shfl_xor_sync(0xffffffffu, selected, d);
+    if (lane == 0 && selected) atomicAdd(p.replay.selected, selected);
+    if (p.key_range != nullptr) {  // learning launch: the key range decides about direct group ids
+        for (int d = 16; d > 0; d >>= 1) {
+            const long long a = __shfl_xor_sync(0xffffffffu, kmin, d), b = __shfl_xor_sync(0xffffffffu, kmax, d);
+            kmin = a < kmin ? a : kmin;
+            kmax = b > kmax ? b : kmax;
+        }
+        if (lane == 0 && kmin <= kmax) {
+            atomicMin(p.key_range, kmin);
+            atomicMax(p.key_range + 1, kmax);
+        }
     }
 }
 

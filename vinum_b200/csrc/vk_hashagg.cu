@@ -406,6 +406,8 @@ struct VkAgg {
     int last_path = 0;
     // fast (shared-memory) path configuration; env overrides are for tuning runs
     int fast_log2s = 12;              // CTA key table slots
+    int fast_pf = -1;                 // L2 bulk prefetch distance of the fused kernel, in tiles (-1: automatic)
+    double fast_selectivity = 1.0;    // share of rows that passed the fused predicate so far
     int fast_warps = FA_MAX_THREADS / 32;  // warps per CTA (fewer warps = more groups per warp-private table)
     bool fast_warps_fixed = false;
     int fast_direct_policy = 1;       // 1: use direct (key - base) group ids when the key range allows, 0: always hash
@@ -436,13 +438,14 @@ bool debug_on() {
 #define VK_DBG(...) do { if (debug_on()) { fprintf(stderr, "[vk_agg] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
 constexpr double kMaxLoad = 0.5;
-constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_RANGE = 8, CTR_WORDS = 16;
+constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_SELECTED = 6, CTR_RANGE = 8, CTR_WORDS = 16;
 
 // Counter blocks (16 device words + a pinned host mirror) are recycled across aggregate
 // objects: cudaMalloc / cudaHostAlloc / cudaFree cost far more than a whole 1e9-row scan.
 struct CtrBlock { int device; unsigned long long* d; unsigned long long* h; };
-std::mutex g_ctr_mu;
-std::vector<CtrBlock> g_ctr_free;
+// leaked on purpose: objects may be destroyed after static destructors have run
+std::mutex& g_ctr_mu = *new std::mutex();
+std::vector<CtrBlock>& g_ctr_free = *new std::vector<CtrBlock>();
 
 int ctr_acquire(VkAgg* a) {
     int dev = 0;
@@ -573,14 +576,58 @@ int grow_table(VkAgg* a, int64_t groups_now, int64_t need_free, cudaStream_t s) 
     return VK_OK;
 }
 
+// Replay lists are sized for the worst case of a whole chunk (up to 4 GB for a 1e9-row batch)
+// and almost never written.  Carving such a block out of the stream-ordered pool on every
+// query fragments it (measured: sporadic multi-ms stalls), so one list per device is kept
+// across aggregate objects, like the counter blocks.
+struct ListBlock { int device; uint32_t* ptr; uint64_t cap; };
+std::vector<ListBlock>& g_list_free = *new std::vector<ListBlock>();
+
 int ensure_list(VkAgg* a, uint64_t want, cudaStream_t s) {
     if (a->list_cap >= want) return VK_OK;
     if (a->list) VK_CUDA(cudaFreeAsync(a->list, s));
     a->list = nullptr;
     a->list_cap = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_ctr_mu);
+        for (size_t i = 0; i < g_list_free.size(); ++i) {
+            if (g_list_free[i].device == dev && g_list_free[i].cap >= want) {
+                a->list = g_list_free[i].ptr;
+                a->list_cap = g_list_free[i].cap;
+                g_list_free.erase(g_list_free.begin() + i);
+                return VK_OK;
+            }
+        }
+    }
     VK_CUDA(cudaMallocAsync((void**) &a->list, want * sizeof(uint32_t), s));
     a->list_cap = want;
     return VK_OK;
+}
+// Called after the object's stream has been drained.
+void release_list(VkAgg* a, cudaStream_t s) {
+    if (!a->list) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    uint32_t* drop = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ctr_mu);
+        size_t i = 0;
+        for (; i < g_list_free.size(); ++i)
+            if (g_list_free[i].device == dev) break;
+        if (i == g_list_free.size()) {
+            g_list_free.push_back(ListBlock{dev, a->list, a->list_cap});
+        } else if (g_list_free[i].cap < a->list_cap) {  // keep the larger one
+            drop = g_list_free[i].ptr;
+            g_list_free[i] = ListBlock{dev, a->list, a->list_cap};
+        } else {
+            drop = a->list;
+        }
+    }
+    if (drop) cudaFreeAsync(drop, s);
+    a->list = nullptr;
+    a->list_cap = 0;
 }
 
 ReplayList make_replay(VkAgg* a) {
@@ -589,6 +636,7 @@ ReplayList make_replay(VkAgg* a) {
     l.count = a->d_ctr + CTR_LIST;
     l.lost = a->d_ctr + CTR_LOST;
     l.spilled = a->d_ctr + CTR_SPILL;
+    l.selected = a->d_ctr + CTR_SELECTED;
     l.capacity = a->list_cap;
     return l;
 }
@@ -678,6 +726,7 @@ void prof_resolve(VkAgg* a) {
 
 // Key range of the (single-key) table -> a->direct_*; decides whether later chunks may use
 // direct group ids.  One small scan of the table plus a counter read-back.
+void apply_key_range(VkAgg* a);
 int measure_key_range(VkAgg* a, cudaStream_t s) {
     const long long init[2] = {INT64_MAX, INT64_MIN};
     VK_CUDA(cudaMemcpyAsync(a->d_ctr + CTR_RANGE, init, sizeof(init), cudaMemcpyHostToDevice, s));
@@ -686,13 +735,16 @@ int measure_key_range(VkAgg* a, cudaStream_t s) {
     VK_CHECK_LAUNCH("agg_key_range_kernel");
     int rc = read_counters(a, s);
     if (rc != VK_OK) return rc;
+    apply_key_range(a);
+    return VK_OK;
+}
+void apply_key_range(VkAgg* a) {
     const long long mn = (long long) a->h_ctr[CTR_RANGE], mx = (long long) a->h_ctr[CTR_RANGE + 1];
     a->direct_known = true;
     a->direct_ok = mn <= mx && (uint64_t) mx - (uint64_t) mn < 0xFFF0ULL;
     a->direct_min = (uint64_t) mn;
     a->direct_span = (uint64_t) mx - (uint64_t) mn;
     VK_DBG("key range: min=%lld max=%lld direct_ok=%d", mn, mx, (int) a->direct_ok);
-    return VK_OK;
 }
 
 bool aligned_for_pairs(const VkColumn& c) {
@@ -838,6 +890,7 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
         a->specs[f] = s;
     }
     if (const char* v = getenv("VINUM_B200_AGG_LOG2S")) a->fast_log2s = atoi(v);
+    if (const char* v = getenv("VINUM_B200_AGG_PF")) a->fast_pf = atoi(v);
     if (a->fast_log2s < 8) a->fast_log2s = 8;
     if (a->fast_log2s > 13) a->fast_log2s = 13;
     if (const char* v = getenv("VINUM_B200_AGG_WARPS")) {
@@ -868,7 +921,7 @@ int vk_agg_destroy(VkAgg* a) {
     prof_resolve(a);
     for (auto& sp : a->prof_free) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     if (a->table_ready) free_table(&a->t, s);
-    if (a->list) cudaFreeAsync(a->list, s);
+    release_list(a, s);
     ctr_release(a);
     delete a;
     return VK_OK;
@@ -1009,9 +1062,17 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
     bool direct = false;
     uint64_t direct_base = 0;
     size_t smem = 0;
+    int pf_dist = 0;
     auto configure_fast = [&](int64_t groups_hint) {
         direct = false;
-        const int w_hi = a->fast_warps_fixed ? a->fast_warps : FA_MAX_THREADS / 32;
+        // Two measured regimes (profiles/): when the predicate drops a good share of the rows
+        // the kernel is HBM-bound and 8 warps + an L2 bulk prefetch 6 tiles ahead stream best;
+        // when (nearly) every row reaches the tables it is bound by the shared-memory pipe
+        // and wants all 12 warps and no prefetch.
+        const bool selective = pk != PK_NONE && a->fast_rows_seen > 0 && a->fast_selectivity <= 0.7;
+        pf_dist = a->fast_pf >= 0 ? a->fast_pf : (selective ? 6 : 0);
+        const int w_auto = selective && FA_MAX_THREADS / 32 >= 8 ? 8 : FA_MAX_THREADS / 32;
+        const int w_hi = a->fast_warps_fixed ? a->fast_warps : w_auto;
         const int w_lo = a->fast_warps_fixed ? a->fast_warps : 2;
         auto next_w = [](int w) { return w > 8 ? w - 2 : w >> 1; };  // 12, 10, 8, 4, 2
         // direct group ids (key - base): the key range seen so far fits the warp-private tables
@@ -1042,7 +1103,13 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
 
     // ---- chunk loop: never more rows in flight than (free slots + replay capacity) ----
     if (a->list_max == 0) {
-        a->list_max = (uint64_t) 1 << 28;
+        // large enough that a 1e9-row batch is ONE launch (the list is only touched by rows
+        // that could not be inserted; the memory comes from the pool and is never written otherwise)
+        int l2 = 30;
+        if (const char* v = getenv("VINUM_B200_LIST_LOG2")) l2 = atoi(v);
+        if (l2 < 16) l2 = 16;
+        if (l2 > 31) l2 = 31;
+        a->list_max = (uint64_t) 1 << l2;
         size_t fr = 0, tot = 0;
         if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
             while (a->list_max * sizeof(uint32_t) > fr / 16 && a->list_max > (1u << 16)) a->list_max >>= 1;
@@ -1068,6 +1135,12 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         }
         int64_t chunk = remaining;
         bool may_fail = false;
+        // the first fast chunk is small: it tells the cardinality, the key range and the
+        // selectivity before the geometry is fixed (and it needs no replay list)
+        if (fast && a->fast_rows_seen == 0) {
+            const int64_t learn = free_slots < ((int64_t) 1 << 20) ? free_slots : ((int64_t) 1 << 20);
+            if (chunk > learn) chunk = learn;
+        }
         if (chunk > free_slots) {
             uint64_t want = (uint64_t) (chunk - free_slots);
             if (want > list_max) want = list_max;
@@ -1077,8 +1150,6 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             may_fail = true;
         }
         if (chunk > (int64_t) 0xfffff000LL) chunk = (int64_t) 0xfffff000LL;  // row ids in the list are 32-bit
-        // the first fast chunk is small: it tells the cardinality before the table geometry is fixed
-        if (fast && a->fast_rows_seen == 0 && chunk > ((int64_t) 1 << 22)) chunk = (int64_t) 1 << 22;
         if (chunk < remaining) {
             // chunk starts stay pair-aligned, and fast chunks are whole tiles (only the last one has a tail)
             const int64_t unit = fast ? (int64_t) warps * 32 * FA_R : 4096;
@@ -1097,6 +1168,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         rc = make_pred(cpred, chunk, &dpred, &pk);
         if (rc != VK_OK) return rc;
 
+        bool fused_range = false;
         GenParams gp{};
         gp.pred = dpred;
         gp.pk = pk;
@@ -1132,6 +1204,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             fp.gmax = gmax;
             fp.direct_base = direct_base;
             fp.row_limit = a->t.max_groups - flush_reserve;
+            fp.pf_dist = warps >= 5 ? pf_dist : 0;  // one prefetching lane per column: needs NV + 2 warps
             fp.table = a->t;
             fp.replay = gp.replay;
             FastLaunch fl;
@@ -1146,6 +1219,13 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             VK_DBG("fast launch: pk=%d mode=%d direct=%d base=%lld gmax=%d warps=%d nw=%d smem=%zu", pk, fl.mode, (int) direct,
                    (long long) direct_base, gmax, warps, plan.nw, smem);
             const int64_t fast_rows = fp.num_tiles * tile_rows;
+            // the learning launch on an empty table also reports its key range (saves a scan + a sync)
+            fused_range = lean && a->fast_direct_policy && !a->direct_known && a->groups_ub == 0 && fast_rows == chunk;
+            if (fused_range) {
+                const long long init[2] = {INT64_MAX, INT64_MIN};
+                VK_CUDA(cudaMemcpyAsync(a->d_ctr + CTR_RANGE, init, sizeof(init), cudaMemcpyHostToDevice, s));
+                fp.key_range = reinterpret_cast<long long*>(a->d_ctr + CTR_RANGE);
+            }
             if (fp.num_tiles > 0) {
                 const int span = prof_begin(a, s, fast_rows, 1);
                 rc = launch_fast(fp, fl, s);
@@ -1170,7 +1250,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             a->groups_ub += chunk;
         }
 
-        if (may_fail || (fast && a->fast_rows_seen < ((uint64_t) 1 << 22))) {
+        if (may_fail || (fast && a->fast_rows_seen < ((uint64_t) 1 << 20))) {
             // rows may have been deferred (or we are still learning the cardinality)
             rc = read_counters(a, s);
             if (rc != VK_OK) return rc;
@@ -1178,6 +1258,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 const uint64_t spill_now = a->h_ctr[CTR_SPILL];
                 a->fast_rows_seen += (uint64_t) chunk;
                 a->fast_spilled += spill_now;
+                a->fast_selectivity = (double) (a->h_ctr[CTR_SELECTED] + a->fast_spilled) / (double) a->fast_rows_seen;
                 a->fast_groups_seen = (int64_t) a->h_ctr[CTR_GROUPS];
                 if (chunk >= 65536 && spill_now * 4 > (uint64_t) chunk) {
                     // this configuration thrashes: most rows fell through to the global path
@@ -1185,8 +1266,12 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                     else a->fast_disabled = true;       // cardinality too high for shared memory
                 } else if (lean && a->fast_direct_policy && !a->direct_known &&
                            a->fast_groups_seen <= fast_gmax(log2s, true, plan.nw, 2)) {
-                    rc = measure_key_range(a, s);
-                    if (rc != VK_OK) return rc;
+                    if (fused_range && spill_now == 0) {
+                        apply_key_range(a);
+                    } else {
+                        rc = measure_key_range(a, s);
+                        if (rc != VK_OK) return rc;
+                    }
                 }
             }
             rc = run_replay_until_empty(a, gp, chunk, s);

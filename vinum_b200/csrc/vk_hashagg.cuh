@@ -234,6 +234,7 @@ struct ReplayList {
     unsigned long long* count;      // appended so far
     unsigned long long* lost;       // rows that did not fit (must stay 0)
     unsigned long long* spilled;    // rows the fast kernel sent to the global path (statistics)
+    unsigned long long* selected;   // rows that passed the fused predicate in the CTA tables (statistics, cumulative)
     uint64_t capacity;
 };
 

@@ -11,6 +11,9 @@ when the buffers are pinned, see `pinned_array`); nothing here computes on the C
 """
 from __future__ import annotations
 
+import atexit
+import sys as _sys
+
 import ctypes as C
 from typing import Dict, Iterable, List, Optional, Sequence
 
@@ -62,6 +65,25 @@ def arrow_type_of_vk(dt: int) -> pa.DataType:
 
 
 # ---------------------------------------------------------------- streams ----
+
+# Device objects that are still alive when the interpreter exits are NOT released one by
+# one: by then the stream they were allocated on (and possibly the CUDA context) is gone,
+# and the process is about to give everything back anyway.
+_finalizing = False
+
+
+def _mark_finalizing() -> None:
+    global _finalizing
+    _finalizing = True
+
+
+atexit.register(_mark_finalizing)
+
+
+def _shutting_down() -> bool:
+    return _finalizing or _sys.is_finalizing()
+
+
 class Stream:
     """Thin owner of a cudaStream_t (or a borrowed handle, e.g. torch's current stream)."""
 
@@ -81,6 +103,8 @@ class Stream:
         return C.c_void_p(self.handle)
 
     def __del__(self):
+        if _shutting_down():
+            return
         if getattr(self, "_owned", False) and getattr(self, "handle", 0):
             try:
                 L._lib.vk_stream_destroy(C.c_void_p(self.handle))
@@ -126,6 +150,8 @@ class DeviceBuffer:
             self.ptr = 0
 
     def __del__(self):
+        if _shutting_down():
+            return
         try:
             self.free()
         except Exception:
@@ -172,6 +198,8 @@ class PinnedBuffer:
         return _keepalive_view(arr, self)
 
     def __del__(self):
+        if _shutting_down():
+            return
         try:
             if self.ptr:
                 L._lib.vk_host_free(C.c_void_p(self.ptr))
