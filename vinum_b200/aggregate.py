@@ -16,7 +16,7 @@ import pyarrow as pa
 
 from . import _lib as L
 from ._lib import lib
-from .device import (DeviceBuffer, DeviceColumn, Stream, VK_SIZE, VK_TO_NUMPY, default_stream, arrow_from_numpy,
+from .device import (_shutting_down, DeviceBuffer, DeviceColumn, Stream, VK_SIZE, VK_TO_NUMPY, default_stream, arrow_from_numpy,
                      vk_dtype_of)
 from .ops import Predicate
 
@@ -98,7 +98,6 @@ class Aggregator:
             self._h = C.c_void_p()
 
     def __del__(self):
-        from .device import _shutting_down
         if _shutting_down():
             return
         try:

@@ -3,6 +3,7 @@
 // loads, warp-ballot ranks, a block prefix and a single-pass decoupled look-back so
 // every input byte is read exactly once.
 #include "vk_common.cuh"
+#include <cstdlib>
 #include "vk_pred.cuh"
 
 namespace vk {
@@ -156,7 +157,14 @@ struct FilterParams {
     unsigned long long* ticket;  // scratch[0]
     unsigned long long* status;  // scratch[1..]
     int64_t num_tiles;
+    int pf;  // bulk-prefetch the tile's payload columns into L2 while the predicate / look-back run
 };
+
+__device__ __forceinline__ void l2_prefetch_span(const uint8_t* begin, const uint8_t* end) {
+    const uint64_t a = reinterpret_cast<uint64_t>(begin) & ~(uint64_t) 15;
+    const uint64_t e = reinterpret_cast<uint64_t>(end) & ~(uint64_t) 15;
+    if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t) (e - a)) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
     unsigned long long v;
@@ -178,6 +186,17 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
     __syncthreads();
     const int64_t tile = s_tile;
     const int64_t base = tile * FT_TILE;
+
+    // The payload columns are only read after the look-back; start moving this tile's slice of
+    // each of them into L2 now (one bulk prefetch per column, no registers, no shared memory).
+    if (p.pf && tid < p.n_cols) {
+        const Col col = p.cols[tid];
+        const int es = dtype_size(col.dtype);
+        const int64_t rows = p.n - base < FT_TILE ? p.n - base : FT_TILE;
+        // (the predicate's own column is being loaded by phase 1 right now: no second request)
+        if (!(p.pred.kind == VK_PRED_CMP && col.data == p.pred.col.data))
+            l2_prefetch_span(col.data + base * es, col.data + (base + rows) * es);
+    }
 
     // ---- phase 1: evaluate the predicate once, keep the flags in registers ----
     uint32_t flags = 0;
@@ -470,6 +489,11 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         p.ticket = reinterpret_cast<unsigned long long*>(scratch);
         p.status = p.ticket + 1;
         p.num_tiles = tiles;
+        {
+            static int pf = -1;
+            if (pf < 0) { const char* v = getenv("VINUM_B200_FILTER_PF"); pf = v ? atoi(v) : 1; }
+            p.pf = pf;
+        }
         VK_CUDA(cudaMemsetAsync(scratch, 0, vk_filter_scratch_bytes(n_rows), s));
         switch (pk) {
             case PK_MASK: filter_kernel<PK_MASK><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); break;

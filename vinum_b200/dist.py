@@ -58,11 +58,17 @@ def all_to_all_records(send: "torch.Tensor", send_sizes: Sequence[int], recv_siz
 
 
 class DistributedAggregator:
-    """Local Aggregator + partial-group repartition.  `finish()` returns, on rank 0, the
+    """Local Aggregator + partial-group repartition.  `gather_raw()` returns, on rank 0, the
     raw finalised groups of the whole job (same tuple as Aggregator.result_raw); None on
-    the other ranks."""
+    the other ranks.
+
+    Everything between the local aggregate and the final read-back is ordered on ONE CUDA
+    stream (torch is pointed at the aggregate's stream through `torch.cuda.ExternalStream`),
+    so the only host synchronisations are the two places where the host needs a number:
+    the count matrix (all-to-all split sizes) and the number of groups per rank."""
 
     def __init__(self, aggregator, stream, group=None):
+        import torch
         import torch.distributed as dist
         self.agg = aggregator
         self.stream = stream
@@ -70,6 +76,8 @@ class DistributedAggregator:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.exchange_bytes = 0
+        self._recv_max = 0
+        self._tstream = torch.cuda.ExternalStream(int(stream.handle)) if stream.handle else torch.cuda.default_stream()
 
     def update(self, keys, values, pred=None) -> None:
         self.agg.update(keys, values, pred, self.stream)
@@ -86,61 +94,75 @@ class DistributedAggregator:
         lib.vk_agg_record_words(self.agg._h, C.byref(words))
         w = words.value
         st = self.stream
-        counts_dev = torch.zeros(self.world, dtype=torch.int64, device=dev)
-        lib.vk_agg_partition_counts(self.agg._h, self.world, C.c_void_p(counts_dev.data_ptr()), st.ptr)
-        st.sync()
-        all_counts = [torch.empty_like(counts_dev) for _ in range(self.world)]
-        dist.all_gather(all_counts, counts_dev, group=self.group)
-        counts = torch.stack(all_counts).cpu().numpy()
-        send_off, send_sz, _recv_off, recv_sz = exchange_plan(counts)
-        my_total = int(send_sz[self.rank].sum())
-        send = torch.empty(max(my_total, 1) * w, dtype=torch.int64, device=dev)
-        offs = torch.from_numpy(np.ascontiguousarray(send_off[self.rank])).to(dev)
-        lib.vk_agg_export_partials(self.agg._h, self.world, C.c_void_p(offs.data_ptr()), C.c_void_p(send.data_ptr()),
-                                   st.ptr)
-        st.sync()
-        recv = all_to_all_records(send, send_sz[self.rank], recv_sz[self.rank], w, self.group)
-        torch.cuda.current_stream().synchronize()
-        self.exchange_bytes = int(send_sz[self.rank].sum() - send_sz[self.rank][self.rank]) * w * 8
-        # the owner's table = merge of everything it received (its own share included)
-        fresh = Aggregator(self.agg.key_types, self.agg.funcs)
-        n_recv = int(recv_sz[self.rank].sum())
-        lib.vk_agg_merge_partials(fresh._h, C.c_void_p(recv.data_ptr()), n_recv, st.ptr)
-        st.sync()
-        self.agg.close()
+        with torch.cuda.stream(self._tstream):
+            counts_dev = torch.empty(self.world, dtype=torch.int64, device=dev)
+            lib.vk_agg_partition_counts(self.agg._h, self.world, C.c_void_p(counts_dev.data_ptr()), st.ptr)
+            all_counts = torch.empty(self.world * self.world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_counts, counts_dev, group=self.group)
+            counts = all_counts.view(self.world, self.world).cpu().numpy()   # host sync 1: split sizes
+            send_off, send_sz, _recv_off, recv_sz = exchange_plan(counts)
+            self._recv_max = int(recv_sz.sum(axis=1).max())
+            my_total = int(send_sz[self.rank].sum())
+            send = torch.empty(max(my_total, 1) * w, dtype=torch.int64, device=dev)
+            offs = torch.from_numpy(np.ascontiguousarray(send_off[self.rank])).to(dev, non_blocking=True)
+            lib.vk_agg_export_partials(self.agg._h, self.world, C.c_void_p(offs.data_ptr()),
+                                       C.c_void_p(send.data_ptr()), st.ptr)
+            recv = all_to_all_records(send, send_sz[self.rank], recv_sz[self.rank], w, self.group)
+            self.exchange_bytes = int(send_sz[self.rank].sum() - send_sz[self.rank][self.rank]) * w * 8
+            # the owner's table = merge of everything it received (its own share included)
+            n_recv = int(recv_sz[self.rank].sum())
+            fresh = Aggregator(self.agg.key_types, self.agg.funcs, expected_groups=max(n_recv, 1))
+            lib.vk_agg_merge_partials(fresh._h, C.c_void_p(recv.data_ptr()), n_recv, st.ptr)
+            # `send` / `recv` / `offs` are torch allocations used by kernels on this same stream
+            recv.record_stream(self._tstream)
+        self.agg.close()   # drains the stream: the exchange buffers may be released after this
         self.agg = fresh
 
     def gather_raw(self):
         """Concatenate every rank's finalised groups on rank 0 (after repartition each
-        group lives on exactly one rank)."""
+        group lives on exactly one rank): finalise into a padded device block, one
+        `gather` of u64 words (the block's last column carries the group count)."""
         import torch
         import torch.distributed as dist
-        raw = self.agg.result_raw(self.stream)
         if self.world == 1:
-            return raw
-        keys, kv, cnt, lo, hi, valid = raw
-        g = len(cnt)
+            return self.agg.result_raw(self.stream)
+        st = self.stream
         dev = torch.device("cuda", torch.cuda.current_device())
-        sizes_dev = torch.tensor([g], dtype=torch.int64, device=dev)
-        sizes = [torch.empty_like(sizes_dev) for _ in range(self.world)]
-        dist.all_gather(sizes, sizes_dev, group=self.group)
-        sizes = [int(s.item()) for s in sizes]
-        gmax = max(max(sizes), 1)
-        nk, nf = keys.shape[0], lo.shape[0]
-        rows = nk * 2 + 1 + nf * 3
-        packed = np.zeros((rows, gmax), dtype=np.uint64)
-        packed[:nk, :g] = keys
-        packed[nk:2 * nk, :g] = kv
-        packed[2 * nk, :g] = cnt
-        packed[2 * nk + 1:2 * nk + 1 + nf, :g] = lo
-        packed[2 * nk + 1 + nf:2 * nk + 1 + 2 * nf, :g] = hi
-        packed[2 * nk + 1 + 2 * nf:, :g] = valid
-        t = torch.from_numpy(packed.view(np.int64)).to(dev)
-        gathered = [torch.empty_like(t) for _ in range(self.world)] if self.rank == 0 else None
-        dist.gather(t, gathered, dst=0, group=self.group)
-        if self.rank != 0:
-            return None
-        parts = [x.cpu().numpy().view(np.uint64)[:, :s] for x, s in zip(gathered, sizes)]
+        nk, nf = len(self.agg.key_vk), len(self.agg.funcs)
+        g = self.agg.num_groups(st)                               # host sync 2
+        if self._recv_max == 0:
+            # no repartition happened: agree on the padded width the slow way
+            with torch.cuda.stream(self._tstream):
+                m = torch.tensor([g], dtype=torch.int64, device=dev)
+                dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+                self._recv_max = int(m.item())
+        gmax = max(self._recv_max, 1)   # identical on every rank; g <= records received <= _recv_max
+        n64 = nk + 1 + 2 * nf          # keys | count | lo | hi
+        n8 = nk + nf                   # key_valid | valid (one byte per group, widened on the wire)
+        with torch.cuda.stream(self._tstream):
+            blk = torch.zeros((n64 + n8, gmax + 1), dtype=torch.int64, device=dev)
+            b8 = torch.zeros((max(n8, 1), gmax), dtype=torch.uint8, device=dev)
+            base, row = blk.data_ptr(), (gmax + 1) * 8
+            p64 = lambda i: base + i * row
+            p8 = lambda i: b8.data_ptr() + i * gmax
+            okeys = (C.c_void_p * max(nk, 1))(*[p64(i) for i in range(nk)])
+            okv = (C.c_void_p * max(nk, 1))(*[p8(i) for i in range(nk)])
+            olo = (C.c_void_p * max(nf, 1))(*[p64(nk + 1 + f) for f in range(nf)])
+            ohi = (C.c_void_p * max(nf, 1))(*[p64(nk + 1 + nf + f) for f in range(nf)])
+            oval = (C.c_void_p * max(nf, 1))(*[p8(nk + f) for f in range(nf)])
+            lib.vk_agg_result(self.agg._h, g, okeys, okv, C.c_void_p(p64(nk)), olo, ohi, oval, st.ptr)
+            if n8:
+                blk[n64:, :gmax] = b8[:n8]
+            blk[0, gmax] = g
+            gathered = [torch.empty_like(blk) for _ in range(self.world)] if self.rank == 0 else None
+            dist.gather(blk, gathered, dst=0, group=self.group)
+            if self.rank != 0:
+                return None
+            allb = torch.stack(gathered).cpu().numpy().view(np.uint64)   # host sync 3 (rank 0)
+        parts = []
+        for r in range(self.world):
+            gr = int(allb[r, 0, gmax])
+            parts.append(allb[r, :, :gr])
         allp = np.concatenate(parts, axis=1)
-        return (allp[:nk], allp[nk:2 * nk].astype(bool), allp[2 * nk], allp[2 * nk + 1:2 * nk + 1 + nf],
-                allp[2 * nk + 1 + nf:2 * nk + 1 + 2 * nf], allp[2 * nk + 1 + 2 * nf:].astype(bool))
+        return (allp[:nk], allp[n64:n64 + nk].astype(bool), allp[nk], allp[nk + 1:nk + 1 + nf],
+                allp[nk + 1 + nf:nk + 1 + 2 * nf], allp[n64 + nk:].astype(bool))
