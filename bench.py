@@ -43,6 +43,16 @@ ALG_BYTES_PER_ROW = 24  # f0 + i0 + f1, 8 B each (SURVEY 8d north-star row)
 FUNCS = [("COUNT_STAR", "", "count_star"), ("SUM", "f1", "sum_f1")]
 
 
+def _traffic_per_row():
+    """DRAM bytes per row of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["dram_bytes_per_row"])
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -320,8 +330,13 @@ def run_ours(args) -> dict:
         per_launch_ms = kernel_ms / kernel_launches
         per_launch_bytes = ALG_BYTES_PER_ROW * (kernel_rows / kernel_launches)
         achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
+        tpr = _traffic_per_row()
         result["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                              "frac": achieved / peak,
+                              "traffic": None if tpr is None else tpr * (kernel_rows / kernel_launches),
+                              "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per row of one "
+                                                "captured launch (profiles/r01_traffic.json) x rows per launch",
+                              "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src,
                               "kernel": "agg_fast_kernel", "launches": kernel_launches,
                               "avg_launch_ms": per_launch_ms,
                               "algorithmic_bytes_per_row": ALG_BYTES_PER_ROW}
