@@ -22,8 +22,16 @@ PBINC=$($PY -c "import pybind11;print(pybind11.get_include())")
 NPINC=$($PY -c "import numpy;print(numpy.get_include())")
 EXT=$($PY -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))")
 TARGET="$OUT/ref_vinum_lib$EXT"
+# GenericHashAggregate (string / any-type keys): generic_hash_aggregate.h:37 calls
+# Scalar::Equals(shared_ptr<Scalar>), an overload Arrow dropped after 3.0.  The header and its
+# .cpp are copied into the (git-ignored) build directory with that ONE token patched
+# (`*iter_two` -> `**iter_two`), compiled from there and deleted again; nothing else changes.
+PATCHED="$OUT/obj/patched"
+mkdir -p "$PATCHED"
+sed 's/Equals(\*iter_two)/Equals(**iter_two)/' "$SRC/operators/aggregate/generic_hash_aggregate.h" > "$PATCHED/generic_hash_aggregate.h"
+cp "$SRC/operators/aggregate/generic_hash_aggregate.cpp" "$PATCHED/generic_hash_aggregate.cpp"
 FLAGS="-O2 -std=c++20 -fPIC -fvisibility=hidden -w -include $HERE/compat.h \
-  -I$PAINC -I$SRC -I$SRC/operators -I$SRC/operators/aggregate -I$SRC/operators/sort \
+  -I$PATCHED -I$PAINC -I$SRC -I$SRC/operators -I$SRC/operators/aggregate -I$SRC/operators/sort \
   -I$PYINC -I$PBINC -I$NPINC"
 FILES="$HERE/ref_wrapper.cpp \
   $SRC/common/huge_int.cpp $SRC/common/array_iterators.cpp \
@@ -31,10 +39,12 @@ FILES="$HERE/ref_wrapper.cpp \
   $SRC/operators/aggregate/one_group_aggregate.cpp \
   $SRC/operators/aggregate/single_numerical_hash_aggregate.cpp \
   $SRC/operators/aggregate/multi_numerical_hash_aggregate.cpp \
+  $PATCHED/generic_hash_aggregate.cpp \
   $SRC/operators/sort/sort.cpp $SRC/operators/table_batch_reader.cpp"
-newest_src=$(stat -c %Y $FILES "$HERE/compat.h" | sort -n | tail -1)
+newest_src=$(stat -c %Y $HERE/ref_wrapper.cpp $SRC/common/*.cpp $SRC/operators/aggregate/*.cpp $SRC/operators/aggregate/*.h \
+  $SRC/operators/sort/sort.cpp "$HERE/compat.h" "$HERE/build_ref.sh" | sort -n | tail -1)
 if [ -f "$TARGET" ] && [ "$(stat -c %Y "$TARGET")" -ge "$newest_src" ]; then
-  echo "build_ref.sh: $TARGET up to date"; exit 0
+  rm -rf "$OUT/obj"; echo "build_ref.sh: $TARGET up to date"; exit 0
 fi
 pids=()
 objs=()

@@ -1,8 +1,7 @@
 // pybind11 bindings for the UNMODIFIED reference operators, compiled where they
 // lie under /root/reference/vinum_cpp/src (see build_ref.sh).  Mirrors the names
-// exported by the reference's vinum/core/vinum_lib.cpp:20-167, minus
-// GenericHashAggregate (generic_hash_aggregate.h:37 does not compile against
-// Arrow >= 4; string/any-type keys are out of the first-bar scope).
+// exported by the reference's vinum/core/vinum_lib.cpp:20-167.  GenericHashAggregate is built
+// from a copy of its header with one token patched for Arrow >= 4 (build_ref.sh).
 // TEST INFRASTRUCTURE ONLY: the product (vinum_b200) never loads this module.
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -10,6 +9,7 @@
 
 #include <single_numerical_hash_aggregate.h>
 #include <multi_numerical_hash_aggregate.h>
+#include <generic_hash_aggregate.h>
 #include <one_group_aggregate.h>
 #include <sort.h>
 #include <table_batch_reader.h>
@@ -55,6 +55,7 @@ PYBIND11_MODULE(ref_vinum_lib, m) {
 
     bind_aggregate<agg::SingleNumericalHashAggregate>(m, "SingleNumericalHashAggregate");
     bind_aggregate<agg::MultiNumericalHashAggregate>(m, "MultiNumericalHashAggregate");
+    bind_aggregate<agg::GenericHashAggregate>(m, "GenericHashAggregate");
 
     py::class_<agg::OneGroupAggregate>(m, "OneGroupAggregate")
         .def(py::init<const std::vector<agg::AggFuncDef>&>())

@@ -1,0 +1,4 @@
+source scripts/gpu_round.sh true
+rm -f gpurun_out/round.log
+TAILN=80 run sql 900 python -m pytest tests/test_sql_gpu.py -m gpu -q -x --tb=short
+TAILN=60 run sql_all 900 python -m pytest tests/test_sql_gpu.py -m gpu -q --tb=line

@@ -1,0 +1,139 @@
+"""CPU tests of the SQL front end: the parser (stand-in for the reference's pglast parser,
+vinum/parser/parser.py) yields the reference's tree shapes (modelled on
+vinum/tests/test_sql_syntax_tree.py) and the output column names of every parity case equal
+the names the REFERENCE produced (tests/golden/sql/manifest.json)."""
+import importlib.util
+import json
+import sys
+import types
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
+# the parser / AST are pure Python: load them without importing the CUDA library
+pkg = types.ModuleType("vb_sql_t")
+pkg.__path__ = [str(ROOT / "vinum_b200" / "sql")]
+sys.modules.setdefault("vb_sql_t", pkg)
+
+
+def _load(name):
+    full = f"vb_sql_t.{name}"
+    if full in sys.modules:
+        return sys.modules[full]
+    spec = importlib.util.spec_from_file_location(full, ROOT / "vinum_b200" / "sql" / f"{name}.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[full] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+A = _load("ast")
+P = _load("parser")
+import sql_cases  # noqa: E402
+
+COLS = ["id", "tax", "tip", "total", "lat", "vendor_id", "city"]
+
+
+def parse(sql):
+    return P.parse_sql(sql, COLS)
+
+
+def test_select_star_expands_schema():
+    q = parse("select * from tbl")
+    assert [c.name for c in q.select] == COLS and q.where is None
+
+
+def test_aliases_and_expression():
+    q = parse("select tip as total, tax + tip as with_tip from t")
+    assert isinstance(q.select[0], A.Column) and q.select[0].name == "tip" and q.select[0].alias == "total"
+    e = q.select[1]
+    assert e.op == A.Op.ADDITION and e.alias == "with_tip" and [a.name for a in e.args] == ["tax", "tip"]
+
+
+def test_functions_and_count_star():
+    q = parse("select np.power(10, np.min(total)) as exp, count(*) as cnt from t")
+    e = q.select[0]
+    assert e.op == A.Op.FUNCTION and e.function_name == "np.power" and e.alias == "exp"
+    assert e.args[0].value == 10 and e.args[1].function_name == "np.min" and e.args[1].args[0].name == "total"
+    c = q.select[1]
+    assert c.function_name == "count_star" and c.args == () and c.alias == "cnt"
+
+
+def test_where_and_is_nary_with_precedence():
+    q = parse("select * from tbl where vendor_id > 1 and lat < 4.5 and tip = 0 or tax <> 1")
+    w = q.where
+    assert w.op == A.Op.OR and len(w.args) == 2
+    assert w.args[0].op == A.Op.AND and len(w.args[0].args) == 3          # BoolExpr is n-ary
+    assert w.args[0].args[1].op == A.Op.LESS_THAN and w.args[0].args[1].args[1].value == 4.5
+    assert w.args[1].op == A.Op.NOT_EQUALS
+
+
+def test_parentheses_and_arithmetic_precedence():
+    q = parse("select (tax + tip) * 2 - total / 4 % 3, -tip, -5, ~id & 3 | 1 from t")
+    e = q.select[0]
+    assert e.op == A.Op.SUBTRACTION and e.args[0].op == A.Op.MULTIPLICATION and e.args[0].args[0].op == A.Op.ADDITION
+    assert e.args[1].op == A.Op.MODULUS and e.args[1].args[0].op == A.Op.DIVISION
+    assert q.select[1].op == A.Op.NEGATION
+    assert isinstance(q.select[2], A.Literal) and q.select[2].value == -5   # sign folded into the constant
+    assert q.select[3].op == A.Op.BINARY_NOT                                 # prefix ~ binds like any "other" operator
+
+
+def test_null_tests_in_between_like():
+    q = parse("select id from t where tip = null and tax != NULL and city is not null and id in (1,2,3) "
+              "and tax not between 1 and 2 and city like 'a%' and city not in ('x','y')")
+    ops = [a.op for a in q.where.args]
+    assert ops == [A.Op.IS_NULL, A.Op.IS_NOT_NULL, A.Op.IS_NOT_NULL, A.Op.IN, A.Op.NOT_BETWEEN, A.Op.LIKE, A.Op.NOT_IN]
+    assert q.where.args[3].args[1].value == [1, 2, 3]
+    assert [a.value for a in q.where.args[4].args[1:]] == [1, 2]
+    assert q.where.args[6].args[1].value == ["x", "y"]
+
+
+def test_group_having_order_limit():
+    q = parse("select city, sum(tip) s from t where tax > 0 group by city having sum(tip) > 10 "
+              "order by s desc, city limit 5 offset 2")
+    assert q.has_group_clause and [g.name for g in q.group_by] == ["city"]
+    assert q.having.op == A.Op.GREATER_THAN
+    assert [o.name for o in q.order_by] == ["s", "city"] and [s.name for s in q.sort_order] == ["DESC", "ASC"]
+    assert (q.limit, q.offset) == (5, 2)
+    assert q.select[1].alias == "s"
+    q = parse("select distinct city from t offset 3")
+    assert q.distinct and q.limit is None and q.offset == 0     # OFFSET is only read next to LIMIT
+
+
+def test_string_literal_quotes_and_concat():
+    q = parse("select city || '_' || 'it''s' from t")
+    e = q.select[0]
+    assert e.op == A.Op.CONCAT and e.args[1].value == "it's" and e.args[0].op == A.Op.CONCAT
+
+
+@pytest.mark.parametrize("sql", ["update t set a = 1", "select from", "select a from t where", "select a, from t",
+                                 "select a from t limit x", "select a from t order a", "select (a from t"])
+def test_errors(sql):
+    with pytest.raises(P.ParserError):
+        parse(sql)
+
+
+def test_every_parity_case_parses_and_names_match_reference():
+    manifest = json.loads((ROOT / "tests" / "golden" / "sql" / "manifest.json").read_text())
+    eng_names = None
+    for entry in manifest:
+        table = sql_cases.TABLES[entry["table"]]()
+        q = P.parse_sql(entry["sql"], table.schema.names)
+        assert entry["sql"] == sql_cases.CASES[entry["id"]][1], "manifest is stale: rerun oracle/gen_sql_golden.py"
+        # QueryPlanner._column_names (planner.py:290-323), restated in engine.output_names
+        out, index, unnamed = [], {}, 0
+        for e in q.select:
+            name = e.output_name()
+            if not name:
+                name = f"col_{unnamed}"
+                unnamed += 1
+            if name in index:
+                index[name] += 1
+                name = f"{name}_{index[name]}"
+            else:
+                index[name] = 0
+            out.append(name)
+        assert out == entry["columns"], entry["sql"]

@@ -1,0 +1,566 @@
+"""Query execution on the device operators.
+
+Host control flow only: it decides WHICH kernels run over WHICH columns, the way the
+reference's planner chains its operators (vinum/planner/planner.py:330-507):
+
+    scan(used columns -> HBM) -> WHERE -> [pre-aggregate projection] -> GROUP BY / aggregate
+        -> HAVING -> ORDER BY -> SELECT projection (+ column names) -> LIMIT/OFFSET -> host table
+
+Numeric / temporal / boolean columns live in HBM as `DeviceColumn`s and every operator on
+them is a CUDA kernel (vinum_b200.ops, vinum_b200.aggregate).  An aggregate query never
+materialises its WHERE: a `column <op> literal` predicate is fused into the aggregate kernel,
+anything else is passed to it as a byte mask.
+
+String columns stay on the HOST ("string predicate falls back to host"): their
+predicates run the reference's own NumPy / pyarrow.compute calls and only the resulting mask
+travels to the device; string GROUP BY keys are dictionary-encoded on the host and grouped
+on the device by their int32 codes.  Scalar functions (`to_int`, `sqrt`, `np.*` ...) are
+NumPy callables in the reference (vinum/core/functions.py:341-367) and are applied on the
+host here as well (functions.py in this package).
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+
+from .. import _lib as L
+from .. import ops
+from ..aggregate import Aggregator
+from ..device import DeviceBatch, DeviceColumn, Stream, default_stream, vk_dtype_of
+from .ast import (AGG_FUNCS, NUMPY_AGG_MAPPING, Column, Expression, Literal, Node, Op, Query, SortOrder,
+                  contains_aggregate, is_aggregate_call, walk)
+from .functions import call_host_function
+from .parser import ParserError, parse_sql
+
+
+class OperatorError(Exception):
+    """vinum/errors/__init__.py: OperatorError."""
+
+
+class HostColumn:
+    """A column the device path does not handle (strings): a pyarrow array on the host."""
+
+    def __init__(self, arr):
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks() if arr.num_chunks != 1 else arr.chunk(0)
+        self.arr = arr
+
+    @property
+    def length(self) -> int:
+        return len(self.arr)
+
+    def to_numpy(self) -> np.ndarray:
+        return self.arr.to_numpy(zero_copy_only=False)
+
+
+Value = Union[DeviceColumn, HostColumn, int, float, bool, str, None, list]
+
+_AGG_CODES = {"count_star": L.AGG_COUNT_STAR, "count": L.AGG_COUNT, "min": L.AGG_MIN, "max": L.AGG_MAX,
+              "sum": L.AGG_SUM, "avg": L.AGG_AVG}
+_CMP_FLIP = {"==": "==", "!=": "!=", ">": "<", ">=": "<=", "<": ">", "<=": ">="}
+_ARITH = {Op.ADDITION: "+", Op.SUBTRACTION: "-", Op.MULTIPLICATION: "*", Op.DIVISION: "/", Op.MODULUS: "%",
+          Op.BINARY_AND: "&", Op.BINARY_OR: "|", Op.BINARY_XOR: "#"}
+_CMP = {Op.EQUALS: "==", Op.NOT_EQUALS: "!=", Op.GREATER_THAN: ">", Op.GREATER_THAN_OR_EQUAL: ">=",
+        Op.LESS_THAN: "<", Op.LESS_THAN_OR_EQUAL: "<="}
+_NP_ARITH = {"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide, "%": np.mod, "&": np.bitwise_and,
+             "|": np.bitwise_or, "#": np.bitwise_xor}
+_NP_CMP = {"==": np.equal, "!=": np.not_equal, ">": np.greater, ">=": np.greater_equal, "<": np.less,
+           "<=": np.less_equal}
+
+
+def _is_col(v) -> bool:
+    return isinstance(v, (DeviceColumn, HostColumn))
+
+
+def _is_num(v) -> bool:
+    return isinstance(v, (int, float, bool, np.integer, np.floating, np.bool_))
+
+
+class Frame:
+    """Named columns of equal length: the batch flowing between operators."""
+
+    def __init__(self, n: int, cols: Optional[Dict[str, Value]] = None):
+        self.n = n
+        self.cols: Dict[str, Value] = dict(cols or {})
+
+
+class Engine:
+    def __init__(self, table: pa.Table, stream: Optional[Stream] = None):
+        self.table = table
+        self.st = stream or default_stream()
+        self.stats = {"kernels_before": int(L.lib.vk_launch_count())}
+
+    # ================================================================ binding
+    def _bind(self, q: Query) -> Query:
+        """Alias substitution, column validation, aggregate detection (Binder.bind,
+        vinum/planner/binder.py:41-89)."""
+        aliases = {e.alias: e for e in q.select if e.alias}
+
+        def subst(node):
+            if node is None:
+                return None
+            if isinstance(node, Column) and node.name in aliases:
+                return _copy(aliases[node.name])
+            if isinstance(node, Expression):
+                return Expression(node.op, tuple(subst(a) for a in node.args), node.function_name, node.alias)
+            return node
+
+        where = subst(q.where)
+        group_by = tuple(subst(g) for g in q.group_by)
+        having = subst(q.having)
+        order_by = tuple(subst(o) for o in q.order_by)
+        names = set(self.table.schema.names)
+        for clause in (q.select, (where,), group_by, (having,), order_by):
+            for root in clause:
+                if root is None:
+                    continue
+                for node in walk(root):
+                    if isinstance(node, Column) and node.name not in names:
+                        raise ParserError(f"Column '{node.name}' is not found.")  # binder.py:141-146
+        bound = Query(q.select, q.distinct, where, group_by, having, order_by, q.sort_order, q.limit, q.offset,
+                      q.has_group_clause)
+        bound.is_aggregate = (q.distinct or q.has_group_clause or any(contains_aggregate(e) for e in q.select))
+        if (q.distinct or q.has_group_clause) and group_by:
+            self._check_group_by(q.select, group_by)
+        return bound
+
+    @staticmethod
+    def _check_group_by(select, group_by) -> None:
+        """binder.py:209-265: a SELECT item is a GROUP BY column / expression or contains an aggregate."""
+        usage = 'Only aggregate functions and columns present in the "GROUP BY" clause are allowed.'
+        gb_keys = {g.key() for g in group_by}
+        for e in select:
+            if isinstance(e, Column):
+                if e.key() not in gb_keys:
+                    raise ParserError(f'Column "{e.name}" is not part of the "GROUP BY" clause. {usage}.')
+            elif isinstance(e, Expression):
+                if e.key() not in gb_keys and not contains_aggregate(e):
+                    opn = e.function_name or e.op.name
+                    raise ParserError(f'Operator "{opn}" is neither aggregate function nor part of the '
+                                      f'"GROUP BY" clause. {usage}.')
+            else:
+                raise ParserError(f'Literal "{e.value}" is not allowed in the aggregate query. {usage}.')
+
+    # ============================================================== execution
+    def execute(self, q: Query) -> pa.Table:
+        q = self._bind(q)
+        used = []
+        for clause in (q.select, (q.where,), q.group_by, (q.having,), q.order_by):
+            for root in clause:
+                if root is not None:
+                    for node in walk(root):
+                        if isinstance(node, Column) and node.name not in used:
+                            used.append(node.name)
+        frame = self._scan(used)
+        if q.is_aggregate:
+            frame, resolved = self._aggregate(q, frame)
+        else:
+            resolved = {}
+            if q.where is not None:
+                frame = self._filter(frame, self._as_mask(self._eval(q.where, frame, resolved), frame.n))
+        if q.having is not None:
+            frame = self._filter(frame, self._as_mask(self._eval(q.having, frame, resolved), frame.n))
+        if q.order_by:
+            frame = self._sort(frame, [self._eval(o, frame, resolved) for o in q.order_by], q.sort_order)
+        values = [self._eval(e, frame, resolved) for e in q.select]
+        names = output_names(q.select)
+        out = self._materialize(values, names, frame.n, q.limit, q.offset)
+        self.stats["kernels"] = int(L.lib.vk_launch_count()) - self.stats["kernels_before"]
+        return out
+
+    # -------------------------------------------------------------------- scan
+    def _scan(self, used: Sequence[str]) -> Frame:
+        """TableReaderOperator + the used-columns projection (planner.py:345-375): only the
+        referenced columns are copied to the device."""
+        t = self.table
+        frame = Frame(t.num_rows)
+        for name in used:
+            col = t.column(name)
+            if vk_dtype_of(col.type) is not None:
+                frame.cols[name] = DeviceColumn.from_arrow(col, self.st)
+            else:
+                frame.cols[name] = HostColumn(col)
+        return frame
+
+    # ------------------------------------------------------------- expressions
+    def _eval(self, node: Node, frame: Frame, resolved: Dict) -> Value:
+        k = node.key() if not isinstance(node, Literal) else None
+        if k is not None and k in resolved:
+            return frame.cols[resolved[k]]
+        if isinstance(node, Literal):
+            return node.value
+        if isinstance(node, Column):
+            if node.name not in frame.cols:
+                raise ParserError(f'Column "{node.name}" is not part of the "GROUP BY" clause. Only aggregate '
+                                  f'functions and columns present in the "GROUP BY" clause are allowed..')
+            return frame.cols[node.name]
+        op = node.op
+        if op in _ARITH:
+            return self._fold(_ARITH[op], [self._eval(a, frame, resolved) for a in node.args], self._arith2)
+        if op == Op.NEGATION or op == Op.BINARY_NOT:
+            x = self._eval(node.args[0], frame, resolved)
+            sym = "neg" if op == Op.NEGATION else "~"
+            if isinstance(x, DeviceColumn):
+                return ops.arith(sym, x, None, self.st)
+            if isinstance(x, HostColumn):
+                raise OperatorError(f"operator {sym} is not defined for column type {x.arr.type}")
+            return (np.negative if op == Op.NEGATION else np.invert)(x).item()
+        if op in _CMP:
+            a, b = (self._eval(x, frame, resolved) for x in node.args)
+            return self._compare(_CMP[op], a, b)
+        if op in (Op.AND, Op.OR):
+            masks = [self._as_mask(self._eval(a, frame, resolved), frame.n) for a in node.args]
+            out = masks[0]
+            for m in masks[1:]:  # folded left like BINARY_EXPRESSIONS (core/base.py:145-151)
+                out = ops.mask_and(out, m, self.st) if op == Op.AND else ops.mask_or(out, m, self.st)
+            return out
+        if op == Op.NOT:
+            return ops.mask_not(self._as_mask(self._eval(node.args[0], frame, resolved), frame.n), self.st)
+        if op in (Op.IS_NULL, Op.IS_NOT_NULL):
+            x = self._eval(node.args[0], frame, resolved)
+            if isinstance(x, DeviceColumn):
+                return ops.is_null(x, self.st) if op == Op.IS_NULL else ops.is_valid(x, self.st)
+            if isinstance(x, HostColumn):
+                m = pc.is_null(x.arr) if op == Op.IS_NULL else pc.is_valid(x.arr)
+                return self._upload_mask(m.to_numpy(zero_copy_only=False))
+            return (x is None) == (op == Op.IS_NULL)
+        if op in (Op.IN, Op.NOT_IN):
+            x = self._eval(node.args[0], frame, resolved)
+            values = node.args[1].value
+            neg = op == Op.NOT_IN
+            if isinstance(x, DeviceColumn) and all(_is_num(v) for v in values):
+                return ops.isin(x, list(values), neg, self.st)
+            if isinstance(x, HostColumn):
+                m = np.isin(x.to_numpy(), values, invert=neg)  # expressions.py:39-40
+                return self._upload_mask(m)
+            if isinstance(x, DeviceColumn):
+                raise OperatorError("IN over a numeric column needs numeric literals")
+            return (x in values) != neg
+        if op in (Op.BETWEEN, Op.NOT_BETWEEN):
+            x, lo, hi = (self._eval(a, frame, resolved) for a in node.args)
+            neg = op == Op.NOT_BETWEEN
+            if isinstance(x, DeviceColumn) and _is_num(lo) and _is_num(hi):
+                return ops.between(x, lo, hi, neg, self.st)
+            if neg:   # expressions.py:46-48
+                return ops.mask_or(self._as_mask(self._compare("<", x, lo), frame.n),
+                                   self._as_mask(self._compare(">", x, hi), frame.n), self.st)
+            return ops.mask_and(self._as_mask(self._compare(">=", x, lo), frame.n),
+                                self._as_mask(self._compare("<=", x, hi), frame.n), self.st)
+        if op in (Op.LIKE, Op.NOT_LIKE):
+            x, pattern = (self._eval(a, frame, resolved) for a in node.args)
+            if not isinstance(x, HostColumn) or not isinstance(pattern, str):
+                raise OperatorError("LIKE needs a string column and a string pattern")
+            rx = re.compile("^" + pattern.replace("_", ".").replace("%", ".*") + "$")  # functions.py:299-304
+            inv = op == Op.NOT_LIKE
+            m = np.fromiter((bool(rx.match(v)) != inv for v in x.to_numpy()), dtype=bool, count=x.length)
+            return self._upload_mask(m)
+        if op == Op.CONCAT:
+            return self._host_call("concat", [self._eval(a, frame, resolved) for a in node.args], frame.n)
+        if op == Op.FUNCTION:
+            if is_aggregate_call(node):
+                raise OperatorError(f"aggregate function {node.function_name}() is not allowed here")
+            return self._host_call(node.function_name, [self._eval(a, frame, resolved) for a in node.args], frame.n)
+        raise OperatorError(f"unsupported expression {op}")
+
+    @staticmethod
+    def _fold(sym, args, fn):
+        out = args[0]
+        for a in args[1:]:
+            out = fn(sym, out, a)
+        return out
+
+    def _arith2(self, sym: str, a: Value, b: Value) -> Value:
+        if isinstance(a, HostColumn) or isinstance(b, HostColumn) or isinstance(a, str) or isinstance(b, str):
+            raise OperatorError(f"operator {sym} is not defined for string operands")
+        if isinstance(a, DeviceColumn) or isinstance(b, DeviceColumn):
+            return ops.arith(sym, a, b, self.st)
+        with np.errstate(all="ignore"):
+            return _NP_ARITH[sym](a, b).item()   # constant folding with the same NumPy ufunc
+
+    def _compare(self, sym: str, a: Value, b: Value) -> Value:
+        if isinstance(a, DeviceColumn) and (isinstance(b, DeviceColumn) or _is_num(b)):
+            return ops.compare(a, sym, b, self.st)
+        if isinstance(b, DeviceColumn) and _is_num(a):
+            return ops.compare(b, _CMP_FLIP[sym], a, self.st)
+        if _is_col(a) or _is_col(b):
+            # a string operand: the reference's NumPy lambda on object arrays (expressions.py:30-36)
+            x = a.to_numpy() if isinstance(a, HostColumn) else (a.to_numpy(self.st) if isinstance(a, DeviceColumn) else a)
+            y = b.to_numpy() if isinstance(b, HostColumn) else (b.to_numpy(self.st) if isinstance(b, DeviceColumn) else b)
+            m = _NP_CMP[sym](x, y)
+            return self._upload_mask(np.asarray(m, dtype=bool))
+        return bool(_NP_CMP[sym](a, b))
+
+    def _host_call(self, name: str, args: List[Value], n: int) -> Value:
+        host_args = []
+        for a in args:
+            if isinstance(a, DeviceColumn):
+                arr = a.to_numpy(self.st)
+                valid = a.validity_to_numpy(self.st)
+                if valid is not None:  # NULL -> NaN view, like get_np_column (record_batch.py:100-125)
+                    arr = arr.astype(np.float64)
+                    arr[~valid] = np.nan
+                host_args.append(arr)
+            elif isinstance(a, HostColumn):
+                host_args.append(a.arr)
+            else:
+                host_args.append(a)
+        res = call_host_function(name, host_args)
+        return self._from_host(res)
+
+    def _from_host(self, res) -> Value:
+        if isinstance(res, (pa.Array, pa.ChunkedArray)):
+            if vk_dtype_of(res.type) is not None:
+                return DeviceColumn.from_arrow(res, self.st)
+            return HostColumn(res)
+        if isinstance(res, np.ndarray) and res.shape != ():
+            if res.dtype.kind in "iufb" and res.dtype.itemsize <= 8 and res.dtype != np.float16:
+                col = DeviceColumn.from_numpy(res if res.dtype != np.bool_ else res.astype(np.bool_), self.st)
+                col._host_ref = res
+                return col
+            return HostColumn(pa.array(res))
+        if isinstance(res, np.generic):
+            return res.item()
+        if isinstance(res, np.ndarray):
+            return res.item()
+        return res
+
+    def _upload_mask(self, m: np.ndarray) -> DeviceColumn:
+        m = np.ascontiguousarray(m, dtype=np.bool_)
+        col = DeviceColumn.from_numpy(m, self.st)
+        col._host_ref = m
+        return col
+
+    def _as_mask(self, v: Value, n: int) -> DeviceColumn:
+        if isinstance(v, DeviceColumn):
+            if v.dtype != L.BOOL8:
+                return ops.compare(v, "!=", 0, self.st)
+            return v
+        if isinstance(v, HostColumn):
+            raise OperatorError("a string expression cannot be used as a condition")
+        return self._upload_mask(np.full(n, bool(v), dtype=np.bool_))
+
+    # ------------------------------------------------------- filter / sort
+    def _filter(self, frame: Frame, mask: DeviceColumn) -> Frame:
+        """FilterOperator (algebra.py:108-123): one compaction kernel over every device column."""
+        names = [k for k, v in frame.cols.items() if isinstance(v, DeviceColumn)]
+        host = [k for k, v in frame.cols.items() if isinstance(v, HostColumn)]
+        out = Frame(0)
+        if names:
+            batch = DeviceBatch([frame.cols[k] for k in names], names, frame.n)
+            res = ops.filter_batch(batch, ops.Predicate.from_mask(mask), self.st)
+            out.n = res.num_rows
+            for k, c in zip(names, res.columns):
+                out.cols[k] = c
+        if host or not names:
+            hm = mask.to_numpy(self.st).astype(bool)
+            out.n = int(hm.sum())
+            for k in host:
+                out.cols[k] = HostColumn(frame.cols[k].arr.filter(pa.array(hm)))
+        return out
+
+    def _sort(self, frame: Frame, keys: List[Value], orders: Sequence[SortOrder]) -> Frame:
+        """SortOperator (algebra.py:126-201) -> device radix sort + gather."""
+        dev_keys, dev_orders = [], []
+        for k, o in zip(keys, orders):
+            if not _is_col(k):
+                continue  # a constant key does not order anything
+            if isinstance(k, HostColumn):
+                k = self._string_ranks(k)
+            if k.dtype == L.BOOL8:
+                raise OperatorError("Sorting by boolean column is not supported yet.")  # algebra.py:191-201
+            dev_keys.append(k)
+            dev_orders.append(L.DESC if o == SortOrder.DESC else L.ASC)
+        if not dev_keys or frame.n == 0:
+            return frame
+        idx = ops.sort_indices(dev_keys, dev_orders, self.st)
+        out = Frame(frame.n)
+        hidx = None
+        for name, v in frame.cols.items():
+            if isinstance(v, DeviceColumn):
+                out.cols[name] = ops.take(v, idx, self.st)
+            else:
+                if hidx is None:
+                    hidx = pa.array(idx.to_numpy(self.st))
+                out.cols[name] = HostColumn(v.arr.take(hidx))
+        return out
+
+    def _string_ranks(self, col: HostColumn) -> DeviceColumn:
+        """Order-preserving int32 codes of a string column (NULLs stay NULL -> sorted last)."""
+        arr = col.arr
+        uniq = pc.unique(arr).drop_null()
+        order = pc.sort_indices(uniq)
+        sorted_uniq = uniq.take(order)
+        codes = pc.index_in(arr, value_set=sorted_uniq)
+        return DeviceColumn.from_arrow(codes, self.st)
+
+    # ------------------------------------------------------------- aggregate
+    def _aggregate(self, q: Query, frame: Frame) -> Tuple[Frame, Dict]:
+        """WHERE + pre-aggregate projection + AggregateOperator (planner.py:383-470,
+        core/aggregate.py:32-124) on the fused / masked device aggregate."""
+        st = self.st
+        # ---- predicate: fused `column <op> literal` or a byte mask; never a compaction ----
+        pred = None
+        if q.where is not None:
+            w = q.where
+            fused = None
+            if isinstance(w, Expression) and w.op in _CMP and len(w.args) == 2:
+                a, b = w.args
+                sym = _CMP[w.op]
+                if isinstance(b, Column) and isinstance(a, Literal):
+                    a, b, sym = b, a, _CMP_FLIP[sym]
+                if isinstance(a, Column) and isinstance(b, Literal) and _is_num(b.value):
+                    col = frame.cols[a.name]
+                    if isinstance(col, DeviceColumn):
+                        fused = ops.Predicate.compare(col, sym, b.value)
+            pred = fused or ops.Predicate.from_mask(self._as_mask(self._eval(w, frame, {}), frame.n))
+
+        # ---- group keys ----
+        group_exprs: List[Node] = []
+        seen = set()
+        for g in list(q.group_by) + (list(q.select) if q.distinct else []):
+            if isinstance(g, Literal):
+                continue
+            if g.key() not in seen:
+                seen.add(g.key())
+                group_exprs.append(g)
+        # ---- aggregate calls anywhere in SELECT / HAVING / ORDER BY ----
+        agg_calls: List[Expression] = []
+        seen_a = set()
+        for root in list(q.select) + [q.having] + list(q.order_by):
+            if root is None:
+                continue
+            for node in walk(root):
+                if is_aggregate_call(node) and node.key() not in seen_a:
+                    seen_a.add(node.key())
+                    agg_calls.append(node)
+
+        key_vals: List[DeviceColumn] = []
+        key_post = []   # how to turn each key's result array back into the user's type
+        for g in group_exprs:
+            v = self._eval(g, frame, {})
+            if not _is_col(v):
+                v = self._from_host(np.full(frame.n, v))
+            if isinstance(v, HostColumn):
+                enc = pc.dictionary_encode(v.arr)
+                if isinstance(enc, pa.ChunkedArray):
+                    enc = enc.combine_chunks()
+                key_vals.append(DeviceColumn.from_arrow(enc.indices, st))
+                key_post.append(("dict", enc.dictionary))
+            elif v.dtype == L.BOOL8:
+                as_u8 = DeviceColumn(v.data, v.validity, v.offset, v.length, L.U8, pa.uint8(), v.null_count, v.data_ptr)
+                key_vals.append(as_u8)
+                key_post.append(("bool", None))
+            else:
+                key_vals.append(v)
+                key_post.append((None, None))
+
+        specs, agg_vals = [], []
+        for call in agg_calls:
+            fname = NUMPY_AGG_MAPPING.get(call.function_name.lower(), call.function_name.lower())
+            code = _AGG_CODES[fname]
+            if code == L.AGG_COUNT_STAR:
+                specs.append((code, None))
+                agg_vals.append(None)
+                continue
+            if len(call.args) != 1:
+                raise OperatorError(f"{fname}() takes exactly one argument")
+            v = self._eval(call.args[0], frame, {})
+            if not _is_col(v):
+                v = self._from_host(np.full(frame.n, v))
+            if isinstance(v, HostColumn):
+                if code != L.AGG_COUNT:
+                    raise OperatorError(f"{fname}() over a string column is not on the device path")
+                # COUNT(str): only the validity matters
+                valid = pc.is_valid(v.arr)
+                dummy = pa.array(np.zeros(v.length, dtype=np.uint8), mask=~valid.to_numpy(zero_copy_only=False))
+                v = DeviceColumn.from_arrow(dummy, st)
+            specs.append((code, v.arrow_type))
+            agg_vals.append(v)
+
+        agg = Aggregator([k.arrow_type for k in key_vals], specs)
+        try:
+            if key_vals or any(v is not None for v in agg_vals):
+                agg.update(key_vals, agg_vals, pred, st)
+            else:
+                agg.update_count_rows(frame.n, pred, st)
+            keys_out, aggs_out = agg.result_arrays(st)
+            self.stats["agg_path"] = agg.last_path
+        finally:
+            agg.close()
+
+        out = Frame(len(aggs_out[0]) if aggs_out else (len(keys_out[0]) if keys_out else 1))
+        resolved: Dict = {}
+        for i, (g, arr, (kind, aux)) in enumerate(zip(group_exprs, keys_out, key_post)):
+            if kind == "dict":
+                arr = aux.take(arr) if len(aux) else pa.array([None] * len(arr), type=aux.type)
+            elif kind == "bool":
+                arr = arr.cast(pa.bool_())
+            name = f"__key{i}"
+            out.cols[name] = self._from_host(arr)
+            resolved[g.key()] = name
+            if isinstance(g, Column):
+                out.cols.setdefault(g.name, out.cols[name])
+        for i, (call, arr) in enumerate(zip(agg_calls, aggs_out)):
+            name = f"__agg{i}"
+            out.cols[name] = self._from_host(arr)
+            resolved[call.key()] = name
+        return out, resolved
+
+    # ------------------------------------------------------------ materialise
+    def _materialize(self, values: List[Value], names: List[str], n: int, limit: Optional[int], offset: int) -> pa.Table:
+        """ProjectOperator(col_names) + SliceOperator + MaterializeTableOperator
+        (planner.py:484-505, algebra.py:204-247,290-295)."""
+        lo, hi = 0, n
+        if limit is not None:
+            lo = min(offset, n)
+            hi = min(lo + limit, n)
+        arrays = []
+        for v in values:
+            if isinstance(v, DeviceColumn):
+                arrays.append(v.slice(lo, hi - lo).to_arrow(self.st))
+            elif isinstance(v, HostColumn):
+                arrays.append(v.arr.slice(lo, hi - lo))
+            else:
+                arrays.append(pa.array(np.repeat(np.array([v]), hi - lo)) if v is not None
+                              else pa.nulls(hi - lo))   # algebra.py:76-87
+        return pa.Table.from_arrays(arrays, names=names)
+
+
+def _copy(node):
+    if isinstance(node, Expression):
+        return Expression(node.op, node.args, node.function_name, node.alias)
+    if isinstance(node, Column):
+        return Column(node.name, node.alias)
+    return Literal(node.value, node.alias)
+
+
+def output_names(select: Sequence[Node]) -> List[str]:
+    """QueryPlanner._column_names (planner.py:290-323): alias / column name / function name,
+    else col_N; repeated names get _1, _2, ... suffixes."""
+    out, index, unnamed = [], {}, 0
+    for e in select:
+        name = e.output_name()
+        if not name:
+            name = f"col_{unnamed}"
+            unnamed += 1
+        if name in index:
+            index[name] += 1
+            name = f"{name}_{index[name]}"
+        else:
+            index[name] = 0
+        out.append(name)
+    return out
+
+
+def execute_sql(sql: str, table: pa.Table, stream: Optional[Stream] = None, stats: Optional[dict] = None) -> pa.Table:
+    """Parse + plan + run one SELECT over a host pyarrow.Table; the result is a host table."""
+    q = parse_sql(sql, table.schema.names)
+    eng = Engine(table, stream)
+    out = eng.execute(q)
+    if stats is not None:
+        stats.update(eng.stats)
+    return out
