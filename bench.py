@@ -11,9 +11,10 @@ aggregate state, fused filter->hash-aggregate over every row, finalise, read the
 groups back).  `value` = rows/s with the table already in HBM; the table (64 GB, 24 GB
 touched per step) is far larger than L2, so no flush is needed between steps.
 
-`e2e` runs the same query through the public host API (vinum_b200.executor
-.filter_aggregate) on a pinned host table: every step copies the three referenced
-columns host->device and reads the result back.
+`e2e` runs the same query through the public API the reference's users call --
+`Table.sql(QUERY)` -- on a host Arrow table in pinned memory: every step parses and plans
+the SQL, copies the three referenced columns host->device (double-buffered chunks) and
+reads the result back.
 
 N > 1 (torchrun): each rank owns its own 1e9-row shard (weak scaling), aggregates it
 locally, repartitions the partial groups with one NCCL all-to-all and gathers on rank 0.
@@ -63,56 +64,72 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons during the timed region.  NVML is read in-process
+    (nvidia_ml_py) every 10 ms -- polling the nvidia-smi binary instead takes the driver lock for
+    milliseconds at a time and shows up as step-time jitter; nvidia-smi is the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device_index: int):
         self.idx = device_index
-        self.samples = []
-        self.proc = None
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
+
+    def _smi_loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(float(parts[0]))
+                self.mx.append(float(parts[1]))
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.25)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-relative index -> NVML handle through the UUID-free common case
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.idx
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
         except Exception:
-            self.proc = None
-            return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            parts = [x.strip() for x in s.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler not started"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "samples": len(self.sm), "source": self.source, "reasons": sorted(self.reasons)}
 
 
 # ---------------------------------------------------------------- reference arm ----
@@ -283,18 +300,20 @@ def run_ours(args) -> dict:
     value = rows * world / (ms_per_step / 1e3)
 
     # ---- end to end through the public host API (pinned host table, rank-local) ----
-    from vinum_b200.executor import filter_aggregate
+    # The call a user makes: Table.sql(<the query>) on a host Arrow table (pinned buffers).
     e2e_rows = args.e2e_rows
     host_cols = {n: vb.pinned_array(datagen.host_column(n, row0, e2e_rows)) for n in ("i0", "f0", "f1")}
     host_table = pa.table({n: pa.array(a) for n, a in host_cols.items()})
-    stats = {}
-    filter_aggregate(host_table, ["i0"], FUNCS, ("f0", ">", 0.5), stats=stats)  # warm-up
+    user_table = vb.Table.from_arrow(host_table)
+    user_table.sql(QUERY)  # warm-up
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
-        out = filter_aggregate(host_table, ["i0"], FUNCS, ("f0", ">", 0.5), stats=stats)
+        out = user_table.sql(QUERY).to_arrow()
     st.sync()
+    stats = user_table.last_stats
+    assert stats.get("streamed") and stats.get("agg_path") == 1, stats
     e2e_t = (time.perf_counter() - t0) / e2e_steps
     if distributed:
         t = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
@@ -324,7 +343,7 @@ def run_ours(args) -> dict:
         "e2e": {"value": e2e_value, "unit": "rows/s", "rows_per_step": e2e_rows * world,
                 "h2d_bytes_per_step": int(stats.get("h2d_bytes", 0)) * world,
                 "d2h_bytes_per_step": int(stats.get("d2h_bytes", 0)), "ms_per_step": e2e_t * 1e3,
-                "api": "vinum_b200.executor.filter_aggregate(pyarrow.Table on pinned host memory)"},
+                "api": "vinum_b200.Table.from_arrow(host pyarrow.Table, pinned buffers).sql(QUERY)"},
     }
     if not distributed and kernel_launches:
         per_launch_ms = kernel_ms / kernel_launches

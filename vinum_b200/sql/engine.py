@@ -155,10 +155,14 @@ class Engine:
                     for node in walk(root):
                         if isinstance(node, Column) and node.name not in used:
                             used.append(node.name)
-        frame = self._scan(used)
-        if q.is_aggregate:
+        streamed = self._stream_aggregate(q) if q.is_aggregate else None
+        if streamed is not None:
+            frame, resolved = streamed
+        elif q.is_aggregate:
+            frame = self._scan(used)
             frame, resolved = self._aggregate(q, frame)
         else:
+            frame = self._scan(used)
             resolved = {}
             if q.where is not None:
                 frame = self._filter(frame, self._as_mask(self._eval(q.where, frame, resolved), frame.n))
@@ -398,6 +402,77 @@ class Engine:
         return DeviceColumn.from_arrow(codes, self.st)
 
     # ------------------------------------------------------------- aggregate
+    def _stream_aggregate(self, q: Query) -> Optional[Tuple[Frame, Dict]]:
+        """The streaming fast path (vinum_b200.executor.filter_aggregate): when every group key and
+        aggregate argument is a plain null-free numeric column and the WHERE is `column <op>
+        literal`, the table is never resident as a whole -- 2^24-row chunks of just the
+        referenced columns are copied host -> device on a copy stream (true DMA from pinned
+        Arrow buffers) while the fused filter -> aggregate kernel consumes the previous chunk."""
+        from ..executor import filter_aggregate
+        if q.distinct or not q.group_by:
+            return None
+        schema = self.table.schema
+
+        def plain(node) -> Optional[str]:
+            if not isinstance(node, Column):
+                return None
+            col = self.table.column(node.name)
+            dt = vk_dtype_of(col.type)
+            if dt is None or dt == L.BOOL8 or col.null_count:
+                return None
+            return node.name
+
+        keys = [plain(g) for g in q.group_by]
+        if any(k is None for k in keys) or len(set(keys)) != len(keys):
+            return None
+        calls: List[Expression] = []
+        seen = set()
+        for root in list(q.select) + [q.having] + list(q.order_by):
+            if root is None:
+                continue
+            for node in walk(root):
+                if is_aggregate_call(node) and node.key() not in seen:
+                    seen.add(node.key())
+                    calls.append(node)
+        if not calls:
+            return None
+        funcs = []
+        for i, call in enumerate(calls):
+            fname = NUMPY_AGG_MAPPING.get(call.function_name.lower(), call.function_name.lower())
+            if fname == "count_star":
+                funcs.append(("COUNT_STAR", "", f"__agg{i}"))
+                continue
+            if len(call.args) != 1 or plain(call.args[0]) is None:
+                return None
+            funcs.append((fname.upper(), call.args[0].name, f"__agg{i}"))
+        where = None
+        if q.where is not None:
+            w = q.where
+            if not (isinstance(w, Expression) and w.op in _CMP and len(w.args) == 2):
+                return None
+            a, b = w.args
+            sym = _CMP[w.op]
+            if isinstance(b, Column) and isinstance(a, Literal):
+                a, b, sym = b, a, _CMP_FLIP[sym]
+            if not (isinstance(b, Literal) and _is_num(b.value) and not isinstance(b.value, bool)) or plain(a) is None:
+                return None
+            where = (a.name, sym, b.value)
+        stats: dict = {}
+        rb = filter_aggregate(self.table, keys, funcs, where, stats=stats)
+        self.stats.update({"agg_path": stats.get("agg_path"), "streamed": True, "h2d_bytes": stats.get("h2d_bytes"),
+                           "d2h_bytes": stats.get("d2h_bytes")})
+        out = Frame(rb.num_rows)
+        resolved: Dict = {}
+        for i, (g, name) in enumerate(zip(q.group_by, keys)):
+            col = self._from_host(rb.column(i))
+            out.cols[f"__key{i}"] = col
+            out.cols[name] = col
+            resolved[g.key()] = f"__key{i}"
+        for i, call in enumerate(calls):
+            out.cols[f"__agg{i}"] = self._from_host(rb.column(len(keys) + i))
+            resolved[call.key()] = f"__agg{i}"
+        return out, resolved
+
     def _aggregate(self, q: Query, frame: Frame) -> Tuple[Frame, Dict]:
         """WHERE + pre-aggregate projection + AggregateOperator (planner.py:383-470,
         core/aggregate.py:32-124) on the fused / masked device aggregate."""
