@@ -2,8 +2,9 @@
 vinum_cpp/test/hash_agg_test.cpp (fixture tables :155-283, expected batches :340-778).
 
 The gtest target cannot be built here (it downloads googletest and needs
-ArrowTesting), so its fixtures are restated as data.  Numeric-key cases only:
-string / bool keys (GenericHashAggregate) are a SURVEY 8f "next" row.
+ArrowTesting), so its fixtures are restated as data.  `cases()` are the numeric-key
+vectors; `generic_cases()` the string / bool key and string MIN/MAX vectors of
+GenericHashAggregate.
 
 Each case: (name, table, groupby_cols, agg_cols, funcs[(type, column, out_name)],
 expected pyarrow.RecordBatch, sort_cols).  As in the gtest (:108-133) the table is fed
@@ -154,6 +155,62 @@ def cases():
     out.append(("empty_table__agg_funcs", empty_batch_table(), [], [],
                 [("COUNT_STAR", "", "count_star")],
                 pa.RecordBatch.from_arrays([pa.array([0], type=pa.uint64())], names=["count_star"]), []))
+    return out
+
+
+def generic_table() -> pa.Table:
+    """The string / bool columns of CreateTestTable (hash_agg_test.cpp:163-183) next to the numeric ones."""
+    t = test_table()
+    extra = {
+        "date": _arr(["", "2020-10-09T04:26:53", "2020-10-10T04:26:52", "2020-10-11T04:26:51", "2020-10-12T04:26:50",
+                      "2020-10-13T04:26:49", "0", "2020-10-15T04:26:47"], [F, T, T, T, T, T, F, T], pa.string()),
+        "is_vendor": _arr([True, True, False, False, True, False, False, False], [T, T, T, F, T, F, F, F], pa.bool_()),
+        "city_from": _arr(["", "Munich", "", "San Francisco", "Berlin", "Munich", "Berlin", "Berlin"],
+                          [F, T, F, T, T, T, T, T], pa.string()),
+        "city_to": _arr(["Munich", "Riva", "Naples", "Naples", "Riva", "Riva", "Munich", "Munich"], [T] * 8, pa.string()),
+        "name": _arr(["Joe", "", "Joseph", "Joseph", "", "Jonas", "Joseph", "Joe"], [T, F, T, T, F, T, T, T], pa.string()),
+    }
+    for k, v in extra.items():
+        t = t.append_column(k, v)
+    return t
+
+
+def generic_cases():
+    out = []
+    # CreateStringGrp_DoubleArgFuncs, :286-338 (NULL key group sorts last)
+    out.append(("string_grp__double_arg_funcs", generic_table(), ["city_from"], ["city_from"],
+                [("COUNT_STAR", "", "count"), ("COUNT", "total", "count_9"), ("MIN", "lat", "min_6"),
+                 ("MAX", "lat", "max_6"), ("SUM", "lat", "sum_6"), ("AVG", "lat", "avg_6")],
+                pa.RecordBatch.from_arrays([
+                    _arr(["Berlin", "Munich", "San Francisco", ""], [T, T, T, F], pa.string()),
+                    pa.array([3, 2, 1, 2], type=pa.uint64()),
+                    pa.array([1, 1, 1, 1], type=pa.uint64()),
+                    pa.array([44.89, 48.51, 42.89, 44.89], type=pa.float64()),
+                    pa.array([52.51, 48.51, 42.89, 52.51], type=pa.float64()),
+                    pa.array([142.29, 97.02, 42.89, 97.4], type=pa.float64()),
+                    pa.array([47.43, 48.51, 42.89, 48.7], type=pa.float64()),
+                ], names=["city_from", "count", "count_9", "min_6", "max_6", "sum_6", "avg_6"]), [0]))
+    # CreateInt64Grp_StringArgFuncs, :439-477
+    dates = _arr(["", "2020-10-09T04:26:53", "2020-10-10T04:26:52", "2020-10-11T04:26:51", "2020-10-12T04:26:50",
+                  "2020-10-13T04:26:49", "", "2020-10-15T04:26:47"], [F, T, T, T, T, T, F, T], pa.string())
+    out.append(("int64_grp__string_arg_funcs", generic_table(), ["id"], ["id"],
+                [("COUNT", "date", "count_2"), ("MIN", "date", "min_2"), ("MAX", "date", "max_2")],
+                pa.RecordBatch.from_arrays([
+                    pa.array([1, 2, 3, 4, 5, 6, 7, 8], type=pa.int64()),
+                    pa.array([0, 1, 1, 1, 1, 1, 0, 1], type=pa.uint64()),
+                    dates, dates,
+                ], names=["id", "count_2", "min_2", "max_2"]), [0]))
+    # CreateBooleanGrp_DateArgFuncs, :601-650
+    t32 = lambda vals, valid: pa.array([v if ok else None for v, ok in zip(vals, valid)], type=pa.int32()).cast(T32_MS)  # noqa: E731
+    out.append(("boolean_grp__date_arg_funcs", generic_table(), ["is_vendor"], ["is_vendor"],
+                [("COUNT_STAR", "", "count"), ("MIN", "time32", "min_12"), ("MAX", "time32", "max_14"),
+                 ("SUM", "time32", "sum_13"), ("AVG", "time32", "avg_13")],
+                pa.RecordBatch.from_arrays([
+                    _arr([False, True, False], [T, T, F], pa.bool_()),
+                    pa.array([1, 3, 4], type=pa.uint64()),
+                    t32([0, 7, 7], [F, T, T]), t32([0, 41, 130], [F, T, T]), t32([0, 48, 267], [F, T, T]),
+                    _arr([0.0, 24.0, 89.0], [F, T, T], pa.float64()),
+                ], names=["is_vendor", "count", "min_12", "max_14", "sum_13", "avg_13"]), [0]))
     return out
 
 

@@ -4,6 +4,7 @@ from pathlib import Path
 
 import numpy as np
 import pyarrow as pa
+import pyarrow.compute  # noqa: F401
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -48,6 +49,12 @@ def canonical(batch, key_cols):
                 code = np.where(bits >> np.uint64(63), ~bits, bits | np.uint64(1 << 63))
             else:
                 code = np.where(np.isnan(v), np.inf, v)
+        elif pa.types.is_string(t) or pa.types.is_large_string(t):
+            uniq = pa.compute.unique(col).drop_null()
+            ranked = uniq.take(pa.compute.sort_indices(uniq))
+            code = np.asarray(pa.compute.index_in(col, value_set=ranked).fill_null(0).to_numpy(zero_copy_only=False)).astype(np.uint64)
+        elif pa.types.is_boolean(t):
+            code = np.asarray(col.cast(pa.uint8()).fill_null(0).to_numpy(zero_copy_only=False)).astype(np.uint64)
         else:
             phys = pa.int32() if (pa.types.is_date32(t) or pa.types.is_time32(t)) else (
                 pa.int64() if pa.types.is_temporal(t) else t)

@@ -181,6 +181,48 @@ def test_aggregate_matches_gtest_vectors(vb, case):
     assert_tables_match(got, expected, rtol=FLOAT_RTOL)
 
 
+@pytest.mark.parametrize("case", G.generic_cases(), ids=lambda c: c[0])
+def test_generic_aggregate_matches_gtest_vectors(vb, case):
+    """GenericHashAggregate (string / bool keys, string MIN/MAX): the reference's expected
+    batches (hash_agg_test.cpp:286-338, :439-477, :601-650), table fed in two halves."""
+    name, table, gb, ac, funcs, expected, sort_cols = case
+    agg = vb.vinum_lib.GenericHashAggregate(gb, ac, _lib_funcs(vb.vinum_lib, funcs))
+    for b in G.split_in_two(table):
+        agg.next(b)
+    got = G.sort_result(agg.result(), sort_cols)
+    assert_tables_match(got, expected, rtol=FLOAT_RTOL)
+
+
+def test_generic_aggregate_random_vs_compiled_reference(vb):
+    """String + numeric keys with NULLs, many batches, against the reference's own
+    GenericHashAggregate (oracle/_ref)."""
+    from oracle import ref
+    lib = ref.ref_lib()
+    if lib is None or not hasattr(lib, "GenericHashAggregate"):
+        pytest.skip("oracle/_ref with GenericHashAggregate is not built")
+    rng = np.random.default_rng(7)
+    n = 50_000
+    words = np.array(["alpha", "beta", "gamma", "delta", "", "epsilon", "zeta", "a much longer key value"], dtype=object)
+    table = pa.table({
+        "s": pa.array(words[rng.integers(0, len(words), n)], type=pa.string(), mask=rng.random(n) < 0.05),
+        "k": pa.array(rng.integers(0, 5, n).astype(np.int16), mask=rng.random(n) < 0.05),
+        "b": pa.array(rng.random(n) < 0.5, mask=rng.random(n) < 0.1),
+        "v": pa.array(rng.normal(0, 10, n), mask=rng.random(n) < 0.1),
+        "w": pa.array(rng.integers(-1000, 1000, n).astype(np.int64)),
+        "t": pa.array(words[rng.integers(0, len(words), n)], type=pa.string(), mask=rng.random(n) < 0.2),
+    })
+    funcs = [("COUNT_STAR", "", "c"), ("COUNT", "t", "ct"), ("SUM", "v", "sv"), ("AVG", "w", "aw"), ("MIN", "v", "mv"),
+             ("MAX", "w", "xw"), ("MIN", "t", "mt"), ("MAX", "t", "xt")]
+    for gb in (["s"], ["s", "k"], ["b", "s", "k"]):
+        want_agg = lib.GenericHashAggregate(gb, gb, [lib.AggFuncDef(getattr(lib.AggFuncType, t), c, o) for t, c, o in funcs])
+        got_agg = vb.vinum_lib.GenericHashAggregate(gb, gb, _lib_funcs(vb.vinum_lib, funcs))
+        for b in table.to_batches(max_chunksize=7000):
+            want_agg.next(b)
+            got_agg.next(b)
+        assert_tables_match(got_agg.result(), want_agg.result(), key_cols=gb, rtol=FLOAT_RTOL,
+                            float_exact_cols=["mv"])
+
+
 @pytest.mark.parametrize("case", MAN["agg"], ids=lambda c: f"{c['table']}.{c['name']}")
 def test_aggregate_matches_reference_fixture(vb, case):
     table = read_arrow(f"{case['table']}.in.arrow")

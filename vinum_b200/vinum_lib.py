@@ -6,7 +6,7 @@ the GPU through the C ABI (include/vinum_b200.h):
 
     AggFuncType, SortOrder, AggFuncDef,
     SingleNumericalHashAggregate, MultiNumericalHashAggregate, OneGroupAggregate,
-    GenericHashAggregate (string / any-type keys: not on the device path yet),
+    GenericHashAggregate (string keys: dictionary codes on the device, strings stay on the host),
     Sort, TableBatchReader, import_pyarrow
 
 `next(batch)` takes a host `pyarrow.RecordBatch` (as the reference does), copies only
@@ -187,15 +187,190 @@ class MultiNumericalHashAggregate(_BaseAggregate):
 
 
 class GenericHashAggregate(_BaseAggregate):
-    """vinum_lib.cpp:92-109.  Numeric keys run on the device; string / bool / nested
-    keys (generic_hash_aggregate.h:9-43) are a SURVEY 8f 'next' row."""
+    """vinum_lib.cpp:92-109; generic_hash_aggregate.{h:9-43,cpp:6-51}: keys of ANY type.
+
+    Numeric / temporal keys go to the device as they are.  String keys never enter HBM: every
+    batch is dictionary-encoded on the host against one dictionary per key column that lives
+    as long as the operator, and the device groups by the int32 codes (NULL stays NULL);
+    boolean keys are grouped as uint8.  Aggregates over numeric columns run on the device as
+    usual.  COUNT over a string column only needs its validity; MIN / MAX over strings
+    (StringMinMaxFunc, agg_funcs.h:219-261) are a host step (pyarrow's hash aggregate per
+    batch, merged at result()) joined to the device result by key."""
     _min_keys = 1
 
+    def __init__(self, groupby_cols, agg_cols, agg_funcs):
+        super().__init__(groupby_cols, agg_cols, agg_funcs)
+        self._key_kind: List[str] = []
+        self._dicts: List[Optional[dict]] = []      # string key -> {value: code}
+        self._dict_values: List[Optional[list]] = []
+        self._str_funcs: List[int] = []             # indices of MIN/MAX functions over string columns
+        self._str_partials: List[pa.Table] = []
+        self._user_key_types: List[pa.DataType] = []
+
     def _check_key_types(self, types) -> None:
-        for t in types:
-            if not (pa.types.is_integer(t) or pa.types.is_floating(t) or pa.types.is_temporal(t)):
-                raise NotImplementedError(
-                    f"GenericHashAggregate over key type {t} is not implemented on the device path")
+        return
+
+    @staticmethod
+    def _is_str(t) -> bool:
+        return pa.types.is_string(t) or pa.types.is_large_string(t)
+
+    def _ensure_init(self, schema: pa.Schema) -> None:
+        if self._agg is not None:
+            return
+        for name in self._groupby_cols + self._agg_cols:
+            if schema.get_field_index(name) == -1:
+                raise RuntimeError("Column not found: " + name)
+        self._user_key_types = [schema.field(n).type for n in self._groupby_cols]
+        dev_types = []
+        for t in self._user_key_types:
+            if self._is_str(t):
+                self._key_kind.append("str")
+                self._dicts.append({})
+                self._dict_values.append([])
+                dev_types.append(pa.int32())
+            elif pa.types.is_boolean(t):
+                self._key_kind.append("bool")
+                self._dicts.append(None)
+                self._dict_values.append(None)
+                dev_types.append(pa.uint8())
+            elif pa.types.is_integer(t) or pa.types.is_floating(t) or pa.types.is_temporal(t):
+                self._key_kind.append("num")
+                self._dicts.append(None)
+                self._dict_values.append(None)
+                dev_types.append(t)
+            else:
+                raise NotImplementedError(f"GenericHashAggregate over key type {t} is not implemented")
+        specs = []
+        for i, f in enumerate(self._funcs):
+            if not f.column_name:
+                specs.append((int(f.func), None))
+                continue
+            if schema.get_field_index(f.column_name) == -1:
+                raise RuntimeError("Column not found: " + f.column_name)
+            t = schema.field(f.column_name).type
+            if self._is_str(t):
+                if int(f.func) == L.AGG_COUNT:
+                    specs.append((L.AGG_COUNT, pa.uint8()))         # validity only
+                elif int(f.func) in (L.AGG_MIN, L.AGG_MAX):
+                    self._str_funcs.append(i)
+                    specs.append((L.AGG_COUNT, pa.uint8()))         # placeholder slot, replaced at result()
+                else:
+                    raise RuntimeError("Column data type is not supported by sum()/avg().")
+            else:
+                specs.append((int(f.func), t))
+        self._key_types = dev_types
+        self._agg = Aggregator(dev_types, specs)
+
+    def _encode_key(self, k: int, arr) -> pa.Array:
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks()
+        kind = self._key_kind[k]
+        if kind == "bool":
+            return arr.cast(pa.uint8())
+        if kind != "str":
+            return arr
+        import numpy as np
+        import pyarrow.compute as pc
+        enc = pc.dictionary_encode(arr)
+        local = enc.dictionary.to_pylist()
+        table, values = self._dicts[k], self._dict_values[k]
+        mapping = np.empty(max(len(local), 1), dtype=np.int32)
+        for j, v in enumerate(local):
+            code = table.get(v)
+            if code is None:
+                code = len(values)
+                table[v] = code
+                values.append(v)
+            mapping[j] = code
+        idx = enc.indices
+        null_mask = idx.is_null().to_numpy(zero_copy_only=False) if idx.null_count else None
+        local_codes = idx.fill_null(0).to_numpy(zero_copy_only=False) if idx.null_count else idx.to_numpy()
+        return pa.array(mapping[local_codes] if len(local) else np.zeros(len(arr), dtype=np.int32), type=pa.int32(),
+                        mask=null_mask)
+
+    @staticmethod
+    def _validity_column(arr) -> pa.Array:
+        import numpy as np
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks()
+        mask = arr.is_null().to_numpy(zero_copy_only=False) if arr.null_count else None
+        return pa.array(np.zeros(len(arr), dtype=np.uint8), mask=mask)
+
+    def next(self, batch) -> None:
+        batch = _as_batch_like(batch)
+        if isinstance(batch, DeviceBatch):
+            raise TypeError("GenericHashAggregate takes host batches (string keys are encoded on the host)")
+        self._ensure_init(batch.schema)
+        st = self._stream
+        schema = batch.schema
+        keep = []
+        keys = []
+        for k, name in enumerate(self._groupby_cols):
+            arr = self._encode_key(k, batch.column(schema.get_field_index(name)))
+            keep.append(arr)
+            keys.append(DeviceColumn.from_arrow(arr, st))
+        values = []
+        for f in self._funcs:
+            if not f.column_name:
+                values.append(None)
+                continue
+            arr = batch.column(schema.get_field_index(f.column_name))
+            if self._is_str(arr.type):
+                arr = self._validity_column(arr)
+            keep.append(arr)
+            values.append(DeviceColumn.from_arrow(arr, st))
+        self._agg.update(keys, values, None, st)
+        if self._str_funcs:
+            # string MIN / MAX: host hash aggregate of this batch, keyed by the same columns
+            cols = {f"k{k}": batch.column(schema.get_field_index(n)) for k, n in enumerate(self._groupby_cols)}
+            aggs = []
+            for i in self._str_funcs:
+                cols[f"v{i}"] = batch.column(schema.get_field_index(self._funcs[i].column_name))
+                aggs.append((f"v{i}", "min" if int(self._funcs[i].func) == L.AGG_MIN else "max"))
+            part = pa.table(cols).group_by([f"k{k}" for k in range(len(self._groupby_cols))], use_threads=False).aggregate(aggs)
+            self._str_partials.append(part)
+        st.sync()
+
+    def result(self) -> pa.RecordBatch:
+        if self._agg is None:
+            return pa.RecordBatch.from_arrays([], names=[])
+        key_arrays, agg_arrays = self._agg.result_arrays(self._stream)
+        user_keys = []
+        for k, arr in enumerate(key_arrays):
+            kind = self._key_kind[k]
+            if kind == "str":
+                values = pa.array(self._dict_values[k], type=self._user_key_types[k])
+                arr = values.take(arr) if len(values) else pa.nulls(len(arr), self._user_key_types[k])
+            elif kind == "bool":
+                arr = arr.cast(pa.bool_())
+            user_keys.append(arr)
+        agg_arrays = list(agg_arrays)
+        if self._str_funcs:
+            nk = len(self._groupby_cols)
+            merged = pa.concat_tables(self._str_partials)
+            names = merged.schema.names
+            val_cols = [n for n in names if not (n.startswith("k") and n[1:].isdigit())]
+            final = merged.group_by([f"k{k}" for k in range(nk)], use_threads=False).aggregate(
+                [(n, "min" if n.endswith("_min") else "max") for n in val_cols])
+            lookup = {}
+            fk = [final.column(f"k{k}").to_pylist() for k in range(nk)]
+            for r in range(final.num_rows):
+                lookup[tuple(col[r] for col in fk)] = r
+            uk = [a.to_pylist() for a in user_keys]
+            order = [lookup[tuple(col[r] for col in uk)] for r in range(len(uk[0]))]
+            take_idx = pa.array(order, type=pa.int64())
+            for i in self._str_funcs:
+                kind = "min" if int(self._funcs[i].func) == L.AGG_MIN else "max"
+                col = final.column(f"v{i}_{kind}_{kind}").combine_chunks()
+                agg_arrays[i] = col.take(take_idx)
+        arrays, names = [], []
+        for name in self._agg_cols:
+            arrays.append(user_keys[self._groupby_cols.index(name)])
+            names.append(name)
+        for f, arr in zip(self._funcs, agg_arrays):
+            arrays.append(arr)
+            names.append(f.out_col_name)
+        return pa.RecordBatch.from_arrays(arrays, names=names)
 
 
 class OneGroupAggregate(_BaseAggregate):
