@@ -11,7 +11,7 @@ from .device import (DeviceBatch, DeviceBuffer, DeviceColumn, PinnedBuffer, Stre
 from . import ops, datagen, vinum_lib  # noqa: F401
 from .aggregate import Aggregator  # noqa: F401
 from .ops import Predicate  # noqa: F401
-from .table import Table, read_csv, read_json, read_parquet  # noqa: F401
+from .table import StreamReader, Table, read_csv, read_json, read_parquet, stream_csv  # noqa: F401
 from .sql.functions import register_numpy, register_python  # noqa: F401
 
 __version__ = "0.1.0"

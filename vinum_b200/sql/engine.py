@@ -148,13 +148,7 @@ class Engine:
     # ============================================================== execution
     def execute(self, q: Query) -> pa.Table:
         q = self._bind(q)
-        used = []
-        for clause in (q.select, (q.where,), q.group_by, (q.having,), q.order_by):
-            for root in clause:
-                if root is not None:
-                    for node in walk(root):
-                        if isinstance(node, Column) and node.name not in used:
-                            used.append(node.name)
+        used = _used_columns(q)
         streamed = self._stream_aggregate(q) if q.is_aggregate else None
         if streamed is not None:
             frame, resolved = streamed
@@ -166,15 +160,7 @@ class Engine:
             resolved = {}
             if q.where is not None:
                 frame = self._filter(frame, self._as_mask(self._eval(q.where, frame, resolved), frame.n))
-        if q.having is not None:
-            frame = self._filter(frame, self._as_mask(self._eval(q.having, frame, resolved), frame.n))
-        if q.order_by:
-            frame = self._sort(frame, [self._eval(o, frame, resolved) for o in q.order_by], q.sort_order)
-        values = [self._eval(e, frame, resolved) for e in q.select]
-        names = output_names(q.select)
-        out = self._materialize(values, names, frame.n, q.limit, q.offset)
-        self.stats["kernels"] = int(L.lib.vk_launch_count()) - self.stats["kernels_before"]
-        return out
+        return self._tail(q, frame, resolved)
 
     # -------------------------------------------------------------------- scan
     def _scan(self, used: Sequence[str]) -> Frame:
@@ -402,7 +388,11 @@ class Engine:
         return DeviceColumn.from_arrow(codes, self.st)
 
     # ------------------------------------------------------------- aggregate
-    def _stream_aggregate(self, q: Query) -> Optional[Tuple[Frame, Dict]]:
+    def _streamable(self, q: Query) -> bool:
+        """Eligibility test of the streaming fast path without running it."""
+        return self._stream_aggregate(q, dry_run=True) is not None
+
+    def _stream_aggregate(self, q: Query, dry_run: bool = False) -> Optional[Tuple[Frame, Dict]]:
         """The streaming fast path (vinum_b200.executor.filter_aggregate): when every group key and
         aggregate argument is a plain null-free numeric column and the WHERE is `column <op>
         literal`, the table is never resident as a whole -- 2^24-row chunks of just the
@@ -457,6 +447,8 @@ class Engine:
             if not (isinstance(b, Literal) and _is_num(b.value) and not isinstance(b.value, bool)) or plain(a) is None:
                 return None
             where = (a.name, sym, b.value)
+        if dry_run:
+            return Frame(0), {}
         stats: dict = {}
         rb = filter_aggregate(self.table, keys, funcs, where, stats=stats)
         self.stats.update({"agg_path": stats.get("agg_path"), "streamed": True, "h2d_bytes": stats.get("h2d_bytes"),
@@ -475,7 +467,18 @@ class Engine:
 
     def _aggregate(self, q: Query, frame: Frame) -> Tuple[Frame, Dict]:
         """WHERE + pre-aggregate projection + AggregateOperator (planner.py:383-470,
-        core/aggregate.py:32-124) on the fused / masked device aggregate."""
+        core/aggregate.py:32-124) on the fused / masked device aggregate, one batch."""
+        state = _AggState(q)
+        try:
+            self._agg_update(q, frame, state)
+            return self._agg_finish(state)
+        finally:
+            state.close()
+
+    def _agg_update(self, q: Query, frame: Frame, state: "_AggState") -> None:
+        """One batch of the stream into the aggregate state (AggregateOperator.next,
+        aggregate.py:114-121): predicate, key and argument expressions are evaluated on this
+        batch's columns, then ONE update of the device aggregate."""
         st = self.st
         # ---- predicate: fused `column <op> literal` or a byte mask; never a compaction ----
         pred = None
@@ -493,48 +496,34 @@ class Engine:
                         fused = ops.Predicate.compare(col, sym, b.value)
             pred = fused or ops.Predicate.from_mask(self._as_mask(self._eval(w, frame, {}), frame.n))
 
-        # ---- group keys ----
-        group_exprs: List[Node] = []
-        seen = set()
-        for g in list(q.group_by) + (list(q.select) if q.distinct else []):
-            if isinstance(g, Literal):
-                continue
-            if g.key() not in seen:
-                seen.add(g.key())
-                group_exprs.append(g)
-        # ---- aggregate calls anywhere in SELECT / HAVING / ORDER BY ----
-        agg_calls: List[Expression] = []
-        seen_a = set()
-        for root in list(q.select) + [q.having] + list(q.order_by):
-            if root is None:
-                continue
-            for node in walk(root):
-                if is_aggregate_call(node) and node.key() not in seen_a:
-                    seen_a.add(node.key())
-                    agg_calls.append(node)
-
+        first = state.agg is None
         key_vals: List[DeviceColumn] = []
-        key_post = []   # how to turn each key's result array back into the user's type
-        for g in group_exprs:
+        keep = []
+        for k, g in enumerate(state.group_exprs):
             v = self._eval(g, frame, {})
             if not _is_col(v):
                 v = self._from_host(np.full(frame.n, v))
             if isinstance(v, HostColumn):
-                enc = pc.dictionary_encode(v.arr)
-                if isinstance(enc, pa.ChunkedArray):
-                    enc = enc.combine_chunks()
-                key_vals.append(DeviceColumn.from_arrow(enc.indices, st))
-                key_post.append(("dict", enc.dictionary))
+                if first:
+                    state.key_kind.append("dict")
+                    state.dicts.append(({}, [], v.arr.type))
+                codes = _encode_with_dictionary(v.arr, state.dicts[k][0], state.dicts[k][1])
+                keep.append(codes)
+                key_vals.append(DeviceColumn.from_arrow(codes, st))
             elif v.dtype == L.BOOL8:
-                as_u8 = DeviceColumn(v.data, v.validity, v.offset, v.length, L.U8, pa.uint8(), v.null_count, v.data_ptr)
-                key_vals.append(as_u8)
-                key_post.append(("bool", None))
+                if first:
+                    state.key_kind.append("bool")
+                    state.dicts.append(None)
+                key_vals.append(DeviceColumn(v.data, v.validity, v.offset, v.length, L.U8, pa.uint8(), v.null_count,
+                                             v.data_ptr))
             else:
+                if first:
+                    state.key_kind.append(None)
+                    state.dicts.append(None)
                 key_vals.append(v)
-                key_post.append((None, None))
 
         specs, agg_vals = [], []
-        for call in agg_calls:
+        for call in state.agg_calls:
             fname = NUMPY_AGG_MAPPING.get(call.function_name.lower(), call.function_name.lower())
             code = _AGG_CODES[fname]
             if code == L.AGG_COUNT_STAR:
@@ -552,26 +541,35 @@ class Engine:
                 # COUNT(str): only the validity matters
                 valid = pc.is_valid(v.arr)
                 dummy = pa.array(np.zeros(v.length, dtype=np.uint8), mask=~valid.to_numpy(zero_copy_only=False))
+                keep.append(dummy)
                 v = DeviceColumn.from_arrow(dummy, st)
             specs.append((code, v.arrow_type))
             agg_vals.append(v)
 
-        agg = Aggregator([k.arrow_type for k in key_vals], specs)
-        try:
-            if key_vals or any(v is not None for v in agg_vals):
-                agg.update(key_vals, agg_vals, pred, st)
-            else:
-                agg.update_count_rows(frame.n, pred, st)
-            keys_out, aggs_out = agg.result_arrays(st)
-            self.stats["agg_path"] = agg.last_path
-        finally:
-            agg.close()
+        if first:
+            state.agg = Aggregator([k.arrow_type for k in key_vals], specs)
+        if key_vals or any(v is not None for v in agg_vals):
+            state.agg.update(key_vals, agg_vals, pred, st)
+        else:
+            state.agg.update_count_rows(frame.n, pred, st)
+        state.batches += 1
+        if keep:
+            st.sync()   # the async copies read host arrays that die with this batch
 
+    def _agg_finish(self, state: "_AggState") -> Tuple[Frame, Dict]:
+        """AggregateOperator result (aggregate.py:122): finalise, read the groups back, give
+        dictionary-coded / boolean keys their user types again."""
+        keys_out, aggs_out = state.agg.result_arrays(self.st)
+        self.stats["agg_path"] = state.agg.last_path
+        self.stats["agg_batches"] = state.batches
         out = Frame(len(aggs_out[0]) if aggs_out else (len(keys_out[0]) if keys_out else 1))
         resolved: Dict = {}
-        for i, (g, arr, (kind, aux)) in enumerate(zip(group_exprs, keys_out, key_post)):
+        for i, (g, arr) in enumerate(zip(state.group_exprs, keys_out)):
+            kind = state.key_kind[i]
             if kind == "dict":
-                arr = aux.take(arr) if len(aux) else pa.array([None] * len(arr), type=aux.type)
+                _table, values, t = state.dicts[i]
+                dictionary = pa.array(values, type=t)
+                arr = dictionary.take(arr) if len(dictionary) else pa.nulls(len(arr), t)
             elif kind == "bool":
                 arr = arr.cast(pa.bool_())
             name = f"__key{i}"
@@ -579,11 +577,64 @@ class Engine:
             resolved[g.key()] = name
             if isinstance(g, Column):
                 out.cols.setdefault(g.name, out.cols[name])
-        for i, (call, arr) in enumerate(zip(agg_calls, aggs_out)):
+        for i, (call, arr) in enumerate(zip(state.agg_calls, aggs_out)):
             name = f"__agg{i}"
             out.cols[name] = self._from_host(arr)
             resolved[call.key()] = name
         return out, resolved
+
+    # --------------------------------------------------------------- streams
+    def execute_stream(self, q: Query, batches, schema: pa.Schema) -> pa.Table:
+        """The query over a STREAM of record batches that need not fit in memory together
+        (StreamReader.sql, vinum/api/stream_reader.py:25-94; FileReaderOperator,
+        algebra.py:268-279).  An aggregate query folds every batch into the device aggregate
+        and only the groups survive; any other query keeps just the rows that pass its WHERE
+        (compacted on the device, batch by batch) and finishes on those."""
+        self.table = schema.empty_table()
+        q = self._bind(q)
+        used = _used_columns(q)
+        if q.is_aggregate:
+            state = _AggState(q)
+            try:
+                for tbl in batches:
+                    self.table = tbl
+                    self._agg_update(q, self._scan(used), state)
+                if state.agg is None:
+                    self.table = schema.empty_table()
+                    self._agg_update(q, self._scan(used), state)
+                frame, resolved = self._agg_finish(state)
+            finally:
+                state.close()
+            return self._tail(q, frame, resolved)
+        # non-aggregate: WHERE per batch, the survivors are concatenated on the host
+        kept = []
+        rows = 0
+        need = None if (q.order_by or q.limit is None) else q.offset + q.limit
+        for tbl in batches:
+            self.table = tbl
+            frame = self._scan(used)
+            if q.where is not None:
+                frame = self._filter(frame, self._as_mask(self._eval(q.where, frame, {}), frame.n))
+            kept.append(pa.table({name: (v.to_arrow(self.st) if isinstance(v, DeviceColumn) else v.arr)
+                                  for name, v in frame.cols.items()}) if frame.cols else pa.table({"__n": pa.nulls(frame.n)}))
+            rows += frame.n
+            if need is not None and rows >= need:
+                break
+        self.table = pa.concat_tables(kept) if kept else pa.table({n: pa.array([], type=schema.field(n).type) for n in used})
+        frame = self._scan(used)
+        if not used:
+            frame.n = rows
+        return self._tail(q, frame, {})
+
+    def _tail(self, q: Query, frame: Frame, resolved: Dict) -> pa.Table:
+        if q.having is not None:
+            frame = self._filter(frame, self._as_mask(self._eval(q.having, frame, resolved), frame.n))
+        if q.order_by:
+            frame = self._sort(frame, [self._eval(o, frame, resolved) for o in q.order_by], q.sort_order)
+        values = [self._eval(e, frame, resolved) for e in q.select]
+        out = self._materialize(values, output_names(q.select), frame.n, q.limit, q.offset)
+        self.stats["kernels"] = int(L.lib.vk_launch_count()) - self.stats["kernels_before"]
+        return out
 
     # ------------------------------------------------------------ materialise
     def _materialize(self, values: List[Value], names: List[str], n: int, limit: Optional[int], offset: int) -> pa.Table:
@@ -603,6 +654,76 @@ class Engine:
                 arrays.append(pa.array(np.repeat(np.array([v]), hi - lo)) if v is not None
                               else pa.nulls(hi - lo))   # algebra.py:76-87
         return pa.Table.from_arrays(arrays, names=names)
+
+
+class _AggState:
+    """Streaming state of one aggregate operator: the device aggregate, the aggregate calls
+    and group expressions of the query, and one host dictionary per string key that lives as
+    long as the stream (so codes mean the same thing in every batch)."""
+
+    def __init__(self, q: Query):
+        self.agg: Optional[Aggregator] = None
+        self.batches = 0
+        self.key_kind: List[Optional[str]] = []
+        self.dicts: List = []
+        self.group_exprs: List[Node] = []
+        seen = set()
+        for g in list(q.group_by) + (list(q.select) if q.distinct else []):
+            if isinstance(g, Literal):
+                continue
+            if g.key() not in seen:
+                seen.add(g.key())
+                self.group_exprs.append(g)
+        self.agg_calls: List[Expression] = []
+        seen_a = set()
+        for root in list(q.select) + [q.having] + list(q.order_by):
+            if root is None:
+                continue
+            for node in walk(root):
+                if is_aggregate_call(node) and node.key() not in seen_a:
+                    seen_a.add(node.key())
+                    self.agg_calls.append(node)
+
+    def close(self):
+        if self.agg is not None:
+            self.agg.close()
+            self.agg = None
+
+
+def _encode_with_dictionary(arr, table: dict, values: list) -> pa.Array:
+    """String array -> int32 codes against a dictionary that persists across batches."""
+    if isinstance(arr, pa.ChunkedArray):
+        arr = arr.combine_chunks()
+    enc = pc.dictionary_encode(arr)
+    local = enc.dictionary.to_pylist()
+    mapping = np.empty(max(len(local), 1), dtype=np.int32)
+    for j, v in enumerate(local):
+        code = table.get(v)
+        if code is None:
+            code = len(values)
+            table[v] = code
+            values.append(v)
+        mapping[j] = code
+    idx = enc.indices
+    if idx.null_count:
+        null_mask = idx.is_null().to_numpy(zero_copy_only=False)
+        local_codes = idx.fill_null(0).to_numpy(zero_copy_only=False)
+    else:
+        null_mask = None
+        local_codes = idx.to_numpy()
+    codes = mapping[local_codes] if len(local) else np.zeros(len(arr), dtype=np.int32)
+    return pa.array(codes, type=pa.int32(), mask=null_mask)
+
+
+def _used_columns(q: Query) -> List[str]:
+    used: List[str] = []
+    for clause in (q.select, (q.where,), q.group_by, (q.having,), q.order_by):
+        for root in clause:
+            if root is not None:
+                for node in walk(root):
+                    if isinstance(node, Column) and node.name not in used:
+                        used.append(node.name)
+    return used
 
 
 def _copy(node):
@@ -631,11 +752,51 @@ def output_names(select: Sequence[Node]) -> List[str]:
     return out
 
 
-def execute_sql(sql: str, table: pa.Table, stream: Optional[Stream] = None, stats: Optional[dict] = None) -> pa.Table:
+CHUNK_ROWS = 1 << 26   # tables above this are executed as a stream of zero-copy slices
+
+
+def execute_sql(sql: str, table: pa.Table, stream: Optional[Stream] = None, stats: Optional[dict] = None,
+                chunk_rows: int = CHUNK_ROWS) -> pa.Table:
     """Parse + plan + run one SELECT over a host pyarrow.Table; the result is a host table."""
     q = parse_sql(sql, table.schema.names)
     eng = Engine(table, stream)
+    if table.num_rows > chunk_rows:
+        bound = eng._bind(q)
+        if not (bound.is_aggregate and eng._streamable(bound)):
+            # bound the device footprint: the table goes through in row slices
+            slices = (table.slice(o, chunk_rows) for o in range(0, table.num_rows, chunk_rows))
+            out = eng.execute_stream(q, slices, table.schema)
+            if stats is not None:
+                stats.update(eng.stats)
+            return out
     out = eng.execute(q)
+    if stats is not None:
+        stats.update(eng.stats)
+    return out
+
+
+def execute_sql_stream(sql: str, reader, stream: Optional[Stream] = None, stats: Optional[dict] = None,
+                       batch_rows: int = 1 << 22) -> pa.Table:
+    """One SELECT over a `pyarrow.RecordBatchReader`-like stream (`.schema`, iteration yields
+    RecordBatches): small reader batches are coalesced into device-sized ones."""
+    schema = reader.schema
+    q = parse_sql(sql, schema.names)
+    eng = Engine(schema.empty_table(), stream)
+
+    def coalesced():
+        pending, rows = [], 0
+        for b in reader:
+            if b.num_rows == 0:
+                continue
+            pending.append(b)
+            rows += b.num_rows
+            if rows >= batch_rows:
+                yield pa.Table.from_batches(pending, schema=schema).combine_chunks()
+                pending, rows = [], 0
+        if pending:
+            yield pa.Table.from_batches(pending, schema=schema).combine_chunks()
+
+    out = eng.execute_stream(q, coalesced(), schema)
     if stats is not None:
         stats.update(eng.stats)
     return out

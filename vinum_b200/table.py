@@ -13,7 +13,7 @@ from typing import Dict, Optional
 
 import pyarrow as pa
 
-from .sql.engine import execute_sql
+from .sql.engine import execute_sql, execute_sql_stream
 from .sql.parser import parse_sql
 
 
@@ -102,7 +102,38 @@ def _has_agg(e) -> bool:
     return contains_aggregate(e)
 
 
+class StreamReader:
+    """A stream of record batches as query input (vinum/api/stream_reader.py:12-94): the file
+    need not fit in memory.  Batches are coalesced to device-sized chunks; an aggregate query
+    folds each chunk into the device aggregate, any other query keeps only the rows that pass
+    its WHERE."""
+
+    def __init__(self, reader):
+        self._reader = reader
+        self.last_stats: dict = {}
+
+    @property
+    def schema(self) -> pa.Schema:
+        return self._reader.schema
+
+    def sql(self, query: str) -> Table:
+        stats: dict = {}
+        out = Table(execute_sql_stream(query, self._reader, stats=stats))
+        self.last_stats = stats
+        return out
+
+    def sql_pd(self, query: str):
+        return self.sql(query).to_pandas()
+
+
 # ------------------------------------------------------------------------- IO
+def stream_csv(input_file, read_options=None, parse_options=None, convert_options=None) -> StreamReader:
+    """vn.stream_csv (vinum/io/arrow.py:9-61): pyarrow's streaming CSV reader as a query source."""
+    import pyarrow.csv
+    return StreamReader(pyarrow.csv.open_csv(input_file, read_options=read_options, parse_options=parse_options,
+                                             convert_options=convert_options))
+
+
 def read_csv(input_file, read_options=None, parse_options=None, convert_options=None) -> Table:
     import pyarrow.csv
     return Table(pyarrow.csv.read_csv(input_file, read_options=read_options, parse_options=parse_options,
