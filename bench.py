@@ -65,7 +65,7 @@ def _peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons during the timed region.  NVML is read in-process
-    (nvidia_ml_py) every 10 ms -- polling the nvidia-smi binary instead takes the driver lock for
+    (nvidia_ml_py) every 25 ms -- polling the nvidia-smi binary instead takes the driver lock for
     milliseconds at a time and shows up as step-time jitter; nvidia-smi is the fallback."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
@@ -87,7 +87,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self.stop_flag.wait(0.01)
+            self.stop_flag.wait(0.025)
 
     def _smi_loop(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -250,8 +250,7 @@ def run_ours(args) -> dict:
         if distributed:
             d = DistributedAggregator(agg, st)
             d.update([key], [None, val], pred)
-            d.repartition()
-            raw = d.gather_raw()
+            raw = d.finish()
             inner = d.agg
         else:
             agg.update([key], [None, val], pred, st)

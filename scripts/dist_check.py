@@ -16,13 +16,17 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 st = vb.default_stream()
 ok = True
-for keyname, keyt, card in (("i0", pa.int64(), 1000), ("i3", pa.int64(), 1_000_000)):
+for keyname, keyt, card, mode in (("i0", pa.int64(), 1000, "finish"), ("i0", pa.int64(), 1000, "repartition"),
+                                  ("i3", pa.int64(), 1_000_000, "finish")):
     t = datagen.device_table([keyname, "f0", "f1", "i1"], rank * n, n, stream=st)
     spec = [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64()), (L.AGG_MIN, pa.int64()), (L.AGG_AVG, pa.int64())]
     d = DistributedAggregator(Aggregator([keyt], spec), st)
     d.update([t.column(keyname)], [None, t.column("f1"), t.column("i1"), t.column("i1")], ops.Predicate.compare(t.column("f0"), ">", 0.5))
-    d.repartition()
-    raw = d.gather_raw()
+    if mode == "finish":
+        raw = d.finish()          # low cardinality: one all-gather; high: all-to-all repartition
+    else:
+        d.repartition()
+        raw = d.gather_raw()
     if rank == 0:
         keys, kv, cnt, lo, hi, valid = raw
         host = {c: datagen.host_column(c, 0, n * world) for c in (keyname, "f0", "f1", "i1")}
@@ -37,7 +41,7 @@ for keyname, keyt, card in (("i0", pa.int64(), 1000), ("i3", pa.int64(), 1_000_0
         good = (np.array_equal(got_k, uk) and np.array_equal(cnt[order].astype(np.int64), want_cnt)
                 and np.allclose(lo[1].view(np.float64)[order], want_sum, rtol=1e-6, atol=1e-6))
         # MIN comes back as an order-preserving code only after finalize: check through result arrays on world==1 only
-        print(f"dist_check key={keyname} world={world} rows={n * world} groups={len(uk)} exchange_bytes={d.exchange_bytes} ok={good}", flush=True)
+        print(f"dist_check key={keyname} mode={mode} world={world} rows={n * world} groups={len(uk)} exchange_bytes={d.exchange_bytes} ok={good}", flush=True)
         ok = ok and good
     d.agg.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")

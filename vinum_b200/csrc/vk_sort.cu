@@ -12,12 +12,13 @@
 // pass reads and writes each (key, row-id) pair exactly once).  Multi-key sorts run
 // the keys from last to first on the running permutation.
 #include "vk_common.cuh"
+#include <cstdlib>
 
 namespace vk {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys
+constexpr int RS_MAX_ITEMS = 16;                // keys per thread of the largest tile geometry
+constexpr int RS_MIN_TILE = RS_THREADS * 8;     // smallest tile any geometry uses (sizes the status array)
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr uint32_t RS_NULLBIT = 0x80000000u;
 
@@ -132,7 +133,9 @@ __device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int s
     return shift == 64 ? (idx >> 31) : (uint32_t) (key >> shift) & 0xffu;
 }
 
-__global__ void __launch_bounds__(RS_THREADS) sort_pass_kernel(const __grid_constant__ PassParams p) {
+template <int RS_ITEMS, int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __grid_constant__ PassParams p) {
+    constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     extern __shared__ __align__(16) uint8_t rs_smem[];
     uint64_t* s_key = reinterpret_cast<uint64_t*>(rs_smem);
     uint32_t* s_idx = reinterpret_cast<uint32_t*>(rs_smem + (size_t) RS_TILE * 8);
@@ -307,7 +310,7 @@ struct SortScratch {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static size_t carve(int64_t n, void* base, SortScratch* s) {
-    const int64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    const int64_t tiles = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;  // enough status rows for any tile geometry
     size_t off = 0;
     auto take = [&](size_t bytes) {
         void* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
@@ -356,8 +359,23 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
     cudaStream_t s = (cudaStream_t) stream;
     SortScratch sc;
     carve(n_rows, scratch, &sc);
-    const int64_t tiles = (n_rows + RS_TILE - 1) / RS_TILE;
-    VK_CUDA(cudaFuncSetAttribute(sort_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 12));
+    // tile geometry: keys per thread x resident CTAs per SM the kernel is compiled for (measured, profiles/)
+    static int cfg = -1;
+    if (cfg < 0) { const char* v = getenv("VINUM_B200_SORT_CFG"); cfg = v ? atoi(v) : 1; }
+    int items;
+    void (*pass_kernel)(PassParams);
+    switch (cfg) {
+        case 0: items = 16; pass_kernel = sort_pass_kernel<16, 2>; break;
+        case 2: items = 12; pass_kernel = sort_pass_kernel<12, 3>; break;
+        case 3: items = 12; pass_kernel = sort_pass_kernel<12, 4>; break;
+        case 4: items = 8; pass_kernel = sort_pass_kernel<8, 4>; break;
+        case 5: items = 8; pass_kernel = sort_pass_kernel<8, 5>; break;
+        case 6: items = 8; pass_kernel = sort_pass_kernel<8, 6>; break;
+        default: items = 16; pass_kernel = sort_pass_kernel<16, 3>; break;  // 8.9 ms vs 10.1 ms (C4)
+    }
+    const int tile_keys = RS_THREADS * items;
+    const int64_t tiles = (n_rows + tile_keys - 1) / tile_keys;
+    VK_CUDA(cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
     int cur = 0;            // buffers holding the running (key', idx)
     bool have_perm = false;
     unsigned long long h_hist[9 * 256];
@@ -401,7 +419,7 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
             ps.status = sc.status;
             VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
             VK_CUDA(cudaMemsetAsync(sc.status, 0, sc.status_bytes, s));
-            sort_pass_kernel<<<(unsigned) tiles, RS_THREADS, RS_TILE * 12, s>>>(ps);
+            pass_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
             VK_CHECK_LAUNCH("sort_pass_kernel");
             cur ^= 1;
         }

@@ -82,6 +82,18 @@ class DistributedAggregator:
     def update(self, keys, values, pred=None) -> None:
         self.agg.update(keys, values, pred, self.stream)
 
+    def _mark(self, label: str) -> None:
+        """Phase trace (VINUM_B200_DIST_TRACE=1): host wall clock between marks, stream drained."""
+        import os
+        import time
+        if not os.environ.get("VINUM_B200_DIST_TRACE"):
+            return
+        self.stream.sync()
+        now = time.perf_counter()
+        if getattr(self, "_t_last", None) is not None and self.rank == 0:
+            print(f"[dist] {label}: {(now - self._t_last) * 1e3:.3f} ms", flush=True)
+        self._t_last = now
+
     def repartition(self) -> None:
         """hash(key) mod world all-to-all of the partial groups, merged into the owner."""
         import torch
@@ -89,6 +101,7 @@ class DistributedAggregator:
         from .aggregate import Aggregator
         if self.world == 1:
             return
+        self._mark("local aggregate")
         dev = torch.device("cuda", torch.cuda.current_device())
         words = C.c_int()
         lib.vk_agg_record_words(self.agg._h, C.byref(words))
@@ -100,6 +113,7 @@ class DistributedAggregator:
             all_counts = torch.empty(self.world * self.world, dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(all_counts, counts_dev, group=self.group)
             counts = all_counts.view(self.world, self.world).cpu().numpy()   # host sync 1: split sizes
+            self._mark("partition counts + all_gather + D2H")
             send_off, send_sz, _recv_off, recv_sz = exchange_plan(counts)
             self._recv_max = int(recv_sz.sum(axis=1).max())
             my_total = int(send_sz[self.rank].sum())
@@ -107,7 +121,9 @@ class DistributedAggregator:
             offs = torch.from_numpy(np.ascontiguousarray(send_off[self.rank])).to(dev, non_blocking=True)
             lib.vk_agg_export_partials(self.agg._h, self.world, C.c_void_p(offs.data_ptr()),
                                        C.c_void_p(send.data_ptr()), st.ptr)
+            self._mark("export partials")
             recv = all_to_all_records(send, send_sz[self.rank], recv_sz[self.rank], w, self.group)
+            self._mark("all_to_all")
             self.exchange_bytes = int(send_sz[self.rank].sum() - send_sz[self.rank][self.rank]) * w * 8
             # the owner's table = merge of everything it received (its own share included)
             n_recv = int(recv_sz[self.rank].sum())
@@ -115,8 +131,74 @@ class DistributedAggregator:
             lib.vk_agg_merge_partials(fresh._h, C.c_void_p(recv.data_ptr()), n_recv, st.ptr)
             # `send` / `recv` / `offs` are torch allocations used by kernels on this same stream
             recv.record_stream(self._tstream)
+        self._mark("merge partials")
         self.agg.close()   # drains the stream: the exchange buffers may be released after this
         self.agg = fresh
+        self._mark("close old aggregate")
+
+    # Partial groups per rank up to which the exchange is ONE all-gather: at low cardinality the
+    # all-to-all's messages are a few KB and the cost is pure collective latency (measured:
+    # ~0.1 ms per collective + host round trip, 4 of them per query), so every rank publishes
+    # its whole partial table in one fixed-size block and rank 0 merges.
+    SMALL_GROUPS = 4096
+
+    def finish(self):
+        """Whole-job result on rank 0 (None elsewhere).  Low cardinality: one all-gather of
+        fixed-size blocks `[n_groups | records...]`, merged on rank 0.  Otherwise (any rank
+        holds more than SMALL_GROUPS partial groups -- every rank sees every header, so the
+        decision is unanimous): hash(key) mod world all-to-all repartition + gather."""
+        import torch
+        import torch.distributed as dist
+        from .aggregate import Aggregator
+        import os
+        if self.world == 1:
+            return self.agg.result_raw(self.stream)
+        if os.environ.get("VINUM_B200_DIST_MODE") == "repartition":   # A/B switch for tuning runs
+            self.repartition()
+            return self.gather_raw()
+        self._mark("local aggregate")
+        st = self.stream
+        dev = torch.device("cuda", torch.cuda.current_device())
+        words = C.c_int()
+        lib.vk_agg_record_words(self.agg._h, C.byref(words))
+        w = words.value
+        cap = self.SMALL_GROUPS
+        g = self.agg.num_groups(st)                                   # host sync 1
+        blk_words = 1 + cap * w
+        with torch.cuda.stream(self._tstream):
+            blk = torch.empty(blk_words, dtype=torch.int64, device=dev)
+            blk[0] = g
+            if 0 < g <= cap:
+                if getattr(self, "_zero_off", None) is None:
+                    self._zero_off = torch.zeros(1, dtype=torch.int64, device=dev)
+                lib.vk_agg_export_partials(self.agg._h, 1, C.c_void_p(self._zero_off.data_ptr()),
+                                           C.c_void_p(blk.data_ptr() + 8), st.ptr)
+            allb = torch.empty(self.world * blk_words, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allb, blk, group=self.group)
+            allb = allb.view(self.world, blk_words)
+            heads = [int(x) for x in allb[:, 0].cpu().tolist()]      # host sync 2
+            self._mark("export + all_gather of partial blocks")
+            if max(heads) > cap:
+                small = False
+            else:
+                small = True
+                if self.rank == 0:
+                    parts = [allb[r, 1:1 + heads[r] * w] for r in range(self.world) if heads[r]]
+                    total = sum(heads)
+                    fresh = Aggregator(self.agg.key_types, self.agg.funcs, expected_groups=max(total, 1))
+                    if parts:
+                        recs = torch.cat(parts)
+                        lib.vk_agg_merge_partials(fresh._h, C.c_void_p(recs.data_ptr()), total, st.ptr)
+        if not small:
+            self.repartition()
+            return self.gather_raw()
+        if self.rank != 0:
+            return None
+        raw = fresh.result_raw(st)
+        self._mark("merge + finalize on rank 0")
+        self.agg.close()
+        self.agg = fresh
+        return raw
 
     def gather_raw(self):
         """Concatenate every rank's finalised groups on rank 0 (after repartition each
@@ -130,6 +212,7 @@ class DistributedAggregator:
         dev = torch.device("cuda", torch.cuda.current_device())
         nk, nf = len(self.agg.key_vk), len(self.agg.funcs)
         g = self.agg.num_groups(st)                               # host sync 2
+        self._mark("num_groups")
         if self._recv_max == 0:
             # no repartition happened: agree on the padded width the slow way
             with torch.cuda.stream(self._tstream):
@@ -154,8 +237,10 @@ class DistributedAggregator:
             if n8:
                 blk[n64:, :gmax] = b8[:n8]
             blk[0, gmax] = g
+            self._mark("finalize into padded block")
             gathered = [torch.empty_like(blk) for _ in range(self.world)] if self.rank == 0 else None
             dist.gather(blk, gathered, dst=0, group=self.group)
+            self._mark("gather")
             if self.rank != 0:
                 return None
             allb = torch.stack(gathered).cpu().numpy().view(np.uint64)   # host sync 3 (rank 0)
