@@ -107,7 +107,9 @@ class ClockSampler:
                 pass
             self.stop_flag.wait(0.25)
 
-    def start(self):
+    def prepare(self):
+        """NVML initialisation costs milliseconds: do it BEFORE the barrier that opens the timed
+        region (rank 0 alone samples; a late start of rank 0 would be charged to every other rank)."""
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -121,6 +123,10 @@ class ClockSampler:
         except Exception:
             self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+
+    def start(self):
+        if self.thread is None:
+            self.prepare()
         self.thread.start()
 
     def stop(self):
@@ -272,8 +278,17 @@ def run_ours(args) -> dict:
     lib.vk_event_create(C.byref(e1))
     for _ in range(args.warmup):
         step(False)
-    barrier()
+    # Python's cyclic collector walks every tracked object of the process (hundreds of thousands once
+    # torch is imported: a 50-100 ms pause that lands in a random step).  Nothing in a step creates
+    # cycles; collect now and keep the collector out of the timed regions.
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.prepare()
+    barrier()
     if rank == 0:
         sampler.start()
     launches0 = lib.vk_launch_count()
@@ -321,6 +336,7 @@ def run_ours(args) -> dict:
     e2e_value = e2e_rows * world / e2e_t
     assert out.num_rows == 1000
 
+    gc.enable()
     if rank != 0:
         if distributed:
             dist.destroy_process_group()

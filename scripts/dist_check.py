@@ -44,6 +44,32 @@ for keyname, keyt, card, mode in (("i0", pa.int64(), 1000, "finish"), ("i0", pa.
         print(f"dist_check key={keyname} mode={mode} world={world} rows={n * world} groups={len(uk)} exchange_bytes={d.exchange_bytes} ok={good}", flush=True)
         ok = ok and good
     d.agg.close()
+# ---- C5 tail: ORDER BY over the gathered groups on rank 0 (device radix sort) ----
+t = datagen.device_table(["i0", "f0", "f1"], rank * n, n, stream=st)
+d = DistributedAggregator(Aggregator([pa.int64()], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64())]), st)
+d.update([t.column("i0")], [None, t.column("f1")], ops.Predicate.compare(t.column("f0"), ">", 0.5))
+raw = d.finish()
+if rank == 0:
+    keys = vb.DeviceColumn.from_numpy(np.ascontiguousarray(raw[0][0].view(np.int64)), st)
+    order = ops.sort_indices([keys], [L.ASC], st).to_numpy(st)
+    good = np.array_equal(raw[0][0].view(np.int64)[order], np.arange(1000))
+    print(f"dist_check C5 pipeline (filter->group-by->agg->order-by) world={world} ok={good}", flush=True)
+    ok = ok and good
+d.agg.close()
+
+# ---- sharded ORDER BY: per-GPU radix sort + host k-way merge ----
+from vinum_b200.dist import sort_sharded
+for colname, desc in (("f3", True), ("i3", False)):
+    col = datagen.device_column(colname, rank * n, n, stream=st)
+    res = sort_sharded(col, rank * n, desc, st)
+    if rank == 0:
+        k, ids = res
+        host = datagen.host_column(colname, 0, n * world)
+        want = np.argsort(-host if desc else host, kind="stable")
+        good = np.array_equal(ids, want) and np.array_equal(k, host[want])
+        print(f"dist_check sharded sort {colname} desc={desc} world={world} rows={n * world} ok={good}", flush=True)
+        ok = ok and good
+
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 dist.barrier()

@@ -196,6 +196,39 @@ def test_exchange_plan():
     assert ro.tolist() == [[0, 1, 5], [0, 2, 2], [0, 3, 9]]
 
 
+def test_merge_sorted_runs_is_a_global_stable_sort():
+    """dist.merge_sorted_runs (SURVEY 8e host merge): merging per-shard stable sorts in shard order
+    equals one stable sort of the whole column, ties and NaN placement included."""
+    from vinum_b200.dist import merge_sorted_runs
+    rng = np.random.default_rng(3)
+    for dtype, desc in [(np.float64, False), (np.float64, True), (np.int64, False), (np.int64, True), (np.uint64, True)]:
+        n = 5000
+        if dtype == np.float64:
+            col = np.round(rng.normal(0, 3, n), 1)
+            col[rng.random(n) < 0.02] = np.nan
+        else:
+            col = rng.integers(0, 40, n).astype(dtype)
+        bounds = [0, 1200, 1200, 3100, n]   # one empty shard
+        runs_k, runs_i = [], []
+        for lo, hi in zip(bounds, bounds[1:]):
+            part = col[lo:hi]
+            if dtype == np.float64:
+                key = np.where(np.isnan(part), np.inf, -part if desc else part)
+                order = np.lexsort((key, np.isnan(part)))
+            else:
+                order = np.argsort(part if not desc else (part.max() - part if len(part) else part), kind="stable")
+            runs_k.append(part[order])
+            runs_i.append(order.astype(np.int64) + lo)
+        k, ids = merge_sorted_runs(runs_k, runs_i, desc)
+        if dtype == np.float64:
+            key = np.where(np.isnan(col), np.inf, -col if desc else col)
+            want = np.lexsort((key, np.isnan(col)))
+        else:
+            want = np.argsort(col if not desc else col.max() - col, kind="stable")
+        assert np.array_equal(ids, want), (dtype, desc)
+        assert np.array_equal(k, col[want], equal_nan=True)
+
+
 _GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})

@@ -251,3 +251,68 @@ class DistributedAggregator:
         allp = np.concatenate(parts, axis=1)
         return (allp[:nk], allp[n64:n64 + nk].astype(bool), allp[nk], allp[nk + 1:nk + 1 + nf],
                 allp[nk + 1 + nf:nk + 1 + 2 * nf], allp[n64 + nk:].astype(bool))
+
+
+# ------------------------------------------------------------------------- sort ----
+def merge_sorted_runs(keys: Sequence[np.ndarray], row_ids: Sequence[np.ndarray], descending: bool = False):
+    """Host k-way merge of per-shard sorted runs ("per-GPU radix sort -> D2H of sorted
+    (key, global row id) runs -> host k-way merge").  Run g holds shard g's rows in sorted order;
+    shards are contiguous row ranges in rank order, so breaking ties by (run, position) keeps
+    the GLOBAL sort stable, exactly like a single stable sort of the whole column.  NaN sorts
+    after every number in both directions (Arrow SortIndices semantics, sort.cpp:33).
+
+    NumPy's stable sort is a run-detecting merge sort: on a concatenation of k sorted runs it
+    does the k-way merge in O(n log k)."""
+    if not keys:
+        return np.empty(0), np.empty(0, dtype=np.int64)
+    k = np.concatenate(keys)
+    ids = np.concatenate(row_ids)
+    if k.dtype.kind == "f":
+        nan = np.isnan(k)
+        rank_key = np.where(nan, np.inf, -k if descending else k)
+        # NaN after +inf: order by (is_nan, key); lexsort is stable
+        order = np.lexsort((rank_key, nan))
+    else:
+        if descending:
+            rank_key = ~k if k.dtype.kind == "u" else -1 - k   # order-reversing, overflow-free
+        else:
+            rank_key = k
+        order = np.argsort(rank_key, kind="stable")
+    return k[order], ids[order]
+
+
+def sort_sharded(column, row0: int, descending: bool, stream, group=None):
+    """ORDER BY one numeric column over row-range shards: every rank sorts its shard on the
+    device (stable LSD radix sort), rank 0 gathers the sorted (key, global row id) runs and
+    merges them on the host.  Returns (sorted keys, global row ids) on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from . import ops
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    idx = ops.sort_indices([column], [L.DESC if descending else L.ASC], stream)
+    keys_sorted = ops.take(column, idx, stream).to_numpy(stream)
+    ids = idx.to_numpy(stream) + np.int64(row0)
+    if world == 1:
+        return keys_sorted, ids
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = torch.tensor([len(ids)], dtype=torch.int64, device=dev)
+    sizes = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    nmax = max(max(sizes), 1)
+    pack = np.zeros((2, nmax), dtype=np.int64)
+    pack[0, :len(ids)] = keys_sorted.view(np.int64) if keys_sorted.dtype.itemsize == 8 else keys_sorted.astype(np.int64)
+    pack[1, :len(ids)] = ids
+    t = torch.from_numpy(pack).to(dev)
+    gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    runs_k, runs_i = [], []
+    for g, s in zip(gathered, sizes):
+        a = g.cpu().numpy()
+        kk = a[0, :s].view(keys_sorted.dtype) if keys_sorted.dtype.itemsize == 8 else a[0, :s].astype(keys_sorted.dtype)
+        runs_k.append(kk)
+        runs_i.append(a[1, :s])
+    return merge_sorted_runs(runs_k, runs_i, descending)
