@@ -227,6 +227,12 @@ def run_ours(args) -> dict:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from vinum_b200.dist import DistributedAggregator
+        # NCCL sets its channels up lazily on the first collectives of each kind: part of start-up
+        _w = torch.zeros(world * 1024, dtype=torch.int64, device="cuda")
+        for _ in range(3):
+            dist.all_gather_into_tensor(_w, _w[:1024].clone())
+            dist.all_reduce(_w[:8])
+        torch.cuda.synchronize()
     st = vb.default_stream()
     rows = args.rows
     row0 = rank * rows
