@@ -137,8 +137,7 @@ __global__ void __launch_bounds__(256) bits_to_mask_kernel(const uint8_t* __rest
 // so an 8-byte column is read with one 16-byte load per lane and the rank of a row
 // inside its tile is (rows selected by lower (it, warp)) + (ballot rank).
 constexpr int FT_THREADS = 256;
-constexpr int FT_ITERS = 4;
-constexpr int FT_TILE = FT_THREADS * 2 * FT_ITERS;  // 2048 rows
+constexpr int FT_MIN_TILE = FT_THREADS * 2 * 4;  // smallest tile geometry (2048 rows): sizes the status array
 constexpr int FT_MAX_COLS = 12;
 
 constexpr uint64_t ST_FLAG_SHIFT = 62;
@@ -175,24 +174,29 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <int PK>  // predicate kind specialisation (see vk_pred.cuh)
+// PK: predicate kind (vk_pred.cuh); ITERS: row pairs per thread (tile = 512 * ITERS rows); KEEP: the
+// predicate column's registers are kept from phase 1 and reused when that column is also an output.
+template <int PK, int ITERS, bool KEEP>
 __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constant__ FilterParams p) {
+    constexpr int TILE = FT_THREADS * 2 * ITERS;
+    constexpr int NCNT = ITERS * (FT_THREADS / 32);   // (iter, warp) counts: 32 or 64
+    constexpr int PER_LANE = NCNT / 32;
     __shared__ int64_t s_tile;
-    __shared__ uint32_t s_cnt[FT_ITERS * (FT_THREADS / 32)];
+    __shared__ uint32_t s_cnt[NCNT];
     __shared__ int64_t s_excl;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = (int64_t) atomicAdd(p.ticket, 1ULL);
     __syncthreads();
     const int64_t tile = s_tile;
-    const int64_t base = tile * FT_TILE;
+    const int64_t base = tile * TILE;
 
     // The payload columns are only read after the look-back; start moving this tile's slice of
     // each of them into L2 now (one bulk prefetch per column, no registers, no shared memory).
     if (p.pf && tid < p.n_cols) {
         const Col col = p.cols[tid];
         const int es = dtype_size(col.dtype);
-        const int64_t rows = p.n - base < FT_TILE ? p.n - base : FT_TILE;
+        const int64_t rows = p.n - base < TILE ? p.n - base : TILE;
         // (the predicate's own column is being loaded by phase 1 right now: no second request)
         if (!(p.pred.kind == VK_PRED_CMP && col.data == p.pred.col.data))
             l2_prefetch_span(col.data + base * es, col.data + (base + rows) * es);
@@ -200,13 +204,41 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
 
     // ---- phase 1: evaluate the predicate once, keep the flags in registers ----
     uint32_t flags = 0;
-    uint32_t lane_off[FT_ITERS];
+    uint32_t lane_off[ITERS];
+    uint4 praw[KEEP ? ITERS : 1];
     const unsigned lt = lanemask_lt();
 #pragma unroll
-    for (int it = 0; it < FT_ITERS; ++it) {
+    for (int it = 0; it < ITERS; ++it) {
         int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
         bool f0, f1;
-        pred_pair<PK>(p.pred, r0, p.n, f0, f1);
+        if constexpr (KEEP && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
+            f0 = f1 = false;
+            if (r0 + 1 < p.n) {
+                const uint4 q = ldg_stream16(p.pred.col.data + r0 * 8);
+                praw[it] = q;
+                if constexpr (PK == PK_F64_VEC) {
+                    const double c = __longlong_as_double((long long) p.pred.scalar.bits);
+                    f0 = apply_cmp(p.pred.op, __hiloint2double(q.y, q.x), c);
+                    f1 = apply_cmp(p.pred.op, __hiloint2double(q.w, q.z), c);
+                } else {
+                    f0 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.y << 32) | q.x), (int64_t) p.pred.scalar.bits);
+                    f1 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.w << 32) | q.z), (int64_t) p.pred.scalar.bits);
+                }
+            } else {
+                praw[it] = make_uint4(0, 0, 0, 0);
+                if (r0 < p.n) {  // last, unpaired row of the batch
+                    const uint2 q = *reinterpret_cast<const uint2*>(p.pred.col.data + r0 * 8);
+                    praw[it].x = q.x;
+                    praw[it].y = q.y;
+                    if constexpr (PK == PK_F64_VEC)
+                        f0 = apply_cmp(p.pred.op, __hiloint2double(q.y, q.x), __longlong_as_double((long long) p.pred.scalar.bits));
+                    else
+                        f0 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.y << 32) | q.x), (int64_t) p.pred.scalar.bits);
+                }
+            }
+        } else {
+            pred_pair<PK>(p.pred, r0, p.n, f0, f1);
+        }
         unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
         lane_off[it] = __popc(b0 & lt) + __popc(b1 & lt);
         flags |= ((uint32_t) f0 << (2 * it)) | ((uint32_t) f1 << (2 * it + 1));
@@ -214,16 +246,26 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
     }
     __syncthreads();
 
-    // ---- block scan of the 32 (iter, warp) counts + decoupled look-back (warp 0) ----
+    // ---- block scan of the (iter, warp) counts + decoupled look-back (warp 0) ----
     if (warp == 0) {
-        uint32_t c = s_cnt[lane];
-        uint32_t inc = c;
+        uint32_t c[PER_LANE], mine = 0;
+#pragma unroll
+        for (int e = 0; e < PER_LANE; ++e) {
+            c[e] = s_cnt[lane * PER_LANE + e];
+            mine += c[e];
+        }
+        uint32_t inc = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += t;
         }
-        s_cnt[lane] = inc - c;  // exclusive offset of (iter, warp) inside the tile
+        uint32_t run = inc - mine;  // exclusive offset of this lane's first (iter, warp) entry inside the tile
+#pragma unroll
+        for (int e = 0; e < PER_LANE; ++e) {
+            s_cnt[lane * PER_LANE + e] = run;
+            run += c[e];
+        }
         uint64_t total = __shfl_sync(0xffffffffu, inc, 31);
         uint64_t excl = 0;
         if (tile == 0) {
@@ -263,15 +305,20 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
         const int es = dtype_size(col.dtype);
         uint8_t* outv = p.out_valid[c];
         const bool vec16 = (es == 8) && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0);
+        const bool from_regs = KEEP && (PK == PK_F64_VEC || PK == PK_I64_VEC) && es == 8 && col.data == p.pred.col.data;
 #pragma unroll
-        for (int it = 0; it < FT_ITERS; ++it) {
+        for (int it = 0; it < ITERS; ++it) {
             const uint32_t f = (flags >> (2 * it)) & 3u;
             if (f == 0) continue;
             const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
             int64_t pos = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
             if (es == 8) {
                 uint64_t v0, v1;
-                if (vec16 && r0 + 1 < p.n) {
+                if (from_regs) {
+                    const uint4 q = praw[KEEP ? it : 0];
+                    v0 = ((uint64_t) q.y << 32) | q.x;
+                    v1 = ((uint64_t) q.w << 32) | q.z;
+                } else if (vec16 && r0 + 1 < p.n) {
                     uint4 q = ldg_stream16(col.data + r0 * 8);
                     v0 = ((uint64_t) q.y << 32) | q.x;
                     v1 = ((uint64_t) q.w << 32) | q.z;
@@ -444,7 +491,7 @@ int vk_bits_to_mask(const uint8_t* bits, int64_t bit_offset, int64_t n, uint8_t*
 }
 
 uint64_t vk_filter_scratch_bytes(int64_t n_rows) {
-    int64_t tiles = (n_rows + FT_TILE - 1) / FT_TILE;
+    int64_t tiles = (n_rows + FT_MIN_TILE - 1) / FT_MIN_TILE;
     if (tiles < 1) tiles = 1;
     return (uint64_t) (tiles + 1) * sizeof(unsigned long long);
 }
@@ -472,7 +519,13 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         VK_REQUIRE(cols[c].validity == nullptr || (out_valid_bytes && out_valid_bytes[c]),
                    "vk_filter: column has validity but no out_valid_bytes buffer");
     }
-    const int64_t tiles = (n_rows + FT_TILE - 1) / FT_TILE;
+    // geometry: row pairs per thread / keep the predicate column in registers (measured, profiles/)
+    static int cfg = -1;
+    if (cfg < 0) { const char* v = getenv("VINUM_B200_FILTER_CFG"); cfg = v ? atoi(v) : 0; }
+    const int iters = (cfg & 1) ? 8 : 4;
+    const bool keep = (cfg & 2) != 0;
+    const int tile_rows = FT_THREADS * 2 * iters;
+    const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
     // columns are processed FT_MAX_COLS at a time; each pass re-evaluates the predicate
     int c0 = 0;
     do {
@@ -495,12 +548,23 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
             p.pf = pf;
         }
         VK_CUDA(cudaMemsetAsync(scratch, 0, vk_filter_scratch_bytes(n_rows), s));
+#define VK_FILTER_GO(PK)                                                                              \
+        do {                                                                                              \
+            if (iters == 8) {                                                                             \
+                if (keep) filter_kernel<PK, 8, true><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);          \
+                else filter_kernel<PK, 8, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);              \
+            } else {                                                                                      \
+                if (keep) filter_kernel<PK, 4, true><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);          \
+                else filter_kernel<PK, 4, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);              \
+            }                                                                                             \
+        } while (0)
         switch (pk) {
-            case PK_MASK: filter_kernel<PK_MASK><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); break;
-            case PK_F64_VEC: filter_kernel<PK_F64_VEC><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); break;
-            case PK_I64_VEC: filter_kernel<PK_I64_VEC><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); break;
-            default: filter_kernel<PK_GENERIC><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); break;
+            case PK_MASK: VK_FILTER_GO(PK_MASK); break;
+            case PK_F64_VEC: VK_FILTER_GO(PK_F64_VEC); break;
+            case PK_I64_VEC: VK_FILTER_GO(PK_I64_VEC); break;
+            default: VK_FILTER_GO(PK_GENERIC); break;
         }
+#undef VK_FILTER_GO
         VK_CHECK_LAUNCH("filter_kernel");
         c0 += p.n_cols;
     } while (c0 < n_cols);
