@@ -397,6 +397,7 @@ struct VkAgg {
     int64_t groups_ub = 0;            // upper bound on groups in the table
     unsigned long long* d_ctr = nullptr;  // [0] num_groups [1] list count [2] lost [3] spilled [4] finalize cursor [5..] scratch
     unsigned long long* h_ctr = nullptr;  // pinned mirror
+    int device = 0;                   // device the object (its counter block, list and table) lives on
     bool ctr_ready = false;           // d_ctr zeroed on the first stream this object is used on
     cudaStream_t last_stream = nullptr;   // every call so far ran on this stream ...
     bool stream_seen = false, multi_stream = false;  // ... unless multi_stream
@@ -450,6 +451,7 @@ std::vector<CtrBlock>& g_ctr_free = *new std::vector<CtrBlock>();
 int ctr_acquire(VkAgg* a) {
     int dev = 0;
     cudaGetDevice(&dev);
+    a->device = dev;
     {
         std::lock_guard<std::mutex> lk(g_ctr_mu);
         for (size_t i = 0; i < g_ctr_free.size(); ++i) {
@@ -473,8 +475,7 @@ int ctr_acquire(VkAgg* a) {
 }
 void ctr_release(VkAgg* a) {
     if (!a->d_ctr) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
+    const int dev = a->device;
     std::lock_guard<std::mutex> lk(g_ctr_mu);
     g_ctr_free.push_back(CtrBlock{dev, a->d_ctr, a->h_ctr});
     a->d_ctr = nullptr;
@@ -588,8 +589,7 @@ int ensure_list(VkAgg* a, uint64_t want, cudaStream_t s) {
     if (a->list) VK_CUDA(cudaFreeAsync(a->list, s));
     a->list = nullptr;
     a->list_cap = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
+    const int dev = a->device;
     {
         std::lock_guard<std::mutex> lk(g_ctr_mu);
         for (size_t i = 0; i < g_list_free.size(); ++i) {
@@ -608,8 +608,7 @@ int ensure_list(VkAgg* a, uint64_t want, cudaStream_t s) {
 // Called after the object's stream has been drained.
 void release_list(VkAgg* a, cudaStream_t s) {
     if (!a->list) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
+    const int dev = a->device;
     uint32_t* drop = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_ctr_mu);

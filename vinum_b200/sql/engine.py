@@ -352,8 +352,10 @@ class Engine:
                 out.cols[k] = HostColumn(frame.cols[k].arr.filter(pa.array(hm)))
         return out
 
-    def _sort(self, frame: Frame, keys: List[Value], orders: Sequence[SortOrder]) -> Frame:
-        """SortOperator (algebra.py:126-201) -> device radix sort + gather."""
+    def _sort(self, frame: Frame, keys: List[Value], orders: Sequence[SortOrder], top: Optional[int] = None) -> Frame:
+        """SortOperator (algebra.py:126-201) -> device radix sort + gather.  With a LIMIT only the
+        first `top` = offset + limit rows of the permutation are gathered (SliceOperator,
+        algebra.py:204-247, pulled below the gather)."""
         dev_keys, dev_orders = [], []
         for k, o in zip(keys, orders):
             if not _is_col(k):
@@ -367,7 +369,10 @@ class Engine:
         if not dev_keys or frame.n == 0:
             return frame
         idx = ops.sort_indices(dev_keys, dev_orders, self.st)
-        out = Frame(frame.n)
+        m = frame.n if top is None else min(top, frame.n)
+        if m < frame.n:
+            idx = idx.slice(0, m)
+        out = Frame(m)
         hidx = None
         for name, v in frame.cols.items():
             if isinstance(v, DeviceColumn):
@@ -630,7 +635,8 @@ class Engine:
         if q.having is not None:
             frame = self._filter(frame, self._as_mask(self._eval(q.having, frame, resolved), frame.n))
         if q.order_by:
-            frame = self._sort(frame, [self._eval(o, frame, resolved) for o in q.order_by], q.sort_order)
+            top = None if q.limit is None else q.offset + q.limit
+            frame = self._sort(frame, [self._eval(o, frame, resolved) for o in q.order_by], q.sort_order, top)
         values = [self._eval(e, frame, resolved) for e in q.select]
         out = self._materialize(values, output_names(q.select), frame.n, q.limit, q.offset)
         self.stats["kernels"] = int(L.lib.vk_launch_count()) - self.stats["kernels_before"]
