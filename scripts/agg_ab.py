@@ -36,7 +36,8 @@ def run(setting, query):
             gbs.append(rows * bpr / ms / 1e6); steps.append((t1 - t0) * 1e3)
         assert len(raw[2]) == 1000
     print(f"{query:9s} [{setting:28s}] kernel GB/s med={statistics.median(gbs):7.1f} max={max(gbs):7.1f} min={min(gbs):7.1f} | "
-          f"step ms med={statistics.median(steps):.3f} min={min(steps):.3f} launches/step={ln}", flush=True)
+          f"step ms med={statistics.median(steps):.3f} min={min(steps):.3f} launches/step={ln} "
+          f"steps={[round(x, 2) for x in steps]}", flush=True)
 for s in sys.argv[1:] or [""]:
     for q in ("northstar", "c3"):
         run(s, q)

@@ -1102,17 +1102,25 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
 
     // ---- chunk loop: never more rows in flight than (free slots + replay capacity) ----
     if (a->list_max == 0) {
-        // large enough that a 1e9-row batch is ONE launch (the list is only touched by rows
-        // that could not be inserted; the memory comes from the pool and is never written otherwise)
-        int l2 = 30;
-        if (const char* v = getenv("VINUM_B200_LIST_LOG2")) l2 = atoi(v);
-        if (l2 < 16) l2 = 16;
-        if (l2 > 31) l2 = 31;
-        a->list_max = (uint64_t) 1 << l2;
-        size_t fr = 0, tot = 0;
-        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
-            while (a->list_max * sizeof(uint32_t) > fr / 16 && a->list_max > (1u << 16)) a->list_max >>= 1;
+        // once per device, not per query: cudaMemGetInfo walks the driver's allocation state and
+        // has been seen to take milliseconds with tens of GB resident
+        static uint64_t g_list_max[64] = {0};
+        const int dev = a->device >= 0 && a->device < 64 ? a->device : 0;
+        if (g_list_max[dev] == 0) {
+            // large enough that a 1e9-row batch is ONE launch (the list is only touched by rows
+            // that could not be inserted; the memory is kept per device and never written otherwise)
+            int l2 = 30;
+            if (const char* v = getenv("VINUM_B200_LIST_LOG2")) l2 = atoi(v);
+            if (l2 < 16) l2 = 16;
+            if (l2 > 31) l2 = 31;
+            uint64_t lm = (uint64_t) 1 << l2;
+            size_t fr = 0, tot = 0;
+            if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+                while (lm * sizeof(uint32_t) > fr / 16 && lm > (1u << 16)) lm >>= 1;
+            }
+            g_list_max[dev] = lm;
         }
+        a->list_max = g_list_max[dev];
     }
     const uint64_t list_max = a->list_max;
     int64_t pos = 0;
