@@ -133,7 +133,23 @@ __device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int s
     return shift == 64 ? (idx >> 31) : (uint32_t) (key >> shift) & 0xffu;
 }
 
-template <int RS_ITEMS, int MINB>
+// Lanes of the warp whose 8-bit digit equals this lane's.  MATCH.ANY runs on the ADU pipe at
+// ~64 issue cycles per warp and was the pass kernel's binding pipe (72 % busy, profiles/); eight
+// ballots (one per digit bit) and eight LOP3 do the same on the ALU / vote path.
+__device__ __forceinline__ unsigned digit_peers_ballot(uint32_t d, bool in, int nbits) {
+    unsigned peers = __ballot_sync(0xffffffffu, in);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (b < nbits) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned vote = __ballot_sync(0xffffffffu, in && bit);
+            peers &= bit ? vote : ~vote;
+        }
+    }
+    return peers;
+}
+
+template <int RS_ITEMS, int MINB, bool BALLOT>
 __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __grid_constant__ PassParams p) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -174,7 +190,13 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
         const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
         const bool in = li < tile_n;
         const uint32_t d = pass_digit(key[k], idx[k], p.shift);
-        const unsigned peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
+        unsigned peers;
+        if constexpr (BALLOT) {
+            peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
+            if (!in) peers = 1u << lane;
+        } else {
+            peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
+        }
         const int leader = __ffs(peers) - 1;
         uint32_t c = 0;
         if (in && lane == leader) {
@@ -361,17 +383,19 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
     carve(n_rows, scratch, &sc);
     // tile geometry: keys per thread x resident CTAs per SM the kernel is compiled for (measured, profiles/)
     static int cfg = -1;
-    if (cfg < 0) { const char* v = getenv("VINUM_B200_SORT_CFG"); cfg = v ? atoi(v) : 1; }
+    if (cfg < 0) { const char* v = getenv("VINUM_B200_SORT_CFG"); cfg = v ? atoi(v) : 9; }
     int items;
     void (*pass_kernel)(PassParams);
     switch (cfg) {
-        case 0: items = 16; pass_kernel = sort_pass_kernel<16, 2>; break;
-        case 2: items = 12; pass_kernel = sort_pass_kernel<12, 3>; break;
-        case 3: items = 12; pass_kernel = sort_pass_kernel<12, 4>; break;
-        case 4: items = 8; pass_kernel = sort_pass_kernel<8, 4>; break;
-        case 5: items = 8; pass_kernel = sort_pass_kernel<8, 5>; break;
-        case 6: items = 8; pass_kernel = sort_pass_kernel<8, 6>; break;
-        default: items = 16; pass_kernel = sort_pass_kernel<16, 3>; break;  // 8.9 ms vs 10.1 ms (C4)
+        case 0: items = 16; pass_kernel = sort_pass_kernel<16, 2, false>; break;
+        case 1: items = 16; pass_kernel = sort_pass_kernel<16, 3, false>; break;   // MATCH.ANY ranking
+        case 2: items = 12; pass_kernel = sort_pass_kernel<12, 3, false>; break;
+        case 4: items = 8; pass_kernel = sort_pass_kernel<8, 4, false>; break;
+        case 8: items = 16; pass_kernel = sort_pass_kernel<16, 2, true>; break;
+        case 10: items = 12; pass_kernel = sort_pass_kernel<12, 3, true>; break;
+        case 11: items = 12; pass_kernel = sort_pass_kernel<12, 4, true>; break;
+        case 12: items = 8; pass_kernel = sort_pass_kernel<8, 4, true>; break;
+        default: items = 16; pass_kernel = sort_pass_kernel<16, 3, true>; break;   // ballot ranking
     }
     const int tile_keys = RS_THREADS * items;
     const int64_t tiles = (n_rows + tile_keys - 1) / tile_keys;
