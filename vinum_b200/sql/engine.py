@@ -86,6 +86,7 @@ class Frame:
     def __init__(self, n: int, cols: Optional[Dict[str, Value]] = None):
         self.n = n
         self.cols: Dict[str, Value] = dict(cols or {})
+        self.virtual = False   # no table column behind it (literal-only SELECT)
 
 
 class Engine:
@@ -158,6 +159,12 @@ class Engine:
         else:
             frame = self._scan(used)
             resolved = {}
+            if not used:
+                # no column is referenced at all: the reference skips the table and projects over
+                # ONE empty batch (EmptyTableReaderOperator, planner.py:345-362, algebra.py:282-287);
+                # the projected arrays / broadcast literals define the row count
+                frame.n = 1
+                frame.virtual = True
             if q.where is not None:
                 frame = self._filter(frame, self._as_mask(self._eval(q.where, frame, resolved), frame.n))
         return self._tail(q, frame, resolved)
@@ -638,7 +645,13 @@ class Engine:
             top = None if q.limit is None else q.offset + q.limit
             frame = self._sort(frame, [self._eval(o, frame, resolved) for o in q.order_by], q.sort_order, top)
         values = [self._eval(e, frame, resolved) for e in q.select]
-        out = self._materialize(values, output_names(q.select), frame.n, q.limit, q.offset)
+        n = frame.n
+        if frame.virtual:
+            lengths = [v.length for v in values if _is_col(v)]
+            n = max(lengths) if lengths else 1
+            if any(length != n for length in lengths):
+                raise OperatorError("SELECT expressions produce arrays of different sizes")   # algebra.py:89-105
+        out = self._materialize(values, output_names(q.select), n, q.limit, q.offset)
         self.stats["kernels"] = int(L.lib.vk_launch_count()) - self.stats["kernels_before"]
         return out
 
