@@ -76,6 +76,26 @@ def _is_col(v) -> bool:
     return isinstance(v, (DeviceColumn, HostColumn))
 
 
+def _is_temporal_value(v) -> bool:
+    if isinstance(v, (np.datetime64, np.timedelta64)):
+        return True
+    return isinstance(v, DeviceColumn) and v.arrow_type is not None and pa.types.is_temporal(v.arrow_type)
+
+
+def _temporal_numpy_dtype(t: pa.DataType) -> Optional[str]:
+    """NumPy dtype a temporal Arrow column is viewed as on the host (what to_numpy() of the
+    reference's NumPy path yields)."""
+    if pa.types.is_timestamp(t):
+        return f"datetime64[{t.unit}]"
+    if pa.types.is_date32(t):
+        return "datetime64[D]"
+    if pa.types.is_date64(t):
+        return "datetime64[ms]"
+    if pa.types.is_duration(t):
+        return f"timedelta64[{t.unit}]"
+    return None
+
+
 def _is_num(v) -> bool:
     return isinstance(v, (int, float, bool, np.integer, np.floating, np.bool_))
 
@@ -273,6 +293,12 @@ class Engine:
     def _arith2(self, sym: str, a: Value, b: Value) -> Value:
         if isinstance(a, HostColumn) or isinstance(b, HostColumn) or isinstance(a, str) or isinstance(b, str):
             raise OperatorError(f"operator {sym} is not defined for string operands")
+        if _is_temporal_value(a) or _is_temporal_value(b):
+            # datetime / timedelta arithmetic is NumPy's in the reference (np.add / np.subtract on
+            # datetime64 arrays): a host step here as well
+            x = self._device_to_numpy(a) if isinstance(a, DeviceColumn) else a
+            y = self._device_to_numpy(b) if isinstance(b, DeviceColumn) else b
+            return self._from_host(_NP_ARITH[sym](x, y))
         if isinstance(a, DeviceColumn) or isinstance(b, DeviceColumn):
             return ops.arith(sym, a, b, self.st)
         with np.errstate(all="ignore"):
@@ -295,12 +321,7 @@ class Engine:
         host_args = []
         for a in args:
             if isinstance(a, DeviceColumn):
-                arr = a.to_numpy(self.st)
-                valid = a.validity_to_numpy(self.st)
-                if valid is not None:  # NULL -> NaN view, like get_np_column (record_batch.py:100-125)
-                    arr = arr.astype(np.float64)
-                    arr[~valid] = np.nan
-                host_args.append(arr)
+                host_args.append(self._device_to_numpy(a))
             elif isinstance(a, HostColumn):
                 host_args.append(a.arr)
             else:
@@ -308,11 +329,32 @@ class Engine:
         res = call_host_function(name, host_args)
         return self._from_host(res)
 
+    def _device_to_numpy(self, a: DeviceColumn) -> np.ndarray:
+        """The NumPy view the reference computes on (RecordBatch.get_np_column, record_batch.py:
+        100-125): NULL -> NaN for numbers, NaT for temporal types."""
+        arr = a.to_numpy(self.st)
+        valid = a.validity_to_numpy(self.st)
+        tdt = _temporal_numpy_dtype(a.arrow_type) if a.arrow_type is not None else None
+        if tdt is not None:
+            arr = arr.view(tdt) if arr.dtype.itemsize == 8 else arr.astype(np.int64).astype(tdt)   # date32: int32 days
+            if valid is not None:
+                arr = arr.copy()
+                arr[~valid] = np.datetime64("NaT") if tdt.startswith("datetime") else np.timedelta64("NaT")
+            return arr
+        if valid is not None:
+            arr = arr.astype(np.float64)
+            arr[~valid] = np.nan
+        return arr
+
     def _from_host(self, res) -> Value:
         if isinstance(res, (pa.Array, pa.ChunkedArray)):
             if vk_dtype_of(res.type) is not None:
                 return DeviceColumn.from_arrow(res, self.st)
             return HostColumn(res)
+        if isinstance(res, np.ndarray) and res.shape != () and res.dtype.kind in "Mm":
+            return self._from_host(pa.array(res))      # NaT -> NULL; datetime64[D] -> date32, [s] -> timestamp[s]
+        if isinstance(res, (np.datetime64, np.timedelta64)):
+            return res
         if isinstance(res, np.ndarray) and res.shape != ():
             if res.dtype.kind in "iufb" and res.dtype.itemsize <= 8 and res.dtype != np.float16:
                 col = DeviceColumn.from_numpy(res if res.dtype != np.bool_ else res.astype(np.bool_), self.st)

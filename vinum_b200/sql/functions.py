@@ -58,7 +58,54 @@ def _concat(*args):
     return pa.array(out) if isinstance(out, np.ndarray) and out.shape != () else str(out)
 
 
+# ---- datetime constructors (DatetimeFunction and subclasses, functions.py:25-147) ----
+_NUMPY_UNITS = ["Y", "M", "W", "D", "h", "m", "s", "ms", "us", "ns"]
+
+
+def _as_numpy(a):
+    if isinstance(a, (pa.Array, pa.ChunkedArray)):
+        return a.to_numpy(zero_copy_only=False)
+    return a
+
+
+def _datetime_function(name: str, units, default_unit):
+    def f(*args):
+        if not args:
+            raise FunctionError(f"No arguments provided for {name} operator.")
+        arg = _as_numpy(args[0])
+        if not isinstance(arg, (np.ndarray, list, tuple)):
+            arg = (arg,)                                     # ensure_is_array
+        unit = default_unit
+        if len(args) > 1:
+            unit = args[1]
+            if unit not in units:
+                raise FunctionError(f"Unsupported {name} unit: '{unit}'. Supported units are: [{', '.join(units)}]")
+        arr = np.array(arg, dtype=f"datetime64[{unit}]" if unit else "datetime64")
+        got = np.datetime_data(arr.dtype)[0]
+        if got not in units:                                 # _ensure_unit_correctness: next finer supported unit
+            finer = units[-1]
+            if got in _NUMPY_UNITS:
+                for u in _NUMPY_UNITS[_NUMPY_UNITS.index(got) + 1:]:
+                    if u in units:
+                        finer = u
+                        break
+            arr = arr.astype(f"datetime64[{finer}]")
+        return arr
+    return f
+
+
+_datetime = _datetime_function("datetime", ["D", "s", "ms", "us", "ns"], None)
+_date = _datetime_function("date", ["D"], "D")
+_from_timestamp = _datetime_function("from_timestamp", ["s", "ms", "us", "ns"], "s")
+
+
+def _now(*_args):
+    return _datetime("now")
+
+
 _REGISTRY: Dict[str, Callable] = {
+    "now": _now, "date": _date, "datetime": _datetime, "from_timestamp": _from_timestamp,
+    "timedelta": np.timedelta64, "is_busday": np.is_busday,
     "to_bool": _cast("bool"), "to_float": _cast("float"), "to_int": _cast("int"), "to_str": _cast("str"),
     "abs": np.absolute, "sqrt": np.sqrt, "cos": np.cos, "sin": np.sin, "tan": np.tan, "power": np.power,
     "log": np.log, "log2": np.log2, "log10": np.log10, "pi": lambda: np.pi, "e": lambda: np.e,
