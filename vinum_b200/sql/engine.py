@@ -112,8 +112,16 @@ class Frame:
 class Engine:
     def __init__(self, table: pa.Table, stream: Optional[Stream] = None):
         self.table = table
-        self.st = stream or default_stream()
+        self._st = stream
         self.stats = {"kernels_before": int(L.lib.vk_launch_count())}
+
+    @property
+    def st(self) -> Stream:
+        """The CUDA stream every operator of this query runs on (created on first use: binding and
+        planning need no device)."""
+        if self._st is None:
+            self._st = default_stream()
+        return self._st
 
     # ================================================================ binding
     def _bind(self, q: Query) -> Query:
