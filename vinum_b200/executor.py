@@ -15,13 +15,12 @@ from __future__ import annotations
 import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
-import numpy as np
 import pyarrow as pa
 
 from . import _lib as L
 from ._lib import lib
-from .aggregate import Aggregator, output_type
-from .device import (DeviceBatch, DeviceBuffer, DeviceColumn, Stream, VK_SIZE, default_stream, vk_dtype_of)
+from .aggregate import Aggregator
+from .device import (DeviceBuffer, DeviceColumn, Stream, VK_SIZE, default_stream, vk_dtype_of)
 from .ops import Predicate
 
 DEFAULT_CHUNK_ROWS = 1 << 24  # the reference's 10 000-row batches would be launch-latency bound

@@ -7,7 +7,7 @@ function here computes on the host.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import List, Optional, Sequence, Union
 
 import numpy as np
 import pyarrow as pa

@@ -31,7 +31,7 @@ from .. import _lib as L
 from .. import ops
 from ..aggregate import Aggregator
 from ..device import DeviceBatch, DeviceColumn, Stream, default_stream, vk_dtype_of
-from .ast import (AGG_FUNCS, NUMPY_AGG_MAPPING, Column, Expression, Literal, Node, Op, Query, SortOrder,
+from .ast import (NUMPY_AGG_MAPPING, Column, Expression, Literal, Node, Op, Query, SortOrder,
                   contains_aggregate, is_aggregate_call, walk)
 from .functions import call_host_function
 from .parser import ParserError, parse_sql

@@ -16,7 +16,7 @@ numeric literal folded into the constant, `*` expanded against the schema (parse
 from __future__ import annotations
 
 import re
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 from .ast import Column, Expression, Literal, Node, Op, Query, SortOrder
 

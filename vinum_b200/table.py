@@ -9,7 +9,7 @@ host `Table`, like the reference's MaterializeTableOperator produces (algebra.py
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import pyarrow as pa
 
