@@ -261,6 +261,61 @@ print("ok", rank)
 """
 
 
+_GLOO_ONESHOT_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from vinum_b200.dist import partial_block_words, collect_partial_blocks
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+w, cap = 5, 8
+for groups in ([3, 6], [0, 8], [9, 2], [0, 0]):          # third case: rank 0 overflows its block
+    g = groups[rank]
+    blk = torch.zeros(partial_block_words(cap, w), dtype=torch.int64)
+    blk[0] = g
+    n = min(g, cap)
+    # record j of rank r = [r, j, r*100+j, 7, 7]
+    for j in range(n):
+        blk[1 + j * w: 1 + (j + 1) * w] = torch.tensor([rank, j, rank * 100 + j, 7, 7])
+    allb = torch.empty(world * blk.numel(), dtype=torch.int64)
+    dist.all_gather_into_tensor(allb, blk)
+    heads = [int(x) for x in allb.view(world, -1)[:, 0].tolist()]
+    assert heads == groups                                   # every rank sees every header
+    res = collect_partial_blocks(allb, heads, cap, w)
+    if max(groups) > cap:
+        assert res is None                                   # unanimous fallback to the repartition path
+        continue
+    total, recs = res
+    assert total == sum(groups) and recs.numel() == total * w
+    recs = recs.view(-1, w)
+    want = [[r, j, r * 100 + j, 7, 7] for r in range(world) for j in range(groups[r])]
+    assert recs.tolist() == want
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_one_shot_partial_block_exchange_over_gloo_world2(tmp_path):
+    """The low-cardinality exchange of DistributedAggregator.finish() (one all-gather of fixed-size
+    `[n_groups | records]` blocks, unanimous overflow fallback) with 2 CPU ranks."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker_oneshot.py"
+    script.write_text(_GLOO_ONESHOT_WORKER.format(root=str(ROOT), port=port))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+
+
 def test_partial_group_exchange_over_gloo_world2(tmp_path):
     """The all-to-all-v of partial-aggregate records with 2 CPU ranks."""
     import socket

@@ -43,6 +43,25 @@ def exchange_plan(counts: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarra
     return send_offsets, send_sizes, recv_offsets, recv_sizes
 
 
+def partial_block_words(cap_groups: int, record_words: int) -> int:
+    """Words of one rank's block in the one-shot exchange: [n_groups | cap_groups records]."""
+    return 1 + cap_groups * record_words
+
+
+def collect_partial_blocks(all_blocks: "torch.Tensor", heads: Sequence[int], cap_groups: int, record_words: int):
+    """After the all-gather of every rank's `[n_groups | records...]` block: None when any rank
+    overflowed its block (every rank sees every header, so the fallback to the all-to-all
+    repartition is unanimous), else (total records, the ranks' valid records as one tensor)."""
+    import torch
+    if max(heads) > cap_groups:
+        return None
+    world = len(heads)
+    blocks = all_blocks.view(world, partial_block_words(cap_groups, record_words))
+    parts = [blocks[r, 1:1 + int(heads[r]) * record_words] for r in range(world) if heads[r]]
+    total = int(sum(int(h) for h in heads))
+    return total, (torch.cat(parts) if parts else blocks.new_empty(0))
+
+
 def all_to_all_records(send: "torch.Tensor", send_sizes: Sequence[int], recv_sizes: Sequence[int], words: int,
                        group=None) -> "torch.Tensor":
     """all-to-all-v of fixed-width u64 records (int64 tensor view): `send` holds the
@@ -164,7 +183,7 @@ class DistributedAggregator:
         w = words.value
         cap = self.SMALL_GROUPS
         g = self.agg.num_groups(st)                                   # host sync 1
-        blk_words = 1 + cap * w
+        blk_words = partial_block_words(cap, w)
         with torch.cuda.stream(self._tstream):
             blk = torch.empty(blk_words, dtype=torch.int64, device=dev)
             blk[0] = g
@@ -175,20 +194,15 @@ class DistributedAggregator:
                                            C.c_void_p(blk.data_ptr() + 8), st.ptr)
             allb = torch.empty(self.world * blk_words, dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(allb, blk, group=self.group)
-            allb = allb.view(self.world, blk_words)
-            heads = [int(x) for x in allb[:, 0].cpu().tolist()]      # host sync 2
+            heads = [int(x) for x in allb.view(self.world, blk_words)[:, 0].cpu().tolist()]      # host sync 2
             self._mark("export + all_gather of partial blocks")
-            if max(heads) > cap:
-                small = False
-            else:
-                small = True
-                if self.rank == 0:
-                    parts = [allb[r, 1:1 + heads[r] * w] for r in range(self.world) if heads[r]]
-                    total = sum(heads)
-                    fresh = Aggregator(self.agg.key_types, self.agg.funcs, expected_groups=max(total, 1))
-                    if parts:
-                        recs = torch.cat(parts)
-                        lib.vk_agg_merge_partials(fresh._h, C.c_void_p(recs.data_ptr()), total, st.ptr)
+            collected = collect_partial_blocks(allb, heads, cap, w)
+            small = collected is not None
+            if small and self.rank == 0:
+                total, recs = collected
+                fresh = Aggregator(self.agg.key_types, self.agg.funcs, expected_groups=max(total, 1))
+                if total:
+                    lib.vk_agg_merge_partials(fresh._h, C.c_void_p(recs.data_ptr()), total, st.ptr)
         if not small:
             self.repartition()
             return self.gather_raw()
