@@ -470,3 +470,34 @@ def test_properties_at_scale(vb, stream):
     r = perm.result_raw(stream)
     assert int(r[3][0][0]) + (int(r[4][0][0]) << 64) == n * (n - 1) // 2
     assert int(r[3][1].view(np.int64)[0]) == 0 and int(r[3][2].view(np.int64)[0]) == n - 1
+
+
+def test_northstar_properties_at_full_size(vb, stream):
+    """BASELINE.json's headline size (1e9 rows; the three referenced columns resident): properties
+    that need no oracle.  The fused filter -> hash aggregate must (a) take the shared-memory path in
+    ONE main launch, (b) find exactly the 1000 keys 0..999, (c) count exactly the rows the
+    predicate selects -- cross-checked by an un-grouped COUNT through the general kernel on a
+    materialised mask -- and (d) sum to the un-grouped SUM over the same mask within 1e-9."""
+    from vinum_b200 import datagen, ops, _lib as L
+    n = int(os.environ.get("VK_TEST_FULL_ROWS", 1_000_000_000))
+    dev = datagen.device_table(["i0", "f0", "f1"], 0, n, stream=stream)
+    pred = ops.Predicate.compare(dev.column("f0"), ">", 0.5)
+    agg = vb.Aggregator([pa.int64()], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64())])
+    agg.profile(True)
+    agg.update([dev.column("i0")], [None, dev.column("f1")], pred, stream)
+    keys, kv, cnt, lo, hi, valid = agg.result_raw(stream)
+    ms, launches, rows = agg.profile_read(1)
+    assert agg.last_path == 1 and launches == 2 and rows >= n - 4096   # learning launch + one main launch
+    agg.close()
+    assert np.array_equal(np.sort(keys[0].view(np.int64)), np.arange(1000)) and kv.all()
+    mask = ops.compare(dev.column("f0"), ">", 0.5, stream)
+    one = vb.Aggregator([], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64())])
+    one.update([], [None, dev.column("f1")], ops.Predicate.from_mask(mask), stream)
+    r = one.result_raw(stream)
+    one.close()
+    selected, total = int(r[2][0]), r[3][1].view(np.float64)[0]
+    assert abs(selected / n - 0.5) < 1e-3
+    assert int(cnt.sum()) == selected
+    assert np.isclose(lo[1].view(np.float64).sum(), total, rtol=1e-9, atol=1e-3)
+    # every group gets its share: uniform keys -> counts within 1 % of n / 2000
+    assert np.all(np.abs(cnt.astype(np.float64) / (selected / 1000) - 1.0) < 0.01)
