@@ -277,13 +277,18 @@ class Parser:
         return left
 
     def _other(self) -> Node:
-        if self._accept_op("~"):
-            return Expression(Op.BINARY_NOT, (self._other(),))
-        node = self._additive()
+        """"Any other operator" level of PostgreSQL (| & # || and prefix ~), left associative:
+        `~a | b` is `(~a) | b`, while `~a + b` is `~(a + b)` because + binds tighter."""
+        node = self._other_operand()
         while self.tok.kind == "op" and self.tok.text in _OTHER:
             op = _OTHER[self._advance().text]
-            node = Expression(op, (node, self._additive()))
+            node = Expression(op, (node, self._other_operand()))
         return node
+
+    def _other_operand(self) -> Node:
+        if self._accept_op("~"):
+            return Expression(Op.BINARY_NOT, (self._other_operand(),))
+        return self._additive()
 
     def _additive(self) -> Node:
         node = self._multiplicative()
