@@ -1,0 +1,31 @@
+# Round-2 opener: the opt-in kernel variants written (unmeasured, no GPU minutes left) at the end
+# of round 1.  Each runs parity first (gpu_check's small cases + the GPU parity tests), then the
+# timing at C2 / C4 size; defaults only change once a variant is both green and faster.
+#   gpurun --timeout 1500 -- 'bash scripts/r02_variants.sh'
+source scripts/gpu_round.sh true
+rm -f gpurun_out/round.log
+# filter_kernel: bit 0 = 4096-row tiles, bits 2-3 = batched scatter (4: single buffer, 8: double)
+for c in 0 4 8 5 9; do
+  export VINUM_B200_FILTER_CFG=$c
+  TAILN=2 run filter_cfg$c 300 python -u scripts/gpu_check.py filter
+done
+for c in 4 8; do
+  export VINUM_B200_FILTER_CFG=$c
+  TAILN=3 run pytest_filter_cfg$c 900 python -m pytest tests -m gpu -x -q -k "filter or where or scale or sql_matches"
+done
+unset VINUM_B200_FILTER_CFG
+# sort_prepare8_kernel<U> and take8_kernel<U>
+for u in 0 2 4; do
+  export VINUM_B200_SORT_PREP=$u VINUM_B200_TAKE_U=$u
+  TAILN=2 run sort_u$u 300 python -u scripts/gpu_check.py sort
+done
+export VINUM_B200_SORT_PREP=4 VINUM_B200_TAKE_U=4
+TAILN=3 run pytest_sort_u4 900 python -m pytest tests -m gpu -x -q -k "sort or order or scale or sql_matches"
+unset VINUM_B200_SORT_PREP VINUM_B200_TAKE_U
+# compare8_kernel<DOM, U>: plain 8-byte columns (scalar, column-column, BETWEEN)
+for u in 0 2 4; do
+  export VINUM_B200_CMP_FAST=$u
+  TAILN=2 run cmp_fast$u 300 python -u scripts/gpu_check.py filter
+done
+export VINUM_B200_CMP_FAST=4
+TAILN=3 run pytest_cmp_fast4 900 python -m pytest tests -m gpu -x -q -k "compare or between or mask or where or sql_matches"

@@ -48,6 +48,47 @@ __global__ void __launch_bounds__(256) compare_kernel(CmpParams p, int64_t n, ui
     }
 }
 
+// Plain 8-byte column(s) compared in their own domain (no validity, no NaN view, 16-byte aligned):
+// U lane-contiguous row pairs per thread, the 16-byte loads of a round issued together, two mask
+// bytes stored per pair.  compare_kernel dispatches on dtype and mode row by row, which leaves one
+// 8-byte load in flight per thread (SASS) -- 3.5 TB/s at 1e8 rows.  Opt-in (VINUM_B200_CMP_FAST=U).
+template <int DOM, int U>
+__global__ void __launch_bounds__(256) compare8_kernel(CmpParams p, int64_t n, uint8_t* __restrict__ out) {
+    using T = typename DomT<DOM>::type;
+    const int64_t npairs = n >> 1;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const T lo = scalar_dom<DOM>(p.lo), hi = scalar_dom<DOM>(p.hi);
+    auto eval = [&](uint64_t xb, uint64_t yb) -> uint32_t {
+        const T x = bits_dom<DOM>(xb);
+        if (p.mode == 0) return apply_cmp(p.op, x, lo);
+        if (p.mode == 1) return apply_cmp(p.op, x, bits_dom<DOM>(yb));
+        if (p.mode == 2) return (x >= lo) & (x <= hi);
+        return (x < lo) | (x > hi);
+    };
+    for (int64_t q0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q0 < npairs; q0 += stride * U) {
+        uint4 a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + u * stride;
+            a[u] = b[u] = make_uint4(0, 0, 0, 0);
+            if (q < npairs) {
+                a[u] = ldg_stream16(p.lhs.data + q * 16);
+                if (p.mode == 1) b[u] = ldg_stream16(p.rhs.data + q * 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + u * stride;
+            if (q < npairs) {
+                const uint32_t r0 = eval(((uint64_t) a[u].y << 32) | a[u].x, ((uint64_t) b[u].y << 32) | b[u].x);
+                const uint32_t r1 = eval(((uint64_t) a[u].w << 32) | a[u].z, ((uint64_t) b[u].w << 32) | b[u].z);
+                reinterpret_cast<uint16_t*>(out)[q] = (uint16_t) (r0 | (r1 << 8));
+            }
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = cmp_row<DOM>(p, n - 1);
+}
+
 struct IsinParams {
     Col x;
     const uint64_t* values;  // device, already converted to the domain's bit pattern
@@ -176,8 +217,15 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 
 // PK: predicate kind (vk_pred.cuh); ITERS: row pairs per thread (tile = 512 * ITERS rows); KEEP: the
 // predicate column's registers are kept from phase 1 and reused when that column is also an output.
-template <int PK, int ITERS, bool KEEP>
+// BATCH (1 or 2; the host checks that every column is 8-byte, 16-byte aligned and has no validity
+// bitmap): phase 2 issues the ITERS 16-byte loads of a column back to back and only then stores, and
+// the first column's loads are issued BEFORE the look-back, whose latency they overlap.  BATCH 2
+// also loads column c+1 before it stores column c.  The BATCH 0 scatter loop loads and stores one
+// row pair at a time (one load in flight per thread: SASS of round 1) and leaves the memory-level
+// parallelism to the 64 resident warps.
+template <int PK, int ITERS, bool KEEP, int BATCH = 0>
 __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constant__ FilterParams p) {
+    static_assert(BATCH == 0 || !KEEP, "the batched scatter re-reads the predicate column");
     constexpr int TILE = FT_THREADS * 2 * ITERS;
     constexpr int NCNT = ITERS * (FT_THREADS / 32);   // (iter, warp) counts: 32 or 64
     constexpr int PER_LANE = NCNT / 32;
@@ -207,11 +255,59 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
     uint32_t lane_off[ITERS];
     uint4 praw[KEEP ? ITERS : 1];
     const unsigned lt = lanemask_lt();
+    // (BATCH) the ITERS predicate loads go out together and the operator is branched on once; the
+    // BATCH 0 loop below compares pair by pair, so each load waits for the previous pair's branches
+    uint32_t pflags = 0;
+    if constexpr (BATCH != 0 && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
+        uint4 pq[ITERS];
+        uint32_t live = 0;  // bit r: row r of this thread exists
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
+            pq[it] = make_uint4(0, 0, 0, 0);
+            if (r0 + 1 < p.n) {
+                pq[it] = ldg_stream16(p.pred.col.data + r0 * 8);
+                live |= 3u << (2 * it);
+            } else if (r0 < p.n) {
+                const uint2 t = ldg_stream8(p.pred.col.data + r0 * 8);
+                pq[it].x = t.x;
+                pq[it].y = t.y;
+                live |= 1u << (2 * it);
+            }
+        }
+#define VK_FILTER_PRED_ROWS(OP)                                                                          \
+        _Pragma("unroll") for (int it = 0; it < ITERS; ++it) {                                           \
+            const uint64_t a = ((uint64_t) pq[it].y << 32) | pq[it].x, b = ((uint64_t) pq[it].w << 32) | pq[it].z; \
+            bool ok0, ok1;                                                                               \
+            if constexpr (PK == PK_F64_VEC) {                                                            \
+                const double c = __longlong_as_double((long long) p.pred.scalar.bits);                   \
+                ok0 = __longlong_as_double((long long) a) OP c;                                          \
+                ok1 = __longlong_as_double((long long) b) OP c;                                          \
+            } else {                                                                                     \
+                ok0 = (int64_t) a OP (int64_t) p.pred.scalar.bits;                                       \
+                ok1 = (int64_t) b OP (int64_t) p.pred.scalar.bits;                                       \
+            }                                                                                            \
+            pflags |= ((uint32_t) ok0 << (2 * it)) | ((uint32_t) ok1 << (2 * it + 1));                   \
+        }
+        switch (p.pred.op) {
+            case VK_EQ: VK_FILTER_PRED_ROWS(==) break;
+            case VK_NE: VK_FILTER_PRED_ROWS(!=) break;
+            case VK_GT: VK_FILTER_PRED_ROWS(>) break;
+            case VK_GE: VK_FILTER_PRED_ROWS(>=) break;
+            case VK_LT: VK_FILTER_PRED_ROWS(<) break;
+            default: VK_FILTER_PRED_ROWS(<=) break;
+        }
+#undef VK_FILTER_PRED_ROWS
+        pflags &= live;
+    }
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
         int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
         bool f0, f1;
-        if constexpr (KEEP && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
+        if constexpr (BATCH != 0 && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
+            f0 = (pflags >> (2 * it)) & 1u;
+            f1 = (pflags >> (2 * it + 1)) & 1u;
+        } else if constexpr (KEEP && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
             f0 = f1 = false;
             if (r0 + 1 < p.n) {
                 const uint4 q = ldg_stream16(p.pred.col.data + r0 * 8);
@@ -243,6 +339,28 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
         lane_off[it] = __popc(b0 & lt) + __popc(b1 & lt);
         flags |= ((uint32_t) f0 << (2 * it)) | ((uint32_t) f1 << (2 * it + 1));
         if (lane == 0) s_cnt[it * (FT_THREADS / 32) + warp] = __popc(b0) + __popc(b1);
+    }
+    // (BATCH) a selected pair's 16 bytes of column c; flags are clear for rows past the end
+    uint4 qa[BATCH ? ITERS : 1], qb[BATCH == 2 ? ITERS : 1];
+    auto load_col = [&](int c, uint4 (&q)[BATCH ? ITERS : 1]) {
+        const uint8_t* d = p.cols[c].data;
+#pragma unroll
+        for (int it = 0; it < (BATCH ? ITERS : 0); ++it) {
+            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
+            q[it] = make_uint4(0, 0, 0, 0);
+            if ((flags >> (2 * it)) & 3u) {
+                if (r0 + 1 < p.n) {
+                    q[it] = ldg_stream16(d + r0 * 8);
+                } else {  // last, unpaired row of the batch
+                    const uint2 t = ldg_stream8(d + r0 * 8);
+                    q[it].x = t.x;
+                    q[it].y = t.y;
+                }
+            }
+        }
+    };
+    if constexpr (BATCH != 0) {
+        if (p.n_cols > 0) load_col(0, qa);
     }
     __syncthreads();
 
@@ -300,44 +418,76 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
     const int64_t tile_excl = s_excl;
 
     // ---- phase 2: scatter every column; a warp writes one contiguous run per iter ----
-    for (int c = 0; c < p.n_cols; ++c) {
-        const Col col = p.cols[c];
-        const int es = dtype_size(col.dtype);
-        uint8_t* outv = p.out_valid[c];
-        const bool vec16 = (es == 8) && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0);
-        const bool from_regs = KEEP && (PK == PK_F64_VEC || PK == PK_I64_VEC) && es == 8 && col.data == p.pred.col.data;
+    if constexpr (BATCH != 0) {
 #pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const uint32_t f = (flags >> (2 * it)) & 3u;
-            if (f == 0) continue;
-            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
-            int64_t pos = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
-            if (es == 8) {
-                uint64_t v0, v1;
-                if (from_regs) {
-                    const uint4 q = praw[KEEP ? it : 0];
-                    v0 = ((uint64_t) q.y << 32) | q.x;
-                    v1 = ((uint64_t) q.w << 32) | q.z;
-                } else if (vec16 && r0 + 1 < p.n) {
-                    uint4 q = ldg_stream16(col.data + r0 * 8);
-                    v0 = ((uint64_t) q.y << 32) | q.x;
-                    v1 = ((uint64_t) q.w << 32) | q.z;
-                } else {
-                    v0 = (f & 1) ? reinterpret_cast<const uint64_t*>(col.data)[r0] : 0;
-                    v1 = (f & 2) ? reinterpret_cast<const uint64_t*>(col.data)[r0 + 1] : 0;
-                }
-                uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
-                if (f & 1) o[pos++] = v0;
-                if (f & 2) o[pos] = v1;
-            } else {
-                int64_t q = pos;
-                if (f & 1) store_from_u64(p.out_data[c], col.dtype, q++, load_as_u64(col, r0));
-                if (f & 2) store_from_u64(p.out_data[c], col.dtype, q, load_as_u64(col, r0 + 1));
+        for (int it = 0; it < ITERS; ++it) lane_off[it] += s_cnt[it * (FT_THREADS / 32) + warp];
+        auto store_col = [&](int c, const uint4 (&q)[ITERS]) {
+            uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const uint32_t f = (flags >> (2 * it)) & 3u;
+                if (f == 0) continue;
+                int64_t pos = tile_excl + lane_off[it];
+                if (f & 1) o[pos++] = ((uint64_t) q[it].y << 32) | q[it].x;
+                if (f & 2) o[pos] = ((uint64_t) q[it].w << 32) | q[it].z;
             }
-            if (outv != nullptr) {
-                int64_t q = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
-                if (f & 1) outv[q++] = col_valid(col, r0);
-                if (f & 2) outv[q] = col_valid(col, r0 + 1);
+        };
+        if constexpr (BATCH == 1) {
+            for (int c = 0; c < p.n_cols; ++c) {
+                if (c > 0) load_col(c, qa);
+                store_col(c, qa);
+            }
+        } else {
+            int c = 0;
+            while (c < p.n_cols) {
+                if (c + 1 < p.n_cols) load_col(c + 1, qb);
+                store_col(c, qa);
+                if (++c >= p.n_cols) break;
+                if (c + 1 < p.n_cols) load_col(c + 1, qa);
+                store_col(c, qb);
+                ++c;
+            }
+        }
+    } else {
+        for (int c = 0; c < p.n_cols; ++c) {
+            const Col col = p.cols[c];
+            const int es = dtype_size(col.dtype);
+            uint8_t* outv = p.out_valid[c];
+            const bool vec16 = (es == 8) && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0);
+            const bool from_regs = KEEP && (PK == PK_F64_VEC || PK == PK_I64_VEC) && es == 8 && col.data == p.pred.col.data;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const uint32_t f = (flags >> (2 * it)) & 3u;
+                if (f == 0) continue;
+                const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
+                int64_t pos = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
+                if (es == 8) {
+                    uint64_t v0, v1;
+                    if (from_regs) {
+                        const uint4 q = praw[KEEP ? it : 0];
+                        v0 = ((uint64_t) q.y << 32) | q.x;
+                        v1 = ((uint64_t) q.w << 32) | q.z;
+                    } else if (vec16 && r0 + 1 < p.n) {
+                        uint4 q = ldg_stream16(col.data + r0 * 8);
+                        v0 = ((uint64_t) q.y << 32) | q.x;
+                        v1 = ((uint64_t) q.w << 32) | q.z;
+                    } else {
+                        v0 = (f & 1) ? reinterpret_cast<const uint64_t*>(col.data)[r0] : 0;
+                        v1 = (f & 2) ? reinterpret_cast<const uint64_t*>(col.data)[r0 + 1] : 0;
+                    }
+                    uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
+                    if (f & 1) o[pos++] = v0;
+                    if (f & 2) o[pos] = v1;
+                } else {
+                    int64_t q = pos;
+                    if (f & 1) store_from_u64(p.out_data[c], col.dtype, q++, load_as_u64(col, r0));
+                    if (f & 2) store_from_u64(p.out_data[c], col.dtype, q, load_as_u64(col, r0 + 1));
+                }
+                if (outv != nullptr) {
+                    int64_t q = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
+                    if (f & 1) outv[q++] = col_valid(col, r0);
+                    if (f & 2) outv[q] = col_valid(col, r0 + 1);
+                }
             }
         }
     }
@@ -361,6 +511,28 @@ static int launch_compare(const CmpParams& p, int64_t n, uint8_t* out, VkStream 
     VK_REQUIRE(out, "compare: out_mask is NULL");
     int g = grid_for((n + 3) / 4);
     cudaStream_t s = (cudaStream_t) stream;
+    static int fast = -1;  // row pairs per thread of compare8_kernel (0: off)
+    if (fast < 0) { const char* v = getenv("VINUM_B200_CMP_FAST"); fast = v ? atoi(v) : 0; }
+    auto plain8 = [&](const Col& c) {
+        const int want = p.domain == DOM_F64 ? VK_F64 : (p.domain == DOM_I64 ? VK_I64 : (p.domain == DOM_U64 ? VK_U64 : -1));
+        return c.dtype == want && c.validity == nullptr && !c.nan_nulls && (reinterpret_cast<uintptr_t>(c.data) & 15) == 0;
+    };
+    if (fast >= 2 && plain8(p.lhs) && (p.mode != 1 || plain8(p.rhs)) && (reinterpret_cast<uintptr_t>(out) & 1) == 0) {
+        const int gp = grid_for((n / 2 + 3) / 4);
+#define VK_CMP8_GO(DOM)                                                             \
+        do {                                                                        \
+            if (fast >= 4) compare8_kernel<DOM, 4><<<gp, 256, 0, s>>>(p, n, out);   \
+            else compare8_kernel<DOM, 2><<<gp, 256, 0, s>>>(p, n, out);             \
+        } while (0)
+        switch (p.domain) {
+            case DOM_I64: VK_CMP8_GO(DOM_I64); break;
+            case DOM_U64: VK_CMP8_GO(DOM_U64); break;
+            default: VK_CMP8_GO(DOM_F64); break;
+        }
+#undef VK_CMP8_GO
+        VK_CHECK_LAUNCH("compare8_kernel");
+        return VK_OK;
+    }
     switch (p.domain) {
         case DOM_I64: compare_kernel<DOM_I64><<<g, 256, 0, s>>>(p, n, out); break;
         case DOM_U64: compare_kernel<DOM_U64><<<g, 256, 0, s>>>(p, n, out); break;
@@ -522,8 +694,11 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
     // geometry: row pairs per thread / keep the predicate column in registers (measured, profiles/)
     static int cfg = -1;
     if (cfg < 0) { const char* v = getenv("VINUM_B200_FILTER_CFG"); cfg = v ? atoi(v) : 0; }
+    // bit 0: 4096-row tiles; bit 1: keep the predicate column; bits 2-3: batched scatter (1 or 2, see
+    // filter_kernel) when every column of the pass qualifies
     const int iters = (cfg & 1) ? 8 : 4;
-    const bool keep = (cfg & 2) != 0;
+    const int batch_cfg = (cfg >> 2) & 3;
+    const bool keep = (cfg & 2) != 0 && batch_cfg == 0;
     const int tile_rows = FT_THREADS * 2 * iters;
     const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
     // columns are processed FT_MAX_COLS at a time; each pass re-evaluates the predicate
@@ -538,6 +713,12 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
             p.out_data[c] = out_data[c0 + c];
             p.out_valid[c] = (cols[c0 + c].validity && out_valid_bytes) ? out_valid_bytes[c0 + c] : nullptr;
         }
+        int batch = batch_cfg > 2 ? 2 : batch_cfg;
+        for (int c = 0; c < p.n_cols && batch; ++c)
+            if (dtype_size(p.cols[c].dtype) != 8 || p.out_valid[c] != nullptr ||
+                ((reinterpret_cast<uintptr_t>(p.cols[c].data) | reinterpret_cast<uintptr_t>(p.out_data[c])) & 7) != 0 ||
+                (reinterpret_cast<uintptr_t>(p.cols[c].data) & 15) != 0)
+                batch = 0;
         p.out_rows = out_rows;
         p.ticket = reinterpret_cast<unsigned long long*>(scratch);
         p.status = p.ticket + 1;
@@ -550,7 +731,12 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         VK_CUDA(cudaMemsetAsync(scratch, 0, vk_filter_scratch_bytes(n_rows), s));
 #define VK_FILTER_GO(PK)                                                                              \
         do {                                                                                              \
-            if (iters == 8) {                                                                             \
+            if (batch) {                                                                                  \
+                if (iters == 8 && batch == 2) filter_kernel<PK, 8, false, 2><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
+                else if (iters == 8) filter_kernel<PK, 8, false, 1><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
+                else if (batch == 2) filter_kernel<PK, 4, false, 2><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
+                else filter_kernel<PK, 4, false, 1><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);           \
+            } else if (iters == 8) {                                                                      \
                 if (keep) filter_kernel<PK, 8, true><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);          \
                 else filter_kernel<PK, 8, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);              \
             } else {                                                                                      \

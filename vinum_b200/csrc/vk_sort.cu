@@ -17,7 +17,6 @@
 namespace vk {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_MAX_ITEMS = 16;                // keys per thread of the largest tile geometry
 constexpr int RS_MIN_TILE = RS_THREADS * 8;     // smallest tile any geometry uses (sizes the status array)
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr uint32_t RS_NULLBIT = 0x80000000u;
@@ -93,6 +92,73 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const __grid_constant
     __syncthreads();
     for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x)
         if (s_hist[i]) atomicAdd(p.hist + i, (unsigned long long) s_hist[i]);
+}
+
+// Same contract for the common case -- 8-byte key column without a validity bitmap -- with U rows per
+// thread per round: the U (gathered) loads are issued together, and the histogram work of a round
+// runs while the next round's loads are in flight.  sort_prepare_kernel has one load in flight per
+// thread at half occupancy (long scoreboard 32 %, profiles/r01_sort_prepare_ncu_full.md).
+// Opt-in (VINUM_B200_SORT_PREP=U) until measured.
+template <int U>
+__global__ void __launch_bounds__(256) sort_prepare8_kernel(const __grid_constant__ PrepParams p) {
+    __shared__ uint32_t s_hist[8 * 256];
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t iters = (p.n + stride * U - 1) / (stride * U);  // uniform trip count: convergent votes
+    const uint64_t* data = reinterpret_cast<const uint64_t*>(p.col.data);
+    const bool is_float = p.col.dtype == VK_F64, is_signed = p.col.dtype == VK_I64;
+    const uint64_t flip = p.desc ? ~0ULL : 0ULL;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i0 = it * stride * U + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t src[U];
+        uint64_t code[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            src[u] = i < p.n ? (p.perm ? (p.perm[i] & ~RS_NULLBIT) : (uint32_t) i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) code[u] = (i0 + u * stride) < p.n ? data[src[u]] : 0ULL;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            const bool in = i < p.n;
+            uint64_t c = code[u];
+            if (is_float) {
+                const double d = __longlong_as_double((long long) c);
+                if (d != d) c = KEY_NAN;
+                else {
+                    if (d == 0.0) c = 0;  // -0.0 -> +0.0
+                    c = f64_to_ordered(c) ^ flip;
+                }
+            } else {
+                c = (is_signed ? (c ^ 0x8000000000000000ULL) : c) ^ flip;
+            }
+            if (in) {
+                p.out_key[i] = c;
+                p.out_idx[i] = src[u];
+            }
+            const unsigned active = __ballot_sync(0xffffffffu, in);
+            if (!active) continue;
+            const int leader = __ffs(active) - 1;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                const uint32_t digit = (uint32_t) (c >> (8 * d)) & 0xffu;
+                const uint32_t first = __shfl_sync(0xffffffffu, digit, leader);
+                if (__all_sync(0xffffffffu, !in || digit == first)) {
+                    if ((threadIdx.x & 31) == leader) atomicAdd(&s_hist[d * 256 + first], (uint32_t) __popc(active));
+                } else if (in) {
+                    atomicAdd(&s_hist[d * 256 + digit], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(p.hist + i, (unsigned long long) s_hist[i]);
+    // row 8 of the histogram (the NULL-bit digit): no NULLs here, every row is in bucket 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.hist + 8 * 256, (unsigned long long) p.n);
 }
 
 // exclusive scan of each digit's 256 buckets: hist -> bucket start offsets (in place)
@@ -314,6 +380,24 @@ __global__ void __launch_bounds__(256) take_kernel(const __grid_constant__ TakeP
     }
 }
 
+// 8-byte elements, no validity: U independent gathers in flight per thread (opt-in, VINUM_B200_TAKE_U).
+template <int U>
+__global__ void __launch_bounds__(256) take8_kernel(const uint64_t* __restrict__ data, const int64_t* __restrict__ indices,
+                                                    int64_t n, uint64_t* __restrict__ out) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * U) {
+        int64_t src[U];
+        uint64_t v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) src[u] = (i0 + u * stride) < n ? indices[i0 + u * stride] : 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (i0 + u * stride) < n ? data[src[u]] : 0ULL;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if ((i0 + u * stride) < n) out[i0 + u * stride] = v[u];
+    }
+}
+
 static unsigned grid_rows(int64_t n, int per_sm = 8) {
     int64_t need = (n + 255) / 256, cap = (int64_t) sm_count() * per_sm;
     if (need < 1) need = 1;
@@ -417,7 +501,13 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         pp.out_idx = sc.idx[nxt];
         pp.hist = sc.hist;
         VK_CUDA(cudaMemsetAsync(sc.hist, 0, 9 * 256 * 8, s));
-        sort_prepare_kernel<<<grid_rows(n_rows, 4), 256, 0, s>>>(pp);
+        static int prep = -1;  // rows per thread per round of the 8-byte fast path (0: general kernel)
+        if (prep < 0) { const char* v = getenv("VINUM_B200_SORT_PREP"); prep = v ? atoi(v) : 0; }
+        const bool plain8 = keys[k].validity == nullptr && !keys[k].nulls_as_nan &&
+                            (keys[k].dtype == VK_F64 || keys[k].dtype == VK_I64 || keys[k].dtype == VK_U64);
+        if (prep >= 4 && plain8) sort_prepare8_kernel<4><<<grid_rows(n_rows, 8), 256, 0, s>>>(pp);
+        else if (prep >= 2 && plain8) sort_prepare8_kernel<2><<<grid_rows(n_rows, 8), 256, 0, s>>>(pp);
+        else sort_prepare_kernel<<<grid_rows(n_rows, 4), 256, 0, s>>>(pp);
         VK_CHECK_LAUNCH("sort_prepare_kernel");
         cur = nxt;
         have_perm = true;
@@ -461,6 +551,16 @@ int vk_take(const VkColumn* col, const int64_t* indices, int64_t n_indices, void
     VK_REQUIRE(dtype_valid(col->dtype), "vk_take: bad dtype");
     VK_REQUIRE(col->validity == nullptr || out_valid_bytes, "vk_take: column has validity but no out_valid_bytes");
     TakeParams p{make_col(*col), indices, n_indices, out, col->validity ? out_valid_bytes : nullptr};
+    static int take_u = -1;
+    if (take_u < 0) { const char* v = getenv("VINUM_B200_TAKE_U"); take_u = v ? atoi(v) : 0; }
+    if (take_u >= 2 && dtype_size(col->dtype) == 8 && col->validity == nullptr &&
+        ((reinterpret_cast<uintptr_t>(p.col.data) | reinterpret_cast<uintptr_t>(out)) & 7) == 0) {
+        const uint64_t* d = reinterpret_cast<const uint64_t*>(p.col.data);
+        if (take_u >= 4) take8_kernel<4><<<grid_rows(n_indices), 256, 0, (cudaStream_t) stream>>>(d, indices, n_indices, (uint64_t*) out);
+        else take8_kernel<2><<<grid_rows(n_indices), 256, 0, (cudaStream_t) stream>>>(d, indices, n_indices, (uint64_t*) out);
+        VK_CHECK_LAUNCH("take8_kernel");
+        return VK_OK;
+    }
     take_kernel<<<grid_rows(n_indices), 256, 0, (cudaStream_t) stream>>>(p);
     VK_CHECK_LAUNCH("take_kernel");
     return VK_OK;
