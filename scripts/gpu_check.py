@@ -310,7 +310,45 @@ def s_sort():
     return res
 
 
-SECTIONS = {f.__name__: f for f in [s_datagen, s_filter, s_agg_parity, s_agg_highcard, s_agg_bench, s_sort]}
+@section("arith")
+def s_arith():
+    st = vb.default_stream()
+    res = {}
+    n = 1_000_003
+    names = ["i1", "i3", "f0", "f1"]
+    dev = {k: datagen.device_column(k, 0, n, stream=st) for k in names}
+    host = {k: datagen.host_column(k, 0, n) for k in names}
+    cases = [("+", "f0", "f1"), ("*", "f1", 2.5), ("/", "i1", "i3"), ("-", 1.0, "f0"), ("%", "i1", 7),
+             ("*", "i1", "i3"), ("neg", "f1", None), ("~", "i3", None), ("&", "i1", "i3")]
+    ok = True
+    with np.errstate(all="ignore"):
+        for op, a, b in cases:
+            da, db = dev.get(a, a) if isinstance(a, str) else a, dev.get(b, b) if isinstance(b, str) else b
+            ha, hb = host.get(a, a) if isinstance(a, str) else a, host.get(b, b) if isinstance(b, str) else b
+            got = ops.arith(op, da, db, st).to_numpy(st)
+            uf = {"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide, "%": np.mod, "&": np.bitwise_and,
+                  "neg": np.negative, "~": np.invert}[op]
+            want = uf(ha) if hb is None else uf(ha, hb)
+            same = got.dtype == want.dtype and np.array_equal(got.view(np.uint8), np.ascontiguousarray(want).view(np.uint8))
+            res[f"{a}{op}{b}"] = bool(same)
+            ok = ok and same
+    res["parity"] = bool(ok)
+    n = 100_000_000
+    f0 = datagen.device_column("f0", 0, n, stream=st)
+    f1 = datagen.device_column("f1", 0, n, stream=st)
+    out = vb.DeviceColumn.empty(n, L.F64, stream=st)
+    a, b = f0.vk(), f1.vk()
+    best, med = timed(lambda: lib.vk_arith(L.ADD, C.byref(a), None, C.byref(b), None, n, L.F64, C.c_void_p(out.data_ptr), st.ptr), st)
+    res["add_f64_ms"] = best
+    res["add_f64_GBps"] = n * 24 / best / 1e6
+    s = L.make_scalar(2.5)
+    best, med = timed(lambda: lib.vk_arith(L.MUL, C.byref(a), None, None, C.byref(s), n, L.F64, C.c_void_p(out.data_ptr), st.ptr), st)
+    res["mul_scalar_ms"] = best
+    res["mul_scalar_GBps"] = n * 16 / best / 1e6
+    return res
+
+
+SECTIONS = {f.__name__: f for f in [s_datagen, s_filter, s_agg_parity, s_agg_highcard, s_agg_bench, s_sort, s_arith]}
 
 if __name__ == "__main__":
     lib.vk_set_device(0)

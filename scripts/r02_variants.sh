@@ -29,3 +29,11 @@ for u in 0 2 4; do
 done
 export VINUM_B200_CMP_FAST=4
 TAILN=3 run pytest_cmp_fast4 900 python -m pytest tests -m gpu -x -q -k "compare or between or mask or where or sql_matches"
+unset VINUM_B200_CMP_FAST
+# arith8_kernel<CC, U>: 8-byte operands in the result's own class
+for u in 0 2 4; do
+  export VINUM_B200_ARITH_FAST=$u
+  TAILN=2 run arith_fast$u 300 python -u scripts/gpu_check.py arith
+done
+export VINUM_B200_ARITH_FAST=4
+TAILN=3 run pytest_arith_fast4 900 python -m pytest tests -m gpu -x -q -k "arith or project or expr or sql_matches"

@@ -2,6 +2,7 @@
 // vinum/core/expressions.py:13-24 evaluated in one coalesced pass.  Compiled with
 // -fmad=false: each result is a single correctly-rounded IEEE operation, as in NumPy.
 #include "vk_common.cuh"
+#include <cstdlib>
 #include "vk_pred.cuh"
 
 namespace vk {
@@ -104,6 +105,58 @@ __global__ void __launch_bounds__(256) arith_kernel(ArithParams p, int64_t n, vo
     }
 }
 
+// 8-byte operands and result in the compute class's own representation (int64 / uint64 / float64
+// columns without the NaN view, or scalars): U lane-contiguous row pairs per thread, 16-byte loads
+// issued together, 16-byte stores.  arith_kernel goes through the per-row dtype dispatch with one
+// 8-byte load per operand in flight.  Opt-in (VINUM_B200_ARITH_FAST=U) until measured.
+template <int CC, int U>
+__global__ void __launch_bounds__(256) arith8_kernel(ArithParams p, int64_t n, void* __restrict__ out) {
+    using T = typename CCT<CC>::type;
+    auto from_bits = [](uint64_t b) -> T {
+        if constexpr (CC == CC_F64) return __longlong_as_double((long long) b);
+        else return (T) b;
+    };
+    auto to_bits = [](T v) -> uint64_t {
+        if constexpr (CC == CC_F64) return (uint64_t) __double_as_longlong(v);
+        else return (uint64_t) v;
+    };
+    const int64_t npairs = n >> 1;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const bool unary = p.op >= VK_NEG;
+    const bool acol = p.a.is_col, bcol = !unary && p.b.is_col;
+    const uint32_t alo = (uint32_t) p.a.bits, ahi = (uint32_t) (p.a.bits >> 32);
+    const uint32_t blo = (uint32_t) p.b.bits, bhi = (uint32_t) (p.b.bits >> 32);
+    for (int64_t q0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q0 < npairs; q0 += stride * U) {
+        uint4 a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + u * stride;
+            a[u] = make_uint4(alo, ahi, alo, ahi);
+            b[u] = make_uint4(blo, bhi, blo, bhi);
+            if (q < npairs) {
+                if (acol) a[u] = ldg_stream16(p.a.col.data + q * 16);
+                if (bcol) b[u] = ldg_stream16(p.b.col.data + q * 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + u * stride;
+            if (q < npairs) {
+                const T x0 = from_bits(((uint64_t) a[u].y << 32) | a[u].x), x1 = from_bits(((uint64_t) a[u].w << 32) | a[u].z);
+                const T y0 = unary ? x0 : from_bits(((uint64_t) b[u].y << 32) | b[u].x);
+                const T y1 = unary ? x1 : from_bits(((uint64_t) b[u].w << 32) | b[u].z);
+                const uint64_t r0 = to_bits(arith_apply<CC>(p.op, x0, y0)), r1 = to_bits(arith_apply<CC>(p.op, x1, y1));
+                reinterpret_cast<uint4*>(out)[q] = make_uint4((uint32_t) r0, (uint32_t) (r0 >> 32), (uint32_t) r1, (uint32_t) (r1 >> 32));
+            }
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // last, unpaired row
+        const T x = load_operand<CC>(p.a, n - 1);
+        const T y = unary ? x : load_operand<CC>(p.b, n - 1);
+        reinterpret_cast<uint64_t*>(out)[n - 1] = to_bits(arith_apply<CC>(p.op, x, y));
+    }
+}
+
 static int make_operand(const VkColumn* col, const VkScalar* sc, int cc, int64_t n, Operand* o, const char* side) {
     if (col) {
         if (!dtype_valid(col->dtype)) return fail(VK_ERR_ARG, std::string("vk_arith: bad dtype on ") + side);
@@ -171,6 +224,32 @@ extern "C" int vk_arith(int op, const VkColumn* lhs_col, const VkScalar* lhs_sca
     int64_t need = (n_rows + 255) / 256, cap = (int64_t) sm_count() * 8;
     int g = (int) (need < cap ? need : cap);
     cudaStream_t s = (cudaStream_t) stream;
+    static int fast = -1;  // row pairs per thread of arith8_kernel (0: off)
+    if (fast < 0) { const char* v = getenv("VINUM_B200_ARITH_FAST"); fast = v ? atoi(v) : 0; }
+    auto raw8 = [&](const Operand& o) {
+        if (!o.is_col) return true;
+        const bool same_class = cc == CC_F64 ? o.col.dtype == VK_F64 : (o.col.dtype == VK_I64 || o.col.dtype == VK_U64);
+        return same_class && !o.col.nan_nulls && (reinterpret_cast<uintptr_t>(o.col.data) & 15) == 0;
+    };
+    const int out8 = cc == CC_F64 ? VK_F64 : (cc == CC_I64 ? VK_I64 : VK_U64);
+    if (fast >= 2 && cc != CC_F32 && out_dtype == out8 && raw8(p.a) && (unary || raw8(p.b)) &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        int64_t need8 = (n_rows / 2 + 256 * 4 - 1) / (256 * 4);
+        const int g8 = (int) (need8 < 1 ? 1 : (need8 < cap ? need8 : cap));
+#define VK_ARITH8_GO(CC)                                                                 \
+        do {                                                                             \
+            if (fast >= 4) arith8_kernel<CC, 4><<<g8, 256, 0, s>>>(p, n_rows, out);      \
+            else arith8_kernel<CC, 2><<<g8, 256, 0, s>>>(p, n_rows, out);                \
+        } while (0)
+        switch (cc) {
+            case CC_I64: VK_ARITH8_GO(CC_I64); break;
+            case CC_U64: VK_ARITH8_GO(CC_U64); break;
+            default: VK_ARITH8_GO(CC_F64); break;
+        }
+#undef VK_ARITH8_GO
+        VK_CHECK_LAUNCH("arith8_kernel");
+        return VK_OK;
+    }
     switch (cc) {
         case CC_I64: arith_kernel<CC_I64><<<g, 256, 0, s>>>(p, n_rows, out); break;
         case CC_U64: arith_kernel<CC_U64><<<g, 256, 0, s>>>(p, n_rows, out); break;
