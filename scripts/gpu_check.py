@@ -348,7 +348,57 @@ def s_arith():
     return res
 
 
-SECTIONS = {f.__name__: f for f in [s_datagen, s_filter, s_agg_parity, s_agg_highcard, s_agg_bench, s_sort, s_arith]}
+@section("onegroup")
+def s_onegroup():
+    """Un-grouped reduction: COUNT(*), SUM(f64), SUM(int64) -> 128-bit, MIN, MAX with and
+    without a fused predicate; parity on an odd row count, timing at 1e8 rows."""
+    st = vb.default_stream()
+    res = {}
+    funcs = [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64()), (L.AGG_SUM, pa.int64()),
+             (L.AGG_MIN, pa.int64()), (L.AGG_MAX, pa.float64()), (L.AGG_COUNT, pa.float64())]
+
+    def run(n, with_pred):
+        dev = datagen.device_table(["f0", "f1", "i1"], 0, n, stream=st)
+        pred = ops.Predicate.compare(dev.column("f0"), ">", 0.5) if with_pred else None
+        agg = Aggregator([], funcs)
+        agg.update([], [None, dev.column("f1"), dev.column("i1"), dev.column("i1"), dev.column("f0"), dev.column("f1")], pred, st)
+        _, aggs = agg.result_arrays(st)
+        agg.close()
+        return dev, pred, [a[0].as_py() for a in aggs]
+    ok = True
+    for with_pred in (False, True):
+        n = 1_000_003
+        _, _, got = run(n, with_pred)
+        f0, f1, i1 = (datagen.host_column(k, 0, n) for k in ("f0", "f1", "i1"))
+        m = f0 > 0.5 if with_pred else np.ones(n, bool)
+        want = [int(m.sum()), float(f1[m].sum()), int(i1[m].astype(object).sum()), int(i1[m].min()), float(f0[m].max()), int(m.sum())]
+        same = got[0] == want[0] and abs(got[1] - want[1]) <= 1e-9 * max(1.0, abs(want[1])) * 1e3 and \
+            int(got[2]) == want[2] and got[3] == want[3] and got[4] == want[4] and got[5] == want[5]
+        res[f"parity_pred{int(with_pred)}"] = bool(same)
+        if not same:
+            res[f"got_pred{int(with_pred)}"] = [str(x) for x in got]
+            res[f"want_pred{int(with_pred)}"] = [str(x) for x in want]
+        ok = ok and same
+    res["parity"] = bool(ok)
+    n = 100_000_000
+    dev = datagen.device_table(["f0", "f1"], 0, n, stream=st)
+    pred = ops.Predicate.compare(dev.column("f0"), ">", 0.5)
+
+    def once():
+        a = Aggregator([], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64())])
+        a.update([], [None, dev.column("f1")], pred, st)
+        return a
+    aggs = []
+    best, med = timed(lambda: aggs.append(once()), st)
+    for a in aggs:
+        a.close()
+    res["count_sum_pred_ms"] = best
+    res["count_sum_pred_GBps_16B_row"] = n * 16 / best / 1e6
+    return res
+
+
+SECTIONS = {f.__name__: f for f in [s_datagen, s_filter, s_agg_parity, s_agg_highcard, s_agg_bench, s_sort, s_arith,
+                                    s_onegroup]}
 
 if __name__ == "__main__":
     lib.vk_set_device(0)

@@ -37,3 +37,12 @@ for u in 0 2 4; do
 done
 export VINUM_B200_ARITH_FAST=4
 TAILN=3 run pytest_arith_fast4 900 python -m pytest tests -m gpu -x -q -k "arith or project or expr or sql_matches"
+unset VINUM_B200_ARITH_FAST
+# agg_onegroup8_kernel<PK, U>: un-grouped reduction over plain 8-byte columns
+for u in 0 2 4; do
+  export VINUM_B200_ONEGROUP_FAST=$u
+  TAILN=2 run onegroup_fast$u 300 python -u scripts/gpu_check.py onegroup
+done
+export VINUM_B200_ONEGROUP_FAST=4
+TAILN=3 run pytest_onegroup_fast4 900 python -m pytest tests -m gpu -x -q -k "onegroup or one_group or no_group or nogroup or sql_matches or gtest"
+unset VINUM_B200_ONEGROUP_FAST

@@ -117,34 +117,9 @@ struct OneParams {
     GTable table;
 };
 
-__global__ void __launch_bounds__(256) agg_onegroup_kernel(const __grid_constant__ OneParams p) {
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    uint64_t lo = 0, hi = 0, nn = 0, rows = 0;
-    double fsum = 0.0;
-    const int acc = p.fi < 0 ? ACC_NONE : p.spec.acc;
-    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
-        if (!pred_row(p.pred, i)) continue;
-        ++rows;
-        if (acc == ACC_NONE) continue;
-        if (!col_valid(p.val, i)) { ++nn; continue; }
-        if (acc == ACC_COUNT) continue;
-        uint64_t v = acc_load(p.spec, p.val, i);
-        switch (acc) {
-            case ACC_SUM_F64: fsum += __longlong_as_double((long long) v); break;
-            case ACC_SUM_I64: lo += v; break;
-            case ACC_SUM_I128: {
-                uint64_t nl = lo + v;
-                hi += ((!p.spec.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL) + (nl < lo ? 1ULL : 0ULL);
-                lo = nl;
-                break;
-            }
-            default: {
-                uint64_t o = ord_transform(p.spec.ord, p.spec.is_min, v);
-                lo = o > lo ? o : lo;
-                break;
-            }
-        }
-    }
+// Warp reduction of the per-thread partials and one atomic per warp into slot 0.
+__device__ __forceinline__ void onegroup_flush(const OneParams& p, int acc, uint64_t rows, uint64_t nn, uint64_t lo,
+                                               uint64_t hi, double fsum) {
     // warp reduction
     for (int d = 16; d > 0; d >>= 1) {
         rows += __shfl_xor_sync(0xffffffffu, rows, d);
@@ -182,6 +157,106 @@ __global__ void __launch_bounds__(256) agg_onegroup_kernel(const __grid_constant
             break;
         default: break;
     }
+}
+
+__global__ void __launch_bounds__(256) agg_onegroup_kernel(const __grid_constant__ OneParams p) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    uint64_t lo = 0, hi = 0, nn = 0, rows = 0;
+    double fsum = 0.0;
+    const int acc = p.fi < 0 ? ACC_NONE : p.spec.acc;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        if (!pred_row(p.pred, i)) continue;
+        ++rows;
+        if (acc == ACC_NONE) continue;
+        if (!col_valid(p.val, i)) { ++nn; continue; }
+        if (acc == ACC_COUNT) continue;
+        uint64_t v = acc_load(p.spec, p.val, i);
+        switch (acc) {
+            case ACC_SUM_F64: fsum += __longlong_as_double((long long) v); break;
+            case ACC_SUM_I64: lo += v; break;
+            case ACC_SUM_I128: {
+                uint64_t nl = lo + v;
+                hi += ((!p.spec.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL) + (nl < lo ? 1ULL : 0ULL);
+                lo = nl;
+                break;
+            }
+            default: {
+                uint64_t o = ord_transform(p.spec.ord, p.spec.is_min, v);
+                lo = o > lo ? o : lo;
+                break;
+            }
+        }
+    }
+    onegroup_flush(p, acc, rows, nn, lo, hi, fsum);
+}
+
+// The common un-grouped case -- no predicate or a vectorisable `column <op> literal` one, value
+// column 8 bytes wide without a validity bitmap -- with U lane-contiguous row pairs per thread and
+// the 16-byte loads of a round issued together (agg_onegroup_kernel has one 8-byte load per operand
+// in flight per thread).  Opt-in (VINUM_B200_ONEGROUP_FAST=U) until measured.
+template <int PK, int U>
+__global__ void __launch_bounds__(256) agg_onegroup8_kernel(const __grid_constant__ OneParams p) {
+    static_assert(PK == PK_NONE || PK == PK_F64_VEC || PK == PK_I64_VEC, "vectorisable predicates only");
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t npairs = p.n >> 1;
+    uint64_t lo = 0, hi = 0, rows = 0;
+    double fsum = 0.0;
+    const int acc = p.fi < 0 ? ACC_NONE : p.spec.acc;
+    const bool need_val = acc >= ACC_SUM_F64;
+    auto add = [&](uint64_t v) {
+        switch (acc) {
+            case ACC_SUM_F64: fsum += __longlong_as_double((long long) v); break;
+            case ACC_SUM_I64: lo += v; break;
+            case ACC_SUM_I128: {
+                const uint64_t nl = lo + v;
+                hi += ((!p.spec.in_unsigned && (int64_t) v < 0) ? ~0ULL : 0ULL) + (nl < lo ? 1ULL : 0ULL);
+                lo = nl;
+                break;
+            }
+            default: {
+                const uint64_t o = ord_transform(p.spec.ord, p.spec.is_min, v);
+                lo = o > lo ? o : lo;
+                break;
+            }
+        }
+    };
+    auto pass = [&](uint64_t bits) -> bool {
+        if constexpr (PK == PK_F64_VEC)
+            return apply_cmp(p.pred.op, __longlong_as_double((long long) bits), __longlong_as_double((long long) p.pred.scalar.bits));
+        else if constexpr (PK == PK_I64_VEC) return apply_cmp(p.pred.op, (int64_t) bits, (int64_t) p.pred.scalar.bits);
+        else return true;
+    };
+    for (int64_t q0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q0 < npairs; q0 += stride * U) {
+        uint4 pq[U], vq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + u * stride;
+            pq[u] = vq[u] = make_uint4(0, 0, 0, 0);
+            if (q < npairs) {
+                if constexpr (PK != PK_NONE) pq[u] = ldg_stream16(p.pred.col.data + q * 16);
+                if (need_val) vq[u] = ldg_stream16(p.val.data + q * 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (q0 + u * stride < npairs) {
+                const bool ok0 = pass(((uint64_t) pq[u].y << 32) | pq[u].x), ok1 = pass(((uint64_t) pq[u].w << 32) | pq[u].z);
+                rows += (uint64_t) ok0 + (uint64_t) ok1;
+                if (need_val) {
+                    if (ok0) add(((uint64_t) vq[u].y << 32) | vq[u].x);
+                    if (ok1) add(((uint64_t) vq[u].w << 32) | vq[u].z);
+                }
+            }
+        }
+    }
+    if ((p.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // last, unpaired row
+        const int64_t i = p.n - 1;
+        if (pred_row(p.pred, i)) {
+            ++rows;
+            if (need_val) add(acc_load(p.spec, p.val, i));
+        }
+    }
+    onegroup_flush(p, acc, rows, 0, lo, hi, fsum);
 }
 
 // ================================================================== finalize
@@ -1039,6 +1114,31 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             if (f >= 0) {
                 op.spec = a->specs[f];
                 op.val = make_col(values[f]);
+            }
+            static int fast1 = -1;  // row pairs per thread of agg_onegroup8_kernel (0: off)
+            if (fast1 < 0) { const char* v = getenv("VINUM_B200_ONEGROUP_FAST"); fast1 = v ? atoi(v) : 0; }
+            bool raw8 = pk == PK_NONE || pk == PK_F64_VEC || pk == PK_I64_VEC;
+            if (f >= 0 && op.spec.acc != ACC_COUNT) {
+                const int dt = op.val.dtype;
+                const bool f64_acc = op.spec.acc == ACC_SUM_F64 || (op.spec.acc == ACC_MAXORD && op.spec.ord == ORD_F64);
+                raw8 = raw8 && (f64_acc ? dt == VK_F64 : (dt == VK_I64 || dt == VK_U64)) && op.spec.acc != ACC_SUM_I64 &&
+                       (reinterpret_cast<uintptr_t>(op.val.data) & 15) == 0;
+            }
+            if (f >= 0) raw8 = raw8 && op.val.validity == nullptr;
+            if (fast1 >= 2 && raw8) {
+                int64_t need8 = (n_rows / 2 + 256 * 4 - 1) / (256 * 4);
+                const unsigned g8 = (unsigned) (need8 < 1 ? 1 : (need8 < capb ? need8 : capb));
+#define VK_ONE8_GO(PK)                                                               \
+                do {                                                                 \
+                    if (fast1 >= 4) agg_onegroup8_kernel<PK, 4><<<g8, 256, 0, s>>>(op); \
+                    else agg_onegroup8_kernel<PK, 2><<<g8, 256, 0, s>>>(op);         \
+                } while (0)
+                if (pk == PK_NONE) VK_ONE8_GO(PK_NONE);
+                else if (pk == PK_F64_VEC) VK_ONE8_GO(PK_F64_VEC);
+                else VK_ONE8_GO(PK_I64_VEC);
+#undef VK_ONE8_GO
+                VK_CHECK_LAUNCH("agg_onegroup8_kernel");
+                continue;
             }
             agg_onegroup_kernel<<<grid, 256, 0, s>>>(op);
             VK_CHECK_LAUNCH("agg_onegroup_kernel");
