@@ -267,6 +267,19 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
 int vk_take(const VkColumn* col, const int64_t* indices, int64_t n_indices, void* out,
             uint8_t* out_valid_bytes, VkStream stream);
 
+/* ORDER BY key <order> LIMIT k without the full sort (SliceOperator below SortOperator,
+ * vinum/core/algebra.py:204-247 + vinum/planner/planner.py:478-501): an MSD radix select over
+ * the key's order-preserving code finds the byte prefix that holds the k-th row, then the ids of
+ * every row at or before that prefix are written to out_rows (a superset of the first k rows of
+ * the stable sort, in no particular order; the caller sorts just these).  *out_count (HOST) is
+ * their number, or -1 when the select does not pay (k > n_rows / 8, an integer key with a
+ * validity bitmap, or more than max_candidates candidates) and the caller should sort
+ * everything.  Reads the key column once per prefix byte examined (at most 8 times) plus once to
+ * collect; synchronises `stream`.  scratch: vk_topk_scratch_bytes() device bytes. */
+uint64_t vk_topk_scratch_bytes(void);
+int vk_topk_candidates(const VkColumn* key, int32_t order, int64_t n_rows, int64_t k, int64_t max_candidates,
+                       int64_t* out_rows, int64_t* out_count, void* scratch, VkStream stream);
+
 #ifdef __cplusplus
 }
 #endif

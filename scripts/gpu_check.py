@@ -397,8 +397,28 @@ def s_onegroup():
     return res
 
 
+@section("topk")
+def s_topk():
+    """ORDER BY f3 DESC LIMIT k at C4 size: radix select + sort of the candidates vs the full sort."""
+    st = vb.default_stream()
+    res = {}
+    n = 100_000_000
+    f3 = datagen.device_column("f3", 0, n, stream=st)
+    full = ops.sort_indices([f3], [L.DESC], st)
+    for k in (10, 1000, 100_000):
+        top = ops.sort_top([f3], [L.DESC], k, st)
+        res[f"k{k}_parity"] = bool(np.array_equal(top.to_numpy(st), full.slice(0, k).to_numpy(st)))
+        cand = ops.topk_candidates(f3, L.DESC, k, st)
+        res[f"k{k}_candidates"] = None if cand is None else cand.length
+        best, med = timed(lambda: ops.sort_top([f3], [L.DESC], k, st), st, reps=3, warm=1)
+        res[f"k{k}_ms"] = best
+    best, med = timed(lambda: ops.sort_indices([f3], [L.DESC], st), st, reps=3, warm=1)
+    res["full_sort_ms"] = best
+    return res
+
+
 SECTIONS = {f.__name__: f for f in [s_datagen, s_filter, s_agg_parity, s_agg_highcard, s_agg_bench, s_sort, s_arith,
-                                    s_onegroup]}
+                                    s_onegroup, s_topk]}
 
 if __name__ == "__main__":
     lib.vk_set_device(0)

@@ -46,3 +46,7 @@ done
 export VINUM_B200_ONEGROUP_FAST=4
 TAILN=3 run pytest_onegroup_fast4 900 python -m pytest tests -m gpu -x -q -k "onegroup or one_group or no_group or nogroup or sql_matches or gtest"
 unset VINUM_B200_ONEGROUP_FAST
+# device top-k (vk_topk_candidates, ops.sort_top; engine opt-in VINUM_B200_TOPK=1) and the rest of
+# the code that has never run
+VINUM_B200_EXPERIMENTAL=1 TAILN=5 run pytest_experimental 900 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q
+TAILN=2 run topk 300 python -u scripts/gpu_check.py topk

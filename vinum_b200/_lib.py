@@ -182,6 +182,8 @@ SIGNATURES = {
     "vk_sort_scratch_bytes": (_u64, [_i64]),
     "vk_sort_indices": (_int, [C.POINTER(VkColumn), C.POINTER(C.c_int32), _int, _i64, _p, _p, _p]),
     "vk_take": (_int, [C.POINTER(VkColumn), _p, _i64, _p, _p, _p]),
+    "vk_topk_scratch_bytes": (_u64, []),
+    "vk_topk_candidates": (_int, [C.POINTER(VkColumn), C.c_int32, _i64, _i64, _i64, _p, C.POINTER(_i64), _p, _p]),
 }
 
 _STATUS_FUNCS = set()

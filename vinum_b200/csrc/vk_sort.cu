@@ -398,6 +398,80 @@ __global__ void __launch_bounds__(256) take8_kernel(const uint64_t* __restrict__
     }
 }
 
+// ------------------------------------------------------------------ top-k ----
+// MSD radix select over sort_code(): level l histograms byte (7 - l) of the codes whose higher
+// bytes equal `prefix`; the host walks the 256 counts to the bucket that holds the k-th row.
+struct TopkParams {
+    Col col;
+    int desc;
+    int64_t n;
+    int level;                 // 0..7
+    uint64_t prefix;           // the `level` bytes already fixed (right-aligned)
+    unsigned long long* hist;  // [256]
+};
+__global__ void __launch_bounds__(256) topk_hist_kernel(const __grid_constant__ TopkParams p) {
+    __shared__ uint32_t s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const int shift = 56 - 8 * p.level;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t iters = (p.n + stride - 1) / stride;  // uniform trip count: convergent votes
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = it * stride + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+        bool hit = false;
+        uint32_t digit = 0;
+        if (i < p.n) {
+            bool is_null;
+            const uint64_t code = sort_code(p.col, i, p.desc, &is_null);
+            hit = p.level == 0 || (code >> (shift + 8)) == p.prefix;
+            digit = (uint32_t) (code >> shift) & 0xffu;
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, hit);
+        if (!active) continue;
+        const int leader = __ffs(active) - 1;
+        const uint32_t first = __shfl_sync(0xffffffffu, digit, leader);
+        if (__all_sync(0xffffffffu, !hit || digit == first)) {  // one bucket per warp: the common case high up
+            if ((threadIdx.x & 31) == leader) atomicAdd(&s_h[first], (uint32_t) __popc(active));
+        } else if (hit) {
+            atomicAdd(&s_h[digit], 1u);
+        }
+    }
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(p.hist + threadIdx.x, (unsigned long long) s_h[threadIdx.x]);
+}
+
+struct TopkCollectParams {
+    Col col;
+    int desc;
+    int64_t n;
+    int shift;                     // candidates: (code >> shift) <= bound
+    uint64_t bound;
+    int64_t* out;
+    unsigned long long* counter;
+    unsigned long long capacity;
+};
+__global__ void __launch_bounds__(256) topk_collect_kernel(const __grid_constant__ TopkCollectParams p) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t iters = (p.n + stride - 1) / stride;
+    const unsigned lt = lanemask_lt();
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = it * stride + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+        bool hit = false;
+        if (i < p.n) {
+            bool is_null;
+            hit = (sort_code(p.col, i, p.desc, &is_null) >> p.shift) <= p.bound;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (!m) continue;
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if ((threadIdx.x & 31) == leader) base = atomicAdd(p.counter, (unsigned long long) __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        const unsigned long long pos = base + __popc(m & lt);
+        if (hit && pos < p.capacity) p.out[pos] = i;
+    }
+}
+
 static unsigned grid_rows(int64_t n, int per_sm = 8) {
     int64_t need = (n + 255) / 256, cap = (int64_t) sm_count() * per_sm;
     if (need < 1) need = 1;
@@ -540,6 +614,77 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
     }
     sort_widen_kernel<<<grid_rows(n_rows), 256, 0, s>>>(sc.idx[cur], n_rows, out_indices);
     VK_CHECK_LAUNCH("sort_widen_kernel");
+    return VK_OK;
+}
+
+uint64_t vk_topk_scratch_bytes(void) { return 257 * sizeof(unsigned long long); }
+
+int vk_topk_candidates(const VkColumn* key, int32_t order, int64_t n_rows, int64_t k, int64_t max_candidates,
+                       int64_t* out_rows, int64_t* out_count, void* scratch, VkStream stream) {
+    VK_REQUIRE(key && out_count, "vk_topk_candidates: NULL argument");
+    VK_REQUIRE(n_rows >= 0 && k >= 0 && max_candidates >= 0, "vk_topk_candidates: negative size");
+    VK_REQUIRE(dtype_valid(key->dtype), "vk_topk_candidates: bad key dtype");
+    VK_REQUIRE(key->dtype != VK_BOOL8, "Sorting by boolean column is not supported yet.");  // algebra.py:191-201
+    VK_REQUIRE(key->length == n_rows, "vk_topk_candidates: key length != n_rows");
+    VK_REQUIRE(order == VK_ASC || order == VK_DESC, "vk_topk_candidates: bad sort order");
+    *out_count = -1;
+    // integer NULLs sort last outside the 64-bit code (bit 31 of the row id in the full sort)
+    if (key->validity != nullptr && !dtype_is_float(key->dtype)) return VK_OK;
+    if (k < 1 || k > n_rows / 8 || n_rows >= (int64_t) 0x7fffffffLL) return VK_OK;
+    VK_REQUIRE(out_rows && scratch, "vk_topk_candidates: NULL buffer");
+    cudaStream_t s = (cudaStream_t) stream;
+    unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(scratch);
+    unsigned long long* d_counter = d_hist + 256;
+    unsigned long long h[256];
+    TopkParams tp{};
+    tp.col = make_col(*key);
+    tp.desc = order == VK_DESC;
+    tp.n = n_rows;
+    tp.hist = d_hist;
+    uint64_t prefix = 0;
+    int64_t below = 0, krem = k, eq = 0;
+    int level = 0;
+    const int64_t enough = k * 4 > (1 << 16) ? k * 4 : (1 << 16);  // stop refining below this many candidates
+    for (;; ++level) {
+        tp.level = level;
+        tp.prefix = prefix;
+        VK_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), s));
+        topk_hist_kernel<<<grid_rows(n_rows, 8), 256, 0, s>>>(tp);
+        VK_CHECK_LAUNCH("topk_hist_kernel");
+        VK_CUDA(cudaMemcpyAsync(h, d_hist, sizeof(h), cudaMemcpyDeviceToHost, s));
+        VK_CUDA(cudaStreamSynchronize(s));
+        int64_t cum = 0;
+        int b = 0;
+        for (; b < 256; ++b) {
+            if (cum + (int64_t) h[b] >= krem) break;
+            cum += (int64_t) h[b];
+        }
+        if (b == 256) return fail(VK_ERR_STATE, "vk_topk_candidates: histogram does not cover k");
+        below += cum;
+        krem -= cum;
+        eq = (int64_t) h[b];
+        prefix = (prefix << 8) | (uint64_t) b;
+        if (level == 7 || below + eq <= enough) break;
+    }
+    const int64_t count = below + eq;
+    if (count > max_candidates) return VK_OK;  // too many ties at the cut: the full sort is the better plan
+    TopkCollectParams cp{};
+    cp.col = tp.col;
+    cp.desc = tp.desc;
+    cp.n = n_rows;
+    cp.shift = 56 - 8 * level;
+    cp.bound = prefix;
+    cp.out = out_rows;
+    cp.counter = d_counter;
+    cp.capacity = (unsigned long long) max_candidates;
+    VK_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), s));
+    topk_collect_kernel<<<grid_rows(n_rows, 8), 256, 0, s>>>(cp);
+    VK_CHECK_LAUNCH("topk_collect_kernel");
+    unsigned long long written = 0;
+    VK_CUDA(cudaMemcpyAsync(&written, d_counter, sizeof(written), cudaMemcpyDeviceToHost, s));
+    VK_CUDA(cudaStreamSynchronize(s));
+    if ((int64_t) written != count) return fail(VK_ERR_STATE, "vk_topk_candidates: collected rows != histogram count");
+    *out_count = count;
     return VK_OK;
 }
 

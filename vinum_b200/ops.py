@@ -301,6 +301,39 @@ def sort_indices(keys: Sequence[DeviceColumn], orders: Sequence[int], stream: Op
     return out
 
 
+def topk_candidates(key: DeviceColumn, order: int, k: int, stream: Optional[Stream] = None) -> Optional[DeviceColumn]:
+    """Row ids (int64, unordered) of a superset of the first `k` rows of `ORDER BY key <order>`, or
+    None when selecting does not pay and the caller should sort every row (vk_topk_candidates)."""
+    st = stream or default_stream()
+    n = key.length
+    cap = max(1 << 16, 4 * k, n // 4)
+    out = DeviceColumn.empty(cap, L.I64, pa.int64(), st)
+    scratch = DeviceBuffer(lib.vk_topk_scratch_bytes(), st)
+    count = C.c_int64(-1)
+    v = key.vk()
+    lib.vk_topk_candidates(C.byref(v), int(order), n, int(k), cap, C.c_void_p(out.data_ptr), C.byref(count),
+                           C.c_void_p(scratch.ptr), st.ptr)
+    if count.value < 0:
+        return None
+    return out.slice(0, count.value)
+
+
+def sort_top(keys: Sequence[DeviceColumn], orders: Sequence[int], k: int, stream: Optional[Stream] = None) -> DeviceColumn:
+    """The first `k` entries of sort_indices(keys, orders) -- `ORDER BY ... LIMIT k` -- through a
+    radix select on the first key when that beats sorting every row.  Candidates are put back
+    into row order before they are sorted, so ties keep their input order exactly as in the
+    full stable sort."""
+    st = stream or default_stream()
+    n = keys[0].length
+    k = min(k, n)
+    cand = topk_candidates(keys[0], orders[0], k, st) if 0 < k < n else None
+    if cand is None:
+        return sort_indices(keys, orders, st).slice(0, k)
+    ids = take(cand, sort_indices([cand], [L.ASC], st), st)
+    perm = sort_indices([take(key, ids, st) for key in keys], orders, st).slice(0, k)
+    return take(ids, perm, st)
+
+
 def sort_batch(batch: DeviceBatch, key_names: Sequence[str], orders: Sequence[int],
                stream: Optional[Stream] = None) -> DeviceBatch:
     """SortIndices + Take of every column (Sort::Sorted, sort.cpp:15-63)."""

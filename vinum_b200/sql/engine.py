@@ -20,6 +20,7 @@ host here as well (functions.py in this package).
 """
 from __future__ import annotations
 
+import os
 import re
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -35,6 +36,8 @@ from .ast import (NUMPY_AGG_MAPPING, Column, Expression, Literal, Node, Op, Quer
                   contains_aggregate, is_aggregate_call, walk)
 from .functions import call_host_function
 from .parser import ParserError, parse_sql
+
+_TOPK_MIN_ROWS = 1 << 20   # below this a full radix sort costs less than the select's round trips
 
 
 class OperatorError(Exception):
@@ -425,10 +428,15 @@ class Engine:
             dev_orders.append(L.DESC if o == SortOrder.DESC else L.ASC)
         if not dev_keys or frame.n == 0:
             return frame
-        idx = ops.sort_indices(dev_keys, dev_orders, self.st)
         m = frame.n if top is None else min(top, frame.n)
-        if m < frame.n:
-            idx = idx.slice(0, m)
+        if 0 < m < frame.n and frame.n >= _TOPK_MIN_ROWS and os.environ.get("VINUM_B200_TOPK"):
+            # opt-in until measured on the GPU: radix select of the LIMIT's rows, then a sort of those only
+            idx = ops.sort_top(dev_keys, dev_orders, m, self.st)
+            self.stats["sort_topk"] = True
+        else:
+            idx = ops.sort_indices(dev_keys, dev_orders, self.st)
+            if m < frame.n:
+                idx = idx.slice(0, m)
         out = Frame(m)
         hidx = None
         for name, v in frame.cols.items():
