@@ -4,12 +4,13 @@
 #   gpurun --timeout 1500 -- 'bash scripts/r02_variants.sh'
 source scripts/gpu_round.sh true
 rm -f gpurun_out/round.log
-# filter_kernel: bit 0 = 4096-row tiles, bits 2-3 = batched scatter (4: single buffer, 8: double)
-for c in 0 4 8 5 9; do
+# filter_kernel: bit 0 = 4096-row tiles, bits 2-3 = batched scatter (4: single buffer, 8: double);
+# filter_tma_kernel: 16 = TMA-staged tiles with 4 column buffers (2 CTAs/SM), 32 = 2 buffers (4 CTAs/SM)
+for c in 0 4 8 5 9 16 32; do
   export VINUM_B200_FILTER_CFG=$c
   TAILN=2 run filter_cfg$c 300 python -u scripts/gpu_check.py filter
 done
-for c in 4 8; do
+for c in 4 8 16 32; do
   export VINUM_B200_FILTER_CFG=$c
   TAILN=3 run pytest_filter_cfg$c 900 python -m pytest tests -m gpu -x -q -k "filter or where or scale or sql_matches"
 done

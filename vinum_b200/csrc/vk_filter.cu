@@ -493,6 +493,219 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
     }
 }
 
+// ---- TMA-staged variant ---------------------------------------------------------------------
+// The tile's slice of the predicate column and of up to CB payload columns is moved into shared
+// memory by the TMA unit (cp.async.bulk, one 16 KB copy per column issued by one thread, each
+// signalling its own mbarrier): nothing is staged in registers, every byte of the tile is in
+// flight at once, and the copies land while the predicate is evaluated and the look-back runs.
+// The scatter then reads shared memory (lane-contiguous 16-byte reads, conflict free).  Columns
+// beyond CB reuse the buffers round by round.  Same eligibility as BATCH; the ragged last tile is
+// staged with ordinary loads.  Opt-in (VINUM_B200_FILTER_CFG 16: CB = 4, 32: CB = 2), unmeasured.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int PK, int ITERS, int CB>
+__global__ void __launch_bounds__(FT_THREADS) filter_tma_kernel(const __grid_constant__ FilterParams p) {
+    static_assert(PK == PK_MASK || PK == PK_F64_VEC || PK == PK_I64_VEC, "predicates that stage as one contiguous slice");
+    constexpr int TILE = FT_THREADS * 2 * ITERS;
+    constexpr int NCNT = ITERS * (FT_THREADS / 32);
+    constexpr int PER_LANE = NCNT / 32;
+    constexpr uint32_t COL_BYTES = TILE * 8;
+    constexpr uint32_t PRED_BYTES = PK == PK_MASK ? TILE : TILE * 8;
+    extern __shared__ __align__(128) uint8_t ft_smem[];   // [predicate slice | CB column slices]
+    __shared__ __align__(8) uint64_t s_bar[1 + CB];
+    __shared__ int64_t s_tile;
+    __shared__ uint32_t s_cnt[NCNT];
+    __shared__ int64_t s_excl;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t a_pred = (uint32_t) __cvta_generic_to_shared(ft_smem);
+    const uint32_t a_col0 = a_pred + COL_BYTES;
+    const uint32_t a_bar = (uint32_t) __cvta_generic_to_shared(s_bar);
+    if (tid == 0) {
+        s_tile = (int64_t) atomicAdd(p.ticket, 1ULL);
+        for (int b = 0; b <= CB; ++b) mbar_init(a_bar + 8 * b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t base = tile * TILE;
+    const int rows = (int) (p.n - base < TILE ? p.n - base : TILE);
+    const bool full = rows == TILE;
+    const uint8_t* pred_src = PK == PK_MASK ? p.pred.mask + base : p.pred.col.data + base * 8;
+
+    // stage round g (columns g*CB ...): TMA for complete tiles, plain loads for the ragged last one
+    auto stage_cols = [&](int g) {
+        const int c0 = g * CB;
+        if (full) {
+            if (tid == 0) {
+                for (int k = 0; k < CB && c0 + k < p.n_cols; ++k) {
+                    mbar_arrive_expect_tx(a_bar + 8 * (1 + k), COL_BYTES);
+                    tma_load_1d(a_col0 + k * COL_BYTES, p.cols[c0 + k].data + base * 8, COL_BYTES, a_bar + 8 * (1 + k));
+                }
+            }
+        } else {
+            for (int k = 0; k < CB && c0 + k < p.n_cols; ++k) {
+                const uint64_t* src = reinterpret_cast<const uint64_t*>(p.cols[c0 + k].data) + base;
+                uint64_t* dst = reinterpret_cast<uint64_t*>(ft_smem + COL_BYTES + (size_t) k * COL_BYTES);
+                for (int i = tid; i < rows; i += FT_THREADS) dst[i] = src[i];
+            }
+        }
+    };
+    if (full) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(a_bar, PRED_BYTES);
+            tma_load_1d(a_pred, pred_src, PRED_BYTES, a_bar);
+        }
+    } else {
+        if constexpr (PK == PK_MASK) {
+            for (int i = tid; i < rows; i += FT_THREADS) ft_smem[i] = pred_src[i];
+        } else {
+            for (int i = tid; i < rows; i += FT_THREADS)
+                reinterpret_cast<uint64_t*>(ft_smem)[i] = reinterpret_cast<const uint64_t*>(pred_src)[i];
+        }
+    }
+    stage_cols(0);
+    if (full) {
+        while (!mbar_try_wait(a_bar, 0)) {}
+    } else {
+        __syncthreads();
+    }
+
+    // ---- phase 1: predicate from shared memory ----
+    uint32_t flags = 0;
+    uint32_t lane_off[ITERS];
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int e = it * (FT_THREADS * 2) + tid * 2;   // row of the tile
+        bool f0 = false, f1 = false;
+        if constexpr (PK == PK_MASK) {
+            uint32_t m;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(m) : "r"(a_pred + e) : "memory");
+            f0 = (m & 0xffu) != 0;
+            f1 = (m >> 8) != 0;
+        } else {
+            uint4 q;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a_pred + e * 8) : "memory");
+            const uint64_t a = ((uint64_t) q.y << 32) | q.x, b = ((uint64_t) q.w << 32) | q.z;
+            if constexpr (PK == PK_F64_VEC) {
+                const double c = __longlong_as_double((long long) p.pred.scalar.bits);
+                f0 = apply_cmp(p.pred.op, __longlong_as_double((long long) a), c);
+                f1 = apply_cmp(p.pred.op, __longlong_as_double((long long) b), c);
+            } else {
+                f0 = apply_cmp(p.pred.op, (int64_t) a, (int64_t) p.pred.scalar.bits);
+                f1 = apply_cmp(p.pred.op, (int64_t) b, (int64_t) p.pred.scalar.bits);
+            }
+        }
+        f0 = f0 && e < rows;
+        f1 = f1 && e + 1 < rows;
+        const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+        lane_off[it] = __popc(b0 & lt) + __popc(b1 & lt);
+        flags |= ((uint32_t) f0 << (2 * it)) | ((uint32_t) f1 << (2 * it + 1));
+        if (lane == 0) s_cnt[it * (FT_THREADS / 32) + warp] = __popc(b0) + __popc(b1);
+    }
+    __syncthreads();
+
+    // ---- block scan of the (iter, warp) counts + decoupled look-back (warp 0), as in filter_kernel ----
+    if (warp == 0) {
+        uint32_t c[PER_LANE], mine = 0;
+#pragma unroll
+        for (int e = 0; e < PER_LANE; ++e) {
+            c[e] = s_cnt[lane * PER_LANE + e];
+            mine += c[e];
+        }
+        uint32_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        uint32_t run = inc - mine;
+#pragma unroll
+        for (int e = 0; e < PER_LANE; ++e) {
+            s_cnt[lane * PER_LANE + e] = run;
+            run += c[e];
+        }
+        const uint64_t total = __shfl_sync(0xffffffffu, inc, 31);
+        uint64_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_status(p.status, ST_PREFIX | total);
+        } else {
+            if (lane == 0) st_status(p.status + tile, ST_AGG | total);
+            int64_t look = tile - 1;
+            while (true) {
+                const int64_t idx = look - lane;
+                unsigned long long st = ST_PREFIX;  // virtual tile -1: prefix 0
+                if (idx >= 0) {
+                    do { st = ld_status(p.status + idx); } while ((st >> ST_FLAG_SHIFT) == 0);
+                }
+                const unsigned is_prefix = __ballot_sync(0xffffffffu, (st >> ST_FLAG_SHIFT) == 2 || idx < 0);
+                const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
+                uint64_t v = (lane <= first) ? (st & ST_VALUE_MASK) : 0;
+                if (idx < 0) v = 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (is_prefix) break;
+                look -= 32;
+            }
+            if (lane == 0) st_status(p.status + tile, ST_PREFIX | (excl + total));
+        }
+        if (lane == 0) {
+            s_excl = (int64_t) excl;
+            if (tile == p.num_tiles - 1) *p.out_rows = (int64_t) (excl + total);
+        }
+    }
+    __syncthreads();
+    const int64_t tile_excl = s_excl;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) lane_off[it] += s_cnt[it * (FT_THREADS / 32) + warp];
+
+    // ---- phase 2: scatter from shared memory, CB columns per round ----
+    const int rounds = (p.n_cols + CB - 1) / CB;
+    for (int g = 0; g < rounds; ++g) {
+        for (int k = 0; k < CB && g * CB + k < p.n_cols; ++k) {
+            if (full) {
+                while (!mbar_try_wait(a_bar + 8 * (1 + k), (uint32_t) (g & 1))) {}
+            }
+            uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[g * CB + k]);
+            const uint32_t a_col = a_col0 + k * COL_BYTES;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const uint32_t f = (flags >> (2 * it)) & 3u;
+                if (f == 0) continue;
+                const int e = it * (FT_THREADS * 2) + tid * 2;
+                uint4 q;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a_col + e * 8) : "memory");
+                int64_t pos = tile_excl + lane_off[it];
+                if (f & 1) o[pos++] = ((uint64_t) q.y << 32) | q.x;
+                if (f & 2) o[pos] = ((uint64_t) q.w << 32) | q.z;
+            }
+        }
+        if (g + 1 < rounds) {
+            __syncthreads();   // every thread has read this round's slices
+            if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
+            stage_cols(g + 1);
+            if (!full) __syncthreads();
+        }
+    }
+}
+
 static int grid_for(int64_t work_items, int per_sm = 8) {
     int64_t need = (work_items + 255) / 256;
     int64_t cap = (int64_t) sm_count() * per_sm;
@@ -695,7 +908,7 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
     static int cfg = -1;
     if (cfg < 0) { const char* v = getenv("VINUM_B200_FILTER_CFG"); cfg = v ? atoi(v) : 0; }
     // bit 0: 4096-row tiles; bit 1: keep the predicate column; bits 2-3: batched scatter (1 or 2, see
-    // filter_kernel) when every column of the pass qualifies
+    // filter_kernel) when every column of the pass qualifies; 16 / 32: TMA-staged tiles (filter_tma_kernel)
     const int iters = (cfg & 1) ? 8 : 4;
     const int batch_cfg = (cfg >> 2) & 3;
     const bool keep = (cfg & 2) != 0 && batch_cfg == 0;
@@ -713,12 +926,14 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
             p.out_data[c] = out_data[c0 + c];
             p.out_valid[c] = (cols[c0 + c].validity && out_valid_bytes) ? out_valid_bytes[c0 + c] : nullptr;
         }
-        int batch = batch_cfg > 2 ? 2 : batch_cfg;
-        for (int c = 0; c < p.n_cols && batch; ++c)
+        // every column 8 bytes wide, 16-byte aligned, without a validity bitmap (BATCH and TMA variants)
+        bool batch_ok = true;
+        for (int c = 0; c < p.n_cols && batch_ok; ++c)
             if (dtype_size(p.cols[c].dtype) != 8 || p.out_valid[c] != nullptr ||
                 ((reinterpret_cast<uintptr_t>(p.cols[c].data) | reinterpret_cast<uintptr_t>(p.out_data[c])) & 7) != 0 ||
                 (reinterpret_cast<uintptr_t>(p.cols[c].data) & 15) != 0)
-                batch = 0;
+                batch_ok = false;
+        const int batch = batch_ok ? (batch_cfg > 2 ? 2 : batch_cfg) : 0;
         p.out_rows = out_rows;
         p.ticket = reinterpret_cast<unsigned long long*>(scratch);
         p.status = p.ticket + 1;
@@ -729,6 +944,29 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
             p.pf = pf;
         }
         VK_CUDA(cudaMemsetAsync(scratch, 0, vk_filter_scratch_bytes(n_rows), s));
+        // TMA-staged variant (cfg 16 / 32): same column eligibility as the batched scatter
+        const int tma_cb = (cfg & 16) ? 4 : ((cfg & 32) ? 2 : 0);
+        if (tma_cb && batch_ok && iters == 4 && (pk == PK_F64_VEC || pk == PK_I64_VEC ||
+            (pk == PK_MASK && (reinterpret_cast<uintptr_t>(p.pred.mask) & 15) == 0))) {
+            const size_t smem = (size_t) FT_THREADS * 2 * 4 * 8 * (1 + tma_cb);
+#define VK_FILTER_TMA_GO(PK)                                                                          \
+            do {                                                                                          \
+                if (tma_cb == 4) {                                                                        \
+                    VK_CUDA(cudaFuncSetAttribute(filter_tma_kernel<PK, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+                    filter_tma_kernel<PK, 4, 4><<<(unsigned) tiles, FT_THREADS, smem, s>>>(p);            \
+                } else {                                                                                  \
+                    VK_CUDA(cudaFuncSetAttribute(filter_tma_kernel<PK, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+                    filter_tma_kernel<PK, 4, 2><<<(unsigned) tiles, FT_THREADS, smem, s>>>(p);            \
+                }                                                                                         \
+            } while (0)
+            if (pk == PK_MASK) VK_FILTER_TMA_GO(PK_MASK);
+            else if (pk == PK_F64_VEC) VK_FILTER_TMA_GO(PK_F64_VEC);
+            else VK_FILTER_TMA_GO(PK_I64_VEC);
+#undef VK_FILTER_TMA_GO
+            VK_CHECK_LAUNCH("filter_tma_kernel");
+            c0 += p.n_cols;
+            continue;
+        }
 #define VK_FILTER_GO(PK)                                                                              \
         do {                                                                                              \
             if (batch) {                                                                                  \
