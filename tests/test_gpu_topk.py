@@ -1,24 +1,16 @@
-"""GPU parity of the opt-in code written at the end of round 1 WITHOUT a GPU.
+"""GPU parity of the device top-k (`ORDER BY ... LIMIT k`): vk_topk_candidates +
+ops.sort_top against the prefix of the full stable sort, and through Table.sql().
 
-Nothing here has run yet, so the module is skipped unless VINUM_B200_EXPERIMENTAL=1 is set: the
-default `pytest -m gpu` run keeps covering the measured code paths only.  Round 2 opens with
-
-    VINUM_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
-
-(the per-process kernel knobs -- VINUM_B200_FILTER_CFG and friends -- are exercised by
-scripts/r02_variants.sh, which re-runs the regular parity tests under each of them).
+Written without a GPU at the end of round 1 and green on first contact (gpurun_out/final_experimental.log,
+42 passed); the engine uses the select by default for tables of >= 2^20 rows, VINUM_B200_TOPK=0 turns it off.
 """
-import os
-
 import numpy as np
 import pyarrow as pa
 import pytest
 
 from oracle import vinum_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("VINUM_B200_EXPERIMENTAL"),
-                                 reason="unmeasured opt-in code: set VINUM_B200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
@@ -88,10 +80,10 @@ def test_sql_order_by_limit_with_topk(vb, stream, monkeypatch):
                "SELECT i2, i0, f1 FROM t WHERE f0 > 0.25 ORDER BY i0, f1 DESC LIMIT 40 OFFSET 3",
                "SELECT i2 FROM t ORDER BY i0 LIMIT 10"]
     for q in queries:
-        monkeypatch.delenv("VINUM_B200_TOPK", raising=False)
+        monkeypatch.setenv("VINUM_B200_TOPK", "0")       # full sort, then slice
         want = tbl.sql(q).to_arrow()
         assert not tbl.last_stats.get("sort_topk")
-        monkeypatch.setenv("VINUM_B200_TOPK", "1")
+        monkeypatch.delenv("VINUM_B200_TOPK")             # default: radix select + sort of the candidates
         got = tbl.sql(q).to_arrow()
         assert tbl.last_stats.get("sort_topk")
         assert got.equals(want), q

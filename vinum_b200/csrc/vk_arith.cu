@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) arith_kernel(ArithParams p, int64_t n, vo
 // 8-byte operands and result in the compute class's own representation (int64 / uint64 / float64
 // columns without the NaN view, or scalars): U lane-contiguous row pairs per thread, 16-byte loads
 // issued together, 16-byte stores.  arith_kernel goes through the per-row dtype dispatch with one
-// 8-byte load per operand in flight.  Opt-in (VINUM_B200_ARITH_FAST=U) until measured.
+// 8-byte load per operand in flight.  Measured at 1e8 rows (profiles/r01_variants.md): f64 a + b 0.396 ms =
+// 6.06 TB/s (0.93 of the peak) against 0.500 ms; VINUM_B200_ARITH_FAST=0 selects arith_kernel.
 template <int CC, int U>
 __global__ void __launch_bounds__(256) arith8_kernel(ArithParams p, int64_t n, void* __restrict__ out) {
     using T = typename CCT<CC>::type;
@@ -224,8 +225,8 @@ extern "C" int vk_arith(int op, const VkColumn* lhs_col, const VkScalar* lhs_sca
     int64_t need = (n_rows + 255) / 256, cap = (int64_t) sm_count() * 8;
     int g = (int) (need < cap ? need : cap);
     cudaStream_t s = (cudaStream_t) stream;
-    static int fast = -1;  // row pairs per thread of arith8_kernel (0: off)
-    if (fast < 0) { const char* v = getenv("VINUM_B200_ARITH_FAST"); fast = v ? atoi(v) : 0; }
+    static int fast = -1;  // row pairs per thread of arith8_kernel (0: off; 4 measured: 6.06 vs 4.80 TB/s on f64 a + b)
+    if (fast < 0) { const char* v = getenv("VINUM_B200_ARITH_FAST"); fast = v ? atoi(v) : 4; }
     auto raw8 = [&](const Operand& o) {
         if (!o.is_col) return true;
         const bool same_class = cc == CC_F64 ? o.col.dtype == VK_F64 : (o.col.dtype == VK_I64 || o.col.dtype == VK_U64);

@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(256) compare_kernel(CmpParams p, int64_t n, ui
 // Plain 8-byte column(s) compared in their own domain (no validity, no NaN view, 16-byte aligned):
 // U lane-contiguous row pairs per thread, the 16-byte loads of a round issued together, two mask
 // bytes stored per pair.  compare_kernel dispatches on dtype and mode row by row, which leaves one
-// 8-byte load in flight per thread (SASS) -- 3.5 TB/s at 1e8 rows.  Opt-in (VINUM_B200_CMP_FAST=U).
+// 8-byte load in flight per thread (SASS) -- 3.58 TB/s at 1e8 rows; this kernel with U = 2: 4.08 TB/s, with
+// U = 4: 2.91 TB/s (profiles/r01_variants.md).  VINUM_B200_CMP_FAST=0 selects compare_kernel.
 template <int DOM, int U>
 __global__ void __launch_bounds__(256) compare8_kernel(CmpParams p, int64_t n, uint8_t* __restrict__ out) {
     using T = typename DomT<DOM>::type;
@@ -724,8 +725,8 @@ static int launch_compare(const CmpParams& p, int64_t n, uint8_t* out, VkStream 
     VK_REQUIRE(out, "compare: out_mask is NULL");
     int g = grid_for((n + 3) / 4);
     cudaStream_t s = (cudaStream_t) stream;
-    static int fast = -1;  // row pairs per thread of compare8_kernel (0: off)
-    if (fast < 0) { const char* v = getenv("VINUM_B200_CMP_FAST"); fast = v ? atoi(v) : 0; }
+    static int fast = -1;  // row pairs per thread of compare8_kernel (0: off; 2 measured best, 4 is slower than off)
+    if (fast < 0) { const char* v = getenv("VINUM_B200_CMP_FAST"); fast = v ? atoi(v) : 2; }
     auto plain8 = [&](const Col& c) {
         const int want = p.domain == DOM_F64 ? VK_F64 : (p.domain == DOM_I64 ? VK_I64 : (p.domain == DOM_U64 ? VK_U64 : -1));
         return c.dtype == want && c.validity == nullptr && !c.nan_nulls && (reinterpret_cast<uintptr_t>(c.data) & 15) == 0;

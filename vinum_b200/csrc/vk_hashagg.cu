@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(256) agg_onegroup_kernel(const __grid_constant
 // The common un-grouped case -- no predicate or a vectorisable `column <op> literal` one, value
 // column 8 bytes wide without a validity bitmap -- with U lane-contiguous row pairs per thread and
 // the 16-byte loads of a round issued together (agg_onegroup_kernel has one 8-byte load per operand
-// in flight per thread).  Opt-in (VINUM_B200_ONEGROUP_FAST=U) until measured.
+// in flight per thread).  Measured at 1e8 rows, COUNT(*) + SUM(f64) WHERE f64 > c (two launches, 24 B/row):
+// 0.676 ms = 3.55 TB/s against 1.305 ms (profiles/r01_variants.md); VINUM_B200_ONEGROUP_FAST=0 selects
+// agg_onegroup_kernel.
 template <int PK, int U>
 __global__ void __launch_bounds__(256) agg_onegroup8_kernel(const __grid_constant__ OneParams p) {
     static_assert(PK == PK_NONE || PK == PK_F64_VEC || PK == PK_I64_VEC, "vectorisable predicates only");
@@ -1115,8 +1117,8 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 op.spec = a->specs[f];
                 op.val = make_col(values[f]);
             }
-            static int fast1 = -1;  // row pairs per thread of agg_onegroup8_kernel (0: off)
-            if (fast1 < 0) { const char* v = getenv("VINUM_B200_ONEGROUP_FAST"); fast1 = v ? atoi(v) : 0; }
+            static int fast1 = -1;  // row pairs per thread of agg_onegroup8_kernel (0: off; 4 measured 1.93x faster)
+            if (fast1 < 0) { const char* v = getenv("VINUM_B200_ONEGROUP_FAST"); fast1 = v ? atoi(v) : 4; }
             bool raw8 = pk == PK_NONE || pk == PK_F64_VEC || pk == PK_I64_VEC;
             if (f >= 0 && op.spec.acc != ACC_COUNT) {
                 const int dt = op.val.dtype;

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const __grid_constant
 // thread per round: the U (gathered) loads are issued together, and the histogram work of a round
 // runs while the next round's loads are in flight.  sort_prepare_kernel has one load in flight per
 // thread at half occupancy (long scoreboard 32 %, profiles/r01_sort_prepare_ncu_full.md).
-// Opt-in (VINUM_B200_SORT_PREP=U) until measured.
+// Measured with U = 4: C4 8.26 ms against 8.61 (profiles/r01_variants.md); VINUM_B200_SORT_PREP=0 selects
+// sort_prepare_kernel.
 template <int U>
 __global__ void __launch_bounds__(256) sort_prepare8_kernel(const __grid_constant__ PrepParams p) {
     __shared__ uint32_t s_hist[8 * 256];
@@ -380,7 +381,8 @@ __global__ void __launch_bounds__(256) take_kernel(const __grid_constant__ TakeP
     }
 }
 
-// 8-byte elements, no validity: U independent gathers in flight per thread (opt-in, VINUM_B200_TAKE_U).
+// 8-byte elements, no validity: U independent gathers in flight per thread (opt-in, VINUM_B200_TAKE_U;
+// measured no faster than take_kernel -- 2.62 vs 2.64 ms at 1e8 rows -- so it stays off).
 template <int U>
 __global__ void __launch_bounds__(256) take8_kernel(const uint64_t* __restrict__ data, const int64_t* __restrict__ indices,
                                                     int64_t n, uint64_t* __restrict__ out) {
@@ -576,7 +578,7 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         pp.hist = sc.hist;
         VK_CUDA(cudaMemsetAsync(sc.hist, 0, 9 * 256 * 8, s));
         static int prep = -1;  // rows per thread per round of the 8-byte fast path (0: general kernel)
-        if (prep < 0) { const char* v = getenv("VINUM_B200_SORT_PREP"); prep = v ? atoi(v) : 0; }
+        if (prep < 0) { const char* v = getenv("VINUM_B200_SORT_PREP"); prep = v ? atoi(v) : 4; }
         const bool plain8 = keys[k].validity == nullptr && !keys[k].nulls_as_nan &&
                             (keys[k].dtype == VK_F64 || keys[k].dtype == VK_I64 || keys[k].dtype == VK_U64);
         if (prep >= 4 && plain8) sort_prepare8_kernel<4><<<grid_rows(n_rows, 8), 256, 0, s>>>(pp);

@@ -103,13 +103,13 @@ class Stream:
         return C.c_void_p(self.handle)
 
     def __del__(self):
-        if _shutting_down():
-            return
-        if getattr(self, "_owned", False) and getattr(self, "handle", 0):
-            try:
+        try:
+            if _shutting_down():
+                return
+            if getattr(self, "_owned", False) and getattr(self, "handle", 0):
                 L._lib.vk_stream_destroy(C.c_void_p(self.handle))
-            except Exception:
-                pass
+        except Exception:   # module globals are already gone at interpreter teardown
+            pass
             self.handle = 0
 
 
