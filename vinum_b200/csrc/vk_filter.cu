@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) bits_to_mask_kernel(const uint8_t* __rest
 // so an 8-byte column is read with one 16-byte load per lane and the rank of a row
 // inside its tile is (rows selected by lower (it, warp)) + (ballot rank).
 constexpr int FT_THREADS = 256;
-constexpr int FT_MIN_TILE = FT_THREADS * 2 * 4;  // smallest tile geometry (2048 rows): sizes the status array
+constexpr int FT_MIN_TILE = 128 * 2 * 2;  // smallest tile geometry (512 rows): sizes the status array
 constexpr int FT_MAX_COLS = 12;
 
 constexpr uint64_t ST_FLAG_SHIFT = 62;
@@ -224,12 +224,13 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 // also loads column c+1 before it stores column c.  The BATCH 0 scatter loop loads and stores one
 // row pair at a time (one load in flight per thread: SASS of round 1) and leaves the memory-level
 // parallelism to the 64 resident warps.
-template <int PK, int ITERS, bool KEEP, int BATCH = 0>
-__global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constant__ FilterParams p) {
+template <int PK, int ITERS, bool KEEP, int BATCH = 0, int THREADS = FT_THREADS>
+__global__ void __launch_bounds__(THREADS) filter_kernel(const __grid_constant__ FilterParams p) {
     static_assert(BATCH == 0 || !KEEP, "the batched scatter re-reads the predicate column");
-    constexpr int TILE = FT_THREADS * 2 * ITERS;
-    constexpr int NCNT = ITERS * (FT_THREADS / 32);   // (iter, warp) counts: 32 or 64
-    constexpr int PER_LANE = NCNT / 32;
+    constexpr int TILE = THREADS * 2 * ITERS;
+    constexpr int NCNT = ITERS * (THREADS / 32);   // (iter, warp) counts: 32 or 64 (8 or 16 for the small-tile variants)
+    constexpr int PER_LANE = NCNT >= 32 ? NCNT / 32 : 1;
+    static_assert(NCNT % 32 == 0 || NCNT < 32, "one or more whole counts per lane");
     __shared__ int64_t s_tile;
     __shared__ uint32_t s_cnt[NCNT];
     __shared__ int64_t s_excl;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
         uint32_t live = 0;  // bit r: row r of this thread exists
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
-            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
+            const int64_t r0 = base + it * (THREADS * 2) + tid * 2;
             pq[it] = make_uint4(0, 0, 0, 0);
             if (r0 + 1 < p.n) {
                 pq[it] = ldg_stream16(p.pred.col.data + r0 * 8);
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
     }
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-        int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
+        int64_t r0 = base + it * (THREADS * 2) + tid * 2;
         bool f0, f1;
         if constexpr (BATCH != 0 && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
             f0 = (pflags >> (2 * it)) & 1u;
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
         unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
         lane_off[it] = __popc(b0 & lt) + __popc(b1 & lt);
         flags |= ((uint32_t) f0 << (2 * it)) | ((uint32_t) f1 << (2 * it + 1));
-        if (lane == 0) s_cnt[it * (FT_THREADS / 32) + warp] = __popc(b0) + __popc(b1);
+        if (lane == 0) s_cnt[it * (THREADS / 32) + warp] = __popc(b0) + __popc(b1);
     }
     // (BATCH) a selected pair's 16 bytes of column c; flags are clear for rows past the end
     uint4 qa[BATCH ? ITERS : 1], qb[BATCH == 2 ? ITERS : 1];
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
         const uint8_t* d = p.cols[c].data;
 #pragma unroll
         for (int it = 0; it < (BATCH ? ITERS : 0); ++it) {
-            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
+            const int64_t r0 = base + it * (THREADS * 2) + tid * 2;
             q[it] = make_uint4(0, 0, 0, 0);
             if ((flags >> (2 * it)) & 3u) {
                 if (r0 + 1 < p.n) {
@@ -368,10 +369,14 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
     // ---- block scan of the (iter, warp) counts + decoupled look-back (warp 0) ----
     if (warp == 0) {
         uint32_t c[PER_LANE], mine = 0;
+        if constexpr (NCNT >= 32) {
 #pragma unroll
-        for (int e = 0; e < PER_LANE; ++e) {
-            c[e] = s_cnt[lane * PER_LANE + e];
-            mine += c[e];
+            for (int e = 0; e < PER_LANE; ++e) {
+                c[e] = s_cnt[lane * PER_LANE + e];
+                mine += c[e];
+            }
+        } else {
+            c[0] = mine = lane < NCNT ? s_cnt[lane] : 0u;   // fewer counts than lanes
         }
         uint32_t inc = mine;
 #pragma unroll
@@ -380,10 +385,14 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
             if (lane >= d) inc += t;
         }
         uint32_t run = inc - mine;  // exclusive offset of this lane's first (iter, warp) entry inside the tile
+        if constexpr (NCNT >= 32) {
 #pragma unroll
-        for (int e = 0; e < PER_LANE; ++e) {
-            s_cnt[lane * PER_LANE + e] = run;
-            run += c[e];
+            for (int e = 0; e < PER_LANE; ++e) {
+                s_cnt[lane * PER_LANE + e] = run;
+                run += c[e];
+            }
+        } else {
+            if (lane < NCNT) s_cnt[lane] = run;
         }
         uint64_t total = __shfl_sync(0xffffffffu, inc, 31);
         uint64_t excl = 0;
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
     // ---- phase 2: scatter every column; a warp writes one contiguous run per iter ----
     if constexpr (BATCH != 0) {
 #pragma unroll
-        for (int it = 0; it < ITERS; ++it) lane_off[it] += s_cnt[it * (FT_THREADS / 32) + warp];
+        for (int it = 0; it < ITERS; ++it) lane_off[it] += s_cnt[it * (THREADS / 32) + warp];
         auto store_col = [&](int c, const uint4 (&q)[ITERS]) {
             uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
 #pragma unroll
@@ -460,8 +469,8 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
             for (int it = 0; it < ITERS; ++it) {
                 const uint32_t f = (flags >> (2 * it)) & 3u;
                 if (f == 0) continue;
-                const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
-                int64_t pos = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
+                const int64_t r0 = base + it * (THREADS * 2) + tid * 2;
+                int64_t pos = tile_excl + s_cnt[it * (THREADS / 32) + warp] + lane_off[it];
                 if (es == 8) {
                     uint64_t v0, v1;
                     if (from_regs) {
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(FT_THREADS) filter_kernel(const __grid_constan
                     if (f & 2) store_from_u64(p.out_data[c], col.dtype, q, load_as_u64(col, r0 + 1));
                 }
                 if (outv != nullptr) {
-                    int64_t q = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
+                    int64_t q = tile_excl + s_cnt[it * (THREADS / 32) + warp] + lane_off[it];
                     if (f & 1) outv[q++] = col_valid(col, r0);
                     if (f & 2) outv[q] = col_valid(col, r0 + 1);
                 }
@@ -913,7 +922,12 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
     const int iters = (cfg & 1) ? 8 : 4;
     const int batch_cfg = (cfg >> 2) & 3;
     const bool keep = (cfg & 2) != 0 && batch_cfg == 0;
-    const int tile_rows = FT_THREADS * 2 * iters;
+    // 64: 128-thread CTAs (1024-row tiles, 16 CTAs/SM); 128: two row pairs per thread (1024-row tiles);
+    // 192: both (512-row tiles).  Opt-in, unmeasured: the plain (BATCH 0, KEEP off) kernel only.
+    const int small = (cfg >> 6) & 3;
+    const int threads = (small & 1) ? 128 : FT_THREADS;
+    const int iters_eff = small ? ((small & 2) ? 2 : 4) : iters;
+    const int tile_rows = threads * 2 * iters_eff;
     const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
     // columns are processed FT_MAX_COLS at a time; each pass re-evaluates the predicate
     int c0 = 0;
@@ -947,7 +961,7 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         VK_CUDA(cudaMemsetAsync(scratch, 0, vk_filter_scratch_bytes(n_rows), s));
         // TMA-staged variant (cfg 16 / 32): same column eligibility as the batched scatter
         const int tma_cb = (cfg & 16) ? 4 : ((cfg & 32) ? 2 : 0);
-        if (tma_cb && batch_ok && iters == 4 && (pk == PK_F64_VEC || pk == PK_I64_VEC ||
+        if (tma_cb && !small && batch_ok && iters == 4 && (pk == PK_F64_VEC || pk == PK_I64_VEC ||
             (pk == PK_MASK && (reinterpret_cast<uintptr_t>(p.pred.mask) & 15) == 0))) {
             const size_t smem = (size_t) FT_THREADS * 2 * 4 * 8 * (1 + tma_cb);
 #define VK_FILTER_TMA_GO(PK)                                                                          \
@@ -970,7 +984,10 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         }
 #define VK_FILTER_GO(PK)                                                                              \
         do {                                                                                              \
-            if (batch) {                                                                                  \
+            if (small == 1) filter_kernel<PK, 4, false, 0, 128><<<(unsigned) tiles, 128, 0, s>>>(p);      \
+            else if (small == 2) filter_kernel<PK, 2, false, 0, 256><<<(unsigned) tiles, 256, 0, s>>>(p); \
+            else if (small == 3) filter_kernel<PK, 2, false, 0, 128><<<(unsigned) tiles, 128, 0, s>>>(p); \
+            else if (batch) {                                                                                  \
                 if (iters == 8 && batch == 2) filter_kernel<PK, 8, false, 2><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
                 else if (iters == 8) filter_kernel<PK, 8, false, 1><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
                 else if (batch == 2) filter_kernel<PK, 4, false, 2><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
