@@ -509,7 +509,9 @@ __global__ void __launch_bounds__(THREADS) filter_kernel(const __grid_constant__
 // signalling its own mbarrier): nothing is staged in registers, every byte of the tile is in
 // flight at once, and the copies land while the predicate is evaluated and the look-back runs.
 // The scatter then reads shared memory (lane-contiguous 16-byte reads, conflict free).  Columns
-// beyond CB reuse the buffers round by round.  Same eligibility as BATCH; the ragged last tile is
+// beyond CB reuse the buffers round by round; an output column that is the predicate column itself
+// is scattered straight from the predicate slice (no second read of it, unlike filter_kernel, where
+// keeping it costs registers and occupancy).  Same eligibility as BATCH; the ragged last tile is
 // staged with ordinary loads.  Opt-in (VINUM_B200_FILTER_CFG 16: CB = 4, 32: CB = 2), unmeasured.
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -558,18 +560,22 @@ __global__ void __launch_bounds__(FT_THREADS) filter_tma_kernel(const __grid_con
     const bool full = rows == TILE;
     const uint8_t* pred_src = PK == PK_MASK ? p.pred.mask + base : p.pred.col.data + base * 8;
 
+    // an output column that IS the predicate column is scattered from the predicate slice: no second read
+    auto is_pred_col = [&](int c) { return PK != PK_MASK && p.cols[c].data == p.pred.col.data; };
     // stage round g (columns g*CB ...): TMA for complete tiles, plain loads for the ragged last one
     auto stage_cols = [&](int g) {
         const int c0 = g * CB;
         if (full) {
             if (tid == 0) {
                 for (int k = 0; k < CB && c0 + k < p.n_cols; ++k) {
+                    if (is_pred_col(c0 + k)) continue;
                     mbar_arrive_expect_tx(a_bar + 8 * (1 + k), COL_BYTES);
                     tma_load_1d(a_col0 + k * COL_BYTES, p.cols[c0 + k].data + base * 8, COL_BYTES, a_bar + 8 * (1 + k));
                 }
             }
         } else {
             for (int k = 0; k < CB && c0 + k < p.n_cols; ++k) {
+                if (is_pred_col(c0 + k)) continue;
                 const uint64_t* src = reinterpret_cast<const uint64_t*>(p.cols[c0 + k].data) + base;
                 uint64_t* dst = reinterpret_cast<uint64_t*>(ft_smem + COL_BYTES + (size_t) k * COL_BYTES);
                 for (int i = tid; i < rows; i += FT_THREADS) dst[i] = src[i];
@@ -687,14 +693,20 @@ __global__ void __launch_bounds__(FT_THREADS) filter_tma_kernel(const __grid_con
     for (int it = 0; it < ITERS; ++it) lane_off[it] += s_cnt[it * (FT_THREADS / 32) + warp];
 
     // ---- phase 2: scatter from shared memory, CB columns per round ----
+    // (a buffer's mbarrier only advances in the rounds that stage a column into it: its parity is tracked)
+    uint32_t phase[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) phase[k] = 0;
     const int rounds = (p.n_cols + CB - 1) / CB;
     for (int g = 0; g < rounds; ++g) {
         for (int k = 0; k < CB && g * CB + k < p.n_cols; ++k) {
-            if (full) {
-                while (!mbar_try_wait(a_bar + 8 * (1 + k), (uint32_t) (g & 1))) {}
+            const bool from_pred = is_pred_col(g * CB + k);
+            if (full && !from_pred) {
+                while (!mbar_try_wait(a_bar + 8 * (1 + k), phase[k])) {}
+                phase[k] ^= 1u;
             }
             uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[g * CB + k]);
-            const uint32_t a_col = a_col0 + k * COL_BYTES;
+            const uint32_t a_col = from_pred ? a_pred : a_col0 + k * COL_BYTES;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
                 const uint32_t f = (flags >> (2 * it)) & 3u;
