@@ -354,17 +354,24 @@ def s_onegroup():
     without a fused predicate; parity on an odd row count, timing at 1e8 rows."""
     st = vb.default_stream()
     res = {}
-    funcs = [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64()), (L.AGG_SUM, pa.int64()),
-             (L.AGG_MIN, pa.int64()), (L.AGG_MAX, pa.float64()), (L.AGG_COUNT, pa.float64())]
+    # two aggregates of <= 4 value functions each, so that the fused single-launch kernel
+    # (VINUM_B200_ONEGROUP_FUSED=1, at most 4 functions) is eligible for both
+    funcs_a = [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64()), (L.AGG_SUM, pa.int64()),
+               (L.AGG_MIN, pa.int64()), (L.AGG_MAX, pa.float64())]
+    funcs_b = [(L.AGG_COUNT, pa.float64())]
 
     def run(n, with_pred):
         dev = datagen.device_table(["f0", "f1", "i1"], 0, n, stream=st)
         pred = ops.Predicate.compare(dev.column("f0"), ">", 0.5) if with_pred else None
-        agg = Aggregator([], funcs)
-        agg.update([], [None, dev.column("f1"), dev.column("i1"), dev.column("i1"), dev.column("f0"), dev.column("f1")], pred, st)
-        _, aggs = agg.result_arrays(st)
-        agg.close()
-        return dev, pred, [a[0].as_py() for a in aggs]
+        got = []
+        for funcs, vals in ((funcs_a, [None, dev.column("f1"), dev.column("i1"), dev.column("i1"), dev.column("f0")]),
+                            (funcs_b, [dev.column("f1")])):
+            agg = Aggregator([], funcs)
+            agg.update([], vals, pred, st)
+            _, aggs = agg.result_arrays(st)
+            agg.close()
+            got += [a[0].as_py() for a in aggs]
+        return dev, pred, got
     ok = True
     for with_pred in (False, True):
         n = 1_000_003

@@ -118,7 +118,7 @@ struct OneParams {
 };
 
 // Warp reduction of the per-thread partials and one atomic per warp into slot 0.
-__device__ __forceinline__ void onegroup_flush(const OneParams& p, int acc, uint64_t rows, uint64_t nn, uint64_t lo,
+__device__ __forceinline__ void onegroup_flush(const GTable& table, int fi, int acc, uint64_t rows, uint64_t nn, uint64_t lo,
                                                uint64_t hi, double fsum) {
     // warp reduction
     for (int d = 16; d > 0; d >>= 1) {
@@ -137,23 +137,23 @@ __device__ __forceinline__ void onegroup_flush(const OneParams& p, int acc, uint
         }
     }
     if ((threadIdx.x & 31) != 0) return;
-    if (p.fi < 0) {
-        if (rows) atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star), (unsigned long long) rows);
+    if (fi < 0) {
+        if (rows) atomicAdd(reinterpret_cast<unsigned long long*>(table.count_star), (unsigned long long) rows);
         return;
     }
-    if (nn) atomicAdd(reinterpret_cast<unsigned long long*>(p.table.nnull[p.fi]), (unsigned long long) nn);
+    if (nn) atomicAdd(reinterpret_cast<unsigned long long*>(table.nnull[fi]), (unsigned long long) nn);
     switch (acc) {
         case ACC_SUM_F64:
-            if (rows - nn) atomicAdd(reinterpret_cast<double*>(p.table.acc_lo[p.fi]), fsum);
+            if (rows - nn) atomicAdd(reinterpret_cast<double*>(table.acc_lo[fi]), fsum);
             break;
         case ACC_SUM_I64:
-            if (lo) atomicAdd(reinterpret_cast<unsigned long long*>(p.table.acc_lo[p.fi]), (unsigned long long) lo);
+            if (lo) atomicAdd(reinterpret_cast<unsigned long long*>(table.acc_lo[fi]), (unsigned long long) lo);
             break;
         case ACC_SUM_I128:
-            if (lo | hi) acc_add_i128(p.table.acc_lo[p.fi], p.table.acc_hi[p.fi], lo, hi);
+            if (lo | hi) acc_add_i128(table.acc_lo[fi], table.acc_hi[fi], lo, hi);
             break;
         case ACC_MAXORD:
-            if (rows - nn) atomicMax(reinterpret_cast<unsigned long long*>(p.table.acc_lo[p.fi]), (unsigned long long) lo);
+            if (rows - nn) atomicMax(reinterpret_cast<unsigned long long*>(table.acc_lo[fi]), (unsigned long long) lo);
             break;
         default: break;
     }
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) agg_onegroup_kernel(const __grid_constant
             }
         }
     }
-    onegroup_flush(p, acc, rows, nn, lo, hi, fsum);
+    onegroup_flush(p.table, p.fi, acc, rows, nn, lo, hi, fsum);
 }
 
 // The common un-grouped case -- no predicate or a vectorisable `column <op> literal` one, value
@@ -258,7 +258,115 @@ __global__ void __launch_bounds__(256) agg_onegroup8_kernel(const __grid_constan
             if (need_val) add(acc_load(p.spec, p.val, i));
         }
     }
-    onegroup_flush(p, acc, rows, 0, lo, hi, fsum);
+    onegroup_flush(p.table, p.fi, acc, rows, 0, lo, hi, fsum);
+}
+
+// Every function of the query in ONE launch (the row counter included): the predicate column and each
+// distinct value column are read once -- `COUNT(*), SUM(f1) WHERE f0 > c` moves 16 B/row instead of the
+// 24 B/row of one launch per function.  Up to ONE8_MAXF functions over up to ONE8_MAXF distinct plain
+// 8-byte columns.  Opt-in (VINUM_B200_ONEGROUP_FUSED=1), unmeasured.
+constexpr int ONE8_MAXF = 4;
+struct OneMultiParams {
+    Pred pred;
+    int n_funcs, n_cols;
+    FuncSpec spec[ONE8_MAXF];
+    int fi[ONE8_MAXF];         // function index in the table
+    int col_of[ONE8_MAXF];     // index into col[] (-1: the function needs no value, e.g. COUNT)
+    Col col[ONE8_MAXF];
+    int64_t n;
+    GTable table;
+};
+
+template <int PK, int U>
+__global__ void __launch_bounds__(256) agg_onegroup8_multi_kernel(const __grid_constant__ OneMultiParams p) {
+    static_assert(PK == PK_NONE || PK == PK_F64_VEC || PK == PK_I64_VEC, "vectorisable predicates only");
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t npairs = p.n >> 1;
+    uint64_t rows = 0, lo[ONE8_MAXF], hi[ONE8_MAXF];
+    double fsum[ONE8_MAXF];
+#pragma unroll
+    for (int f = 0; f < ONE8_MAXF; ++f) lo[f] = hi[f] = 0, fsum[f] = 0.0;
+    auto pass = [&](uint64_t bits) -> bool {
+        if constexpr (PK == PK_F64_VEC)
+            return apply_cmp(p.pred.op, __longlong_as_double((long long) bits), __longlong_as_double((long long) p.pred.scalar.bits));
+        else if constexpr (PK == PK_I64_VEC) return apply_cmp(p.pred.op, (int64_t) bits, (int64_t) p.pred.scalar.bits);
+        else return true;
+    };
+    // one selected row of column values v[] into every function's accumulator
+    auto add_row = [&](const uint64_t (&v)[ONE8_MAXF]) {
+#pragma unroll
+        for (int f = 0; f < ONE8_MAXF; ++f) {
+            if (f >= p.n_funcs || p.col_of[f] < 0) continue;
+            uint64_t x = 0;
+#pragma unroll
+            for (int c = 0; c < ONE8_MAXF; ++c)
+                if (p.col_of[f] == c) x = v[c];
+            switch (p.spec[f].acc) {
+                case ACC_SUM_F64: fsum[f] += __longlong_as_double((long long) x); break;
+                case ACC_SUM_I128: {
+                    const uint64_t nl = lo[f] + x;
+                    hi[f] += ((!p.spec[f].in_unsigned && (int64_t) x < 0) ? ~0ULL : 0ULL) + (nl < lo[f] ? 1ULL : 0ULL);
+                    lo[f] = nl;
+                    break;
+                }
+                case ACC_MAXORD: {
+                    const uint64_t o = ord_transform(p.spec[f].ord, p.spec[f].is_min, x);
+                    lo[f] = o > lo[f] ? o : lo[f];
+                    break;
+                }
+                default: break;
+            }
+        }
+    };
+    for (int64_t q0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q0 < npairs; q0 += stride * U) {
+        uint4 pq[U], vq[ONE8_MAXF][U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + u * stride;
+            pq[u] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int c = 0; c < ONE8_MAXF; ++c) vq[c][u] = make_uint4(0, 0, 0, 0);
+            if (q < npairs) {
+                if constexpr (PK != PK_NONE) pq[u] = ldg_stream16(p.pred.col.data + q * 16);
+#pragma unroll
+                for (int c = 0; c < ONE8_MAXF; ++c)
+                    if (c < p.n_cols) vq[c][u] = ldg_stream16(p.col[c].data + q * 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (q0 + u * stride < npairs) {
+                const bool ok0 = pass(((uint64_t) pq[u].y << 32) | pq[u].x), ok1 = pass(((uint64_t) pq[u].w << 32) | pq[u].z);
+                rows += (uint64_t) ok0 + (uint64_t) ok1;
+                uint64_t v0[ONE8_MAXF], v1[ONE8_MAXF];
+#pragma unroll
+                for (int c = 0; c < ONE8_MAXF; ++c) {
+                    v0[c] = ((uint64_t) vq[c][u].y << 32) | vq[c][u].x;
+                    v1[c] = ((uint64_t) vq[c][u].w << 32) | vq[c][u].z;
+                }
+                if (ok0) add_row(v0);
+                if (ok1) add_row(v1);
+            }
+        }
+    }
+    if ((p.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // last, unpaired row
+        const int64_t i = p.n - 1;
+        if (pred_row(p.pred, i)) {
+            ++rows;
+            uint64_t v[ONE8_MAXF] = {0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < ONE8_MAXF; ++c)
+                if (c < p.n_cols) v[c] = reinterpret_cast<const uint64_t*>(p.col[c].data)[i];
+            add_row(v);
+        }
+    }
+    // flush: the row counter once, then every function through the single-function helper
+    onegroup_flush(p.table, -1, ACC_NONE, rows, 0, 0, 0, 0.0);
+#pragma unroll
+    for (int f = 0; f < ONE8_MAXF; ++f) {
+        if (f >= p.n_funcs) continue;
+        onegroup_flush(p.table, p.fi[f], p.spec[f].acc, rows, 0, lo[f], hi[f], fsum[f]);
+    }
 }
 
 // ================================================================== finalize
@@ -1104,6 +1212,48 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         a->last_path = 3;
         int64_t need = (n_rows + 255) / 256, capb = (int64_t) sm_count() * 8;
         const unsigned grid = (unsigned) (need < capb ? need : capb);
+        // ---- every function in one launch (opt-in, unmeasured) ----
+        static int fused = -1;
+        if (fused < 0) { const char* v = getenv("VINUM_B200_ONEGROUP_FUSED"); fused = v ? atoi(v) : 0; }
+        if (fused) {
+            OneMultiParams mp{};
+            int pk;
+            int rc = make_pred(*pred, n_rows, &mp.pred, &pk);
+            if (rc != VK_OK) return rc;
+            bool ok = pk == PK_NONE || pk == PK_F64_VEC || pk == PK_I64_VEC;
+            for (int f = 0; f < a->n_funcs && ok; ++f) {
+                const FuncSpec sp = a->specs[f];
+                if (sp.acc == ACC_NONE) continue;
+                if (mp.n_funcs == ONE8_MAXF || sp.acc == ACC_SUM_I64 || values[f].validity != nullptr) { ok = false; break; }
+                const int j = mp.n_funcs++;
+                mp.spec[j] = sp;
+                mp.fi[j] = f;
+                mp.col_of[j] = -1;
+                if (sp.acc == ACC_COUNT) continue;
+                const Col c = make_col(values[f]);
+                const bool f64_acc = sp.acc == ACC_SUM_F64 || (sp.acc == ACC_MAXORD && sp.ord == ORD_F64);
+                if (!(f64_acc ? c.dtype == VK_F64 : (c.dtype == VK_I64 || c.dtype == VK_U64)) ||
+                    (reinterpret_cast<uintptr_t>(c.data) & 15) != 0) { ok = false; break; }
+                for (int k = 0; k < mp.n_cols; ++k)
+                    if (mp.col[k].data == c.data) mp.col_of[j] = k;
+                if (mp.col_of[j] < 0) {
+                    if (mp.n_cols == ONE8_MAXF) { ok = false; break; }
+                    mp.col[mp.n_cols] = c;
+                    mp.col_of[j] = mp.n_cols++;
+                }
+            }
+            if (ok) {
+                mp.n = n_rows;
+                mp.table = a->t;
+                int64_t need8 = (n_rows / 2 + 256 * 2 - 1) / (256 * 2);
+                const unsigned g8 = (unsigned) (need8 < 1 ? 1 : (need8 < capb ? need8 : capb));
+                if (pk == PK_NONE) agg_onegroup8_multi_kernel<PK_NONE, 2><<<g8, 256, 0, s>>>(mp);
+                else if (pk == PK_F64_VEC) agg_onegroup8_multi_kernel<PK_F64_VEC, 2><<<g8, 256, 0, s>>>(mp);
+                else agg_onegroup8_multi_kernel<PK_I64_VEC, 2><<<g8, 256, 0, s>>>(mp);
+                VK_CHECK_LAUNCH("agg_onegroup8_multi_kernel");
+                return VK_OK;
+            }
+        }
         for (int f = -1; f < a->n_funcs; ++f) {
             if (f >= 0 && a->specs[f].acc == ACC_NONE) continue;
             OneParams op{};
