@@ -194,6 +194,7 @@ struct PassParams {
     const unsigned long long* bucket_start;  // [256] for this digit
     unsigned long long* ticket;
     unsigned long long* status;         // [tiles][256]
+    int64_t* out_final;                 // LAST pass: the permutation (vk_sort_indices' out_indices)
 };
 
 __device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int shift) {
@@ -216,7 +217,10 @@ __device__ __forceinline__ unsigned digit_peers_ballot(uint32_t d, bool in, int 
     return peers;
 }
 
-template <int RS_ITEMS, int MINB, bool BALLOT>
+// LAST: the final pass of the sort writes the permutation itself (row ids widened to int64 into
+// PassParams::out_final, NULL flag dropped) and no keys -- nothing reads them any more -- which saves the
+// 8 B/row key write and the separate widen pass (4 B/row read + 8 B/row write).
+template <int RS_ITEMS, int MINB, bool BALLOT, bool LAST = false>
 __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __grid_constant__ PassParams p) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -345,8 +349,12 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
         const uint32_t ix = s_idx[i];
         const uint32_t d = pass_digit(kx, ix, p.shift);
         const unsigned long long dst = s_gbase[d] + (uint32_t) (i - s_lb[d]);
-        p.out_key[dst] = kx;
-        p.out_idx[dst] = ix;
+        if constexpr (LAST) {
+            p.out_final[dst] = (int64_t) (ix & ~RS_NULLBIT);
+        } else {
+            p.out_key[dst] = kx;
+            p.out_idx[dst] = ix;
+        }
     }
 }
 
@@ -560,6 +568,15 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
     const int tile_keys = RS_THREADS * items;
     const int64_t tiles = (n_rows + tile_keys - 1) / tile_keys;
     VK_CUDA(cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
+    // opt-in, unmeasured: the last pass writes out_indices directly (default geometry only)
+    static int fuse_last = -1;
+    if (fuse_last < 0) { const char* v = getenv("VINUM_B200_SORT_FUSE_LAST"); fuse_last = v ? atoi(v) : 0; }
+    void (*last_kernel)(PassParams) = nullptr;
+    if (fuse_last && pass_kernel == sort_pass_kernel<16, 3, true>) {
+        last_kernel = sort_pass_kernel<16, 3, true, true>;
+        VK_CUDA(cudaFuncSetAttribute(last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
+    }
+    bool wrote_final = false;
     int cur = 0;            // buffers holding the running (key', idx)
     bool have_perm = false;
     unsigned long long h_hist[9 * 256];
@@ -592,11 +609,19 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         sort_scan_kernel<<<9, 256, 0, s>>>(sc.hist);
         VK_CHECK_LAUNCH("sort_scan_kernel");
         // ---- one pass per digit that actually varies ----
+        int last_d = -1;
+        for (int d = 0; d < 9; ++d) {
+            bool varies = true;
+            for (int b = 0; b < 256; ++b)
+                if (h_hist[d * 256 + b] == (unsigned long long) n_rows) { varies = false; break; }
+            if (varies) last_d = d;
+        }
         for (int d = 0; d < 9; ++d) {
             bool varies = true;
             for (int b = 0; b < 256; ++b)
                 if (h_hist[d * 256 + b] == (unsigned long long) n_rows) { varies = false; break; }
             if (!varies) continue;
+            const bool is_final = last_kernel != nullptr && k == 0 && d == last_d;
             PassParams ps{};
             ps.in_key = sc.key[cur];
             ps.in_idx = sc.idx[cur];
@@ -609,11 +634,18 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
             ps.status = sc.status;
             VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
             VK_CUDA(cudaMemsetAsync(sc.status, 0, sc.status_bytes, s));
-            pass_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
+            ps.out_final = out_indices;
+            if (is_final) {
+                last_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
+                wrote_final = true;
+            } else {
+                pass_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
+            }
             VK_CHECK_LAUNCH("sort_pass_kernel");
             cur ^= 1;
         }
     }
+    if (wrote_final) return VK_OK;
     sort_widen_kernel<<<grid_rows(n_rows), 256, 0, s>>>(sc.idx[cur], n_rows, out_indices);
     VK_CHECK_LAUNCH("sort_widen_kernel");
     return VK_OK;
