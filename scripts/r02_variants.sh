@@ -17,7 +17,9 @@ VINUM_B200_ARITH_FAST=0 VINUM_B200_ONEGROUP_FAST=0 run arith_onegroup_off 60 pyt
 VINUM_B200_ARITH_FAST=2 VINUM_B200_ONEGROUP_FAST=2 run arith_onegroup_u2 60 python -u scripts/gpu_check.py arith onegroup
 VINUM_B200_ONEGROUP_FUSED=1 run onegroup_fused 60 python -u scripts/gpu_check.py onegroup   # never run: one launch for all functions
 VINUM_B200_SORT_FUSE_LAST=1 run sort_fuse_last 60 python -u scripts/gpu_check.py sort   # never run: last pass writes the permutation
+VINUM_B200_SORT_FUSE_FIRST=1 run sort_fuse_first 60 python -u scripts/gpu_check.py sort   # never run: first pass computes the codes
+VINUM_B200_SORT_FUSE_FIRST=1 VINUM_B200_SORT_FUSE_LAST=1 run sort_fuse_both 60 python -u scripts/gpu_check.py sort
 VINUM_B200_SORT_PREP=0 run sort_prep_off 60 python -u scripts/gpu_check.py sort
 VINUM_B200_SORT_PREP=2 VINUM_B200_TAKE_U=4 run sort_prep_u2_take4 60 python -u scripts/gpu_check.py sort
 run pytest_gpu 900 python -m pytest tests -m gpu -x -q
-VINUM_B200_ONEGROUP_FUSED=1 VINUM_B200_SORT_FUSE_LAST=1 run pytest_gpu_fused 900 python -m pytest tests -m gpu -x -q
+VINUM_B200_ONEGROUP_FUSED=1 VINUM_B200_SORT_FUSE_LAST=1 VINUM_B200_SORT_FUSE_FIRST=1 run pytest_gpu_fused 900 python -m pytest tests -m gpu -x -q

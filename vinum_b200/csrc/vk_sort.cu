@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) sort_prepare8_kernel(const __grid_constan
             } else {
                 c = (is_signed ? (c ^ 0x8000000000000000ULL) : c) ^ flip;
             }
-            if (in) {
+            if (in && p.out_key != nullptr) {  // nullptr: histograms only (the first pass recomputes the codes)
                 p.out_key[i] = c;
                 p.out_idx[i] = src[u];
             }
@@ -195,6 +195,9 @@ struct PassParams {
     unsigned long long* ticket;
     unsigned long long* status;         // [tiles][256]
     int64_t* out_final;                 // LAST pass: the permutation (vk_sort_indices' out_indices)
+    const uint64_t* src;                // FIRST pass: the plain 8-byte key column itself (in_key unused)
+    int src_kind;                       // FIRST pass: 0 uint64, 1 int64, 2 float64
+    int desc;                           // FIRST pass
 };
 
 __device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int shift) {
@@ -220,7 +223,10 @@ __device__ __forceinline__ unsigned digit_peers_ballot(uint32_t d, bool in, int 
 // LAST: the final pass of the sort writes the permutation itself (row ids widened to int64 into
 // PassParams::out_final, NULL flag dropped) and no keys -- nothing reads them any more -- which saves the
 // 8 B/row key write and the separate widen pass (4 B/row read + 8 B/row write).
-template <int RS_ITEMS, int MINB, bool BALLOT, bool LAST = false>
+// FIRST: the first pass of a plain 8-byte key computes the codes while it loads (row = in_idx[i], or i
+// itself when there is no running permutation yet), so the prepare pass only builds histograms: no
+// 12 B/row written by prepare and 8 instead of 12 B/row read here.
+template <int RS_ITEMS, int MINB, bool BALLOT, bool LAST = false, bool FIRST = false>
 __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __grid_constant__ PassParams p) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -248,11 +254,34 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
     for (int k = 0; k < RS_ITEMS; ++k) {
         const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
         if (li < tile_n) {
-            key[k] = p.in_key[base + li];
-            idx[k] = p.in_idx[base + li];
+            if constexpr (FIRST) {
+                idx[k] = p.in_idx ? (p.in_idx[base + li] & ~RS_NULLBIT) : (uint32_t) (base + li);
+                key[k] = p.src[idx[k]];
+            } else {
+                key[k] = p.in_key[base + li];
+                idx[k] = p.in_idx[base + li];
+            }
         } else {
             key[k] = 0;
             idx[k] = 0;
+        }
+    }
+    if constexpr (FIRST) {
+        const uint64_t flip = p.desc ? ~0ULL : 0ULL;
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            uint64_t c = key[k];
+            if (p.src_kind == 2) {
+                const double d = __longlong_as_double((long long) c);
+                if (d != d) c = KEY_NAN;
+                else {
+                    if (d == 0.0) c = 0;  // -0.0 -> +0.0
+                    c = f64_to_ordered(c) ^ flip;
+                }
+            } else {
+                c = (p.src_kind == 1 ? (c ^ 0x8000000000000000ULL) : c) ^ flip;
+            }
+            key[k] = c;   // (rows past the end of the tile are never ranked or written)
         }
     }
     // ---- stable rank inside the warp's 512 items ----
@@ -576,6 +605,15 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         last_kernel = sort_pass_kernel<16, 3, true, true>;
         VK_CUDA(cudaFuncSetAttribute(last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
     }
+    static int fuse_first = -1;
+    if (fuse_first < 0) { const char* v = getenv("VINUM_B200_SORT_FUSE_FIRST"); fuse_first = v ? atoi(v) : 0; }
+    void (*first_kernel)(PassParams) = nullptr, (*first_last_kernel)(PassParams) = nullptr;
+    if (fuse_first && pass_kernel == sort_pass_kernel<16, 3, true>) {
+        first_kernel = sort_pass_kernel<16, 3, true, false, true>;
+        first_last_kernel = sort_pass_kernel<16, 3, true, true, true>;
+        VK_CUDA(cudaFuncSetAttribute(first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
+        VK_CUDA(cudaFuncSetAttribute(first_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
+    }
     bool wrote_final = false;
     int cur = 0;            // buffers holding the running (key', idx)
     bool have_perm = false;
@@ -598,12 +636,24 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         if (prep < 0) { const char* v = getenv("VINUM_B200_SORT_PREP"); prep = v ? atoi(v) : 4; }
         const bool plain8 = keys[k].validity == nullptr && !keys[k].nulls_as_nan &&
                             (keys[k].dtype == VK_F64 || keys[k].dtype == VK_I64 || keys[k].dtype == VK_U64);
+        // fused first pass: prepare builds the histograms only (they do not depend on the row order, so it
+        // reads the column sequentially) and leaves the running permutation where it is
+        const bool fused_first = first_kernel != nullptr && plain8 && prep >= 2 &&
+                                 (reinterpret_cast<uintptr_t>(pp.col.data) & 7) == 0;
+        if (fused_first) {
+            pp.perm = nullptr;
+            pp.out_key = nullptr;
+            pp.out_idx = nullptr;
+        }
         if (prep >= 4 && plain8) sort_prepare8_kernel<4><<<grid_rows(n_rows, 8), 256, 0, s>>>(pp);
         else if (prep >= 2 && plain8) sort_prepare8_kernel<2><<<grid_rows(n_rows, 8), 256, 0, s>>>(pp);
         else sort_prepare_kernel<<<grid_rows(n_rows, 4), 256, 0, s>>>(pp);
         VK_CHECK_LAUNCH("sort_prepare_kernel");
-        cur = nxt;
-        have_perm = true;
+        bool first_pending = fused_first;
+        if (!fused_first) {
+            cur = nxt;
+            have_perm = true;
+        }
         VK_CUDA(cudaMemcpyAsync(h_hist, sc.hist, sizeof(h_hist), cudaMemcpyDeviceToHost, s));
         VK_CUDA(cudaStreamSynchronize(s));
         sort_scan_kernel<<<9, 256, 0, s>>>(sc.hist);
@@ -635,7 +685,22 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
             VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
             VK_CUDA(cudaMemsetAsync(sc.status, 0, sc.status_bytes, s));
             ps.out_final = out_indices;
-            if (is_final) {
+            if (first_pending) {
+                // codes are computed from the column itself; rows come from the running permutation, if any
+                ps.in_key = nullptr;
+                ps.in_idx = have_perm ? sc.idx[cur] : nullptr;
+                ps.src = reinterpret_cast<const uint64_t*>(pp.col.data);
+                ps.src_kind = keys[k].dtype == VK_F64 ? 2 : (keys[k].dtype == VK_I64 ? 1 : 0);
+                ps.desc = pp.desc;
+                if (is_final) {
+                    first_last_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
+                    wrote_final = true;
+                } else {
+                    first_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
+                }
+                first_pending = false;
+                have_perm = true;
+            } else if (is_final) {
                 last_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
                 wrote_final = true;
             } else {
@@ -646,6 +711,10 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         }
     }
     if (wrote_final) return VK_OK;
+    if (!have_perm) {  // (fused first pass) no key had a varying digit: the permutation is the identity
+        sort_iota_kernel<<<grid_rows(n_rows), 256, 0, s>>>(sc.idx[cur], n_rows);
+        VK_CHECK_LAUNCH("sort_iota_kernel");
+    }
     sort_widen_kernel<<<grid_rows(n_rows), 256, 0, s>>>(sc.idx[cur], n_rows, out_indices);
     VK_CHECK_LAUNCH("sort_widen_kernel");
     return VK_OK;
