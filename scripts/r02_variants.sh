@@ -7,8 +7,9 @@ rm -f gpurun_out/round.log
 export TAILN=3
 run defaults 120 python -u scripts/gpu_check.py filter sort arith onegroup topk
 # filter: 0 default, 1 = 4096-row tiles, 4 / 8 = batched scatter, 16 / 32 = TMA-staged tiles,
-# 64 = 128-thread CTAs, 128 = two row pairs per thread, 192 = both (never run: parity is checked by the section)
-for c in 64 128 192 1 4 8 16 32; do
+# 64 = 128-thread CTAs, 128 = two row pairs per thread, 192 = both, 256 / 512 = split variant (flags + scan +
+# one scatter per column / one scatter launch) -- 64..512 have never run: parity is checked by the section
+for c in 256 512 64 128 192 1 4 8 16 32; do
   VINUM_B200_FILTER_CFG=$c run filter_cfg$c 60 python -u scripts/gpu_check.py filter
 done
 VINUM_B200_CMP_FAST=0 run cmp_off 60 python -u scripts/gpu_check.py filter

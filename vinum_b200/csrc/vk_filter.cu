@@ -728,6 +728,146 @@ __global__ void __launch_bounds__(FT_THREADS) filter_tma_kernel(const __grid_con
     }
 }
 
+// ---- split variant: flags + counts, scan, one scatter per column ---------------------------------
+// The single-pass kernels keep about nine DRAM streams open at once (predicate + every column read, every
+// column written at data-dependent offsets) and chain the tiles through the look-back.  This variant
+// evaluates the predicate once into ONE BIT PER ROW (the warp ballots, 12.5 MB per 1e8 rows) plus a count
+// per tile, scans the tile counts, and then compacts the columns one launch per column: two or three
+// streams at a time, every tile independent.  Costs 1/64 of the predicate column in flag traffic.
+// Opt-in (VINUM_B200_FILTER_CFG 256: one launch per column, 512: one launch, blockIdx.y = column), unmeasured.
+constexpr int FS_ITERS = 4;
+constexpr int FS_TILE = FT_THREADS * 2 * FS_ITERS;              // 2048 rows
+constexpr int FS_WORDS = FS_ITERS * (FT_THREADS / 32) * 2;      // 64 ballot words per tile
+
+struct SplitParams {
+    Pred pred;
+    int64_t n;
+    int64_t num_tiles;
+    uint32_t* flags;          // [tiles][FS_WORDS]: ballots (b0, b1) of (iteration, warp)
+    uint32_t* tile_count;     // [tiles] selected rows per tile
+    int64_t* tile_offset;     // [tiles] exclusive prefix (written by the scan)
+    int64_t* out_rows;
+    int n_cols;
+    Col cols[FT_MAX_COLS];
+    void* out_data[FT_MAX_COLS];
+};
+
+template <int PK>
+__global__ void __launch_bounds__(FT_THREADS) filter_flags_kernel(const __grid_constant__ SplitParams p) {
+    __shared__ uint32_t s_cnt[FT_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int64_t base = tile * FS_TILE;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int it = 0; it < FS_ITERS; ++it) {
+            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
+            bool f0, f1;
+            pred_pair<PK>(p.pred, r0, p.n, f0, f1);
+            const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+            if (lane == 0) {
+                uint32_t* w = p.flags + tile * FS_WORDS + (it * (FT_THREADS / 32) + warp) * 2;
+                w[0] = b0;
+                w[1] = b1;
+            }
+            cnt += __popc(b0) + __popc(b1);
+        }
+        if (lane == 0) s_cnt[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < FT_THREADS / 32; ++w) t += s_cnt[w];
+            p.tile_count[tile] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// exclusive scan of the tile counts (one CTA; 48 828 tiles per 1e8 rows)
+__global__ void __launch_bounds__(1024) filter_scan_kernel(const __grid_constant__ SplitParams p) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < p.num_tiles; t0 += 1024) {
+        const int64_t t = t0 + tid;
+        const int64_t v = t < p.num_tiles ? (int64_t) p.tile_count[t] : 0;
+        int64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t o = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += o;
+            }
+            s_warp[lane] = winc - w;   // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int64_t carry = s_carry;
+        if (t < p.num_tiles) p.tile_offset[t] = carry + s_warp[warp] + inc - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[warp] + inc;
+        __syncthreads();
+    }
+    if (tid == 0) *p.out_rows = s_carry;
+}
+
+// one column (blockIdx.y, or column0 + blockIdx.y) of one tile per CTA
+__global__ void __launch_bounds__(FT_THREADS) filter_scatter_kernel(const __grid_constant__ SplitParams p, int column0) {
+    __shared__ uint32_t s_flags[FS_WORDS];
+    __shared__ uint32_t s_pre[FS_WORDS / 2];     // selected rows before (iteration, warp) inside the tile
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = column0 + blockIdx.y;
+    const Col col = p.cols[c];
+    const int es = dtype_size(col.dtype);
+    const unsigned lt = lanemask_lt();
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int64_t base = tile * FS_TILE;
+        if (tid < FS_WORDS) s_flags[tid] = p.flags[tile * FS_WORDS + tid];
+        __syncthreads();
+        if (warp == 0) {   // exclusive scan of the 32 (iteration, warp) counts
+            const uint32_t mine = __popc(s_flags[2 * lane]) + __popc(s_flags[2 * lane + 1]);
+            uint32_t inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            s_pre[lane] = inc - mine;
+        }
+        __syncthreads();
+        const int64_t tile_excl = p.tile_offset[tile];
+#pragma unroll
+        for (int it = 0; it < FS_ITERS; ++it) {
+            const int slot = it * (FT_THREADS / 32) + warp;
+            const uint32_t b0 = s_flags[2 * slot], b1 = s_flags[2 * slot + 1];
+            const uint32_t f = ((b0 >> lane) & 1u) | (((b1 >> lane) & 1u) << 1);
+            if (f == 0) continue;
+            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
+            int64_t pos = tile_excl + s_pre[slot] + __popc(b0 & lt) + __popc(b1 & lt);
+            if (es == 8 && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0) && r0 + 1 < p.n) {
+                const uint4 q = ldg_stream16(col.data + r0 * 8);
+                uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
+                if (f & 1) o[pos++] = ((uint64_t) q.y << 32) | q.x;
+                if (f & 2) o[pos] = ((uint64_t) q.w << 32) | q.z;
+            } else {
+                if (f & 1) store_from_u64(p.out_data[c], col.dtype, pos++, load_as_u64(col, r0));
+                if (f & 2) store_from_u64(p.out_data[c], col.dtype, pos, load_as_u64(col, r0 + 1));
+            }
+        }
+        __syncthreads();
+    }
+}
+
 static int grid_for(int64_t work_items, int per_sm = 8) {
     int64_t need = (work_items + 255) / 256;
     int64_t cap = (int64_t) sm_count() * per_sm;
@@ -930,7 +1070,8 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
     static int cfg = -1;
     if (cfg < 0) { const char* v = getenv("VINUM_B200_FILTER_CFG"); cfg = v ? atoi(v) : 0; }
     // bit 0: 4096-row tiles; bit 1: keep the predicate column; bits 2-3: batched scatter (1 or 2, see
-    // filter_kernel) when every column of the pass qualifies; 16 / 32: TMA-staged tiles (filter_tma_kernel)
+    // filter_kernel) when every column of the pass qualifies; 16 / 32: TMA-staged tiles (filter_tma_kernel);
+    // 64 / 128: small tiles; 256 / 512: split variant (flags + scan + one scatter per column)
     const int iters = (cfg & 1) ? 8 : 4;
     const int batch_cfg = (cfg >> 2) & 3;
     const bool keep = (cfg & 2) != 0 && batch_cfg == 0;
@@ -941,6 +1082,59 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
     const int iters_eff = small ? ((small & 2) ? 2 : 4) : iters;
     const int tile_rows = threads * 2 * iters_eff;
     const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
+    // ---- split variant (cfg 256 / 512): flags + counts, scan, one scatter per column ----
+    if (cfg & (256 | 512)) {
+        bool plain = true;
+        for (int c = 0; c < n_cols; ++c) plain = plain && cols[c].validity == nullptr;
+        if (plain) {
+            const int64_t stiles = (n_rows + FS_TILE - 1) / FS_TILE;
+            uint32_t* d_flags = nullptr;
+            uint32_t* d_count = nullptr;
+            int64_t* d_offset = nullptr;
+            VK_CUDA(cudaMallocAsync((void**) &d_flags, (size_t) stiles * FS_WORDS * sizeof(uint32_t), s));
+            VK_CUDA(cudaMallocAsync((void**) &d_count, (size_t) stiles * sizeof(uint32_t), s));
+            VK_CUDA(cudaMallocAsync((void**) &d_offset, (size_t) stiles * sizeof(int64_t), s));
+            SplitParams sp{};
+            sp.pred = dp;
+            sp.n = n_rows;
+            sp.num_tiles = stiles;
+            sp.flags = d_flags;
+            sp.tile_count = d_count;
+            sp.tile_offset = d_offset;
+            sp.out_rows = out_rows;
+            const int64_t cap = (int64_t) sm_count() * 8;
+            const unsigned gx = (unsigned) (stiles < cap ? stiles : cap);
+            switch (pk) {
+                case PK_MASK: filter_flags_kernel<PK_MASK><<<gx, FT_THREADS, 0, s>>>(sp); break;
+                case PK_F64_VEC: filter_flags_kernel<PK_F64_VEC><<<gx, FT_THREADS, 0, s>>>(sp); break;
+                case PK_I64_VEC: filter_flags_kernel<PK_I64_VEC><<<gx, FT_THREADS, 0, s>>>(sp); break;
+                default: filter_flags_kernel<PK_GENERIC><<<gx, FT_THREADS, 0, s>>>(sp); break;
+            }
+            VK_CHECK_LAUNCH("filter_flags_kernel");
+            filter_scan_kernel<<<1, 1024, 0, s>>>(sp);
+            VK_CHECK_LAUNCH("filter_scan_kernel");
+            for (int g0 = 0; g0 < n_cols; g0 += FT_MAX_COLS) {
+                sp.n_cols = (n_cols - g0 < FT_MAX_COLS) ? n_cols - g0 : FT_MAX_COLS;
+                for (int c = 0; c < sp.n_cols; ++c) {
+                    sp.cols[c] = make_col(cols[g0 + c]);
+                    sp.out_data[c] = out_data[g0 + c];
+                }
+                if (cfg & 512) {
+                    filter_scatter_kernel<<<dim3(gx, (unsigned) sp.n_cols), FT_THREADS, 0, s>>>(sp, 0);
+                    VK_CHECK_LAUNCH("filter_scatter_kernel");
+                } else {
+                    for (int c = 0; c < sp.n_cols; ++c) {
+                        filter_scatter_kernel<<<dim3(gx, 1), FT_THREADS, 0, s>>>(sp, c);
+                        VK_CHECK_LAUNCH("filter_scatter_kernel");
+                    }
+                }
+            }
+            VK_CUDA(cudaFreeAsync(d_flags, s));
+            VK_CUDA(cudaFreeAsync(d_count, s));
+            VK_CUDA(cudaFreeAsync(d_offset, s));
+            return VK_OK;
+        }
+    }
     // columns are processed FT_MAX_COLS at a time; each pass re-evaluates the predicate
     int c0 = 0;
     do {
