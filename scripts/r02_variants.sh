@@ -20,6 +20,9 @@ VINUM_B200_ONEGROUP_FUSED=1 run onegroup_fused 60 python -u scripts/gpu_check.py
 VINUM_B200_SORT_FUSE_LAST=1 run sort_fuse_last 60 python -u scripts/gpu_check.py sort   # never run: last pass writes the permutation
 VINUM_B200_SORT_FUSE_FIRST=1 run sort_fuse_first 60 python -u scripts/gpu_check.py sort   # never run: first pass computes the codes
 VINUM_B200_SORT_FUSE_FIRST=1 VINUM_B200_SORT_FUSE_LAST=1 run sort_fuse_both 60 python -u scripts/gpu_check.py sort
+for c in 20 21 22; do   # never run: direct scatter, no shared-memory reorder (16 keys x 3 CTAs, 8 x 5, 8 x 6)
+  VINUM_B200_SORT_CFG=$c run sort_cfg$c 60 python -u scripts/gpu_check.py sort
+done
 VINUM_B200_SORT_PREP=0 run sort_prep_off 60 python -u scripts/gpu_check.py sort
 VINUM_B200_SORT_PREP=2 VINUM_B200_TAKE_U=4 run sort_prep_u2_take4 60 python -u scripts/gpu_check.py sort
 run pytest_gpu 900 python -m pytest tests -m gpu -x -q

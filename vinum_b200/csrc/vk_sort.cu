@@ -226,7 +226,12 @@ __device__ __forceinline__ unsigned digit_peers_ballot(uint32_t d, bool in, int 
 // FIRST: the first pass of a plain 8-byte key computes the codes while it loads (row = in_idx[i], or i
 // itself when there is no running permutation yet), so the prepare pass only builds histograms: no
 // 12 B/row written by prepare and 8 instead of 12 B/row read here.
-template <int RS_ITEMS, int MINB, bool BALLOT, bool LAST = false, bool FIRST = false>
+// DIRECT: no reorder through shared memory -- every key goes from its register straight to its global
+// position (s_gbase + rank inside the tile's bucket).  A warp's store then touches up to 32 sectors
+// instead of a few contiguous runs, which costs L2 write transactions but no DRAM traffic (the sectors
+// are completed by the neighbouring keys of the same tile before they are evicted), and the kernel needs
+// neither the 48 KB staging buffer nor the last two barriers: more CTAs per SM.  Opt-in, unmeasured.
+template <int RS_ITEMS, int MINB, bool BALLOT, bool LAST = false, bool FIRST = false, bool DIRECT = false>
 __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __grid_constant__ PassParams p) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -361,28 +366,45 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
     }
     __syncthreads();
 
-    // ---- reorder inside shared memory, then write bucket runs ----
+    if constexpr (DIRECT) {
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
-        const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
-        if (li < tile_n) {
-            const uint32_t d = pass_digit(key[k], idx[k], p.shift);
-            const uint32_t pos = s_lb[d] + s_wcnt[warp][d] + rank[k];
-            s_key[pos] = key[k];
-            s_idx[pos] = idx[k];
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+            if (li < tile_n) {
+                const uint32_t d = pass_digit(key[k], idx[k], p.shift);
+                const unsigned long long dst = s_gbase[d] + s_wcnt[warp][d] + rank[k];
+                if constexpr (LAST) {
+                    p.out_final[dst] = (int64_t) (idx[k] & ~RS_NULLBIT);
+                } else {
+                    p.out_key[dst] = key[k];
+                    p.out_idx[dst] = idx[k];
+                }
+            }
         }
-    }
-    __syncthreads();
-    for (int i = tid; i < tile_n; i += RS_THREADS) {
-        const uint64_t kx = s_key[i];
-        const uint32_t ix = s_idx[i];
-        const uint32_t d = pass_digit(kx, ix, p.shift);
-        const unsigned long long dst = s_gbase[d] + (uint32_t) (i - s_lb[d]);
-        if constexpr (LAST) {
-            p.out_final[dst] = (int64_t) (ix & ~RS_NULLBIT);
-        } else {
-            p.out_key[dst] = kx;
-            p.out_idx[dst] = ix;
+    } else {
+        // ---- reorder inside shared memory, then write bucket runs ----
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+            if (li < tile_n) {
+                const uint32_t d = pass_digit(key[k], idx[k], p.shift);
+                const uint32_t pos = s_lb[d] + s_wcnt[warp][d] + rank[k];
+                s_key[pos] = key[k];
+                s_idx[pos] = idx[k];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < tile_n; i += RS_THREADS) {
+            const uint64_t kx = s_key[i];
+            const uint32_t ix = s_idx[i];
+            const uint32_t d = pass_digit(kx, ix, p.shift);
+            const unsigned long long dst = s_gbase[d] + (uint32_t) (i - s_lb[d]);
+            if constexpr (LAST) {
+                p.out_final[dst] = (int64_t) (ix & ~RS_NULLBIT);
+            } else {
+                p.out_key[dst] = kx;
+                p.out_idx[dst] = ix;
+            }
         }
     }
 }
@@ -582,6 +604,7 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
     static int cfg = -1;
     if (cfg < 0) { const char* v = getenv("VINUM_B200_SORT_CFG"); cfg = v ? atoi(v) : 9; }
     int items;
+    bool direct = false;
     void (*pass_kernel)(PassParams);
     switch (cfg) {
         case 0: items = 16; pass_kernel = sort_pass_kernel<16, 2, false>; break;
@@ -592,11 +615,18 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         case 10: items = 12; pass_kernel = sort_pass_kernel<12, 3, true>; break;
         case 11: items = 12; pass_kernel = sort_pass_kernel<12, 4, true>; break;
         case 12: items = 8; pass_kernel = sort_pass_kernel<8, 4, true>; break;
+        // direct scatter (no shared-memory reorder, no dynamic shared memory): opt-in, unmeasured
+        case 20: items = 16; direct = true; pass_kernel = sort_pass_kernel<16, 3, true, false, false, true>; break;
+        case 21: items = 8; direct = true; pass_kernel = sort_pass_kernel<8, 5, true, false, false, true>; break;
+        case 22: items = 8; direct = true; pass_kernel = sort_pass_kernel<8, 6, true, false, false, true>; break;
         default: items = 16; pass_kernel = sort_pass_kernel<16, 3, true>; break;   // ballot ranking
     }
     const int tile_keys = RS_THREADS * items;
     const int64_t tiles = (n_rows + tile_keys - 1) / tile_keys;
-    VK_CUDA(cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
+    // only the status rows of this geometry's tiles are cleared per pass (the array is sized for the smallest tile)
+    const size_t status_used = (size_t) tiles * 256 * sizeof(unsigned long long);
+    const size_t pass_smem = direct ? 0 : (size_t) tile_keys * 12;
+    VK_CUDA(cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pass_smem));
     // opt-in, unmeasured: the last pass writes out_indices directly (default geometry only)
     static int fuse_last = -1;
     if (fuse_last < 0) { const char* v = getenv("VINUM_B200_SORT_FUSE_LAST"); fuse_last = v ? atoi(v) : 0; }
@@ -683,7 +713,7 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
             ps.ticket = sc.ticket;
             ps.status = sc.status;
             VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
-            VK_CUDA(cudaMemsetAsync(sc.status, 0, sc.status_bytes, s));
+            VK_CUDA(cudaMemsetAsync(sc.status, 0, status_used, s));
             ps.out_final = out_indices;
             if (first_pending) {
                 // codes are computed from the column itself; rows come from the running permutation, if any
@@ -704,7 +734,7 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
                 last_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
                 wrote_final = true;
             } else {
-                pass_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
+                pass_kernel<<<(unsigned) tiles, RS_THREADS, pass_smem, s>>>(ps);
             }
             VK_CHECK_LAUNCH("sort_pass_kernel");
             cur ^= 1;
