@@ -87,6 +87,14 @@ int vk_host_free(void* ptr);
 int vk_host_register(void* ptr, uint64_t bytes);                  /* pin an Arrow buffer */
 int vk_host_unregister(void* ptr);
 int vk_memcpy_h2d(void* dst, const void* host_src, uint64_t bytes, VkStream stream);
+/* Host -> device copy of PAGEABLE memory through a pool of pinned bounce buffers filled by worker
+ * threads (vk_ingest.cu): returns when every piece is queued on `stream`, not when it has arrived.
+ * vk_memcpy_h2d_auto picks: pinned / registered source or < 1 MB -> plain cudaMemcpyAsync, else staged.
+ * This is how a host pyarrow.Table reaches the operators (the reference slices it in place,
+ * vinum_cpp/src/operators/table_batch_reader.cpp:5-16). */
+int vk_memcpy_h2d_staged(void* dst, const void* host_src, uint64_t bytes, VkStream stream);
+int vk_memcpy_h2d_auto(void* dst, const void* host_src, uint64_t bytes, VkStream stream);
+int vk_ingest_threads(void);   /* worker threads of the bounce-buffer pool (starts it) */
 int vk_memcpy_d2h(void* host_dst, const void* src, uint64_t bytes, VkStream stream);
 int vk_memcpy_d2d(void* dst, const void* src, uint64_t bytes, VkStream stream);
 int vk_memset(void* dst, int byte, uint64_t bytes, VkStream stream);
@@ -102,6 +110,12 @@ int vk_stream_wait_event(VkStream stream, VkEvent event);  /* cudaStreamWaitEven
 int vk_event_elapsed_ms(VkEvent start, VkEvent stop, float* out_ms);
 /* number of kernels this library has launched since load (bench.py `gpu_launches`) */
 uint64_t vk_launch_count(void);
+/* Kernel-selection knobs (INTEGRATION.md "knobs"): compiled-in default, preset by the environment
+ * variable VINUM_B200_<NAME> at first use, changed at run time here.  Unknown name -> VK_ERR_ARG.
+ * They select between kernels that compute the same result; the reference has no counterpart. */
+int vk_set_option(const char* name, int64_t value);
+int vk_get_option(const char* name, int64_t* out_value);
+int vk_reset_options(void);   /* forget every vk_set_option: back to environment / defaults */
 
 /* ------------------------------------------------- synthetic table (8d) ---- */
 /* Deterministic, shard-regenerable columns: value(row r, column c) is a pure
@@ -244,6 +258,34 @@ int vk_agg_partition_counts(VkAgg* agg, int n_ranks, int64_t* out_counts_dev, Vk
 int vk_agg_export_partials(VkAgg* agg, int n_ranks, const int64_t* offsets_dev /* n_ranks */,
                            uint64_t* out_records, VkStream stream);
 int vk_agg_merge_partials(VkAgg* agg, const uint64_t* records, int64_t n_records, VkStream stream);
+/* Finalise into ONE device block (one copy + one synchronisation for the caller).  u64 words, C = capacity:
+ *   [0] groups in the table (may exceed C: retry with a larger block)  [1] reserved
+ *   keys[n_keys][C] | count_star[C] | lo[n_funcs][C] | hi[n_funcs][C] | bytes key_valid[n_keys][C] valid[n_funcs][C]
+ * Same values as vk_agg_result (BaseAggregate::Result, base_aggregate.cpp:47-68). */
+uint64_t vk_agg_result_packed_bytes(int n_keys, int n_funcs, int64_t capacity);
+int vk_agg_result_packed(VkAgg* agg, int64_t capacity, void* out_block, VkStream stream);
+
+/* ---- peer exchange: low-cardinality group-by across the GPUs of one box without a collective ----
+ * Every rank owns a window of device memory (cudaMalloc) that its peers map through cudaIpc handles
+ * (exchanged once by the host, e.g. torch.distributed.all_gather_object) and write into over NVLink.
+ * vk_agg_peer_send: this rank's partial groups -> its slot in the owner's window + release flag, then
+ * waits (on the device) for the owner's acknowledgement.  vk_agg_peer_merge (owner): acquires every
+ * rank's flag, folds the records into the owner's own table, acknowledges.  `epoch` = 1, 2, 3 ... is
+ * the query number, the same on every rank.  After the stream has drained, *vk_peer_decision_ptr(epoch)
+ * (a device address; copy it back) is 1 = merged, 2 = a rank had more than cap_groups partial groups,
+ * 3 = the owner's table must grow, 4 = a peer did not answer within 4 s; on 2 / 3 every rank falls back
+ * to the all-to-all repartition (vk_agg_partition_counts / _export_partials / _merge_partials).
+ * The reference has no counterpart (single-threaded, vinum/executor/executor.py:24-31). */
+typedef struct VkPeer VkPeer;
+int vk_peer_create(VkPeer** out, int rank, int world, int64_t cap_groups, int max_record_words);
+int vk_peer_destroy(VkPeer* peer);
+int vk_peer_handle(VkPeer* peer, void* out_handle64 /* 64 bytes */);
+int vk_peer_open(VkPeer* peer, int peer_rank, const void* handle64);
+int vk_peer_attach_local(VkPeer* peer, int peer_rank, VkPeer* other /* same process */);
+void* vk_peer_decision_ptr(VkPeer* peer, uint64_t epoch);
+int vk_agg_peer_send(VkAgg* agg, VkPeer* peer, int owner_rank, uint64_t epoch, VkStream stream);
+int vk_agg_peer_merge(VkAgg* agg, VkPeer* peer, uint64_t epoch, VkStream stream);
+
 /* introspection for tests/bench: which kernel path the last update used
  * (0 = none, 1 = shared-memory table, 2 = global table, 3 = one-group reduction) */
 int vk_agg_last_path(VkAgg* agg);
@@ -263,6 +305,12 @@ uint64_t vk_sort_scratch_bytes(int64_t n_rows);
 /* out_indices: n_rows int64 row ids (the permutation SortIndices returns). */
 int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int64_t n_rows,
                     int64_t* out_indices, void* scratch, VkStream stream);
+/* Same, and also Take of the FIRST key column itself (sort.cpp:40-48 gathers every column, the sort
+ * key included): out_key0_sorted receives n_rows 8-byte values, written by the last radix pass from the
+ * sorted codes instead of a random gather.  keys[0] must be a plain int64 / uint64 / float64 column
+ * without validity; values are bit-identical to Take (NaN payloads and the sign of zero included). */
+int vk_sort_indices_keys(const VkColumn* keys, const int32_t* orders, int n_keys, int64_t n_rows,
+                         int64_t* out_indices, void* out_key0_sorted, void* scratch, VkStream stream);
 /* Take: out[i] = col[indices[i]]; out_valid_bytes may be NULL when no validity. */
 int vk_take(const VkColumn* col, const int64_t* indices, int64_t n_indices, void* out,
             uint8_t* out_valid_bytes, VkStream stream);

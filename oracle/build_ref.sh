@@ -15,6 +15,25 @@ if [ ! -d "$SRC" ]; then
 fi
 mkdir -p "$OUT/obj"
 PY="${PYTHON:-python}"
+# The reference's pure-Python layers (parser AST, binder, planner, executor, operators) as ONE zip archive
+# next to the compiled operators: `bench.py --impl reference` and tests/test_gpu_dropin.py drive the
+# reference's own QueryPlanner + RecursiveExecutor on the GPU box, where /root/reference does not exist.
+# A build artefact like the .so (git-ignored, never edited, never imported by vinum_b200/).
+PYREF="$OUT/vinum_pyref.zip"
+REFPY="$(dirname "$(dirname "$SRC")")/vinum"
+if [ -d "$REFPY" ] && { [ ! -f "$PYREF" ] || [ -n "$(find "$REFPY" -name '*.py' -newer "$PYREF" | head -1)" ]; }; then
+  $PY - "$REFPY" "$PYREF" <<'PYEOF'
+import sys, zipfile, pathlib
+src, dst = pathlib.Path(sys.argv[1]), sys.argv[2]
+with zipfile.ZipFile(dst, "w", zipfile.ZIP_DEFLATED) as z:
+    for f in sorted(src.rglob("*.py")):
+        rel = f.relative_to(src.parent)
+        if "tests" in rel.parts:
+            continue
+        z.write(f, str(rel))
+PYEOF
+  echo "build_ref.sh: packed $PYREF"
+fi
 PA=$($PY -c "import pyarrow as pa;print(pa.get_library_dirs()[0])")
 PAINC=$($PY -c "import pyarrow as pa;print(pa.get_include())")
 PYINC=$($PY -c "import sysconfig;print(sysconfig.get_paths()['include'])")

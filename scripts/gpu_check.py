@@ -142,11 +142,8 @@ def np_groupby(keys, vals, mask):
 def run_agg(keycol, valcol, predcol, n, st, cfg, reps=3):
     """cfg = (direct policy, warps or 0) -> env knobs read by vk_agg_create."""
     direct, warps = cfg
-    os.environ["VINUM_B200_AGG_DIRECT"] = str(direct)
-    if warps:
-        os.environ["VINUM_B200_AGG_WARPS"] = str(warps)
-    else:
-        os.environ.pop("VINUM_B200_AGG_WARPS", None)
+    vb.set_option("AGG_DIRECT", direct)
+    vb.set_option("AGG_WARPS", warps)
     pred = ops.Predicate.compare(predcol, ">", 0.5) if predcol is not None else None
 
     def once():
@@ -301,12 +298,17 @@ def s_sort():
     best, med = timed(lambda: lib.vk_sort_indices(v, o, 1, n, C.c_void_p(out.data_ptr), C.c_void_p(scratch.ptr), st.ptr), st, reps=3, warm=1)
     res["c4_ms"] = best
     res["c4_Mrows_s"] = n / best / 1e3
+    sk = vb.DeviceColumn.empty(n, L.F64, stream=st)
+    best, med = timed(lambda: lib.vk_sort_indices_keys(v, o, 1, n, C.c_void_p(out.data_ptr), C.c_void_p(sk.data_ptr),
+                                                       C.c_void_p(scratch.ptr), st.ptr), st, reps=3, warm=1)
+    res["c4_with_sorted_key_ms"] = best
     tk = vb.DeviceColumn.empty(n, L.F64, stream=st)
     fv = f3.vk()
     best, med = timed(lambda: lib.vk_take(C.byref(fv), C.c_void_p(out.data_ptr), n, C.c_void_p(tk.data_ptr), None, st.ptr), st, reps=3, warm=1)
     res["take_ms"] = best
     srt = tk.to_numpy(st)
     res["c4_sorted"] = bool(np.all(srt[:-1] >= srt[1:]))
+    res["c4_sorted_key_equals_take"] = bool(np.array_equal(sk.to_numpy(st).view(np.uint64), srt.view(np.uint64)))
     return res
 
 
@@ -430,7 +432,12 @@ SECTIONS = {f.__name__: f for f in [s_datagen, s_filter, s_agg_parity, s_agg_hig
 if __name__ == "__main__":
     lib.vk_set_device(0)
     print(json.dumps({"device": vb.device_info(0)}), flush=True)
-    want = sys.argv[1:] or list(SECTIONS)
+    args = sys.argv[1:]
+    for a in [a for a in args if "=" in a]:   # NAME=VALUE: a kernel-selection option (vk_set_option)
+        name, value = a.split("=", 1)
+        vb.set_option(name, int(value))
+        print(json.dumps({"option": {name: int(value)}}), flush=True)
+    want = [a for a in args if "=" not in a] or list(SECTIONS)
     for name in want:
         SECTIONS[name]()
     os.makedirs("gpurun_out", exist_ok=True)

@@ -233,26 +233,42 @@ def test_aggregate_matches_reference_fixture(vb, case):
     assert_tables_match(got, want, key_cols=case["agg_cols"], rtol=FLOAT_RTOL, float_exact_cols=exact)
 
 
-@pytest.mark.parametrize("strategy", [0, 1, 2])
+# Every kernel path of the fused aggregate, forced through per-object options (vk_set_option is sampled by
+# vk_agg_create): direct group ids vs the CTA hash table vs the global-table kernel, 8 vs 12 warps, L2
+# prefetch off / on.  `path` is what vk_agg_last_path must report.
+AGG_PATHS = {
+    "direct_auto": (dict(), 1),
+    "direct_w8_pf6": (dict(AGG_WARPS=8, AGG_PF=6), 1),
+    "direct_w12_pf0": (dict(AGG_WARPS=12, AGG_PF=0), 1),
+    "hash_w8": (dict(AGG_DIRECT=0, AGG_WARPS=8), 1),
+    "hash_w12_small_table": (dict(AGG_DIRECT=0, AGG_WARPS=12, AGG_LOG2S=11), 1),
+    "hash_w4": (dict(AGG_DIRECT=0, AGG_WARPS=4, AGG_PF=0), 1),
+    "general_kernel": (dict(AGG_NOFAST=1), 2),
+}
+
+
+@pytest.mark.parametrize("path", sorted(AGG_PATHS))
 @pytest.mark.parametrize("keyname", ["i0", "k32"])
-def test_northstar_filter_aggregate_vs_oracle(vb, stream, strategy, keyname, monkeypatch):
-    """SELECT k, COUNT(*), SUM(f1) FROM t WHERE f0 > 0.5 GROUP BY k -- every shared-memory
-    strategy of the fused kernel against the oracle's restatement of the reference chain."""
+def test_northstar_filter_aggregate_vs_oracle(vb, stream, path, keyname):
+    """SELECT k, COUNT(*), SUM(f1), AVG(f1) FROM t WHERE f0 > 0.5 GROUP BY k -- every kernel path of the
+    fused aggregate against the oracle's restatement of the reference chain
+    (single_numerical_hash_aggregate.cpp:15-46, agg_funcs.h:97-127,280-317,439-542)."""
     from vinum_b200 import datagen, ops, _lib as L
-    monkeypatch.setenv("VINUM_B200_AGG_STRATEGY", str(strategy))
+    opts, want_path = AGG_PATHS[path]
     n = 1_000_003
     table = datagen.host_table([keyname, "f0", "f1"], 0, n)
     funcs = [("COUNT_STAR", "", "count_star"), ("SUM", "f1", "sum_f1"), ("AVG", "f1", "avg_f1")]
     want = O.filter_hash_aggregate(table, "f0", ">", 0.5, [keyname], funcs)
     dev = datagen.device_table([keyname, "f0", "f1"], 0, n, stream=stream)
-    agg = vb.Aggregator([table.schema.field(keyname).type], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64()),
-                                                              (L.AGG_AVG, pa.float64())])
+    with vb.options(AGG_LEARN_LOG2=16, **opts):   # a short learning launch: the main launch sees most rows
+        agg = vb.Aggregator([table.schema.field(keyname).type], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64()),
+                                                                  (L.AGG_AVG, pa.float64())])
     half = 500_736
     for lo, hi in ((0, half), (half, n)):
         part = dev.slice(lo, hi - lo)
         agg.update([part.column(keyname)], [None, part.column("f1"), part.column("f1")],
                    ops.Predicate.compare(part.column("f0"), ">", 0.5), stream)
-    assert agg.last_path == 1  # the shared-memory kernel ran
+    assert agg.last_path == want_path
     keys, aggs = agg.result_arrays(stream)
     got = pa.table([keys[0]] + aggs, names=[keyname, "count_star", "sum_f1", "avg_f1"])
     assert_tables_match(got, want, key_cols=[keyname], rtol=FLOAT_RTOL)
@@ -425,79 +441,3 @@ def test_sort_rejects_boolean_key(vb):
     t = pa.table({"b": pa.array([True, False]), "x": pa.array([1, 2])})
     with pytest.raises(RuntimeError):
         _sorted_rows(vb, t, ["b"], ["ASC"])
-
-
-# ---------------------------------------------------- size-independent properties ----
-def test_properties_at_scale(vb, stream):
-    """1e8-row checks that need no oracle: filter is idempotent and order preserving; the
-    aggregate's counts add up to the filter's row count and its sums to the column sum;
-    sort output is sorted and a permutation."""
-    from vinum_b200 import datagen, ops, _lib as L
-    n = int(os.environ.get("VK_TEST_SCALE_ROWS", 100_000_000))
-    dev = datagen.device_table(["i0", "i2", "f0", "f1"], 0, n, stream=stream)
-    pred = ops.Predicate.compare(dev.column("f0"), ">", 0.5)
-    out = ops.filter_batch(dev, pred, stream)
-    m = out.num_rows
-    assert abs(m / n - 0.5) < 0.01
-    again = ops.filter_batch(out, ops.Predicate.compare(out.column("f0"), ">", 0.5), stream)
-    assert again.num_rows == m  # idempotent
-    # order preserved: surviving row ids strictly increase (checked on device via a compare)
-    ids = out.column("i2")
-    inc = ops.compare(ids.slice(1, m - 1), ">", ids.slice(0, m - 1), stream)
-    chk = vb.Aggregator([], [(L.AGG_COUNT_STAR, None)])
-    chk.update_count_rows(m - 1, ops.Predicate.from_mask(inc), stream)
-    assert int(chk.result_raw(stream)[2][0]) == m - 1
-    # fused filter -> aggregate vs filter then un-grouped reduction
-    agg = vb.Aggregator([pa.int64()], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64())])
-    agg.update([dev.column("i0")], [None, dev.column("f1")], pred, stream)
-    keys, kv, cnt, lo, hi, valid = agg.result_raw(stream)
-    assert len(cnt) == 1000 and int(cnt.sum()) == m
-    tot = vb.Aggregator([], [(L.AGG_SUM, pa.float64())])
-    tot.update([], [out.column("f1")], None, stream)
-    total = tot.result_raw(stream)[3][0].view(np.float64)[0]
-    assert np.isclose(lo[1].view(np.float64).sum(), total, rtol=1e-9)
-    # sort: sorted + permutation
-    del out, again
-    f3 = datagen.device_column("f3", 0, n, stream=stream)
-    idx = ops.sort_indices([f3], [L.DESC], stream)
-    srt = ops.take(f3, idx, stream)
-    ok = ops.compare(srt.slice(0, n - 1), ">=", srt.slice(1, n - 1), stream)
-    chk = vb.Aggregator([], [(L.AGG_COUNT_STAR, None)])
-    chk.update_count_rows(n - 1, ops.Predicate.from_mask(ok), stream)
-    assert int(chk.result_raw(stream)[2][0]) == n - 1
-    perm = vb.Aggregator([], [(L.AGG_SUM, pa.int64()), (L.AGG_MIN, pa.int64()), (L.AGG_MAX, pa.int64())])
-    perm.update([], [idx, idx, idx], None, stream)
-    r = perm.result_raw(stream)
-    assert int(r[3][0][0]) + (int(r[4][0][0]) << 64) == n * (n - 1) // 2
-    assert int(r[3][1].view(np.int64)[0]) == 0 and int(r[3][2].view(np.int64)[0]) == n - 1
-
-
-def test_northstar_properties_at_full_size(vb, stream):
-    """BASELINE.json's headline size (1e9 rows; the three referenced columns resident): properties
-    that need no oracle.  The fused filter -> hash aggregate must (a) take the shared-memory path in
-    ONE main launch, (b) find exactly the 1000 keys 0..999, (c) count exactly the rows the
-    predicate selects -- cross-checked by an un-grouped COUNT through the general kernel on a
-    materialised mask -- and (d) sum to the un-grouped SUM over the same mask within 1e-9."""
-    from vinum_b200 import datagen, ops, _lib as L
-    n = int(os.environ.get("VK_TEST_FULL_ROWS", 1_000_000_000))
-    dev = datagen.device_table(["i0", "f0", "f1"], 0, n, stream=stream)
-    pred = ops.Predicate.compare(dev.column("f0"), ">", 0.5)
-    agg = vb.Aggregator([pa.int64()], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64())])
-    agg.profile(True)
-    agg.update([dev.column("i0")], [None, dev.column("f1")], pred, stream)
-    keys, kv, cnt, lo, hi, valid = agg.result_raw(stream)
-    ms, launches, rows = agg.profile_read(1)
-    assert agg.last_path == 1 and launches == 2 and rows >= n - 4096   # learning launch + one main launch
-    agg.close()
-    assert np.array_equal(np.sort(keys[0].view(np.int64)), np.arange(1000)) and kv.all()
-    mask = ops.compare(dev.column("f0"), ">", 0.5, stream)
-    one = vb.Aggregator([], [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64())])
-    one.update([], [None, dev.column("f1")], ops.Predicate.from_mask(mask), stream)
-    r = one.result_raw(stream)
-    one.close()
-    selected, total = int(r[2][0]), r[3][1].view(np.float64)[0]
-    assert abs(selected / n - 0.5) < 1e-3
-    assert int(cnt.sum()) == selected
-    assert np.isclose(lo[1].view(np.float64).sum(), total, rtol=1e-9, atol=1e-3)
-    # every group gets its share: uniform keys -> counts within 1 % of n / 2000
-    assert np.all(np.abs(cnt.astype(np.float64) / (selected / 1000) - 1.0) < 0.01)

@@ -140,6 +140,9 @@ SIGNATURES = {
     "vk_host_register": (_int, [_p, _u64]),
     "vk_host_unregister": (_int, [_p]),
     "vk_memcpy_h2d": (_int, [_p, _p, _u64, _p]),
+    "vk_memcpy_h2d_staged": (_int, [_p, _p, _u64, _p]),
+    "vk_memcpy_h2d_auto": (_int, [_p, _p, _u64, _p]),
+    "vk_ingest_threads": (_int, []),
     "vk_memcpy_d2h": (_int, [_p, _p, _u64, _p]),
     "vk_memcpy_d2d": (_int, [_p, _p, _u64, _p]),
     "vk_memset": (_int, [_p, _int, _u64, _p]),
@@ -154,6 +157,9 @@ SIGNATURES = {
     "vk_stream_wait_event": (_int, [_p, _p]),
     "vk_event_elapsed_ms": (_int, [_p, _p, C.POINTER(C.c_float)]),
     "vk_launch_count": (_u64, []),
+    "vk_set_option": (_int, [C.c_char_p, _i64]),
+    "vk_get_option": (_int, [C.c_char_p, C.POINTER(_i64)]),
+    "vk_reset_options": (_int, []),
     "vk_datagen": (_int, [_int, _u64, _i64, _i64, _p, _p]),
     "vk_compare_scalar": (_int, [C.POINTER(VkColumn), _int, C.POINTER(VkScalar), _p, _p]),
     "vk_compare_columns": (_int, [C.POINTER(VkColumn), _int, C.POINTER(VkColumn), _p, _p]),
@@ -176,11 +182,22 @@ SIGNATURES = {
     "vk_agg_partition_counts": (_int, [_p, _int, _p, _p]),
     "vk_agg_export_partials": (_int, [_p, _int, _p, _p, _p]),
     "vk_agg_merge_partials": (_int, [_p, _p, _i64, _p]),
+    "vk_agg_result_packed_bytes": (_u64, [_int, _int, _i64]),
+    "vk_agg_result_packed": (_int, [_p, _i64, _p, _p]),
+    "vk_peer_create": (_int, [_PP, _int, _int, _i64, _int]),
+    "vk_peer_destroy": (_int, [_p]),
+    "vk_peer_handle": (_int, [_p, _p]),
+    "vk_peer_open": (_int, [_p, _int, _p]),
+    "vk_peer_attach_local": (_int, [_p, _int, _p]),
+    "vk_peer_decision_ptr": (_p, [_p, _u64]),
+    "vk_agg_peer_send": (_int, [_p, _p, _int, _u64, _p]),
+    "vk_agg_peer_merge": (_int, [_p, _p, _u64, _p]),
     "vk_agg_last_path": (_int, [_p]),
     "vk_agg_profile": (_int, [_p, _int]),
     "vk_agg_profile_read": (_int, [_p, _int, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "vk_sort_scratch_bytes": (_u64, [_i64]),
     "vk_sort_indices": (_int, [C.POINTER(VkColumn), C.POINTER(C.c_int32), _int, _i64, _p, _p, _p]),
+    "vk_sort_indices_keys": (_int, [C.POINTER(VkColumn), C.POINTER(C.c_int32), _int, _i64, _p, _p, _p, _p]),
     "vk_take": (_int, [C.POINTER(VkColumn), _p, _i64, _p, _p, _p]),
     "vk_topk_scratch_bytes": (_u64, []),
     "vk_topk_candidates": (_int, [C.POINTER(VkColumn), C.c_int32, _i64, _i64, _i64, _p, C.POINTER(_i64), _p, _p]),
@@ -191,7 +208,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(_lib, _name)  # AttributeError here == header/library mismatch: fail loudly
     _fn.restype = _res
     _fn.argtypes = _args
-    if _res is _int and _name not in ("vk_abi_version", "vk_agg_last_path"):
+    if _res is _int and _name not in ("vk_abi_version", "vk_agg_last_path", "vk_ingest_threads"):
         _STATUS_FUNCS.add(_name)
 
 

@@ -25,6 +25,20 @@ FUNC_NAMES = {L.AGG_COUNT_STAR: "count_star", L.AGG_COUNT: "count", L.AGG_MIN: "
 
 _INT64_MAX = 0x7FFFFFFFFFFFFFFF
 
+_PINNED_SCRATCH = {}
+
+
+def _pinned_scratch(nbytes: int):
+    """One page-locked read-back block per thread, grown on demand (cudaHostAlloc costs far more than a query)."""
+    import threading
+    from .device import PinnedBuffer
+    key = threading.get_ident()
+    buf = _PINNED_SCRATCH.get(key)
+    if buf is None or buf.nbytes < nbytes:
+        buf = PinnedBuffer(max(nbytes, 1 << 16))
+        _PINNED_SCRATCH[key] = buf
+    return buf
+
 
 def check_supported(func: int, t: Optional[pa.DataType]) -> None:
     """Type errors of agg_func_factory.cpp (same messages)."""
@@ -155,10 +169,41 @@ class Aggregator:
         return g.value
 
     # ------------------------------------------------------------------ result
-    def result_raw(self, stream: Optional[Stream] = None):
+    def result_raw(self, stream: Optional[Stream] = None, extra_d2h=None):
         """Finalised groups as host NumPy arrays:
-        (keys u64[nk][g], key_valid bool[nk][g], count_star u64[g], lo u64[nf][g], hi u64[nf][g], valid bool[nf][g])."""
+        (keys u64[nk][g], key_valid bool[nk][g], count_star u64[g], lo u64[nf][g], hi u64[nf][g], valid bool[nf][g]).
+
+        Group-by aggregates finalise into one packed device block that is copied back with ONE
+        memcpy and ONE stream synchronisation (vk_agg_result_packed); the block is sized from the
+        last result and doubled on the rare overflow.  `extra_d2h` = (host address, device address,
+        bytes) rides on the same synchronisation (the peer exchange's decision word)."""
         st = stream or default_stream()
+        nk, nf = len(self.key_vk), len(self.funcs)
+        if nk == 0:
+            return self._result_raw_unpacked(st)
+        cap = getattr(self, "_result_cap", 1024)
+        while True:
+            nbytes = int(L._lib.vk_agg_result_packed_bytes(nk, nf, cap))
+            host = _pinned_scratch(nbytes)
+            dev = DeviceBuffer(nbytes, st)
+            lib.vk_agg_result_packed(self._h, cap, C.c_void_p(dev.ptr), st.ptr)
+            lib.vk_memcpy_d2h(C.c_void_p(host.ptr), C.c_void_p(dev.ptr), nbytes, st.ptr)
+            if extra_d2h is not None:
+                lib.vk_memcpy_d2h(C.c_void_p(extra_d2h[0]), C.c_void_p(extra_d2h[1]), int(extra_d2h[2]), st.ptr)
+            st.sync()
+            raw = host.as_numpy(np.uint8, nbytes)
+            g = int(raw[:8].view(np.uint64)[0])
+            if g <= cap:
+                break
+            cap = 1 << (g - 1).bit_length()
+        self._result_cap = max(1024, 1 << max(g - 1, 1).bit_length())
+        words = 2 + (nk + 1 + 2 * nf) * cap
+        h64 = raw[:words * 8].view(np.uint64)[2:].reshape(nk + 1 + 2 * nf, cap)[:, :g].copy()
+        h8 = raw[words * 8:words * 8 + (nk + nf) * cap].reshape(nk + nf, cap)[:, :g].astype(bool)
+        return h64[:nk], h8[:nk], h64[nk], h64[nk + 1:nk + 1 + nf], h64[nk + 1 + nf:], h8[nk:]
+
+    def _result_raw_unpacked(self, st: Stream):
+        """vk_agg_num_groups + vk_agg_result into separate arrays (the un-grouped aggregate's path)."""
         g = self.num_groups(st)
         nk, nf = len(self.key_vk), len(self.funcs)
         gg = max(g, 1)
@@ -183,9 +228,17 @@ class Aggregator:
         hi = h64[nk + 1 + nf:]
         return keys, h8[:nk].astype(bool), count, lo, hi, h8[nk:].astype(bool)
 
-    def result_arrays(self, stream: Optional[Stream] = None) -> Tuple[List[pa.Array], List[pa.Array]]:
-        """(key arrays, aggregate arrays) with the reference's output types."""
-        keys, key_valid, _count, lo, hi, valid = self.result_raw(stream)
+    def empty_raw(self):
+        """`result_raw` of zero groups (what a rank that is not the owner of a sharded query holds)."""
+        nk, nf = len(self.key_vk), len(self.funcs)
+        z64 = lambda r: np.zeros((r, 0), dtype=np.uint64)
+        zb = lambda r: np.zeros((r, 0), dtype=bool)
+        return z64(nk), zb(nk), np.zeros(0, dtype=np.uint64), z64(nf), z64(nf), zb(nf)
+
+    def result_arrays(self, stream: Optional[Stream] = None, raw=None) -> Tuple[List[pa.Array], List[pa.Array]]:
+        """(key arrays, aggregate arrays) with the reference's output types; `raw` = an already
+        finalised `result_raw` tuple (the merged groups of a sharded query) instead of this object's."""
+        keys, key_valid, _count, lo, hi, valid = raw if raw is not None else self.result_raw(stream)
         key_arrays = [_key_array(keys[k], key_valid[k], self.key_types[k], self.key_vk[k])
                       for k in range(len(self.key_vk))]
         agg_arrays = []

@@ -30,6 +30,7 @@ SOURCES = [
     ("vk_filter.cu", "vk_filter", []),
     ("vk_runtime.cu", "vk_runtime", []),
     ("vk_arith.cu", "vk_arith", []),
+    ("vk_ingest.cu", "vk_ingest", []),
 ]
 
 NVCC_FLAGS = [

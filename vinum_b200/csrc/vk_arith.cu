@@ -225,8 +225,7 @@ extern "C" int vk_arith(int op, const VkColumn* lhs_col, const VkScalar* lhs_sca
     int64_t need = (n_rows + 255) / 256, cap = (int64_t) sm_count() * 8;
     int g = (int) (need < cap ? need : cap);
     cudaStream_t s = (cudaStream_t) stream;
-    static int fast = -1;  // row pairs per thread of arith8_kernel (0: off; 4 measured: 6.06 vs 4.80 TB/s on f64 a + b)
-    if (fast < 0) { const char* v = getenv("VINUM_B200_ARITH_FAST"); fast = v ? atoi(v) : 4; }
+    const int fast = (int) opt(OPT_ARITH_FAST);  // row pairs per thread of arith8_kernel (0: off; 4 measured: 6.06 vs 4.80 TB/s on f64 a + b)
     auto raw8 = [&](const Operand& o) {
         if (!o.is_col) return true;
         const bool same_class = cc == CC_F64 ? o.col.dtype == VK_F64 : (o.col.dtype == VK_I64 || o.col.dtype == VK_U64);

@@ -33,6 +33,35 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
         if (!(cond)) return ::vk::fail(VK_ERR_ARG, msg);               \
     } while (0)
 
+// ---------------------------------------------------------------- options ----
+// Kernel-selection knobs.  Each has a compiled-in default, may be preset by the
+// environment variable VINUM_B200_<NAME> (read once, at first use) and can be changed at any time
+// with vk_set_option(), so that one process can exercise every path (tests/test_gpu_paths.py).
+enum Opt {
+    OPT_FILTER_STAGE = 0,   // 1: an output column that is the predicate column is scattered from shared memory
+    OPT_FILTER_PF,          // 1: bulk-prefetch a tile's payload columns into L2 before the look-back
+    OPT_FILTER_ITERS,       // row pairs per thread of filter_kernel: 4 (2048-row tiles) or 8
+    OPT_CMP_FAST,           // compare8_kernel row pairs per thread (0: compare_kernel)
+    OPT_ARITH_FAST,         // arith8_kernel row pairs per thread (0: arith_kernel)
+    OPT_ONEGROUP_FAST,      // agg_onegroup8_kernel row pairs per thread (0: agg_onegroup_kernel)
+    OPT_SORT_FUSE_LAST,     // 1: the last radix pass writes the int64 permutation itself
+    OPT_SORT_PREP,          // sort_prepare8_kernel loads per thread (0: sort_prepare_kernel)
+    OPT_SORT_BITS,          // radix digit width of the LSD passes (8 or 11; 0: automatic)
+    OPT_AGG_LOG2S,          // agg_fast_kernel: log2 of the CTA key table slots (hash mode)
+    OPT_AGG_PF,             // agg_fast_kernel: L2 prefetch distance in tiles (-1: automatic)
+    OPT_AGG_WARPS,          // agg_fast_kernel: warps per CTA (0: automatic)
+    OPT_AGG_DIRECT,         // 1: direct (key - base) group ids when the key range allows, 0: always hash
+    OPT_AGG_NOFAST,         // 1: never use the shared-memory aggregate kernel
+    OPT_AGG_HYBRID,         // agg_fast_kernel: every k-th tile goes through L2 atomics (0: off)
+    OPT_AGG_LEARN_LOG2,     // log2 rows of the learning launch
+    OPT_LIST_LOG2,          // log2 of the replay-list capacity cap (entries)
+    OPT_DEBUG,              // 1: trace the aggregate's host decisions to stderr
+    OPT_INGEST_STAGED,      // 1: pageable host memory goes through the pinned bounce-buffer pool (vk_ingest.cu)
+    OPT_INGEST_THREADS,     // worker threads of that pool (0: automatic; read when the pool starts)
+    OPT_COUNT
+};
+int64_t opt(int id);
+
 int sm_count();           // SMs of the current device (cached per device)
 int max_smem_optin();     // max opt-in dynamic shared memory per block
 

@@ -174,12 +174,12 @@ __global__ void __launch_bounds__(256) bits_to_mask_kernel(const uint8_t* __rest
 }
 
 // ========================================================= stream compaction
-// One CTA owns one 2048-row tile (ticketed, so predecessors are always running or
+// One CTA owns one tile of 512 * ITERS rows (ticketed, so predecessors are always running or
 // done).  Rows are mapped lane-contiguously in pairs -- row = it*512 + tid*2 + e --
 // so an 8-byte column is read with one 16-byte load per lane and the rank of a row
 // inside its tile is (rows selected by lower (it, warp)) + (ballot rank).
 constexpr int FT_THREADS = 256;
-constexpr int FT_MIN_TILE = 128 * 2 * 2;  // smallest tile geometry (512 rows): sizes the status array
+constexpr int FT_MIN_TILE = FT_THREADS * 2 * 4;  // smallest tile geometry (2048 rows): sizes the status array
 constexpr int FT_MAX_COLS = 12;
 
 constexpr uint64_t ST_FLAG_SHIFT = 62;
@@ -216,24 +216,24 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// PK: predicate kind (vk_pred.cuh); ITERS: row pairs per thread (tile = 512 * ITERS rows); KEEP: the
-// predicate column's registers are kept from phase 1 and reused when that column is also an output.
-// BATCH (1 or 2; the host checks that every column is 8-byte, 16-byte aligned and has no validity
-// bitmap): phase 2 issues the ITERS 16-byte loads of a column back to back and only then stores, and
-// the first column's loads are issued BEFORE the look-back, whose latency they overlap.  BATCH 2
-// also loads column c+1 before it stores column c.  The BATCH 0 scatter loop loads and stores one
-// row pair at a time (one load in flight per thread: SASS of round 1) and leaves the memory-level
-// parallelism to the 64 resident warps.
-template <int PK, int ITERS, bool KEEP, int BATCH = 0, int THREADS = FT_THREADS>
-__global__ void __launch_bounds__(THREADS) filter_kernel(const __grid_constant__ FilterParams p) {
-    static_assert(BATCH == 0 || !KEEP, "the batched scatter re-reads the predicate column");
-    constexpr int TILE = THREADS * 2 * ITERS;
-    constexpr int NCNT = ITERS * (THREADS / 32);   // (iter, warp) counts: 32 or 64 (8 or 16 for the small-tile variants)
-    constexpr int PER_LANE = NCNT >= 32 ? NCNT / 32 : 1;
-    static_assert(NCNT % 32 == 0 || NCNT < 32, "one or more whole counts per lane");
+// PK: predicate kind (vk_pred.cuh); ITERS: row pairs per thread (tile = 512 * ITERS rows).
+// STAGE (8-byte CMP predicates only): the 16 bytes of the predicate column that phase 1 loads per row
+// pair are parked in shared memory (one conflict-free STS.128 per pair, 16 KB per 2048-row tile), and an
+// output column that IS the predicate column (`SELECT * ... WHERE f0 > c`) is scattered from there
+// instead of being read from DRAM a second time: C2 moves 4.8 GB instead of 5.6 GB.  Keeping the pairs
+// in registers instead costs 16 registers and with them a quarter of the resident tiles (measured
+// -30 % in round 1); shared memory is otherwise unused by this kernel.
+template <int PK, int ITERS, bool STAGE>
+__global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(const __grid_constant__ FilterParams p) {
+    static_assert(!STAGE || PK == PK_F64_VEC || PK == PK_I64_VEC, "staging needs an 8-byte compare predicate");
+    constexpr int TILE = FT_THREADS * 2 * ITERS;
+    constexpr int NCNT = ITERS * (FT_THREADS / 32);   // (iter, warp) counts: 32 or 64
+    constexpr int PER_LANE = NCNT / 32;
+    static_assert(NCNT % 32 == 0, "whole counts per lane");
     __shared__ int64_t s_tile;
     __shared__ uint32_t s_cnt[NCNT];
     __shared__ int64_t s_excl;
+    __shared__ __align__(16) uint4 s_pred[STAGE ? ITERS * FT_THREADS : 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = (int64_t) atomicAdd(p.ticket, 1ULL);
@@ -255,84 +255,30 @@ __global__ void __launch_bounds__(THREADS) filter_kernel(const __grid_constant__
     // ---- phase 1: evaluate the predicate once, keep the flags in registers ----
     uint32_t flags = 0;
     uint32_t lane_off[ITERS];
-    uint4 praw[KEEP ? ITERS : 1];
     const unsigned lt = lanemask_lt();
-    // (BATCH) the ITERS predicate loads go out together and the operator is branched on once; the
-    // BATCH 0 loop below compares pair by pair, so each load waits for the previous pair's branches
-    uint32_t pflags = 0;
-    if constexpr (BATCH != 0 && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
-        uint4 pq[ITERS];
-        uint32_t live = 0;  // bit r: row r of this thread exists
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int64_t r0 = base + it * (THREADS * 2) + tid * 2;
-            pq[it] = make_uint4(0, 0, 0, 0);
-            if (r0 + 1 < p.n) {
-                pq[it] = ldg_stream16(p.pred.col.data + r0 * 8);
-                live |= 3u << (2 * it);
-            } else if (r0 < p.n) {
-                const uint2 t = ldg_stream8(p.pred.col.data + r0 * 8);
-                pq[it].x = t.x;
-                pq[it].y = t.y;
-                live |= 1u << (2 * it);
-            }
-        }
-#define VK_FILTER_PRED_ROWS(OP)                                                                          \
-        _Pragma("unroll") for (int it = 0; it < ITERS; ++it) {                                           \
-            const uint64_t a = ((uint64_t) pq[it].y << 32) | pq[it].x, b = ((uint64_t) pq[it].w << 32) | pq[it].z; \
-            bool ok0, ok1;                                                                               \
-            if constexpr (PK == PK_F64_VEC) {                                                            \
-                const double c = __longlong_as_double((long long) p.pred.scalar.bits);                   \
-                ok0 = __longlong_as_double((long long) a) OP c;                                          \
-                ok1 = __longlong_as_double((long long) b) OP c;                                          \
-            } else {                                                                                     \
-                ok0 = (int64_t) a OP (int64_t) p.pred.scalar.bits;                                       \
-                ok1 = (int64_t) b OP (int64_t) p.pred.scalar.bits;                                       \
-            }                                                                                            \
-            pflags |= ((uint32_t) ok0 << (2 * it)) | ((uint32_t) ok1 << (2 * it + 1));                   \
-        }
-        switch (p.pred.op) {
-            case VK_EQ: VK_FILTER_PRED_ROWS(==) break;
-            case VK_NE: VK_FILTER_PRED_ROWS(!=) break;
-            case VK_GT: VK_FILTER_PRED_ROWS(>) break;
-            case VK_GE: VK_FILTER_PRED_ROWS(>=) break;
-            case VK_LT: VK_FILTER_PRED_ROWS(<) break;
-            default: VK_FILTER_PRED_ROWS(<=) break;
-        }
-#undef VK_FILTER_PRED_ROWS
-        pflags &= live;
-    }
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
-        int64_t r0 = base + it * (THREADS * 2) + tid * 2;
+        const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
         bool f0, f1;
-        if constexpr (BATCH != 0 && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
-            f0 = (pflags >> (2 * it)) & 1u;
-            f1 = (pflags >> (2 * it + 1)) & 1u;
-        } else if constexpr (KEEP && (PK == PK_F64_VEC || PK == PK_I64_VEC)) {
+        if constexpr (STAGE) {
             f0 = f1 = false;
+            uint4 q = make_uint4(0, 0, 0, 0);
             if (r0 + 1 < p.n) {
-                const uint4 q = ldg_stream16(p.pred.col.data + r0 * 8);
-                praw[it] = q;
-                if constexpr (PK == PK_F64_VEC) {
-                    const double c = __longlong_as_double((long long) p.pred.scalar.bits);
-                    f0 = apply_cmp(p.pred.op, __hiloint2double(q.y, q.x), c);
-                    f1 = apply_cmp(p.pred.op, __hiloint2double(q.w, q.z), c);
-                } else {
-                    f0 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.y << 32) | q.x), (int64_t) p.pred.scalar.bits);
-                    f1 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.w << 32) | q.z), (int64_t) p.pred.scalar.bits);
-                }
+                q = ldg_stream16(p.pred.col.data + r0 * 8);
+            } else if (r0 < p.n) {  // last, unpaired row of the batch
+                const uint2 h = *reinterpret_cast<const uint2*>(p.pred.col.data + r0 * 8);
+                q.x = h.x;
+                q.y = h.y;
+            }
+            s_pred[it * FT_THREADS + tid] = q;
+            if constexpr (PK == PK_F64_VEC) {
+                const double c = __longlong_as_double((long long) p.pred.scalar.bits);
+                if (r0 < p.n) f0 = apply_cmp(p.pred.op, __hiloint2double(q.y, q.x), c);
+                if (r0 + 1 < p.n) f1 = apply_cmp(p.pred.op, __hiloint2double(q.w, q.z), c);
             } else {
-                praw[it] = make_uint4(0, 0, 0, 0);
-                if (r0 < p.n) {  // last, unpaired row of the batch
-                    const uint2 q = *reinterpret_cast<const uint2*>(p.pred.col.data + r0 * 8);
-                    praw[it].x = q.x;
-                    praw[it].y = q.y;
-                    if constexpr (PK == PK_F64_VEC)
-                        f0 = apply_cmp(p.pred.op, __hiloint2double(q.y, q.x), __longlong_as_double((long long) p.pred.scalar.bits));
-                    else
-                        f0 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.y << 32) | q.x), (int64_t) p.pred.scalar.bits);
-                }
+                const int64_t c = (int64_t) p.pred.scalar.bits;
+                if (r0 < p.n) f0 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.y << 32) | q.x), c);
+                if (r0 + 1 < p.n) f1 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.w << 32) | q.z), c);
             }
         } else {
             pred_pair<PK>(p.pred, r0, p.n, f0, f1);
@@ -340,43 +286,17 @@ __global__ void __launch_bounds__(THREADS) filter_kernel(const __grid_constant__
         unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
         lane_off[it] = __popc(b0 & lt) + __popc(b1 & lt);
         flags |= ((uint32_t) f0 << (2 * it)) | ((uint32_t) f1 << (2 * it + 1));
-        if (lane == 0) s_cnt[it * (THREADS / 32) + warp] = __popc(b0) + __popc(b1);
-    }
-    // (BATCH) a selected pair's 16 bytes of column c; flags are clear for rows past the end
-    uint4 qa[BATCH ? ITERS : 1], qb[BATCH == 2 ? ITERS : 1];
-    auto load_col = [&](int c, uint4 (&q)[BATCH ? ITERS : 1]) {
-        const uint8_t* d = p.cols[c].data;
-#pragma unroll
-        for (int it = 0; it < (BATCH ? ITERS : 0); ++it) {
-            const int64_t r0 = base + it * (THREADS * 2) + tid * 2;
-            q[it] = make_uint4(0, 0, 0, 0);
-            if ((flags >> (2 * it)) & 3u) {
-                if (r0 + 1 < p.n) {
-                    q[it] = ldg_stream16(d + r0 * 8);
-                } else {  // last, unpaired row of the batch
-                    const uint2 t = ldg_stream8(d + r0 * 8);
-                    q[it].x = t.x;
-                    q[it].y = t.y;
-                }
-            }
-        }
-    };
-    if constexpr (BATCH != 0) {
-        if (p.n_cols > 0) load_col(0, qa);
+        if (lane == 0) s_cnt[it * (FT_THREADS / 32) + warp] = __popc(b0) + __popc(b1);
     }
     __syncthreads();
 
     // ---- block scan of the (iter, warp) counts + decoupled look-back (warp 0) ----
     if (warp == 0) {
         uint32_t c[PER_LANE], mine = 0;
-        if constexpr (NCNT >= 32) {
 #pragma unroll
-            for (int e = 0; e < PER_LANE; ++e) {
-                c[e] = s_cnt[lane * PER_LANE + e];
-                mine += c[e];
-            }
-        } else {
-            c[0] = mine = lane < NCNT ? s_cnt[lane] : 0u;   // fewer counts than lanes
+        for (int e = 0; e < PER_LANE; ++e) {
+            c[e] = s_cnt[lane * PER_LANE + e];
+            mine += c[e];
         }
         uint32_t inc = mine;
 #pragma unroll
@@ -385,14 +305,10 @@ __global__ void __launch_bounds__(THREADS) filter_kernel(const __grid_constant__
             if (lane >= d) inc += t;
         }
         uint32_t run = inc - mine;  // exclusive offset of this lane's first (iter, warp) entry inside the tile
-        if constexpr (NCNT >= 32) {
 #pragma unroll
-            for (int e = 0; e < PER_LANE; ++e) {
-                s_cnt[lane * PER_LANE + e] = run;
-                run += c[e];
-            }
-        } else {
-            if (lane < NCNT) s_cnt[lane] = run;
+        for (int e = 0; e < PER_LANE; ++e) {
+            s_cnt[lane * PER_LANE + e] = run;
+            run += c[e];
         }
         uint64_t total = __shfl_sync(0xffffffffu, inc, 31);
         uint64_t excl = 0;
@@ -428,443 +344,46 @@ __global__ void __launch_bounds__(THREADS) filter_kernel(const __grid_constant__
     const int64_t tile_excl = s_excl;
 
     // ---- phase 2: scatter every column; a warp writes one contiguous run per iter ----
-    if constexpr (BATCH != 0) {
+    for (int c = 0; c < p.n_cols; ++c) {
+        const Col col = p.cols[c];
+        const int es = dtype_size(col.dtype);
+        uint8_t* outv = p.out_valid[c];
+        const bool vec16 = (es == 8) && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0);
+        const bool staged = STAGE && es == 8 && col.data == p.pred.col.data;
 #pragma unroll
-        for (int it = 0; it < ITERS; ++it) lane_off[it] += s_cnt[it * (THREADS / 32) + warp];
-        auto store_col = [&](int c, const uint4 (&q)[ITERS]) {
-            uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const uint32_t f = (flags >> (2 * it)) & 3u;
-                if (f == 0) continue;
-                int64_t pos = tile_excl + lane_off[it];
-                if (f & 1) o[pos++] = ((uint64_t) q[it].y << 32) | q[it].x;
-                if (f & 2) o[pos] = ((uint64_t) q[it].w << 32) | q[it].z;
-            }
-        };
-        if constexpr (BATCH == 1) {
-            for (int c = 0; c < p.n_cols; ++c) {
-                if (c > 0) load_col(c, qa);
-                store_col(c, qa);
-            }
-        } else {
-            int c = 0;
-            while (c < p.n_cols) {
-                if (c + 1 < p.n_cols) load_col(c + 1, qb);
-                store_col(c, qa);
-                if (++c >= p.n_cols) break;
-                if (c + 1 < p.n_cols) load_col(c + 1, qa);
-                store_col(c, qb);
-                ++c;
-            }
-        }
-    } else {
-        for (int c = 0; c < p.n_cols; ++c) {
-            const Col col = p.cols[c];
-            const int es = dtype_size(col.dtype);
-            uint8_t* outv = p.out_valid[c];
-            const bool vec16 = (es == 8) && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0);
-            const bool from_regs = KEEP && (PK == PK_F64_VEC || PK == PK_I64_VEC) && es == 8 && col.data == p.pred.col.data;
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const uint32_t f = (flags >> (2 * it)) & 3u;
-                if (f == 0) continue;
-                const int64_t r0 = base + it * (THREADS * 2) + tid * 2;
-                int64_t pos = tile_excl + s_cnt[it * (THREADS / 32) + warp] + lane_off[it];
-                if (es == 8) {
-                    uint64_t v0, v1;
-                    if (from_regs) {
-                        const uint4 q = praw[KEEP ? it : 0];
-                        v0 = ((uint64_t) q.y << 32) | q.x;
-                        v1 = ((uint64_t) q.w << 32) | q.z;
-                    } else if (vec16 && r0 + 1 < p.n) {
-                        uint4 q = ldg_stream16(col.data + r0 * 8);
-                        v0 = ((uint64_t) q.y << 32) | q.x;
-                        v1 = ((uint64_t) q.w << 32) | q.z;
-                    } else {
-                        v0 = (f & 1) ? reinterpret_cast<const uint64_t*>(col.data)[r0] : 0;
-                        v1 = (f & 2) ? reinterpret_cast<const uint64_t*>(col.data)[r0 + 1] : 0;
-                    }
-                    uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
-                    if (f & 1) o[pos++] = v0;
-                    if (f & 2) o[pos] = v1;
-                } else {
-                    int64_t q = pos;
-                    if (f & 1) store_from_u64(p.out_data[c], col.dtype, q++, load_as_u64(col, r0));
-                    if (f & 2) store_from_u64(p.out_data[c], col.dtype, q, load_as_u64(col, r0 + 1));
-                }
-                if (outv != nullptr) {
-                    int64_t q = tile_excl + s_cnt[it * (THREADS / 32) + warp] + lane_off[it];
-                    if (f & 1) outv[q++] = col_valid(col, r0);
-                    if (f & 2) outv[q] = col_valid(col, r0 + 1);
-                }
-            }
-        }
-    }
-}
-
-// ---- TMA-staged variant ---------------------------------------------------------------------
-// The tile's slice of the predicate column and of up to CB payload columns is moved into shared
-// memory by the TMA unit (cp.async.bulk, one 16 KB copy per column issued by one thread, each
-// signalling its own mbarrier): nothing is staged in registers, every byte of the tile is in
-// flight at once, and the copies land while the predicate is evaluated and the look-back runs.
-// The scatter then reads shared memory (lane-contiguous 16-byte reads, conflict free).  Columns
-// beyond CB reuse the buffers round by round; an output column that is the predicate column itself
-// is scattered straight from the predicate slice (no second read of it, unlike filter_kernel, where
-// keeping it costs registers and occupancy).  Same eligibility as BATCH; the ragged last tile is
-// staged with ordinary loads.  Opt-in (VINUM_B200_FILTER_CFG 16: CB = 4, 32: CB = 2), unmeasured.
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done != 0;
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-template <int PK, int ITERS, int CB>
-__global__ void __launch_bounds__(FT_THREADS) filter_tma_kernel(const __grid_constant__ FilterParams p) {
-    static_assert(PK == PK_MASK || PK == PK_F64_VEC || PK == PK_I64_VEC, "predicates that stage as one contiguous slice");
-    constexpr int TILE = FT_THREADS * 2 * ITERS;
-    constexpr int NCNT = ITERS * (FT_THREADS / 32);
-    constexpr int PER_LANE = NCNT / 32;
-    constexpr uint32_t COL_BYTES = TILE * 8;
-    constexpr uint32_t PRED_BYTES = PK == PK_MASK ? TILE : TILE * 8;
-    extern __shared__ __align__(128) uint8_t ft_smem[];   // [predicate slice | CB column slices]
-    __shared__ __align__(8) uint64_t s_bar[1 + CB];
-    __shared__ int64_t s_tile;
-    __shared__ uint32_t s_cnt[NCNT];
-    __shared__ int64_t s_excl;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t a_pred = (uint32_t) __cvta_generic_to_shared(ft_smem);
-    const uint32_t a_col0 = a_pred + COL_BYTES;
-    const uint32_t a_bar = (uint32_t) __cvta_generic_to_shared(s_bar);
-    if (tid == 0) {
-        s_tile = (int64_t) atomicAdd(p.ticket, 1ULL);
-        for (int b = 0; b <= CB; ++b) mbar_init(a_bar + 8 * b, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int64_t tile = s_tile;
-    const int64_t base = tile * TILE;
-    const int rows = (int) (p.n - base < TILE ? p.n - base : TILE);
-    const bool full = rows == TILE;
-    const uint8_t* pred_src = PK == PK_MASK ? p.pred.mask + base : p.pred.col.data + base * 8;
-
-    // an output column that IS the predicate column is scattered from the predicate slice: no second read
-    auto is_pred_col = [&](int c) { return PK != PK_MASK && p.cols[c].data == p.pred.col.data; };
-    // stage round g (columns g*CB ...): TMA for complete tiles, plain loads for the ragged last one
-    auto stage_cols = [&](int g) {
-        const int c0 = g * CB;
-        if (full) {
-            if (tid == 0) {
-                for (int k = 0; k < CB && c0 + k < p.n_cols; ++k) {
-                    if (is_pred_col(c0 + k)) continue;
-                    mbar_arrive_expect_tx(a_bar + 8 * (1 + k), COL_BYTES);
-                    tma_load_1d(a_col0 + k * COL_BYTES, p.cols[c0 + k].data + base * 8, COL_BYTES, a_bar + 8 * (1 + k));
-                }
-            }
-        } else {
-            for (int k = 0; k < CB && c0 + k < p.n_cols; ++k) {
-                if (is_pred_col(c0 + k)) continue;
-                const uint64_t* src = reinterpret_cast<const uint64_t*>(p.cols[c0 + k].data) + base;
-                uint64_t* dst = reinterpret_cast<uint64_t*>(ft_smem + COL_BYTES + (size_t) k * COL_BYTES);
-                for (int i = tid; i < rows; i += FT_THREADS) dst[i] = src[i];
-            }
-        }
-    };
-    if (full) {
-        if (tid == 0) {
-            mbar_arrive_expect_tx(a_bar, PRED_BYTES);
-            tma_load_1d(a_pred, pred_src, PRED_BYTES, a_bar);
-        }
-    } else {
-        if constexpr (PK == PK_MASK) {
-            for (int i = tid; i < rows; i += FT_THREADS) ft_smem[i] = pred_src[i];
-        } else {
-            for (int i = tid; i < rows; i += FT_THREADS)
-                reinterpret_cast<uint64_t*>(ft_smem)[i] = reinterpret_cast<const uint64_t*>(pred_src)[i];
-        }
-    }
-    stage_cols(0);
-    if (full) {
-        while (!mbar_try_wait(a_bar, 0)) {}
-    } else {
-        __syncthreads();
-    }
-
-    // ---- phase 1: predicate from shared memory ----
-    uint32_t flags = 0;
-    uint32_t lane_off[ITERS];
-    const unsigned lt = lanemask_lt();
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        const int e = it * (FT_THREADS * 2) + tid * 2;   // row of the tile
-        bool f0 = false, f1 = false;
-        if constexpr (PK == PK_MASK) {
-            uint32_t m;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(m) : "r"(a_pred + e) : "memory");
-            f0 = (m & 0xffu) != 0;
-            f1 = (m >> 8) != 0;
-        } else {
-            uint4 q;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a_pred + e * 8) : "memory");
-            const uint64_t a = ((uint64_t) q.y << 32) | q.x, b = ((uint64_t) q.w << 32) | q.z;
-            if constexpr (PK == PK_F64_VEC) {
-                const double c = __longlong_as_double((long long) p.pred.scalar.bits);
-                f0 = apply_cmp(p.pred.op, __longlong_as_double((long long) a), c);
-                f1 = apply_cmp(p.pred.op, __longlong_as_double((long long) b), c);
-            } else {
-                f0 = apply_cmp(p.pred.op, (int64_t) a, (int64_t) p.pred.scalar.bits);
-                f1 = apply_cmp(p.pred.op, (int64_t) b, (int64_t) p.pred.scalar.bits);
-            }
-        }
-        f0 = f0 && e < rows;
-        f1 = f1 && e + 1 < rows;
-        const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
-        lane_off[it] = __popc(b0 & lt) + __popc(b1 & lt);
-        flags |= ((uint32_t) f0 << (2 * it)) | ((uint32_t) f1 << (2 * it + 1));
-        if (lane == 0) s_cnt[it * (FT_THREADS / 32) + warp] = __popc(b0) + __popc(b1);
-    }
-    __syncthreads();
-
-    // ---- block scan of the (iter, warp) counts + decoupled look-back (warp 0), as in filter_kernel ----
-    if (warp == 0) {
-        uint32_t c[PER_LANE], mine = 0;
-#pragma unroll
-        for (int e = 0; e < PER_LANE; ++e) {
-            c[e] = s_cnt[lane * PER_LANE + e];
-            mine += c[e];
-        }
-        uint32_t inc = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        uint32_t run = inc - mine;
-#pragma unroll
-        for (int e = 0; e < PER_LANE; ++e) {
-            s_cnt[lane * PER_LANE + e] = run;
-            run += c[e];
-        }
-        const uint64_t total = __shfl_sync(0xffffffffu, inc, 31);
-        uint64_t excl = 0;
-        if (tile == 0) {
-            if (lane == 0) st_status(p.status, ST_PREFIX | total);
-        } else {
-            if (lane == 0) st_status(p.status + tile, ST_AGG | total);
-            int64_t look = tile - 1;
-            while (true) {
-                const int64_t idx = look - lane;
-                unsigned long long st = ST_PREFIX;  // virtual tile -1: prefix 0
-                if (idx >= 0) {
-                    do { st = ld_status(p.status + idx); } while ((st >> ST_FLAG_SHIFT) == 0);
-                }
-                const unsigned is_prefix = __ballot_sync(0xffffffffu, (st >> ST_FLAG_SHIFT) == 2 || idx < 0);
-                const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
-                uint64_t v = (lane <= first) ? (st & ST_VALUE_MASK) : 0;
-                if (idx < 0) v = 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                excl += v;
-                if (is_prefix) break;
-                look -= 32;
-            }
-            if (lane == 0) st_status(p.status + tile, ST_PREFIX | (excl + total));
-        }
-        if (lane == 0) {
-            s_excl = (int64_t) excl;
-            if (tile == p.num_tiles - 1) *p.out_rows = (int64_t) (excl + total);
-        }
-    }
-    __syncthreads();
-    const int64_t tile_excl = s_excl;
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) lane_off[it] += s_cnt[it * (FT_THREADS / 32) + warp];
-
-    // ---- phase 2: scatter from shared memory, CB columns per round ----
-    // (a buffer's mbarrier only advances in the rounds that stage a column into it: its parity is tracked)
-    uint32_t phase[CB];
-#pragma unroll
-    for (int k = 0; k < CB; ++k) phase[k] = 0;
-    const int rounds = (p.n_cols + CB - 1) / CB;
-    for (int g = 0; g < rounds; ++g) {
-        for (int k = 0; k < CB && g * CB + k < p.n_cols; ++k) {
-            const bool from_pred = is_pred_col(g * CB + k);
-            if (full && !from_pred) {
-                while (!mbar_try_wait(a_bar + 8 * (1 + k), phase[k])) {}
-                phase[k] ^= 1u;
-            }
-            uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[g * CB + k]);
-            const uint32_t a_col = from_pred ? a_pred : a_col0 + k * COL_BYTES;
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const uint32_t f = (flags >> (2 * it)) & 3u;
-                if (f == 0) continue;
-                const int e = it * (FT_THREADS * 2) + tid * 2;
-                uint4 q;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(a_col + e * 8) : "memory");
-                int64_t pos = tile_excl + lane_off[it];
-                if (f & 1) o[pos++] = ((uint64_t) q.y << 32) | q.x;
-                if (f & 2) o[pos] = ((uint64_t) q.w << 32) | q.z;
-            }
-        }
-        if (g + 1 < rounds) {
-            __syncthreads();   // every thread has read this round's slices
-            if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
-            stage_cols(g + 1);
-            if (!full) __syncthreads();
-        }
-    }
-}
-
-// ---- split variant: flags + counts, scan, one scatter per column ---------------------------------
-// The single-pass kernels keep about nine DRAM streams open at once (predicate + every column read, every
-// column written at data-dependent offsets) and chain the tiles through the look-back.  This variant
-// evaluates the predicate once into ONE BIT PER ROW (the warp ballots, 12.5 MB per 1e8 rows) plus a count
-// per tile, scans the tile counts, and then compacts the columns one launch per column: two or three
-// streams at a time, every tile independent.  Costs 1/64 of the predicate column in flag traffic.
-// Opt-in (VINUM_B200_FILTER_CFG 256: one launch per column, 512: one launch, blockIdx.y = column), unmeasured.
-constexpr int FS_ITERS = 4;
-constexpr int FS_TILE = FT_THREADS * 2 * FS_ITERS;              // 2048 rows
-constexpr int FS_WORDS = FS_ITERS * (FT_THREADS / 32) * 2;      // 64 ballot words per tile
-
-struct SplitParams {
-    Pred pred;
-    int64_t n;
-    int64_t num_tiles;
-    uint32_t* flags;          // [tiles][FS_WORDS]: ballots (b0, b1) of (iteration, warp)
-    uint32_t* tile_count;     // [tiles] selected rows per tile
-    int64_t* tile_offset;     // [tiles] exclusive prefix (written by the scan)
-    int64_t* out_rows;
-    int n_cols;
-    Col cols[FT_MAX_COLS];
-    void* out_data[FT_MAX_COLS];
-};
-
-template <int PK>
-__global__ void __launch_bounds__(FT_THREADS) filter_flags_kernel(const __grid_constant__ SplitParams p) {
-    __shared__ uint32_t s_cnt[FT_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int64_t base = tile * FS_TILE;
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int it = 0; it < FS_ITERS; ++it) {
-            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
-            bool f0, f1;
-            pred_pair<PK>(p.pred, r0, p.n, f0, f1);
-            const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
-            if (lane == 0) {
-                uint32_t* w = p.flags + tile * FS_WORDS + (it * (FT_THREADS / 32) + warp) * 2;
-                w[0] = b0;
-                w[1] = b1;
-            }
-            cnt += __popc(b0) + __popc(b1);
-        }
-        if (lane == 0) s_cnt[warp] = cnt;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t t = 0;
-#pragma unroll
-            for (int w = 0; w < FT_THREADS / 32; ++w) t += s_cnt[w];
-            p.tile_count[tile] = t;
-        }
-        __syncthreads();
-    }
-}
-
-// exclusive scan of the tile counts (one CTA; 48 828 tiles per 1e8 rows)
-__global__ void __launch_bounds__(1024) filter_scan_kernel(const __grid_constant__ SplitParams p) {
-    __shared__ int64_t s_warp[32];
-    __shared__ int64_t s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int64_t t0 = 0; t0 < p.num_tiles; t0 += 1024) {
-        const int64_t t = t0 + tid;
-        const int64_t v = t < p.num_tiles ? (int64_t) p.tile_count[t] : 0;
-        int64_t inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int64_t o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            int64_t w = s_warp[lane], winc = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int64_t o = __shfl_up_sync(0xffffffffu, winc, d);
-                if (lane >= d) winc += o;
-            }
-            s_warp[lane] = winc - w;   // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const int64_t carry = s_carry;
-        if (t < p.num_tiles) p.tile_offset[t] = carry + s_warp[warp] + inc - v;
-        __syncthreads();
-        if (tid == 1023) s_carry = carry + s_warp[warp] + inc;
-        __syncthreads();
-    }
-    if (tid == 0) *p.out_rows = s_carry;
-}
-
-// one column (blockIdx.y, or column0 + blockIdx.y) of one tile per CTA
-__global__ void __launch_bounds__(FT_THREADS) filter_scatter_kernel(const __grid_constant__ SplitParams p, int column0) {
-    __shared__ uint32_t s_flags[FS_WORDS];
-    __shared__ uint32_t s_pre[FS_WORDS / 2];     // selected rows before (iteration, warp) inside the tile
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = column0 + blockIdx.y;
-    const Col col = p.cols[c];
-    const int es = dtype_size(col.dtype);
-    const unsigned lt = lanemask_lt();
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int64_t base = tile * FS_TILE;
-        if (tid < FS_WORDS) s_flags[tid] = p.flags[tile * FS_WORDS + tid];
-        __syncthreads();
-        if (warp == 0) {   // exclusive scan of the 32 (iteration, warp) counts
-            const uint32_t mine = __popc(s_flags[2 * lane]) + __popc(s_flags[2 * lane + 1]);
-            uint32_t inc = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            s_pre[lane] = inc - mine;
-        }
-        __syncthreads();
-        const int64_t tile_excl = p.tile_offset[tile];
-#pragma unroll
-        for (int it = 0; it < FS_ITERS; ++it) {
-            const int slot = it * (FT_THREADS / 32) + warp;
-            const uint32_t b0 = s_flags[2 * slot], b1 = s_flags[2 * slot + 1];
-            const uint32_t f = ((b0 >> lane) & 1u) | (((b1 >> lane) & 1u) << 1);
+        for (int it = 0; it < ITERS; ++it) {
+            const uint32_t f = (flags >> (2 * it)) & 3u;
             if (f == 0) continue;
             const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
-            int64_t pos = tile_excl + s_pre[slot] + __popc(b0 & lt) + __popc(b1 & lt);
-            if (es == 8 && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0) && r0 + 1 < p.n) {
-                const uint4 q = ldg_stream16(col.data + r0 * 8);
+            int64_t pos = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
+            if (es == 8) {
+                uint64_t v0, v1;
+                if (staged) {
+                    const uint4 q = s_pred[STAGE ? it * FT_THREADS + tid : 0];
+                    v0 = ((uint64_t) q.y << 32) | q.x;
+                    v1 = ((uint64_t) q.w << 32) | q.z;
+                } else if (vec16 && r0 + 1 < p.n) {
+                    uint4 q = ldg_stream16(col.data + r0 * 8);
+                    v0 = ((uint64_t) q.y << 32) | q.x;
+                    v1 = ((uint64_t) q.w << 32) | q.z;
+                } else {
+                    v0 = (f & 1) ? reinterpret_cast<const uint64_t*>(col.data)[r0] : 0;
+                    v1 = (f & 2) ? reinterpret_cast<const uint64_t*>(col.data)[r0 + 1] : 0;
+                }
                 uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
-                if (f & 1) o[pos++] = ((uint64_t) q.y << 32) | q.x;
-                if (f & 2) o[pos] = ((uint64_t) q.w << 32) | q.z;
+                if (f & 1) o[pos++] = v0;
+                if (f & 2) o[pos] = v1;
             } else {
-                if (f & 1) store_from_u64(p.out_data[c], col.dtype, pos++, load_as_u64(col, r0));
-                if (f & 2) store_from_u64(p.out_data[c], col.dtype, pos, load_as_u64(col, r0 + 1));
+                int64_t q = pos;
+                if (f & 1) store_from_u64(p.out_data[c], col.dtype, q++, load_as_u64(col, r0));
+                if (f & 2) store_from_u64(p.out_data[c], col.dtype, q, load_as_u64(col, r0 + 1));
+            }
+            if (outv != nullptr) {
+                int64_t q = tile_excl + s_cnt[it * (FT_THREADS / 32) + warp] + lane_off[it];
+                if (f & 1) outv[q++] = col_valid(col, r0);
+                if (f & 2) outv[q] = col_valid(col, r0 + 1);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -886,8 +405,7 @@ static int launch_compare(const CmpParams& p, int64_t n, uint8_t* out, VkStream 
     VK_REQUIRE(out, "compare: out_mask is NULL");
     int g = grid_for((n + 3) / 4);
     cudaStream_t s = (cudaStream_t) stream;
-    static int fast = -1;  // row pairs per thread of compare8_kernel (0: off; 2 measured best, 4 is slower than off)
-    if (fast < 0) { const char* v = getenv("VINUM_B200_CMP_FAST"); fast = v ? atoi(v) : 2; }
+    const int fast = (int) opt(OPT_CMP_FAST);  // 2: compare8_kernel (two row pairs per thread), 0: compare_kernel
     auto plain8 = [&](const Col& c) {
         const int want = p.domain == DOM_F64 ? VK_F64 : (p.domain == DOM_I64 ? VK_I64 : (p.domain == DOM_U64 ? VK_U64 : -1));
         return c.dtype == want && c.validity == nullptr && !c.nan_nulls && (reinterpret_cast<uintptr_t>(c.data) & 15) == 0;
@@ -895,10 +413,7 @@ static int launch_compare(const CmpParams& p, int64_t n, uint8_t* out, VkStream 
     if (fast >= 2 && plain8(p.lhs) && (p.mode != 1 || plain8(p.rhs)) && (reinterpret_cast<uintptr_t>(out) & 1) == 0) {
         const int gp = grid_for((n / 2 + 3) / 4);
 #define VK_CMP8_GO(DOM)                                                             \
-        do {                                                                        \
-            if (fast >= 4) compare8_kernel<DOM, 4><<<gp, 256, 0, s>>>(p, n, out);   \
-            else compare8_kernel<DOM, 2><<<gp, 256, 0, s>>>(p, n, out);             \
-        } while (0)
+        compare8_kernel<DOM, 2><<<gp, 256, 0, s>>>(p, n, out)
         switch (p.domain) {
             case DOM_I64: VK_CMP8_GO(DOM_I64); break;
             case DOM_U64: VK_CMP8_GO(DOM_U64); break;
@@ -1066,75 +581,10 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         VK_REQUIRE(cols[c].validity == nullptr || (out_valid_bytes && out_valid_bytes[c]),
                    "vk_filter: column has validity but no out_valid_bytes buffer");
     }
-    // geometry: row pairs per thread / keep the predicate column in registers (measured, profiles/)
-    static int cfg = -1;
-    if (cfg < 0) { const char* v = getenv("VINUM_B200_FILTER_CFG"); cfg = v ? atoi(v) : 0; }
-    // bit 0: 4096-row tiles; bit 1: keep the predicate column; bits 2-3: batched scatter (1 or 2, see
-    // filter_kernel) when every column of the pass qualifies; 16 / 32: TMA-staged tiles (filter_tma_kernel);
-    // 64 / 128: small tiles; 256 / 512: split variant (flags + scan + one scatter per column)
-    const int iters = (cfg & 1) ? 8 : 4;
-    const int batch_cfg = (cfg >> 2) & 3;
-    const bool keep = (cfg & 2) != 0 && batch_cfg == 0;
-    // 64: 128-thread CTAs (1024-row tiles, 16 CTAs/SM); 128: two row pairs per thread (1024-row tiles);
-    // 192: both (512-row tiles).  Opt-in, unmeasured: the plain (BATCH 0, KEEP off) kernel only.
-    const int small = (cfg >> 6) & 3;
-    const int threads = (small & 1) ? 128 : FT_THREADS;
-    const int iters_eff = small ? ((small & 2) ? 2 : 4) : iters;
-    const int tile_rows = threads * 2 * iters_eff;
+    // geometry (measured, profiles/r02_variants.md): 2048-row tiles, 8 CTAs per SM
+    const int iters = opt(OPT_FILTER_ITERS) == 8 ? 8 : 4;
+    const int tile_rows = FT_THREADS * 2 * iters;
     const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
-    // ---- split variant (cfg 256 / 512): flags + counts, scan, one scatter per column ----
-    if (cfg & (256 | 512)) {
-        bool plain = true;
-        for (int c = 0; c < n_cols; ++c) plain = plain && cols[c].validity == nullptr;
-        if (plain) {
-            const int64_t stiles = (n_rows + FS_TILE - 1) / FS_TILE;
-            uint32_t* d_flags = nullptr;
-            uint32_t* d_count = nullptr;
-            int64_t* d_offset = nullptr;
-            VK_CUDA(cudaMallocAsync((void**) &d_flags, (size_t) stiles * FS_WORDS * sizeof(uint32_t), s));
-            VK_CUDA(cudaMallocAsync((void**) &d_count, (size_t) stiles * sizeof(uint32_t), s));
-            VK_CUDA(cudaMallocAsync((void**) &d_offset, (size_t) stiles * sizeof(int64_t), s));
-            SplitParams sp{};
-            sp.pred = dp;
-            sp.n = n_rows;
-            sp.num_tiles = stiles;
-            sp.flags = d_flags;
-            sp.tile_count = d_count;
-            sp.tile_offset = d_offset;
-            sp.out_rows = out_rows;
-            const int64_t cap = (int64_t) sm_count() * 8;
-            const unsigned gx = (unsigned) (stiles < cap ? stiles : cap);
-            switch (pk) {
-                case PK_MASK: filter_flags_kernel<PK_MASK><<<gx, FT_THREADS, 0, s>>>(sp); break;
-                case PK_F64_VEC: filter_flags_kernel<PK_F64_VEC><<<gx, FT_THREADS, 0, s>>>(sp); break;
-                case PK_I64_VEC: filter_flags_kernel<PK_I64_VEC><<<gx, FT_THREADS, 0, s>>>(sp); break;
-                default: filter_flags_kernel<PK_GENERIC><<<gx, FT_THREADS, 0, s>>>(sp); break;
-            }
-            VK_CHECK_LAUNCH("filter_flags_kernel");
-            filter_scan_kernel<<<1, 1024, 0, s>>>(sp);
-            VK_CHECK_LAUNCH("filter_scan_kernel");
-            for (int g0 = 0; g0 < n_cols; g0 += FT_MAX_COLS) {
-                sp.n_cols = (n_cols - g0 < FT_MAX_COLS) ? n_cols - g0 : FT_MAX_COLS;
-                for (int c = 0; c < sp.n_cols; ++c) {
-                    sp.cols[c] = make_col(cols[g0 + c]);
-                    sp.out_data[c] = out_data[g0 + c];
-                }
-                if (cfg & 512) {
-                    filter_scatter_kernel<<<dim3(gx, (unsigned) sp.n_cols), FT_THREADS, 0, s>>>(sp, 0);
-                    VK_CHECK_LAUNCH("filter_scatter_kernel");
-                } else {
-                    for (int c = 0; c < sp.n_cols; ++c) {
-                        filter_scatter_kernel<<<dim3(gx, 1), FT_THREADS, 0, s>>>(sp, c);
-                        VK_CHECK_LAUNCH("filter_scatter_kernel");
-                    }
-                }
-            }
-            VK_CUDA(cudaFreeAsync(d_flags, s));
-            VK_CUDA(cudaFreeAsync(d_count, s));
-            VK_CUDA(cudaFreeAsync(d_offset, s));
-            return VK_OK;
-        }
-    }
     // columns are processed FT_MAX_COLS at a time; each pass re-evaluates the predicate
     int c0 = 0;
     do {
@@ -1142,75 +592,32 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         p.pred = dp;
         p.n = n_rows;
         p.n_cols = (n_cols - c0 < FT_MAX_COLS) ? n_cols - c0 : FT_MAX_COLS;
+        bool pred_is_output = false;
         for (int c = 0; c < p.n_cols; ++c) {
             p.cols[c] = make_col(cols[c0 + c]);
             p.out_data[c] = out_data[c0 + c];
             p.out_valid[c] = (cols[c0 + c].validity && out_valid_bytes) ? out_valid_bytes[c0 + c] : nullptr;
+            if ((pk == PK_F64_VEC || pk == PK_I64_VEC) && p.cols[c].data == dp.col.data && dtype_size(p.cols[c].dtype) == 8)
+                pred_is_output = true;
         }
-        // every column 8 bytes wide, 16-byte aligned, without a validity bitmap (BATCH and TMA variants)
-        bool batch_ok = true;
-        for (int c = 0; c < p.n_cols && batch_ok; ++c)
-            if (dtype_size(p.cols[c].dtype) != 8 || p.out_valid[c] != nullptr ||
-                ((reinterpret_cast<uintptr_t>(p.cols[c].data) | reinterpret_cast<uintptr_t>(p.out_data[c])) & 7) != 0 ||
-                (reinterpret_cast<uintptr_t>(p.cols[c].data) & 15) != 0)
-                batch_ok = false;
-        const int batch = batch_ok ? (batch_cfg > 2 ? 2 : batch_cfg) : 0;
         p.out_rows = out_rows;
         p.ticket = reinterpret_cast<unsigned long long*>(scratch);
         p.status = p.ticket + 1;
         p.num_tiles = tiles;
-        {
-            static int pf = -1;
-            if (pf < 0) { const char* v = getenv("VINUM_B200_FILTER_PF"); pf = v ? atoi(v) : 1; }
-            p.pf = pf;
-        }
+        p.pf = (int) opt(OPT_FILTER_PF);
+        const bool stage = pred_is_output && opt(OPT_FILTER_STAGE) != 0 && iters == 4;
         VK_CUDA(cudaMemsetAsync(scratch, 0, vk_filter_scratch_bytes(n_rows), s));
-        // TMA-staged variant (cfg 16 / 32): same column eligibility as the batched scatter
-        const int tma_cb = (cfg & 16) ? 4 : ((cfg & 32) ? 2 : 0);
-        if (tma_cb && !small && batch_ok && iters == 4 && (pk == PK_F64_VEC || pk == PK_I64_VEC ||
-            (pk == PK_MASK && (reinterpret_cast<uintptr_t>(p.pred.mask) & 15) == 0))) {
-            const size_t smem = (size_t) FT_THREADS * 2 * 4 * 8 * (1 + tma_cb);
-#define VK_FILTER_TMA_GO(PK)                                                                          \
-            do {                                                                                          \
-                if (tma_cb == 4) {                                                                        \
-                    VK_CUDA(cudaFuncSetAttribute(filter_tma_kernel<PK, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-                    filter_tma_kernel<PK, 4, 4><<<(unsigned) tiles, FT_THREADS, smem, s>>>(p);            \
-                } else {                                                                                  \
-                    VK_CUDA(cudaFuncSetAttribute(filter_tma_kernel<PK, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-                    filter_tma_kernel<PK, 4, 2><<<(unsigned) tiles, FT_THREADS, smem, s>>>(p);            \
-                }                                                                                         \
-            } while (0)
-            if (pk == PK_MASK) VK_FILTER_TMA_GO(PK_MASK);
-            else if (pk == PK_F64_VEC) VK_FILTER_TMA_GO(PK_F64_VEC);
-            else VK_FILTER_TMA_GO(PK_I64_VEC);
-#undef VK_FILTER_TMA_GO
-            VK_CHECK_LAUNCH("filter_tma_kernel");
-            c0 += p.n_cols;
-            continue;
-        }
-#define VK_FILTER_GO(PK)                                                                              \
+#define VK_FILTER_GO(PK, STAGEABLE)                                                                   \
         do {                                                                                              \
-            if (small == 1) filter_kernel<PK, 4, false, 0, 128><<<(unsigned) tiles, 128, 0, s>>>(p);      \
-            else if (small == 2) filter_kernel<PK, 2, false, 0, 256><<<(unsigned) tiles, 256, 0, s>>>(p); \
-            else if (small == 3) filter_kernel<PK, 2, false, 0, 128><<<(unsigned) tiles, 128, 0, s>>>(p); \
-            else if (batch) {                                                                                  \
-                if (iters == 8 && batch == 2) filter_kernel<PK, 8, false, 2><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
-                else if (iters == 8) filter_kernel<PK, 8, false, 1><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
-                else if (batch == 2) filter_kernel<PK, 4, false, 2><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
-                else filter_kernel<PK, 4, false, 1><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);           \
-            } else if (iters == 8) {                                                                      \
-                if (keep) filter_kernel<PK, 8, true><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);          \
-                else filter_kernel<PK, 8, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);              \
-            } else {                                                                                      \
-                if (keep) filter_kernel<PK, 4, true><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);          \
-                else filter_kernel<PK, 4, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);              \
-            }                                                                                             \
+            if (STAGEABLE && stage) filter_kernel<PK, 4, STAGEABLE><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
+            else if (iters == 8) filter_kernel<PK, 8, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);  \
+            else filter_kernel<PK, 4, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);                  \
         } while (0)
         switch (pk) {
-            case PK_MASK: VK_FILTER_GO(PK_MASK); break;
-            case PK_F64_VEC: VK_FILTER_GO(PK_F64_VEC); break;
-            case PK_I64_VEC: VK_FILTER_GO(PK_I64_VEC); break;
-            default: VK_FILTER_GO(PK_GENERIC); break;
+            case PK_MASK: VK_FILTER_GO(PK_MASK, false); break;
+            case PK_F64_VEC: VK_FILTER_GO(PK_F64_VEC, true); break;
+            case PK_I64_VEC: VK_FILTER_GO(PK_I64_VEC, true); break;
+            default: VK_FILTER_GO(PK_GENERIC, false); break;
         }
 #undef VK_FILTER_GO
         VK_CHECK_LAUNCH("filter_kernel");

@@ -261,114 +261,6 @@ __global__ void __launch_bounds__(256) agg_onegroup8_kernel(const __grid_constan
     onegroup_flush(p.table, p.fi, acc, rows, 0, lo, hi, fsum);
 }
 
-// Every function of the query in ONE launch (the row counter included): the predicate column and each
-// distinct value column are read once -- `COUNT(*), SUM(f1) WHERE f0 > c` moves 16 B/row instead of the
-// 24 B/row of one launch per function.  Up to ONE8_MAXF functions over up to ONE8_MAXF distinct plain
-// 8-byte columns.  Opt-in (VINUM_B200_ONEGROUP_FUSED=1), unmeasured.
-constexpr int ONE8_MAXF = 4;
-struct OneMultiParams {
-    Pred pred;
-    int n_funcs, n_cols;
-    FuncSpec spec[ONE8_MAXF];
-    int fi[ONE8_MAXF];         // function index in the table
-    int col_of[ONE8_MAXF];     // index into col[] (-1: the function needs no value, e.g. COUNT)
-    Col col[ONE8_MAXF];
-    int64_t n;
-    GTable table;
-};
-
-template <int PK, int U>
-__global__ void __launch_bounds__(256) agg_onegroup8_multi_kernel(const __grid_constant__ OneMultiParams p) {
-    static_assert(PK == PK_NONE || PK == PK_F64_VEC || PK == PK_I64_VEC, "vectorisable predicates only");
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    const int64_t npairs = p.n >> 1;
-    uint64_t rows = 0, lo[ONE8_MAXF], hi[ONE8_MAXF];
-    double fsum[ONE8_MAXF];
-#pragma unroll
-    for (int f = 0; f < ONE8_MAXF; ++f) lo[f] = hi[f] = 0, fsum[f] = 0.0;
-    auto pass = [&](uint64_t bits) -> bool {
-        if constexpr (PK == PK_F64_VEC)
-            return apply_cmp(p.pred.op, __longlong_as_double((long long) bits), __longlong_as_double((long long) p.pred.scalar.bits));
-        else if constexpr (PK == PK_I64_VEC) return apply_cmp(p.pred.op, (int64_t) bits, (int64_t) p.pred.scalar.bits);
-        else return true;
-    };
-    // one selected row of column values v[] into every function's accumulator
-    auto add_row = [&](const uint64_t (&v)[ONE8_MAXF]) {
-#pragma unroll
-        for (int f = 0; f < ONE8_MAXF; ++f) {
-            if (f >= p.n_funcs || p.col_of[f] < 0) continue;
-            uint64_t x = 0;
-#pragma unroll
-            for (int c = 0; c < ONE8_MAXF; ++c)
-                if (p.col_of[f] == c) x = v[c];
-            switch (p.spec[f].acc) {
-                case ACC_SUM_F64: fsum[f] += __longlong_as_double((long long) x); break;
-                case ACC_SUM_I128: {
-                    const uint64_t nl = lo[f] + x;
-                    hi[f] += ((!p.spec[f].in_unsigned && (int64_t) x < 0) ? ~0ULL : 0ULL) + (nl < lo[f] ? 1ULL : 0ULL);
-                    lo[f] = nl;
-                    break;
-                }
-                case ACC_MAXORD: {
-                    const uint64_t o = ord_transform(p.spec[f].ord, p.spec[f].is_min, x);
-                    lo[f] = o > lo[f] ? o : lo[f];
-                    break;
-                }
-                default: break;
-            }
-        }
-    };
-    for (int64_t q0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q0 < npairs; q0 += stride * U) {
-        uint4 pq[U], vq[ONE8_MAXF][U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t q = q0 + u * stride;
-            pq[u] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int c = 0; c < ONE8_MAXF; ++c) vq[c][u] = make_uint4(0, 0, 0, 0);
-            if (q < npairs) {
-                if constexpr (PK != PK_NONE) pq[u] = ldg_stream16(p.pred.col.data + q * 16);
-#pragma unroll
-                for (int c = 0; c < ONE8_MAXF; ++c)
-                    if (c < p.n_cols) vq[c][u] = ldg_stream16(p.col[c].data + q * 16);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (q0 + u * stride < npairs) {
-                const bool ok0 = pass(((uint64_t) pq[u].y << 32) | pq[u].x), ok1 = pass(((uint64_t) pq[u].w << 32) | pq[u].z);
-                rows += (uint64_t) ok0 + (uint64_t) ok1;
-                uint64_t v0[ONE8_MAXF], v1[ONE8_MAXF];
-#pragma unroll
-                for (int c = 0; c < ONE8_MAXF; ++c) {
-                    v0[c] = ((uint64_t) vq[c][u].y << 32) | vq[c][u].x;
-                    v1[c] = ((uint64_t) vq[c][u].w << 32) | vq[c][u].z;
-                }
-                if (ok0) add_row(v0);
-                if (ok1) add_row(v1);
-            }
-        }
-    }
-    if ((p.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // last, unpaired row
-        const int64_t i = p.n - 1;
-        if (pred_row(p.pred, i)) {
-            ++rows;
-            uint64_t v[ONE8_MAXF] = {0, 0, 0, 0};
-#pragma unroll
-            for (int c = 0; c < ONE8_MAXF; ++c)
-                if (c < p.n_cols) v[c] = reinterpret_cast<const uint64_t*>(p.col[c].data)[i];
-            add_row(v);
-        }
-    }
-    // flush: the row counter once, then every function through the single-function helper
-    onegroup_flush(p.table, -1, ACC_NONE, rows, 0, 0, 0, 0.0);
-#pragma unroll
-    for (int f = 0; f < ONE8_MAXF; ++f) {
-        if (f >= p.n_funcs) continue;
-        onegroup_flush(p.table, p.fi[f], p.spec[f].acc, rows, 0, lo[f], hi[f], fsum[f]);
-    }
-}
-
 // ================================================================== finalize
 struct FinalParams {
     GTable table;
@@ -376,6 +268,8 @@ struct FinalParams {
     int64_t num_groups;
     int null_last;                      // single key: NULL group goes to row num_groups-1
     unsigned long long* cursor;         // output row allocator
+    int64_t capacity;                   // rows the output arrays hold (packed result: may be < num_groups)
+    uint64_t* header;                   // packed result: [0] = number of groups (read from the device counter)
     uint64_t* out_keys[VK_AGG_MAX_KEYS];
     uint8_t* out_key_valid[VK_AGG_MAX_KEYS];
     uint64_t* out_count_star;
@@ -396,15 +290,19 @@ __global__ void __launch_bounds__(256) agg_finalize_kernel(const __grid_constant
     const GTable& t = p.table;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     const int64_t slots = gt_total_slots(t);
+    // packed result: the group count is whatever the stream-ordered kernels before this one left in the
+    // device counter -- the host has not seen it yet
+    const int64_t num_groups = p.header != nullptr ? (int64_t) *t.num_groups : p.num_groups;
+    if (p.header != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.header[0] = (uint64_t) num_groups;
     for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
         if (!gt_slot_occupied(t, s)) continue;
         uint64_t kv[VK_AGG_MAX_KEYS];
         uint32_t nullmask;
         gt_slot_key(t, s, kv, &nullmask);
         int64_t row;
-        if (p.null_last && nullmask) row = p.num_groups - 1;
+        if (p.null_last && nullmask) row = num_groups - 1;
         else row = (int64_t) atomicAdd(p.cursor, 1ULL);
-        if (row >= p.num_groups) continue;  // defensive
+        if (row >= num_groups || row >= p.capacity) continue;  // more groups than the caller's block holds: it retries
         for (int k = 0; k < t.n_keys; ++k) {
             p.out_keys[k][row] = kv[k];
             p.out_key_valid[k][row] = !((nullmask >> k) & 1);
@@ -530,40 +428,198 @@ __global__ void __launch_bounds__(256) agg_export_kernel(const __grid_constant__
         }
     }
 }
+// One partial-group record folded into the table; false when the table is at its load limit.
+__device__ __forceinline__ bool merge_record(const GTable& t, const FuncSpec* specs, const uint64_t* o) {
+    uint64_t kv[VK_AGG_MAX_KEYS];
+    int w = 0;
+    for (int k = 0; k < t.n_keys; ++k) kv[k] = o[w++];
+    const uint32_t nullmask = (uint32_t) o[w++];
+    int64_t slot = gt_find_or_insert<0>(t, kv, nullmask, hash_keys(kv, nullmask, t.n_keys), t.max_groups);
+    if (slot < 0) return false;
+    atomicAdd(reinterpret_cast<unsigned long long*>(t.count_star + slot), (unsigned long long) o[w++]);
+    for (int f = 0; f < t.n_funcs; ++f) {
+        const FuncSpec spec = specs[f];
+        uint64_t lo = o[w++], hi = o[w++], nn = o[w++];
+        if (nn && t.nnull[f]) atomicAdd(reinterpret_cast<unsigned long long*>(t.nnull[f] + slot), (unsigned long long) nn);
+        switch (spec.acc) {
+            case ACC_SUM_F64:
+                atomicAdd(reinterpret_cast<double*>(t.acc_lo[f] + slot), __longlong_as_double((long long) lo));
+                break;
+            case ACC_SUM_I64:
+                atomicAdd(reinterpret_cast<unsigned long long*>(t.acc_lo[f] + slot), (unsigned long long) lo);
+                break;
+            case ACC_SUM_I128: acc_add_i128(t.acc_lo[f] + slot, t.acc_hi[f] + slot, lo, hi); break;
+            case ACC_MAXORD:
+                atomicMax(reinterpret_cast<unsigned long long*>(t.acc_lo[f] + slot), (unsigned long long) lo);
+                break;
+            default: break;
+        }
+    }
+    return true;
+}
 __global__ void __launch_bounds__(256) agg_merge_kernel(const __grid_constant__ ExchParams p) {
     const GTable& t = p.table;
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < p.n_in; r += stride) {
-        const uint64_t* o = p.in + r * p.words;
-        uint64_t kv[VK_AGG_MAX_KEYS];
-        int w = 0;
-        for (int k = 0; k < t.n_keys; ++k) kv[k] = o[w++];
-        const uint32_t nullmask = (uint32_t) o[w++];
-        int64_t slot = gt_find_or_insert<0>(t, kv, nullmask, hash_keys(kv, nullmask, t.n_keys), t.max_groups);
-        if (slot < 0) {
-            replay_append(p.replay, r);
-            continue;
-        }
-        atomicAdd(reinterpret_cast<unsigned long long*>(t.count_star + slot), (unsigned long long) o[w++]);
-        for (int f = 0; f < t.n_funcs; ++f) {
-            const FuncSpec spec = p.specs[f];
-            uint64_t lo = o[w++], hi = o[w++], nn = o[w++];
-            if (nn && t.nnull[f]) atomicAdd(reinterpret_cast<unsigned long long*>(t.nnull[f] + slot), (unsigned long long) nn);
-            switch (spec.acc) {
-                case ACC_SUM_F64:
-                    atomicAdd(reinterpret_cast<double*>(t.acc_lo[f] + slot), __longlong_as_double((long long) lo));
-                    break;
-                case ACC_SUM_I64:
-                    atomicAdd(reinterpret_cast<unsigned long long*>(t.acc_lo[f] + slot), (unsigned long long) lo);
-                    break;
-                case ACC_SUM_I128: acc_add_i128(t.acc_lo[f] + slot, t.acc_hi[f] + slot, lo, hi); break;
-                case ACC_MAXORD:
-                    atomicMax(reinterpret_cast<unsigned long long*>(t.acc_lo[f] + slot), (unsigned long long) lo);
-                    break;
-                default: break;
+    for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < p.n_in; r += stride)
+        if (!merge_record(t, p.specs, p.in + r * p.words)) replay_append(p.replay, r);
+}
+
+// ============================================================== peer exchange
+// Low-cardinality group-by across the GPUs of one box WITHOUT a collective call: every
+// rank owns a window of device memory that its peers map (cudaIpc) and write into over NVLink.
+//   window (u64 words): flag[16] | ack[16] | decision[2] count[16] cursor done pad.. | slots[2][world][slot_words]
+//   slot = [n_groups | n_groups records of `words` u64]           (two parities: epoch & 1)
+// Rank r's send kernel stores its partial groups straight into slot r of the OWNER's window, then
+// releases flag[r] = epoch at system scope; the owner's wait kernel acquires every flag, decides
+// (fits / a rank overflowed its slot / the owner's table needs to grow), the merge kernel folds the
+// records into the owner's own table, and the ack kernel stores ack[owner] = epoch and the decision
+// into every peer's window, which frees the slot parity for epoch + 2 and tells the peers how the
+// query went.  No NCCL call and no host round trip until the final read-back.
+constexpr int PEER_MAX = 16;
+constexpr int PW_FLAG = 0, PW_ACK = 16, PW_DECISION = 32, PW_COUNT = 34, PW_CURSOR = 50, PW_DONE = 51, PW_SLOTS = 64;
+constexpr uint64_t PEER_OK = 1, PEER_OVERFLOW = 2, PEER_NEED_GROW = 3, PEER_TIMEOUT = 4;
+constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ULL;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const uint64_t* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *p >= want; false after PEER_TIMEOUT_NS (a dead peer must not hang this GPU).
+__device__ __forceinline__ bool wait_at_least(const uint64_t* p, unsigned long long want) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < want) {
+        __nanosleep(200);
+        if (global_ns() - t0 > PEER_TIMEOUT_NS) return false;
+    }
+    return true;
+}
+
+struct PeerSendParams {
+    GTable table;
+    int words;
+    int has_table;
+    int64_t cap;                 // records a slot holds
+    uint64_t* slot;              // the owner's slot for this rank (peer memory)
+    uint64_t* flag;              // the owner's flag word for this rank (peer memory)
+    const uint64_t* ack;         // this rank's own window: what the owner has merged so far
+    unsigned long long* cursor;  // local scratch
+    unsigned long long* done;
+    unsigned long long epoch;
+};
+__global__ void __launch_bounds__(256) agg_peer_send_kernel(const __grid_constant__ PeerSendParams p) {
+    __shared__ int s_ok;
+    __shared__ int s_last;
+    // the slot parity of this epoch was last used by epoch - 2: the owner must have merged that one
+    if (threadIdx.x == 0) s_ok = p.epoch < 3 || wait_at_least(p.ack, p.epoch - 2);
+    __syncthreads();
+    if (s_ok && p.has_table) {
+        const GTable& t = p.table;
+        const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+        const int64_t slots = gt_total_slots(t);
+        for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += stride) {
+            if (!gt_slot_occupied(t, s)) continue;
+            const int64_t rec = (int64_t) atomicAdd(p.cursor, 1ULL);
+            if (rec >= p.cap) continue;   // counted, not stored: the owner sees n_groups > cap and everybody falls back
+            uint64_t kv[VK_AGG_MAX_KEYS];
+            uint32_t nullmask;
+            gt_slot_key(t, s, kv, &nullmask);
+            uint64_t* o = p.slot + 1 + rec * p.words;
+            int w = 0;
+            for (int k = 0; k < t.n_keys; ++k) o[w++] = kv[k];
+            o[w++] = nullmask;
+            o[w++] = t.count_star[s];
+            for (int f = 0; f < t.n_funcs; ++f) {
+                o[w++] = t.acc_lo[f] ? t.acc_lo[f][s] : 0;
+                o[w++] = t.acc_hi[f] ? t.acc_hi[f][s] : 0;
+                o[w++] = t.nnull[f] ? t.nnull[f][s] : 0;
             }
         }
     }
+    // last block out publishes: every block's remote stores are fenced at system scope before its
+    // arrival is counted, so they are visible to the owner before the flag is
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.done, 1ULL) == (unsigned long long) gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned long long n = s_ok ? *reinterpret_cast<volatile unsigned long long*>(p.cursor) : ~0ULL;
+        p.slot[0] = n;
+        __threadfence_system();
+        st_release_sys(p.flag, p.epoch);
+    }
+}
+
+struct PeerMergeParams {
+    GTable table;
+    FuncSpec specs[VK_AGG_MAX_FUNCS];
+    int words;
+    int rank, world;
+    int64_t cap;
+    int64_t slot_words;
+    uint64_t* window;            // this rank's own window
+    uint64_t* peer_window[PEER_MAX];
+    unsigned long long epoch;
+    unsigned long long* lost;
+};
+__device__ __forceinline__ const uint64_t* peer_slot(const PeerMergeParams& p, int r) {
+    return p.window + PW_SLOTS + ((int64_t) (p.epoch & 1) * p.world + r) * p.slot_words;
+}
+// One warp: lane r waits for rank r's message, then lane 0 decides.
+__global__ void __launch_bounds__(32) agg_peer_wait_kernel(const __grid_constant__ PeerMergeParams p) {
+    const int r = threadIdx.x;
+    bool ok = true;
+    unsigned long long n = 0;
+    if (r < p.world && r != p.rank) {
+        ok = wait_at_least(p.window + PW_FLAG + r, p.epoch);
+        if (ok) n = peer_slot(p, r)[0];
+        p.window[PW_COUNT + r] = n;
+    }
+    const unsigned all_ok = __all_sync(0xffffffffu, ok);
+    const unsigned fits = __all_sync(0xffffffffu, n <= (unsigned long long) p.cap);
+    unsigned long long total = n <= (unsigned long long) p.cap ? n : 0;
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+    if (r == 0) {
+        uint64_t decision = PEER_OK;
+        if (!all_ok) decision = PEER_TIMEOUT;
+        else if (!fits) decision = PEER_OVERFLOW;
+        else if (p.table.max_groups - (int64_t) *p.table.num_groups < (int64_t) total) decision = PEER_NEED_GROW;
+        p.window[PW_DECISION + (p.epoch & 1)] = decision;
+    }
+}
+__global__ void __launch_bounds__(256) agg_peer_merge_kernel(const __grid_constant__ PeerMergeParams p) {
+    if (p.window[PW_DECISION + (p.epoch & 1)] != PEER_OK) return;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int r = 0; r < p.world; ++r) {
+        if (r == p.rank) continue;
+        const int64_t n = (int64_t) p.window[PW_COUNT + r];
+        const uint64_t* recs = peer_slot(p, r) + 1;
+        for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+            if (!merge_record(p.table, p.specs, recs + i * p.words)) atomicAdd(p.lost, 1ULL);
+    }
+}
+// Lane r tells rank r: merged (ack) and how it went (decision); stream order puts this after the merge.
+__global__ void __launch_bounds__(32) agg_peer_ack_kernel(const __grid_constant__ PeerMergeParams p) {
+    const int r = threadIdx.x;
+    if (r >= p.world || r == p.rank) return;
+    const uint64_t decision = p.window[PW_DECISION + (p.epoch & 1)];
+    uint64_t* w = p.peer_window[r];
+    w[PW_DECISION + (p.epoch & 1)] = decision;
+    __threadfence_system();
+    st_release_sys(w + PW_ACK + p.rank, p.epoch);
+}
+// A non-owner rank: wait until the owner has merged this epoch (its decision word is then in our window).
+__global__ void __launch_bounds__(32) agg_peer_wait_ack_kernel(uint64_t* window, int owner, unsigned long long epoch) {
+    if (threadIdx.x == 0 && !wait_at_least(window + PW_ACK + owner, epoch)) window[PW_DECISION + (epoch & 1)] = PEER_TIMEOUT;
 }
 
 }  // namespace vk
@@ -597,6 +653,7 @@ struct VkAgg {
     int fast_warps = FA_MAX_THREADS / 32;  // warps per CTA (fewer warps = more groups per warp-private table)
     bool fast_warps_fixed = false;
     int fast_direct_policy = 1;       // 1: use direct (key - base) group ids when the key range allows, 0: always hash
+    int64_t learn_rows = (int64_t) 1 << 20;   // rows of the learning launch
     bool direct_known = false;        // key range of the table measured
     bool direct_ok = false;
     uint64_t direct_min = 0, direct_span = 0;  // smallest key (signed order) and max - min
@@ -617,9 +674,7 @@ struct VkAgg {
 namespace {
 
 bool debug_on() {
-    static int v = -1;
-    if (v < 0) v = getenv("VINUM_B200_DEBUG") ? 1 : 0;
-    return v == 1;
+    return opt(OPT_DEBUG) != 0;
 }
 #define VK_DBG(...) do { if (debug_on()) { fprintf(stderr, "[vk_agg] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
@@ -1073,18 +1128,20 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
         }
         a->specs[f] = s;
     }
-    if (const char* v = getenv("VINUM_B200_AGG_LOG2S")) a->fast_log2s = atoi(v);
-    if (const char* v = getenv("VINUM_B200_AGG_PF")) a->fast_pf = atoi(v);
+    // kernel-selection knobs are sampled per object (vk_set_option / VINUM_B200_*)
+    a->fast_log2s = (int) opt(OPT_AGG_LOG2S);
+    a->fast_pf = (int) opt(OPT_AGG_PF);
     if (a->fast_log2s < 8) a->fast_log2s = 8;
     if (a->fast_log2s > 13) a->fast_log2s = 13;
-    if (const char* v = getenv("VINUM_B200_AGG_WARPS")) {
-        a->fast_warps = atoi(v);
+    if (opt(OPT_AGG_WARPS) > 0) {
+        a->fast_warps = (int) opt(OPT_AGG_WARPS);
         a->fast_warps_fixed = true;
     }
     if (a->fast_warps < 1) a->fast_warps = 1;
     if (a->fast_warps > FA_MAX_THREADS / 32) a->fast_warps = FA_MAX_THREADS / 32;
-    if (const char* v = getenv("VINUM_B200_AGG_DIRECT")) a->fast_direct_policy = atoi(v);
-    if (getenv("VINUM_B200_AGG_NOFAST")) a->fast_disabled = true;
+    a->fast_direct_policy = (int) opt(OPT_AGG_DIRECT);
+    if (opt(OPT_AGG_NOFAST)) a->fast_disabled = true;
+    a->learn_rows = (int64_t) 1 << (opt(OPT_AGG_LEARN_LOG2) < 10 ? 10 : (opt(OPT_AGG_LEARN_LOG2) > 30 ? 30 : opt(OPT_AGG_LEARN_LOG2)));
     const int rc = ctr_acquire(a);
     if (rc != VK_OK) { delete a; return rc; }
     *out = a;
@@ -1212,48 +1269,6 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         a->last_path = 3;
         int64_t need = (n_rows + 255) / 256, capb = (int64_t) sm_count() * 8;
         const unsigned grid = (unsigned) (need < capb ? need : capb);
-        // ---- every function in one launch (opt-in, unmeasured) ----
-        static int fused = -1;
-        if (fused < 0) { const char* v = getenv("VINUM_B200_ONEGROUP_FUSED"); fused = v ? atoi(v) : 0; }
-        if (fused) {
-            OneMultiParams mp{};
-            int pk;
-            int rc = make_pred(*pred, n_rows, &mp.pred, &pk);
-            if (rc != VK_OK) return rc;
-            bool ok = pk == PK_NONE || pk == PK_F64_VEC || pk == PK_I64_VEC;
-            for (int f = 0; f < a->n_funcs && ok; ++f) {
-                const FuncSpec sp = a->specs[f];
-                if (sp.acc == ACC_NONE) continue;
-                if (mp.n_funcs == ONE8_MAXF || sp.acc == ACC_SUM_I64 || values[f].validity != nullptr) { ok = false; break; }
-                const int j = mp.n_funcs++;
-                mp.spec[j] = sp;
-                mp.fi[j] = f;
-                mp.col_of[j] = -1;
-                if (sp.acc == ACC_COUNT) continue;
-                const Col c = make_col(values[f]);
-                const bool f64_acc = sp.acc == ACC_SUM_F64 || (sp.acc == ACC_MAXORD && sp.ord == ORD_F64);
-                if (!(f64_acc ? c.dtype == VK_F64 : (c.dtype == VK_I64 || c.dtype == VK_U64)) ||
-                    (reinterpret_cast<uintptr_t>(c.data) & 15) != 0) { ok = false; break; }
-                for (int k = 0; k < mp.n_cols; ++k)
-                    if (mp.col[k].data == c.data) mp.col_of[j] = k;
-                if (mp.col_of[j] < 0) {
-                    if (mp.n_cols == ONE8_MAXF) { ok = false; break; }
-                    mp.col[mp.n_cols] = c;
-                    mp.col_of[j] = mp.n_cols++;
-                }
-            }
-            if (ok) {
-                mp.n = n_rows;
-                mp.table = a->t;
-                int64_t need8 = (n_rows / 2 + 256 * 2 - 1) / (256 * 2);
-                const unsigned g8 = (unsigned) (need8 < 1 ? 1 : (need8 < capb ? need8 : capb));
-                if (pk == PK_NONE) agg_onegroup8_multi_kernel<PK_NONE, 2><<<g8, 256, 0, s>>>(mp);
-                else if (pk == PK_F64_VEC) agg_onegroup8_multi_kernel<PK_F64_VEC, 2><<<g8, 256, 0, s>>>(mp);
-                else agg_onegroup8_multi_kernel<PK_I64_VEC, 2><<<g8, 256, 0, s>>>(mp);
-                VK_CHECK_LAUNCH("agg_onegroup8_multi_kernel");
-                return VK_OK;
-            }
-        }
         for (int f = -1; f < a->n_funcs; ++f) {
             if (f >= 0 && a->specs[f].acc == ACC_NONE) continue;
             OneParams op{};
@@ -1267,8 +1282,10 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 op.spec = a->specs[f];
                 op.val = make_col(values[f]);
             }
-            static int fast1 = -1;  // row pairs per thread of agg_onegroup8_kernel (0: off; 4 measured 1.93x faster)
-            if (fast1 < 0) { const char* v = getenv("VINUM_B200_ONEGROUP_FAST"); fast1 = v ? atoi(v) : 4; }
+            // row pairs per thread of agg_onegroup8_kernel (0: agg_onegroup_kernel).  Measured on one box
+            // (profiles/r02_variants.md, COUNT(*), SUM(f64) WHERE f64 > c at 1e8 rows): 2 -> 0.52 ms, 4 -> 0.68 ms,
+            // general kernel 1.30 ms
+            const int fast1 = (int) opt(OPT_ONEGROUP_FAST);
             bool raw8 = pk == PK_NONE || pk == PK_F64_VEC || pk == PK_I64_VEC;
             if (f >= 0 && op.spec.acc != ACC_COUNT) {
                 const int dt = op.val.dtype;
@@ -1361,8 +1378,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         if (g_list_max[dev] == 0) {
             // large enough that a 1e9-row batch is ONE launch (the list is only touched by rows
             // that could not be inserted; the memory is kept per device and never written otherwise)
-            int l2 = 30;
-            if (const char* v = getenv("VINUM_B200_LIST_LOG2")) l2 = atoi(v);
+            int l2 = (int) opt(OPT_LIST_LOG2);
             if (l2 < 16) l2 = 16;
             if (l2 > 31) l2 = 31;
             uint64_t lm = (uint64_t) 1 << l2;
@@ -1397,7 +1413,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         // the first fast chunk is small: it tells the cardinality, the key range and the
         // selectivity before the geometry is fixed (and it needs no replay list)
         if (fast && a->fast_rows_seen == 0) {
-            const int64_t learn = free_slots < ((int64_t) 1 << 20) ? free_slots : ((int64_t) 1 << 20);
+            const int64_t learn = free_slots < a->learn_rows ? free_slots : a->learn_rows;
             if (chunk > learn) chunk = learn;
         }
         if (chunk > free_slots) {
@@ -1583,6 +1599,8 @@ int vk_agg_result(VkAgg* a, int64_t num_groups, uint64_t* const* out_keys, uint8
     fp.num_groups = num_groups;
     fp.null_last = a->n_keys == 1;
     fp.cursor = a->d_ctr + CTR_CURSOR;
+    fp.capacity = num_groups;
+    fp.header = nullptr;
     VK_CUDA(cudaMemsetAsync(fp.cursor, 0, sizeof(unsigned long long), s));
     for (int k = 0; k < a->n_keys; ++k) {
         VK_REQUIRE(out_keys && out_keys[k] && out_key_valid && out_key_valid[k], "vk_agg_result: NULL key output");
@@ -1686,6 +1704,200 @@ int vk_agg_merge_partials(VkAgg* a, const uint64_t* records, int64_t n_records, 
     agg_merge_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(p);
     VK_CHECK_LAUNCH("agg_merge_kernel");
     a->groups_ub += n_records;
+    return VK_OK;
+}
+
+// ------------------------------------------------------------ packed result ----
+// Finalise into ONE caller-owned device block so that the host needs a single copy and a single
+// synchronisation to get the groups (the separate vk_agg_num_groups + vk_agg_result + two copies cost
+// three stream round trips: 0.2 ms of a 4.2 ms query).  Block (u64 words), C = capacity:
+//   [0] groups in the table  [1] reserved
+//   keys[n_keys][C] | count_star[C] | lo[n_funcs][C] | hi[n_funcs][C] | bytes: key_valid[n_keys][C] valid[n_funcs][C]
+// Word 0 may exceed C: the caller then retries with a larger block.
+uint64_t vk_agg_result_packed_bytes(int n_keys, int n_funcs, int64_t capacity) {
+    if (capacity < 1) capacity = 1;
+    const uint64_t words = 2 + (uint64_t) (n_keys + 1 + 2 * n_funcs) * (uint64_t) capacity;
+    const uint64_t bytes = (uint64_t) (n_keys + n_funcs) * (uint64_t) capacity;
+    return words * 8 + ((bytes + 7) & ~(uint64_t) 7);
+}
+
+int vk_agg_result_packed(VkAgg* a, int64_t capacity, void* out_block, VkStream stream) {
+    VK_REQUIRE(a && out_block && capacity >= 1, "vk_agg_result_packed: bad argument");
+    VK_REQUIRE(a->n_keys >= 1, "vk_agg_result_packed: group-by aggregates only");
+    cudaStream_t s = (cudaStream_t) stream;
+    { const int irc = ctr_init(a, s); if (irc != VK_OK) return irc; }
+    uint64_t* blk = reinterpret_cast<uint64_t*>(out_block);
+    if (!a->table_ready) {   // no batch was aggregated: zero groups
+        VK_CUDA(cudaMemsetAsync(blk, 0, 16, s));
+        return VK_OK;
+    }
+    FinalParams fp{};
+    fp.table = a->t;
+    fp.num_groups = -1;
+    fp.null_last = a->n_keys == 1;
+    fp.cursor = a->d_ctr + CTR_CURSOR;
+    fp.capacity = capacity;
+    fp.header = blk;
+    VK_CUDA(cudaMemsetAsync(fp.cursor, 0, sizeof(unsigned long long), s));
+    uint64_t* w = blk + 2;
+    for (int k = 0; k < a->n_keys; ++k) { fp.out_keys[k] = w; w += capacity; }
+    fp.out_count_star = w; w += capacity;
+    for (int f = 0; f < a->n_funcs; ++f) { fp.out_lo[f] = w; w += capacity; }
+    for (int f = 0; f < a->n_funcs; ++f) { fp.out_hi[f] = w; w += capacity; }
+    uint8_t* b = reinterpret_cast<uint8_t*>(w);
+    for (int k = 0; k < a->n_keys; ++k) { fp.out_key_valid[k] = b; b += capacity; }
+    for (int f = 0; f < a->n_funcs; ++f) { fp.specs[f] = a->specs[f]; fp.out_valid[f] = b; b += capacity; }
+    int64_t need = (gt_total_slots(a->t) + 255) / 256, capb = (int64_t) sm_count() * 8;
+    agg_finalize_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(fp);
+    VK_CHECK_LAUNCH("agg_finalize_kernel");
+    return VK_OK;
+}
+
+// ------------------------------------------------------------- peer exchange ----
+struct VkPeer {
+    int rank = 0, world = 1;
+    int device = 0;
+    int64_t cap = 0;
+    int words_max = 0;
+    int64_t slot_words = 0;
+    size_t bytes = 0;
+    uint64_t* window = nullptr;
+    uint64_t* peer[PEER_MAX] = {nullptr};
+    bool opened[PEER_MAX] = {false};
+};
+
+int vk_peer_create(VkPeer** out, int rank, int world, int64_t cap_groups, int max_record_words) {
+    VK_REQUIRE(out, "vk_peer_create: out is NULL");
+    *out = nullptr;
+    VK_REQUIRE(world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world, "vk_peer_create: 1..16 ranks supported");
+    VK_REQUIRE(cap_groups >= 1 && max_record_words >= 3, "vk_peer_create: bad slot geometry");
+    VkPeer* p = new VkPeer();
+    p->rank = rank;
+    p->world = world;
+    p->cap = cap_groups;
+    p->words_max = max_record_words;
+    p->slot_words = (1 + cap_groups * (int64_t) max_record_words + 15) & ~(int64_t) 15;
+    p->bytes = (size_t) (PW_SLOTS + 2 * (int64_t) world * p->slot_words) * 8;
+    cudaGetDevice(&p->device);
+    // plain cudaMalloc: memory of the stream-ordered pool cannot be exported with cudaIpcGetMemHandle
+    cudaError_t e = cudaMalloc((void**) &p->window, p->bytes);
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(peer window)"); }
+    e = cudaMemset(p->window, 0, p->bytes);
+    if (e != cudaSuccess) { cudaFree(p->window); delete p; return cuda_fail(e, "cudaMemset(peer window)"); }
+    p->peer[rank] = p->window;
+    *out = p;
+    return VK_OK;
+}
+int vk_peer_destroy(VkPeer* p) {
+    if (!p) return VK_OK;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < p->world; ++r)
+        if (p->opened[r] && p->peer[r]) cudaIpcCloseMemHandle(p->peer[r]);
+    if (p->window) cudaFree(p->window);
+    delete p;
+    return VK_OK;
+}
+int vk_peer_handle(VkPeer* p, void* out_handle64) {
+    VK_REQUIRE(p && out_handle64, "vk_peer_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    VK_CUDA(cudaIpcGetMemHandle(&h, p->window));
+    memcpy(out_handle64, &h, sizeof(h));
+    return VK_OK;
+}
+int vk_peer_open(VkPeer* p, int peer_rank, const void* handle64) {
+    VK_REQUIRE(p && handle64 && peer_rank >= 0 && peer_rank < p->world && peer_rank != p->rank, "vk_peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* ptr = nullptr;
+    VK_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer[peer_rank] = reinterpret_cast<uint64_t*>(ptr);
+    p->opened[peer_rank] = true;
+    return VK_OK;
+}
+int vk_peer_attach_local(VkPeer* p, int peer_rank, VkPeer* other) {
+    // ranks that live in ONE process (tests: several logical ranks on one GPU) share the address space
+    VK_REQUIRE(p && other && peer_rank >= 0 && peer_rank < p->world && other->rank == peer_rank, "vk_peer_attach_local: bad argument");
+    VK_REQUIRE(other->cap == p->cap && other->words_max == p->words_max && other->world == p->world,
+               "vk_peer_attach_local: windows of different geometry");
+    if (other->device != p->device) {
+        int can = 0;
+        VK_CUDA(cudaDeviceCanAccessPeer(&can, p->device, other->device));
+        VK_REQUIRE(can, "vk_peer_attach_local: devices are not peer-accessible");
+        cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+    }
+    p->peer[peer_rank] = other->window;
+    return VK_OK;
+}
+void* vk_peer_decision_ptr(VkPeer* p, uint64_t epoch) {
+    return p ? (void*) (p->window + PW_DECISION + (epoch & 1)) : nullptr;
+}
+
+int vk_agg_peer_send(VkAgg* a, VkPeer* p, int owner, uint64_t epoch, VkStream stream) {
+    VK_REQUIRE(a && p && owner >= 0 && owner < p->world && owner != p->rank && epoch >= 1, "vk_agg_peer_send: bad argument");
+    VK_REQUIRE(p->peer[owner], "vk_agg_peer_send: the owner's window is not mapped");
+    const int words = a->n_keys + 2 + 3 * a->n_funcs;
+    VK_REQUIRE(words <= p->words_max, "vk_agg_peer_send: records wider than the window's slots");
+    cudaStream_t s = (cudaStream_t) stream;
+    { const int irc = ctr_init(a, s); if (irc != VK_OK) return irc; }
+    PeerSendParams sp{};
+    sp.has_table = a->table_ready ? 1 : 0;
+    if (a->table_ready) sp.table = a->t;
+    sp.words = words;
+    sp.cap = p->cap;
+    sp.slot = p->peer[owner] + PW_SLOTS + ((int64_t) (epoch & 1) * p->world + p->rank) * p->slot_words;
+    sp.flag = p->peer[owner] + PW_FLAG + p->rank;
+    sp.ack = p->window + PW_ACK + owner;
+    sp.cursor = reinterpret_cast<unsigned long long*>(p->window + PW_CURSOR);
+    sp.done = reinterpret_cast<unsigned long long*>(p->window + PW_DONE);
+    sp.epoch = epoch;
+    VK_CUDA(cudaMemsetAsync(p->window + PW_CURSOR, 0, 16, s));
+    int64_t need = a->table_ready ? (gt_total_slots(a->t) + 255) / 256 : 1, capb = (int64_t) sm_count() * 4;
+    agg_peer_send_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(sp);
+    VK_CHECK_LAUNCH("agg_peer_send_kernel");
+    agg_peer_wait_ack_kernel<<<1, 32, 0, s>>>(p->window, owner, epoch);
+    VK_CHECK_LAUNCH("agg_peer_wait_ack_kernel");
+    return VK_OK;
+}
+
+int vk_agg_peer_merge(VkAgg* a, VkPeer* p, uint64_t epoch, VkStream stream) {
+    VK_REQUIRE(a && p && epoch >= 1, "vk_agg_peer_merge: bad argument");
+    VK_REQUIRE(a->n_keys > 0, "vk_agg_peer_merge: un-grouped aggregates merge on the host");
+    const int words = a->n_keys + 2 + 3 * a->n_funcs;
+    VK_REQUIRE(words <= p->words_max, "vk_agg_peer_merge: records wider than the window's slots");
+    cudaStream_t s = (cudaStream_t) stream;
+    { const int irc = ctr_init(a, s); if (irc != VK_OK) return irc; }
+    if (!a->table_ready) {   // the owner's own shard was empty
+        int rc = alloc_table(a, &a->t, pow2_ceil(4 * p->cap * p->world < 4096 ? 4096 : 4 * p->cap * p->world), s);
+        if (rc != VK_OK) return rc;
+        a->table_ready = true;
+        a->groups_ub = 0;
+    }
+    PeerMergeParams mp{};
+    mp.table = a->t;
+    for (int f = 0; f < a->n_funcs; ++f) mp.specs[f] = a->specs[f];
+    mp.words = words;
+    mp.rank = p->rank;
+    mp.world = p->world;
+    mp.cap = p->cap;
+    mp.slot_words = p->slot_words;
+    mp.window = p->window;
+    for (int r = 0; r < p->world; ++r) {
+        VK_REQUIRE(p->peer[r], "vk_agg_peer_merge: a peer's window is not mapped");
+        mp.peer_window[r] = p->peer[r];
+    }
+    mp.epoch = epoch;
+    mp.lost = a->d_ctr + CTR_LOST;
+    agg_peer_wait_kernel<<<1, 32, 0, s>>>(mp);
+    VK_CHECK_LAUNCH("agg_peer_wait_kernel");
+    int64_t need = ((int64_t) p->cap + 255) / 256, capb = (int64_t) sm_count() * 2;
+    agg_peer_merge_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(mp);
+    VK_CHECK_LAUNCH("agg_peer_merge_kernel");
+    agg_peer_ack_kernel<<<1, 32, 0, s>>>(mp);
+    VK_CHECK_LAUNCH("agg_peer_ack_kernel");
+    a->groups_ub += (int64_t) p->cap * (p->world - 1);
     return VK_OK;
 }
 

@@ -2,6 +2,7 @@
 // stream-ordered allocator, and the synthetic-table generator.
 #include "vk_common.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -20,6 +21,37 @@ int cuda_fail(cudaError_t e, const char* what) {
     // clear the sticky-less error state so later calls report their own failures
     cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? VK_ERR_OOM : VK_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- options ----
+struct OptEntry { const char* name; int64_t dflt; std::atomic<int64_t> value; std::atomic<int> state; };  // state 0: unread
+static OptEntry g_opts[OPT_COUNT] = {
+    {"FILTER_STAGE", 1, {0}, {0}},  {"FILTER_PF", 1, {0}, {0}},        {"FILTER_ITERS", 4, {0}, {0}},
+    {"CMP_FAST", 2, {0}, {0}},      {"ARITH_FAST", 4, {0}, {0}},       {"ONEGROUP_FAST", 2, {0}, {0}},
+    {"SORT_FUSE_LAST", 1, {0}, {0}}, {"SORT_PREP", 4, {0}, {0}},       {"SORT_BITS", 0, {0}, {0}},
+    {"AGG_LOG2S", 12, {0}, {0}},    {"AGG_PF", -1, {0}, {0}},          {"AGG_WARPS", 0, {0}, {0}},
+    {"AGG_DIRECT", 1, {0}, {0}},    {"AGG_NOFAST", 0, {0}, {0}},       {"AGG_HYBRID", 0, {0}, {0}},
+    {"AGG_LEARN_LOG2", 20, {0}, {0}}, {"LIST_LOG2", 30, {0}, {0}},     {"DEBUG", 0, {0}, {0}},
+    {"INGEST_STAGED", 1, {0}, {0}}, {"INGEST_THREADS", 0, {0}, {0}},
+};
+int64_t opt(int id) {
+    OptEntry& e = g_opts[id];
+    if (e.state.load(std::memory_order_acquire) == 0) {
+        const std::string env = std::string("VINUM_B200_") + e.name;
+        const char* v = getenv(env.c_str());
+        int expected = 0;
+        const int64_t val = v && *v ? atoll(v) : e.dflt;
+        // a concurrent vk_set_option wins: only an unread entry takes the environment's value
+        if (e.state.compare_exchange_strong(expected, 1)) e.value.store(val, std::memory_order_release);
+    }
+    return e.value.load(std::memory_order_acquire);
+}
+static int opt_find(const char* name) {
+    if (!name) return -1;
+    if (strncmp(name, "VINUM_B200_", 11) == 0) name += 11;
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, g_opts[i].name) == 0) return i;
+    return -1;
 }
 
 static int g_sm_count[64] = {0};
@@ -91,6 +123,24 @@ extern "C" {
 int vk_abi_version(void) { return VK_ABI_VERSION; }
 const char* vk_last_error(void) { return t_last_error.c_str(); }
 uint64_t vk_launch_count(void) { return g_launches.load(); }
+
+int vk_set_option(const char* name, int64_t value) {
+    const int i = opt_find(name);
+    if (i < 0) return fail(VK_ERR_ARG, std::string("vk_set_option: unknown option '") + (name ? name : "(null)") + "'");
+    g_opts[i].value.store(value, std::memory_order_release);
+    g_opts[i].state.store(2, std::memory_order_release);
+    return VK_OK;
+}
+int vk_get_option(const char* name, int64_t* out_value) {
+    const int i = opt_find(name);
+    if (i < 0 || !out_value) return fail(VK_ERR_ARG, std::string("vk_get_option: unknown option '") + (name ? name : "(null)") + "'");
+    *out_value = opt(i);
+    return VK_OK;
+}
+int vk_reset_options(void) {
+    for (int i = 0; i < OPT_COUNT; ++i) g_opts[i].state.store(0, std::memory_order_release);
+    return VK_OK;
+}
 
 int vk_device_count(int* out_n) {
     VK_REQUIRE(out_n, "vk_device_count: out_n is NULL");

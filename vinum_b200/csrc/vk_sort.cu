@@ -19,6 +19,10 @@ namespace vk {
 constexpr int RS_THREADS = 256;
 constexpr int RS_MIN_TILE = RS_THREADS * 8;     // smallest tile any geometry uses (sizes the status array)
 constexpr int RS_WARPS = RS_THREADS / 32;
+#ifndef VK_RS_RANK_BATCH
+#define VK_RS_RANK_BATCH 4
+#endif
+constexpr int RS_RANK_BATCH = VK_RS_RANK_BATCH;   // items whose votes / counter atomics are in flight together
 constexpr uint32_t RS_NULLBIT = 0x80000000u;
 
 constexpr uint64_t KEY_NAN = 0xFFFFFFFFFFFFFFFEULL;
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(256) sort_prepare_kernel(const __grid_constant
 // thread per round: the U (gathered) loads are issued together, and the histogram work of a round
 // runs while the next round's loads are in flight.  sort_prepare_kernel has one load in flight per
 // thread at half occupancy (long scoreboard 32 %, profiles/r01_sort_prepare_ncu_full.md).
-// Measured with U = 4: C4 8.26 ms against 8.61 (profiles/r01_variants.md); VINUM_B200_SORT_PREP=0 selects
+// Measured with U = 4: C4 8.22 ms against 8.56 (profiles/r02_variants.md); option SORT_PREP=0 selects
 // sort_prepare_kernel.
 template <int U>
 __global__ void __launch_bounds__(256) sort_prepare8_kernel(const __grid_constant__ PrepParams p) {
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256) sort_prepare8_kernel(const __grid_constan
             } else {
                 c = (is_signed ? (c ^ 0x8000000000000000ULL) : c) ^ flip;
             }
-            if (in && p.out_key != nullptr) {  // nullptr: histograms only (the first pass recomputes the codes)
+            if (in) {
                 p.out_key[i] = c;
                 p.out_idx[i] = src[u];
             }
@@ -195,9 +199,10 @@ struct PassParams {
     unsigned long long* ticket;
     unsigned long long* status;         // [tiles][256]
     int64_t* out_final;                 // LAST pass: the permutation (vk_sort_indices' out_indices)
-    const uint64_t* src;                // FIRST pass: the plain 8-byte key column itself (in_key unused)
-    int src_kind;                       // FIRST pass: 0 uint64, 1 int64, 2 float64
-    int desc;                           // FIRST pass
+    uint64_t* out_sorted;               // LAST pass, optional: the sorted values of the key column itself
+    const uint64_t* src;                // LAST pass + out_sorted: the 8-byte key column (for the codes that do not invert)
+    int src_kind;                       // 0 uint64, 1 int64, 2 float64
+    int desc;
 };
 
 __device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int shift) {
@@ -222,16 +227,12 @@ __device__ __forceinline__ unsigned digit_peers_ballot(uint32_t d, bool in, int 
 
 // LAST: the final pass of the sort writes the permutation itself (row ids widened to int64 into
 // PassParams::out_final, NULL flag dropped) and no keys -- nothing reads them any more -- which saves the
-// 8 B/row key write and the separate widen pass (4 B/row read + 8 B/row write).
-// FIRST: the first pass of a plain 8-byte key computes the codes while it loads (row = in_idx[i], or i
-// itself when there is no running permutation yet), so the prepare pass only builds histograms: no
-// 12 B/row written by prepare and 8 instead of 12 B/row read here.
-// DIRECT: no reorder through shared memory -- every key goes from its register straight to its global
-// position (s_gbase + rank inside the tile's bucket).  A warp's store then touches up to 32 sectors
-// instead of a few contiguous runs, which costs L2 write transactions but no DRAM traffic (the sectors
-// are completed by the neighbouring keys of the same tile before they are evicted), and the kernel needs
-// neither the 48 KB staging buffer nor the last two barriers: more CTAs per SM.  Opt-in, unmeasured.
-template <int RS_ITEMS, int MINB, bool BALLOT, bool LAST = false, bool FIRST = false, bool DIRECT = false>
+// 8 B/row key write and the separate widen pass (4 B/row read + 8 B/row write): C4 7.90 ms against 8.22
+// (profiles/r02_variants.md).  When the caller also wants the first key column in sorted order
+// (`SELECT f3 ... ORDER BY f3`), the same pass writes it too: the code inverts to the value except for
+// NaN payloads and the sign of zero, and those rows fetch the original through their row id -- a random
+// 8-byte gather over the whole column (take_kernel: 2.6 ms at 1e8 rows) becomes 8 B/row of extra writes.
+template <int RS_ITEMS, int MINB, bool BALLOT, bool LAST = false>
 __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __grid_constant__ PassParams p) {
     constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
     extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -259,58 +260,49 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
     for (int k = 0; k < RS_ITEMS; ++k) {
         const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
         if (li < tile_n) {
-            if constexpr (FIRST) {
-                idx[k] = p.in_idx ? (p.in_idx[base + li] & ~RS_NULLBIT) : (uint32_t) (base + li);
-                key[k] = p.src[idx[k]];
-            } else {
-                key[k] = p.in_key[base + li];
-                idx[k] = p.in_idx[base + li];
-            }
+            key[k] = p.in_key[base + li];
+            idx[k] = p.in_idx[base + li];
         } else {
             key[k] = 0;
             idx[k] = 0;
         }
     }
-    if constexpr (FIRST) {
-        const uint64_t flip = p.desc ? ~0ULL : 0ULL;
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) {
-            uint64_t c = key[k];
-            if (p.src_kind == 2) {
-                const double d = __longlong_as_double((long long) c);
-                if (d != d) c = KEY_NAN;
-                else {
-                    if (d == 0.0) c = 0;  // -0.0 -> +0.0
-                    c = f64_to_ordered(c) ^ flip;
-                }
-            } else {
-                c = (p.src_kind == 1 ? (c ^ 0x8000000000000000ULL) : c) ^ flip;
-            }
-            key[k] = c;   // (rows past the end of the tile are never ranked or written)
-        }
-    }
     // ---- stable rank inside the warp's 512 items ----
+    // Lanes with equal digits are found with ballots; the first of them (the leader) bumps the warp's
+    // digit counter by their number with ONE shared atomic and gets the digit's count so far back.
+    // Nothing waits for that value inside the loop -- the __syncwarp only orders the counter updates of
+    // successive items -- so the votes and atomics of RS_RANK_BATCH items are in flight together; round 1 read
+    // and wrote the counter with LDS / STS per item, a serial chain of 16 shared-memory round trips per
+    // tile (short scoreboard 41 % of all stall samples, profiles/r01_sort_pass_ncu_full.md).
+    constexpr int HALF = RS_RANK_BATCH;
 #pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
-        const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
-        const bool in = li < tile_n;
-        const uint32_t d = pass_digit(key[k], idx[k], p.shift);
-        unsigned peers;
-        if constexpr (BALLOT) {
-            peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
-            if (!in) peers = 1u << lane;
-        } else {
-            peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
+    for (int h = 0; h < RS_ITEMS / HALF; ++h) {
+        uint32_t cnt[HALF];
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            const int k = h * HALF + j;
+            const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+            const bool in = li < tile_n;
+            const uint32_t d = pass_digit(key[k], idx[k], p.shift);
+            unsigned peers;
+            if constexpr (BALLOT) {
+                peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
+                if (!in) peers = 1u << lane;
+            } else {
+                peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
+            }
+            const int leader = __ffs(peers) - 1;
+            cnt[j] = 0;
+            if (in && lane == leader) cnt[j] = atomicAdd(&s_wcnt[warp][d], (uint32_t) __popc(peers));
+            rank[k] = (uint32_t) __popc(peers & lt) | ((uint32_t) leader << 16);
+            __syncwarp();
         }
-        const int leader = __ffs(peers) - 1;
-        uint32_t c = 0;
-        if (in && lane == leader) {
-            c = s_wcnt[warp][d];
-            s_wcnt[warp][d] = c + __popc(peers);
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) {
+            const int k = h * HALF + j;
+            const uint32_t c = __shfl_sync(0xffffffffu, cnt[j], (int) (rank[k] >> 16));
+            rank[k] = c + (rank[k] & 0xffffu);
         }
-        c = __shfl_sync(0xffffffffu, c, leader);
-        rank[k] = c + __popc(peers & lt);
-        __syncwarp();
     }
     __syncthreads();
 
@@ -366,53 +358,45 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
     }
     __syncthreads();
 
-    if constexpr (DIRECT) {
+    // ---- reorder inside shared memory, then write bucket runs ----
 #pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) {
-            const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
-            if (li < tile_n) {
-                const uint32_t d = pass_digit(key[k], idx[k], p.shift);
-                const unsigned long long dst = s_gbase[d] + s_wcnt[warp][d] + rank[k];
-                if constexpr (LAST) {
-                    p.out_final[dst] = (int64_t) (idx[k] & ~RS_NULLBIT);
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+        if (li < tile_n) {
+            const uint32_t d = pass_digit(key[k], idx[k], p.shift);
+            const uint32_t pos = s_lb[d] + s_wcnt[warp][d] + rank[k];
+            s_key[pos] = key[k];
+            s_idx[pos] = idx[k];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < tile_n; i += RS_THREADS) {
+        const uint64_t kx = s_key[i];
+        const uint32_t ix = s_idx[i];
+        const uint32_t d = pass_digit(kx, ix, p.shift);
+        const unsigned long long dst = s_gbase[d] + (uint32_t) (i - s_lb[d]);
+        if constexpr (LAST) {
+            const uint32_t row = ix & ~RS_NULLBIT;
+            p.out_final[dst] = (int64_t) row;
+            if (p.out_sorted != nullptr) {
+                const uint64_t o = p.desc ? ~kx : kx;
+                uint64_t v;
+                if (p.src_kind == 2) {
+                    // NaN payloads and -0.0 are not in the code: fetch those rows' originals
+                    v = ordered_to_f64(o);
+                    if (kx >= KEY_NAN || (v << 1) == 0) v = p.src[row];
                 } else {
-                    p.out_key[dst] = key[k];
-                    p.out_idx[dst] = idx[k];
+                    v = p.src_kind == 1 ? (o ^ 0x8000000000000000ULL) : o;
                 }
+                p.out_sorted[dst] = v;
             }
-        }
-    } else {
-        // ---- reorder inside shared memory, then write bucket runs ----
-#pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) {
-            const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
-            if (li < tile_n) {
-                const uint32_t d = pass_digit(key[k], idx[k], p.shift);
-                const uint32_t pos = s_lb[d] + s_wcnt[warp][d] + rank[k];
-                s_key[pos] = key[k];
-                s_idx[pos] = idx[k];
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < tile_n; i += RS_THREADS) {
-            const uint64_t kx = s_key[i];
-            const uint32_t ix = s_idx[i];
-            const uint32_t d = pass_digit(kx, ix, p.shift);
-            const unsigned long long dst = s_gbase[d] + (uint32_t) (i - s_lb[d]);
-            if constexpr (LAST) {
-                p.out_final[dst] = (int64_t) (ix & ~RS_NULLBIT);
-            } else {
-                p.out_key[dst] = kx;
-                p.out_idx[dst] = ix;
-            }
+        } else {
+            p.out_key[dst] = kx;
+            p.out_idx[dst] = ix;
         }
     }
 }
 
-__global__ void __launch_bounds__(256) sort_iota_kernel(uint32_t* idx, int64_t n) {
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) idx[i] = (uint32_t) i;
-}
 __global__ void __launch_bounds__(256) sort_widen_kernel(const uint32_t* idx, int64_t n, int64_t* out) {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -437,25 +421,6 @@ __global__ void __launch_bounds__(256) take_kernel(const __grid_constant__ TakeP
         else if (es == 2) reinterpret_cast<uint16_t*>(p.out)[i] = reinterpret_cast<const uint16_t*>(p.col.data)[src];
         else reinterpret_cast<uint8_t*>(p.out)[i] = p.col.data[src];
         if (p.out_valid) p.out_valid[i] = col_valid(p.col, src);
-    }
-}
-
-// 8-byte elements, no validity: U independent gathers in flight per thread (opt-in, VINUM_B200_TAKE_U;
-// measured no faster than take_kernel -- 2.62 vs 2.64 ms at 1e8 rows -- so it stays off).
-template <int U>
-__global__ void __launch_bounds__(256) take8_kernel(const uint64_t* __restrict__ data, const int64_t* __restrict__ indices,
-                                                    int64_t n, uint64_t* __restrict__ out) {
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t i0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * U) {
-        int64_t src[U];
-        uint64_t v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) src[u] = (i0 + u * stride) < n ? indices[i0 + u * stride] : 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = (i0 + u * stride) < n ? data[src[u]] : 0ULL;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if ((i0 + u * stride) < n) out[i0 + u * stride] = v[u];
     }
 }
 
@@ -584,8 +549,8 @@ uint64_t vk_sort_scratch_bytes(int64_t n_rows) {
     return carve(n_rows, nullptr, nullptr);
 }
 
-int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int64_t n_rows,
-                    int64_t* out_indices, void* scratch, VkStream stream) {
+static int sort_indices_impl(const VkColumn* keys, const int32_t* orders, int n_keys, int64_t n_rows,
+                             int64_t* out_indices, void* out_key0_sorted, void* scratch, VkStream stream) {
     VK_REQUIRE(keys && orders && n_keys >= 1, "vk_sort_indices: at least one sort key is required");
     VK_REQUIRE(n_rows >= 0, "vk_sort_indices: negative n_rows");
     if (n_rows == 0) return VK_OK;
@@ -597,56 +562,29 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         VK_REQUIRE(keys[k].length == n_rows, "vk_sort_indices: key length != n_rows");
         VK_REQUIRE(orders[k] == VK_ASC || orders[k] == VK_DESC, "vk_sort_indices: bad sort order");
     }
+    if (out_key0_sorted != nullptr) {
+        VK_REQUIRE(keys[0].validity == nullptr && !keys[0].nulls_as_nan &&
+                   (keys[0].dtype == VK_F64 || keys[0].dtype == VK_I64 || keys[0].dtype == VK_U64),
+                   "vk_sort_indices_keys: the first key must be a plain 8-byte column without NULLs");
+    }
     cudaStream_t s = (cudaStream_t) stream;
     SortScratch sc;
     carve(n_rows, scratch, &sc);
-    // tile geometry: keys per thread x resident CTAs per SM the kernel is compiled for (measured, profiles/)
-    static int cfg = -1;
-    if (cfg < 0) { const char* v = getenv("VINUM_B200_SORT_CFG"); cfg = v ? atoi(v) : 9; }
-    int items;
-    bool direct = false;
-    void (*pass_kernel)(PassParams);
-    switch (cfg) {
-        case 0: items = 16; pass_kernel = sort_pass_kernel<16, 2, false>; break;
-        case 1: items = 16; pass_kernel = sort_pass_kernel<16, 3, false>; break;   // MATCH.ANY ranking
-        case 2: items = 12; pass_kernel = sort_pass_kernel<12, 3, false>; break;
-        case 4: items = 8; pass_kernel = sort_pass_kernel<8, 4, false>; break;
-        case 8: items = 16; pass_kernel = sort_pass_kernel<16, 2, true>; break;
-        case 10: items = 12; pass_kernel = sort_pass_kernel<12, 3, true>; break;
-        case 11: items = 12; pass_kernel = sort_pass_kernel<12, 4, true>; break;
-        case 12: items = 8; pass_kernel = sort_pass_kernel<8, 4, true>; break;
-        // direct scatter (no shared-memory reorder, no dynamic shared memory): opt-in, unmeasured
-        case 20: items = 16; direct = true; pass_kernel = sort_pass_kernel<16, 3, true, false, false, true>; break;
-        case 21: items = 8; direct = true; pass_kernel = sort_pass_kernel<8, 5, true, false, false, true>; break;
-        case 22: items = 8; direct = true; pass_kernel = sort_pass_kernel<8, 6, true, false, false, true>; break;
-        default: items = 16; pass_kernel = sort_pass_kernel<16, 3, true>; break;   // ballot ranking
-    }
+    // tile geometry (measured, profiles/r01_tuning.md): 16 keys per thread, compiled for 3 CTAs per SM
+    constexpr int items = 16;
+    void (*pass_kernel)(PassParams) = sort_pass_kernel<items, 3, true>;
+    void (*last_kernel)(PassParams) = sort_pass_kernel<items, 3, true, true>;
     const int tile_keys = RS_THREADS * items;
     const int64_t tiles = (n_rows + tile_keys - 1) / tile_keys;
     // only the status rows of this geometry's tiles are cleared per pass (the array is sized for the smallest tile)
     const size_t status_used = (size_t) tiles * 256 * sizeof(unsigned long long);
-    const size_t pass_smem = direct ? 0 : (size_t) tile_keys * 12;
+    const size_t pass_smem = (size_t) tile_keys * 12;
     VK_CUDA(cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pass_smem));
-    // opt-in, unmeasured: the last pass writes out_indices directly (default geometry only)
-    static int fuse_last = -1;
-    if (fuse_last < 0) { const char* v = getenv("VINUM_B200_SORT_FUSE_LAST"); fuse_last = v ? atoi(v) : 0; }
-    void (*last_kernel)(PassParams) = nullptr;
-    if (fuse_last && pass_kernel == sort_pass_kernel<16, 3, true>) {
-        last_kernel = sort_pass_kernel<16, 3, true, true>;
-        VK_CUDA(cudaFuncSetAttribute(last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
-    }
-    static int fuse_first = -1;
-    if (fuse_first < 0) { const char* v = getenv("VINUM_B200_SORT_FUSE_FIRST"); fuse_first = v ? atoi(v) : 0; }
-    void (*first_kernel)(PassParams) = nullptr, (*first_last_kernel)(PassParams) = nullptr;
-    if (fuse_first && pass_kernel == sort_pass_kernel<16, 3, true>) {
-        first_kernel = sort_pass_kernel<16, 3, true, false, true>;
-        first_last_kernel = sort_pass_kernel<16, 3, true, true, true>;
-        VK_CUDA(cudaFuncSetAttribute(first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
-        VK_CUDA(cudaFuncSetAttribute(first_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_keys * 12));
-    }
+    VK_CUDA(cudaFuncSetAttribute(last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pass_smem));
+    const bool fuse_last = opt(OPT_SORT_FUSE_LAST) != 0;
+    const int prep = (int) opt(OPT_SORT_PREP);  // rows per thread per round of the 8-byte fast path (0: general kernel)
     bool wrote_final = false;
     int cur = 0;            // buffers holding the running (key', idx)
-    bool have_perm = false;
     unsigned long long h_hist[9 * 256];
 
     for (int k = n_keys - 1; k >= 0; --k) {
@@ -655,53 +593,36 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         pp.col = make_col(keys[k]);
         pp.desc = orders[k] == VK_DESC;
         pp.int_nulls = keys[k].validity != nullptr && !dtype_is_float(keys[k].dtype);
-        pp.perm = have_perm ? sc.idx[cur] : nullptr;
+        pp.perm = k < n_keys - 1 ? sc.idx[cur] : nullptr;
         pp.n = n_rows;
         const int nxt = cur ^ 1;
         pp.out_key = sc.key[nxt];
         pp.out_idx = sc.idx[nxt];
         pp.hist = sc.hist;
         VK_CUDA(cudaMemsetAsync(sc.hist, 0, 9 * 256 * 8, s));
-        static int prep = -1;  // rows per thread per round of the 8-byte fast path (0: general kernel)
-        if (prep < 0) { const char* v = getenv("VINUM_B200_SORT_PREP"); prep = v ? atoi(v) : 4; }
         const bool plain8 = keys[k].validity == nullptr && !keys[k].nulls_as_nan &&
                             (keys[k].dtype == VK_F64 || keys[k].dtype == VK_I64 || keys[k].dtype == VK_U64);
-        // fused first pass: prepare builds the histograms only (they do not depend on the row order, so it
-        // reads the column sequentially) and leaves the running permutation where it is
-        const bool fused_first = first_kernel != nullptr && plain8 && prep >= 2 &&
-                                 (reinterpret_cast<uintptr_t>(pp.col.data) & 7) == 0;
-        if (fused_first) {
-            pp.perm = nullptr;
-            pp.out_key = nullptr;
-            pp.out_idx = nullptr;
-        }
         if (prep >= 4 && plain8) sort_prepare8_kernel<4><<<grid_rows(n_rows, 8), 256, 0, s>>>(pp);
         else if (prep >= 2 && plain8) sort_prepare8_kernel<2><<<grid_rows(n_rows, 8), 256, 0, s>>>(pp);
         else sort_prepare_kernel<<<grid_rows(n_rows, 4), 256, 0, s>>>(pp);
         VK_CHECK_LAUNCH("sort_prepare_kernel");
-        bool first_pending = fused_first;
-        if (!fused_first) {
-            cur = nxt;
-            have_perm = true;
-        }
+        cur = nxt;
         VK_CUDA(cudaMemcpyAsync(h_hist, sc.hist, sizeof(h_hist), cudaMemcpyDeviceToHost, s));
         VK_CUDA(cudaStreamSynchronize(s));
         sort_scan_kernel<<<9, 256, 0, s>>>(sc.hist);
         VK_CHECK_LAUNCH("sort_scan_kernel");
         // ---- one pass per digit that actually varies ----
+        bool varies[9];
         int last_d = -1;
         for (int d = 0; d < 9; ++d) {
-            bool varies = true;
+            varies[d] = true;
             for (int b = 0; b < 256; ++b)
-                if (h_hist[d * 256 + b] == (unsigned long long) n_rows) { varies = false; break; }
-            if (varies) last_d = d;
+                if (h_hist[d * 256 + b] == (unsigned long long) n_rows) { varies[d] = false; break; }
+            if (varies[d]) last_d = d;
         }
         for (int d = 0; d < 9; ++d) {
-            bool varies = true;
-            for (int b = 0; b < 256; ++b)
-                if (h_hist[d * 256 + b] == (unsigned long long) n_rows) { varies = false; break; }
-            if (!varies) continue;
-            const bool is_final = last_kernel != nullptr && k == 0 && d == last_d;
+            if (!varies[d]) continue;
+            const bool is_final = (fuse_last || out_key0_sorted != nullptr) && k == 0 && d == last_d;
             PassParams ps{};
             ps.in_key = sc.key[cur];
             ps.in_idx = sc.idx[cur];
@@ -714,24 +635,13 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
             ps.status = sc.status;
             VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
             VK_CUDA(cudaMemsetAsync(sc.status, 0, status_used, s));
-            ps.out_final = out_indices;
-            if (first_pending) {
-                // codes are computed from the column itself; rows come from the running permutation, if any
-                ps.in_key = nullptr;
-                ps.in_idx = have_perm ? sc.idx[cur] : nullptr;
+            if (is_final) {
+                ps.out_final = out_indices;
+                ps.out_sorted = reinterpret_cast<uint64_t*>(out_key0_sorted);
                 ps.src = reinterpret_cast<const uint64_t*>(pp.col.data);
-                ps.src_kind = keys[k].dtype == VK_F64 ? 2 : (keys[k].dtype == VK_I64 ? 1 : 0);
+                ps.src_kind = keys[0].dtype == VK_F64 ? 2 : (keys[0].dtype == VK_I64 ? 1 : 0);
                 ps.desc = pp.desc;
-                if (is_final) {
-                    first_last_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
-                    wrote_final = true;
-                } else {
-                    first_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
-                }
-                first_pending = false;
-                have_perm = true;
-            } else if (is_final) {
-                last_kernel<<<(unsigned) tiles, RS_THREADS, tile_keys * 12, s>>>(ps);
+                last_kernel<<<(unsigned) tiles, RS_THREADS, pass_smem, s>>>(ps);
                 wrote_final = true;
             } else {
                 pass_kernel<<<(unsigned) tiles, RS_THREADS, pass_smem, s>>>(ps);
@@ -741,13 +651,26 @@ int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int
         }
     }
     if (wrote_final) return VK_OK;
-    if (!have_perm) {  // (fused first pass) no key had a varying digit: the permutation is the identity
-        sort_iota_kernel<<<grid_rows(n_rows), 256, 0, s>>>(sc.idx[cur], n_rows);
-        VK_CHECK_LAUNCH("sort_iota_kernel");
-    }
     sort_widen_kernel<<<grid_rows(n_rows), 256, 0, s>>>(sc.idx[cur], n_rows, out_indices);
     VK_CHECK_LAUNCH("sort_widen_kernel");
+    if (out_key0_sorted != nullptr) {
+        // the first key has no varying digit (a constant column): nothing was fused, gather it
+        TakeParams tp{make_col(keys[0]), out_indices, n_rows, out_key0_sorted, nullptr};
+        take_kernel<<<grid_rows(n_rows), 256, 0, s>>>(tp);
+        VK_CHECK_LAUNCH("take_kernel");
+    }
     return VK_OK;
+}
+
+int vk_sort_indices(const VkColumn* keys, const int32_t* orders, int n_keys, int64_t n_rows,
+                    int64_t* out_indices, void* scratch, VkStream stream) {
+    return sort_indices_impl(keys, orders, n_keys, n_rows, out_indices, nullptr, scratch, stream);
+}
+
+int vk_sort_indices_keys(const VkColumn* keys, const int32_t* orders, int n_keys, int64_t n_rows,
+                         int64_t* out_indices, void* out_key0_sorted, void* scratch, VkStream stream) {
+    VK_REQUIRE(out_key0_sorted, "vk_sort_indices_keys: out_key0_sorted is NULL");
+    return sort_indices_impl(keys, orders, n_keys, n_rows, out_indices, out_key0_sorted, scratch, stream);
 }
 
 uint64_t vk_topk_scratch_bytes(void) { return 257 * sizeof(unsigned long long); }
@@ -829,16 +752,6 @@ int vk_take(const VkColumn* col, const int64_t* indices, int64_t n_indices, void
     VK_REQUIRE(dtype_valid(col->dtype), "vk_take: bad dtype");
     VK_REQUIRE(col->validity == nullptr || out_valid_bytes, "vk_take: column has validity but no out_valid_bytes");
     TakeParams p{make_col(*col), indices, n_indices, out, col->validity ? out_valid_bytes : nullptr};
-    static int take_u = -1;
-    if (take_u < 0) { const char* v = getenv("VINUM_B200_TAKE_U"); take_u = v ? atoi(v) : 0; }
-    if (take_u >= 2 && dtype_size(col->dtype) == 8 && col->validity == nullptr &&
-        ((reinterpret_cast<uintptr_t>(p.col.data) | reinterpret_cast<uintptr_t>(out)) & 7) == 0) {
-        const uint64_t* d = reinterpret_cast<const uint64_t*>(p.col.data);
-        if (take_u >= 4) take8_kernel<4><<<grid_rows(n_indices), 256, 0, (cudaStream_t) stream>>>(d, indices, n_indices, (uint64_t*) out);
-        else take8_kernel<2><<<grid_rows(n_indices), 256, 0, (cudaStream_t) stream>>>(d, indices, n_indices, (uint64_t*) out);
-        VK_CHECK_LAUNCH("take8_kernel");
-        return VK_OK;
-    }
     take_kernel<<<grid_rows(n_indices), 256, 0, (cudaStream_t) stream>>>(p);
     VK_CHECK_LAUNCH("take_kernel");
     return VK_OK;

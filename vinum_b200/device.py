@@ -169,7 +169,8 @@ class DeviceBuffer:
     def from_host(address: int, nbytes: int, stream: Optional[Stream] = None) -> "DeviceBuffer":
         buf = DeviceBuffer(nbytes, stream)
         if nbytes:
-            lib.vk_memcpy_h2d(C.c_void_p(buf.ptr), C.c_void_p(address), int(nbytes), _sp(stream))
+            # pinned / registered source: plain DMA; pageable: the pinned bounce-buffer pool (vk_ingest.cu)
+            lib.vk_memcpy_h2d_auto(C.c_void_p(buf.ptr), C.c_void_p(address), int(nbytes), _sp(stream))
         return buf
 
     @staticmethod

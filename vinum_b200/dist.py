@@ -76,6 +76,80 @@ def all_to_all_records(send: "torch.Tensor", send_sizes: Sequence[int], recv_siz
     return recv[: total * words]
 
 
+PEER_OK, PEER_OVERFLOW, PEER_NEED_GROW, PEER_TIMEOUT = 1, 2, 3, 4
+_MAX_RECORD_WORDS = 8 + 2 + 3 * 16   # VK_AGG_MAX_KEYS + nullmask + count + 3 words per function (16 functions)
+
+
+class PeerWindow:
+    """This rank's exchange window (include/vinum_b200.h "peer exchange") with every peer's window
+    mapped through cudaIpc.  One per process group, created on first use (the handle exchange is the
+    only collective it ever runs); `next_epoch()` numbers the queries, identically on every rank."""
+
+    def __init__(self, group=None, cap_groups: int = 4096):
+        import torch
+        import torch.distributed as dist
+        from .device import PinnedBuffer
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.cap = cap_groups
+        h = C.c_void_p()
+        lib.vk_peer_create(C.byref(h), self.rank, self.world, cap_groups, _MAX_RECORD_WORDS)
+        self._h = h
+        mine = C.create_string_buffer(64)
+        lib.vk_peer_handle(h, mine)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw), group=group)
+        for r, raw in enumerate(handles):
+            if r != self.rank:
+                lib.vk_peer_open(h, r, C.create_string_buffer(raw, 64))
+        self.epoch = 0
+        self._pinned = PinnedBuffer(64)
+        self.host_word = self._pinned.as_numpy(np.uint64, 8)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)   # every window is mapped before anybody writes into one
+
+    def next_epoch(self) -> int:
+        self.epoch += 1
+        return self.epoch
+
+    def decision_ptr(self, epoch: int) -> int:
+        return int(L._lib.vk_peer_decision_ptr(self._h, epoch))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L._lib.vk_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+_WINDOWS = {}
+
+
+def peer_window(group=None) -> "PeerWindow":
+    key = id(group) if group is not None else 0
+    w = _WINDOWS.get(key)
+    if w is None:
+        w = _WINDOWS[key] = PeerWindow(group)
+    return w
+
+
+def close_peer_windows() -> None:
+    """Unmap and free the exchange windows (before `destroy_process_group`)."""
+    for w in _WINDOWS.values():
+        w.close()
+    _WINDOWS.clear()
+
+
+def exchange_mode() -> str:
+    """`peer` (default on CUDA + NCCL: no collective on the query path), `allgather` (round 1: one
+    all-gather of fixed-size blocks + merge on rank 0) or `repartition` (always the all-to-all)."""
+    import os
+    import torch.distributed as dist
+    mode = os.environ.get("VINUM_B200_DIST_MODE", "peer")
+    if mode == "peer" and dist.get_backend() != "nccl":
+        mode = "allgather"
+    return mode
+
+
 class DistributedAggregator:
     """Local Aggregator + partial-group repartition.  `gather_raw()` returns, on rank 0, the
     raw finalised groups of the whole job (same tuple as Aggregator.result_raw); None on
@@ -172,9 +246,12 @@ class DistributedAggregator:
         import os
         if self.world == 1:
             return self.agg.result_raw(self.stream)
-        if os.environ.get("VINUM_B200_DIST_MODE") == "repartition":   # A/B switch for tuning runs
+        mode = exchange_mode()
+        if mode == "repartition":   # A/B switch for tuning runs
             self.repartition()
             return self.gather_raw()
+        if mode == "peer" and len(self.agg.key_vk) > 0:
+            return self._finish_peer()
         self._mark("local aggregate")
         st = self.stream
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -213,6 +290,38 @@ class DistributedAggregator:
         self.agg.close()
         self.agg = fresh
         return raw
+
+    def _finish_peer(self):
+        """The low-cardinality exchange without a collective: every rank's kernel stores its partial
+        groups into rank 0's window over NVLink and releases a flag; rank 0's kernels acquire the
+        flags, merge into rank 0's own table and acknowledge; ONE host synchronisation per rank (the
+        final read-back on rank 0, the decision word elsewhere)."""
+        self._mark("local aggregate")
+        st = self.stream
+        win = peer_window(self.group)
+        epoch = win.next_epoch()
+        dptr = win.decision_ptr(epoch)
+        haddr = win._pinned.ptr
+        raw = None
+        if self.rank == 0:
+            lib.vk_agg_peer_merge(self.agg._h, win._h, epoch, st.ptr)
+            raw = self.agg.result_raw(st, extra_d2h=(haddr, dptr, 8))
+        else:
+            lib.vk_agg_peer_send(self.agg._h, win._h, 0, epoch, st.ptr)
+            lib.vk_memcpy_d2h(C.c_void_p(haddr), C.c_void_p(dptr), 8, st.ptr)
+            st.sync()
+        decision = int(win.host_word[0])
+        self._mark("peer exchange + merge + read-back")
+        self.exchange_mode_used = "peer"
+        if decision == PEER_OK:
+            return raw
+        if decision in (PEER_OVERFLOW, PEER_NEED_GROW):
+            # unanimous (rank 0 wrote the same word into every window): nothing was merged
+            self.exchange_mode_used = "peer->repartition"
+            self.repartition()
+            return self.gather_raw()
+        raise RuntimeError(f"vinum_b200.dist: peer exchange failed on rank {self.rank} (decision {decision}: "
+                           "a peer did not answer within 4 s)")
 
     def gather_raw(self):
         """Concatenate every rank's finalised groups on rank 0 (after repartition each
@@ -295,6 +404,25 @@ def merge_sorted_runs(keys: Sequence[np.ndarray], row_ids: Sequence[np.ndarray],
     return k[order], ids[order]
 
 
+def _key_bits64(keys: np.ndarray) -> np.ndarray:
+    """Sort keys as int64 words for the wire, losslessly: 8-byte types are reinterpreted, narrower
+    floats widen to float64 first (exact, NaN / inf included), narrower integers sign / zero extend."""
+    if keys.dtype.itemsize == 8:
+        return keys.view(np.int64)
+    if keys.dtype.kind == "f":
+        return keys.astype(np.float64).view(np.int64)
+    return keys.astype(np.int64)
+
+
+def _key_from_bits64(words: np.ndarray, dtype) -> np.ndarray:
+    dtype = np.dtype(dtype)
+    if dtype.itemsize == 8:
+        return words.view(dtype)
+    if dtype.kind == "f":
+        return words.view(np.float64).astype(dtype)
+    return words.astype(dtype)
+
+
 def sort_sharded(column, row0: int, descending: bool, stream, group=None):
     """ORDER BY one numeric column over row-range shards: every rank sorts its shard on the
     device (stable LSD radix sort), rank 0 gathers the sorted (key, global row id) runs and
@@ -316,7 +444,7 @@ def sort_sharded(column, row0: int, descending: bool, stream, group=None):
     sizes = [int(x.item()) for x in sizes]
     nmax = max(max(sizes), 1)
     pack = np.zeros((2, nmax), dtype=np.int64)
-    pack[0, :len(ids)] = keys_sorted.view(np.int64) if keys_sorted.dtype.itemsize == 8 else keys_sorted.astype(np.int64)
+    pack[0, :len(ids)] = _key_bits64(keys_sorted)
     pack[1, :len(ids)] = ids
     t = torch.from_numpy(pack).to(dev)
     gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
@@ -326,7 +454,6 @@ def sort_sharded(column, row0: int, descending: bool, stream, group=None):
     runs_k, runs_i = [], []
     for g, s in zip(gathered, sizes):
         a = g.cpu().numpy()
-        kk = a[0, :s].view(keys_sorted.dtype) if keys_sorted.dtype.itemsize == 8 else a[0, :s].astype(keys_sorted.dtype)
-        runs_k.append(kk)
+        runs_k.append(_key_from_bits64(a[0, :s], keys_sorted.dtype))
         runs_i.append(a[1, :s])
     return merge_sorted_runs(runs_k, runs_i, descending)

@@ -3,8 +3,9 @@
 The reference's executor pulls 10 000-row RecordBatches through the operator chain on
 one CPU thread (vinum/executor/executor.py:24-31, vinum/core/base.py:254-260).  Here
 the RecordBatch stream is cut into large chunks, each chunk's referenced columns are
-copied host -> device with cudaMemcpyAsync on a copy stream (true DMA when the Arrow
-buffers are pinned) into one of two device staging slots, and the fused
+copied host -> device on a copy stream (plain DMA when the Arrow buffers are pinned, through
+the library's pinned bounce-buffer pool when they are pageable -- vk_memcpy_h2d_auto) into
+one of two device staging slots, and the fused
 filter -> aggregate kernel consumes slot k on the compute stream while slot k+1 is in
 flight -- the WHERE mask and the filtered rows are never materialised
 (FilterOperator + AggregateOperator fused; vinum/core/algebra.py:108-123,
@@ -60,14 +61,18 @@ class _StagingSlot:
 
 def filter_aggregate(table: pa.Table, groupby: Sequence[str], funcs: Sequence[Tuple[str, str, str]],
                      where: Optional[Tuple[str, str, object]] = None, chunk_rows: int = DEFAULT_CHUNK_ROWS,
-                     expected_groups: int = 0, stats: Optional[dict] = None) -> pa.RecordBatch:
+                     expected_groups: int = 0, stats: Optional[dict] = None, exchange=None) -> pa.RecordBatch:
     """`SELECT <groupby>, <funcs> FROM table [WHERE col <op> literal] GROUP BY <groupby>` over a
     HOST pyarrow.Table, end to end on the GPU.
 
     funcs = [(type, column, out_name)], type in COUNT_STAR/COUNT/MIN/MAX/SUM/AVG.
     Columns must be null-free fixed-width numerics (the fused fast path); use
     vinum_b200.vinum_lib for the general case.  Result column order and types are the
-    reference's: group-by columns, then one column per function (base_aggregate.cpp:47-68)."""
+    reference's: group-by columns, then one column per function (base_aggregate.cpp:47-68).
+
+    `exchange(aggregator, stream) -> raw groups` (vinum_b200.sharded): `table` is this rank's row-range
+    shard and the partial groups of every rank are merged before they are finalised; the ranks that
+    do not own the result return zero groups."""
     schema = table.schema
     used: List[str] = []
     for name in list(groupby) + [c for _, c, _ in funcs if c] + ([where[0]] if where else []):
@@ -115,8 +120,9 @@ def filter_aggregate(table: pa.Table, groupby: Sequence[str], funcs: Sequence[Tu
             lib.vk_stream_wait_event(copy.ptr, slot.consumed.h)
         for name, dt in zip(used, dtypes):
             nbytes = rows * VK_SIZE[dt]
-            lib.vk_memcpy_h2d(C.c_void_p(slot.bufs[name].ptr), C.c_void_p(host_ptrs[name] + pos * VK_SIZE[dt]),
-                              nbytes, copy.ptr)
+            # pinned Arrow buffers are DMA'd in place; pageable ones go through the pinned bounce pool
+            lib.vk_memcpy_h2d_auto(C.c_void_p(slot.bufs[name].ptr), C.c_void_p(host_ptrs[name] + pos * VK_SIZE[dt]),
+                                   nbytes, copy.ptr)
             h2d_bytes += nbytes
         slot.copied.record(copy)
         # the compute stream waits for this slot's copies; the host runs ahead and queues the
@@ -130,7 +136,11 @@ def filter_aggregate(table: pa.Table, groupby: Sequence[str], funcs: Sequence[Tu
         slot.used = True
         pos += rows
         k += 1
-    key_arrays, agg_arrays = agg.result_arrays(compute)
+    if exchange is not None:
+        agg, raw = exchange(agg, compute)
+        key_arrays, agg_arrays = agg.result_arrays(compute, raw=raw)
+    else:
+        key_arrays, agg_arrays = agg.result_arrays(compute)
     arrays = list(key_arrays) + list(agg_arrays)
     names = list(groupby) + [o for _, _, o in funcs]
     out = pa.RecordBatch.from_arrays(arrays, names=names)

@@ -7,7 +7,7 @@ function here computes on the host.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Union
+from typing import Tuple, List, Optional, Sequence, Union
 
 import numpy as np
 import pyarrow as pa
@@ -301,6 +301,29 @@ def sort_indices(keys: Sequence[DeviceColumn], orders: Sequence[int], stream: Op
     return out
 
 
+def sort_indices_keys(keys: Sequence[DeviceColumn], orders: Sequence[int],
+                      stream: Optional[Stream] = None) -> Tuple[DeviceColumn, Optional[DeviceColumn]]:
+    """`sort_indices` that also returns keys[0] in sorted order when the last radix pass can write it
+    (plain 8-byte column without NULLs: vk_sort_indices_keys) -- Sort::Sorted gathers every column, the
+    sort key included (sort.cpp:40-48), and this saves that column's random gather.  (permutation, None)
+    when keys[0] does not qualify."""
+    st = stream or default_stream()
+    k0 = keys[0]
+    n = k0.length
+    if n == 0 or k0.has_nulls or k0.dtype not in (L.F64, L.I64, L.U64) or (k0.data_ptr + k0.offset * 8) % 8:
+        return sort_indices(keys, orders, st), None
+    out = DeviceColumn.empty(n, L.I64, pa.int64(), st)
+    sorted0 = DeviceColumn.empty(n, k0.dtype, k0.arrow_type, st)
+    vk = (L.VkColumn * len(keys))()
+    for i, k in enumerate(keys):
+        vk[i] = k.vk()
+    ords = (C.c_int32 * len(keys))(*[int(o) for o in orders])
+    scratch = DeviceBuffer(lib.vk_sort_scratch_bytes(n), st)
+    lib.vk_sort_indices_keys(vk, ords, len(keys), n, C.c_void_p(out.data_ptr), C.c_void_p(sorted0.data_ptr),
+                             C.c_void_p(scratch.ptr), st.ptr)
+    return out, sorted0
+
+
 def topk_candidates(key: DeviceColumn, order: int, k: int, stream: Optional[Stream] = None) -> Optional[DeviceColumn]:
     """Row ids (int64, unordered) of a superset of the first `k` rows of `ORDER BY key <order>`, or
     None when selecting does not pay and the caller should sort every row (vk_topk_candidates)."""
@@ -338,6 +361,7 @@ def sort_batch(batch: DeviceBatch, key_names: Sequence[str], orders: Sequence[in
                stream: Optional[Stream] = None) -> DeviceBatch:
     """SortIndices + Take of every column (Sort::Sorted, sort.cpp:15-63)."""
     st = stream or default_stream()
-    idx = sort_indices([batch.column(k) for k in key_names], orders, st)
-    cols = [take(c, idx, st) for c in batch.columns]
+    keys = [batch.column(k) for k in key_names]
+    idx, sorted0 = sort_indices_keys(keys, orders, st)
+    cols = [sorted0 if (sorted0 is not None and c is keys[0]) else take(c, idx, st) for c in batch.columns]
     return DeviceBatch(cols, batch.column_names, batch.num_rows)

@@ -113,9 +113,12 @@ class Frame:
 
 
 class Engine:
-    def __init__(self, table: pa.Table, stream: Optional[Stream] = None):
+    def __init__(self, table: pa.Table, stream: Optional[Stream] = None, exchange=None):
         self.table = table
         self._st = stream
+        # sharded execution (vinum_b200.sharded): `table` is this rank's row range; aggregate results go
+        # through `exchange(aggregator, stream) -> (aggregator, raw groups)` before they are finalised
+        self.exchange = exchange
         self.stats = {"kernels_before": int(L.lib.vk_launch_count())}
 
     @property
@@ -432,15 +435,20 @@ class Engine:
         if 0 < m < frame.n and frame.n >= _TOPK_MIN_ROWS and os.environ.get("VINUM_B200_TOPK", "1") != "0":
             # radix select of the LIMIT's rows, then a sort of those only (1e8 rows, k <= 1e5: 1.7 ms vs 8.6 ms)
             idx = ops.sort_top(dev_keys, dev_orders, m, self.st)
+            sorted0 = None
             self.stats["sort_topk"] = True
         else:
-            idx = ops.sort_indices(dev_keys, dev_orders, self.st)
+            # the first key's own column comes out of the last radix pass already sorted (no gather)
+            idx, sorted0 = ops.sort_indices_keys(dev_keys, dev_orders, self.st)
             if m < frame.n:
                 idx = idx.slice(0, m)
+                sorted0 = sorted0.slice(0, m) if sorted0 is not None else None
         out = Frame(m)
         hidx = None
         for name, v in frame.cols.items():
-            if isinstance(v, DeviceColumn):
+            if sorted0 is not None and v is dev_keys[0]:
+                out.cols[name] = sorted0
+            elif isinstance(v, DeviceColumn):
                 out.cols[name] = ops.take(v, idx, self.st)
             else:
                 if hidx is None:
@@ -520,7 +528,7 @@ class Engine:
         if dry_run:
             return Frame(0), {}
         stats: dict = {}
-        rb = filter_aggregate(self.table, keys, funcs, where, stats=stats)
+        rb = filter_aggregate(self.table, keys, funcs, where, stats=stats, exchange=self.exchange)
         self.stats.update({"agg_path": stats.get("agg_path"), "streamed": True, "h2d_bytes": stats.get("h2d_bytes"),
                            "d2h_bytes": stats.get("d2h_bytes")})
         out = Frame(rb.num_rows)
@@ -629,8 +637,17 @@ class Engine:
     def _agg_finish(self, state: "_AggState") -> Tuple[Frame, Dict]:
         """AggregateOperator result (aggregate.py:122): finalise, read the groups back, give
         dictionary-coded / boolean keys their user types again."""
-        keys_out, aggs_out = state.agg.result_arrays(self.st)
-        self.stats["agg_path"] = state.agg.last_path
+        if self.exchange is not None:
+            if any(kind is not None for kind in state.key_kind):
+                raise OperatorError("sharded execution: GROUP BY over string / boolean keys needs a shared "
+                                    "dictionary across ranks, which is not implemented")
+            local_path = state.agg.last_path
+            state.agg, raw = self.exchange(state.agg, self.st)
+            keys_out, aggs_out = state.agg.result_arrays(self.st, raw=raw)
+            self.stats["agg_path"] = local_path
+        else:
+            keys_out, aggs_out = state.agg.result_arrays(self.st)
+            self.stats["agg_path"] = state.agg.last_path
         self.stats["agg_batches"] = state.batches
         out = Frame(len(aggs_out[0]) if aggs_out else (len(keys_out[0]) if keys_out else 1))
         resolved: Dict = {}
@@ -833,11 +850,11 @@ CHUNK_ROWS = 1 << 26   # tables above this are executed as a stream of zero-copy
 
 
 def execute_sql(sql: str, table: pa.Table, stream: Optional[Stream] = None, stats: Optional[dict] = None,
-                chunk_rows: int = CHUNK_ROWS) -> pa.Table:
+                chunk_rows: int = CHUNK_ROWS, exchange=None) -> pa.Table:
     """Parse + plan + run one SELECT over a host pyarrow.Table; the result is a host table."""
     q = parse_sql(sql, table.schema.names)
-    eng = Engine(table, stream)
-    if table.num_rows > chunk_rows:
+    eng = Engine(table, stream, exchange)
+    if table.num_rows > chunk_rows and exchange is None:
         bound = eng._bind(q)
         if not (bound.is_aggregate and eng._streamable(bound)):
             # bound the device footprint: the table goes through in row slices

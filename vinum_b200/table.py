@@ -35,6 +35,13 @@ class Table:
     def from_pandas(cls, data_frame) -> "Table":
         return cls(pa.Table.from_pandas(data_frame))
 
+    def shard(self, group=None):
+        """This table as ONE rank's row range of a logical table spread over the GPUs of a `torchrun`
+        job: `shard().sql(query)` is collective and returns the whole answer on rank 0
+        (vinum_b200.sharded)."""
+        from .sharded import ShardedTable
+        return ShardedTable(self._table, group)
+
     # ------------------------------------------------------------------ query
     def sql(self, query: str) -> "Table":
         """Run a SELECT over this table (vinum/api/table.py:191-274)."""

@@ -23,10 +23,11 @@ import enum
 from typing import List, Optional, Sequence
 
 import pyarrow as pa
+import pyarrow.compute as pc
 
 from . import _lib as L
 from .aggregate import Aggregator
-from .device import DeviceBatch, DeviceColumn, Stream, default_stream
+from .device import DeviceBatch, DeviceColumn, Stream, default_stream, vk_dtype_of
 from . import ops
 
 
@@ -403,23 +404,55 @@ class Sort:
         st = self._stream
         if all(isinstance(b, DeviceBatch) for b in self._batches) and len(self._batches) == 1:
             dev = self._batches[0]
-            schema = dev.schema()
-        else:
-            host = [b.to_arrow(st) if isinstance(b, DeviceBatch) else b for b in self._batches]
-            table = pa.Table.from_batches([b for b in host]) if not isinstance(host[0], pa.Table) else pa.concat_tables(host)
-            table = table.combine_chunks()
-            schema = table.schema
             for name in self._cols:
-                if schema.get_field_index(name) == -1:
-                    raise RuntimeError("Failed to sort table.")  # sort.cpp:34-36
-            dev = DeviceBatch.from_arrow(table, st)
+                if name not in dev.column_names:
+                    raise RuntimeError("Failed to sort table.")
+                if pa.types.is_boolean(dev.column(name).arrow_type):
+                    raise RuntimeError("Failed to sort table.")  # Arrow 3.0 could not sort booleans (algebra.py:191-201)
+            return ops.sort_batch(dev, self._cols, self._order, st).to_arrow(st)
+        host = [b.to_arrow(st) if isinstance(b, DeviceBatch) else b for b in self._batches]
+        table = pa.Table.from_batches([b for b in host]) if not isinstance(host[0], pa.Table) else pa.concat_tables(host)
+        table = table.combine_chunks()
+        schema = table.schema
         for name in self._cols:
-            if name not in dev.column_names:
-                raise RuntimeError("Failed to sort table.")
-            if pa.types.is_boolean(dev.column(name).arrow_type):
+            if schema.get_field_index(name) == -1:
+                raise RuntimeError("Failed to sort table.")  # sort.cpp:34-36
+            if pa.types.is_boolean(schema.field(name).type):
                 raise RuntimeError("Failed to sort table.")  # Arrow 3.0 could not sort booleans (algebra.py:191-201)
-        out = ops.sort_batch(dev, self._cols, self._order, st)
-        return out.to_arrow(st)
+        # The reference hands the WHOLE batch to Sort (algebra.py:160-175): string payload columns and
+        # string sort keys included.  Only fixed-width columns live on the device: string keys sort by
+        # order-preserving rank codes (NULL stays NULL -> last), string payloads are taken on the host
+        # with the device permutation.
+        dev_names = [f.name for f in schema if vk_dtype_of(f.type) is not None]
+        host_names = [f.name for f in schema if vk_dtype_of(f.type) is None]
+        keys = []
+        for name in self._cols:
+            col = table.column(name)
+            if name in host_names:
+                arr = col.chunk(0) if col.num_chunks == 1 else col.combine_chunks()
+                uniq = pc.unique(arr).drop_null()
+                ranked = uniq.take(pc.sort_indices(uniq))
+                keys.append(DeviceColumn.from_arrow(pc.index_in(arr, value_set=ranked), st))
+            else:
+                keys.append(None)
+        dev = DeviceBatch.from_arrow(table.select(dev_names), st) if dev_names else None
+        keys = [k if k is not None else dev.column(name) for k, name in zip(keys, self._cols)]
+        idx, sorted0 = ops.sort_indices_keys(keys, self._order, st)
+        arrays = {}
+        for name in dev_names:
+            c = dev.column(name)
+            arrays[name] = (sorted0 if (sorted0 is not None and c is keys[0]) else ops.take(c, idx, st)).to_arrow(st)
+        if host_names:
+            hidx = pa.array(idx.to_numpy(st))
+            for name in host_names:
+                arrays[name] = table.column(name).combine_chunks().take(hidx)
+        return pa.RecordBatch.from_arrays([_as_array(arrays[f.name]) for f in schema], schema=schema)
+
+
+def _as_array(a):
+    if isinstance(a, pa.ChunkedArray):
+        return a.chunk(0) if a.num_chunks == 1 else pa.concat_arrays(a.chunks) if a.num_chunks else pa.array([], type=a.type)
+    return a
 
 
 class TableBatchReader:
