@@ -175,13 +175,37 @@ int vk_bits_to_mask(const uint8_t* bits, int64_t bit_offset, int64_t n, uint8_t*
  * elements; out_valid_bytes[i] (may be NULL when cols[i].validity is NULL)
  * receives one validity byte per selected row.  *out_rows (device int64) receives
  * the number of selected rows.  `scratch` is vk_filter_scratch_bytes(n) bytes. */
-typedef enum VkPredKind { VK_PRED_NONE = 0, VK_PRED_MASK = 1, VK_PRED_CMP = 2 } VkPredKind;
+typedef enum VkPredKind { VK_PRED_NONE = 0, VK_PRED_MASK = 1, VK_PRED_CMP = 2, VK_PRED_EXPR = 3 } VkPredKind;
+/* Fused expression chain (row a3): t0 <op1> t1 <op2> t2 ..., evaluated strictly left to right in
+ * registers with NumPy's promotion per step (int64 op int64 wraps and stays int64 except `/`; anything
+ * with a float64 is float64) -- what VectorizedExpression.evaluate (vinum/core/base.py:105-125) computes
+ * node by node with one materialised array per node.  Terms: int64 / float64 columns without validity,
+ * int64 / float64 scalars; ops: VK_ADD..VK_BITXOR (declared below). */
+#define VK_EXPR_MAX_TERMS 4
+typedef struct VkExprTerm {
+    VkColumn column;       /* is_column != 0 */
+    VkScalar scalar;       /* is_column == 0 */
+    int32_t is_column;
+    int32_t op;            /* VkArithOp: acc = acc <op> term; ignored for the first term */
+} VkExprTerm;
+typedef struct VkExprChain {
+    int32_t n_terms;       /* 1 .. VK_EXPR_MAX_TERMS */
+    int32_t _pad;
+    VkExprTerm terms[VK_EXPR_MAX_TERMS];
+} VkExprChain;
+typedef struct VkExprCompare {
+    VkExprChain lhs;
+    VkExprChain rhs;
+    int32_t op;            /* VkCmpOp */
+    int32_t _pad;
+} VkExprCompare;
 typedef struct VkPredicate {
     int32_t kind;          /* VkPredKind                                   */
     int32_t op;            /* VkCmpOp (VK_PRED_CMP)                        */
     const uint8_t* mask;   /* VK_PRED_MASK: one byte per row               */
     VkColumn column;       /* VK_PRED_CMP: left-hand side                  */
     VkScalar scalar;       /* VK_PRED_CMP: right-hand side                 */
+    const VkExprCompare* expr;  /* VK_PRED_EXPR: <chain> <cmp> <chain>, e.g. WHERE a * 10 > b */
 } VkPredicate;
 uint64_t vk_filter_scratch_bytes(int64_t n_rows);
 int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int n_cols,
@@ -202,6 +226,11 @@ typedef enum VkArithOp {
  * side is entirely NULL. */
 int vk_arith(int op, const VkColumn* lhs_col, const VkScalar* lhs_scalar, const VkColumn* rhs_col,
              const VkScalar* rhs_scalar, int64_t n_rows, int out_dtype, void* out, VkStream stream);
+/* A whole chain in one pass (`SELECT a * 10 + b`): out = n_rows int64 or float64 values, *out_dtype tells
+ * which (VK_I64 / VK_F64, decided by the promotion rules above).  vk_expr_compare: <chain> <cmp> <chain>
+ * -> one mask byte per row. */
+int vk_expr_eval(const VkExprChain* chain, int64_t n_rows, void* out, int32_t* out_dtype, VkStream stream);
+int vk_expr_compare(const VkExprCompare* cmp, int64_t n_rows, uint8_t* out_mask, VkStream stream);
 
 /* ------------------------------------------------ hash aggregate (a8-a14) -- */
 /* Replaces BaseAggregate / SingleNumericalHashAggregate / MultiNumericalHashAggregate

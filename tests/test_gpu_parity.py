@@ -241,6 +241,7 @@ AGG_PATHS = {
     "direct_w8_pf6": (dict(AGG_WARPS=8, AGG_PF=6), 1),
     "direct_w12_pf0": (dict(AGG_WARPS=12, AGG_PF=0), 1),
     "hash_w8": (dict(AGG_DIRECT=0, AGG_WARPS=8), 1),
+    "hash_insert_w8": (dict(AGG_DIRECT=0, AGG_DICT=0, AGG_WARPS=8), 1),
     "hash_w12_small_table": (dict(AGG_DIRECT=0, AGG_WARPS=12, AGG_LOG2S=11), 1),
     "hash_w4": (dict(AGG_DIRECT=0, AGG_WARPS=4, AGG_PF=0), 1),
     "general_kernel": (dict(AGG_NOFAST=1), 2),

@@ -67,7 +67,8 @@ def _device_groupby(vb, stream, table, where=None, opts=None, chunks=1):
 
 PATH_OPTS = {
     "auto": {},
-    "hash": {"AGG_DIRECT": 0},
+    "hash": {"AGG_DIRECT": 0},                                     # read-only cuckoo dictionary after the learning launch
+    "hash_insert": {"AGG_DIRECT": 0, "AGG_DICT": 0},               # insert-as-you-go CTA table
     "hash_small": {"AGG_DIRECT": 0, "AGG_LOG2S": 10, "AGG_WARPS": 12},
     "general": {"AGG_NOFAST": 1},
 }
@@ -116,7 +117,7 @@ def test_group_by_hostile_key_distributions(vb, stream, kind, path):
         assert paths == [2]
 
 
-@pytest.mark.parametrize("path", ["auto", "hash", "general"])
+@pytest.mark.parametrize("path", ["auto", "hash", "hash_insert", "general"])
 def test_group_by_without_predicate_and_streamed_chunks(vb, stream, path):
     """C3's shape (no WHERE), fed in five ragged chunks: state carries across vk_agg_update calls
     (BaseAggregate::Next, base_aggregate.cpp:23-45)."""
@@ -128,7 +129,7 @@ def test_group_by_without_predicate_and_streamed_chunks(vb, stream, path):
     assert_tables_match(got, want, key_cols=["k"], rtol=FLOAT_RTOL)
 
 
-@pytest.mark.parametrize("path", ["auto", "hash", "general"])
+@pytest.mark.parametrize("path", ["auto", "hash", "hash_insert", "general"])
 def test_float_keys_nan_payloads_and_signed_zero(vb, stream, path):
     """Float keys group by BIT PATTERN (FloatArrayIter::floatToInt, array_iterators.h:239-248):
     -0.0 and +0.0 are two groups, NaNs with different payloads are different groups."""

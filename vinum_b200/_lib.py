@@ -36,7 +36,7 @@ EQ, NE, GT, GE, LT, LE = range(6)
 # VkMaskOp
 MASK_AND, MASK_OR, MASK_NOT = range(3)
 # VkPredKind
-PRED_NONE, PRED_MASK, PRED_CMP = range(3)
+PRED_NONE, PRED_MASK, PRED_CMP, PRED_EXPR = range(4)
 # VkArithOp
 ADD, SUB, MUL, DIV, MOD, BITAND, BITOR, BITXOR, NEG, BITNOT = range(10)
 # VkAggFunc
@@ -69,6 +69,21 @@ class VkScalar(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("_pad", C.c_int32), ("v", _ScalarValue)]
 
 
+VK_EXPR_MAX_TERMS = 4
+
+
+class VkExprTerm(C.Structure):
+    _fields_ = [("column", VkColumn), ("scalar", VkScalar), ("is_column", C.c_int32), ("op", C.c_int32)]
+
+
+class VkExprChain(C.Structure):
+    _fields_ = [("n_terms", C.c_int32), ("_pad", C.c_int32), ("terms", VkExprTerm * VK_EXPR_MAX_TERMS)]
+
+
+class VkExprCompare(C.Structure):
+    _fields_ = [("lhs", VkExprChain), ("rhs", VkExprChain), ("op", C.c_int32), ("_pad", C.c_int32)]
+
+
 class VkPredicate(C.Structure):
     _fields_ = [
         ("kind", C.c_int32),
@@ -76,6 +91,7 @@ class VkPredicate(C.Structure):
         ("mask", C.c_void_p),
         ("column", VkColumn),
         ("scalar", VkScalar),
+        ("expr", C.POINTER(VkExprCompare)),
     ]
 
 
@@ -173,6 +189,8 @@ SIGNATURES = {
     "vk_filter": (_int, [C.POINTER(VkPredicate), _i64, C.POINTER(VkColumn), _int, _PP, _PP, _p, _p, _p]),
     "vk_arith": (_int, [_int, C.POINTER(VkColumn), C.POINTER(VkScalar), C.POINTER(VkColumn), C.POINTER(VkScalar),
                         _i64, _int, _p, _p]),
+    "vk_expr_eval": (_int, [C.POINTER(VkExprChain), _i64, _p, C.POINTER(C.c_int32), _p]),
+    "vk_expr_compare": (_int, [C.POINTER(VkExprCompare), _i64, _p, _p]),
     "vk_agg_create": (_int, [_PP, _int, C.POINTER(C.c_int32), _int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i64]),
     "vk_agg_destroy": (_int, [_p]),
     "vk_agg_update": (_int, [_p, C.POINTER(VkPredicate), _i64, C.POINTER(VkColumn), C.POINTER(VkColumn), _p]),

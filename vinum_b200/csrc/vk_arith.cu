@@ -259,3 +259,47 @@ extern "C" int vk_arith(int op, const VkColumn* lhs_col, const VkScalar* lhs_sca
     VK_CHECK_LAUNCH("arith_kernel");
     return VK_OK;
 }
+
+// ---- fused expression chains (vk_expr.cuh) ------------------------------------------------
+__global__ void __launch_bounds__(256) expr_eval_kernel(const __grid_constant__ vk::EChain c, int64_t n, uint64_t* __restrict__ out) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = vk::chain_eval(c, i);
+}
+// two rows per thread, two mask bytes per store (the mask buffer is 2-byte aligned)
+__global__ void __launch_bounds__(256) expr_compare_kernel(const __grid_constant__ vk::ECompare e, int64_t n, uint8_t* __restrict__ out) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t pairs = n >> 1;
+    for (int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += stride) {
+        const uint16_t m = (uint16_t) vk::compare_eval(e, 2 * q) | ((uint16_t) vk::compare_eval(e, 2 * q + 1) << 8);
+        reinterpret_cast<uint16_t*>(out)[q] = m;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = vk::compare_eval(e, n - 1);
+}
+
+extern "C" int vk_expr_eval(const VkExprChain* chain, int64_t n_rows, void* out, int32_t* out_dtype, VkStream stream) {
+    VK_REQUIRE(chain && out_dtype && n_rows >= 0, "vk_expr_eval: bad argument");
+    EChain c;
+    int rc = make_chain(*chain, n_rows, &c);
+    if (rc != VK_OK) return rc;
+    *out_dtype = c.out_dom == EX_F64 ? VK_F64 : VK_I64;
+    if (n_rows == 0) return VK_OK;
+    VK_REQUIRE(out, "vk_expr_eval: out is NULL");
+    int64_t need = (n_rows + 255) / 256, cap = (int64_t) sm_count() * 8;
+    expr_eval_kernel<<<(unsigned) (need < cap ? need : cap), 256, 0, (cudaStream_t) stream>>>(c, n_rows, reinterpret_cast<uint64_t*>(out));
+    VK_CHECK_LAUNCH("expr_eval_kernel");
+    return VK_OK;
+}
+
+extern "C" int vk_expr_compare(const VkExprCompare* cmp, int64_t n_rows, uint8_t* out_mask, VkStream stream) {
+    VK_REQUIRE(cmp && n_rows >= 0, "vk_expr_compare: bad argument");
+    ECompare e;
+    int rc = make_compare(*cmp, n_rows, &e);
+    if (rc != VK_OK) return rc;
+    if (n_rows == 0) return VK_OK;
+    VK_REQUIRE(out_mask && (reinterpret_cast<uintptr_t>(out_mask) & 1) == 0, "vk_expr_compare: out_mask must be 2-byte aligned");
+    int64_t need = (n_rows / 2 + 255) / 256, cap = (int64_t) sm_count() * 8;
+    if (need < 1) need = 1;
+    expr_compare_kernel<<<(unsigned) (need < cap ? need : cap), 256, 0, (cudaStream_t) stream>>>(e, n_rows, out_mask);
+    VK_CHECK_LAUNCH("expr_compare_kernel");
+    return VK_OK;
+}

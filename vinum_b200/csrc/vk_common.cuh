@@ -46,13 +46,12 @@ enum Opt {
     OPT_ONEGROUP_FAST,      // agg_onegroup8_kernel row pairs per thread (0: agg_onegroup_kernel)
     OPT_SORT_FUSE_LAST,     // 1: the last radix pass writes the int64 permutation itself
     OPT_SORT_PREP,          // sort_prepare8_kernel loads per thread (0: sort_prepare_kernel)
-    OPT_SORT_BITS,          // radix digit width of the LSD passes (8 or 11; 0: automatic)
     OPT_AGG_LOG2S,          // agg_fast_kernel: log2 of the CTA key table slots (hash mode)
     OPT_AGG_PF,             // agg_fast_kernel: L2 prefetch distance in tiles (-1: automatic)
     OPT_AGG_WARPS,          // agg_fast_kernel: warps per CTA (0: automatic)
     OPT_AGG_DIRECT,         // 1: direct (key - base) group ids when the key range allows, 0: always hash
+    OPT_AGG_DICT,           // 1: hash mode looks keys up in a host-built read-only cuckoo dictionary
     OPT_AGG_NOFAST,         // 1: never use the shared-memory aggregate kernel
-    OPT_AGG_HYBRID,         // agg_fast_kernel: every k-th tile goes through L2 atomics (0: off)
     OPT_AGG_LEARN_LOG2,     // log2 rows of the learning launch
     OPT_LIST_LOG2,          // log2 of the replay-list capacity cap (entries)
     OPT_DEBUG,              // 1: trace the aggregate's host decisions to stderr

@@ -564,7 +564,8 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
     VK_REQUIRE(pred && out_rows && scratch, "vk_filter: NULL argument");
     VK_REQUIRE(n_rows >= 0 && n_cols >= 0, "vk_filter: negative size");
     VK_REQUIRE(n_cols == 0 || (cols && out_data), "vk_filter: NULL column arrays");
-    VK_REQUIRE(pred->kind == VK_PRED_MASK || pred->kind == VK_PRED_CMP, "vk_filter: predicate kind must be MASK or CMP");
+    VK_REQUIRE(pred->kind == VK_PRED_MASK || pred->kind == VK_PRED_CMP || pred->kind == VK_PRED_EXPR,
+               "vk_filter: predicate kind must be MASK, CMP or EXPR");
     cudaStream_t s = (cudaStream_t) stream;
     if (n_rows == 0) {
         VK_CUDA(cudaMemsetAsync(out_rows, 0, sizeof(int64_t), s));

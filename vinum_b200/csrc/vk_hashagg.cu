@@ -50,6 +50,17 @@ __global__ void __launch_bounds__(256) agg_key_range_kernel(GTable t, long long*
     }
 }
 
+// Keys of a single-key table as a dense list (the dictionary builder reads them back).
+__global__ void __launch_bounds__(256) agg_export_keys_kernel(GTable t, uint64_t* out, unsigned long long* cursor,
+                                                              unsigned long long cap) {
+    const int64_t slots = t.capacity + 1;  // + the slot of the all-ones key; the NULL group has no key
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (int64_t) gridDim.x * blockDim.x) {
+        if (!gt_slot_occupied(t, s)) continue;
+        const unsigned long long pos = atomicAdd(cursor, 1ULL);
+        if (pos < cap) out[pos] = s < t.capacity ? t.keys[s] : ~0ULL;
+    }
+}
+
 // ============================================================ general kernel
 struct GenParams {
     Pred pred;
@@ -654,6 +665,16 @@ struct VkAgg {
     bool fast_warps_fixed = false;
     int fast_direct_policy = 1;       // 1: use direct (key - base) group ids when the key range allows, 0: always hash
     int64_t learn_rows = (int64_t) 1 << 20;   // rows of the learning launch
+    // hash mode: read-only cuckoo dictionary of the keys seen so far (built by the host after the learning
+    // launch, vk_agg_fast.cuh); rows with other keys go to the global table
+    bool dict_ready = false, dict_failed = false;
+    int dict_policy = 1;
+    int dict_n = 0;                   // keys in the dictionary
+    int dict_log2s = 0;
+    uint8_t* dict_dev = nullptr;      // [S] u64 keys | [S] u16 ids
+    uint64_t seed_a = 0, seed_b = 0;
+    std::vector<uint64_t> dict_hk;
+    std::vector<uint16_t> dict_hg;
     bool direct_known = false;        // key range of the table measured
     bool direct_ok = false;
     uint64_t direct_min = 0, direct_span = 0;  // smallest key (signed order) and max - min
@@ -986,6 +1007,78 @@ void apply_key_range(VkAgg* a) {
     VK_DBG("key range: min=%lld max=%lld direct_ok=%d", mn, mx, (int) a->direct_ok);
 }
 
+// Hash mode: place the table's keys into a cuckoo dictionary (two slot choices per key, S = 1 << log2s
+// slots) and upload it.  Leaves dict_ready false when there are too many keys or no seed pair works.
+int build_dict(VkAgg* a, int64_t n_groups, int log2s, cudaStream_t s) {
+    a->dict_ready = false;
+    const int64_t S = (int64_t) 1 << log2s;
+    if (n_groups < 1 || n_groups > S / 4 || n_groups >= 0xFFF0) return VK_OK;
+    uint64_t* d_keys = nullptr;
+    VK_CUDA(cudaMallocAsync((void**) &d_keys, (size_t) n_groups * 8, s));
+    VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_CURSOR, 0, sizeof(unsigned long long), s));
+    int64_t need = (a->t.capacity + 1 + 255) / 256, capb = (int64_t) sm_count() * 8;
+    agg_export_keys_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(a->t, d_keys, a->d_ctr + CTR_CURSOR,
+                                                                                   (unsigned long long) n_groups);
+    VK_CHECK_LAUNCH("agg_export_keys_kernel");
+    std::vector<uint64_t> keys((size_t) n_groups);
+    VK_CUDA(cudaMemcpyAsync(keys.data(), d_keys, (size_t) n_groups * 8, cudaMemcpyDeviceToHost, s));
+    int rc = read_counters(a, s);   // synchronises: the keys are on the host
+    VK_CUDA(cudaFreeAsync(d_keys, s));
+    if (rc != VK_OK) return rc;
+    if ((int64_t) a->h_ctr[CTR_CURSOR] != n_groups) return VK_OK;   // the table moved on (or holds a NULL group): no dictionary
+    const uint32_t shift = 32 - log2s;
+    a->dict_hk.assign((size_t) S, LK_EMPTY);
+    a->dict_hg.assign((size_t) S, 0);
+    bool placed = false;
+    uint64_t sa = 0x9E3779B97F4A7C15ULL, sb = 0xC2B2AE3D27D4EB4FULL;
+    for (int attempt = 0; attempt < 32 && !placed; ++attempt) {
+        std::fill(a->dict_hk.begin(), a->dict_hk.end(), LK_EMPTY);
+        placed = true;
+        for (int64_t i = 0; i < n_groups && placed; ++i) {
+            uint64_t key = keys[(size_t) i];
+            uint16_t gid = (uint16_t) i;
+            if (key == LK_EMPTY) continue;   // the sentinel cannot live in the dictionary: its rows take the global path
+            uint32_t slot = dict_hash_a(key, sa) >> shift;
+            bool done = false;
+            for (int kick = 0; kick < 256; ++kick) {
+                if (a->dict_hk[slot] == LK_EMPTY) {
+                    a->dict_hk[slot] = key;
+                    a->dict_hg[slot] = gid;
+                    done = true;
+                    break;
+                }
+                std::swap(key, a->dict_hk[slot]);
+                std::swap(gid, a->dict_hg[slot]);
+                const uint32_t ha = dict_hash_a(key, sa) >> shift, hb = dict_hash_b(key, sb) >> shift;
+                slot = slot == ha ? hb : ha;   // the evicted key moves to its other slot
+            }
+            placed = done;
+        }
+        if (!placed) {
+            sa = splitmix64(sa + attempt);
+            sb = splitmix64(sb ^ sa);
+        }
+    }
+    if (!placed) {
+        a->dict_failed = true;
+        return VK_OK;
+    }
+    if (a->dict_dev == nullptr || a->dict_log2s != log2s) {
+        if (a->dict_dev) VK_CUDA(cudaFreeAsync(a->dict_dev, s));
+        a->dict_dev = nullptr;
+        VK_CUDA(cudaMallocAsync((void**) &a->dict_dev, (size_t) S * 10, s));
+        a->dict_log2s = log2s;
+    }
+    VK_CUDA(cudaMemcpyAsync(a->dict_dev, a->dict_hk.data(), (size_t) S * 8, cudaMemcpyHostToDevice, s));
+    VK_CUDA(cudaMemcpyAsync(a->dict_dev + (size_t) S * 8, a->dict_hg.data(), (size_t) S * 2, cudaMemcpyHostToDevice, s));
+    a->seed_a = sa;
+    a->seed_b = sb;
+    a->dict_n = (int) n_groups;
+    a->dict_ready = true;
+    VK_DBG("dictionary: %d keys in %lld slots", a->dict_n, (long long) S);
+    return VK_OK;
+}
+
 bool aligned_for_pairs(const VkColumn& c) {
     const int es = dtype_size(c.dtype);
     uintptr_t addr = reinterpret_cast<uintptr_t>(c.data) + (uintptr_t) c.offset * es;
@@ -1140,6 +1233,7 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
     if (a->fast_warps < 1) a->fast_warps = 1;
     if (a->fast_warps > FA_MAX_THREADS / 32) a->fast_warps = FA_MAX_THREADS / 32;
     a->fast_direct_policy = (int) opt(OPT_AGG_DIRECT);
+    a->dict_policy = (int) opt(OPT_AGG_DICT);
     if (opt(OPT_AGG_NOFAST)) a->fast_disabled = true;
     a->learn_rows = (int64_t) 1 << (opt(OPT_AGG_LEARN_LOG2) < 10 ? 10 : (opt(OPT_AGG_LEARN_LOG2) > 30 ? 30 : opt(OPT_AGG_LEARN_LOG2)));
     const int rc = ctr_acquire(a);
@@ -1162,6 +1256,7 @@ int vk_agg_destroy(VkAgg* a) {
     prof_resolve(a);
     for (auto& sp : a->prof_free) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     if (a->table_ready) free_table(&a->t, s);
+    if (a->dict_dev) cudaFreeAsync(a->dict_dev, s);
     release_list(a, s);
     ctr_release(a);
     delete a;
@@ -1357,7 +1452,14 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 }
             }
         }
-        if (!direct) {
+        if (!direct && a->dict_ready) {
+            // read-only dictionary: the dense ids are exactly 0 .. dict_n - 1
+            warps = w_hi;
+            const int need = (a->dict_n + 15) & ~15;
+            while (warps > w_lo && need > fast_gmax(log2s, false, plan.nw, warps)) warps = next_w(warps);
+            gmax = need < 16 ? 16 : need;
+            if (gmax > fast_gmax(log2s, false, plan.nw, warps)) fast = false;
+        } else if (!direct) {
             // fewer warps per CTA leave more shared memory per warp-private table
             warps = w_hi;
             while (warps > w_lo && groups_hint + groups_hint / 32 + 8 > fast_gmax(log2s, false, plan.nw, warps)) warps = next_w(warps);
@@ -1438,8 +1540,16 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                (long long) a->t.capacity, (long long) a->groups_ub, (unsigned long long) a->list_cap);
 
         VkPredicate cpred = *pred;
+        VkExprCompare cexpr;
         if (cpred.kind == VK_PRED_MASK) cpred.mask += pos;
         if (cpred.kind == VK_PRED_CMP) cpred.column = slice_col(cpred.column, pos, chunk);
+        if (cpred.kind == VK_PRED_EXPR && cpred.expr != nullptr) {
+            cexpr = *cpred.expr;
+            for (VkExprChain* ch : {&cexpr.lhs, &cexpr.rhs})
+                for (int k = 0; k < ch->n_terms && k < VK_EXPR_MAX_TERMS; ++k)
+                    if (ch->terms[k].is_column) ch->terms[k].column = slice_col(ch->terms[k].column, pos, chunk);
+            cpred.expr = &cexpr;
+        }
         rc = make_pred(cpred, chunk, &dpred, &pk);
         if (rc != VK_OK) return rc;
 
@@ -1482,6 +1592,12 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             fp.pf_dist = warps >= 5 ? pf_dist : 0;  // one prefetching lane per column: needs NV + 2 warps
             fp.table = a->t;
             fp.replay = gp.replay;
+            if (!direct && a->dict_ready) {
+                fp.dict_keys = reinterpret_cast<const uint64_t*>(a->dict_dev);
+                fp.dict_gids = reinterpret_cast<const uint16_t*>(a->dict_dev + ((size_t) 8 << log2s));
+                fp.seed_a = a->seed_a;
+                fp.seed_b = a->seed_b;
+            }
             FastLaunch fl;
             fl.pk = pk;
             fl.nw = plan.nw;
@@ -1538,6 +1654,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 if (chunk >= 65536 && spill_now * 4 > (uint64_t) chunk) {
                     // this configuration thrashes: most rows fell through to the global path
                     if (direct) a->direct_ok = false;   // the key range moved: back to hash mode
+                    else if (a->dict_ready) a->dict_ready = false;   // stale dictionary: rebuilt below from the table as it is now
                     else a->fast_disabled = true;       // cardinality too high for shared memory
                 } else if (lean && a->fast_direct_policy && !a->direct_known &&
                            a->fast_groups_seen <= fast_gmax(log2s, true, plan.nw, 2)) {
@@ -1552,6 +1669,14 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             rc = run_replay_until_empty(a, gp, chunk, s);
             if (rc != VK_OK) return rc;
             if (a->fast_disabled) fast = false;
+            // no dense key range: look the keys up in a read-only dictionary from now on; a dictionary that
+            // most rows miss (the keys moved on) is rebuilt from the table as it is now
+            const bool want_dict = fast && a->dict_policy && !a->dict_failed &&
+                                   !(a->fast_direct_policy && a->direct_known && a->direct_ok && lean);
+            if (want_dict && !a->dict_ready) {
+                rc = build_dict(a, (int64_t) a->h_ctr[CTR_GROUPS], log2s, s);
+                if (rc != VK_OK) return rc;
+            }
             if (fast) configure_fast(a->fast_groups_seen);
         }
         pos += chunk;

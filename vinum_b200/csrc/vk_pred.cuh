@@ -9,6 +9,7 @@
 // is first materialised as float with NaN (vinum/arrow/record_batch.py:100-125).
 #pragma once
 #include "vk_common.cuh"
+#include "vk_expr.cuh"
 #include <cmath>
 
 namespace vk {
@@ -128,6 +129,7 @@ struct Pred {
     const uint8_t* mask;
     Col col;
     PredScalar scalar;
+    ECompare expr;   // VK_PRED_EXPR: <chain> <cmp> <chain> evaluated in registers (vk_expr.cuh)
 };
 
 // Predicate kernel specialisations.
@@ -144,6 +146,7 @@ __device__ __forceinline__ bool pred_row_dom(const Pred& p, int64_t i) {
     return apply_cmp(p.op, load_dom<DOM>(p.col, i), scalar_dom<DOM>(p.scalar));
 }
 __device__ __forceinline__ bool pred_row_generic(const Pred& p, int64_t i) {
+    if (p.kind == VK_PRED_EXPR) return compare_eval(p.expr, i);
     switch (p.domain) {
         case DOM_I64: return pred_row_dom<DOM_I64>(p, i);
         case DOM_U64: return pred_row_dom<DOM_U64>(p, i);
@@ -210,6 +213,14 @@ inline int make_pred(const VkPredicate& in, int64_t n_rows, Pred* out, int* out_
         p.mask = in.mask;
         *out = p;
         *out_pk = PK_MASK;
+        return VK_OK;
+    }
+    if (in.kind == VK_PRED_EXPR) {
+        if (!in.expr) return fail(VK_ERR_ARG, "predicate: expr is NULL");
+        const int rc = make_compare(*in.expr, n_rows, &p.expr);
+        if (rc != VK_OK) return rc;
+        *out = p;
+        *out_pk = PK_GENERIC;
         return VK_OK;
     }
     if (in.kind != VK_PRED_CMP) return fail(VK_ERR_ARG, "predicate: unknown kind");

@@ -132,7 +132,7 @@ def _sp(stream: Optional[Stream]) -> C.c_void_p:
 class DeviceBuffer:
     """Owning handle of a device allocation from the stream-ordered pool."""
 
-    __slots__ = ("ptr", "nbytes", "_stream_handle", "__weakref__")
+    __slots__ = ("ptr", "nbytes", "_stream_handle", "_stream", "__weakref__")
 
     def __init__(self, nbytes: int, stream: Optional[Stream] = None, zero: bool = False):
         st = stream or default_stream()
@@ -141,6 +141,9 @@ class DeviceBuffer:
         self.ptr = p.value or 0
         self.nbytes = int(nbytes)
         self._stream_handle = st.handle
+        # the allocation is freed in stream order on the stream it came from: keep that stream alive
+        # (a Stream collected before its buffers would leave cudaFreeAsync with a destroyed handle)
+        self._stream = st
         if zero and nbytes:
             lib.vk_memset(C.c_void_p(self.ptr), 0, int(nbytes), st.ptr)
 

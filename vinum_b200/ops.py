@@ -131,10 +131,17 @@ class Predicate:
     mask or a `column <op> scalar` comparison that the kernel evaluates in registers."""
 
     def __init__(self, mask: Optional[DeviceColumn] = None, column: Optional[DeviceColumn] = None,
-                 op: Optional[str] = None, scalar: Optional[Scalar] = None):
-        self.mask, self.column, self.op, self.scalar = mask, column, op, scalar
-        if mask is None and column is None:
+                 op: Optional[str] = None, scalar: Optional[Scalar] = None, chains=None):
+        self.mask, self.column, self.op, self.scalar, self.chains = mask, column, op, scalar, chains
+        if mask is None and column is None and chains is None:
             raise ValueError("Predicate needs a mask or a comparison")
+        self._expr = None
+
+    @staticmethod
+    def expr(lhs: "Chain", op: str, rhs: "Chain") -> "Predicate":
+        """`<chain> <op> <chain>` fused into the consumer kernel (VK_PRED_EXPR): `WHERE a * 10 > b` reaches
+        vk_filter / vk_agg_update as an expression, no intermediate column or mask is written."""
+        return Predicate(op=op, chains=(lhs, rhs))
 
     @staticmethod
     def compare(column: DeviceColumn, op: str, scalar: Scalar) -> "Predicate":
@@ -146,6 +153,11 @@ class Predicate:
 
     def vk(self) -> L.VkPredicate:
         p = L.VkPredicate()
+        if self.chains is not None:
+            self._expr = _vk_compare(self.chains[0], self.op, self.chains[1])   # kept alive with the predicate
+            p.kind = L.PRED_EXPR
+            p.expr = C.pointer(self._expr)
+            return p
         if self.mask is not None:
             if self.mask.dtype != L.BOOL8:
                 raise TypeError("filter mask must be boolean")
@@ -160,7 +172,77 @@ class Predicate:
 
     @property
     def length(self) -> int:
+        if self.chains is not None:
+            return chain_length(self.chains[0]) or chain_length(self.chains[1])
         return self.mask.length if self.mask is not None else self.column.length
+
+
+# ------------------------------------------------------- expression chains ----
+# A chain is a list of (op, term): [(None, a), ("*", 10), ("+", b)] means (a * 10) + b, evaluated left to
+# right in ONE pass (vk_expr.cuh).  Terms: null-free int64 / float64 DeviceColumns, Python ints / floats.
+Chain = List[Tuple[Optional[str], Union[DeviceColumn, Scalar]]]
+CHAIN_OPS = ("+", "-", "*", "/", "%", "&", "|", "#")
+MAX_CHAIN_TERMS = L.VK_EXPR_MAX_TERMS
+
+
+def chain_term_ok(x) -> bool:
+    if _is_col(x):
+        return x.dtype in (L.I64, L.F64) and not x.has_nulls
+    return isinstance(x, (int, float, np.integer, np.floating)) and not isinstance(x, (bool, np.bool_)) and \
+        (not isinstance(x, (int, np.integer)) or -(1 << 63) <= int(x) < (1 << 63))
+
+
+def chain_length(chain: Chain) -> int:
+    for _, t in chain:
+        if _is_col(t):
+            return t.length
+    return 0
+
+
+def _vk_chain(chain: Chain) -> L.VkExprChain:
+    if not 1 <= len(chain) <= MAX_CHAIN_TERMS:
+        raise ValueError("an expression chain has 1..4 terms")
+    c = L.VkExprChain()
+    c.n_terms = len(chain)
+    for i, (op, term) in enumerate(chain):
+        t = c.terms[i]
+        if _is_col(term):
+            t.is_column = 1
+            t.column = term.vk()
+        else:
+            t.is_column = 0
+            t.scalar = L.make_scalar(float(term) if isinstance(term, (float, np.floating)) else int(term))
+        t.op = ARITH_OPS[op] if i else 0
+    return c
+
+
+def _vk_compare(lhs: Chain, op: str, rhs: Chain) -> L.VkExprCompare:
+    e = L.VkExprCompare()
+    e.lhs = _vk_chain(lhs)
+    e.rhs = _vk_chain(rhs)
+    e.op = CMP_OPS[op]
+    return e
+
+
+def eval_chain(chain: Chain, stream: Optional[Stream] = None) -> DeviceColumn:
+    """The whole arithmetic chain in one pass (vk_expr_eval); the result dtype follows NumPy's promotion."""
+    st = stream or default_stream()
+    n = chain_length(chain)
+    c = _vk_chain(chain)
+    out = DeviceBuffer(max(n, 1) * 8, st)
+    dt = C.c_int32()
+    lib.vk_expr_eval(C.byref(c), n, C.c_void_p(out.ptr), C.byref(dt), st.ptr)
+    return DeviceColumn(out, None, 0, n, int(dt.value), pa.float64() if dt.value == L.F64 else pa.int64())
+
+
+def compare_chains(lhs: Chain, op: str, rhs: Chain, stream: Optional[Stream] = None) -> DeviceColumn:
+    """`<chain> <op> <chain>` -> byte mask in one pass (vk_expr_compare)."""
+    st = stream or default_stream()
+    n = chain_length(lhs) or chain_length(rhs)
+    out = _mask_column(n, st)
+    e = _vk_compare(lhs, op, rhs)
+    lib.vk_expr_compare(C.byref(e), n, C.c_void_p(out.data_ptr), st.ptr)
+    return out
 
 
 def filter_batch(batch: DeviceBatch, pred: Predicate, stream: Optional[Stream] = None) -> DeviceBatch:

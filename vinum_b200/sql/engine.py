@@ -200,7 +200,7 @@ class Engine:
                 frame.n = 1
                 frame.virtual = True
             if q.where is not None:
-                frame = self._filter(frame, self._as_mask(self._eval(q.where, frame, resolved), frame.n))
+                frame = self._filter(frame, self._predicate(q.where, frame, resolved))
         return self._tail(q, frame, resolved)
 
     # -------------------------------------------------------------------- scan
@@ -231,6 +231,11 @@ class Engine:
             return frame.cols[node.name]
         op = node.op
         if op in _ARITH:
+            ch = self._chain(node, frame, resolved)
+            if ch is not None and len(ch) >= 3:
+                # two or more operations over plain columns: one pass, no intermediate array (row a3)
+                self.stats["fused_expr"] = self.stats.get("fused_expr", 0) + 1
+                return ops.eval_chain(ch, self.st)
             return self._fold(_ARITH[op], [self._eval(a, frame, resolved) for a in node.args], self._arith2)
         if op == Op.NEGATION or op == Op.BINARY_NOT:
             x = self._eval(node.args[0], frame, resolved)
@@ -241,6 +246,10 @@ class Engine:
                 raise OperatorError(f"operator {sym} is not defined for column type {x.arr.type}")
             return (np.negative if op == Op.NEGATION else np.invert)(x).item()
         if op in _CMP:
+            fused = self._chain_compare(node, frame, resolved)
+            if fused is not None:
+                self.stats["fused_expr"] = self.stats.get("fused_expr", 0) + 1
+                return ops.compare_chains(fused[0], fused[1], fused[2], self.st)
             a, b = (self._eval(x, frame, resolved) for x in node.args)
             return self._compare(_CMP[op], a, b)
         if op in (Op.AND, Op.OR):
@@ -296,6 +305,74 @@ class Engine:
                 raise OperatorError(f"aggregate function {node.function_name}() is not allowed here")
             return self._host_call(node.function_name, [self._eval(a, frame, resolved) for a in node.args], frame.n)
         raise OperatorError(f"unsupported expression {op}")
+
+    # ---------------------------------------------------------- expression fusion
+    def _chain(self, node: Node, frame: Frame, resolved: Dict):
+        """`node` as a left-deep chain [(None, t0), (op1, t1), ...] over null-free int64 / float64 device
+        columns and numeric literals (vk_expr.cuh), or None.  a + (b * c) is rewritten (b * c) + a for
+        the commutative operators: the same IEEE / wrapping operations in the same tree order."""
+        if os.environ.get("VINUM_B200_FUSE_EXPR", "1") == "0":
+            return None
+        if isinstance(node, Literal):
+            return [(None, node.value)] if ops.chain_term_ok(node.value) else None
+        k = node.key()
+        if k in resolved:
+            v = frame.cols[resolved[k]]
+            return [(None, v)] if isinstance(v, DeviceColumn) and ops.chain_term_ok(v) else None
+        if isinstance(node, Column):
+            v = frame.cols.get(node.name)
+            return [(None, v)] if isinstance(v, DeviceColumn) and ops.chain_term_ok(v) else None
+        if not isinstance(node, Expression) or node.op not in _ARITH or len(node.args) < 2:
+            return None
+        sym = _ARITH[node.op]
+        out = self._chain(node.args[0], frame, resolved)
+        for arg in node.args[1:]:   # n-ary nodes fold left (BINARY_EXPRESSIONS, core/base.py:145-151)
+            rhs = self._chain(arg, frame, resolved)
+            if out is None or rhs is None:
+                return None
+            if len(rhs) == 1:
+                out = out + [(sym, rhs[0][1])]
+            elif len(out) == 1 and sym in ("+", "*", "&", "|", "#"):
+                out = rhs + [(sym, out[0][1])]
+            else:
+                return None
+            if len(out) > ops.MAX_CHAIN_TERMS:
+                return None
+        if not any(isinstance(t, DeviceColumn) for _, t in out):
+            return None   # constants only: folded on the host
+        floats = any((isinstance(t, DeviceColumn) and t.dtype == L.F64) or isinstance(t, (float, np.floating)) for _, t in out)
+        if floats and any(o in ("&", "|", "#") for o, _ in out[1:]):
+            return None   # NumPy raises for bitwise operators on floats: keep that path
+        return out
+
+    def _chain_compare(self, node: Node, frame: Frame, resolved: Dict):
+        """(lhs chain, op, rhs chain) when a comparison's two sides are chains and fusing saves a pass
+        (`a * 10 > b`); None for plain `column <op> column / literal`, which has its own kernels."""
+        if not (isinstance(node, Expression) and node.op in _CMP and len(node.args) == 2):
+            return None
+        lc = self._chain(node.args[0], frame, resolved)
+        rc = self._chain(node.args[1], frame, resolved) if lc is not None else None
+        if lc is None or rc is None or (len(lc) < 2 and len(rc) < 2):
+            return None
+        return lc, _CMP[node.op], rc
+
+    def _predicate(self, w: Node, frame: Frame, resolved: Dict) -> "ops.Predicate":
+        """WHERE / HAVING as the predicate the consumer kernel evaluates itself: `column <op> literal`
+        (vectorised in registers), a fused expression chain, or -- anything else -- a byte mask."""
+        if isinstance(w, Expression) and w.op in _CMP and len(w.args) == 2:
+            a, b = w.args
+            sym = _CMP[w.op]
+            if isinstance(b, Column) and isinstance(a, Literal):
+                a, b, sym = b, a, _CMP_FLIP[sym]
+            if isinstance(a, Column) and isinstance(b, Literal) and _is_num(b.value) and not isinstance(b.value, bool):
+                col = frame.cols.get(a.name)
+                if isinstance(col, DeviceColumn) and col.dtype != L.BOOL8:
+                    return ops.Predicate.compare(col, sym, b.value)
+            fused = self._chain_compare(w, frame, resolved)
+            if fused is not None:
+                self.stats["fused_expr"] = self.stats.get("fused_expr", 0) + 1
+                return ops.Predicate.expr(*fused)
+        return ops.Predicate.from_mask(self._as_mask(self._eval(w, frame, resolved), frame.n))
 
     @staticmethod
     def _fold(sym, args, fn):
@@ -391,20 +468,36 @@ class Engine:
         if isinstance(v, DeviceColumn):
             if v.dtype != L.BOOL8:
                 return ops.compare(v, "!=", 0, self.st)
+            if v.has_nulls:
+                # a NULL condition drops the row (RecordBatch.filter with a nullable mask keeps only
+                # true slots on this path, record_batch.py:85-90): the raw byte under a NULL is garbage
+                plain = DeviceColumn(v.data, None, v.offset, v.length, L.BOOL8, pa.bool_(), 0, v.data_ptr)
+                return ops.mask_and(plain, ops.is_valid(v, self.st), self.st)
             return v
         if isinstance(v, HostColumn):
             raise OperatorError("a string expression cannot be used as a condition")
         return self._upload_mask(np.full(n, bool(v), dtype=np.bool_))
 
     # ------------------------------------------------------- filter / sort
-    def _filter(self, frame: Frame, mask: DeviceColumn) -> Frame:
-        """FilterOperator (algebra.py:108-123): one compaction kernel over every device column."""
+    def _filter(self, frame: Frame, mask) -> Frame:
+        """FilterOperator (algebra.py:108-123): one compaction kernel over every device column; `mask` is
+        a byte-mask column or an `ops.Predicate` the kernel evaluates itself (no mask is written)."""
         names = [k for k, v in frame.cols.items() if isinstance(v, DeviceColumn)]
         host = [k for k, v in frame.cols.items() if isinstance(v, HostColumn)]
+        pred = mask if isinstance(mask, ops.Predicate) else ops.Predicate.from_mask(mask)
+        if (host or not names) and pred.mask is None:
+            # host (string) columns are filtered on the host: they need the mask itself
+            if pred.chains is not None:
+                mask = ops.compare_chains(pred.chains[0], pred.op, pred.chains[1], self.st)
+            else:
+                mask = ops.compare(pred.column, pred.op, pred.scalar, self.st)
+            pred = ops.Predicate.from_mask(mask)
+        else:
+            mask = pred.mask
         out = Frame(0)
         if names:
             batch = DeviceBatch([frame.cols[k] for k in names], names, frame.n)
-            res = ops.filter_batch(batch, ops.Predicate.from_mask(mask), self.st)
+            res = ops.filter_batch(batch, pred, self.st)
             out.n = res.num_rows
             for k, c in zip(names, res.columns):
                 out.cols[k] = c
@@ -559,20 +652,7 @@ class Engine:
         batch's columns, then ONE update of the device aggregate."""
         st = self.st
         # ---- predicate: fused `column <op> literal` or a byte mask; never a compaction ----
-        pred = None
-        if q.where is not None:
-            w = q.where
-            fused = None
-            if isinstance(w, Expression) and w.op in _CMP and len(w.args) == 2:
-                a, b = w.args
-                sym = _CMP[w.op]
-                if isinstance(b, Column) and isinstance(a, Literal):
-                    a, b, sym = b, a, _CMP_FLIP[sym]
-                if isinstance(a, Column) and isinstance(b, Literal) and _is_num(b.value):
-                    col = frame.cols[a.name]
-                    if isinstance(col, DeviceColumn):
-                        fused = ops.Predicate.compare(col, sym, b.value)
-            pred = fused or ops.Predicate.from_mask(self._as_mask(self._eval(w, frame, {}), frame.n))
+        pred = self._predicate(q.where, frame, {}) if q.where is not None else None
 
         first = state.agg is None
         key_vals: List[DeviceColumn] = []
@@ -701,7 +781,7 @@ class Engine:
             self.table = tbl
             frame = self._scan(used)
             if q.where is not None:
-                frame = self._filter(frame, self._as_mask(self._eval(q.where, frame, {}), frame.n))
+                frame = self._filter(frame, self._predicate(q.where, frame, {}))
             kept.append(pa.table({name: (v.to_arrow(self.st) if isinstance(v, DeviceColumn) else v.arr)
                                   for name, v in frame.cols.items()}) if frame.cols else pa.table({"__n": pa.nulls(frame.n)}))
             rows += frame.n
