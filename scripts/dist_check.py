@@ -1,6 +1,8 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU): every rank aggregates its
-own row range with the fused kernel, partial groups are repartitioned with one NCCL
-all-to-all, rank 0 gathers and compares with the oracle over the whole row range.
+own row range with the fused kernel; the partial groups meet on rank 0 through the peer-memory exchange
+(default), the round-1 all-gather (VINUM_B200_DIST_MODE=allgather) or the NCCL all-to-all repartition;
+rank 0 compares with NumPy over the whole row range.  Then: one logical SQL query over the sharded host
+table (vinum_b200.sharded), the sharded ORDER BY with a host merge, and the GPU sample sort.
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/dist_check.py [ROWS_PER_RANK]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,14 +18,19 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 st = vb.default_stream()
 ok = True
-for keyname, keyt, card, mode in (("i0", pa.int64(), 1000, "finish"), ("i0", pa.int64(), 1000, "repartition"),
+for keyname, keyt, card, mode in (("i0", pa.int64(), 1000, "finish"), ("i0", pa.int64(), 1000, "finish"),
+                                  ("i0", pa.int64(), 1000, "allgather"), ("i0", pa.int64(), 1000, "repartition"),
                                   ("i3", pa.int64(), 1_000_000, "finish")):
     t = datagen.device_table([keyname, "f0", "f1", "i1"], rank * n, n, stream=st)
     spec = [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64()), (L.AGG_MIN, pa.int64()), (L.AGG_AVG, pa.int64())]
     d = DistributedAggregator(Aggregator([keyt], spec), st)
     d.update([t.column(keyname)], [None, t.column("f1"), t.column("i1"), t.column("i1")], ops.Predicate.compare(t.column("f0"), ">", 0.5))
-    if mode == "finish":
-        raw = d.finish()          # low cardinality: one all-gather; high: all-to-all repartition
+    if mode in ("finish", "allgather"):
+        if mode == "allgather":
+            os.environ["VINUM_B200_DIST_MODE"] = "allgather"
+        raw = d.finish()          # low cardinality: peer exchange (or one all-gather); high: all-to-all repartition
+        os.environ.pop("VINUM_B200_DIST_MODE", None)
+        mode = f"{mode}[{getattr(d, 'exchange_mode_used', 'allgather')}]"
     else:
         d.repartition()
         raw = d.gather_raw()
@@ -70,6 +77,74 @@ for colname, desc in (("f3", True), ("i3", False)):
         print(f"dist_check sharded sort {colname} desc={desc} world={world} rows={n * world} ok={good}", flush=True)
         ok = ok and good
 
+# ---- GPU sample sort: splitters + one all-to-all, every rank ends up with its range of the global order ----
+from vinum_b200.dist import sample_sort_sharded
+for colname, desc in (("f3", True), ("i3", False), ("i0", True)):
+    col = datagen.device_column(colname, rank * n, n, stream=st)
+    k, ids = sample_sort_sharded(col, rank * n, desc, st)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((k, ids), parts, dst=0)
+    if rank == 0:
+        kk, ii = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+        host = datagen.host_column(colname, 0, n * world)
+        want = np.argsort(-host if desc else host, kind="stable")
+        good = np.array_equal(ii, want) and np.array_equal(kk, host[want])
+        print(f"dist_check sample sort {colname} desc={desc} world={world} rows={n * world} "
+              f"range sizes={[len(p[1]) for p in parts]} ok={good}", flush=True)
+        ok = ok and good
+
+# ---- float32 keys through the host-merge path (lossless widening on the wire) ----
+f32 = datagen.host_column("f2", rank * n, n).astype(np.float32)
+res = sort_sharded(vb.DeviceColumn.from_numpy(f32, st), rank * n, False, st)
+if rank == 0:
+    k, ids = res
+    host = datagen.host_column("f2", 0, n * world).astype(np.float32)
+    want = np.argsort(host, kind="stable")
+    good = np.array_equal(ids, want) and np.array_equal(k, host[want])
+    print(f"dist_check sharded sort float32 keys world={world} ok={good}", flush=True)
+    ok = ok and good
+
+# ---- ONE logical SQL query over the row-range-sharded HOST table (vinum_b200.sharded) ----
+names = ["i0", "i1", "f0", "f1"]
+shard = pa.table({c: datagen.host_column(c, rank * n, n) for c in names})
+tbl = vb.Table.from_arrow(shard).shard()
+whole = {c: datagen.host_column(c, 0, n * world) for c in names} if rank == 0 else None
+res = tbl.sql("SELECT i0, COUNT(*) AS c, SUM(f1) AS s FROM t WHERE f0 > 0.5 GROUP BY i0 ORDER BY i0").to_arrow()
+if rank == 0:
+    m = whole["f0"] > 0.5
+    good = (np.array_equal(res.column("i0").to_numpy(), np.arange(1000))
+            and np.array_equal(res.column("c").to_numpy().astype(np.int64), np.bincount(whole["i0"][m], minlength=1000))
+            and np.allclose(res.column("s").to_numpy(), np.bincount(whole["i0"][m], weights=whole["f1"][m], minlength=1000), rtol=1e-6, atol=0))
+    print(f"dist_check sharded Table.sql aggregate world={world} exchange={tbl.last_stats.get('exchange')} streamed={tbl.last_stats.get('streamed')} ok={good}", flush=True)
+    ok = ok and good
+else:
+    ok = ok and res.num_rows == 0
+res = tbl.sql("SELECT i0, AVG(f1) AS a, MAX(i1) AS mx FROM t WHERE f0 * 2 > f1 / 1000 GROUP BY i0 HAVING COUNT(*) > 10 ORDER BY a DESC LIMIT 7").to_arrow()
+if rank == 0:
+    m = whole["f0"] * 2 > whole["f1"] / 1000
+    cnt = np.bincount(whole["i0"][m], minlength=1000)
+    avg = np.bincount(whole["i0"][m], weights=whole["f1"][m], minlength=1000) / cnt
+    top = np.argsort(-avg, kind="stable")[:7]
+    good = np.array_equal(res.column("i0").to_numpy(), top) and np.allclose(res.column("a").to_numpy(), avg[top], rtol=1e-6)
+    mx = np.full(1000, np.iinfo(np.int64).min); np.maximum.at(mx, whole["i0"][m], whole["i1"][m])
+    good = good and np.array_equal(res.column("mx").to_numpy(), mx[top])
+    print(f"dist_check sharded Table.sql fused-expression aggregate + HAVING + ORDER BY + LIMIT ok={good}", flush=True)
+    ok = ok and good
+res = tbl.sql("SELECT i1, f1 FROM t WHERE f0 > 0.999 ORDER BY f1 DESC LIMIT 20").to_arrow()
+if rank == 0:
+    m = whole["f0"] > 0.999
+    o = np.argsort(-whole["f1"][m], kind="stable")[:20]
+    good = np.array_equal(res.column("i1").to_numpy(), whole["i1"][m][o]) and np.array_equal(res.column("f1").to_numpy(), whole["f1"][m][o])
+    print(f"dist_check sharded Table.sql filter + ORDER BY + LIMIT (rows gathered: {tbl.last_stats.get('gathered_rows')}) ok={good}", flush=True)
+    ok = ok and good
+res = tbl.sql("SELECT i1 FROM t WHERE f0 < 0.0001").to_arrow()
+if rank == 0:
+    good = np.array_equal(res.column("i1").to_numpy(), whole["i1"][whole["f0"] < 0.0001])
+    print(f"dist_check sharded Table.sql plain filter keeps global row order ok={good}", flush=True)
+    ok = ok and good
+
+from vinum_b200.dist import close_peer_windows
+close_peer_windows()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 dist.barrier()

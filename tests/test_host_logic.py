@@ -334,3 +334,91 @@ def test_partial_group_exchange_over_gloo_world2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+_GLOO_SAMPLE_SORT_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from vinum_b200.dist import order_codes, choose_splitters, split_counts, shard_range
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+rng = np.random.default_rng(5)
+n = 40_001
+for kind, desc in (("f", False), ("f", True), ("i", True), ("ties", False)):
+    if kind == "f":
+        col = rng.normal(0, 1, n); col[::97] = np.nan; col[::31] = -0.0; col[::29] = 0.0
+    elif kind == "i":
+        col = rng.integers(-2**62, 2**62, n)
+    else:
+        col = rng.integers(0, 4, n).astype(np.int64)      # four values: every splitter sits inside a run of ties
+    lo, hi = shard_range(n, rank, world)
+    mine = torch.from_numpy(col[lo:hi].copy())
+    codes = order_codes(mine, desc)
+    perm = torch.argsort(codes, stable=True)              # stands in for the device radix sort of the shard
+    codes, keys, ids = codes[perm], mine[perm], perm + lo
+    S = 64
+    take = torch.linspace(0, codes.numel() - 1, S).long()
+    allc = [torch.empty(S, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allc, codes[take].contiguous())
+    splitters = choose_splitters(torch.stack(allc), world)
+    sc = split_counts(codes, splitters)
+    cm = [torch.empty(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(cm, sc.contiguous())
+    counts = torch.stack(cm)
+    in_split, out_split = [int(x) for x in counts[rank]], [int(x) for x in counts[:, rank]]
+    rc = torch.empty(sum(out_split), dtype=torch.int64); ri = torch.empty(sum(out_split), dtype=torch.int64)
+    dist.all_to_all_single(rc, codes.contiguous(), out_split, in_split)
+    dist.all_to_all_single(ri, ids.contiguous(), out_split, in_split)
+    p2 = torch.argsort(rc, stable=True)                   # the owner's stable sort over runs in source-rank order
+    out_ids = ri[p2]
+    parts = [torch.empty(int(counts[:, r].sum()), dtype=torch.int64) for r in range(world)] if rank == 0 else None
+    sizes = [int(counts[:, r].sum()) for r in range(world)]
+    if rank == 0:
+        parts[0] = out_ids
+        for r in range(1, world):
+            dist.recv(parts[r], src=r)
+        got = torch.cat(parts).numpy()
+        want = torch.argsort(order_codes(torch.from_numpy(col.copy()), desc), stable=True).numpy()
+        assert np.array_equal(got, want), (kind, desc)     # == ONE stable sort of the whole column
+    else:
+        dist.send(out_ids, dst=0)
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sample_sort_plan_over_gloo_world2(tmp_path):
+    """The splitter / all-to-all plan of dist.sample_sort_sharded with 2 CPU ranks (torch's stable
+    argsort stands in for the device radix sort): the concatenation of the ranks' ranges must be
+    exactly one stable sort of the whole column -- NaN last in both directions, both zeros equal,
+    ties in global row order even when a splitter falls inside a run of equal keys."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker_ssort.py"
+    script.write_text(_GLOO_SAMPLE_SORT_WORKER.format(root=str(ROOT), port=port))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+
+
+def test_every_option_has_a_default_and_a_name():
+    import vinum_b200 as vb
+    names = ("FILTER_STAGE FILTER_PF FILTER_ITERS CMP_FAST ARITH_FAST ONEGROUP_FAST SORT_FUSE_LAST SORT_PREP SORT_RANK "
+             "AGG_LOG2S AGG_PF AGG_WARPS AGG_DIRECT AGG_DICT AGG_NOFAST AGG_LEARN_LOG2 LIST_LOG2 DEBUG INGEST_STAGED "
+             "INGEST_THREADS").split()
+    for n in names:
+        assert isinstance(vb.get_option(n), int)
+    assert vb.get_option("VINUM_B200_SORT_RANK") == vb.get_option("SORT_RANK")   # the environment spelling resolves too
+    with vb.options(AGG_DICT=0, SORT_RANK=0):
+        assert vb.get_option("AGG_DICT") == 0 and vb.get_option("SORT_RANK") == 0
+    assert vb.get_option("AGG_DICT") == 1 and vb.get_option("SORT_RANK") == 1

@@ -46,6 +46,7 @@ enum Opt {
     OPT_ONEGROUP_FAST,      // agg_onegroup8_kernel row pairs per thread (0: agg_onegroup_kernel)
     OPT_SORT_FUSE_LAST,     // 1: the last radix pass writes the int64 permutation itself
     OPT_SORT_PREP,          // sort_prepare8_kernel loads per thread (0: sort_prepare_kernel)
+    OPT_SORT_RANK,          // 1: radix ranking with pipelined counter atomics, 0: serial counter update per item
     OPT_AGG_LOG2S,          // agg_fast_kernel: log2 of the CTA key table slots (hash mode)
     OPT_AGG_PF,             // agg_fast_kernel: L2 prefetch distance in tiles (-1: automatic)
     OPT_AGG_WARPS,          // agg_fast_kernel: warps per CTA (0: automatic)

@@ -203,6 +203,7 @@ struct PassParams {
     const uint64_t* src;                // LAST pass + out_sorted: the 8-byte key column (for the codes that do not invert)
     int src_kind;                       // 0 uint64, 1 int64, 2 float64
     int desc;
+    int rank_serial;                    // option SORT_RANK=0: serial counter update per item (round 1's form)
 };
 
 __device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int shift) {
@@ -275,6 +276,26 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
     // and wrote the counter with LDS / STS per item, a serial chain of 16 shared-memory round trips per
     // tile (short scoreboard 41 % of all stall samples, profiles/r01_sort_pass_ncu_full.md).
     constexpr int HALF = RS_RANK_BATCH;
+    if (p.rank_serial) {
+        // round 1's form (option SORT_RANK=0): the leader reads and writes the counter item by item
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k) {
+            const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+            const bool in = li < tile_n;
+            const uint32_t d = pass_digit(key[k], idx[k], p.shift);
+            unsigned peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
+            if (!in) peers = 1u << lane;
+            const int leader = __ffs(peers) - 1;
+            uint32_t c = 0;
+            if (in && lane == leader) {
+                c = s_wcnt[warp][d];
+                s_wcnt[warp][d] = c + __popc(peers);
+            }
+            c = __shfl_sync(0xffffffffu, c, leader);
+            rank[k] = c + __popc(peers & lt);
+            __syncwarp();
+        }
+    } else {
 #pragma unroll
     for (int h = 0; h < RS_ITEMS / HALF; ++h) {
         uint32_t cnt[HALF];
@@ -303,6 +324,7 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
             const uint32_t c = __shfl_sync(0xffffffffu, cnt[j], (int) (rank[k] >> 16));
             rank[k] = c + (rank[k] & 0xffffu);
         }
+    }
     }
     __syncthreads();
 
@@ -633,6 +655,7 @@ static int sort_indices_impl(const VkColumn* keys, const int32_t* orders, int n_
             ps.bucket_start = sc.hist + d * 256;
             ps.ticket = sc.ticket;
             ps.status = sc.status;
+            ps.rank_serial = opt(OPT_SORT_RANK) == 0;
             VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
             VK_CUDA(cudaMemsetAsync(sc.status, 0, status_used, s));
             if (is_final) {

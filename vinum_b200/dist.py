@@ -457,3 +457,114 @@ def sort_sharded(column, row0: int, descending: bool, stream, group=None):
         runs_k.append(_key_from_bits64(a[0, :s], keys_sorted.dtype))
         runs_i.append(a[1, :s])
     return merge_sorted_runs(runs_k, runs_i, descending)
+
+
+# ------------------------------------------------------------------ sample sort ----
+def order_codes(values: "torch.Tensor", descending: bool) -> "torch.Tensor":
+    """Signed int64 codes that order like Arrow's SortIndices orders the values (sort.cpp:22-48):
+    ascending or descending numbers, -0.0 == +0.0, NaN after every number in BOTH directions.
+    `values`: int64 or float64 tensor."""
+    import torch
+    if values.dtype == torch.float64:
+        bits = values.view(torch.int64)
+        nan = torch.isnan(values)
+        bits = torch.where(values == 0, torch.zeros_like(bits), bits)                  # -0.0 -> +0.0
+        code = bits ^ ((bits >> 63) & 0x7FFFFFFFFFFFFFFF)                               # monotonic in the value
+        if descending:
+            code = ~code
+        return torch.where(nan, torch.full_like(code, 0x7FFFFFFFFFFFFFFF), code)
+    if values.dtype != torch.int64:
+        raise TypeError("order_codes: int64 or float64")
+    return ~values if descending else values
+
+
+def choose_splitters(all_samples: "torch.Tensor", world: int) -> "torch.Tensor":
+    """world - 1 splitters at the equal quantiles of the gathered (sorted-per-rank) samples."""
+    import torch
+    s, _ = torch.sort(all_samples.flatten())
+    n = s.numel()
+    pos = [(n * (r + 1)) // world for r in range(world - 1)]
+    return s[torch.tensor([min(max(p, 1), n) - 1 for p in pos], dtype=torch.long, device=s.device)] if n else s[:0]
+
+
+def split_counts(sorted_codes: "torch.Tensor", splitters: "torch.Tensor") -> "torch.Tensor":
+    """Rows of an ascending code run that go to each of len(splitters) + 1 destinations: destination r
+    gets the codes in (splitter[r-1], splitter[r]] -- equal codes always travel together, whatever rank
+    they come from, so the destination's stable sort keeps ties in global row order."""
+    import torch
+    cuts = torch.searchsorted(sorted_codes, splitters, right=True)
+    edges = torch.cat([cuts.new_zeros(1), cuts, cuts.new_full((1,), sorted_codes.numel())])
+    return edges[1:] - edges[:-1]
+
+
+def sample_sort_sharded(column, row0: int, descending: bool, stream, group=None, samples_per_rank: int = 256):
+    """ORDER BY one null-free int64 / float64 column over row-range shards, entirely on the GPUs
+    (SURVEY 8f row 4): every rank radix-sorts its shard, the ranks agree on world - 1 splitters from a
+    sample, ONE all-to-all (NCCL over NVLink) sends every row to the rank that owns its key range, and
+    that rank's stable radix sort over the received runs -- concatenated in source-rank order, which is
+    row order -- finishes its range.  Rank r returns (keys, global row ids) of the r-th range of the
+    global order as NumPy arrays; the concatenation over ranks is what one stable sort of the whole
+    column returns (Sort::Sorted, sort.cpp:15-63).  Replaces the rank-0 host merge of `sort_sharded`."""
+    import torch
+    import torch.distributed as dist
+    from . import ops
+    from .device import DeviceColumn
+    world = dist.get_world_size(group)
+    st = stream
+    ts = torch.cuda.ExternalStream(int(st.handle)) if st.handle else torch.cuda.default_stream()
+    order = L.DESC if descending else L.ASC
+    if column.has_nulls or column.dtype not in (L.I64, L.F64):
+        raise TypeError("sample_sort_sharded: null-free int64 / float64 keys (use sort_sharded otherwise)")
+    n = column.length
+    idx, keys_sorted = ops.sort_indices_keys([column], [order], st)
+    if world == 1:
+        return keys_sorted.to_numpy(st), idx.to_numpy(st) + np.int64(row0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    tdt = torch.float64 if column.dtype == L.F64 else torch.int64
+    with torch.cuda.stream(ts):
+        keys_t = _as_tensor(keys_sorted, n, tdt, dev)
+        ids_t = _as_tensor(idx, n, torch.int64, dev) + row0
+        codes = order_codes(keys_t, descending)
+        # ---- splitters from an evenly spaced sample of every rank's sorted run ----
+        take = torch.linspace(0, max(n - 1, 0), samples_per_rank, device=dev).long() if n else torch.zeros(0, dtype=torch.long, device=dev)
+        mine = codes[take] if n else codes.new_full((samples_per_rank,), 0x7FFFFFFFFFFFFFFF)
+        if mine.numel() < samples_per_rank:
+            mine = torch.cat([mine, mine.new_full((samples_per_rank - mine.numel(),), 0x7FFFFFFFFFFFFFFF)])
+        gathered = torch.empty(world * samples_per_rank, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, mine.contiguous(), group=group)
+        splitters = choose_splitters(gathered, world)
+        send_counts = split_counts(codes, splitters)
+        counts = torch.empty(world * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, send_counts.contiguous(), group=group)
+        counts = counts.view(world, world).cpu()                                   # host sync: split sizes
+        rank = dist.get_rank(group)
+        in_split = [int(x) for x in counts[rank]]
+        out_split = [int(x) for x in counts[:, rank]]
+        total = sum(out_split)
+        recv_k = torch.empty(max(total, 1), dtype=tdt, device=dev)[:total]
+        recv_i = torch.empty(max(total, 1), dtype=torch.int64, device=dev)[:total]
+        dist.all_to_all_single(recv_k, keys_t.contiguous(), out_split, in_split, group=group)
+        dist.all_to_all_single(recv_i, ids_t.contiguous(), out_split, in_split, group=group)
+        ts.synchronize()
+    if total == 0:
+        return np.empty(0, dtype=np.float64 if tdt == torch.float64 else np.int64), np.empty(0, dtype=np.int64)
+    # ---- the received runs, in source-rank order, through one more stable device sort ----
+    rk = DeviceColumn.from_device_ptr(recv_k.data_ptr(), total, column.dtype, owner=recv_k)
+    ri = DeviceColumn.from_device_ptr(recv_i.data_ptr(), total, L.I64, owner=recv_i)
+    perm, out_keys = ops.sort_indices_keys([rk], [order], st)
+    out_ids = ops.take(ri, perm, st)
+    return out_keys.to_numpy(st), out_ids.to_numpy(st)
+
+
+def _as_tensor(col, n: int, dtype, dev):
+    """A torch view of a device column's values (no copy; the column must outlive the tensor's use)."""
+    import torch
+    if n == 0:
+        return torch.empty(0, dtype=dtype, device=dev)
+    iface = {"shape": (n,), "typestr": "<f8" if dtype == torch.float64 else "<i8",
+             "data": (col.data_ptr + col.offset * 8, False), "version": 3, "strides": None}
+
+    class _Holder:
+        __cuda_array_interface__ = iface
+        _keep = col
+    return torch.as_tensor(_Holder(), device=dev)
