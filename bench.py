@@ -267,6 +267,46 @@ def cpu_baseline_single(rows: int) -> dict:
                       f"compiled C++ operators, batch 10000), best of 2, one process / one thread"}
 
 
+def _dropin_worker(rows: int):
+    """The reference's own `vinum.Table.sql` (its binder, planner, executor, Python operators) on top of
+    vinum_b200: `vinum_lib` = vinum_b200.vinum_lib and AggregateOperator dispatching scan -> filter ->
+    aggregate plans to the fused device path (vinum_b200.compat.install)."""
+    from oracle import ref_stack
+    import pyarrow as pa
+    from vinum_b200 import datagen
+    vn = ref_stack.reference_vinum(gpu_operators=True)
+    table = pa.table({n: pa.array(datagen.host_column(n, 0, rows)) for n in ("i0", "f0", "f1")})
+    tbl = vn.Table.from_arrow(table)
+    best, groups = None, 0
+    for _ in range(4):
+        t0 = time.perf_counter()
+        out = tbl.sql(QUERY).to_arrow()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        groups = out.num_rows
+    return best, groups
+
+
+def dropin_reference_api(rows: int) -> dict:
+    """Rows/s of the drop-in under the REFERENCE's Python layers (separate process: the reference binds
+    `vinum_lib` at import time).  Reported beside cpu_baseline, which is the same call on the reference's
+    own operators."""
+    from oracle import ref_stack
+    if not ref_stack.available():
+        return {"value": None, "note": "oracle/_ref (vinum_pyref.zip) not built"}
+    code = ("import sys, json; sys.path.insert(0, %r); import bench; "
+            "print(json.dumps(bench._dropin_worker(%d)))" % (ROOT, rows))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        return {"value": None, "note": "failed: " + r.stderr[-400:]}
+    best, groups = json.loads(r.stdout.strip().splitlines()[-1])
+    assert groups == 1000
+    return {"value": rows / best, "unit": "rows/s", "rows": rows, "ms": best * 1e3,
+            "api": "reference's vinum.Table.from_arrow(pageable table).sql(QUERY) after vinum_b200.compat.install()",
+            "note": "best of 4; the reference's parser stand-in, binder, planner and executor run unchanged; "
+                    "AggregateOperator.next dispatches the scan -> filter -> aggregate plan to the fused device path"}
+
+
 # --------------------------------------------------------------------- our arm ----
 class _Timer:
     """CUDA-event timing on the package's stream (torch.cuda.Event only sees torch's stream)."""
@@ -641,6 +681,7 @@ def run_ours(args) -> dict:
         if not args.no_configs:
             result["configs"] = run_configs(vb, t8, rows, st, peak)
         result["cpu_baseline"] = cpu_baseline_single(args.cpu_rows)
+        result["dropin_reference_api"] = dropin_reference_api(e2e_rows)
     if distributed:
         close_peer_windows()
         dist.destroy_process_group()

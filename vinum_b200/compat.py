@@ -11,6 +11,9 @@ this package without touching its sources.
 * `vinum_lib` (the pybind11 extension, vinum/core/vinum_lib.cpp:20-167) -> `vinum_b200.vinum_lib`,
   looked up by module name, so `AggregateOperator` / `SortOperator` / `TableReaderOperator`
   (vinum/core/aggregate.py:96-124, vinum/core/algebra.py:150-177,250-265) drive the GPU operators;
+* `AggregateOperator.next` (the operator dispatch of vinum/core) -> the fused, streaming
+  filter -> hash-aggregate path when the plan below it is scan -> [prune] -> [filter] -> aggregate over
+  plain numeric columns (`_install_operator_dispatch`); every other plan is untouched;
 * `parser_factory` (vinum/parser/parser.py:295-311) -> a parser object whose `.parse()` returns the
   reference's own `Query` tree, built by this package's recursive-descent parser -- the reference's
   parser needs the pglast C extension (pinned ==1.17); when pglast is not importable a stub
@@ -93,6 +96,98 @@ class _Parser:
                         q.limit, q.offset)
 
 
+def _install_operator_dispatch() -> None:
+    """The operator dispatch of vinum/core routed to the fused device path (BASELINE.json north_star).
+
+    `AggregateOperator.next` (vinum/core/aggregate.py:114-124) pulls 10 000-row batches through
+    TableReaderOperator -> [ProjectOperator: column pruning] -> FilterOperator -> AggregateOperator, one
+    NumPy comparison, one Arrow filter of every column and one `vinum_lib` call per batch.  When that
+    chain is exactly this shape -- the WHERE is `column <cmp> numeric literal`, keys and aggregate
+    arguments are plain null-free numeric columns of the table -- the patched `next` hands the WHOLE table
+    to `vinum_b200.executor.filter_aggregate` (chunks copied host -> device on a copy stream while the
+    fused filter -> hash-aggregate kernel consumes the previous one; no mask, no filtered batch) and yields
+    the one RecordBatch `BaseAggregate::Result` would have produced (base_aggregate.cpp:47-68).  Any other
+    plan runs the reference's own loop unchanged, on `vinum_b200.vinum_lib`'s aggregate classes."""
+    import pyarrow as pa
+    import vinum.core.aggregate as ra
+    import vinum.core.algebra as alg
+    import vinum.core.expressions as rex
+    from vinum.arrow.record_batch import RecordBatch
+    from vinum.core.base import VectorizedExpression
+    from vinum.parser.query import Column, Literal, SQLExpression
+    from . import executor
+
+    if getattr(ra.AggregateOperator, "_vinum_b200_dispatch", False):
+        return
+    cmp_of = {id(rex.EXPRESSION_FUNCTIONS[k][0]): sym for k, sym in (
+        (SQLExpression.EQUALS, "=="), (SQLExpression.NOT_EQUALS, "!="), (SQLExpression.GREATER_THAN, ">"),
+        (SQLExpression.GREATER_THAN_OR_EQUAL, ">="), (SQLExpression.LESS_THAN, "<"), (SQLExpression.LESS_THAN_OR_EQUAL, "<="))}
+    flip = {"==": "==", "!=": "!=", ">": "<", ">=": "<=", "<": ">", "<=": ">="}
+    original_next = ra.AggregateOperator.next
+
+    def match(op):
+        """(table, where, group-by names, [(FUNC, column, out name)]) of a fusable plan, else None."""
+        p = op._parent_operator
+        where = None
+        if isinstance(p, alg.FilterOperator):
+            pred = p._arguments[0]
+            if type(pred) is not VectorizedExpression or id(pred._function) not in cmp_of or len(pred._arguments) != 2:
+                return None
+            a, b = pred._arguments
+            sym = cmp_of[id(pred._function)]
+            if isinstance(a, Literal) and isinstance(b, Column):
+                a, b, sym = b, a, flip[sym]
+            if not (isinstance(a, Column) and isinstance(b, Literal)) or isinstance(b.value, bool) or \
+                    not isinstance(b.value, (int, float)):
+                return None
+            where = (a.get_column_name(), sym, b.value)
+            p = p._parent_operator
+        if isinstance(p, alg.ProjectOperator):
+            if p._keep_input_table or p._col_names or not all(isinstance(x, Column) for x in p._arguments):
+                return None
+            p = p._parent_operator
+        if type(p) is not alg.TableReaderOperator:
+            return None
+        table = getattr(p._reader, "_table", None)
+        if not isinstance(table, pa.Table):
+            return None
+        keys = [c.get_column_name() for c in op._group_by_columns]
+        if not keys or len(set(keys)) != len(keys):
+            return None
+        funcs = []
+        for f in op._agg_funcs:
+            name = f.get_agg_func_name()
+            if name not in ("COUNT_STAR", "COUNT", "MIN", "MAX", "SUM", "AVG"):
+                return None
+            funcs.append((name, f.get_input_column_name(), f.get_column_name()))
+        if not funcs:
+            return None
+        for name in keys + [c for _, c, _ in funcs if c] + ([where[0]] if where else []):
+            i = table.schema.get_field_index(name)
+            if i < 0:
+                return None
+            col = table.column(i)
+            t = col.type
+            if col.null_count or not (pa.types.is_integer(t) or pa.types.is_floating(t)) or pa.types.is_float16(t):
+                return None
+        return table, where, keys, funcs
+
+    def next(self):
+        plan = match(self)
+        if plan is None:
+            yield from original_next(self)
+            return
+        table, where, keys, funcs = plan
+        rb = executor.filter_aggregate(table, keys, funcs, where)
+        names = [c.get_column_name() for c in self._agg_cols] + [o for _, _, o in funcs]
+        arrays = [rb.column(rb.schema.get_field_index(n)) for n in names]   # agg_cols first (base_aggregate.cpp:100-118)
+        self.fused_device_path = True
+        yield RecordBatch(pa.RecordBatch.from_arrays(arrays, names=names))
+
+    ra.AggregateOperator.next = next
+    ra.AggregateOperator._vinum_b200_dispatch = True
+
+
 def install(use_gpu_operators: bool = True, use_parser: bool = True) -> None:
     """Register the substitutions.  Call before the first `import vinum`."""
     if use_gpu_operators:
@@ -110,3 +205,5 @@ def install(use_gpu_operators: bool = True, use_parser: bool = True) -> None:
                 __import__(name)
                 mod = sys.modules[name]
             mod.parser_factory = factory
+    if use_gpu_operators:
+        _install_operator_dispatch()

@@ -58,6 +58,7 @@ enum Opt {
     OPT_DEBUG,              // 1: trace the aggregate's host decisions to stderr
     OPT_INGEST_STAGED,      // 1: pageable host memory goes through the pinned bounce-buffer pool (vk_ingest.cu)
     OPT_INGEST_THREADS,     // worker threads of that pool (0: automatic; read when the pool starts)
+    OPT_INGEST_PIECE_KB,    // bytes per bounce copy, in KB
     OPT_COUNT
 };
 int64_t opt(int id);

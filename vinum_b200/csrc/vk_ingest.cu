@@ -3,7 +3,7 @@
 //
 // cudaMemcpyAsync from pageable memory is staged by the driver through one internal bounce buffer on
 // the calling thread: ~6-10 GB/s, a fifth of what the PCIe Gen5 link carries.  A pyarrow.Table that a
-// user builds from NumPy / pandas / a CSV file is pageable.  Here the copy is cut into 4 MB pieces;
+// user builds from NumPy / pandas / a CSV file is pageable.  Here the copy is cut into pieces (option INGEST_PIECE_KB, default 1 MB);
 // a small pool of worker threads copies each piece into a package-owned PINNED slot (two per worker)
 // and queues the DMA of that slot on the caller's stream; a slot is refilled only after the event
 // recorded behind its DMA has fired.  The CPU copy of piece k+1 overlaps the DMA of piece k, so the
@@ -21,8 +21,18 @@
 namespace vk {
 namespace {
 
-constexpr size_t PIECE_BYTES = 4u << 20;
+constexpr size_t MAX_PIECE_BYTES = 8u << 20;   // slot size; the piece actually used is option INGEST_PIECE_KB
 constexpr int SLOTS_PER_WORKER = 2;
+
+// Piece size: small enough that the workers' slots together stay in the host's last-level cache (the DMA
+// engine then reads a piece from cache instead of DRAM: one pass over host memory per byte instead of
+// three), large enough that the per-copy driver overhead (a few microseconds) stays small.
+size_t piece_bytes() {
+    int64_t kb = opt(OPT_INGEST_PIECE_KB);
+    if (kb < 64) kb = 64;
+    if (kb > (int64_t) (MAX_PIECE_BYTES >> 10)) kb = (int64_t) (MAX_PIECE_BYTES >> 10);
+    return (size_t) kb << 10;
+}
 
 struct Job {
     std::mutex mu;
@@ -79,7 +89,7 @@ private:
             }
             Slot& s = slots[next];
             next = (next + 1) % SLOTS_PER_WORKER;
-            if (e == cudaSuccess && s.host == nullptr) e = cudaHostAlloc((void**) &s.host, PIECE_BYTES, cudaHostAllocPortable);
+            if (e == cudaSuccess && s.host == nullptr) e = cudaHostAlloc((void**) &s.host, MAX_PIECE_BYTES, cudaHostAllocPortable);
             if (e == cudaSuccess && s.busy) e = cudaEventSynchronize(s.ev);   // the slot's previous DMA has read it
             if (e == cudaSuccess && s.ev_device != p.device) {
                 // (the old event, if any, has fired: it was just waited for)
@@ -151,11 +161,12 @@ int vk_memcpy_h2d_staged(void* dst, const void* host_src, uint64_t bytes, VkStre
     VK_CUDA(cudaGetDevice(&device));
     IngestPool* pl = pool();
     Job job;
-    const size_t n_pieces = (size_t) ((bytes + PIECE_BYTES - 1) / PIECE_BYTES);
+    const size_t piece = piece_bytes();
+    const size_t n_pieces = (size_t) ((bytes + piece - 1) / piece);
     job.remaining = (int) n_pieces;
     for (size_t i = 0; i < n_pieces; ++i) {
-        const size_t off = i * PIECE_BYTES;
-        const size_t len = bytes - off < PIECE_BYTES ? (size_t) (bytes - off) : PIECE_BYTES;
+        const size_t off = i * piece;
+        const size_t len = bytes - off < piece ? (size_t) (bytes - off) : piece;
         pl->submit(Piece{static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(host_src) + off, len,
                          (cudaStream_t) stream, device, &job});
     }

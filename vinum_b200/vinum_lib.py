@@ -85,6 +85,35 @@ def _as_batch_like(batch):
     raise TypeError(f"expected pyarrow.RecordBatch, got {type(batch).__name__}")
 
 
+def _rejoin(col: pa.ChunkedArray) -> pa.Array:
+    """The chunks of `col` as one array: without a copy when they are consecutive slices of one buffer
+    (fixed-width, no NULLs -- what zero-copy row-range slices of a table are), else concatenated."""
+    chunks = [c for c in col.chunks if len(c)]
+    if not chunks:
+        return pa.array([], type=col.type)
+    if len(chunks) == 1:
+        return chunks[0]
+    t = col.type
+    try:
+        width = t.bit_width // 8 if t.bit_width % 8 == 0 else 0
+    except ValueError:
+        width = 0
+    if width and all(c.null_count == 0 for c in chunks):
+        bufs = [c.buffers()[1] for c in chunks]
+        start = bufs[0].address + chunks[0].offset * width
+        pos, ok = start, True
+        for c, b in zip(chunks, bufs):
+            if b is None or b.address + c.offset * width != pos:
+                ok = False
+                break
+            pos += len(c) * width
+        if ok:
+            total = sum(len(c) for c in chunks)
+            whole = pa.foreign_buffer(start, total * width, base=(chunks, bufs))
+            return pa.Array.from_buffers(t, total, [None, whole])
+    return pa.concat_arrays(chunks)
+
+
 def _schema_of(batch) -> pa.Schema:
     return batch.schema() if isinstance(batch, DeviceBatch) else batch.schema
 
@@ -140,9 +169,52 @@ class _BaseAggregate:
             if not (pa.types.is_integer(t) or pa.types.is_floating(t) or pa.types.is_temporal(t)):
                 raise RuntimeError("Unsupported data type for aggregation column.")  # array_iterators.cpp:79
 
+    # The reference feeds 10 000-row batches (vinum/__init__.py:52).  One device launch and one stream
+    # synchronisation per such batch is launch-latency bound, so host batches are collected until
+    # COALESCE_ROWS rows are pending and go to the device as ONE chunk: consecutive zero-copy slices of
+    # the same table (what TableBatchReader yields) are re-joined without touching the data, anything
+    # else (FilterOperator's fresh arrays) is concatenated on the host first.
+    COALESCE_ROWS = 1 << 22
+
     def next(self, batch) -> None:
         batch = _as_batch_like(batch)
         self._ensure_init(_schema_of(batch))
+        if isinstance(batch, DeviceBatch):
+            self._flush()
+            self._update(batch)
+            return
+        if not hasattr(self, "_pending"):
+            self._pending, self._pending_rows = [], 0
+        if batch.num_rows == 0 and self._pending:
+            return
+        self._pending.append(batch)
+        self._pending_rows += batch.num_rows
+        if self._pending_rows >= self.COALESCE_ROWS:
+            self._flush()
+
+    def _flush(self) -> None:
+        pending = getattr(self, "_pending", None)
+        if not pending:
+            return
+        self._pending, self._pending_rows = [], 0
+        if len(pending) == 1:
+            chunk = pending[0]
+        else:
+            names = self._needed_columns(pending[0].schema)
+            tables = [b if isinstance(b, pa.Table) else pa.Table.from_batches([b]) for b in pending]
+            chunk = pa.table({n: _rejoin(pa.chunked_array([c for t in tables for c in t.column(n).chunks],
+                                                          type=tables[0].schema.field(n).type)) for n in names}) \
+                if names else pa.table({"__rows": pa.nulls(sum(t.num_rows for t in tables))})
+        self._update(chunk)
+
+    def _needed_columns(self, schema: pa.Schema) -> List[str]:
+        out = []
+        for n in self._groupby_cols + [f.column_name for f in self._funcs if f.column_name]:
+            if n not in out:
+                out.append(n)
+        return out
+
+    def _update(self, batch) -> None:
         st = self._stream
         cache = {}
 
@@ -161,6 +233,7 @@ class _BaseAggregate:
             st.sync()  # the async copies read the caller's Arrow buffers
 
     def result(self) -> pa.RecordBatch:
+        self._flush()
         if self._agg is None:
             # result() before any batch: the reference builds an empty batch with no
             # schema information (base_aggregate.cpp:47-68)
