@@ -80,6 +80,7 @@ struct FastParams {
     uint64_t direct_base;         // direct mode: gid = key - direct_base
     int64_t row_limit;            // row-level global inserts stop here (flush reserve above it)
     int pf_dist;                  // L2 bulk prefetch distance in tiles (0 = off)
+    int gid_bits;                 // MATCHC: bits that distinguish the dense group ids (ceil(log2(gmax)))
     // hash mode with a host-built dictionary (read-only in the kernel): cuckoo placement of the keys the
     // learning launch found, two hash functions, S = 1 << log2s slots; nullptr = insert-as-you-go table
     const uint64_t* dict_keys;    // [S], LK_EMPTY = free
@@ -325,7 +326,7 @@ struct FastCtx {
 // Phase 2 is one short critical section per row: store the lane id as the entry's tag,
 // sync the warp, load the whole entry (tag + COUNT + cell in one LDS.128); the lane that
 // reads its own tag back applies the row and stores the entry, the others go round again.
-template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64>
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, bool MATCHC>
 __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx, RawTile<PK, NV>& t, uint8_t* smem,
                                           uint32_t* s_ngroups, int64_t row0, int tid, int nthreads, int64_t refill_tile,
                                           uint32_t& spilled) {
@@ -486,6 +487,61 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
     // the key / predicate registers are dead: refill them with the tile after next
     if (refill_tile >= 0) load_tile_keys<PK, NV, MODE>(p, refill_tile, tid, nthreads, t);
 
+    // ---- phase 2 (MATCHC): lanes with equal group ids combine in registers, ONE update per group ----
+    // C3's regime (every row reaches the tables) is bound by the shared-memory pipe: tag store + entry
+    // load + entry store per row, 61 % of the wavefronts bank-conflict replays (profiles/r01_agg_fast_c3).
+    // Here the lanes of a warp that hold the same group id in row r are found with one ballot per id bit
+    // (no shared memory, no MATCH.ANY: 64 issue cycles on the ADU pipe); the lowest of them pulls the
+    // others' values over with shuffles and alone does the LDS.128 / STS.128 of the entry -- no tag, no
+    // retry rounds, and a hot key costs shuffles instead of up to 32 serial rounds of shared-memory traffic.
+    if constexpr (MATCHC) {
+        static_assert(SUMF64 && NW == 2, "the match-combine path is the COUNT + SUM(float64) entry");
+        const uint32_t lane_bit = 1u << cx.lane;
+        uint32_t peers[FA_R];
+#pragma unroll
+        for (int r = 0; r < FA_R; ++r) {
+            const bool on = (todo >> r) & 1u;
+            const uint32_t g = (ea[r] - cx.a_ent) >> 4;
+            uint32_t m = __ballot_sync(0xffffffffu, on);
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                if (b < p.gid_bits) {
+                    const bool bit = (g >> b) & 1u;
+                    const uint32_t vote = __ballot_sync(0xffffffffu, on && bit);
+                    m &= bit ? vote : ~vote;
+                }
+            }
+            peers[r] = on ? m : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < FA_R; ++r) {
+            const bool leader = peers[r] != 0u && (peers[r] & (lane_bit - 1u)) == 0u;
+            double acc = __longlong_as_double((long long) row_val<MODE>(p, 0, t.vq[0], r));
+            const double mine = acc;
+            uint32_t rem = leader ? (peers[r] & ~lane_bit) : 0u;
+            while (__any_sync(0xffffffffu, rem != 0u)) {   // one trip per extra lane of the fullest group
+                const int src = rem ? __ffs(rem) - 1 : (int) cx.lane;
+                const double x = __shfl_sync(0xffffffffu, mine, src);
+                if (rem) {
+                    acc += x;
+                    rem &= rem - 1u;
+                }
+            }
+            if (leader) {
+                uint32_t e[4];
+                lds128(ea[r], e);
+                e[0] += (uint32_t) __popc(peers[r]);
+                const double sum = __hiloint2double((int) e[3], (int) e[2]) + acc;
+                e[2] = (uint32_t) __double2loint(sum);
+                e[3] = (uint32_t) __double2hiint(sum);
+                sts128(ea[r], e);
+            }
+            __syncwarp();   // the next row's leader may be another lane updating the same entry
+            if ((r & 1) && refill_tile >= 0) load_tile_vals<PK, NV, MODE>(p, refill_tile, tid, nthreads, t, r >> 1);
+        }
+        return;
+    }
+
     // ---- phase 2: accumulate into the warp-private entries, FA_K rows per round ----
     // The FA_K rows of a group arbitrate and update in the same round, so their
     // shared-memory round trips overlap (the kernel is bound by this dependent chain, not by
@@ -563,7 +619,7 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
     }
 }
 
-template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64>
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, bool MATCHC = false>
 __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_ngroups;
@@ -623,7 +679,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
     };
     auto process = [&](int64_t tl, RawTile<PK, NV>& t) {
         const int64_t nx = tl + 2 * stride;
-        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64>(p, cx, t, smem, &s_ngroups, tl * tile_rows + tid * 2, tid, nthreads,
+        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64, MATCHC>(p, cx, t, smem, &s_ngroups, tl * tile_rows + tid * 2, tid, nthreads,
                                                     nx < p.num_tiles ? nx : (int64_t) -1, spilled);
     };
     if (tile < p.num_tiles) load_all(tile, ta);
@@ -740,14 +796,15 @@ struct FastLaunch {
     int mode;      // FastMode
     bool direct;
     bool sumf64;
+    bool matchc;   // SUMF64 only: combine equal group ids of a warp in registers (C3's regime)
     int grid, threads;
     size_t smem;
 };
 
 
-#define VK_FAST_GO(PK, NV, NW, MODE, DIRECT, SUMF64)                                                             \
+#define VK_FAST_GO(PK, NV, NW, MODE, DIRECT, SUMF64, ...)                                                        \
     do {                                                                                                       \
-        auto kernel = agg_fast_kernel<PK, NV, NW, MODE, DIRECT, SUMF64>;                                        \
+        auto kernel = agg_fast_kernel<PK, NV, NW, MODE, DIRECT, SUMF64, ##__VA_ARGS__>;                         \
         VK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) l.smem));      \
         kernel<<<l.grid, l.threads, l.smem, s>>>(p);                                                           \
         VK_CHECK_LAUNCH("agg_fast_kernel");                                                                    \
@@ -760,6 +817,7 @@ int launch_fast_lean(const FastParams& p, const FastLaunch& l, cudaStream_t s) {
     switch (p.n_cols) {
         case 0: VK_FAST_GO(PK, 0, 2, MODE, DIRECT, false);
         case 1:
+            if (l.nw == 2 && l.sumf64 && l.matchc) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true, true);
             if (l.nw == 2 && l.sumf64) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true);
             if (l.nw == 2) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, false);
             VK_FAST_GO(PK, 1, 4, MODE, DIRECT, false);
