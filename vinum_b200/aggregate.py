@@ -185,7 +185,7 @@ class Aggregator:
         while True:
             nbytes = int(L._lib.vk_agg_result_packed_bytes(nk, nf, cap))
             host = _pinned_scratch(nbytes)
-            dev = DeviceBuffer(nbytes, st)
+            dev = DeviceBuffer(nbytes, st, zero=True)   # the whole block is copied back: no uninitialised padding
             lib.vk_agg_result_packed(self._h, cap, C.c_void_p(dev.ptr), st.ptr)
             lib.vk_memcpy_d2h(C.c_void_p(host.ptr), C.c_void_p(dev.ptr), nbytes, st.ptr)
             if extra_d2h is not None:

@@ -85,7 +85,7 @@ struct FastParams {
     // learning launch found, two hash functions, S = 1 << log2s slots; nullptr = insert-as-you-go table
     const uint64_t* dict_keys;    // [S], LK_EMPTY = free
     const uint16_t* dict_gids;    // [S] dense group id of the slot's key
-    uint64_t seed_a, seed_b;
+    uint64_t seed_a;              // seed of the key fold (dict_fold)
     long long* key_range;         // optional {min, max} (signed order) of the keys this launch flushes
     GTable table;
     ReplayList replay;
@@ -248,11 +248,14 @@ __host__ __device__ __forceinline__ uint32_t fast_hash32(uint64_t key) {
     return x * 0x9E3779B1u;  // Fibonacci hashing: the TOP bits index the table
 }
 // The dictionary's two slot choices for a key (cuckoo hashing; the host retries other seeds on a cycle).
-__host__ __device__ __forceinline__ uint32_t dict_hash_a(uint64_t key, uint64_t seed) { return fast_hash32(key ^ seed); }
-__host__ __device__ __forceinline__ uint32_t dict_hash_b(uint64_t key, uint64_t seed) {
-    const uint64_t k = ((key << 29) | (key >> 35)) * 0xD6E8FEB86659FD93ULL + seed;
-    return fast_hash32(k ^ (k >> 32));
+// Both come from ONE 32-bit fold of the key (3 instructions) and one multiply each: the lookup runs per
+// selected row, and the first version's two independent 64-bit hashes cost 1.6x the instructions of the
+// direct-id kernel (profiles/r02_agg_fast_dict_ncu_full.md).
+__host__ __device__ __forceinline__ uint32_t dict_fold(uint64_t key, uint64_t seed) {
+    return ((uint32_t) key ^ (uint32_t) seed) ^ (((uint32_t) (key >> 32) ^ (uint32_t) (seed >> 32)) * 0x85EBCA77u);
 }
+__host__ __device__ __forceinline__ uint32_t dict_slot_a(uint32_t x, uint32_t shift) { return ((x ^ (x >> 16)) * 0x9E3779B1u) >> shift; }
+__host__ __device__ __forceinline__ uint32_t dict_slot_b(uint32_t x, uint32_t shift) { return ((x ^ (x >> 13)) * 0xC2B2AE35u + 0x27D4EB2Fu) >> shift; }
 
 // One folded group of a CTA (or one spilled row) into the global table.
 __device__ __forceinline__ void fast_global_update(const FastParams& p, int64_t g, uint64_t cnt, const uint64_t* w /*cells*/) {
@@ -390,7 +393,8 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
         for (int r = 0; r < FA_R; ++r) {
             ea[r] = cx.a_ent;
             if ((act >> r) & 1u) {
-                const uint32_t ha = dict_hash_a(key[r], p.seed_a) >> cx.hshift, hb = dict_hash_b(key[r], p.seed_b) >> cx.hshift;
+                const uint32_t x = dict_fold(key[r], p.seed_a);
+                const uint32_t ha = dict_slot_a(x, cx.hshift), hb = dict_slot_b(x, cx.hshift);
                 const uint64_t ka = lds64(cx.a_keys + ha * 8), kb = lds64(cx.a_keys + hb * 8);
                 const bool in_a = ka == key[r], in_b = kb == key[r];
                 const uint32_t g = lds16(cx.a_gid + (in_a ? ha : hb) * 2);

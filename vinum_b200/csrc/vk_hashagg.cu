@@ -673,7 +673,7 @@ struct VkAgg {
     int dict_n = 0;                   // keys in the dictionary
     int dict_log2s = 0;
     uint8_t* dict_dev = nullptr;      // [S] u64 keys | [S] u16 ids
-    uint64_t seed_a = 0, seed_b = 0;
+    uint64_t seed_a = 0;
     std::vector<uint64_t> dict_hk;
     std::vector<uint16_t> dict_hg;
     bool direct_known = false;        // key range of the table measured
@@ -1031,7 +1031,7 @@ int build_dict(VkAgg* a, int64_t n_groups, int log2s, cudaStream_t s) {
     a->dict_hk.assign((size_t) S, LK_EMPTY);
     a->dict_hg.assign((size_t) S, 0);
     bool placed = false;
-    uint64_t sa = 0x9E3779B97F4A7C15ULL, sb = 0xC2B2AE3D27D4EB4FULL;
+    uint64_t sa = 0x9E3779B97F4A7C15ULL;
     for (int attempt = 0; attempt < 32 && !placed; ++attempt) {
         std::fill(a->dict_hk.begin(), a->dict_hk.end(), LK_EMPTY);
         placed = true;
@@ -1039,7 +1039,7 @@ int build_dict(VkAgg* a, int64_t n_groups, int log2s, cudaStream_t s) {
             uint64_t key = keys[(size_t) i];
             uint16_t gid = (uint16_t) i;
             if (key == LK_EMPTY) continue;   // the sentinel cannot live in the dictionary: its rows take the global path
-            uint32_t slot = dict_hash_a(key, sa) >> shift;
+            uint32_t slot = dict_slot_a(dict_fold(key, sa), shift);
             bool done = false;
             for (int kick = 0; kick < 256; ++kick) {
                 if (a->dict_hk[slot] == LK_EMPTY) {
@@ -1050,15 +1050,13 @@ int build_dict(VkAgg* a, int64_t n_groups, int log2s, cudaStream_t s) {
                 }
                 std::swap(key, a->dict_hk[slot]);
                 std::swap(gid, a->dict_hg[slot]);
-                const uint32_t ha = dict_hash_a(key, sa) >> shift, hb = dict_hash_b(key, sb) >> shift;
+                const uint32_t x = dict_fold(key, sa);
+                const uint32_t ha = dict_slot_a(x, shift), hb = dict_slot_b(x, shift);
                 slot = slot == ha ? hb : ha;   // the evicted key moves to its other slot
             }
             placed = done;
         }
-        if (!placed) {
-            sa = splitmix64(sa + attempt);
-            sb = splitmix64(sb ^ sa);
-        }
+        if (!placed) sa = splitmix64(sa + attempt);
     }
     if (!placed) {
         a->dict_failed = true;
@@ -1073,7 +1071,6 @@ int build_dict(VkAgg* a, int64_t n_groups, int log2s, cudaStream_t s) {
     VK_CUDA(cudaMemcpyAsync(a->dict_dev, a->dict_hk.data(), (size_t) S * 8, cudaMemcpyHostToDevice, s));
     VK_CUDA(cudaMemcpyAsync(a->dict_dev + (size_t) S * 8, a->dict_hg.data(), (size_t) S * 2, cudaMemcpyHostToDevice, s));
     a->seed_a = sa;
-    a->seed_b = sb;
     a->dict_n = (int) n_groups;
     a->dict_ready = true;
     VK_DBG("dictionary: %d keys in %lld slots", a->dict_n, (long long) S);
@@ -1455,8 +1452,10 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             }
         }
         if (!direct && a->dict_ready) {
-            // read-only dictionary: the dense ids are exactly 0 .. dict_n - 1
-            warps = w_hi;
+            // read-only dictionary: the dense ids are exactly 0 .. dict_n - 1.  The lookup makes the kernel
+            // instruction / latency bound rather than HBM bound (8 warps: 42 % issue utilisation, 0.5 eligible
+            // warps per cycle, profiles/r02_agg_fast_dict_ncu_full.md): as many warps as the tables leave room for
+            warps = a->fast_warps_fixed ? a->fast_warps : FA_MAX_THREADS / 32;
             const int need = (a->dict_n + 15) & ~15;
             while (warps > w_lo && need > fast_gmax(log2s, false, plan.nw, warps)) warps = next_w(warps);
             gmax = need < 16 ? 16 : need;
@@ -1598,7 +1597,6 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 fp.dict_keys = reinterpret_cast<const uint64_t*>(a->dict_dev);
                 fp.dict_gids = reinterpret_cast<const uint16_t*>(a->dict_dev + ((size_t) 8 << log2s));
                 fp.seed_a = a->seed_a;
-                fp.seed_b = a->seed_b;
             }
             FastLaunch fl;
             fl.pk = pk;
