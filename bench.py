@@ -439,7 +439,9 @@ def run_ours(args) -> dict:
     e2e_rows = args.e2e_rows
     cores = os.cpu_count() or 1
     my_cores = max(1, cores // max(local_world, 1))
-    os.environ.setdefault("VINUM_B200_INGEST_THREADS", str(max(2, min(12, my_cores))))
+    # bounce-copy workers of the pageable ingest: 4 - 8 saturate one PCIe link (profiles/r02_tuning.md); more
+    # only contend for host memory bandwidth, and N ranks share the host's cores
+    os.environ.setdefault("VINUM_B200_INGEST_THREADS", str(max(2, min(8, my_cores // 2))))
 
     # ---- what the answers must be (NumPy over the regenerated rows; before CUDA is touched) ----
     want = want_e2e = None

@@ -32,7 +32,7 @@ static OptEntry g_opts[OPT_COUNT] = {
     {"AGG_LOG2S", 12, {0}, {0}},    {"AGG_PF", -1, {0}, {0}},          {"AGG_WARPS", 0, {0}, {0}},
     {"AGG_DIRECT", 1, {0}, {0}},    {"AGG_DICT", 1, {0}, {0}},         {"AGG_MATCH", 1, {0}, {0}},         {"AGG_NOFAST", 0, {0}, {0}},
     {"AGG_LEARN_LOG2", 20, {0}, {0}}, {"LIST_LOG2", 30, {0}, {0}},     {"DEBUG", 0, {0}, {0}},
-    {"INGEST_STAGED", 1, {0}, {0}}, {"INGEST_THREADS", 0, {0}, {0}}, {"INGEST_PIECE_KB", 1024, {0}, {0}},
+    {"INGEST_STAGED", 1, {0}, {0}}, {"INGEST_THREADS", 0, {0}, {0}}, {"INGEST_PIECE_KB", 2048, {0}, {0}},
 };
 int64_t opt(int id) {
     OptEntry& e = g_opts[id];
