@@ -37,9 +37,8 @@ def run(key, kt, pred_col, thr=0.5, reps=5):
 
 
 out = {}
-for name, opts in (("default", {}), ("match0", {"AGG_MATCH": 0}), ("match2", {"AGG_MATCH": 2}),
-                   ("match2_w8", {"AGG_MATCH": 2, "AGG_WARPS": 8}), ("match2_pf6", {"AGG_MATCH": 2, "AGG_PF": 6}),
-                   ("dict_w8", {"AGG_WARPS": 8}), ("dict_off", {"AGG_DICT": 0})):
+for name, opts in (("entry0_tag_arbitration", {"AGG_ENTRY": 0}), ("entry2_split", {"AGG_ENTRY": 2}),
+                   ("entry2_split_w8", {"AGG_ENTRY": 2, "AGG_WARPS": 8}), ("entry0_w8", {"AGG_ENTRY": 0, "AGG_WARPS": 8})):
     with vb.options(**opts):
         out[name] = {"c3": run(k32, pa.int32(), None), "northstar": run(i0, pa.int64(), f0), "northstar_hash": run(hk, pa.int64(), f0),
                      "northstar_sel09": run(i0, pa.int64(), f0, 0.1)}

@@ -244,9 +244,9 @@ AGG_PATHS = {
     "hash_insert_w8": (dict(AGG_DIRECT=0, AGG_DICT=0, AGG_WARPS=8), 1),
     "hash_w12_small_table": (dict(AGG_DIRECT=0, AGG_WARPS=12, AGG_LOG2S=11), 1),
     "hash_w4": (dict(AGG_DIRECT=0, AGG_WARPS=4, AGG_PF=0), 1),
-    "direct_match_combine": (dict(AGG_MATCH=2), 1),
-    "direct_tag_arbitration": (dict(AGG_MATCH=0), 1),
-    "hash_match_combine": (dict(AGG_DIRECT=0, AGG_MATCH=2), 1),
+    "direct_split_entries": (dict(AGG_ENTRY=2), 1),
+    "direct_tag_arbitration": (dict(AGG_ENTRY=0), 1),
+    "hash_split_entries": (dict(AGG_DIRECT=0, AGG_ENTRY=2), 1),
     "general_kernel": (dict(AGG_NOFAST=1), 2),
 }
 

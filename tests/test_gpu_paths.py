@@ -70,8 +70,8 @@ PATH_OPTS = {
     "hash": {"AGG_DIRECT": 0},                                     # read-only cuckoo dictionary after the learning launch
     "hash_insert": {"AGG_DIRECT": 0, "AGG_DICT": 0},               # insert-as-you-go CTA table
     "hash_small": {"AGG_DIRECT": 0, "AGG_LOG2S": 10, "AGG_WARPS": 12},
-    "match_combine": {"AGG_MATCH": 2},                             # equal ids of a warp combined in registers
-    "tag_arbitration": {"AGG_MATCH": 0},
+    "tag_arbitration": {"AGG_ENTRY": 0},
+    "split_entries": {"AGG_ENTRY": 2},                             # SUM array + {tag | COUNT} array
     "general": {"AGG_NOFAST": 1},
 }
 
@@ -119,7 +119,7 @@ def test_group_by_hostile_key_distributions(vb, stream, kind, path):
         assert paths == [2]
 
 
-@pytest.mark.parametrize("path", ["auto", "hash", "hash_insert", "match_combine", "tag_arbitration", "general"])
+@pytest.mark.parametrize("path", ["auto", "hash", "hash_insert", "tag_arbitration", "split_entries", "general"])
 def test_group_by_without_predicate_and_streamed_chunks(vb, stream, path):
     """C3's shape (no WHERE), fed in five ragged chunks: state carries across vk_agg_update calls
     (BaseAggregate::Next, base_aggregate.cpp:23-45)."""

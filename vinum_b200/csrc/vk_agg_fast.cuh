@@ -80,7 +80,6 @@ struct FastParams {
     uint64_t direct_base;         // direct mode: gid = key - direct_base
     int64_t row_limit;            // row-level global inserts stop here (flush reserve above it)
     int pf_dist;                  // L2 bulk prefetch distance in tiles (0 = off)
-    int gid_bits;                 // MATCHC: bits that distinguish the dense group ids (ceil(log2(gmax)))
     // hash mode with a host-built dictionary (read-only in the kernel): cuckoo placement of the keys the
     // learning launch found, two hash functions, S = 1 << log2s slots; nullptr = insert-as-you-go table
     const uint64_t* dict_keys;    // [S], LK_EMPTY = free
@@ -112,6 +111,17 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
 }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint64_t v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -329,7 +339,7 @@ struct FastCtx {
 // Phase 2 is one short critical section per row: store the lane id as the entry's tag,
 // sync the warp, load the whole entry (tag + COUNT + cell in one LDS.128); the lane that
 // reads its own tag back applies the row and stores the entry, the others go round again.
-template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, bool MATCHC>
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, int VAR>
 __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx, RawTile<PK, NV>& t, uint8_t* smem,
                                           uint32_t* s_ngroups, int64_t row0, int tid, int nthreads, int64_t refill_tile,
                                           uint32_t& spilled) {
@@ -491,57 +501,59 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
     // the key / predicate registers are dead: refill them with the tile after next
     if (refill_tile >= 0) load_tile_keys<PK, NV, MODE>(p, refill_tile, tid, nthreads, t);
 
-    // ---- phase 2 (MATCHC): lanes with equal group ids combine in registers, ONE update per group ----
-    // C3's regime (every row reaches the tables) is bound by the shared-memory pipe: tag store + entry
-    // load + entry store per row, 61 % of the wavefronts bank-conflict replays (profiles/r01_agg_fast_c3).
-    // Here the lanes of a warp that hold the same group id in row r are found with one ballot per id bit
-    // (no shared memory, no MATCH.ANY: 64 issue cycles on the ADU pipe); the lowest of them pulls the
-    // others' values over with shuffles and alone does the LDS.128 / STS.128 of the entry -- no tag, no
-    // retry rounds, and a hot key costs shuffles instead of up to 32 serial rounds of shared-memory traffic.
-    if constexpr (MATCHC) {
-        static_assert(SUMF64 && NW == 2, "the match-combine path is the COUNT + SUM(float64) entry");
-        const uint32_t lane_bit = 1u << cx.lane;
-        uint32_t peers[FA_R];
+    // ---- phase 2 (VAR 2): split entries -- SUM in an 8-byte array, {tag:8 | COUNT:24} in a 4-byte array ----
+    // The 16-byte entry costs 7.3 + 10.4 + 10.4 shared-memory wavefronts per 32 rows (tag STS.32: the tag
+    // words of 16-byte entries fall into only 8 of the 32 banks; LDS.128 / STS.128: four quarter-warp phases
+    // of 8 random bank groups each) -- measured 31.5 with retries, 61 % of them bank-conflict replays, and
+    // the pipe is 86 % busy at C3.  Split: tag byte store 3.5 + LDS.32 3.5 + LDS.64 6.2 + STS.64 6.2 +
+    // STS.32 3.5 = 22.9.  Same arbitration protocol, same memory footprint (the region is carved in two).
+    if constexpr (VAR == 2) {
+        static_assert(SUMF64 && NW == 2, "the split layout is the COUNT + SUM(float64) entry");
+        const uint32_t ct_off = (uint32_t) p.gmax * 8u;   // count/tag array behind the SUM array
 #pragma unroll
-        for (int r = 0; r < FA_R; ++r) {
-            const bool on = (todo >> r) & 1u;
-            const uint32_t g = (ea[r] - cx.a_ent) >> 4;
-            uint32_t m = __ballot_sync(0xffffffffu, on);
+        for (int q = 0; q < FA_R / FA_K; ++q) {
+            uint32_t pend = (todo >> (q * FA_K)) & ((1u << FA_K) - 1u);
+            uint32_t a_sum[FA_K], a_ct[FA_K];
 #pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                if (b < p.gid_bits) {
-                    const bool bit = (g >> b) & 1u;
-                    const uint32_t vote = __ballot_sync(0xffffffffu, on && bit);
-                    m &= bit ? vote : ~vote;
+            for (int k = 0; k < FA_K; ++k) {
+                const uint32_t g = (ea[q * FA_K + k] - cx.a_ent) >> 4;
+                a_sum[k] = cx.a_ent + g * 8u;
+                a_ct[k] = cx.a_ent + ct_off + g * 4u;
+            }
+            while (__any_sync(0xffffffffu, pend != 0)) {
+#pragma unroll
+                for (int k = 0; k < FA_K; ++k)
+                    if ((pend >> k) & 1u) sts8(a_ct[k] + 3, cx.lane | ((uint32_t) k << 5));
+                __syncwarp();
+                uint32_t ct[FA_K];
+                uint64_t sm[FA_K];
+#pragma unroll
+                for (int k = 0; k < FA_K; ++k) {
+                    ct[k] = 0xFFFFFFFFu;
+                    sm[k] = 0;
+                    if ((pend >> k) & 1u) {
+                        ct[k] = lds32(a_ct[k]);
+                        sm[k] = lds64(a_sum[k]);
+                    }
                 }
-            }
-            peers[r] = on ? m : 0u;
-        }
 #pragma unroll
-        for (int r = 0; r < FA_R; ++r) {
-            const bool leader = peers[r] != 0u && (peers[r] & (lane_bit - 1u)) == 0u;
-            double acc = __longlong_as_double((long long) row_val<MODE>(p, 0, t.vq[0], r));
-            const double mine = acc;
-            uint32_t rem = leader ? (peers[r] & ~lane_bit) : 0u;
-            while (__any_sync(0xffffffffu, rem != 0u)) {   // one trip per extra lane of the fullest group
-                const int src = rem ? __ffs(rem) - 1 : (int) cx.lane;
-                const double x = __shfl_sync(0xffffffffu, mine, src);
-                if (rem) {
-                    acc += x;
-                    rem &= rem - 1u;
+                for (int k = 0; k < FA_K; ++k) {
+                    const uint32_t mine = cx.lane | ((uint32_t) k << 5);
+                    if ((ct[k] >> 24) == mine) {   // 0xFF for rows that are not pending: never a tag
+                        const int r = q * FA_K + k;
+                        pend &= ~(1u << k);
+                        const double sum = __longlong_as_double((long long) sm[k]) +
+                                           __longlong_as_double((long long) row_val<MODE>(p, 0, t.vq[0], r));
+                        sts64(a_sum[k], (uint64_t) __double_as_longlong(sum));
+                        sts32(a_ct[k], ((ct[k] + 1u) & 0x00FFFFFFu) | (mine << 24));
+                    }
                 }
+                __syncwarp();
             }
-            if (leader) {
-                uint32_t e[4];
-                lds128(ea[r], e);
-                e[0] += (uint32_t) __popc(peers[r]);
-                const double sum = __hiloint2double((int) e[3], (int) e[2]) + acc;
-                e[2] = (uint32_t) __double2loint(sum);
-                e[3] = (uint32_t) __double2hiint(sum);
-                sts128(ea[r], e);
+            if (refill_tile >= 0) {
+#pragma unroll
+                for (int j = q * FA_K / 2; j < (q + 1) * FA_K / 2; ++j) load_tile_vals<PK, NV, MODE>(p, refill_tile, tid, nthreads, t, j);
             }
-            __syncwarp();   // the next row's leader may be another lane updating the same entry
-            if ((r & 1) && refill_tile >= 0) load_tile_vals<PK, NV, MODE>(p, refill_tile, tid, nthreads, t, r >> 1);
         }
         return;
     }
@@ -623,7 +635,7 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
     }
 }
 
-template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, bool MATCHC = false>
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, int VAR = 0>
 __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_ngroups;
@@ -683,7 +695,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
     };
     auto process = [&](int64_t tl, RawTile<PK, NV>& t) {
         const int64_t nx = tl + 2 * stride;
-        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64, MATCHC>(p, cx, t, smem, &s_ngroups, tl * tile_rows + tid * 2, tid, nthreads,
+        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64, VAR>(p, cx, t, smem, &s_ngroups, tl * tile_rows + tid * 2, tid, nthreads,
                                                     nx < p.num_tiles ? nx : (int64_t) -1, spilled);
     };
     if (tile < p.num_tiles) load_all(tile, ta);
@@ -741,6 +753,12 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
         uint64_t acc[FA_MAX_CELLS] = {0, 0, 0};
         double facc[FA_MAX_CELLS] = {0.0, 0.0, 0.0};
         for (int w = 0; w < nwarps; ++w) {
+            if constexpr (VAR == 2) {   // split entries: SUM array, then {tag | COUNT} array
+                const uint32_t wb = a_warp0 + (uint32_t) w * warp_bytes;
+                cnt += lds32(wb + (uint32_t) G * 8u + g16 * 4u) & 0x00FFFFFFu;
+                facc[0] += __longlong_as_double((long long) lds64(wb + g16 * 8u));
+                continue;
+            }
             const uint32_t ea = a_warp0 + (uint32_t) w * warp_bytes + g16 * (NW * 8);
             uint32_t e[4], f[4] = {0, 0, 0, 0};
             lds128(ea, e);
@@ -800,7 +818,7 @@ struct FastLaunch {
     int mode;      // FastMode
     bool direct;
     bool sumf64;
-    bool matchc;   // SUMF64 only: combine equal group ids of a warp in registers (C3's regime)
+    int variant;   // SUMF64 only: 0 = 16-byte entries, 2 = split (SoA) entries; both with tag arbitration
     int grid, threads;
     size_t smem;
 };
@@ -821,7 +839,7 @@ int launch_fast_lean(const FastParams& p, const FastLaunch& l, cudaStream_t s) {
     switch (p.n_cols) {
         case 0: VK_FAST_GO(PK, 0, 2, MODE, DIRECT, false);
         case 1:
-            if (l.nw == 2 && l.sumf64 && l.matchc) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true, true);
+            if (l.nw == 2 && l.sumf64 && l.variant == 2) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true, 2);
             if (l.nw == 2 && l.sumf64) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true);
             if (l.nw == 2) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, false);
             VK_FAST_GO(PK, 1, 4, MODE, DIRECT, false);

@@ -669,7 +669,7 @@ struct VkAgg {
     // launch, vk_agg_fast.cuh); rows with other keys go to the global table
     bool dict_ready = false, dict_failed = false;
     int dict_policy = 1;
-    int match_policy = 1;
+    int match_policy = 0;             // option AGG_ENTRY: layout / update protocol of the COUNT + SUM(f64) entry
     int dict_n = 0;                   // keys in the dictionary
     int dict_log2s = 0;
     uint8_t* dict_dev = nullptr;      // [S] u64 keys | [S] u16 ids
@@ -1232,7 +1232,8 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
     if (a->fast_warps > FA_MAX_THREADS / 32) a->fast_warps = FA_MAX_THREADS / 32;
     a->fast_direct_policy = (int) opt(OPT_AGG_DIRECT);
     a->dict_policy = (int) opt(OPT_AGG_DICT);
-    a->match_policy = (int) opt(OPT_AGG_MATCH);
+    a->match_policy = (int) opt(OPT_AGG_ENTRY);
+    if (a->match_policy != 2) a->match_policy = 0;
     if (opt(OPT_AGG_NOFAST)) a->fast_disabled = true;
     a->learn_rows = (int64_t) 1 << (opt(OPT_AGG_LEARN_LOG2) < 10 ? 10 : (opt(OPT_AGG_LEARN_LOG2) > 30 ? 30 : opt(OPT_AGG_LEARN_LOG2)));
     const int rc = ctr_acquire(a);
@@ -1606,10 +1607,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             fl.sumf64 = plan.sumf64;
             // match-combine (one entry update per distinct group id per warp-row): policy 1 = where the
             // shared-memory pipe binds (nearly every row reaches the tables), 2 = always, 0 = never
-            fl.matchc = lean && plan.sumf64 && plan.nw == 2 &&
-                        (a->match_policy == 2 || (a->match_policy == 1 && !(pk != PK_NONE && a->fast_rows_seen > 0 && a->fast_selectivity <= 0.7)));
-            fp.gid_bits = 1;
-            while ((1 << fp.gid_bits) < gmax && fp.gid_bits < 16) ++fp.gid_bits;
+            fl.variant = (lean && plan.sumf64 && plan.nw == 2) ? a->match_policy : 0;   // option AGG_ENTRY
             fl.grid = fp.num_tiles < fast_grid_max ? (int) fp.num_tiles : fast_grid_max;
             fl.threads = threads;
             fl.smem = smem;
