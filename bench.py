@@ -441,7 +441,7 @@ def run_ours(args) -> dict:
     my_cores = max(1, cores // max(local_world, 1))
     # bounce-copy workers of the pageable ingest: 4 - 8 saturate one PCIe link (profiles/r02_tuning.md); more
     # only contend for host memory bandwidth, and N ranks share the host's cores
-    os.environ.setdefault("VINUM_B200_INGEST_THREADS", str(max(2, min(8, my_cores // 2))))
+    os.environ.setdefault("VINUM_B200_INGEST_THREADS", str(max(2, min(8, my_cores))))
 
     # ---- what the answers must be (NumPy over the regenerated rows; before CUDA is touched) ----
     want = want_e2e = None
