@@ -518,11 +518,11 @@ def run_ours(args) -> dict:
     e0, e1 = C.c_void_p(), C.c_void_p()
     lib.vk_event_create(C.byref(e0))
     lib.vk_event_create(C.byref(e1))
-    for _ in range(args.warmup):
-        step(False)
     # Python's cyclic collector walks every tracked object of the process (hundreds of thousands once
     # torch is imported: a 50-100 ms pause that lands in a random step).  Nothing in a step creates
-    # cycles; collect now and keep the collector out of the timed regions.
+    # cycles; collect now and keep the collector out of the timed regions.  This and the NVML start-up
+    # come BEFORE the warm-up steps: an idle gap of tens of milliseconds right before the timed region
+    # lets the SM clock drop, and the first timed step then ran 0.2-0.3 ms slow.
     import gc
     gc.collect()
     gc.freeze()
@@ -530,6 +530,8 @@ def run_ours(args) -> dict:
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.prepare()
+    for _ in range(args.warmup):
+        step(False)
     barrier()
     if rank == 0:
         sampler.start()

@@ -40,6 +40,7 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 enum Opt {
     OPT_FILTER_STAGE = 0,   // 1: an output column that is the predicate column is scattered from shared memory
     OPT_FILTER_PF,          // 1: bulk-prefetch a tile's payload columns into L2 before the look-back
+    OPT_FILTER_CS,          // 1: streaming (evict-first) stores for the compacted output
     OPT_FILTER_ITERS,       // row pairs per thread of filter_kernel: 4 (2048-row tiles) or 8
     OPT_CMP_FAST,           // compare8_kernel row pairs per thread (0: compare_kernel)
     OPT_ARITH_FAST,         // arith8_kernel row pairs per thread (0: arith_kernel)

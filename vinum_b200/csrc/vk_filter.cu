@@ -198,8 +198,13 @@ struct FilterParams {
     unsigned long long* ticket;  // scratch[0]
     unsigned long long* status;  // scratch[1..]
     int64_t num_tiles;
-    int pf;  // bulk-prefetch the tile's payload columns into L2 while the predicate / look-back run
+    int pf;  // bulk-prefetch the tile's payload columns into L2 while the predicate / look-back run (1: at tile start, 2: after phase 1)
+    int cs;  // streaming (evict-first) stores for the output columns
 };
+
+__device__ __forceinline__ void stg_cs64(uint64_t* p, uint64_t v) {
+    asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 __device__ __forceinline__ void l2_prefetch_span(const uint8_t* begin, const uint8_t* end) {
     const uint64_t a = reinterpret_cast<uint64_t>(begin) & ~(uint64_t) 15;
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(
 
     // The payload columns are only read after the look-back; start moving this tile's slice of
     // each of them into L2 now (one bulk prefetch per column, no registers, no shared memory).
-    if (p.pf && tid < p.n_cols) {
+    if (p.pf == 1 && tid < p.n_cols) {
         const Col col = p.cols[tid];
         const int es = dtype_size(col.dtype);
         const int64_t rows = p.n - base < TILE ? p.n - base : TILE;
@@ -287,6 +292,15 @@ __global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(
         lane_off[it] = __popc(b0 & lt) + __popc(b1 & lt);
         flags |= ((uint32_t) f0 << (2 * it)) | ((uint32_t) f1 << (2 * it + 1));
         if (lane == 0) s_cnt[it * (FT_THREADS / 32) + warp] = __popc(b0) + __popc(b1);
+    }
+    // (FILTER_PF=2) the same prefetch issued only now, after the predicate loads: the slices sit in L2 for a
+    // shorter time -- 1184 resident tiles x 64 KB of prefetched payload is most of the L2
+    if (p.pf == 2 && tid < p.n_cols) {
+        const Col col = p.cols[tid];
+        const int es = dtype_size(col.dtype);
+        const int64_t rows = p.n - base < TILE ? p.n - base : TILE;
+        if (!(p.pred.kind == VK_PRED_CMP && col.data == p.pred.col.data))
+            l2_prefetch_span(col.data + base * es, col.data + (base + rows) * es);
     }
     __syncthreads();
 
@@ -371,8 +385,13 @@ __global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(
                     v1 = (f & 2) ? reinterpret_cast<const uint64_t*>(col.data)[r0 + 1] : 0;
                 }
                 uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
-                if (f & 1) o[pos++] = v0;
-                if (f & 2) o[pos] = v1;
+                if (p.cs) {   // write-once output: streaming stores leave the L2 to the prefetched input slices
+                    if (f & 1) stg_cs64(o + pos++, v0);
+                    if (f & 2) stg_cs64(o + pos, v1);
+                } else {
+                    if (f & 1) o[pos++] = v0;
+                    if (f & 2) o[pos] = v1;
+                }
             } else {
                 int64_t q = pos;
                 if (f & 1) store_from_u64(p.out_data[c], col.dtype, q++, load_as_u64(col, r0));
@@ -606,6 +625,7 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         p.status = p.ticket + 1;
         p.num_tiles = tiles;
         p.pf = (int) opt(OPT_FILTER_PF);
+        p.cs = (int) opt(OPT_FILTER_CS);
         const bool stage = pred_is_output && opt(OPT_FILTER_STAGE) != 0 && iters == 4;
         VK_CUDA(cudaMemsetAsync(scratch, 0, vk_filter_scratch_bytes(n_rows), s));
 #define VK_FILTER_GO(PK, STAGEABLE)                                                                   \
