@@ -203,7 +203,7 @@ struct PassParams {
     const uint64_t* src;                // LAST pass + out_sorted: the 8-byte key column (for the codes that do not invert)
     int src_kind;                       // 0 uint64, 1 int64, 2 float64
     int desc;
-    int rank_serial;                    // option SORT_RANK=0: serial counter update per item (round 1's form)
+    int rank_serial;                    // option SORT_RANK: 1 = serial counter update per item (SORT_RANK=0), 2 = the same with MATCH.ANY for every other item (SORT_RANK=2), 0 = pipelined counter atomics (SORT_RANK=1)
 };
 
 __device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int shift) {
@@ -283,8 +283,15 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
             const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
             const bool in = li < tile_n;
             const uint32_t d = pass_digit(key[k], idx[k], p.shift);
-            unsigned peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
-            if (!in) peers = 1u << lane;
+            unsigned peers;
+            // (SORT_RANK=2) every other item finds its peers with MATCH.ANY: one ADU instruction instead of
+            // ~32 ALU / vote instructions; all items on the ADU pipe bound the kernel in round 1, half do not
+            if (p.rank_serial == 2 && (k & 1)) {
+                peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
+            } else {
+                peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
+                if (!in) peers = 1u << lane;
+            }
             const int leader = __ffs(peers) - 1;
             uint32_t c = 0;
             if (in && lane == leader) {
@@ -655,7 +662,7 @@ static int sort_indices_impl(const VkColumn* keys, const int32_t* orders, int n_
             ps.bucket_start = sc.hist + d * 256;
             ps.ticket = sc.ticket;
             ps.status = sc.status;
-            ps.rank_serial = opt(OPT_SORT_RANK) == 0;
+            ps.rank_serial = opt(OPT_SORT_RANK) == 1 ? 0 : (opt(OPT_SORT_RANK) == 2 ? 2 : 1);
             VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
             VK_CUDA(cudaMemsetAsync(sc.status, 0, status_used, s));
             if (is_final) {
