@@ -163,7 +163,7 @@ def _c2_table(n, seed=0):
                      "f1": rng.normal(0, 1000, n), "s": rng.integers(-100, 100, n).astype(np.int16)})
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(FILTER_STAGE=0), dict(FILTER_PF=0), dict(FILTER_PF=1), dict(FILTER_PF=3), dict(FILTER_CS=1),
+@pytest.mark.parametrize("opts", [dict(), dict(FILTER_STAGE=0), dict(FILTER_PF=0), dict(FILTER_PF=1), dict(FILTER_CS=1),
                                   dict(FILTER_ITERS=8), dict(FILTER_ITERS=8, FILTER_PF=0)], ids=str)
 @pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 300_001])
 def test_filter_every_option_vs_numpy_indexing(vb, stream, opts, n):
@@ -187,8 +187,7 @@ def test_filter_every_option_vs_numpy_indexing(vb, stream, opts, n):
         assert np.array_equal(out.column(name).to_numpy(stream), table.column(name).to_numpy()[m]), name
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(SORT_FUSE_LAST=0), dict(SORT_PREP=0), dict(SORT_PREP=2), dict(SORT_RANK=0), dict(SORT_RANK=1),
-                                  dict(SORT_RANK=2)], ids=str)
+@pytest.mark.parametrize("opts", [dict(), dict(SORT_FUSE_LAST=0), dict(SORT_PREP=0), dict(SORT_PREP=2)], ids=str)
 def test_sort_every_option_vs_reference(vb, stream, opts):
     """Sort::Sorted (sort.cpp:15-63): identical permutation, ties / NaN / NULL / both zeros included,
     multi-key with integer NULLs, for every selectable prepare / last-pass kernel."""

@@ -413,12 +413,12 @@ def test_sample_sort_plan_over_gloo_world2(tmp_path):
 
 def test_every_option_has_a_default_and_a_name():
     import vinum_b200 as vb
-    names = ("FILTER_STAGE FILTER_PF FILTER_CS FILTER_ITERS CMP_FAST ARITH_FAST ONEGROUP_FAST SORT_FUSE_LAST SORT_PREP SORT_RANK "
+    names = ("FILTER_STAGE FILTER_PF FILTER_CS FILTER_ITERS CMP_FAST ARITH_FAST ONEGROUP_FAST SORT_FUSE_LAST SORT_PREP "
              "AGG_LOG2S AGG_PF AGG_WARPS AGG_DIRECT AGG_DICT AGG_ENTRY AGG_NOFAST AGG_LEARN_LOG2 LIST_LOG2 DEBUG INGEST_STAGED "
              "INGEST_THREADS INGEST_PIECE_KB").split()
     for n in names:
         assert isinstance(vb.get_option(n), int)
-    assert vb.get_option("VINUM_B200_SORT_RANK") == vb.get_option("SORT_RANK")   # the environment spelling resolves too
-    with vb.options(AGG_DICT=0, SORT_RANK=0):
-        assert vb.get_option("AGG_DICT") == 0 and vb.get_option("SORT_RANK") == 0
-    assert vb.get_option("AGG_DICT") == 1 and vb.get_option("SORT_RANK") == 1
+    assert vb.get_option("VINUM_B200_SORT_PREP") == vb.get_option("SORT_PREP")   # the environment spelling resolves too
+    with vb.options(AGG_DICT=0, SORT_PREP=0):
+        assert vb.get_option("AGG_DICT") == 0 and vb.get_option("SORT_PREP") == 0
+    assert vb.get_option("AGG_DICT") == 1 and vb.get_option("SORT_PREP") == 4

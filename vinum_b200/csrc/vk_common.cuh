@@ -39,7 +39,7 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 // with vk_set_option(), so that one process can exercise every path (tests/test_gpu_paths.py).
 enum Opt {
     OPT_FILTER_STAGE = 0,   // 1: an output column that is the predicate column is scattered from shared memory
-    OPT_FILTER_PF,          // bulk-prefetch of a tile's payload slices into L2: 0 off, 1 at tile start, 2 after the predicate loads, 3 one column ahead of the scatter
+    OPT_FILTER_PF,          // bulk-prefetch of a tile's payload slices into L2: 0 off, 1 at tile start, 2 after the predicate loads
     OPT_FILTER_CS,          // 1: streaming (evict-first) stores for the compacted output
     OPT_FILTER_ITERS,       // row pairs per thread of filter_kernel: 4 (2048-row tiles) or 8
     OPT_CMP_FAST,           // compare8_kernel row pairs per thread (0: compare_kernel)
@@ -47,7 +47,6 @@ enum Opt {
     OPT_ONEGROUP_FAST,      // agg_onegroup8_kernel row pairs per thread (0: agg_onegroup_kernel)
     OPT_SORT_FUSE_LAST,     // 1: the last radix pass writes the int64 permutation itself
     OPT_SORT_PREP,          // sort_prepare8_kernel loads per thread (0: sort_prepare_kernel)
-    OPT_SORT_RANK,          // radix ranking: 0 = serial counter update per item, 1 = pipelined counter atomics, 2 = serial with MATCH.ANY for every other item
     OPT_AGG_LOG2S,          // agg_fast_kernel: log2 of the CTA key table slots (hash mode)
     OPT_AGG_PF,             // agg_fast_kernel: L2 prefetch distance in tiles (-1: automatic)
     OPT_AGG_WARPS,          // agg_fast_kernel: warps per CTA (0: automatic)

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(
     }
     // (FILTER_PF=2) the same prefetch issued only now, after the predicate loads: the slices sit in L2 for a
     // shorter time -- 1184 resident tiles x 64 KB of prefetched payload is most of the L2
-    if ((p.pf == 2 && tid < p.n_cols) || (p.pf == 3 && tid < 1 && tid < p.n_cols)) {   // (3: first column only, the rest below)
+    if (p.pf == 2 && tid < p.n_cols) {
         const Col col = p.cols[tid];
         const int es = dtype_size(col.dtype);
         const int64_t rows = p.n - base < TILE ? p.n - base : TILE;
@@ -362,13 +362,6 @@ __global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(
         const Col col = p.cols[c];
         const int es = dtype_size(col.dtype);
         uint8_t* outv = p.out_valid[c];
-        if (p.pf == 3 && tid == 0 && c + 1 < p.n_cols) {   // one column ahead of the scatter
-            const Col nx = p.cols[c + 1];
-            const int nes = dtype_size(nx.dtype);
-            const int64_t rows = p.n - base < TILE ? p.n - base : TILE;
-            if (!(p.pred.kind == VK_PRED_CMP && nx.data == p.pred.col.data))
-                l2_prefetch_span(nx.data + base * nes, nx.data + (base + rows) * nes);
-        }
         const bool vec16 = (es == 8) && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0);
         const bool staged = STAGE && es == 8 && col.data == p.pred.col.data;
 #pragma unroll

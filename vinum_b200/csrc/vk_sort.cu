@@ -19,10 +19,10 @@ namespace vk {
 constexpr int RS_THREADS = 256;
 constexpr int RS_MIN_TILE = RS_THREADS * 8;     // smallest tile any geometry uses (sizes the status array)
 constexpr int RS_WARPS = RS_THREADS / 32;
-#ifndef VK_RS_RANK_BATCH
-#define VK_RS_RANK_BATCH 4
+#ifndef VK_RS_LB
+#define VK_RS_LB 4
 #endif
-constexpr int RS_RANK_BATCH = VK_RS_RANK_BATCH;   // items whose votes / counter atomics are in flight together
+constexpr int RS_LB = VK_RS_LB;   // predecessor status words a look-back step reads at once
 constexpr uint32_t RS_NULLBIT = 0x80000000u;
 
 constexpr uint64_t KEY_NAN = 0xFFFFFFFFFFFFFFFEULL;
@@ -203,7 +203,6 @@ struct PassParams {
     const uint64_t* src;                // LAST pass + out_sorted: the 8-byte key column (for the codes that do not invert)
     int src_kind;                       // 0 uint64, 1 int64, 2 float64
     int desc;
-    int rank_serial;                    // option SORT_RANK: 1 = serial counter update per item (SORT_RANK=0), 2 = the same with MATCH.ANY for every other item (SORT_RANK=2), 0 = pipelined counter atomics (SORT_RANK=1)
 };
 
 __device__ __forceinline__ uint32_t pass_digit(uint64_t key, uint32_t idx, int shift) {
@@ -269,69 +268,30 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
         }
     }
     // ---- stable rank inside the warp's 512 items ----
-    // Lanes with equal digits are found with ballots; the first of them (the leader) bumps the warp's
-    // digit counter by their number with ONE shared atomic and gets the digit's count so far back.
-    // Nothing waits for that value inside the loop -- the __syncwarp only orders the counter updates of
-    // successive items -- so the votes and atomics of RS_RANK_BATCH items are in flight together; round 1 read
-    // and wrote the counter with LDS / STS per item, a serial chain of 16 shared-memory round trips per
-    // tile (short scoreboard 41 % of all stall samples, profiles/r01_sort_pass_ncu_full.md).
-    constexpr int HALF = RS_RANK_BATCH;
-    if (p.rank_serial) {
-        // round 1's form (option SORT_RANK=0): the leader reads and writes the counter item by item
+    // (Round 2 measured three other forms of this loop on one box -- digit-counter atomics pipelined four
+    // items deep, MATCH.ANY for every other item, both -- all within 1 % of this one: the pass is not bound
+    // by the ranking, profiles/r02_tuning.md.)
 #pragma unroll
-        for (int k = 0; k < RS_ITEMS; ++k) {
-            const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
-            const bool in = li < tile_n;
-            const uint32_t d = pass_digit(key[k], idx[k], p.shift);
-            unsigned peers;
-            // (SORT_RANK=2) every other item finds its peers with MATCH.ANY: one ADU instruction instead of
-            // ~32 ALU / vote instructions; all items on the ADU pipe bound the kernel in round 1, half do not
-            if (p.rank_serial == 2 && (k & 1)) {
-                peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
-            } else {
-                peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
-                if (!in) peers = 1u << lane;
-            }
-            const int leader = __ffs(peers) - 1;
-            uint32_t c = 0;
-            if (in && lane == leader) {
-                c = s_wcnt[warp][d];
-                s_wcnt[warp][d] = c + __popc(peers);
-            }
-            c = __shfl_sync(0xffffffffu, c, leader);
-            rank[k] = c + __popc(peers & lt);
-            __syncwarp();
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
+        const bool in = li < tile_n;
+        const uint32_t d = pass_digit(key[k], idx[k], p.shift);
+        unsigned peers;
+        if constexpr (BALLOT) {
+            peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
+            if (!in) peers = 1u << lane;
+        } else {
+            peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
         }
-    } else {
-#pragma unroll
-    for (int h = 0; h < RS_ITEMS / HALF; ++h) {
-        uint32_t cnt[HALF];
-#pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-            const int k = h * HALF + j;
-            const int li = warp * (32 * RS_ITEMS) + k * 32 + lane;
-            const bool in = li < tile_n;
-            const uint32_t d = pass_digit(key[k], idx[k], p.shift);
-            unsigned peers;
-            if constexpr (BALLOT) {
-                peers = digit_peers_ballot(d, in, p.shift == 64 ? 1 : 8);
-                if (!in) peers = 1u << lane;
-            } else {
-                peers = __match_any_sync(0xffffffffu, in ? d : (0x100u | lane));
-            }
-            const int leader = __ffs(peers) - 1;
-            cnt[j] = 0;
-            if (in && lane == leader) cnt[j] = atomicAdd(&s_wcnt[warp][d], (uint32_t) __popc(peers));
-            rank[k] = (uint32_t) __popc(peers & lt) | ((uint32_t) leader << 16);
-            __syncwarp();
+        const int leader = __ffs(peers) - 1;
+        uint32_t c = 0;
+        if (in && lane == leader) {
+            c = s_wcnt[warp][d];
+            s_wcnt[warp][d] = c + __popc(peers);
         }
-#pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-            const int k = h * HALF + j;
-            const uint32_t c = __shfl_sync(0xffffffffu, cnt[j], (int) (rank[k] >> 16));
-            rank[k] = c + (rank[k] & 0xffffu);
-        }
-    }
+        c = __shfl_sync(0xffffffffu, c, leader);
+        rank[k] = c + __popc(peers & lt);
+        __syncwarp();
     }
     __syncthreads();
 
@@ -352,16 +312,30 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(st), "l"(RS_PREFIX | total) : "memory");
         } else {
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(st), "l"(RS_AGG | total) : "memory");
+            // The predecessors' status words are read RS_LB at a time: walking back one tile per dependent L2
+            // round trip cost ~24 serial loads per bucket (19 % of all stall samples sat on this loop,
+            // profiles/r02_sort_pass_ncu_full.md) because ~20 tiles are between "aggregate published" and
+            // "prefix published" at any moment; independent loads overlap those round trips.
             int64_t look = tile - 1;
-            while (true) {
-                unsigned long long v;
-                const unsigned long long* q = p.status + look * 256 + b;
-                do {
-                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
-                } while ((v >> RS_FLAG_SHIFT) == 0);
-                excl += v & RS_VALUE_MASK;
-                if ((v >> RS_FLAG_SHIFT) == 2) break;
-                --look;
+            bool done = false;
+            while (!done) {
+                unsigned long long v[RS_LB];
+#pragma unroll
+                for (int j = 0; j < RS_LB; ++j) {
+                    const int64_t t = look - j;
+                    v[j] = RS_PREFIX;   // before tile 0: prefix 0
+                    if (t >= 0) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[j]) : "l"(p.status + t * 256 + b) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < RS_LB; ++j) {
+                    if (!done) {
+                        while ((v[j] >> RS_FLAG_SHIFT) == 0)   // not published yet: poll this one
+                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[j]) : "l"(p.status + (look - j) * 256 + b) : "memory");
+                        excl += v[j] & RS_VALUE_MASK;
+                        done = (v[j] >> RS_FLAG_SHIFT) == 2;
+                    }
+                }
+                look -= RS_LB;
             }
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(st), "l"(RS_PREFIX | (excl + total)) : "memory");
         }
@@ -662,7 +636,6 @@ static int sort_indices_impl(const VkColumn* keys, const int32_t* orders, int n_
             ps.bucket_start = sc.hist + d * 256;
             ps.ticket = sc.ticket;
             ps.status = sc.status;
-            ps.rank_serial = opt(OPT_SORT_RANK) == 1 ? 0 : (opt(OPT_SORT_RANK) == 2 ? 2 : 1);
             VK_CUDA(cudaMemsetAsync(sc.ticket, 0, 8, s));
             VK_CUDA(cudaMemsetAsync(sc.status, 0, status_used, s));
             if (is_final) {
