@@ -20,7 +20,7 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_MIN_TILE = RS_THREADS * 8;     // smallest tile any geometry uses (sizes the status array)
 constexpr int RS_WARPS = RS_THREADS / 32;
 #ifndef VK_RS_LB
-#define VK_RS_LB 4
+#define VK_RS_LB 2
 #endif
 constexpr int RS_LB = VK_RS_LB;   // predecessor status words a look-back step reads at once
 constexpr uint32_t RS_NULLBIT = 0x80000000u;
@@ -147,12 +147,20 @@ __global__ void __launch_bounds__(256) sort_prepare8_kernel(const __grid_constan
             const unsigned active = __ballot_sync(0xffffffffu, in);
             if (!active) continue;
             const int leader = __ffs(active) - 1;
+            // Which digits are the same in every active lane of the warp?  One OR-reduction of the differences
+            // to the leader's code answers that for all 8 digits (two REDUX.OR); the per-digit
+            // shuffle + vote of round 1 made this kernel instruction-bound (234 instructions per key).
+            const uint64_t first = __shfl_sync(0xffffffffu, c, leader);
+            const uint64_t diff = in ? (c ^ first) : 0ULL;
+            const uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t) diff);
+            const uint32_t dhi = __reduce_or_sync(0xffffffffu, (uint32_t) (diff >> 32));
 #pragma unroll
             for (int d = 0; d < 8; ++d) {
                 const uint32_t digit = (uint32_t) (c >> (8 * d)) & 0xffu;
-                const uint32_t first = __shfl_sync(0xffffffffu, digit, leader);
-                if (__all_sync(0xffffffffu, !in || digit == first)) {
-                    if ((threadIdx.x & 31) == leader) atomicAdd(&s_hist[d * 256 + first], (uint32_t) __popc(active));
+                const uint32_t varies = ((d < 4 ? dlo : dhi) >> (8 * (d & 3))) & 0xffu;
+                if (varies == 0) {
+                    // constant digits are the common case (small integers): one add per warp
+                    if ((threadIdx.x & 31) == leader) atomicAdd(&s_hist[d * 256 + digit], (uint32_t) __popc(active));
                 } else if (in) {
                     atomicAdd(&s_hist[d * 256 + digit], 1u);
                 }
@@ -312,7 +320,8 @@ __global__ void __launch_bounds__(RS_THREADS, MINB) sort_pass_kernel(const __gri
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(st), "l"(RS_PREFIX | total) : "memory");
         } else {
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(st), "l"(RS_AGG | total) : "memory");
-            // The predecessors' status words are read RS_LB at a time: walking back one tile per dependent L2
+            // The predecessors' status words are read RS_LB (2: measured 7.73 ms at C4 against 7.89 with 4, 8.40 with 8
+            // and 8.1 one at a time) at a time: walking back one tile per dependent L2
             // round trip cost ~24 serial loads per bucket (19 % of all stall samples sat on this loop,
             // profiles/r02_sort_pass_ncu_full.md) because ~20 tiles are between "aggregate published" and
             // "prefix published" at any moment; independent loads overlap those round trips.
