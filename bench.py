@@ -60,7 +60,7 @@ FUNCS = [("COUNT_STAR", "", "count_star"), ("SUM", "f1", "sum_f1")]
 
 def _traffic_per_row():
     """DRAM bytes per row of the dominant kernel from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(p) as f:
             return float(json.load(f)["dram_bytes_per_row"])
@@ -675,7 +675,7 @@ def run_ours(args) -> dict:
                               "frac": achieved / peak,
                               "traffic": None if tpr is None else tpr * (kernel_rows / kernel_launches),
                               "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per row of one "
-                                                "captured launch (profiles/r01_traffic.json) x rows per launch",
+                                                "captured launch (profiles/r02_traffic.json) x rows per launch",
                               "algorithmic_bytes_per_launch": per_launch_bytes, "peak_source": peak_src,
                               "kernel": "agg_fast_kernel (rank 0's launches)" if distributed else "agg_fast_kernel",
                               "launches": kernel_launches, "avg_launch_ms": per_launch_ms,
