@@ -163,8 +163,7 @@ def _c2_table(n, seed=0):
                      "f1": rng.normal(0, 1000, n), "s": rng.integers(-100, 100, n).astype(np.int16)})
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(FILTER_STAGE=0), dict(FILTER_PF=0), dict(FILTER_PF=1), dict(FILTER_PIPE=1), dict(FILTER_PIPE=1, FILTER_STAGE=0), dict(FILTER_CS=1),
-                                  dict(FILTER_ITERS=8), dict(FILTER_ITERS=8, FILTER_PF=0)], ids=str)
+@pytest.mark.parametrize("opts", [dict(), dict(FILTER_STAGE=0), dict(FILTER_PF=0), dict(FILTER_PF=1), dict(FILTER_STAGE=0, FILTER_PF=0)], ids=str)
 @pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 300_001])
 def test_filter_every_option_vs_numpy_indexing(vb, stream, opts, n):
     """RecordBatch.filter (record_batch.py:85-90): every column compacted, input order kept -- the

@@ -40,9 +40,6 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 enum Opt {
     OPT_FILTER_STAGE = 0,   // 1: an output column that is the predicate column is scattered from shared memory
     OPT_FILTER_PF,          // bulk-prefetch of a tile's payload slices into L2: 0 off, 1 at tile start, 2 after the predicate loads
-    OPT_FILTER_CS,          // 1: streaming (evict-first) stores for the compacted output
-    OPT_FILTER_PIPE,        // 1: persistent, software-pipelined compaction kernel (filter_pipe_kernel)
-    OPT_FILTER_ITERS,       // row pairs per thread of filter_kernel: 4 (2048-row tiles) or 8
     OPT_CMP_FAST,           // compare8_kernel row pairs per thread (0: compare_kernel)
     OPT_ARITH_FAST,         // arith8_kernel row pairs per thread (0: arith_kernel)
     OPT_ONEGROUP_FAST,      // agg_onegroup8_kernel row pairs per thread (0: agg_onegroup_kernel)

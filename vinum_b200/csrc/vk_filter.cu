@@ -199,12 +199,7 @@ struct FilterParams {
     unsigned long long* status;  // scratch[1..]
     int64_t num_tiles;
     int pf;  // bulk-prefetch the tile's payload columns into L2 while the predicate / look-back run (1: at tile start, 2: after phase 1)
-    int cs;  // streaming (evict-first) stores for the output columns
 };
-
-__device__ __forceinline__ void stg_cs64(uint64_t* p, uint64_t v) {
-    asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 __device__ __forceinline__ void l2_prefetch_span(const uint8_t* begin, const uint8_t* end) {
     const uint64_t a = reinterpret_cast<uint64_t>(begin) & ~(uint64_t) 15;
@@ -229,7 +224,7 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 // in registers instead costs 16 registers and with them a quarter of the resident tiles (measured
 // -30 % in round 1); shared memory is otherwise unused by this kernel.
 template <int PK, int ITERS, bool STAGE>
-__global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(const __grid_constant__ FilterParams p) {
+__global__ void __launch_bounds__(FT_THREADS, 8) filter_kernel(const __grid_constant__ FilterParams p) {
     static_assert(!STAGE || PK == PK_F64_VEC || PK == PK_I64_VEC, "staging needs an 8-byte compare predicate");
     constexpr int TILE = FT_THREADS * 2 * ITERS;
     constexpr int NCNT = ITERS * (FT_THREADS / 32);   // (iter, warp) counts: 32 or 64
@@ -385,13 +380,8 @@ __global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(
                     v1 = (f & 2) ? reinterpret_cast<const uint64_t*>(col.data)[r0 + 1] : 0;
                 }
                 uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
-                if (p.cs) {   // write-once output: streaming stores leave the L2 to the prefetched input slices
-                    if (f & 1) stg_cs64(o + pos++, v0);
-                    if (f & 2) stg_cs64(o + pos, v1);
-                } else {
-                    if (f & 1) o[pos++] = v0;
-                    if (f & 2) o[pos] = v1;
-                }
+                if (f & 1) o[pos++] = v0;
+                if (f & 2) o[pos] = v1;
             } else {
                 int64_t q = pos;
                 if (f & 1) store_from_u64(p.out_data[c], col.dtype, q++, load_as_u64(col, r0));
@@ -403,226 +393,6 @@ __global__ void __launch_bounds__(FT_THREADS, ITERS == 4 ? 8 : 1) filter_kernel(
                 if (f & 2) outv[q] = col_valid(col, r0 + 1);
             }
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// filter_pipe_kernel -- the same compaction as filter_kernel, persistent and software-pipelined.
-//
-// filter_kernel does, per tile: predicate -> publish the tile's count -> look back for the prefix ->
-// scatter.  The look-back needs the predecessors' counts, which they publish at the same point of THEIR
-// life -- so seven of eight warps sit at the barrier behind warp 0's look-back for about as long as a
-// predicate load takes (32 % of all stall samples, profiles/r02_filter_ncu_full.md).  Here a CTA stays
-// resident, takes tiles from the ticket counter, and publishes tile k+1's count BEFORE it scatters the
-// payload of tile k: by the time it looks back for tile k+1, every predecessor's count has been out for a
-// whole scatter phase and the look-back is one L2 round trip.
-//   A  look back for the current tile (warp 0), publish its prefix
-//   B  scatter the predicate column from shared memory (frees the staging buffer)
-//   C  take the next tile: predicate -> flags (2 registers: 8 flag bits + four packed lane offsets),
-//      counts -> scan -> publish the aggregate
-//   D  scatter the other columns of the current tile
-#ifndef VK_FP_MINB
-#define VK_FP_MINB 8
-#endif
-template <int PK, bool STAGE>
-__global__ void __launch_bounds__(FT_THREADS, VK_FP_MINB) filter_pipe_kernel(const __grid_constant__ FilterParams p) {
-    static_assert(!STAGE || PK == PK_F64_VEC || PK == PK_I64_VEC, "staging needs an 8-byte compare predicate");
-    constexpr int ITERS = 4;
-    constexpr int TILE = FT_THREADS * 2 * ITERS;
-    constexpr int NCNT = ITERS * (FT_THREADS / 32);   // 32 (iter, warp) counts
-    static_assert(NCNT == 32, "one count per lane of warp 0");
-    __shared__ int64_t s_tile;
-    __shared__ uint32_t s_cnt[2][NCNT];
-    __shared__ uint32_t s_total[2];
-    __shared__ int64_t s_excl;
-    __shared__ __align__(16) uint4 s_pred[STAGE ? ITERS * FT_THREADS : 1];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt = lanemask_lt();
-
-    // predicate of one tile -> (flags, packed lane offsets); per-(iter, warp) counts into s_cnt[buf]
-    auto phase1 = [&](int64_t tile, int buf, uint32_t& flags, uint32_t& loff) {
-        const int64_t base = tile * TILE;
-        flags = 0;
-        loff = 0;
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
-            bool f0, f1;
-            if constexpr (STAGE) {
-                f0 = f1 = false;
-                uint4 q = make_uint4(0, 0, 0, 0);
-                if (r0 + 1 < p.n) {
-                    q = ldg_stream16(p.pred.col.data + r0 * 8);
-                } else if (r0 < p.n) {  // last, unpaired row of the batch
-                    const uint2 h = *reinterpret_cast<const uint2*>(p.pred.col.data + r0 * 8);
-                    q.x = h.x;
-                    q.y = h.y;
-                }
-                s_pred[it * FT_THREADS + tid] = q;
-                if constexpr (PK == PK_F64_VEC) {
-                    const double c = __longlong_as_double((long long) p.pred.scalar.bits);
-                    if (r0 < p.n) f0 = apply_cmp(p.pred.op, __hiloint2double(q.y, q.x), c);
-                    if (r0 + 1 < p.n) f1 = apply_cmp(p.pred.op, __hiloint2double(q.w, q.z), c);
-                } else {
-                    const int64_t c = (int64_t) p.pred.scalar.bits;
-                    if (r0 < p.n) f0 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.y << 32) | q.x), c);
-                    if (r0 + 1 < p.n) f1 = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q.w << 32) | q.z), c);
-                }
-            } else {
-                pred_pair<PK>(p.pred, r0, p.n, f0, f1);
-            }
-            const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
-            loff |= (uint32_t) (__popc(b0 & lt) + __popc(b1 & lt)) << (8 * it);
-            flags |= ((uint32_t) f0 << (2 * it)) | ((uint32_t) f1 << (2 * it + 1));
-            if (lane == 0) s_cnt[buf][it * (FT_THREADS / 32) + warp] = __popc(b0) + __popc(b1);
-        }
-    };
-    // warp 0: counts of s_cnt[buf] -> exclusive offsets in place, tile total; publish the aggregate
-    auto scan_publish = [&](int64_t tile, int buf) {
-        const uint32_t mine = s_cnt[buf][lane];
-        uint32_t inc = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        s_cnt[buf][lane] = inc - mine;
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        if (lane == 0) {
-            s_total[buf] = total;
-            st_status(p.status + tile, (tile == 0 ? ST_PREFIX : ST_AGG) | total);
-        }
-    };
-    auto prefetch_payload = [&](int64_t tile) {
-        if (p.pf && tid < p.n_cols) {
-            const Col col = p.cols[tid];
-            const int es = dtype_size(col.dtype);
-            const int64_t base = tile * TILE;
-            const int64_t rows = p.n - base < TILE ? p.n - base : TILE;
-            if (!(p.pred.kind == VK_PRED_CMP && col.data == p.pred.col.data))
-                l2_prefetch_span(col.data + base * es, col.data + (base + rows) * es);
-        }
-    };
-    // scatter column c of a tile
-    auto scatter = [&](int c, int64_t tile, int buf, uint32_t flags, uint32_t loff, int64_t tile_excl) {
-        const int64_t base = tile * TILE;
-        const Col col = p.cols[c];
-        const int es = dtype_size(col.dtype);
-        uint8_t* outv = p.out_valid[c];
-        const bool vec16 = (es == 8) && ((reinterpret_cast<uintptr_t>(col.data) & 15) == 0);
-        const bool staged = STAGE && es == 8 && col.data == p.pred.col.data;
-#pragma unroll
-        for (int it = 0; it < ITERS; ++it) {
-            const uint32_t f = (flags >> (2 * it)) & 3u;
-            if (f == 0) continue;
-            const int64_t r0 = base + it * (FT_THREADS * 2) + tid * 2;
-            int64_t pos = tile_excl + s_cnt[buf][it * (FT_THREADS / 32) + warp] + ((loff >> (8 * it)) & 0xffu);
-            if (es == 8) {
-                uint64_t v0, v1;
-                if (staged) {
-                    const uint4 q = s_pred[STAGE ? it * FT_THREADS + tid : 0];
-                    v0 = ((uint64_t) q.y << 32) | q.x;
-                    v1 = ((uint64_t) q.w << 32) | q.z;
-                } else if (vec16 && r0 + 1 < p.n) {
-                    const uint4 q = ldg_stream16(col.data + r0 * 8);
-                    v0 = ((uint64_t) q.y << 32) | q.x;
-                    v1 = ((uint64_t) q.w << 32) | q.z;
-                } else {
-                    v0 = (f & 1) ? reinterpret_cast<const uint64_t*>(col.data)[r0] : 0;
-                    v1 = (f & 2) ? reinterpret_cast<const uint64_t*>(col.data)[r0 + 1] : 0;
-                }
-                uint64_t* o = reinterpret_cast<uint64_t*>(p.out_data[c]);
-                if (f & 1) o[pos++] = v0;
-                if (f & 2) o[pos] = v1;
-            } else {
-                int64_t q = pos;
-                if (f & 1) store_from_u64(p.out_data[c], col.dtype, q++, load_as_u64(col, r0));
-                if (f & 2) store_from_u64(p.out_data[c], col.dtype, q, load_as_u64(col, r0 + 1));
-            }
-            if (outv != nullptr) {
-                int64_t q = tile_excl + s_cnt[buf][it * (FT_THREADS / 32) + warp] + ((loff >> (8 * it)) & 0xffu);
-                if (f & 1) outv[q++] = col_valid(col, r0);
-                if (f & 2) outv[q] = col_valid(col, r0 + 1);
-            }
-        }
-    };
-
-    // ---- prologue: the first tile of this CTA ----
-    if (tid == 0) s_tile = (int64_t) atomicAdd(p.ticket, 1ULL);
-    __syncthreads();
-    int64_t cur = s_tile;
-    if (cur >= p.num_tiles) return;
-    int buf = 0;
-    uint32_t flags, loff;
-    phase1(cur, buf, flags, loff);
-    prefetch_payload(cur);
-    __syncthreads();
-    if (warp == 0) scan_publish(cur, buf);
-
-    while (true) {
-        // ---- A: look back for the current tile ----
-        if (warp == 0) {
-            const uint64_t total = lane == 0 ? s_total[buf] : 0;   // lane 0 wrote it (scan_publish) and alone uses it
-            uint64_t excl = 0;
-            if (cur != 0) {
-                int64_t look = cur - 1;
-                while (true) {
-                    const int64_t idx = look - lane;
-                    unsigned long long st = ST_PREFIX;  // virtual tile -1: prefix 0
-                    if (idx >= 0) {
-                        do { st = ld_status(p.status + idx); } while ((st >> ST_FLAG_SHIFT) == 0);
-                    }
-                    const unsigned is_prefix = __ballot_sync(0xffffffffu, (st >> ST_FLAG_SHIFT) == 2 || idx < 0);
-                    const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
-                    uint64_t v = (lane <= first) ? (st & ST_VALUE_MASK) : 0;
-                    if (idx < 0) v = 0;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    excl += v;
-                    if (is_prefix) break;
-                    look -= 32;
-                }
-                if (lane == 0) st_status(p.status + cur, ST_PREFIX | (excl + total));
-            }
-            if (lane == 0) {
-                s_excl = (int64_t) excl;
-                if (cur == p.num_tiles - 1) *p.out_rows = (int64_t) (excl + total);
-            }
-        }
-        __syncthreads();
-        const int64_t tile_excl = s_excl;
-
-        // ---- B: the predicate column leaves the staging buffer first ----
-        int staged_col = -1;
-        if constexpr (STAGE) {
-            for (int c = 0; c < p.n_cols; ++c)
-                if (dtype_size(p.cols[c].dtype) == 8 && p.cols[c].data == p.pred.col.data) {
-                    scatter(c, cur, buf, flags, loff, tile_excl);
-                    staged_col = c;   // (the same column listed twice is scattered from DRAM the second time)
-                    break;
-                }
-        }
-        // ---- C: the next tile's predicate and aggregate ----
-        if (tid == 0) s_tile = (int64_t) atomicAdd(p.ticket, 1ULL);
-        __syncthreads();   // also: every warp is done reading s_pred and s_excl
-        const int64_t nxt = s_tile;
-        uint32_t nflags = 0, nloff = 0;
-        if (nxt < p.num_tiles) {
-            phase1(nxt, buf ^ 1, nflags, nloff);
-            __syncthreads();
-            if (warp == 0) scan_publish(nxt, buf ^ 1);
-        }
-        // ---- D: the payload of the current tile ----
-        for (int c = 0; c < p.n_cols; ++c)
-            if (c != staged_col) scatter(c, cur, buf, flags, loff, tile_excl);
-        if (nxt >= p.num_tiles) return;
-        prefetch_payload(nxt);
-        cur = nxt;
-        buf ^= 1;
-        flags = nflags;
-        loff = nloff;
-        __syncthreads();   // s_cnt[old buf] and s_tile are free again; warp 0's scan of the new tile is visible
     }
 }
 
@@ -822,7 +592,7 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
                    "vk_filter: column has validity but no out_valid_bytes buffer");
     }
     // geometry (measured, profiles/r02_variants.md): 2048-row tiles, 8 CTAs per SM
-    const int iters = opt(OPT_FILTER_ITERS) == 8 ? 8 : 4;
+    constexpr int iters = 4;   // 4096-row tiles measured 12 % slower (profiles/r02_variants.md)
     const int tile_rows = FT_THREADS * 2 * iters;
     const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
     // columns are processed FT_MAX_COLS at a time; each pass re-evaluates the predicate
@@ -845,25 +615,11 @@ int vk_filter(const VkPredicate* pred, int64_t n_rows, const VkColumn* cols, int
         p.status = p.ticket + 1;
         p.num_tiles = tiles;
         p.pf = (int) opt(OPT_FILTER_PF);
-        p.cs = (int) opt(OPT_FILTER_CS);
-        const bool stage = pred_is_output && opt(OPT_FILTER_STAGE) != 0 && iters == 4;
-        const bool pipe = opt(OPT_FILTER_PIPE) != 0;
+        const bool stage = pred_is_output && opt(OPT_FILTER_STAGE) != 0;
         VK_CUDA(cudaMemsetAsync(scratch, 0, vk_filter_scratch_bytes(n_rows), s));
 #define VK_FILTER_GO(PK, STAGEABLE)                                                                   \
         do {                                                                                              \
-            if (pipe && iters == 4) {                                                                     \
-                int per_sm = 0;                                                                           \
-                if (STAGEABLE && stage) {                                                                 \
-                    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pipe_kernel<PK, STAGEABLE>, FT_THREADS, 0)); \
-                    const int64_t g = (int64_t) sm_count() * (per_sm > 0 ? per_sm : 1);                  \
-                    filter_pipe_kernel<PK, STAGEABLE><<<(unsigned) (tiles < g ? tiles : g), FT_THREADS, 0, s>>>(p); \
-                } else {                                                                                  \
-                    VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter_pipe_kernel<PK, false>, FT_THREADS, 0)); \
-                    const int64_t g = (int64_t) sm_count() * (per_sm > 0 ? per_sm : 1);                  \
-                    filter_pipe_kernel<PK, false><<<(unsigned) (tiles < g ? tiles : g), FT_THREADS, 0, s>>>(p); \
-                }                                                                                         \
-            } else if (STAGEABLE && stage) filter_kernel<PK, 4, STAGEABLE><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
-            else if (iters == 8) filter_kernel<PK, 8, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);  \
+            if (STAGEABLE && stage) filter_kernel<PK, 4, STAGEABLE><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p); \
             else filter_kernel<PK, 4, false><<<(unsigned) tiles, FT_THREADS, 0, s>>>(p);                  \
         } while (0)
         switch (pk) {

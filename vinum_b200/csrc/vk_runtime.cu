@@ -26,7 +26,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 // ---------------------------------------------------------------- options ----
 struct OptEntry { const char* name; int64_t dflt; std::atomic<int64_t> value; std::atomic<int> state; };  // state 0: unread
 static OptEntry g_opts[OPT_COUNT] = {
-    {"FILTER_STAGE", 1, {0}, {0}},  {"FILTER_PF", 2, {0}, {0}},        {"FILTER_CS", 0, {0}, {0}},        {"FILTER_PIPE", 0, {0}, {0}},      {"FILTER_ITERS", 4, {0}, {0}},
+    {"FILTER_STAGE", 1, {0}, {0}},  {"FILTER_PF", 2, {0}, {0}},        
     {"CMP_FAST", 2, {0}, {0}},      {"ARITH_FAST", 4, {0}, {0}},       {"ONEGROUP_FAST", 2, {0}, {0}},
     {"SORT_FUSE_LAST", 1, {0}, {0}}, {"SORT_PREP", 4, {0}, {0}},
     {"AGG_LOG2S", 12, {0}, {0}},    {"AGG_PF", -1, {0}, {0}},          {"AGG_WARPS", 0, {0}, {0}},
