@@ -37,8 +37,7 @@ def run(key, kt, pred_col, thr=0.5, reps=5):
 
 
 out = {}
-for name, opts in (("entry0_tag_arbitration", {"AGG_ENTRY": 0}), ("entry2_split", {"AGG_ENTRY": 2}),
-                   ("entry2_split_w8", {"AGG_ENTRY": 2, "AGG_WARPS": 8}), ("entry0_w8", {"AGG_ENTRY": 0, "AGG_WARPS": 8})):
+for name, opts in (("default", {}), ("hot_off", {"AGG_HOT": 0}), ("entry0", {"AGG_ENTRY": 0}), ("entry0_hot_off", {"AGG_ENTRY": 0, "AGG_HOT": 0})):
     with vb.options(**opts):
         out[name] = {"c3": run(k32, pa.int32(), None), "northstar": run(i0, pa.int64(), f0), "northstar_hash": run(hk, pa.int64(), f0),
                      "northstar_sel09": run(i0, pa.int64(), f0, 0.1)}

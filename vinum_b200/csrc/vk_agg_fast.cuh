@@ -80,6 +80,7 @@ struct FastParams {
     uint64_t direct_base;         // direct mode: gid = key - direct_base
     int64_t row_limit;            // row-level global inserts stop here (flush reserve above it)
     int pf_dist;                  // L2 bulk prefetch distance in tiles (0 = off)
+    int hot;                      // take a hot group out of the arbitration in one step (option AGG_HOT)
     // hash mode with a host-built dictionary (read-only in the kernel): cuckoo placement of the keys the
     // learning launch found, two hash functions, S = 1 << log2s slots; nullptr = insert-as-you-go table
     const uint64_t* dict_keys;    // [S], LK_EMPTY = free
@@ -329,6 +330,49 @@ struct FastCtx {
     uint32_t lane;
 };
 
+// ---- a hot group leaves the arbitration in one step ------------------------------------------------------
+// Tag arbitration admits ONE lane per entry per round: a key that most lanes of a warp hold costs up to 32
+// rounds of shared-memory traffic per row (26 Grows/s with one key against 193 uniform, profiles/r02_skew.md).
+// Before a row slot arbitrates, the lanes that share the entry of the LOWEST pending lane are counted with one
+// ballot; if they are FA_HOT_MIN or more, their values are summed with a warp butterfly (lanes outside the group
+// add 0.0) and that lane alone updates the entry for all of them.  Uniform keys pay two votes and a shuffle per
+// row slot and never take the branch.  (COUNT + SUM(float64) entries, both layouts.)
+constexpr int FA_HOT_MIN = 6;
+template <int MODE, int PK, int NV, int VAR>
+__device__ __forceinline__ void fast_hot_group(const FastParams& p, const FastCtx& cx, const RawTile<PK, NV>& t, uint32_t ea_r,
+                                               int r, uint32_t& pend, int k) {
+    const bool on = (pend >> k) & 1u;
+    const uint32_t m_on = __ballot_sync(0xffffffffu, on);
+    if (m_on == 0u) return;
+    const int l0 = __ffs(m_on) - 1;
+    const uint32_t ea0 = __shfl_sync(0xffffffffu, ea_r, l0);
+    const uint32_t grp = __ballot_sync(0xffffffffu, on && ea_r == ea0);
+    if (__popc(grp) < FA_HOT_MIN) return;
+    const bool mine = (grp >> cx.lane) & 1u;
+    double v = mine ? __longlong_as_double((long long) row_val<MODE>(p, 0, t.vq[0], r)) : 0.0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((int) cx.lane == l0) {
+        if constexpr (VAR == 2) {
+            const uint32_t g = (ea0 - cx.a_ent) >> 4;
+            const uint32_t a_sum = cx.a_ent + g * 8u, a_ct = cx.a_ent + (uint32_t) p.gmax * 8u + g * 4u;
+            const double sum = __longlong_as_double((long long) lds64(a_sum)) + v;
+            sts64(a_sum, (uint64_t) __double_as_longlong(sum));
+            sts32(a_ct, (lds32(a_ct) + (uint32_t) __popc(grp)) & 0x00FFFFFFu);
+        } else {
+            uint32_t e[4];
+            lds128(ea0, e);
+            e[0] += (uint32_t) __popc(grp);
+            const double sum = __hiloint2double((int) e[3], (int) e[2]) + v;
+            e[2] = (uint32_t) __double2loint(sum);
+            e[3] = (uint32_t) __double2hiint(sum);
+            sts128(ea0, e);
+        }
+    }
+    if (mine) pend &= ~(1u << k);
+    __syncwarp();
+}
+
 // Entry layout (NW 64-bit words, NW = 2 or 4):
 //   word 0 = COUNT (low 32 bits: one warp in one launch) | arbitration tag (high 32 bits)
 //   word 1.. = accumulator cells
@@ -520,6 +564,10 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
                 a_sum[k] = cx.a_ent + g * 8u;
                 a_ct[k] = cx.a_ent + ct_off + g * 4u;
             }
+            if (p.hot) {
+#pragma unroll
+                for (int k = 0; k < FA_K; ++k) fast_hot_group<MODE, PK, NV, 2>(p, cx, t, ea[q * FA_K + k], q * FA_K + k, pend, k);
+            }
             while (__any_sync(0xffffffffu, pend != 0)) {
 #pragma unroll
                 for (int k = 0; k < FA_K; ++k)
@@ -602,6 +650,12 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
 #pragma unroll
     for (int q = 0; q < FA_R / FA_K; ++q) {
         uint32_t pend = (todo >> (q * FA_K)) & ((1u << FA_K) - 1u);
+        if constexpr (SUMF64) {
+            if (p.hot) {
+#pragma unroll
+                for (int k = 0; k < FA_K; ++k) fast_hot_group<MODE, PK, NV, 0>(p, cx, t, ea[q * FA_K + k], q * FA_K + k, pend, k);
+            }
+        }
         while (__any_sync(0xffffffffu, pend != 0)) {
 #pragma unroll
             for (int k = 0; k < FA_K; ++k)

@@ -1591,6 +1591,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             fp.gmax = gmax;
             fp.direct_base = direct_base;
             fp.row_limit = a->t.max_groups - flush_reserve;
+            fp.hot = (int) opt(OPT_AGG_HOT);
             fp.pf_dist = warps >= 5 ? pf_dist : 0;  // one prefetching lane per column: needs NV + 2 warps
             fp.table = a->t;
             fp.replay = gp.replay;
