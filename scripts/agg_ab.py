@@ -37,7 +37,7 @@ def run(key, kt, pred_col, thr=0.5, reps=5):
 
 
 out = {}
-for name, opts in (("default", {}), ("hot_off", {"AGG_HOT": 0}), ("entry0", {"AGG_ENTRY": 0}), ("entry0_hot_off", {"AGG_ENTRY": 0, "AGG_HOT": 0})):
+for name, opts in (("default", {}), ("hot_off", {"AGG_HOT": 0}), ("hot_always", {"AGG_HOT": 2})):
     with vb.options(**opts):
         out[name] = {"c3": run(k32, pa.int32(), None), "northstar": run(i0, pa.int64(), f0), "northstar_hash": run(hk, pa.int64(), f0),
                      "northstar_sel09": run(i0, pa.int64(), f0, 0.1)}

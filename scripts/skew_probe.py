@@ -41,7 +41,7 @@ for kind in ("uniform", "zipf1.0", "hot90", "hot100"):
     want_c = np.bincount(k_h[p_h], minlength=1000)
     want_s = np.bincount(k_h[p_h], weights=v_h[p_h], minlength=1000)
     row = {}
-    for name, opts in (("default", {}), ("no_hot_step", {"AGG_HOT": 0}), ("split_entries", {"AGG_ENTRY": 2}), ("global_table", {"AGG_NOFAST": 1})):
+    for name, opts in (("default", {}), ("no_hot_step", {"AGG_HOT": 0}), ("hot_step_always", {"AGG_HOT": 2}), ("global_table", {"AGG_NOFAST": 1})):
         ts = []
         with vb.options(**opts):
             for i in range(5):

@@ -72,7 +72,8 @@ PATH_OPTS = {
     "hash_small": {"AGG_DIRECT": 0, "AGG_LOG2S": 10, "AGG_WARPS": 12},
     "tag_arbitration": {"AGG_ENTRY": 0},
     "no_hot_group_step": {"AGG_HOT": 0},
-    "split_no_hot_group_step": {"AGG_ENTRY": 2, "AGG_HOT": 0},
+    "hot_group_step_always": {"AGG_HOT": 2},
+    "split_hot_group_step_always": {"AGG_ENTRY": 2, "AGG_HOT": 2},
     "split_entries": {"AGG_ENTRY": 2},                             # SUM array + {tag | COUNT} array
     "general": {"AGG_NOFAST": 1},
 }

@@ -80,7 +80,6 @@ struct FastParams {
     uint64_t direct_base;         // direct mode: gid = key - direct_base
     int64_t row_limit;            // row-level global inserts stop here (flush reserve above it)
     int pf_dist;                  // L2 bulk prefetch distance in tiles (0 = off)
-    int hot;                      // take a hot group out of the arbitration in one step (option AGG_HOT)
     // hash mode with a host-built dictionary (read-only in the kernel): cuckoo placement of the keys the
     // learning launch found, two hash functions, S = 1 << log2s slots; nullptr = insert-as-you-go table
     const uint64_t* dict_keys;    // [S], LK_EMPTY = free
@@ -336,7 +335,9 @@ struct FastCtx {
 // Before a row slot arbitrates, the lanes that share the entry of the LOWEST pending lane are counted with one
 // ballot; if they are FA_HOT_MIN or more, their values are summed with a warp butterfly (lanes outside the group
 // add 0.0) and that lane alone updates the entry for all of them.  Uniform keys pay two votes and a shuffle per
-// row slot and never take the branch.  (COUNT + SUM(float64) entries, both layouts.)
+// row slot and never take the branch -- but even that costs the HBM-bound north-star kernel 50 % (7.03 against
+// 4.71 ms), so the step is a template parameter and the host picks the kernel that has it only when the learning
+// launch saw one key hold >= 30 % of the rows (option AGG_HOT: 1 = that rule, 2 = always, 0 = never).
 constexpr int FA_HOT_MIN = 6;
 template <int MODE, int PK, int NV, int VAR>
 __device__ __forceinline__ void fast_hot_group(const FastParams& p, const FastCtx& cx, const RawTile<PK, NV>& t, uint32_t ea_r,
@@ -383,7 +384,7 @@ __device__ __forceinline__ void fast_hot_group(const FastParams& p, const FastCt
 // Phase 2 is one short critical section per row: store the lane id as the entry's tag,
 // sync the warp, load the whole entry (tag + COUNT + cell in one LDS.128); the lane that
 // reads its own tag back applies the row and stores the entry, the others go round again.
-template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, int VAR>
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, int VAR, bool HOT>
 __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx, RawTile<PK, NV>& t, uint8_t* smem,
                                           uint32_t* s_ngroups, int64_t row0, int tid, int nthreads, int64_t refill_tile,
                                           uint32_t& spilled) {
@@ -564,7 +565,7 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
                 a_sum[k] = cx.a_ent + g * 8u;
                 a_ct[k] = cx.a_ent + ct_off + g * 4u;
             }
-            if (p.hot) {
+            if constexpr (HOT) {
 #pragma unroll
                 for (int k = 0; k < FA_K; ++k) fast_hot_group<MODE, PK, NV, 2>(p, cx, t, ea[q * FA_K + k], q * FA_K + k, pend, k);
             }
@@ -650,11 +651,9 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
 #pragma unroll
     for (int q = 0; q < FA_R / FA_K; ++q) {
         uint32_t pend = (todo >> (q * FA_K)) & ((1u << FA_K) - 1u);
-        if constexpr (SUMF64) {
-            if (p.hot) {
+        if constexpr (SUMF64 && HOT) {
 #pragma unroll
-                for (int k = 0; k < FA_K; ++k) fast_hot_group<MODE, PK, NV, 0>(p, cx, t, ea[q * FA_K + k], q * FA_K + k, pend, k);
-            }
+            for (int k = 0; k < FA_K; ++k) fast_hot_group<MODE, PK, NV, 0>(p, cx, t, ea[q * FA_K + k], q * FA_K + k, pend, k);
         }
         while (__any_sync(0xffffffffu, pend != 0)) {
 #pragma unroll
@@ -689,7 +688,7 @@ __device__ __forceinline__ void fast_tile(const FastParams& p, const FastCtx& cx
     }
 }
 
-template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, int VAR = 0>
+template <int PK, int NV, int NW, int MODE, bool DIRECT, bool SUMF64, int VAR = 0, bool HOT = false>
 __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t s_ngroups;
@@ -749,7 +748,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) agg_fast_kernel(const __gri
     };
     auto process = [&](int64_t tl, RawTile<PK, NV>& t) {
         const int64_t nx = tl + 2 * stride;
-        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64, VAR>(p, cx, t, smem, &s_ngroups, tl * tile_rows + tid * 2, tid, nthreads,
+        fast_tile<PK, NV, NW, MODE, DIRECT, SUMF64, VAR, HOT>(p, cx, t, smem, &s_ngroups, tl * tile_rows + tid * 2, tid, nthreads,
                                                     nx < p.num_tiles ? nx : (int64_t) -1, spilled);
     };
     if (tile < p.num_tiles) load_all(tile, ta);
@@ -873,6 +872,7 @@ struct FastLaunch {
     bool direct;
     bool sumf64;
     int variant;   // SUMF64 only: 0 = 16-byte entries, 2 = split (SoA) entries; both with tag arbitration
+    bool hot;      // SUMF64 only: the kernel with the hot-group step (a key that holds a large share of the rows)
     int grid, threads;
     size_t smem;
 };
@@ -893,6 +893,8 @@ int launch_fast_lean(const FastParams& p, const FastLaunch& l, cudaStream_t s) {
     switch (p.n_cols) {
         case 0: VK_FAST_GO(PK, 0, 2, MODE, DIRECT, false);
         case 1:
+            if (l.nw == 2 && l.sumf64 && l.hot && l.variant == 2) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true, 2, true);
+            if (l.nw == 2 && l.sumf64 && l.hot) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true, 0, true);
             if (l.nw == 2 && l.sumf64 && l.variant == 2) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true, 2);
             if (l.nw == 2 && l.sumf64) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, true);
             if (l.nw == 2) VK_FAST_GO(PK, 1, 2, MODE, DIRECT, false);

@@ -51,7 +51,7 @@ enum Opt {
     OPT_AGG_DIRECT,         // 1: direct (key - base) group ids when the key range allows, 0: always hash
     OPT_AGG_DICT,           // 1: hash mode looks keys up in a host-built read-only cuckoo dictionary
     OPT_AGG_ENTRY,          // agg_fast_kernel, COUNT + SUM(f64) entry: 0 = 16-byte entries, 2 = split entries (SUM array + {tag | COUNT} array), 1 = by selectivity
-    OPT_AGG_HOT,            // 1: a group that >= 6 lanes of a warp hold leaves the tag arbitration in one butterfly-reduced update
+    OPT_AGG_HOT,            // hot-group step (>= 6 lanes of a warp on one entry -> one butterfly-reduced update): 1 = when the learning launch saw a key with >= 30 % of the rows, 2 = always, 0 = never
     OPT_AGG_NOFAST,         // 1: never use the shared-memory aggregate kernel
     OPT_AGG_LEARN_LOG2,     // log2 rows of the learning launch
     OPT_LIST_LOG2,          // log2 of the replay-list capacity cap (entries)

@@ -50,6 +50,19 @@ __global__ void __launch_bounds__(256) agg_key_range_kernel(GTable t, long long*
     }
 }
 
+// Rows of the largest group of a table (the learning launch's measure of key skew).
+__global__ void __launch_bounds__(256) agg_max_count_kernel(GTable t, unsigned long long* out) {
+    unsigned long long mx = 0;
+    const int64_t slots = gt_total_slots(t);
+    for (int64_t s = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (int64_t) gridDim.x * blockDim.x)
+        if (gt_slot_occupied(t, s) && t.count_star[s] > mx) mx = t.count_star[s];
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, d);
+        mx = o > mx ? o : mx;
+    }
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+
 // Keys of a single-key table as a dense list (the dictionary builder reads them back).
 __global__ void __launch_bounds__(256) agg_export_keys_kernel(GTable t, uint64_t* out, unsigned long long* cursor,
                                                               unsigned long long cap) {
@@ -669,6 +682,8 @@ struct VkAgg {
     // launch, vk_agg_fast.cuh); rows with other keys go to the global table
     bool dict_ready = false, dict_failed = false;
     int dict_policy = 1;
+    int hot_policy = 1;               // option AGG_HOT
+    double hot_share = 0.0;           // largest group's share of the selected rows (learning launch)
     int match_policy = 1;             // option AGG_ENTRY: layout / update protocol of the COUNT + SUM(f64) entry
     int dict_n = 0;                   // keys in the dictionary
     int dict_log2s = 0;
@@ -701,7 +716,7 @@ bool debug_on() {
 #define VK_DBG(...) do { if (debug_on()) { fprintf(stderr, "[vk_agg] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
 constexpr double kMaxLoad = 0.5;
-constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_SELECTED = 6, CTR_RANGE = 8, CTR_WORDS = 16;
+constexpr int CTR_GROUPS = 0, CTR_LIST = 1, CTR_LOST = 2, CTR_SPILL = 3, CTR_CURSOR = 4, CTR_SELECTED = 6, CTR_RANGE = 8, CTR_MAXCOUNT = 10, CTR_WORDS = 16;
 
 // Counter blocks (16 device words + a pinned host mirror) are recycled across aggregate
 // objects: cudaMalloc / cudaHostAlloc / cudaFree cost far more than a whole 1e9-row scan.
@@ -1232,6 +1247,7 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
     if (a->fast_warps > FA_MAX_THREADS / 32) a->fast_warps = FA_MAX_THREADS / 32;
     a->fast_direct_policy = (int) opt(OPT_AGG_DIRECT);
     a->dict_policy = (int) opt(OPT_AGG_DICT);
+    a->hot_policy = (int) opt(OPT_AGG_HOT);
     a->match_policy = (int) opt(OPT_AGG_ENTRY);
     if (a->match_policy < 0 || a->match_policy > 2) a->match_policy = 1;
     if (opt(OPT_AGG_NOFAST)) a->fast_disabled = true;
@@ -1591,7 +1607,6 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             fp.gmax = gmax;
             fp.direct_base = direct_base;
             fp.row_limit = a->t.max_groups - flush_reserve;
-            fp.hot = (int) opt(OPT_AGG_HOT);
             fp.pf_dist = warps >= 5 ? pf_dist : 0;  // one prefetching lane per column: needs NV + 2 warps
             fp.table = a->t;
             fp.replay = gp.replay;
@@ -1606,8 +1621,6 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             fl.mode = lean ? plan.mode : FM_RUNTIME;
             fl.direct = direct;
             fl.sumf64 = plan.sumf64;
-            // match-combine (one entry update per distinct group id per warp-row): policy 1 = where the
-            // shared-memory pipe binds (nearly every row reaches the tables), 2 = always, 0 = never
             // COUNT + SUM(f64) entry layout (option AGG_ENTRY): split entries move 11 % fewer shared-memory
             // wavefronts and win where that pipe binds (C3: 3.89 ms against 4.17), 16-byte entries win by 2 %
             // where HBM binds (selective predicate); 1 = choose by the selectivity the learning launch measured
@@ -1615,6 +1628,9 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 const bool pipe_bound = !(pk != PK_NONE && a->fast_rows_seen > 0 && a->fast_selectivity <= 0.7);
                 const int want = a->match_policy == 1 ? (pipe_bound ? 2 : 0) : a->match_policy;
                 fl.variant = (lean && plan.sumf64 && plan.nw == 2) ? want : 0;
+                // the kernel with the hot-group step only where a key holds a large share of the rows: for
+                // uniform keys its two extra votes per row slot cost the HBM-bound kernel 50 %
+                fl.hot = lean && plan.sumf64 && plan.nw == 2 && (a->hot_policy == 2 || (a->hot_policy == 1 && a->hot_share >= 0.3));
             }
             fl.grid = fp.num_tiles < fast_grid_max ? (int) fp.num_tiles : fast_grid_max;
             fl.threads = threads;
@@ -1655,6 +1671,13 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
 
         if (may_fail || (fast && a->fast_rows_seen < ((uint64_t) 1 << 20))) {
             // rows may have been deferred (or we are still learning the cardinality)
+            if (fast && a->hot_policy == 1 && plan.sumf64) {
+                // key skew so far: the largest group's share of the selected rows (one scan of the table)
+                VK_CUDA(cudaMemsetAsync(a->d_ctr + CTR_MAXCOUNT, 0, sizeof(unsigned long long), s));
+                int64_t need = (gt_total_slots(a->t) + 255) / 256, capb = (int64_t) sms * 8;
+                agg_max_count_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(a->t, a->d_ctr + CTR_MAXCOUNT);
+                VK_CHECK_LAUNCH("agg_max_count_kernel");
+            }
             rc = read_counters(a, s);
             if (rc != VK_OK) return rc;
             if (fast) {
@@ -1663,6 +1686,11 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 a->fast_spilled += spill_now;
                 a->fast_selectivity = (double) (a->h_ctr[CTR_SELECTED] + a->fast_spilled) / (double) a->fast_rows_seen;
                 a->fast_groups_seen = (int64_t) a->h_ctr[CTR_GROUPS];
+                if (a->hot_policy == 1 && plan.sumf64) {
+                    const double selected = (double) (a->h_ctr[CTR_SELECTED] + a->fast_spilled);
+                    a->hot_share = selected > 0 ? (double) a->h_ctr[CTR_MAXCOUNT] / selected : 0.0;
+                    VK_DBG("largest group holds %.1f %% of the rows", 100.0 * a->hot_share);
+                }
                 if (chunk >= 65536 && spill_now * 4 > (uint64_t) chunk) {
                     // this configuration thrashes: most rows fell through to the global path
                     if (direct) a->direct_ok = false;   // the key range moved: back to hash mode
