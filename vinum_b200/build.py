@@ -23,7 +23,7 @@ LIB_PATH = OUT_DIR / "libvinum_b200.so"
 # (source, object stem, extra defines): vk_agg_fast_inst.cu is compiled once per slice of
 # the fused-aggregate kernel variants so that they build in parallel
 SOURCES = [
-    ("vk_agg_fast_inst.cu", f"vk_agg_fast_inst{part}", [f"-DVK_FAST_PART={part}"]) for part in range(5)
+    ("vk_agg_fast_inst.cu", f"vk_agg_fast_inst{part}", [f"-DVK_FAST_PART={part}"]) for part in range(15)
 ] + [
     ("vk_hashagg.cu", "vk_hashagg", []),
     ("vk_sort.cu", "vk_sort", []),
@@ -92,7 +92,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", defines
             print(r.stderr, flush=True)
         return obj
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = lib_path.with_suffix(".so.tmp")
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *map(str, objs)]

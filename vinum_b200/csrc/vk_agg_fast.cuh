@@ -918,15 +918,32 @@ int launch_fast_generic(const FastParams& p, const FastLaunch& l, cudaStream_t s
 // The instantiations are spread over several translation units (vk_agg_fast_inst.cu is
 // compiled once per VK_FAST_PART) so that they build in parallel.
 #define VK_FAST_DECL(name) int name(const FastParams& p, const FastLaunch& l, cudaStream_t s)
-VK_FAST_DECL(launch_fast_none_all8);
-VK_FAST_DECL(launch_fast_none_key4);
+VK_FAST_DECL(launch_fast_none_all8_d);   // _d: direct group ids, _t: CTA key table / dictionary
+VK_FAST_DECL(launch_fast_none_all8_t);
+VK_FAST_DECL(launch_fast_none_key4_d);
+VK_FAST_DECL(launch_fast_none_key4_t);
 VK_FAST_DECL(launch_fast_none_rt);
-VK_FAST_DECL(launch_fast_f64_all8);
-VK_FAST_DECL(launch_fast_f64_key4);
+VK_FAST_DECL(launch_fast_f64_all8_d);
+VK_FAST_DECL(launch_fast_f64_all8_t);
+VK_FAST_DECL(launch_fast_f64_key4_d);
+VK_FAST_DECL(launch_fast_f64_key4_t);
 VK_FAST_DECL(launch_fast_f64_rt);
 VK_FAST_DECL(launch_fast_mask_rt);
 VK_FAST_DECL(launch_fast_i64_rt);
-VK_FAST_DECL(launch_fast_gen_rt);
+// PK_GENERIC carries the fused expression evaluator: one kernel per translation unit (each takes ~1 min of ptxas)
+VK_FAST_DECL(launch_fast_gen_rt_c0);
+VK_FAST_DECL(launch_fast_gen_rt_c1n);   // one value column, 2 warps per table
+VK_FAST_DECL(launch_fast_gen_rt_c1);
+VK_FAST_DECL(launch_fast_gen_rt_c2);
+VK_FAST_DECL(launch_fast_gen_rt_c3);
+inline int launch_fast_gen_rt(const FastParams& p, const FastLaunch& l, cudaStream_t s) {
+    switch (p.n_cols) {
+        case 0: return launch_fast_gen_rt_c0(p, l, s);
+        case 1: return l.nw == 2 ? launch_fast_gen_rt_c1n(p, l, s) : launch_fast_gen_rt_c1(p, l, s);
+        case 2: return launch_fast_gen_rt_c2(p, l, s);
+        default: return launch_fast_gen_rt_c3(p, l, s);
+    }
+}
 
 // Which predicate kinds have the lean set (the host only asks for direct / compile-time modes there).
 __host__ inline bool fast_pk_is_lean(int pk) { return pk == PK_NONE || pk == PK_F64_VEC; }

@@ -950,11 +950,13 @@ int fast_gmax(int log2s, bool direct, int nw, int warps) {
 int launch_fast(const FastParams& p, const FastLaunch& l, cudaStream_t s) {
     switch (l.pk) {
         case PK_NONE:
-            return l.mode == FM_ALL8 ? launch_fast_none_all8(p, l, s)
-                 : l.mode == FM_KEY4 ? launch_fast_none_key4(p, l, s) : launch_fast_none_rt(p, l, s);
+            return l.mode == FM_ALL8 ? (l.direct ? launch_fast_none_all8_d(p, l, s) : launch_fast_none_all8_t(p, l, s))
+                 : l.mode == FM_KEY4 ? (l.direct ? launch_fast_none_key4_d(p, l, s) : launch_fast_none_key4_t(p, l, s))
+                                     : launch_fast_none_rt(p, l, s);
         case PK_F64_VEC:
-            return l.mode == FM_ALL8 ? launch_fast_f64_all8(p, l, s)
-                 : l.mode == FM_KEY4 ? launch_fast_f64_key4(p, l, s) : launch_fast_f64_rt(p, l, s);
+            return l.mode == FM_ALL8 ? (l.direct ? launch_fast_f64_all8_d(p, l, s) : launch_fast_f64_all8_t(p, l, s))
+                 : l.mode == FM_KEY4 ? (l.direct ? launch_fast_f64_key4_d(p, l, s) : launch_fast_f64_key4_t(p, l, s))
+                                     : launch_fast_f64_rt(p, l, s);
         case PK_MASK: return launch_fast_mask_rt(p, l, s);
         case PK_I64_VEC: return launch_fast_i64_rt(p, l, s);
         default: return launch_fast_gen_rt(p, l, s);
