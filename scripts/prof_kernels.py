@@ -1,5 +1,5 @@
 """Workloads for ncu captures (one kernel family per invocation, BASELINE sizes):
-    python scripts/prof_kernels.py northstar|hash|c3|filter|sort|arith|compare|onegroup|topk [ROWS]"""
+    python scripts/prof_kernels.py northstar|hash|groups1e6|groups1e5|groups8m|c3|filter|sort|arith|compare|onegroup|topk [ROWS]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pyarrow as pa
@@ -7,13 +7,19 @@ import vinum_b200 as vb
 from vinum_b200 import _lib as L, datagen, ops
 what = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else (1_000_000_000 if what in ("northstar", "hash", "c3") else 100_000_000)
+if what in ("groups1e6", "groups1e5", "groups8m") and len(sys.argv) <= 2:
+    n = 200_000_000
 vb.lib.vk_set_device(0)
 st = vb.default_stream()
 spec = [(L.AGG_COUNT_STAR, None), (L.AGG_SUM, pa.float64())]
-if what in ("northstar", "hash", "c3"):
-    key = datagen.device_column("k32" if what == "c3" else "i0", 0, n, stream=st)
+if what in ("northstar", "hash", "c3", "groups1e6", "groups1e5", "groups8m"):
+    key = datagen.device_column("k32" if what == "c3" else ("i3" if what in ("groups1e6", "groups1e5") else "i0"), 0, n, stream=st)
     if what == "hash":
         key = ops.arith("*", key, 2654435761, st)
+    if what == "groups8m":
+        key = ops.arith("&", datagen.device_column("i1", 0, n, stream=st), (1 << 23) - 1, st)
+    if what == "groups1e5":
+        key = ops.arith("%", key, 100000, st)
     f1 = datagen.device_column("f1", 0, n, stream=st)
     f0 = datagen.device_column("f0", 0, n, stream=st) if what != "c3" else None
     for _ in range(2):

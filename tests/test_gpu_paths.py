@@ -75,7 +75,8 @@ PATH_OPTS = {
     "hot_group_step_always": {"AGG_HOT": 2},
     "split_hot_group_step_always": {"AGG_ENTRY": 2, "AGG_HOT": 2},
     "split_entries": {"AGG_ENTRY": 2},                             # SUM array + {tag | COUNT} array
-    "general": {"AGG_NOFAST": 1},
+    "general": {"AGG_NOFAST": 1},                                  # global table, four rows per thread (agg_wide_kernel)
+    "general_one_row": {"AGG_NOFAST": 1, "AGG_WIDE": 0},           # agg_general_kernel
 }
 
 
@@ -120,6 +121,38 @@ def test_group_by_hostile_key_distributions(vb, stream, kind, path):
     assert_tables_match(got, want, key_cols=["k"], rtol=FLOAT_RTOL)
     if path == "general":
         assert paths == [2]
+
+
+def _many_keys(kind: str, n: int, rng) -> np.ndarray:
+    if kind == "uniform_2e6":        # the estimate g = G (1 - exp(-n / G)) is exact in expectation
+        return rng.integers(0, 2_000_000, n).astype(np.int64)
+    if kind == "all_distinct":       # g == n: no estimate, every row left is taken for a new group
+        return rng.permutation(n).astype(np.int64) * 7919
+    if kind == "sorted_runs":        # new groups arrive at a constant rate: the even-draw estimate is far too low
+        return (np.arange(n, dtype=np.int64) // 3) - 12345
+    if kind == "skewed_long_tail":   # half the rows on 100 keys, the rest spread thin
+        k = rng.integers(0, 3_000_000, n).astype(np.int64)
+        hot = rng.random(n) < 0.5
+        k[hot] = rng.integers(0, 100, int(hot.sum()))
+        return k
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("path", ["auto", "general", "general_one_row"])
+@pytest.mark.parametrize("chunks", [1, 3])
+@pytest.mark.parametrize("kind", ["uniform_2e6", "all_distinct", "sorted_runs", "skewed_long_tail"])
+def test_group_by_more_groups_than_the_first_table_holds(vb, stream, kind, chunks, path):
+    """Millions of groups: the global table (2 Mi slots at first) is sized from the estimate the host makes at
+    every chunk boundary, grown when the estimate was low, and rows that found it full are replayed; nothing
+    is lost or counted twice whichever of these happens (unordered_map semantics of
+    single_numerical_hash_aggregate.cpp:15-46)."""
+    rng = np.random.default_rng(zlib.crc32(kind.encode()) + chunks)
+    n = 4_300_007
+    table = pa.table({"k": _many_keys(kind, n, rng), "v": rng.normal(0, 100, n), "p": rng.random(n)})
+    want = _reference_groupby(table, ("p", ">", 0.25))
+    got, paths = _device_groupby(vb, stream, table, ("p", ">", 0.25), dict(AGG_LEARN_LOG2=16, **PATH_OPTS[path]), chunks=chunks)
+    assert_tables_match(got, want, key_cols=["k"], rtol=FLOAT_RTOL)
+    assert paths[-1] == 2
 
 
 @pytest.mark.parametrize("path", ["auto", "hash", "hash_insert", "tag_arbitration", "split_entries", "general"])

@@ -20,6 +20,7 @@
 // never loses rows whatever the cardinality turns out to be.
 #include "vk_hashagg.cuh"
 #include "vk_agg_fast.cuh"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -97,13 +98,24 @@ __device__ __forceinline__ bool pred_row(const Pred& p, int64_t i) {
     return pred_row_generic(p, i);
 }
 
+// Rows that passed the predicate (first visits only), one atomic per warp: the host sizes the table from
+// (selected rows, groups) while the number of groups is still rising.
+__device__ __forceinline__ void count_selected(const GenParams& p, unsigned n_selected) {
+    if (p.row_list != nullptr || p.replay.selected == nullptr) return;
+    __syncwarp();
+    n_selected = __reduce_add_sync(0xffffffffu, n_selected);
+    if ((threadIdx.x & 31) == 0 && n_selected) atomicAdd(p.replay.selected, (unsigned long long) n_selected);
+}
+
 __global__ void __launch_bounds__(256) agg_general_kernel(const __grid_constant__ GenParams p) {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     const bool replaying = p.row_list != nullptr;
     const int64_t total = replaying ? (int64_t) *p.row_list_count : p.n;
+    unsigned n_selected = 0;
     for (int64_t it = (replaying ? 0 : p.row_begin) + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; it < total; it += stride) {
         const int64_t i = replaying ? (int64_t) p.row_list[it] : it;
         if (!replaying && !pred_row(p.pred, i)) continue;  // listed rows already passed the predicate
+        ++n_selected;
         uint64_t kv[VK_AGG_MAX_KEYS];
         uint32_t nullmask = 0;
         for (int k = 0; k < p.n_keys; ++k) {
@@ -127,6 +139,221 @@ __global__ void __launch_bounds__(256) agg_general_kernel(const __grid_constant_
             if (spec.acc == ACC_COUNT) continue;
             acc_update_global(p.table, f, spec, slot, acc_load(spec, p.vals[f], i));
         }
+    }
+    count_selected(p, n_selected);
+}
+
+// ---- the same update for single-key tables, R rows per thread ---------------------------------
+// agg_general_kernel keeps ONE row per thread in flight and walks a chain of dependent loads for it
+// (predicate -> key -> table slot -> value): at 1e6 groups ncu shows 62 % long-scoreboard stalls at
+// 94 % occupancy (profiles/r02_agg_general_1e6_ncu_full.md).  Here a thread owns R rows of a tile
+// (as R/2 adjacent pairs, so that 8-byte predicate columns arrive by 16-byte loads) and every stage
+// is issued for all R rows before the next stage waits on it: R predicate loads in flight, then R
+// key loads, then R first-probe loads of the table (the wait-free single-key protocol of
+// gt1_find_or_insert makes a plain load a complete look-up when the key is already there), then the
+// value loads, then the fire-and-forget reductions.  Rows that meet a foreign slot probe on in lock step
+// with the other rows of the warp; an empty slot is claimed by the same CAS as in gt1_find_or_insert.
+template <int PK, int R>
+__global__ void __launch_bounds__(256) agg_wide_kernel(const __grid_constant__ GenParams p) {
+    constexpr int64_t TILE = 256 * R;
+    const GTable& t = p.table;
+    const Col& kc = p.keys[0];
+    const uint64_t mask = (uint64_t) t.capacity - 1;
+    const int64_t n_tiles = (p.n - p.row_begin + TILE - 1) / TILE;
+    unsigned n_selected = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // the tile loop is warp-uniform; a warp that entered a tile diverged was measured at 4.3 active lanes
+        // per issued instruction and 3.6 x the DRAM traffic
+        __syncwarp();
+        const int64_t base = p.row_begin + tile * TILE + 2 * (int64_t) threadIdx.x;   // row_begin is even
+        bool sel[R];
+        if ((PK == PK_F64_VEC || PK == PK_I64_VEC) && p.row_begin + (tile + 1) * TILE <= p.n) {
+            // whole tile: the R/2 predicate loads first, the comparisons after them
+            uint4 q[R / 2];
+#pragma unroll
+            for (int j = 0; j < R / 2; ++j) q[j] = ldg_stream16(p.pred.col.data + (base + j * 512) * 8);
+#pragma unroll
+            for (int j = 0; j < R / 2; ++j) {
+                if (PK == PK_F64_VEC) {
+                    const double c = __longlong_as_double((long long) p.pred.scalar.bits);
+                    sel[2 * j] = apply_cmp(p.pred.op, __hiloint2double(q[j].y, q[j].x), c);
+                    sel[2 * j + 1] = apply_cmp(p.pred.op, __hiloint2double(q[j].w, q[j].z), c);
+                } else {
+                    const int64_t c = (int64_t) p.pred.scalar.bits;
+                    sel[2 * j] = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q[j].y << 32) | q[j].x), c);
+                    sel[2 * j + 1] = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q[j].w << 32) | q[j].z), c);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; j += 2) pred_pair<PK>(p.pred, base + (j / 2) * 512, p.n, sel[j], sel[j + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) n_selected += sel[j] ? 1u : 0u;
+        uint64_t key[R];
+        bool plain[R];   // an ordinary key: not NULL, not the value that marks a free slot
+        if (kc.validity == nullptr && (kc.dtype == VK_I64 || kc.dtype == VK_U64 || kc.dtype == VK_F64)) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                key[j] = 0;
+                plain[j] = sel[j];
+                if (sel[j]) key[j] = reinterpret_cast<const uint64_t*>(kc.data)[base + (j / 2) * 512 + (j & 1)];
+            }
+        } else if (kc.validity == nullptr && kc.dtype == VK_I32) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                key[j] = 0;
+                plain[j] = sel[j];
+                if (sel[j]) key[j] = (uint64_t) (int64_t) reinterpret_cast<const int32_t*>(kc.data)[base + (j / 2) * 512 + (j & 1)];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int64_t i = base + (j / 2) * 512 + (j & 1);
+                key[j] = 0;
+                plain[j] = false;
+                if (sel[j]) {
+                    plain[j] = col_valid(kc, i);
+                    if (plain[j]) key[j] = load_as_u64(kc, i);
+                }
+            }
+        }
+        int64_t slot[R];
+        bool pend[R];   // rows still looking for their slot
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            pend[j] = plain[j] && key[j] != GT_EMPTY;
+            slot[j] = (int64_t) (hash_key1(key[j]) & mask);
+            if (sel[j] && !pend[j]) {
+                // NULL key / the key value that marks a free slot: their two dedicated slots
+                const int64_t i = base + (j / 2) * 512 + (j & 1);
+                slot[j] = gt1_find_or_insert(t, key[j], !plain[j], 0, t.max_groups);
+                if (slot[j] < 0) {
+                    replay_append(p.replay, i);
+                    sel[j] = false;
+                }
+            }
+        }
+        // Linear probing in lock step: one round loads the current slot of every pending row of the warp
+        // (R loads in flight per lane); each row is then found, inserted by CAS (the protocol of
+        // gt1_find_or_insert) or moves one slot on.  Votes keep the warp converged; the group counter, one
+        // hot address, is read once per warp and round and advanced once per warp.  (Loading two slots per
+        // round was measured: fewer rounds, but 64 registers instead of 56 and 10 % slower at 1e4 - 1e6 groups.)
+        const unsigned lane = threadIdx.x & 31u;
+        for (int64_t probes = 0; probes < t.capacity; ++probes) {
+            uint64_t seen[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                seen[j] = key[j];
+                if (pend[j]) seen[j] = ld_key_relaxed(t.keys + slot[j]);
+            }
+            bool more = false;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const bool claim = pend[j] && seen[j] == GT_EMPTY;
+                const unsigned claimers = __ballot_sync(0xffffffffu, claim);
+                if (claimers) {   // warp-uniform
+                    unsigned long long groups_now = 0;
+                    if (lane == 0) groups_now = *reinterpret_cast<volatile unsigned long long*>(t.num_groups);
+                    groups_now = __shfl_sync(0xffffffffu, groups_now, 0);
+                    bool inserted = false;
+                    if (claim) {
+                        if (groups_now + __popc(claimers & ((1u << lane) - 1u)) >= (unsigned long long) t.max_groups) {
+                            replay_append(p.replay, base + (j / 2) * 512 + (j & 1));
+                            sel[j] = false;
+                            pend[j] = false;
+                        } else {
+                            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(t.keys + slot[j]),
+                                                                     (unsigned long long) GT_EMPTY, (unsigned long long) key[j]);
+                            inserted = old == GT_EMPTY;
+                            if (inserted || old == key[j]) pend[j] = false;
+                            else slot[j] = (int64_t) (((uint64_t) slot[j] + 1) & mask);   // another key took it
+                        }
+                    }
+                    const unsigned won = __ballot_sync(0xffffffffu, inserted);
+                    if (lane == 0 && won) atomicAdd(t.num_groups, (unsigned long long) __popc(won));
+                }
+                if (pend[j] && !claim) {
+                    if (seen[j] == key[j]) pend[j] = false;
+                    else slot[j] = (int64_t) (((uint64_t) slot[j] + 1) & mask);
+                }
+                more = more || pend[j];
+            }
+            if (!__any_sync(0xffffffffu, more)) break;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (pend[j]) {   // every slot visited: cannot happen below the load limit, but no row may be lost
+                replay_append(p.replay, base + (j / 2) * 512 + (j & 1));
+                sel[j] = false;
+            }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (sel[j]) atomicAdd(reinterpret_cast<unsigned long long*>(t.count_star + slot[j]), 1ULL);
+        for (int f = 0; f < p.n_funcs; ++f) {
+            const FuncSpec spec = p.specs[f];
+            if (spec.acc == ACC_NONE) continue;
+            const Col& vc = p.vals[f];
+            uint64_t v[R];
+            bool ok[R];
+            if (spec.acc == ACC_SUM_F64 && vc.dtype == VK_F64 && vc.validity == nullptr) {
+                // the common shape, free of per-row switches so that the R loads issue back to back
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    ok[j] = sel[j];
+                    v[j] = 0;
+                    if (sel[j]) v[j] = reinterpret_cast<const uint64_t*>(vc.data)[base + (j / 2) * 512 + (j & 1)];
+                }
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    if (ok[j]) atomicAdd(reinterpret_cast<double*>(t.acc_lo[f] + slot[j]), __longlong_as_double((long long) v[j]));
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int64_t i = base + (j / 2) * 512 + (j & 1);
+                ok[j] = false;
+                v[j] = 0;
+                if (!sel[j]) continue;
+                if (!col_valid(vc, i)) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(t.nnull[f] + slot[j]), 1ULL);
+                    continue;
+                }
+                if (spec.acc == ACC_COUNT) continue;
+                ok[j] = true;
+                v[j] = acc_load(spec, vc, i);
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+                if (ok[j]) acc_update_global(t, f, spec, slot[j], v[j]);
+        }
+    }
+    count_selected(p, n_selected);
+}
+
+// One launch: as many CTAs as are resident at once (the tile loop is persistent).
+static int launch_wide(const GenParams& gp, int sms, cudaStream_t s) {
+    constexpr int R = 4;
+    const int64_t tiles = (gp.n - gp.row_begin + 256 * R - 1) / (256 * R);
+    auto go = [&](auto kernel) -> int {
+        static int per_sm = 0;   // same for every device of this architecture
+        if (per_sm == 0) {
+            int b = 0;
+            VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, 256, 0));
+            per_sm = b > 0 ? b : 1;
+        }
+        const int64_t cap = (int64_t) sms * per_sm;
+        kernel<<<(unsigned) (tiles < cap ? tiles : cap), 256, 0, s>>>(gp);
+        VK_CHECK_LAUNCH("agg_wide_kernel");
+        return VK_OK;
+    };
+    switch (gp.pk) {
+        case PK_NONE: return go(agg_wide_kernel<PK_NONE, R>);
+        case PK_MASK: return go(agg_wide_kernel<PK_MASK, R>);
+        case PK_F64_VEC: return go(agg_wide_kernel<PK_F64_VEC, R>);
+        case PK_I64_VEC: return go(agg_wide_kernel<PK_I64_VEC, R>);
+        default: return go(agg_wide_kernel<PK_GENERIC, R>);
     }
 }
 
@@ -678,6 +905,7 @@ struct VkAgg {
     bool fast_warps_fixed = false;
     int fast_direct_policy = 1;       // 1: use direct (key - base) group ids when the key range allows, 0: always hash
     int64_t learn_rows = (int64_t) 1 << 20;   // rows of the learning launch
+    int wide_rows = 1;                        // option AGG_WIDE
     // hash mode: read-only cuckoo dictionary of the keys seen so far (built by the host after the learning
     // launch, vk_agg_fast.cuh); rows with other keys go to the global table
     bool dict_ready = false, dict_failed = false;
@@ -697,6 +925,12 @@ struct VkAgg {
     bool fast_disabled = false;       // cardinality turned out too high for the shared-memory table
     uint64_t fast_rows_seen = 0, fast_spilled = 0;
     int64_t fast_groups_seen = 0;
+    // global-table path while the number of groups is still rising: chunks grow geometrically and the
+    // table is sized at every chunk boundary from an estimate of the final number of groups
+    bool sizing = true;
+    int64_t rows_seen = 0;            // rows of every update so far
+    int64_t sized_groups = 0;         // groups / selected rows at the last estimate
+    uint64_t sized_selected = 0;
     // optional per-launch timing of the update kernels (bench.py roofline): events are
     // recorded on the launch stream and resolved lazily, so profiling adds no sync
     bool profile = false;
@@ -852,6 +1086,30 @@ int grow_table(VkAgg* a, int64_t groups_now, int64_t need_free, cudaStream_t s) 
     free_table(&a->t, s);
     a->t = nt;
     return VK_OK;
+}
+
+// Number of distinct keys behind (selected rows n, groups g so far) if the keys are drawn evenly from G
+// values: g = G (1 - exp(-n / G)).  Solved for x = n / G by bisection on (1 - exp(-x)) / x = g / n.  Skewed
+// keys make this an under-estimate (the caller treats it as a lower bound and keeps the replay list as the
+// safety net); g == n gives no upper bound at all and returns 0.
+double estimate_groups(double n, double g) {
+    if (g <= 0 || n <= 0) return 0;
+    if (g >= n) return 0;
+    const double r = g / n;
+    double lo = 1e-9, hi = 64.0;
+    for (int it = 0; it < 60; ++it) {
+        const double x = 0.5 * (lo + hi);
+        if ((1.0 - exp(-x)) / x > r) lo = x;
+        else hi = x;
+    }
+    return n / (0.5 * (lo + hi));
+}
+
+// Bytes of one table slot (key, row counter, per function: accumulator lanes + NULL counter).
+int64_t slot_bytes(const VkAgg* a) {
+    int64_t b = a->n_keys == 1 ? 16 : 8 * a->n_keys + 16;
+    for (int f = 0; f < a->n_funcs; ++f) b += a->specs[f].acc == ACC_SUM_I128 ? 24 : 16;
+    return b;
 }
 
 // Replay lists are sized for the worst case of a whole chunk (up to 4 GB for a 1e9-row batch)
@@ -1253,6 +1511,7 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
     a->match_policy = (int) opt(OPT_AGG_ENTRY);
     if (a->match_policy < 0 || a->match_policy > 2) a->match_policy = 1;
     if (opt(OPT_AGG_NOFAST)) a->fast_disabled = true;
+    a->wide_rows = (int) opt(OPT_AGG_WIDE);
     a->learn_rows = (int64_t) 1 << (opt(OPT_AGG_LEARN_LOG2) < 10 ? 10 : (opt(OPT_AGG_LEARN_LOG2) > 30 ? 30 : opt(OPT_AGG_LEARN_LOG2)));
     const int rc = ctr_acquire(a);
     if (rc != VK_OK) { delete a; return rc; }
@@ -1538,6 +1797,13 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             const int64_t learn = free_slots < a->learn_rows ? free_slots : a->learn_rows;
             if (chunk > learn) chunk = learn;
         }
+        // global-table path, groups still rising: no more than 8 x the rows seen so far in one launch, so that
+        // a table that turns out too small is found out (and sized from an estimate) before most rows arrive
+        const bool sizing = !fast && a->sizing;
+        if (sizing) {
+            const int64_t lim = a->rows_seen < ((int64_t) 1 << 17) ? ((int64_t) 1 << 20) : 8 * a->rows_seen;
+            if (chunk > lim) chunk = lim;
+        }
         if (chunk > free_slots) {
             uint64_t want = (uint64_t) (chunk - free_slots);
             if (want > list_max) want = list_max;
@@ -1665,13 +1931,19 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             a->last_path = 2;
             int64_t need = (chunk + 255) / 256, capb = (int64_t) sms * 8;
             const int span = prof_begin(a, s, chunk, 2);
-            agg_general_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(gp);
+            // single-key tables: several rows per thread, the loads of each stage issued together
+            if (a->t.single && a->wide_rows != 0) rc = launch_wide(gp, sms, s);
+            else {
+                agg_general_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(gp);
+                VK_CHECK_LAUNCH("agg_general_kernel");
+            }
             prof_end(a, s, span);
-            VK_CHECK_LAUNCH("agg_general_kernel");
+            if (rc != VK_OK) return rc;
             a->groups_ub += chunk;
         }
 
-        if (may_fail || (fast && a->fast_rows_seen < ((uint64_t) 1 << 20))) {
+        a->rows_seen += chunk;
+        if (may_fail || sizing || (fast && a->fast_rows_seen < ((uint64_t) 1 << 20))) {
             // rows may have been deferred (or we are still learning the cardinality)
             if (fast && a->hot_policy == 1 && plan.sumf64) {
                 // key skew so far: the largest group's share of the selected rows (one scan of the table)
@@ -1720,6 +1992,42 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 if (rc != VK_OK) return rc;
             }
             if (fast) configure_fast(a->fast_groups_seen);
+            if (!fast && a->sizing) {
+                // counters as of the end of this chunk (the replay loop may have moved them)
+                rc = read_counters(a, s);
+                if (rc != VK_OK) return rc;
+                const int64_t groups = (int64_t) a->h_ctr[CTR_GROUPS];
+                const uint64_t selected = a->h_ctr[CTR_SELECTED] + a->fast_spilled;
+                const int64_t new_groups = groups - a->sized_groups;
+                const uint64_t new_selected = selected - a->sized_selected;
+                a->groups_ub = groups;
+                if (sizing && (uint64_t) new_groups * 64 < new_selected) {
+                    a->sizing = false;   // fewer than 1 row in 64 opened a group: the table has seen most keys
+                } else if (pos + chunk < n_rows && selected > 0) {
+                    const double left = (double) (n_rows - pos - chunk) * ((double) selected / (double) a->rows_seen);
+                    double est = estimate_groups((double) selected, (double) groups);
+                    if (est <= 0 || est > (double) groups + left) est = (double) groups + left;   // every row left a new group
+                    // 2 % over the estimate (its own error is a few tenths of a percent; a table one doubling larger
+                    // than needed costs L2 residency: 1e6 groups fit the 2 Mi-slot table, 48 MB, and must stay there)
+                    int64_t want = (int64_t) (est * 1.02);
+                    // never more than a third of the free memory in one step
+                    if (want > a->t.max_groups && want * 2 >= ((int64_t) 1 << 26)) {
+                        size_t fr = 0, tot = 0;
+                        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+                            const int64_t fit = (int64_t) (fr / 3) / slot_bytes(a) / 2;   // groups at the load limit
+                            if (want > fit) want = fit;
+                        }
+                    }
+                    VK_DBG("sizing: groups=%lld selected=%llu estimate=%.0f want=%lld max_groups=%lld", (long long) groups,
+                           (unsigned long long) selected, est, (long long) want, (long long) a->t.max_groups);
+                    if (want > a->t.max_groups) {
+                        rc = grow_table(a, groups, want - groups, s);
+                        if (rc != VK_OK) return rc;
+                    }
+                }
+                a->sized_groups = groups;
+                a->sized_selected = selected;
+            }
         }
         pos += chunk;
     }
