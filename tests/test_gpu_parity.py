@@ -223,6 +223,81 @@ def test_generic_aggregate_random_vs_compiled_reference(vb):
                             float_exact_cols=["mv"])
 
 
+def test_string_min_max_with_numeric_keys_vs_compiled_reference(vb):
+    """MIN / MAX / COUNT over a string column under every aggregate class (StringMinMaxFunc,
+    agg_funcs.h:219-261): rank codes reduced on the device batch by batch, winners merged on the host.
+    NULL strings, a group whose strings are all NULL, NaN keys, many batches."""
+    from oracle import ref
+    lib = ref.ref_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref is not built")
+    rng = np.random.default_rng(11)
+    n = 60_000
+    words = np.array(["pear", "apple", "fig", "", "Apple", "zucchini", "fig tree", "\u00e9clair", "apple pie"], dtype=object)
+    k = rng.integers(0, 40, n).astype(np.int64)
+    strings = words[rng.integers(0, len(words), n)]
+    null_s = rng.random(n) < 0.15
+    null_s[k == 7] = True                      # a group whose strings are all NULL
+    f = rng.integers(0, 6, n).astype(np.float64)
+    f[rng.random(n) < 0.1] = np.nan
+    table = pa.table({
+        "k": pa.array(k),          # (the compiled reference's numerical classes crash on NULL keys: none here)
+        "j": pa.array(rng.integers(0, 3, n).astype(np.int32)),
+        "f": pa.array(f),
+        "t": pa.array(strings, type=pa.string(), mask=null_s),
+        "v": pa.array(rng.normal(0, 10, n)),
+    })
+    funcs = [("COUNT_STAR", "", "c"), ("MIN", "t", "mt"), ("MAX", "t", "xt"), ("COUNT", "t", "ct"), ("SUM", "v", "sv")]
+    for cls, gb in (("SingleNumericalHashAggregate", ["k"]), ("SingleNumericalHashAggregate", ["f"]),
+                    ("MultiNumericalHashAggregate", ["k", "j"]), ("OneGroupAggregate", [])):
+        mk = lambda m: (getattr(m, cls)([m.AggFuncDef(getattr(m.AggFuncType, a), c, o) for a, c, o in funcs]) if not gb else
+                        getattr(m, cls)(gb, gb, [m.AggFuncDef(getattr(m.AggFuncType, a), c, o) for a, c, o in funcs]))
+        got_agg = mk(vb.vinum_lib)
+        want_agg = mk(lib) if gb else None     # the compiled reference's OneGroupAggregate crashes on a string MIN
+        for b in table.to_batches(max_chunksize=9000):
+            if want_agg is not None:
+                want_agg.next(b)
+            got_agg.next(b)
+        got = got_agg.result()
+        if gb:
+            assert_tables_match(got, want_agg.result(), key_cols=gb, rtol=FLOAT_RTOL)
+        else:
+            import pyarrow.compute as pc
+            assert got.column("mt").to_pylist() == [pc.min(table.column("t")).as_py()]
+            assert got.column("xt").to_pylist() == [pc.max(table.column("t")).as_py()]
+            assert got.column("ct").to_pylist() == [len(table) - table.column("t").null_count]
+
+
+def test_sql_string_min_max(vb):
+    """The same through Table.sql, with a WHERE (the fused predicate applies to the rank-code aggregate too)
+    and a string GROUP BY key."""
+    import pyarrow.compute as pc
+    rng = np.random.default_rng(12)
+    n = 200_003
+    words = np.array([f"w{i:04d}" for i in range(3000)], dtype=object)
+    table = pa.table({
+        "k": rng.integers(0, 500, n).astype(np.int64),
+        "g": pa.array(np.array(["x", "y", "z"], dtype=object)[rng.integers(0, 3, n)], type=pa.string()),
+        "t": pa.array(words[rng.integers(0, len(words), n)], type=pa.string(), mask=rng.random(n) < 0.1),
+        "p": rng.random(n),
+    })
+    tbl = vb.Table.from_arrow(table)
+    kept = table.filter(pc.greater(table.column("p"), 0.3))
+    got = tbl.sql("SELECT k, MIN(t) AS mn, MAX(t) AS mx, COUNT(t) AS c FROM t WHERE p > 0.3 GROUP BY k ORDER BY k").to_arrow()
+    want = kept.group_by("k", use_threads=False).aggregate([("t", "min"), ("t", "max"), ("t", "count")]).sort_by("k")
+    assert got.column("k").to_pylist() == want.column("k").to_pylist()
+    assert got.column("mn").to_pylist() == want.column("t_min").to_pylist()
+    assert got.column("mx").to_pylist() == want.column("t_max").to_pylist()
+    assert got.column("c").to_pylist() == want.column("t_count").to_pylist()
+    got = tbl.sql("SELECT g, MAX(t) AS mx FROM t GROUP BY g ORDER BY g").to_arrow()
+    want = table.group_by("g", use_threads=False).aggregate([("t", "max")]).sort_by("g")
+    assert got.column("mx").to_pylist() == want.column("t_max").to_pylist()
+    got = tbl.sql("SELECT MIN(t) AS mn, MAX(t) AS mx FROM t WHERE p < 0.001").to_arrow()
+    few = table.filter(pc.less(table.column("p"), 0.001))
+    assert got.column("mn").to_pylist() == [pc.min(few.column("t")).as_py()]
+    assert got.column("mx").to_pylist() == [pc.max(few.column("t")).as_py()]
+
+
 @pytest.mark.parametrize("case", MAN["agg"], ids=lambda c: f"{c['table']}.{c['name']}")
 def test_aggregate_matches_reference_fixture(vb, case):
     table = read_arrow(f"{case['table']}.in.arrow")

@@ -31,6 +31,7 @@ import pyarrow.compute as pc
 from .. import _lib as L
 from .. import ops
 from ..aggregate import Aggregator
+from ..strings import StringMinMax
 from ..device import DeviceBatch, DeviceColumn, Stream, default_stream, vk_dtype_of
 from .ast import (NUMPY_AGG_MAPPING, Column, Expression, Literal, Node, Op, Query, SortOrder,
                   contains_aggregate, is_aggregate_call, walk)
@@ -680,7 +681,7 @@ class Engine:
                     state.dicts.append(None)
                 key_vals.append(v)
 
-        specs, agg_vals = [], []
+        specs, agg_vals, str_calls = [], [], []
         for call in state.agg_calls:
             fname = NUMPY_AGG_MAPPING.get(call.function_name.lower(), call.function_name.lower())
             code = _AGG_CODES[fname]
@@ -694,7 +695,12 @@ class Engine:
             if not _is_col(v):
                 v = self._from_host(np.full(frame.n, v))
             if isinstance(v, HostColumn):
-                if code != L.AGG_COUNT:
+                if code in (L.AGG_MIN, L.AGG_MAX):
+                    # rank codes of this batch reduced on the device, winners merged at finish (vinum_b200.strings);
+                    # the slot in the main aggregate is a validity COUNT that _agg_finish replaces
+                    str_calls.append((len(specs), code == L.AGG_MIN, v))
+                    code = L.AGG_COUNT
+                elif code != L.AGG_COUNT:
                     raise OperatorError(f"{fname}() over a string column is not on the device path")
                 # COUNT(str): only the validity matters
                 valid = pc.is_valid(v.arr)
@@ -710,6 +716,10 @@ class Engine:
             state.agg.update(key_vals, agg_vals, pred, st)
         else:
             state.agg.update_count_rows(frame.n, pred, st)
+        for i, is_min, v in str_calls:
+            if i not in state.str_minmax:
+                state.str_minmax[i] = StringMinMax([k.arrow_type for k in key_vals], is_min, v.arr.type)
+            state.str_minmax[i].update(key_vals, v.arr, pred, st)
         state.batches += 1
         if keep:
             st.sync()   # the async copies read host arrays that die with this batch
@@ -718,6 +728,8 @@ class Engine:
         """AggregateOperator result (aggregate.py:122): finalise, read the groups back, give
         dictionary-coded / boolean keys their user types again."""
         if self.exchange is not None:
+            if state.str_minmax:
+                raise OperatorError("sharded execution: MIN / MAX over a string column is not implemented")
             if any(kind is not None for kind in state.key_kind):
                 raise OperatorError("sharded execution: GROUP BY over string / boolean keys needs a shared "
                                     "dictionary across ranks, which is not implemented")
@@ -729,6 +741,9 @@ class Engine:
             keys_out, aggs_out = state.agg.result_arrays(self.st)
             self.stats["agg_path"] = state.agg.last_path
         self.stats["agg_batches"] = state.batches
+        aggs_out = list(aggs_out)
+        for i, smm in state.str_minmax.items():
+            aggs_out[i] = smm.result(keys_out, len(aggs_out[i]))
         out = Frame(len(aggs_out[0]) if aggs_out else (len(keys_out[0]) if keys_out else 1))
         resolved: Dict = {}
         for i, (g, arr) in enumerate(zip(state.group_exprs, keys_out)):
@@ -838,6 +853,7 @@ class _AggState:
     def __init__(self, q: Query):
         self.agg: Optional[Aggregator] = None
         self.batches = 0
+        self.str_minmax: Dict[int, StringMinMax] = {}    # aggregate call index -> MIN / MAX over a string column
         self.key_kind: List[Optional[str]] = []
         self.dicts: List = []
         self.group_exprs: List[Node] = []

@@ -27,6 +27,7 @@ import pyarrow.compute as pc
 
 from . import _lib as L
 from .aggregate import Aggregator
+from .strings import StringMinMax
 from .device import DeviceBatch, DeviceColumn, Stream, default_stream, vk_dtype_of
 from . import ops
 
@@ -144,6 +145,39 @@ class _BaseAggregate:
         self._agg: Optional[Aggregator] = None
         self._key_types: List[pa.DataType] = []
         self._stream = default_stream()
+        self._str_funcs: List[int] = []             # indices of MIN / MAX functions over string columns
+        self._str_state: dict = {}                  # function index -> StringMinMax
+
+    @staticmethod
+    def _is_str(t) -> bool:
+        return pa.types.is_string(t) or pa.types.is_large_string(t)
+
+    @staticmethod
+    def _validity_column(arr) -> pa.Array:
+        """What COUNT(string column) needs on the device: a uint8 column with the strings' validity."""
+        import numpy as np
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks()
+        mask = arr.is_null().to_numpy(zero_copy_only=False) if arr.null_count else None
+        return pa.array(np.zeros(len(arr), dtype=np.uint8), mask=mask)
+
+    def _string_spec(self, i: int, f: "AggFuncDef"):
+        """Device spec of function i over a STRING column (AggFuncFactory's string cases,
+        agg_func_factory.cpp: COUNT and MIN / MAX only)."""
+        if int(f.func) == L.AGG_COUNT:
+            return (L.AGG_COUNT, pa.uint8())             # validity only
+        if int(f.func) in (L.AGG_MIN, L.AGG_MAX):
+            self._str_funcs.append(i)
+            return (L.AGG_COUNT, pa.uint8())             # placeholder slot, replaced at result()
+        raise RuntimeError("Column data type is not supported by sum()/avg().")
+
+    def _update_strings(self, keys, batch, schema, st) -> None:
+        """String MIN / MAX of one host batch: the device groups it by the same keys and reduces rank codes."""
+        for i in self._str_funcs:
+            f = self._funcs[i]
+            if i not in self._str_state:
+                self._str_state[i] = StringMinMax(self._key_types, int(f.func) == L.AGG_MIN, schema.field(f.column_name).type)
+            self._str_state[i].update(keys, batch.column(schema.get_field_index(f.column_name)), None, st)
 
     # -- BaseAggregate::EnsureInitAggFuncs, base_aggregate.cpp:91-119
     def _ensure_init(self, schema: pa.Schema) -> None:
@@ -154,11 +188,12 @@ class _BaseAggregate:
                 raise RuntimeError("Column not found: " + name)  # base_aggregate.cpp:121-131
         self._key_types = [schema.field(n).type for n in self._groupby_cols]
         specs = []
-        for f in self._funcs:
+        for i, f in enumerate(self._funcs):
             if f.column_name:
                 if schema.get_field_index(f.column_name) == -1:
                     raise RuntimeError("Column not found: " + f.column_name)
-                specs.append((int(f.func), schema.field(f.column_name).type))
+                t = schema.field(f.column_name).type
+                specs.append(self._string_spec(i, f) if self._is_str(t) else (int(f.func), t))
             else:
                 specs.append((int(f.func), None))
         self._check_key_types(self._key_types)
@@ -223,12 +258,28 @@ class _BaseAggregate:
                 cache[name] = _column_to_device(batch, name, st)
             return cache[name]
 
+        def value(f):
+            if not f.column_name:
+                return None
+            if not isinstance(batch, DeviceBatch) and self._is_str(batch.schema.field(f.column_name).type):
+                key = "\0validity:" + f.column_name
+                if key not in cache:
+                    keep.append(self._validity_column(batch.column(batch.schema.get_field_index(f.column_name))))
+                    cache[key] = DeviceColumn.from_arrow(keep[-1], st)
+                return cache[key]
+            return col(f.column_name)
+
+        keep = []
         keys = [col(n) for n in self._groupby_cols]
-        values = [col(f.column_name) if f.column_name else None for f in self._funcs]
+        values = [value(f) for f in self._funcs]
         if not keys and all(v is None for v in values):
             self._agg.update_count_rows(batch.num_rows, None, st)
         else:
             self._agg.update(keys, values, None, st)
+        if self._str_funcs:
+            if isinstance(batch, DeviceBatch):
+                raise TypeError("string columns do not live on the device: MIN / MAX over them takes host batches")
+            self._update_strings(keys, batch, batch.schema, st)
         if not isinstance(batch, DeviceBatch):
             st.sync()  # the async copies read the caller's Arrow buffers
 
@@ -239,6 +290,9 @@ class _BaseAggregate:
             # schema information (base_aggregate.cpp:47-68)
             return pa.RecordBatch.from_arrays([], names=[])
         key_arrays, agg_arrays = self._agg.result_arrays(self._stream)
+        agg_arrays = list(agg_arrays)
+        for i in self._str_funcs:
+            agg_arrays[i] = self._str_state[i].result(key_arrays, len(agg_arrays[i]))
         arrays, names = [], []
         for name in self._agg_cols:  # GROUP_BUILDER columns first, base_aggregate.cpp:100-108
             arrays.append(key_arrays[self._groupby_cols.index(name)])
@@ -268,8 +322,9 @@ class GenericHashAggregate(_BaseAggregate):
     as long as the operator, and the device groups by the int32 codes (NULL stays NULL);
     boolean keys are grouped as uint8.  Aggregates over numeric columns run on the device as
     usual.  COUNT over a string column only needs its validity; MIN / MAX over strings
-    (StringMinMaxFunc, agg_funcs.h:219-261) are a host step (pyarrow's hash aggregate per
-    batch, merged at result()) joined to the device result by key."""
+    (StringMinMaxFunc, agg_funcs.h:219-261) reduce order-preserving rank codes on the device,
+    batch by batch (vinum_b200.strings.StringMinMax); only groups x batches strings are merged
+    on the host at result()."""
     _min_keys = 1
 
     def __init__(self, groupby_cols, agg_cols, agg_funcs):
@@ -277,16 +332,10 @@ class GenericHashAggregate(_BaseAggregate):
         self._key_kind: List[str] = []
         self._dicts: List[Optional[dict]] = []      # string key -> {value: code}
         self._dict_values: List[Optional[list]] = []
-        self._str_funcs: List[int] = []             # indices of MIN/MAX functions over string columns
-        self._str_partials: List[pa.Table] = []
         self._user_key_types: List[pa.DataType] = []
 
     def _check_key_types(self, types) -> None:
         return
-
-    @staticmethod
-    def _is_str(t) -> bool:
-        return pa.types.is_string(t) or pa.types.is_large_string(t)
 
     def _ensure_init(self, schema: pa.Schema) -> None:
         if self._agg is not None:
@@ -322,16 +371,7 @@ class GenericHashAggregate(_BaseAggregate):
             if schema.get_field_index(f.column_name) == -1:
                 raise RuntimeError("Column not found: " + f.column_name)
             t = schema.field(f.column_name).type
-            if self._is_str(t):
-                if int(f.func) == L.AGG_COUNT:
-                    specs.append((L.AGG_COUNT, pa.uint8()))         # validity only
-                elif int(f.func) in (L.AGG_MIN, L.AGG_MAX):
-                    self._str_funcs.append(i)
-                    specs.append((L.AGG_COUNT, pa.uint8()))         # placeholder slot, replaced at result()
-                else:
-                    raise RuntimeError("Column data type is not supported by sum()/avg().")
-            else:
-                specs.append((int(f.func), t))
+            specs.append(self._string_spec(i, f) if self._is_str(t) else (int(f.func), t))
         self._key_types = dev_types
         self._agg = Aggregator(dev_types, specs)
 
@@ -362,14 +402,6 @@ class GenericHashAggregate(_BaseAggregate):
         return pa.array(mapping[local_codes] if len(local) else np.zeros(len(arr), dtype=np.int32), type=pa.int32(),
                         mask=null_mask)
 
-    @staticmethod
-    def _validity_column(arr) -> pa.Array:
-        import numpy as np
-        if isinstance(arr, pa.ChunkedArray):
-            arr = arr.combine_chunks()
-        mask = arr.is_null().to_numpy(zero_copy_only=False) if arr.null_count else None
-        return pa.array(np.zeros(len(arr), dtype=np.uint8), mask=mask)
-
     def next(self, batch) -> None:
         batch = _as_batch_like(batch)
         if isinstance(batch, DeviceBatch):
@@ -394,15 +426,7 @@ class GenericHashAggregate(_BaseAggregate):
             keep.append(arr)
             values.append(DeviceColumn.from_arrow(arr, st))
         self._agg.update(keys, values, None, st)
-        if self._str_funcs:
-            # string MIN / MAX: host hash aggregate of this batch, keyed by the same columns
-            cols = {f"k{k}": batch.column(schema.get_field_index(n)) for k, n in enumerate(self._groupby_cols)}
-            aggs = []
-            for i in self._str_funcs:
-                cols[f"v{i}"] = batch.column(schema.get_field_index(self._funcs[i].column_name))
-                aggs.append((f"v{i}", "min" if int(self._funcs[i].func) == L.AGG_MIN else "max"))
-            part = pa.table(cols).group_by([f"k{k}" for k in range(len(self._groupby_cols))], use_threads=False).aggregate(aggs)
-            self._str_partials.append(part)
+        self._update_strings(keys, batch, schema, st)
         st.sync()
 
     def result(self) -> pa.RecordBatch:
@@ -419,24 +443,9 @@ class GenericHashAggregate(_BaseAggregate):
                 arr = arr.cast(pa.bool_())
             user_keys.append(arr)
         agg_arrays = list(agg_arrays)
-        if self._str_funcs:
-            nk = len(self._groupby_cols)
-            merged = pa.concat_tables(self._str_partials)
-            names = merged.schema.names
-            val_cols = [n for n in names if not (n.startswith("k") and n[1:].isdigit())]
-            final = merged.group_by([f"k{k}" for k in range(nk)], use_threads=False).aggregate(
-                [(n, "min" if n.endswith("_min") else "max") for n in val_cols])
-            lookup = {}
-            fk = [final.column(f"k{k}").to_pylist() for k in range(nk)]
-            for r in range(final.num_rows):
-                lookup[tuple(col[r] for col in fk)] = r
-            uk = [a.to_pylist() for a in user_keys]
-            order = [lookup[tuple(col[r] for col in uk)] for r in range(len(uk[0]))]
-            take_idx = pa.array(order, type=pa.int64())
-            for i in self._str_funcs:
-                kind = "min" if int(self._funcs[i].func) == L.AGG_MIN else "max"
-                col = final.column(f"v{i}_{kind}_{kind}").combine_chunks()
-                agg_arrays[i] = col.take(take_idx)
+        for i in self._str_funcs:
+            # joined by the DEVICE keys (dictionary codes, uint8 booleans), which mean the same in every batch
+            agg_arrays[i] = self._str_state[i].result(key_arrays, len(agg_arrays[i]))
         arrays, names = [], []
         for name in self._agg_cols:
             arrays.append(user_keys[self._groupby_cols.index(name)])
