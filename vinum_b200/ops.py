@@ -21,7 +21,7 @@ Scalar = Union[int, float, bool, np.generic]
 
 CMP_OPS = {"==": L.EQ, "=": L.EQ, "!=": L.NE, "<>": L.NE, ">": L.GT, ">=": L.GE, "<": L.LT, "<=": L.LE}
 ARITH_OPS = {"+": L.ADD, "-": L.SUB, "*": L.MUL, "/": L.DIV, "%": L.MOD, "&": L.BITAND, "|": L.BITOR,
-             "#": L.BITXOR, "^": L.BITXOR, "neg": L.NEG, "~": L.BITNOT}
+             "#": L.BITXOR, "neg": L.NEG, "~": L.BITNOT}
 _NUMPY_UFUNC = {L.ADD: np.add, L.SUB: np.subtract, L.MUL: np.multiply, L.DIV: np.divide, L.MOD: np.mod,
                 L.BITAND: np.bitwise_and, L.BITOR: np.bitwise_or, L.BITXOR: np.bitwise_xor,
                 L.NEG: np.negative, L.BITNOT: np.invert}
