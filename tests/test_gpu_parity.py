@@ -324,6 +324,7 @@ AGG_PATHS = {
     "hash_split_entries": (dict(AGG_DIRECT=0, AGG_ENTRY=2), 1),
     "general_kernel": (dict(AGG_NOFAST=1), 2),
     "general_kernel_one_row": (dict(AGG_NOFAST=1, AGG_WIDE=0), 2),
+    "partitioned": (dict(AGG_NOFAST=1, AGG_PARTITION=2), 4),
 }
 
 

@@ -414,7 +414,7 @@ def test_sample_sort_plan_over_gloo_world2(tmp_path):
 def test_every_option_has_a_default_and_a_name():
     import vinum_b200 as vb
     names = ("FILTER_STAGE FILTER_PF CMP_FAST ARITH_FAST ONEGROUP_FAST SORT_FUSE_LAST SORT_PREP "
-             "AGG_LOG2S AGG_PF AGG_WARPS AGG_DIRECT AGG_DICT AGG_ENTRY AGG_HOT AGG_NOFAST AGG_WIDE AGG_LEARN_LOG2 LIST_LOG2 DEBUG INGEST_STAGED "
+             "AGG_LOG2S AGG_PF AGG_WARPS AGG_DIRECT AGG_DICT AGG_ENTRY AGG_HOT AGG_NOFAST AGG_WIDE AGG_PARTITION AGG_LEARN_LOG2 LIST_LOG2 DEBUG INGEST_STAGED "
              "INGEST_THREADS INGEST_PIECE_KB").split()
     for n in names:
         assert isinstance(vb.get_option(n), int)

@@ -9,6 +9,7 @@ the reference's (`agg_func_factory.cpp:13-329`).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -38,6 +39,37 @@ def _pinned_scratch(nbytes: int):
         buf = PinnedBuffer(max(nbytes, 1 << 16))
         _PINNED_SCRATCH[key] = buf
     return buf
+
+
+# Large results (1e6 groups = 48 MB) are handed out as VIEWS of the page-locked block they were copied into: one more
+# host copy of the block costs more than the PCIe transfer.  The block goes back to this free list when the last view
+# of it dies (results of a later query then overwrite it), so a loop of queries pins memory once.
+_PINNED_POOL: list = []
+_PINNED_POOL_MAX = 8
+_PINNED_POOL_BYTES = 2 << 30
+_LARGE_RESULT = 4 << 20
+
+
+def _pinned_take(nbytes: int):
+    from .device import PinnedBuffer
+    best = None
+    for i, b in enumerate(_PINNED_POOL):
+        if b.nbytes >= nbytes and (best is None or b.nbytes < _PINNED_POOL[best].nbytes):
+            best = i
+    if best is not None:
+        try:
+            return _PINNED_POOL.pop(best)
+        except IndexError:      # another thread took it
+            pass
+    return PinnedBuffer(nbytes)
+
+
+def _pinned_give_back(buf) -> None:
+    # keep the large blocks (pinning 400 MB costs ~0.1 s, as does unpinning it): when the list is over its budget the
+    # SMALLEST block goes, never the one a loop of large queries is about to ask for again
+    _PINNED_POOL.append(buf)
+    while len(_PINNED_POOL) > _PINNED_POOL_MAX or (len(_PINNED_POOL) > 1 and sum(b.nbytes for b in _PINNED_POOL) > _PINNED_POOL_BYTES):
+        _PINNED_POOL.remove(min(_PINNED_POOL, key=lambda b: b.nbytes))
 
 
 def check_supported(func: int, t: Optional[pa.DataType]) -> None:
@@ -184,7 +216,8 @@ class Aggregator:
         cap = getattr(self, "_result_cap", 1024)
         while True:
             nbytes = int(L._lib.vk_agg_result_packed_bytes(nk, nf, cap))
-            host = _pinned_scratch(nbytes)
+            large = nbytes >= _LARGE_RESULT
+            host = _pinned_take(nbytes) if large else _pinned_scratch(nbytes)
             dev = DeviceBuffer(nbytes, st, zero=True)   # the whole block is copied back: no uninitialised padding
             lib.vk_agg_result_packed(self._h, cap, C.c_void_p(dev.ptr), st.ptr)
             lib.vk_memcpy_d2h(C.c_void_p(host.ptr), C.c_void_p(dev.ptr), nbytes, st.ptr)
@@ -192,13 +225,17 @@ class Aggregator:
                 lib.vk_memcpy_d2h(C.c_void_p(extra_d2h[0]), C.c_void_p(extra_d2h[1]), int(extra_d2h[2]), st.ptr)
             st.sync()
             raw = host.as_numpy(np.uint8, nbytes)
+            if large:
+                weakref.finalize(raw, _pinned_give_back, host)   # every view derived below keeps `raw` alive
             g = int(raw[:8].view(np.uint64)[0])
             if g <= cap:
                 break
             cap = 1 << (g - 1).bit_length()
         self._result_cap = max(1024, 1 << max(g - 1, 1).bit_length())
         words = 2 + (nk + 1 + 2 * nf) * cap
-        h64 = raw[:words * 8].view(np.uint64)[2:].reshape(nk + 1 + 2 * nf, cap)[:, :g].copy()
+        h64 = raw[:words * 8].view(np.uint64)[2:].reshape(nk + 1 + 2 * nf, cap)[:, :g]
+        if not large:
+            h64 = h64.copy()    # the small scratch block is reused by the next call
         h8 = raw[words * 8:words * 8 + (nk + nf) * cap].reshape(nk + nf, cap)[:, :g].astype(bool)
         return h64[:nk], h8[:nk], h64[nk], h64[nk + 1:nk + 1 + nf], h64[nk + 1 + nf:], h8[nk:]
 

@@ -357,6 +357,285 @@ static int launch_wide(const GenParams& gp, int sms, cudaStream_t s) {
     }
 }
 
+// ============================================================ partitioned aggregate (many groups)
+// With 1e6 and more groups the global table is a random-access target: three L2 (or, beyond ~1.5e6 groups,
+// DRAM) sectors per row, 27 ms at 1e6 groups and 167 ms at 8.4e6 for 1e9 rows.  Two sequential passes cost
+// less than that random traffic:
+//   scatter  every selected row's (key, row id) is appended to one of P buckets chosen by a hash of the key
+//            (one atomic on the bucket's cursor, one 16-byte store; the L2 merges neighbouring appends into
+//            full sectors);
+//   reduce   one CTA per bucket aggregates its rows in a SHARED-memory table with shared-memory atomics
+//            (a bucket holds ~S/4 groups by construction), gathering the value columns by row id, and
+//            flushes one update per group into the global table.
+// Nothing can be lost: a key's global slot is claimed BEFORE the key enters the CTA table, so the flush
+// cannot fail; a row whose group cannot be created (global table at its limit), or that does not fit its
+// bucket, goes to the replay list like in every other kernel; a bucket with more groups than its table
+// holds sends the extra rows straight to the global table.
+struct PartParams {
+    FastParams f;            // predicate, key, value columns, cells, global table, replay list
+    int log2p;               // buckets = 1 << log2p (one CTA table of the reduce pass each)
+    uint32_t cap;            // records per bucket
+    ulonglong2* recs;        // [P][cap] records {key, row id relative to the chunk}: ONE 16-byte store each (the scatter
+                             // pass is bound by the number of uncoalesced transactions, ~60 G/s on this part, not by bytes)
+    unsigned int* cursor;    // [P * 32]: one counter per 128-byte line (8 cursors per bucket, chosen by further hash bits, were
+                             // measured: no change, the pass is not bound by same-address atomics)
+    int log2s;               // reduce: slots of the CTA table
+};
+
+__device__ __forceinline__ uint32_t part_bucket(uint64_t key, int log2p) { return fast_hash32(key) >> (32 - log2p); }
+// Slot hash of the reduce pass: other multipliers than fast_hash32, whose top bits are equal within a bucket.
+__device__ __forceinline__ uint32_t part_slot_hash(uint64_t key) {
+    uint32_t x = ((uint32_t) key * 0xCC9E2D51u) ^ ((uint32_t) (key >> 32) * 0x1B873593u);
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 12;
+    x *= 0x297A2D39u;
+    return x ^ (x >> 15);
+}
+__device__ __forceinline__ uint64_t part_load_key(const FastParams& f, int64_t i) {
+    if (f.key_mode == 0) return reinterpret_cast<const uint64_t*>(f.key.data)[i];
+    return widen4(reinterpret_cast<const uint32_t*>(f.key.data)[i], f.key_mode == 1 ? 1 : 2);
+}
+__device__ __forceinline__ uint64_t part_load_val(const FastParams& f, int c, int64_t i) {
+    if (f.col_mode[c] == 0) return reinterpret_cast<const uint64_t*>(f.col[c].data)[i];
+    return widen4(reinterpret_cast<const uint32_t*>(f.col[c].data)[i], f.col_mode[c]);
+}
+__device__ __forceinline__ void part_global_row(const FastParams& f, uint64_t key, int64_t row) {
+    uint64_t v[FA_MAX_COLS] = {0, 0, 0};
+    for (int c = 0; c < f.n_cols; ++c) v[c] = part_load_val(f, c, row);
+    fast_global_row(f, key, v[0], v[1], v[2], row);
+}
+
+template <int PK>
+__global__ void __launch_bounds__(256) agg_part_scatter_kernel(const __grid_constant__ PartParams p) {
+    constexpr int R = 8;
+    constexpr int64_t TILE = 256 * R;
+    const FastParams& f = p.f;
+    const int64_t n_tiles = (f.n + TILE - 1) / TILE;
+    unsigned n_selected = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncwarp();
+        const int64_t base = tile * TILE + 2 * (int64_t) threadIdx.x;
+        const bool whole = (tile + 1) * TILE <= f.n;
+        bool sel[R];
+        if ((PK == PK_F64_VEC || PK == PK_I64_VEC) && whole) {
+            uint4 q[R / 2];
+#pragma unroll
+            for (int j = 0; j < R / 2; ++j) q[j] = ldg_stream16(f.pred.col.data + (base + j * 512) * 8);
+#pragma unroll
+            for (int j = 0; j < R / 2; ++j) {
+                if (PK == PK_F64_VEC) {
+                    const double c = __longlong_as_double((long long) f.pred.scalar.bits);
+                    sel[2 * j] = apply_cmp(f.pred.op, __hiloint2double(q[j].y, q[j].x), c);
+                    sel[2 * j + 1] = apply_cmp(f.pred.op, __hiloint2double(q[j].w, q[j].z), c);
+                } else {
+                    const int64_t c = (int64_t) f.pred.scalar.bits;
+                    sel[2 * j] = apply_cmp(f.pred.op, (int64_t) (((uint64_t) q[j].y << 32) | q[j].x), c);
+                    sel[2 * j + 1] = apply_cmp(f.pred.op, (int64_t) (((uint64_t) q[j].w << 32) | q[j].z), c);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; j += 2) pred_pair<PK>(f.pred, base + (j / 2) * 512, f.n, sel[j], sel[j + 1]);
+        }
+        uint64_t key[R];
+        if (whole && f.key_mode == 0) {   // key columns of the plan are 16-byte aligned (aligned_for_pairs)
+#pragma unroll
+            for (int j = 0; j < R / 2; ++j) {
+                const uint4 q = ldg_stream16(f.key.data + (base + j * 512) * 8);
+                key[2 * j] = u64_of(q.x, q.y);
+                key[2 * j + 1] = u64_of(q.z, q.w);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int64_t i = base + (j / 2) * 512 + (j & 1);
+                key[j] = sel[j] ? part_load_key(f, i) : 0;
+            }
+        }
+        uint32_t pos[R], bucket[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            n_selected += sel[j] ? 1u : 0u;
+            bucket[j] = part_bucket(key[j], p.log2p);
+            pos[j] = 0xFFFFFFFFu;
+            if (sel[j] && key[j] != GT_EMPTY) pos[j] = atomicAdd(p.cursor + (size_t) bucket[j] * 32, 1u);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (!sel[j]) continue;
+            const int64_t i = base + (j / 2) * 512 + (j & 1);
+            if (key[j] == GT_EMPTY) {
+                part_global_row(f, key[j], i);          // the key value that marks a free slot: its dedicated slot
+            } else if (pos[j] < p.cap) {
+                p.recs[(size_t) bucket[j] * p.cap + pos[j]] = make_ulonglong2(key[j], (unsigned long long) i);
+            } else {
+                replay_append(f.replay, i);             // bucket full (skewed keys): the replay pass takes the row
+            }
+        }
+    }
+    if (f.replay.selected != nullptr) {
+        __syncwarp();
+        n_selected = __reduce_add_sync(0xffffffffu, n_selected);
+        if ((threadIdx.x & 31) == 0 && n_selected) atomicAdd(f.replay.selected, (unsigned long long) n_selected);
+    }
+}
+
+// One record into the CTA table of the reduce pass.
+__device__ __forceinline__ void part_reduce_record(const FastParams& f, uint64_t* keys, uint64_t* cells, uint32_t* gslot, uint32_t* cnt,
+                                                   unsigned* s_groups, uint32_t S, uint64_t key, int64_t row, uint64_t v0, uint64_t v1, uint64_t v2) {
+    const uint32_t smask = S - 1, full = S - S / 4;
+    uint32_t slot = part_slot_hash(key) & smask;
+    int where = -1;   // >= 0: CTA slot, -1: CTA table full or probe chain too long, -2: no global slot
+    for (int probe = 0; probe < FA_MAXPROBE; ++probe) {
+        const uint64_t k = *reinterpret_cast<volatile uint64_t*>(keys + slot);
+        if (k == key) {
+            where = (int) slot;
+            break;
+        }
+        if (k == GT_EMPTY) {
+            if (*reinterpret_cast<volatile unsigned*>(s_groups) >= full) break;
+            // the global slot first: a key whose group cannot be created never enters the CTA table
+            const int64_t g = gt1_find_or_insert(f.table, key, false, hash_key1(key), f.row_limit);
+            if (g < 0) {
+                where = -2;
+                break;
+            }
+            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot),
+                                                     (unsigned long long) GT_EMPTY, (unsigned long long) key);
+            if (old == GT_EMPTY) {
+                gslot[slot] = (uint32_t) g;
+                atomicAdd(s_groups, 1u);
+                where = (int) slot;
+                break;
+            }
+            if (old == key) {
+                where = (int) slot;
+                break;
+            }
+        }
+        slot = (slot + 1) & smask;
+    }
+    if (where >= 0) {
+        atomicAdd(cnt + where, 1u);
+        for (int c = 0; c < f.n_cells; ++c) {
+            const FastCell cell = f.cell[c];
+            uint64_t* at = cells + (size_t) c * S + where;
+            const uint64_t x = cell.col == 0 ? v0 : (cell.col == 1 ? v1 : v2);   // (an indexed array would live in local memory)
+            if (cell.op == CELL_ADD_F64) atomicAdd(reinterpret_cast<double*>(at), __longlong_as_double((long long) x));
+            else if (cell.op == CELL_MAXORD)
+                atomicMax(reinterpret_cast<unsigned long long*>(at), (unsigned long long) ord_transform(cell.ord, cell.is_min, x));
+            else atomicAdd(reinterpret_cast<unsigned long long*>(at), (unsigned long long) x);
+        }
+    } else if (where == -2) {
+        replay_append(f.replay, row);
+    } else {
+        fast_global_row(f, key, v0, v1, v2, row);
+    }
+}
+
+constexpr int PART_THREADS = 1024;
+__global__ void __launch_bounds__(PART_THREADS) agg_part_reduce_kernel(const __grid_constant__ PartParams p) {
+    extern __shared__ __align__(16) uint8_t part_smem[];
+    __shared__ unsigned s_groups;
+    const FastParams& f = p.f;
+    const uint32_t S = 1u << p.log2s;
+    const int nc = f.n_cells;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(part_smem);
+    uint64_t* cells = keys + S;                                     // [nc][S]
+    uint32_t* gslot = reinterpret_cast<uint32_t*>(cells + (size_t) nc * S);
+    uint32_t* cnt = gslot + S;
+    const uint32_t n_buckets = 1u << p.log2p;
+    for (uint32_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+        uint32_t n_b = p.cursor[(size_t) b * 32];
+        if (n_b > p.cap) n_b = p.cap;
+        if (n_b == 0) continue;   // CTA-uniform
+        if (threadIdx.x == 0) s_groups = 0;
+        for (uint32_t s = threadIdx.x; s < S; s += PART_THREADS) {
+            keys[s] = GT_EMPTY;
+            cnt[s] = 0;
+            for (int c = 0; c < nc; ++c) cells[(size_t) c * S + s] = 0;
+        }
+        __syncthreads();
+        const ulonglong2* recs = p.recs + (size_t) b * p.cap;
+        // U records per thread and step: the U record loads, then the U x n_cols gathers, are in flight together
+        constexpr int U = 4;
+        for (uint32_t r0 = threadIdx.x; r0 < n_b; r0 += PART_THREADS * U) {
+            uint64_t key[U];
+            uint32_t row[U];
+            uint64_t v[U][FA_MAX_COLS];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t r = r0 + u * PART_THREADS;
+                key[u] = GT_EMPTY;   // no record
+                row[u] = 0;
+                if (r < n_b) {
+                    const ulonglong2 rec = recs[r];
+                    key[u] = rec.x;
+                    row[u] = (uint32_t) rec.y;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int c = 0; c < FA_MAX_COLS; ++c) v[u][c] = (c < f.n_cols && key[u] != GT_EMPTY) ? part_load_val(f, c, (int64_t) row[u]) : 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (key[u] == GT_EMPTY) continue;
+                part_reduce_record(f, keys, cells, gslot, cnt, &s_groups, S, key[u], (int64_t) row[u], v[u][0], v[u][1], v[u][2]);
+            }
+        }
+        __syncthreads();
+        for (uint32_t s = threadIdx.x; s < S; s += PART_THREADS) {
+            if (keys[s] == GT_EMPTY) continue;
+            uint64_t w[FA_MAX_CELLS] = {0, 0, 0};
+            for (int c = 0; c < nc; ++c) w[c] = cells[(size_t) c * S + s];
+            fast_global_update(f, (int64_t) gslot[s], (uint64_t) cnt[s], w);
+        }
+        __syncthreads();
+    }
+}
+
+// option AGG_PARTITION = 1: partition from this many (estimated) groups.  Measured (profiles/r02_tuning.md): at 1e6 groups the
+// table (48 MB) lives in L2 and the global-table kernel wins 16 ms to 30; at 8.4e6 it is DRAM-resident and loses 72 ms to 49
+constexpr int64_t PART_MIN_GROUPS = (int64_t) 1 << 21;
+constexpr int64_t PART_MAX_CHUNK = (int64_t) 1 << 27;    // rows per scatter + reduce round (bounds the scratch: 16 B per selected row)
+
+static int launch_part(const PartParams& pp, int pk, int sms, cudaStream_t s) {
+    const int64_t tiles = (pp.f.n + 2047) / 2048;
+    auto scatter = [&](auto kernel) -> int {
+        static int per_sm = 0;
+        if (per_sm == 0) {
+            int b = 0;
+            VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, 256, 0));
+            per_sm = b > 0 ? b : 1;
+        }
+        const int64_t cap = (int64_t) sms * per_sm;
+        kernel<<<(unsigned) (tiles < cap ? tiles : cap), 256, 0, s>>>(pp);
+        VK_CHECK_LAUNCH("agg_part_scatter_kernel");
+        return VK_OK;
+    };
+    int rc;
+    switch (pk) {
+        case PK_NONE: rc = scatter(agg_part_scatter_kernel<PK_NONE>); break;
+        case PK_MASK: rc = scatter(agg_part_scatter_kernel<PK_MASK>); break;
+        case PK_F64_VEC: rc = scatter(agg_part_scatter_kernel<PK_F64_VEC>); break;
+        case PK_I64_VEC: rc = scatter(agg_part_scatter_kernel<PK_I64_VEC>); break;
+        default: rc = scatter(agg_part_scatter_kernel<PK_GENERIC>); break;
+    }
+    if (rc != VK_OK) return rc;
+    const size_t smem = ((size_t) 16 + 8 * (size_t) pp.f.n_cells) << pp.log2s;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VK_CUDA(cudaFuncSetAttribute(agg_part_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin() - 1024));
+        attr_set = true;
+    }
+    const int64_t n_buckets = (int64_t) 1 << pp.log2p;
+    agg_part_reduce_kernel<<<(unsigned) (n_buckets < sms ? n_buckets : sms), PART_THREADS, smem, s>>>(pp);
+    VK_CHECK_LAUNCH("agg_part_reduce_kernel");
+    return VK_OK;
+}
+
 // ============================================================ one-group kernel
 // One launch per aggregate function; slot 0 of the table is the single group.
 struct OneParams {
@@ -928,6 +1207,8 @@ struct VkAgg {
     // global-table path while the number of groups is still rising: chunks grow geometrically and the
     // table is sized at every chunk boundary from an estimate of the final number of groups
     bool sizing = true;
+    double est_groups = 0;            // latest estimate of the final number of groups (0: none yet)
+    int part_policy = 1;              // option AGG_PARTITION
     int64_t rows_seen = 0;            // rows of every update so far
     int64_t sized_groups = 0;         // groups / selected rows at the last estimate
     uint64_t sized_selected = 0;
@@ -1512,6 +1793,7 @@ int vk_agg_create(VkAgg** out, int n_keys, const int32_t* key_dtypes, int n_func
     if (a->match_policy < 0 || a->match_policy > 2) a->match_policy = 1;
     if (opt(OPT_AGG_NOFAST)) a->fast_disabled = true;
     a->wide_rows = (int) opt(OPT_AGG_WIDE);
+    a->part_policy = (int) opt(OPT_AGG_PARTITION);
     a->learn_rows = (int64_t) 1 << (opt(OPT_AGG_LEARN_LOG2) < 10 ? 10 : (opt(OPT_AGG_LEARN_LOG2) > 30 ? 30 : opt(OPT_AGG_LEARN_LOG2)));
     const int rc = ctr_acquire(a);
     if (rc != VK_OK) { delete a; return rc; }
@@ -1689,7 +1971,12 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
 
     // ---- path selection ----
     FastPlan plan;
-    bool fast = a->n_keys == 1 && !a->fast_disabled && build_fast_plan(a, keys, values, &plan);
+    const bool plan_ok = a->n_keys == 1 && build_fast_plan(a, keys, values, &plan);
+    bool fast = plan_ok && !a->fast_disabled;
+    // the partitioned plan (scatter + reduce) takes what the fused kernel takes, except 128-bit sums
+    bool part_ok = plan_ok && a->part_policy != 0;
+    for (int c = 0; part_ok && c < plan.n_cells; ++c)
+        if (plan.cells[c].op == CELL_ADD_I128 || plan.cells[c].op == CELL_I128_HI) part_ok = false;
     Pred dpred;
     int pk;
     int rc = make_pred(*pred, n_rows, &dpred, &pk);
@@ -1804,7 +2091,18 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             const int64_t lim = a->rows_seen < ((int64_t) 1 << 17) ? ((int64_t) 1 << 20) : 8 * a->rows_seen;
             if (chunk > lim) chunk = lim;
         }
-        if (chunk > free_slots) {
+        // many groups: scatter into buckets + reduce per bucket instead of random updates of the global table
+        const bool use_part = !fast && part_ok && (a->part_policy == 2 || a->est_groups >= (double) PART_MIN_GROUPS);
+        if (use_part && chunk > PART_MAX_CHUNK) chunk = PART_MAX_CHUNK;
+        if (use_part) {
+            // any row may be deferred (its bucket full, its group not creatable): the list must hold a whole chunk
+            uint64_t want = (uint64_t) chunk;
+            if (want > list_max) want = list_max;
+            rc = ensure_list(a, want, s);
+            if (rc != VK_OK) return rc;
+            if (chunk > (int64_t) a->list_cap) chunk = (int64_t) a->list_cap;
+            may_fail = true;
+        } else if (chunk > free_slots) {
             uint64_t want = (uint64_t) (chunk - free_slots);
             if (want > list_max) want = list_max;
             rc = ensure_list(a, want, s);
@@ -1927,6 +2225,53 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 VK_CHECK_LAUNCH("agg_general_kernel(tail)");
             }
             a->groups_ub += chunk;
+        } else if (use_part) {
+            a->last_path = 4;
+            PartParams pp{};
+            FastParams& fp = pp.f;
+            fp.pred = dpred;
+            fp.key = gp.keys[0];
+            fp.key_mode = plan.key_mode;
+            fp.n_cols = plan.n_cols;
+            for (int v = 0; v < plan.n_cols; ++v) {
+                fp.col[v] = make_col(slice_col(plan.cols[v], pos, chunk));
+                fp.col_mode[v] = plan.col_mode[v];
+            }
+            fp.n_cells = plan.n_cells;
+            for (int c = 0; c < plan.n_cells; ++c) fp.cell[c] = plan.cells[c];
+            fp.n = chunk;
+            fp.row_limit = a->t.max_groups;
+            fp.table = a->t;
+            fp.replay = gp.replay;
+            // CTA table of the reduce pass: 8 Ki slots with at most one accumulator cell, else 4 Ki; buckets so that
+            // one holds a quarter of that many groups on average
+            pp.log2s = plan.n_cells <= 1 ? 13 : 12;
+            const double per_bucket = (double) ((int64_t) 1 << pp.log2s) / 4.0;
+            pp.log2p = 6;
+            while (pp.log2p < 13 && (double) ((int64_t) 1 << pp.log2p) * per_bucket < a->est_groups * 1.25) ++pp.log2p;
+            const int64_t n_buckets = (int64_t) 1 << pp.log2p;
+            // records per bucket: from the share of the rows selected so far, 15 % over
+            const uint64_t selected_so_far = a->h_ctr[CTR_SELECTED] + a->fast_spilled;
+            double sel = a->sized_selected > 0 && a->rows_seen > 0 ? (double) selected_so_far / (double) a->rows_seen : 1.0;
+            sel = sel * 1.15 + 0.01;
+            if (sel > 1.0 || pk == PK_NONE) sel = 1.0;
+            const double mean = (double) chunk * sel / (double) n_buckets;
+            pp.cap = (uint32_t) (mean * 1.1 + 6.0 * sqrt(mean) + 64.0);   // the hash spreads keys evenly: Poisson tails + 10 %
+            const size_t recs = (size_t) n_buckets * pp.cap;
+            uint8_t* scratch = nullptr;
+            const size_t cursor_bytes = (size_t) n_buckets * 128;
+            VK_CUDA(cudaMallocAsync((void**) &scratch, cursor_bytes + recs * 16, s));
+            pp.cursor = reinterpret_cast<unsigned int*>(scratch);
+            pp.recs = reinterpret_cast<ulonglong2*>(scratch + cursor_bytes);
+            VK_CUDA(cudaMemsetAsync(pp.cursor, 0, cursor_bytes, s));
+            VK_DBG("partitioned: buckets=%lld cap=%u slots=%d est_groups=%.0f scratch=%.1f MB", (long long) n_buckets, pp.cap,
+                   1 << pp.log2s, a->est_groups, (double) (cursor_bytes + recs * 16) / 1e6);
+            const int span = prof_begin(a, s, chunk, 2);
+            rc = launch_part(pp, pk, sms, s);
+            prof_end(a, s, span);
+            VK_CUDA(cudaFreeAsync(scratch, s));
+            if (rc != VK_OK) return rc;
+            a->groups_ub += chunk;
         } else {
             a->last_path = 2;
             int64_t need = (chunk + 255) / 256, capb = (int64_t) sms * 8;
@@ -2007,6 +2352,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                     const double left = (double) (n_rows - pos - chunk) * ((double) selected / (double) a->rows_seen);
                     double est = estimate_groups((double) selected, (double) groups);
                     if (est <= 0 || est > (double) groups + left) est = (double) groups + left;   // every row left a new group
+                    a->est_groups = est;
                     // 2 % over the estimate (its own error is a few tenths of a percent; a table one doubling larger
                     // than needed costs L2 residency: 1e6 groups fit the 2 Mi-slot table, 48 MB, and must stay there)
                     int64_t want = (int64_t) (est * 1.02);

@@ -31,7 +31,7 @@ static OptEntry g_opts[OPT_COUNT] = {
     {"SORT_FUSE_LAST", 1, {0}, {0}}, {"SORT_PREP", 4, {0}, {0}},
     {"AGG_LOG2S", 12, {0}, {0}},    {"AGG_PF", -1, {0}, {0}},          {"AGG_WARPS", 0, {0}, {0}},
     {"AGG_DIRECT", 1, {0}, {0}},    {"AGG_DICT", 1, {0}, {0}},         {"AGG_ENTRY", 1, {0}, {0}},         {"AGG_HOT", 1, {0}, {0}},          {"AGG_NOFAST", 0, {0}, {0}},
-    {"AGG_WIDE", 1, {0}, {0}},
+    {"AGG_WIDE", 1, {0}, {0}},      {"AGG_PARTITION", 1, {0}, {0}},
     {"AGG_LEARN_LOG2", 20, {0}, {0}}, {"LIST_LOG2", 30, {0}, {0}},     {"DEBUG", 0, {0}, {0}},
     {"INGEST_STAGED", 1, {0}, {0}}, {"INGEST_THREADS", 0, {0}, {0}}, {"INGEST_PIECE_KB", 2048, {0}, {0}},
 };
