@@ -159,6 +159,51 @@ def test_group_by_more_groups_than_the_first_table_holds(vb, stream, kind, chunk
         assert paths == [4] * chunks
 
 
+@pytest.mark.parametrize("path", ["partitioned", "general", "general_one_row"])
+@pytest.mark.parametrize("pred_kind", ["none", "f64_cmp", "i64_cmp", "i32_cmp", "mask", "expr"])
+def test_global_table_plans_every_predicate_kind_and_cell(vb, stream, pred_kind, path):
+    """The plans behind the shared-memory kernel (partitioned scatter + reduce, four rows per thread, one row per
+    thread) under every predicate specialisation (PK_NONE / F64_VEC / I64_VEC / GENERIC / MASK / fused expression),
+    an int32 key, and MIN(int64) / SUM(int32) / AVG(float32) accumulators (CELL_MAXORD, CELL_ADD_I64, CELL_ADD_F64
+    with a widened float32), in two ragged updates."""
+    from vinum_b200 import ops, _lib as L
+    import pyarrow.compute as pc
+    rng = np.random.default_rng(zlib.crc32(pred_kind.encode()))
+    n = 600_011
+    host = {"k": rng.integers(-20_000, 20_000, n).astype(np.int32), "a": rng.integers(-1000, 1000, n).astype(np.int32),
+            "x": rng.normal(0, 50, n), "y": rng.random(n).astype(np.float32), "w": rng.integers(-10**12, 10**12, n),
+            "q": rng.integers(-5, 5, n).astype(np.int32)}
+    sel = {"none": np.ones(n, bool), "f64_cmp": host["x"] > 3.0, "i64_cmp": host["w"] <= 0, "i32_cmp": host["q"] != 2,
+           "mask": (host["x"] > 0) & (host["q"] < 3), "expr": host["x"] * 2.0 > host["w"] / 1e10}[pred_kind]
+    with vb.options(AGG_LEARN_LOG2=14, **PATH_OPTS[path]):
+        # three value columns and three accumulator cells: the most the fused / partitioned plans take
+        agg = vb.Aggregator([pa.int32()], [(L.AGG_COUNT_STAR, None), (L.AGG_MIN, pa.int64()), (L.AGG_SUM, pa.int32()),
+                                           (L.AGG_AVG, pa.float32())])
+    cut = 250_002
+    for lo, hi in ((0, cut), (cut, n)):
+        d = {c: vb.DeviceColumn.from_numpy(np.ascontiguousarray(v[lo:hi]), stream) for c, v in host.items()}
+        pred = {"none": lambda: None,
+                "f64_cmp": lambda: ops.Predicate.compare(d["x"], ">", 3.0),
+                "i64_cmp": lambda: ops.Predicate.compare(d["w"], "<=", 0),
+                "i32_cmp": lambda: ops.Predicate.compare(d["q"], "!=", 2),
+                "mask": lambda: ops.Predicate.from_mask(ops.mask_and(ops.compare(d["x"], ">", 0.0, stream), ops.compare(d["q"], "<", 3, stream), stream)),
+                "expr": lambda: ops.Predicate.expr([(None, d["x"]), ("*", 2.0)], ">", [(None, d["w"]), ("/", 1e10)])}[pred_kind]()
+        agg.update([d["k"]], [None, d["w"], d["a"], d["y"]], pred, stream)
+        assert agg.last_path == (4 if path == "partitioned" else 2)
+    keys, aggs = agg.result_arrays(stream)
+    agg.close()
+    got = pa.table([keys[0]] + aggs, names=["k", "c", "mn", "sa", "ay"]).sort_by("k")
+    t = pa.table({c: v[sel] for c, v in host.items()})
+    want = t.group_by("k", use_threads=False).aggregate([("k", "count"), ("w", "min"), ("a", "sum")]).sort_by("k")
+    assert got.column("k").to_pylist() == want.column("k").to_pylist()
+    assert got.column("c").to_pylist() == want.column("k_count").to_pylist()
+    assert got.column("mn").to_pylist() == want.column("w_min").to_pylist()
+    assert got.column("sa").to_pylist() == want.column("a_sum").to_pylist()
+    inv = np.unique(host["k"][sel], return_inverse=True)[1]
+    want_avg = np.bincount(inv, weights=host["y"][sel].astype(np.float64)) / np.bincount(inv)
+    np.testing.assert_allclose(got.column("ay").to_numpy().astype(np.float64), want_avg, rtol=1e-5)
+
+
 @pytest.mark.parametrize("path", ["auto", "hash", "hash_insert", "tag_arbitration", "split_entries", "general", "partitioned"])
 def test_group_by_without_predicate_and_streamed_chunks(vb, stream, path):
     """C3's shape (no WHERE), fed in five ragged chunks: state carries across vk_agg_update calls
