@@ -317,7 +317,7 @@ int vk_agg_peer_merge(VkAgg* agg, VkPeer* peer, uint64_t epoch, VkStream stream)
 
 /* introspection for tests/bench: which kernel path the last update used
  * (0 = none, 1 = shared-memory table, 2 = global table, 3 = one-group reduction,
- * 4 = partitioned: scatter into hash buckets + per-bucket shared-memory reduce) */
+ * 4 = partitioned: scatter into buckets that are slices of the global table + update slice by slice) */
 int vk_agg_last_path(VkAgg* agg);
 /* Optional per-launch kernel timing (CUDA events recorded on the launch stream, resolved
  * lazily: no extra synchronisation).  vk_agg_profile_read returns, for `path` (1/2 as

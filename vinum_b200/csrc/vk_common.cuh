@@ -54,7 +54,7 @@ enum Opt {
     OPT_AGG_HOT,            // hot-group step (>= 6 lanes of a warp on one entry -> one butterfly-reduced update): 1 = when the learning launch saw a key with >= 30 % of the rows, 2 = always, 0 = never
     OPT_AGG_NOFAST,         // 1: never use the shared-memory aggregate kernel
     OPT_AGG_WIDE,           // global-table kernel on single-key tables: 1 = agg_wide_kernel (four rows per thread, lock-step probing), 0 = the one-row agg_general_kernel
-    OPT_AGG_PARTITION,      // many groups: scatter (key, row) into hash buckets + reduce each bucket in shared memory: 1 = from 2^21 estimated groups, 2 = whenever the plan allows, 0 = never
+    OPT_AGG_PARTITION,      // tables beyond the L2: scatter (key, row) into buckets = table slices + update slice by slice: 1 = when the touched table exceeds 96 MB, 2 = always (single key), 0 = never
     OPT_AGG_LEARN_LOG2,     // log2 rows of the learning launch
     OPT_LIST_LOG2,          // log2 of the replay-list capacity cap (entries)
     OPT_DEBUG,              // 1: trace the aggregate's host decisions to stderr

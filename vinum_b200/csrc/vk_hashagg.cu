@@ -107,6 +107,34 @@ __device__ __forceinline__ void count_selected(const GenParams& p, unsigned n_se
     if ((threadIdx.x & 31) == 0 && n_selected) atomicAdd(p.replay.selected, (unsigned long long) n_selected);
 }
 
+// One row (that passed the predicate) into the global table: any key arity / dtype / NULLs / function.
+__device__ __forceinline__ void general_update_row(const GenParams& p, int64_t i) {
+    uint64_t kv[VK_AGG_MAX_KEYS];
+    uint32_t nullmask = 0;
+    for (int k = 0; k < p.n_keys; ++k) {
+        bool valid = col_valid(p.keys[k], i);
+        kv[k] = valid ? load_as_u64(p.keys[k], i) : 0;
+        nullmask |= (uint32_t) (!valid) << k;
+    }
+    int64_t slot = gt_find_or_insert<0>(p.table, kv, nullmask, hash_keys(kv, nullmask, p.n_keys), p.table.max_groups);
+    if (slot < 0) {
+        replay_append(p.replay, i);
+        return;
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + slot), 1ULL);
+    for (int f = 0; f < p.n_funcs; ++f) {
+        const FuncSpec spec = p.specs[f];
+        if (spec.acc == ACC_NONE) continue;
+        if (!col_valid(p.vals[f], i)) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.table.nnull[f] + slot), 1ULL);
+            continue;
+        }
+        if (spec.acc == ACC_COUNT) continue;
+        acc_update_global(p.table, f, spec, slot, acc_load(spec, p.vals[f], i));
+    }
+}
+static __device__ __noinline__ void general_update_row_cold(const GenParams& p, int64_t i) { general_update_row(p, i); }
+
 __global__ void __launch_bounds__(256) agg_general_kernel(const __grid_constant__ GenParams p) {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     const bool replaying = p.row_list != nullptr;
@@ -116,31 +144,242 @@ __global__ void __launch_bounds__(256) agg_general_kernel(const __grid_constant_
         const int64_t i = replaying ? (int64_t) p.row_list[it] : it;
         if (!replaying && !pred_row(p.pred, i)) continue;  // listed rows already passed the predicate
         ++n_selected;
-        uint64_t kv[VK_AGG_MAX_KEYS];
-        uint32_t nullmask = 0;
-        for (int k = 0; k < p.n_keys; ++k) {
-            bool valid = col_valid(p.keys[k], i);
-            kv[k] = valid ? load_as_u64(p.keys[k], i) : 0;
-            nullmask |= (uint32_t) (!valid) << k;
+        general_update_row(p, i);
+    }
+    count_selected(p, n_selected);
+}
+
+// L2 residency control for the partitioned update: the slice of the table a bucket updates must stay in the L2 while
+// records and gathered values stream through it.  Without hints every gathered 32-byte sector claims a 128-byte line,
+// the L2 turns over in a few microseconds and the table slice is evicted between two touches (measured: RED hit rate
+// 24 %, 227 DRAM bytes per record).  Table loads / reductions carry an evict_last policy, streams an evict_first one.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t ld_key_relaxed_hint(const uint64_t* p, uint64_t pol) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_add_u64_hint(uint64_t* p, uint64_t v, uint64_t pol) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_f64_hint(uint64_t* p, double v, uint64_t pol) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t ldg_u64_stream_hint(const void* p, uint64_t pol) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ ulonglong2 ldg_rec_stream_hint(const ulonglong2* p, uint64_t pol) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
+// Stage 1 of a tile of the global-table kernels: which of the thread's R rows (R/2 adjacent pairs, 512 rows apart) pass
+// the predicate, and their keys.  `plain` = an ordinary key: not NULL (the value that marks a free slot is sorted out later).
+template <int PK, int R>
+__device__ __forceinline__ void wide_select_and_keys(const GenParams& p, int64_t base, bool whole, bool (&sel)[R], uint64_t (&key)[R],
+                                                     bool (&plain)[R]) {
+    const Col& kc = p.keys[0];
+    if ((PK == PK_F64_VEC || PK == PK_I64_VEC) && whole) {
+        // whole tile: the R/2 predicate loads first, the comparisons after them
+        uint4 q[R / 2];
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) q[j] = ldg_stream16(p.pred.col.data + (base + j * 512) * 8);
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) {
+            if (PK == PK_F64_VEC) {
+                const double c = __longlong_as_double((long long) p.pred.scalar.bits);
+                sel[2 * j] = apply_cmp(p.pred.op, __hiloint2double(q[j].y, q[j].x), c);
+                sel[2 * j + 1] = apply_cmp(p.pred.op, __hiloint2double(q[j].w, q[j].z), c);
+            } else {
+                const int64_t c = (int64_t) p.pred.scalar.bits;
+                sel[2 * j] = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q[j].y << 32) | q[j].x), c);
+                sel[2 * j + 1] = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q[j].w << 32) | q[j].z), c);
+            }
         }
-        int64_t slot = gt_find_or_insert<0>(p.table, kv, nullmask, hash_keys(kv, nullmask, p.n_keys), p.table.max_groups);
-        if (slot < 0) {
-            replay_append(p.replay, i);
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; j += 2) pred_pair<PK>(p.pred, base + (j / 2) * 512, p.n, sel[j], sel[j + 1]);
+    }
+    if (kc.validity == nullptr && (kc.dtype == VK_I64 || kc.dtype == VK_U64 || kc.dtype == VK_F64)) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            key[j] = 0;
+            plain[j] = sel[j];
+            if (sel[j]) key[j] = reinterpret_cast<const uint64_t*>(kc.data)[base + (j / 2) * 512 + (j & 1)];
+        }
+    } else if (kc.validity == nullptr && kc.dtype == VK_I32) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            key[j] = 0;
+            plain[j] = sel[j];
+            if (sel[j]) key[j] = (uint64_t) (int64_t) reinterpret_cast<const int32_t*>(kc.data)[base + (j / 2) * 512 + (j & 1)];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int64_t i = base + (j / 2) * 512 + (j & 1);
+            key[j] = 0;
+            plain[j] = false;
+            if (sel[j]) {
+                plain[j] = col_valid(kc, i);
+                if (plain[j]) key[j] = load_as_u64(kc, i);
+            }
+        }
+    }
+}
+
+// Stages 2 - 4: the slot of every selected row (lock-step probing), then the accumulator updates.  `row` = row ids
+// (for the value columns and the replay list).  Must be called by all 32 lanes of a warp together.
+template <int R, bool HINTS = false>
+__device__ __forceinline__ void wide_update(const GenParams& p, bool (&sel)[R], const uint64_t (&key)[R], const bool (&plain)[R],
+                                            const uint32_t (&row)[R]) {   // row ids fit 32 bits (chunks are cut accordingly)
+    const GTable& t = p.table;
+    const Col& kc = p.keys[0];
+    (void) kc;
+    const uint64_t mask = (uint64_t) t.capacity - 1;
+    const uint64_t keep = HINTS ? l2_policy_keep() : 0, stream = HINTS ? l2_policy_stream() : 0;
+    int64_t slot[R];
+    bool pend[R];   // rows still looking for their slot
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        pend[j] = plain[j] && key[j] != GT_EMPTY;
+        slot[j] = (int64_t) (hash_key1(key[j]) & mask);
+        if (sel[j] && !pend[j]) {
+            // NULL key / the key value that marks a free slot: their two dedicated slots
+            slot[j] = gt1_find_or_insert(t, key[j], !plain[j], 0, t.max_groups);
+            if (slot[j] < 0) {
+                replay_append(p.replay, (int64_t) row[j]);
+                sel[j] = false;
+            }
+        }
+    }
+    // Linear probing in lock step: one round loads the current slot of every pending row of the warp
+    // (R loads in flight per lane); each row is then found, inserted by CAS (the protocol of
+    // gt1_find_or_insert) or moves one slot on.  Votes keep the warp converged; the group counter, one
+    // hot address, is read once per warp and round and advanced once per warp.  (Loading two slots per
+    // round was measured: fewer rounds, but 64 registers instead of 56 and 10 % slower at 1e4 - 1e6 groups.)
+    const unsigned lane = threadIdx.x & 31u;
+    for (int64_t probes = 0; probes < t.capacity; ++probes) {
+        uint64_t seen[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            seen[j] = key[j];
+            if (pend[j]) seen[j] = HINTS ? ld_key_relaxed_hint(t.keys + slot[j], keep) : ld_key_relaxed(t.keys + slot[j]);
+        }
+        // rows at a free slot claim it by CAS; the group counter (one hot address) is read once per warp and round and
+        // advanced once, whatever the number of claims (an insert-heavy launch spent most of its time on that line)
+        bool claims = false;
+        unsigned settled = 0;   // bit j: row slot j was dealt with in the claim block (found, inserted, deferred or moved on)
+#pragma unroll
+        for (int j = 0; j < R; ++j) claims = claims || (pend[j] && seen[j] == GT_EMPTY);
+        if (__any_sync(0xffffffffu, claims)) {   // warp-uniform; nothing of this block is live on the common path
+            unsigned long long groups_now = 0;
+            if (lane == 0) groups_now = *reinterpret_cast<volatile unsigned long long*>(t.num_groups);
+            groups_now = __shfl_sync(0xffffffffu, groups_now, 0);
+            unsigned before = 0, won_total = 0;   // claims of earlier row slots / inserts of this round
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const bool claim = pend[j] && seen[j] == GT_EMPTY;
+                const unsigned claimers = __ballot_sync(0xffffffffu, claim);
+                if (!claimers) continue;   // warp-uniform
+                bool inserted = false;
+                if (claim) {
+                    settled |= 1u << j;
+                    if (groups_now + before + __popc(claimers & ((1u << lane) - 1u)) >= (unsigned long long) t.max_groups) {
+                        replay_append(p.replay, (int64_t) row[j]);
+                        sel[j] = false;
+                        pend[j] = false;
+                    } else {
+                        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(t.keys + slot[j]),
+                                                                 (unsigned long long) GT_EMPTY, (unsigned long long) key[j]);
+                        inserted = old == GT_EMPTY;
+                        if (inserted || old == key[j]) pend[j] = false;
+                        else slot[j] = (int64_t) (((uint64_t) slot[j] + 1) & mask);   // another key took it
+                    }
+                }
+                won_total += __popc(__ballot_sync(0xffffffffu, inserted));
+                before += __popc(claimers);
+            }
+            if (lane == 0 && won_total) atomicAdd(t.num_groups, (unsigned long long) won_total);
+        }
+        bool more = false;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (pend[j] && !((settled >> j) & 1u)) {
+                if (seen[j] == key[j]) pend[j] = false;
+                else slot[j] = (int64_t) (((uint64_t) slot[j] + 1) & mask);
+            }
+            more = more || pend[j];
+        }
+        if (!__any_sync(0xffffffffu, more)) break;
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+        if (pend[j]) {   // every slot visited: cannot happen below the load limit, but no row may be lost
+            replay_append(p.replay, (int64_t) row[j]);
+            sel[j] = false;
+        }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+        if (sel[j]) {
+            if (HINTS) red_add_u64_hint(t.count_star + slot[j], 1ULL, keep);
+            else atomicAdd(reinterpret_cast<unsigned long long*>(t.count_star + slot[j]), 1ULL);
+        }
+    for (int f = 0; f < p.n_funcs; ++f) {
+        const FuncSpec spec = p.specs[f];
+        if (spec.acc == ACC_NONE) continue;
+        const Col& vc = p.vals[f];
+        uint64_t v[R];
+        bool ok[R];
+        if (spec.acc == ACC_SUM_F64 && vc.dtype == VK_F64 && vc.validity == nullptr) {
+            // the common shape, free of per-row switches so that the R loads issue back to back
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                ok[j] = sel[j];
+                v[j] = 0;
+                if (sel[j])
+                    v[j] = HINTS ? ldg_u64_stream_hint(reinterpret_cast<const uint64_t*>(vc.data) + row[j], stream)
+                                 : reinterpret_cast<const uint64_t*>(vc.data)[row[j]];
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+                if (ok[j]) {
+                    if (HINTS) red_add_f64_hint(t.acc_lo[f] + slot[j], __longlong_as_double((long long) v[j]), keep);
+                    else atomicAdd(reinterpret_cast<double*>(t.acc_lo[f] + slot[j]), __longlong_as_double((long long) v[j]));
+                }
             continue;
         }
-        atomicAdd(reinterpret_cast<unsigned long long*>(p.table.count_star + slot), 1ULL);
-        for (int f = 0; f < p.n_funcs; ++f) {
-            const FuncSpec spec = p.specs[f];
-            if (spec.acc == ACC_NONE) continue;
-            if (!col_valid(p.vals[f], i)) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(p.table.nnull[f] + slot), 1ULL);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int64_t i = (int64_t) row[j];
+            ok[j] = false;
+            v[j] = 0;
+            if (!sel[j]) continue;
+            if (!col_valid(vc, i)) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(t.nnull[f] + slot[j]), 1ULL);
                 continue;
             }
             if (spec.acc == ACC_COUNT) continue;
-            acc_update_global(p.table, f, spec, slot, acc_load(spec, p.vals[f], i));
+            ok[j] = true;
+            v[j] = acc_load(spec, vc, i);
         }
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (ok[j]) acc_update_global(t, f, spec, slot[j], v[j]);
     }
-    count_selected(p, n_selected);
 }
 
 // ---- the same update for single-key tables, R rows per thread ---------------------------------
@@ -156,9 +395,6 @@ __global__ void __launch_bounds__(256) agg_general_kernel(const __grid_constant_
 template <int PK, int R>
 __global__ void __launch_bounds__(256) agg_wide_kernel(const __grid_constant__ GenParams p) {
     constexpr int64_t TILE = 256 * R;
-    const GTable& t = p.table;
-    const Col& kc = p.keys[0];
-    const uint64_t mask = (uint64_t) t.capacity - 1;
     const int64_t n_tiles = (p.n - p.row_begin + TILE - 1) / TILE;
     unsigned n_selected = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -166,168 +402,16 @@ __global__ void __launch_bounds__(256) agg_wide_kernel(const __grid_constant__ G
         // per issued instruction and 3.6 x the DRAM traffic
         __syncwarp();
         const int64_t base = p.row_begin + tile * TILE + 2 * (int64_t) threadIdx.x;   // row_begin is even
-        bool sel[R];
-        if ((PK == PK_F64_VEC || PK == PK_I64_VEC) && p.row_begin + (tile + 1) * TILE <= p.n) {
-            // whole tile: the R/2 predicate loads first, the comparisons after them
-            uint4 q[R / 2];
-#pragma unroll
-            for (int j = 0; j < R / 2; ++j) q[j] = ldg_stream16(p.pred.col.data + (base + j * 512) * 8);
-#pragma unroll
-            for (int j = 0; j < R / 2; ++j) {
-                if (PK == PK_F64_VEC) {
-                    const double c = __longlong_as_double((long long) p.pred.scalar.bits);
-                    sel[2 * j] = apply_cmp(p.pred.op, __hiloint2double(q[j].y, q[j].x), c);
-                    sel[2 * j + 1] = apply_cmp(p.pred.op, __hiloint2double(q[j].w, q[j].z), c);
-                } else {
-                    const int64_t c = (int64_t) p.pred.scalar.bits;
-                    sel[2 * j] = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q[j].y << 32) | q[j].x), c);
-                    sel[2 * j + 1] = apply_cmp(p.pred.op, (int64_t) (((uint64_t) q[j].w << 32) | q[j].z), c);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < R; j += 2) pred_pair<PK>(p.pred, base + (j / 2) * 512, p.n, sel[j], sel[j + 1]);
-        }
-#pragma unroll
-        for (int j = 0; j < R; ++j) n_selected += sel[j] ? 1u : 0u;
+        bool sel[R], plain[R];
         uint64_t key[R];
-        bool plain[R];   // an ordinary key: not NULL, not the value that marks a free slot
-        if (kc.validity == nullptr && (kc.dtype == VK_I64 || kc.dtype == VK_U64 || kc.dtype == VK_F64)) {
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                key[j] = 0;
-                plain[j] = sel[j];
-                if (sel[j]) key[j] = reinterpret_cast<const uint64_t*>(kc.data)[base + (j / 2) * 512 + (j & 1)];
-            }
-        } else if (kc.validity == nullptr && kc.dtype == VK_I32) {
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                key[j] = 0;
-                plain[j] = sel[j];
-                if (sel[j]) key[j] = (uint64_t) (int64_t) reinterpret_cast<const int32_t*>(kc.data)[base + (j / 2) * 512 + (j & 1)];
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const int64_t i = base + (j / 2) * 512 + (j & 1);
-                key[j] = 0;
-                plain[j] = false;
-                if (sel[j]) {
-                    plain[j] = col_valid(kc, i);
-                    if (plain[j]) key[j] = load_as_u64(kc, i);
-                }
-            }
-        }
-        int64_t slot[R];
-        bool pend[R];   // rows still looking for their slot
+        uint32_t row[R];
+        wide_select_and_keys<PK, R>(p, base, p.row_begin + (tile + 1) * TILE <= p.n, sel, key, plain);
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            pend[j] = plain[j] && key[j] != GT_EMPTY;
-            slot[j] = (int64_t) (hash_key1(key[j]) & mask);
-            if (sel[j] && !pend[j]) {
-                // NULL key / the key value that marks a free slot: their two dedicated slots
-                const int64_t i = base + (j / 2) * 512 + (j & 1);
-                slot[j] = gt1_find_or_insert(t, key[j], !plain[j], 0, t.max_groups);
-                if (slot[j] < 0) {
-                    replay_append(p.replay, i);
-                    sel[j] = false;
-                }
-            }
+            n_selected += sel[j] ? 1u : 0u;
+            row[j] = (uint32_t) (base + (j / 2) * 512 + (j & 1));
         }
-        // Linear probing in lock step: one round loads the current slot of every pending row of the warp
-        // (R loads in flight per lane); each row is then found, inserted by CAS (the protocol of
-        // gt1_find_or_insert) or moves one slot on.  Votes keep the warp converged; the group counter, one
-        // hot address, is read once per warp and round and advanced once per warp.  (Loading two slots per
-        // round was measured: fewer rounds, but 64 registers instead of 56 and 10 % slower at 1e4 - 1e6 groups.)
-        const unsigned lane = threadIdx.x & 31u;
-        for (int64_t probes = 0; probes < t.capacity; ++probes) {
-            uint64_t seen[R];
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                seen[j] = key[j];
-                if (pend[j]) seen[j] = ld_key_relaxed(t.keys + slot[j]);
-            }
-            bool more = false;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const bool claim = pend[j] && seen[j] == GT_EMPTY;
-                const unsigned claimers = __ballot_sync(0xffffffffu, claim);
-                if (claimers) {   // warp-uniform
-                    unsigned long long groups_now = 0;
-                    if (lane == 0) groups_now = *reinterpret_cast<volatile unsigned long long*>(t.num_groups);
-                    groups_now = __shfl_sync(0xffffffffu, groups_now, 0);
-                    bool inserted = false;
-                    if (claim) {
-                        if (groups_now + __popc(claimers & ((1u << lane) - 1u)) >= (unsigned long long) t.max_groups) {
-                            replay_append(p.replay, base + (j / 2) * 512 + (j & 1));
-                            sel[j] = false;
-                            pend[j] = false;
-                        } else {
-                            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(t.keys + slot[j]),
-                                                                     (unsigned long long) GT_EMPTY, (unsigned long long) key[j]);
-                            inserted = old == GT_EMPTY;
-                            if (inserted || old == key[j]) pend[j] = false;
-                            else slot[j] = (int64_t) (((uint64_t) slot[j] + 1) & mask);   // another key took it
-                        }
-                    }
-                    const unsigned won = __ballot_sync(0xffffffffu, inserted);
-                    if (lane == 0 && won) atomicAdd(t.num_groups, (unsigned long long) __popc(won));
-                }
-                if (pend[j] && !claim) {
-                    if (seen[j] == key[j]) pend[j] = false;
-                    else slot[j] = (int64_t) (((uint64_t) slot[j] + 1) & mask);
-                }
-                more = more || pend[j];
-            }
-            if (!__any_sync(0xffffffffu, more)) break;
-        }
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-            if (pend[j]) {   // every slot visited: cannot happen below the load limit, but no row may be lost
-                replay_append(p.replay, base + (j / 2) * 512 + (j & 1));
-                sel[j] = false;
-            }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-            if (sel[j]) atomicAdd(reinterpret_cast<unsigned long long*>(t.count_star + slot[j]), 1ULL);
-        for (int f = 0; f < p.n_funcs; ++f) {
-            const FuncSpec spec = p.specs[f];
-            if (spec.acc == ACC_NONE) continue;
-            const Col& vc = p.vals[f];
-            uint64_t v[R];
-            bool ok[R];
-            if (spec.acc == ACC_SUM_F64 && vc.dtype == VK_F64 && vc.validity == nullptr) {
-                // the common shape, free of per-row switches so that the R loads issue back to back
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    ok[j] = sel[j];
-                    v[j] = 0;
-                    if (sel[j]) v[j] = reinterpret_cast<const uint64_t*>(vc.data)[base + (j / 2) * 512 + (j & 1)];
-                }
-#pragma unroll
-                for (int j = 0; j < R; ++j)
-                    if (ok[j]) atomicAdd(reinterpret_cast<double*>(t.acc_lo[f] + slot[j]), __longlong_as_double((long long) v[j]));
-                continue;
-            }
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const int64_t i = base + (j / 2) * 512 + (j & 1);
-                ok[j] = false;
-                v[j] = 0;
-                if (!sel[j]) continue;
-                if (!col_valid(vc, i)) {
-                    atomicAdd(reinterpret_cast<unsigned long long*>(t.nnull[f] + slot[j]), 1ULL);
-                    continue;
-                }
-                if (spec.acc == ACC_COUNT) continue;
-                ok[j] = true;
-                v[j] = acc_load(spec, vc, i);
-            }
-#pragma unroll
-            for (int j = 0; j < R; ++j)
-                if (ok[j]) acc_update_global(t, f, spec, slot[j], v[j]);
-        }
+        wide_update<R>(p, sel, key, plain, row);
     }
     count_selected(p, n_selected);
 }
@@ -357,266 +441,134 @@ static int launch_wide(const GenParams& gp, int sms, cudaStream_t s) {
     }
 }
 
-// ============================================================ partitioned aggregate (many groups)
-// With 1e6 and more groups the global table is a random-access target: three L2 (or, beyond ~1.5e6 groups,
-// DRAM) sectors per row, 27 ms at 1e6 groups and 167 ms at 8.4e6 for 1e9 rows.  Two sequential passes cost
-// less than that random traffic:
-//   scatter  every selected row's (key, row id) is appended to one of P buckets chosen by a hash of the key
-//            (one atomic on the bucket's cursor, one 16-byte store; the L2 merges neighbouring appends into
-//            full sectors);
-//   reduce   one CTA per bucket aggregates its rows in a SHARED-memory table with shared-memory atomics
-//            (a bucket holds ~S/4 groups by construction), gathering the value columns by row id, and
-//            flushes one update per group into the global table.
-// Nothing can be lost: a key's global slot is claimed BEFORE the key enters the CTA table, so the flush
-// cannot fail; a row whose group cannot be created (global table at its limit), or that does not fit its
-// bucket, goes to the replay list like in every other kernel; a bucket with more groups than its table
-// holds sends the extra rows straight to the global table.
+// ============================================================ partitioned aggregate (tables beyond the L2)
+// Once the global table no longer fits the L2 (1.5e6 groups and more) every row costs three random DRAM sectors:
+// 72 ms at 8.4e6 groups for 1e9 rows.  Two passes that keep the table traffic inside the L2 cost less:
+//   scatter  every selected row's (key, row id) is appended to one of P buckets, the bucket being the RANGE OF TABLE
+//            SLOTS the key hashes into (top bits of hash & mask): one atomic on the bucket's cursor and ONE 16-byte store
+//            per row (the pass is bound by uncoalesced transactions, ~60 G/s, not by bytes; the L2 merges neighbouring
+//            appends into full sectors);
+//   update   the records are consumed bucket by bucket by the very update of agg_wide_kernel (wide_update: lock-step
+//            probing, RED accumulation, value columns gathered by row id): all CTAs work on the same one or two buckets
+//            at a time, whose slice of the table (capacity / P slots, ~4 MB) stays in the L2.
+// Everything the global-table kernel supports is supported (any key dtype, NULL keys, every function); rows that cannot
+// be placed (bucket full, table at its limit) go to the replay list like everywhere else.
 struct PartParams {
-    FastParams f;            // predicate, key, value columns, cells, global table, replay list
-    int log2p;               // buckets = 1 << log2p (one CTA table of the reduce pass each)
+    GenParams g;             // predicate, key, value columns, functions, global table, replay list
+    int log2p;               // buckets = 1 << log2p
+    int shift;               // bucket = (hash & mask) >> shift
     uint32_t cap;            // records per bucket
-    ulonglong2* recs;        // [P][cap] records {key, row id relative to the chunk}: ONE 16-byte store each (the scatter
-                             // pass is bound by the number of uncoalesced transactions, ~60 G/s on this part, not by bytes)
+    ulonglong2* recs;        // [P][cap] records {key, row id relative to the chunk}
     unsigned int* cursor;    // [P * 32]: one counter per 128-byte line (8 cursors per bucket, chosen by further hash bits, were
                              // measured: no change, the pass is not bound by same-address atomics)
-    int log2s;               // reduce: slots of the CTA table
 };
-
-__device__ __forceinline__ uint32_t part_bucket(uint64_t key, int log2p) { return fast_hash32(key) >> (32 - log2p); }
-// Slot hash of the reduce pass: other multipliers than fast_hash32, whose top bits are equal within a bucket.
-__device__ __forceinline__ uint32_t part_slot_hash(uint64_t key) {
-    uint32_t x = ((uint32_t) key * 0xCC9E2D51u) ^ ((uint32_t) (key >> 32) * 0x1B873593u);
-    x ^= x >> 15;
-    x *= 0x2C1B3C6Du;
-    x ^= x >> 12;
-    x *= 0x297A2D39u;
-    return x ^ (x >> 15);
-}
-__device__ __forceinline__ uint64_t part_load_key(const FastParams& f, int64_t i) {
-    if (f.key_mode == 0) return reinterpret_cast<const uint64_t*>(f.key.data)[i];
-    return widen4(reinterpret_cast<const uint32_t*>(f.key.data)[i], f.key_mode == 1 ? 1 : 2);
-}
-__device__ __forceinline__ uint64_t part_load_val(const FastParams& f, int c, int64_t i) {
-    if (f.col_mode[c] == 0) return reinterpret_cast<const uint64_t*>(f.col[c].data)[i];
-    return widen4(reinterpret_cast<const uint32_t*>(f.col[c].data)[i], f.col_mode[c]);
-}
-__device__ __forceinline__ void part_global_row(const FastParams& f, uint64_t key, int64_t row) {
-    uint64_t v[FA_MAX_COLS] = {0, 0, 0};
-    for (int c = 0; c < f.n_cols; ++c) v[c] = part_load_val(f, c, row);
-    fast_global_row(f, key, v[0], v[1], v[2], row);
-}
 
 template <int PK>
 __global__ void __launch_bounds__(256) agg_part_scatter_kernel(const __grid_constant__ PartParams p) {
     constexpr int R = 8;
     constexpr int64_t TILE = 256 * R;
-    const FastParams& f = p.f;
-    const int64_t n_tiles = (f.n + TILE - 1) / TILE;
+    const GenParams& g = p.g;
+    const uint64_t mask = (uint64_t) g.table.capacity - 1;
+    const int64_t n_tiles = (g.n + TILE - 1) / TILE;
     unsigned n_selected = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncwarp();
         const int64_t base = tile * TILE + 2 * (int64_t) threadIdx.x;
-        const bool whole = (tile + 1) * TILE <= f.n;
-        bool sel[R];
-        if ((PK == PK_F64_VEC || PK == PK_I64_VEC) && whole) {
-            uint4 q[R / 2];
-#pragma unroll
-            for (int j = 0; j < R / 2; ++j) q[j] = ldg_stream16(f.pred.col.data + (base + j * 512) * 8);
-#pragma unroll
-            for (int j = 0; j < R / 2; ++j) {
-                if (PK == PK_F64_VEC) {
-                    const double c = __longlong_as_double((long long) f.pred.scalar.bits);
-                    sel[2 * j] = apply_cmp(f.pred.op, __hiloint2double(q[j].y, q[j].x), c);
-                    sel[2 * j + 1] = apply_cmp(f.pred.op, __hiloint2double(q[j].w, q[j].z), c);
-                } else {
-                    const int64_t c = (int64_t) f.pred.scalar.bits;
-                    sel[2 * j] = apply_cmp(f.pred.op, (int64_t) (((uint64_t) q[j].y << 32) | q[j].x), c);
-                    sel[2 * j + 1] = apply_cmp(f.pred.op, (int64_t) (((uint64_t) q[j].w << 32) | q[j].z), c);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < R; j += 2) pred_pair<PK>(f.pred, base + (j / 2) * 512, f.n, sel[j], sel[j + 1]);
-        }
+        bool sel[R], plain[R];
         uint64_t key[R];
-        if (whole && f.key_mode == 0) {   // key columns of the plan are 16-byte aligned (aligned_for_pairs)
-#pragma unroll
-            for (int j = 0; j < R / 2; ++j) {
-                const uint4 q = ldg_stream16(f.key.data + (base + j * 512) * 8);
-                key[2 * j] = u64_of(q.x, q.y);
-                key[2 * j + 1] = u64_of(q.z, q.w);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const int64_t i = base + (j / 2) * 512 + (j & 1);
-                key[j] = sel[j] ? part_load_key(f, i) : 0;
-            }
-        }
+        uint32_t row[R];
+        wide_select_and_keys<PK, R>(g, base, (tile + 1) * TILE <= g.n, sel, key, plain);
         uint32_t pos[R], bucket[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             n_selected += sel[j] ? 1u : 0u;
-            bucket[j] = part_bucket(key[j], p.log2p);
+            row[j] = (uint32_t) (base + (j / 2) * 512 + (j & 1));
+            bucket[j] = (uint32_t) ((hash_key1(key[j]) & mask) >> p.shift);
             pos[j] = 0xFFFFFFFFu;
-            if (sel[j] && key[j] != GT_EMPTY) pos[j] = atomicAdd(p.cursor + (size_t) bucket[j] * 32, 1u);
+            // (a NULL key, or the key value that marks a free slot, has a dedicated slot: straight to the table, below)
+            if (sel[j] && plain[j] && key[j] != GT_EMPTY) pos[j] = atomicAdd(p.cursor + (size_t) bucket[j] * 32, 1u);
         }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             if (!sel[j]) continue;
-            const int64_t i = base + (j / 2) * 512 + (j & 1);
-            if (key[j] == GT_EMPTY) {
-                part_global_row(f, key[j], i);          // the key value that marks a free slot: its dedicated slot
-            } else if (pos[j] < p.cap) {
-                p.recs[(size_t) bucket[j] * p.cap + pos[j]] = make_ulonglong2(key[j], (unsigned long long) i);
-            } else {
-                replay_append(f.replay, i);             // bucket full (skewed keys): the replay pass takes the row
-            }
+            if (pos[j] == 0xFFFFFFFFu) general_update_row_cold(g, (int64_t) row[j]);
+            else if (pos[j] < p.cap) p.recs[(size_t) bucket[j] * p.cap + pos[j]] = make_ulonglong2(key[j], (unsigned long long) row[j]);
+            else replay_append(g.replay, (int64_t) row[j]);   // bucket full (skewed keys): the replay pass takes the row
         }
     }
-    if (f.replay.selected != nullptr) {
-        __syncwarp();
-        n_selected = __reduce_add_sync(0xffffffffu, n_selected);
-        if ((threadIdx.x & 31) == 0 && n_selected) atomicAdd(f.replay.selected, (unsigned long long) n_selected);
-    }
+    count_selected(g, n_selected);
 }
 
-// One record into the CTA table of the reduce pass.
-__device__ __forceinline__ void part_reduce_record(const FastParams& f, uint64_t* keys, uint64_t* cells, uint32_t* gslot, uint32_t* cnt,
-                                                   unsigned* s_groups, uint32_t S, uint64_t key, int64_t row, uint64_t v0, uint64_t v1, uint64_t v2) {
-    const uint32_t smask = S - 1, full = S - S / 4;
-    uint32_t slot = part_slot_hash(key) & smask;
-    int where = -1;   // >= 0: CTA slot, -1: CTA table full or probe chain too long, -2: no global slot
-    for (int probe = 0; probe < FA_MAXPROBE; ++probe) {
-        const uint64_t k = *reinterpret_cast<volatile uint64_t*>(keys + slot);
-        if (k == key) {
-            where = (int) slot;
-            break;
-        }
-        if (k == GT_EMPTY) {
-            if (*reinterpret_cast<volatile unsigned*>(s_groups) >= full) break;
-            // the global slot first: a key whose group cannot be created never enters the CTA table
-            const int64_t g = gt1_find_or_insert(f.table, key, false, hash_key1(key), f.row_limit);
-            if (g < 0) {
-                where = -2;
-                break;
-            }
-            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot),
-                                                     (unsigned long long) GT_EMPTY, (unsigned long long) key);
-            if (old == GT_EMPTY) {
-                gslot[slot] = (uint32_t) g;
-                atomicAdd(s_groups, 1u);
-                where = (int) slot;
-                break;
-            }
-            if (old == key) {
-                where = (int) slot;
-                break;
-            }
-        }
-        slot = (slot + 1) & smask;
-    }
-    if (where >= 0) {
-        atomicAdd(cnt + where, 1u);
-        for (int c = 0; c < f.n_cells; ++c) {
-            const FastCell cell = f.cell[c];
-            uint64_t* at = cells + (size_t) c * S + where;
-            const uint64_t x = cell.col == 0 ? v0 : (cell.col == 1 ? v1 : v2);   // (an indexed array would live in local memory)
-            if (cell.op == CELL_ADD_F64) atomicAdd(reinterpret_cast<double*>(at), __longlong_as_double((long long) x));
-            else if (cell.op == CELL_MAXORD)
-                atomicMax(reinterpret_cast<unsigned long long*>(at), (unsigned long long) ord_transform(cell.ord, cell.is_min, x));
-            else atomicAdd(reinterpret_cast<unsigned long long*>(at), (unsigned long long) x);
-        }
-    } else if (where == -2) {
-        replay_append(f.replay, row);
-    } else {
-        fast_global_row(f, key, v0, v1, v2, row);
-    }
-}
-
-constexpr int PART_THREADS = 1024;
-__global__ void __launch_bounds__(PART_THREADS) agg_part_reduce_kernel(const __grid_constant__ PartParams p) {
-    extern __shared__ __align__(16) uint8_t part_smem[];
-    __shared__ unsigned s_groups;
-    const FastParams& f = p.f;
-    const uint32_t S = 1u << p.log2s;
-    const int nc = f.n_cells;
-    uint64_t* keys = reinterpret_cast<uint64_t*>(part_smem);
-    uint64_t* cells = keys + S;                                     // [nc][S]
-    uint32_t* gslot = reinterpret_cast<uint32_t*>(cells + (size_t) nc * S);
-    uint32_t* cnt = gslot + S;
-    const uint32_t n_buckets = 1u << p.log2p;
-    for (uint32_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+__global__ void __launch_bounds__(256) agg_part_update_kernel(const __grid_constant__ PartParams p) {
+    constexpr int R = 4;
+    constexpr uint32_t TILE = 256 * R;
+    const GenParams& g = p.g;
+    const uint32_t tiles_per_bucket = (p.cap + TILE - 1) / TILE;
+    const int64_t n_tiles = (int64_t) tiles_per_bucket << p.log2p;
+    const uint64_t stream = l2_policy_stream();
+    // Tiles are handed out in bucket-major order from a queue, not by a fixed stride: with a stride the CTAs drift apart
+    // (a quarter of the tiles are empty tails that cost nothing) and the slices of dozens of buckets compete for the L2
+    // (measured: 42 % hit rate on the table even with the evict_last hint).
+    __shared__ unsigned long long s_tile;
+    unsigned long long* queue = reinterpret_cast<unsigned long long*>(p.cursor + ((size_t) 32 << p.log2p));
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(queue, 1ULL);
+        __syncthreads();
+        const int64_t tile = (int64_t) s_tile;
+        if (tile >= n_tiles) break;
+        const uint32_t b = (uint32_t) (tile / tiles_per_bucket);
+        const uint32_t first = (uint32_t) (tile % tiles_per_bucket) * TILE;
         uint32_t n_b = p.cursor[(size_t) b * 32];
         if (n_b > p.cap) n_b = p.cap;
-        if (n_b == 0) continue;   // CTA-uniform
-        if (threadIdx.x == 0) s_groups = 0;
-        for (uint32_t s = threadIdx.x; s < S; s += PART_THREADS) {
-            keys[s] = GT_EMPTY;
-            cnt[s] = 0;
-            for (int c = 0; c < nc; ++c) cells[(size_t) c * S + s] = 0;
-        }
-        __syncthreads();
+        if (first >= n_b) continue;   // CTA-uniform
         const ulonglong2* recs = p.recs + (size_t) b * p.cap;
-        // U records per thread and step: the U record loads, then the U x n_cols gathers, are in flight together
-        constexpr int U = 4;
-        for (uint32_t r0 = threadIdx.x; r0 < n_b; r0 += PART_THREADS * U) {
-            uint64_t key[U];
-            uint32_t row[U];
-            uint64_t v[U][FA_MAX_COLS];
+        bool sel[R], plain[R];
+        uint64_t key[R];
+        uint32_t row[R];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t r = r0 + u * PART_THREADS;
-                key[u] = GT_EMPTY;   // no record
-                row[u] = 0;
-                if (r < n_b) {
-                    const ulonglong2 rec = recs[r];
-                    key[u] = rec.x;
-                    row[u] = (uint32_t) rec.y;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int c = 0; c < FA_MAX_COLS; ++c) v[u][c] = (c < f.n_cols && key[u] != GT_EMPTY) ? part_load_val(f, c, (int64_t) row[u]) : 0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (key[u] == GT_EMPTY) continue;
-                part_reduce_record(f, keys, cells, gslot, cnt, &s_groups, S, key[u], (int64_t) row[u], v[u][0], v[u][1], v[u][2]);
+        for (int j = 0; j < R; ++j) {
+            const uint32_t r = first + j * 256 + threadIdx.x;
+            sel[j] = plain[j] = r < n_b;
+            key[j] = 0;
+            row[j] = 0;
+            if (sel[j]) {
+                const ulonglong2 rec = ldg_rec_stream_hint(recs + r, stream);
+                key[j] = rec.x;
+                row[j] = (uint32_t) rec.y;
             }
         }
-        __syncthreads();
-        for (uint32_t s = threadIdx.x; s < S; s += PART_THREADS) {
-            if (keys[s] == GT_EMPTY) continue;
-            uint64_t w[FA_MAX_CELLS] = {0, 0, 0};
-            for (int c = 0; c < nc; ++c) w[c] = cells[(size_t) c * S + s];
-            fast_global_update(f, (int64_t) gslot[s], (uint64_t) cnt[s], w);
-        }
-        __syncthreads();
+        wide_update<R, true>(g, sel, key, plain, row);
     }
 }
 
-// option AGG_PARTITION = 1: partition from this many (estimated) groups.  Measured (profiles/r02_tuning.md): at 1e6 groups the
-// table (48 MB) lives in L2 and the global-table kernel wins 16 ms to 30; at 8.4e6 it is DRAM-resident and loses 72 ms to 49
-constexpr int64_t PART_MIN_GROUPS = (int64_t) 1 << 21;
+// option AGG_PARTITION = 1: partition when the table (all its arrays) is larger than this.  Measured (profiles/r02_tuning.md):
+// at 1e6 groups the table (48 MB) lives in the L2 and the global-table kernel alone wins; at 8.4e6 groups (805 MB) it loses
+constexpr int64_t PART_MIN_TABLE_BYTES = (int64_t) 96 << 20;
+constexpr int64_t PART_BUCKET_BYTES = (int64_t) 4 << 20;   // slice of the table one bucket updates (256 KB - 16 MB measured: no difference)
 constexpr int64_t PART_MAX_CHUNK = (int64_t) 1 << 27;    // rows per scatter + reduce round (bounds the scratch: 16 B per selected row)
 
-static int launch_part(const PartParams& pp, int pk, int sms, cudaStream_t s) {
-    const int64_t tiles = (pp.f.n + 2047) / 2048;
-    auto scatter = [&](auto kernel) -> int {
-        static int per_sm = 0;
-        if (per_sm == 0) {
+static int launch_part(const PartParams& pp, int sms, cudaStream_t s) {
+    auto resident = [&](auto kernel, int* per_sm) -> int {
+        if (*per_sm == 0) {
             int b = 0;
             VK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, 256, 0));
-            per_sm = b > 0 ? b : 1;
+            *per_sm = b > 0 ? b : 1;
         }
+        return VK_OK;
+    };
+    const int64_t tiles = (pp.g.n + 2047) / 2048;
+    auto scatter = [&](auto kernel) -> int {
+        static int per_sm = 0;
+        const int rc = resident(kernel, &per_sm);
+        if (rc != VK_OK) return rc;
         const int64_t cap = (int64_t) sms * per_sm;
         kernel<<<(unsigned) (tiles < cap ? tiles : cap), 256, 0, s>>>(pp);
         VK_CHECK_LAUNCH("agg_part_scatter_kernel");
         return VK_OK;
     };
     int rc;
-    switch (pk) {
+    switch (pp.g.pk) {
         case PK_NONE: rc = scatter(agg_part_scatter_kernel<PK_NONE>); break;
         case PK_MASK: rc = scatter(agg_part_scatter_kernel<PK_MASK>); break;
         case PK_F64_VEC: rc = scatter(agg_part_scatter_kernel<PK_F64_VEC>); break;
@@ -624,15 +576,12 @@ static int launch_part(const PartParams& pp, int pk, int sms, cudaStream_t s) {
         default: rc = scatter(agg_part_scatter_kernel<PK_GENERIC>); break;
     }
     if (rc != VK_OK) return rc;
-    const size_t smem = ((size_t) 16 + 8 * (size_t) pp.f.n_cells) << pp.log2s;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VK_CUDA(cudaFuncSetAttribute(agg_part_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin() - 1024));
-        attr_set = true;
-    }
-    const int64_t n_buckets = (int64_t) 1 << pp.log2p;
-    agg_part_reduce_kernel<<<(unsigned) (n_buckets < sms ? n_buckets : sms), PART_THREADS, smem, s>>>(pp);
-    VK_CHECK_LAUNCH("agg_part_reduce_kernel");
+    static int per_sm_update = 0;
+    rc = resident(agg_part_update_kernel, &per_sm_update);
+    if (rc != VK_OK) return rc;
+    const int64_t update_tiles = (int64_t) ((pp.cap + 1023) / 1024) << pp.log2p, cap = (int64_t) sms * per_sm_update;
+    agg_part_update_kernel<<<(unsigned) (update_tiles < cap ? update_tiles : cap), 256, 0, s>>>(pp);
+    VK_CHECK_LAUNCH("agg_part_update_kernel");
     return VK_OK;
 }
 
@@ -1973,10 +1922,8 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
     FastPlan plan;
     const bool plan_ok = a->n_keys == 1 && build_fast_plan(a, keys, values, &plan);
     bool fast = plan_ok && !a->fast_disabled;
-    // the partitioned plan (scatter + reduce) takes what the fused kernel takes, except 128-bit sums
-    bool part_ok = plan_ok && a->part_policy != 0;
-    for (int c = 0; part_ok && c < plan.n_cells; ++c)
-        if (plan.cells[c].op == CELL_ADD_I128 || plan.cells[c].op == CELL_I128_HI) part_ok = false;
+    // the partitioned plan (scatter + update per table slice) takes every single-key aggregate
+    const bool part_ok = a->n_keys == 1 && a->part_policy != 0;
     Pred dpred;
     int pk;
     int rc = make_pred(*pred, n_rows, &dpred, &pk);
@@ -2092,7 +2039,9 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             if (chunk > lim) chunk = lim;
         }
         // many groups: scatter into buckets + reduce per bucket instead of random updates of the global table
-        const bool use_part = !fast && part_ok && (a->part_policy == 2 || a->est_groups >= (double) PART_MIN_GROUPS);
+        // (the part of the table that is touched counts, not what is allocated: groups at the load limit)
+        const bool use_part = !fast && part_ok &&
+                              (a->part_policy == 2 || a->est_groups * (double) slot_bytes(a) / kMaxLoad > (double) PART_MIN_TABLE_BYTES);
         if (use_part && chunk > PART_MAX_CHUNK) chunk = PART_MAX_CHUNK;
         if (use_part) {
             // any row may be deferred (its bucket full, its group not creatable): the list must hold a whole chunk
@@ -2228,27 +2177,13 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         } else if (use_part) {
             a->last_path = 4;
             PartParams pp{};
-            FastParams& fp = pp.f;
-            fp.pred = dpred;
-            fp.key = gp.keys[0];
-            fp.key_mode = plan.key_mode;
-            fp.n_cols = plan.n_cols;
-            for (int v = 0; v < plan.n_cols; ++v) {
-                fp.col[v] = make_col(slice_col(plan.cols[v], pos, chunk));
-                fp.col_mode[v] = plan.col_mode[v];
-            }
-            fp.n_cells = plan.n_cells;
-            for (int c = 0; c < plan.n_cells; ++c) fp.cell[c] = plan.cells[c];
-            fp.n = chunk;
-            fp.row_limit = a->t.max_groups;
-            fp.table = a->t;
-            fp.replay = gp.replay;
-            // CTA table of the reduce pass: 8 Ki slots with at most one accumulator cell, else 4 Ki; buckets so that
-            // one holds a quarter of that many groups on average
-            pp.log2s = plan.n_cells <= 1 ? 13 : 12;
-            const double per_bucket = (double) ((int64_t) 1 << pp.log2s) / 4.0;
-            pp.log2p = 6;
-            while (pp.log2p < 13 && (double) ((int64_t) 1 << pp.log2p) * per_bucket < a->est_groups * 1.25) ++pp.log2p;
+            pp.g = gp;
+            // buckets = slices of the table of ~4 MB (all its arrays), so that the slice being updated stays in the L2
+            int log2cap = 0;
+            while (((int64_t) 1 << log2cap) < a->t.capacity) ++log2cap;
+            pp.log2p = 0;
+            while (pp.log2p < 12 && pp.log2p + 8 < log2cap && (a->t.capacity >> pp.log2p) * slot_bytes(a) > PART_BUCKET_BYTES) ++pp.log2p;
+            pp.shift = log2cap - pp.log2p;
             const int64_t n_buckets = (int64_t) 1 << pp.log2p;
             // records per bucket: from the share of the rows selected so far, 15 % over
             const uint64_t selected_so_far = a->h_ctr[CTR_SELECTED] + a->fast_spilled;
@@ -2259,15 +2194,15 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             pp.cap = (uint32_t) (mean * 1.1 + 6.0 * sqrt(mean) + 64.0);   // the hash spreads keys evenly: Poisson tails + 10 %
             const size_t recs = (size_t) n_buckets * pp.cap;
             uint8_t* scratch = nullptr;
-            const size_t cursor_bytes = (size_t) n_buckets * 128;
+            const size_t cursor_bytes = (size_t) n_buckets * 128 + 128;   // + the tile queue of the update pass
             VK_CUDA(cudaMallocAsync((void**) &scratch, cursor_bytes + recs * 16, s));
             pp.cursor = reinterpret_cast<unsigned int*>(scratch);
             pp.recs = reinterpret_cast<ulonglong2*>(scratch + cursor_bytes);
             VK_CUDA(cudaMemsetAsync(pp.cursor, 0, cursor_bytes, s));
-            VK_DBG("partitioned: buckets=%lld cap=%u slots=%d est_groups=%.0f scratch=%.1f MB", (long long) n_buckets, pp.cap,
-                   1 << pp.log2s, a->est_groups, (double) (cursor_bytes + recs * 16) / 1e6);
+            VK_DBG("partitioned: buckets=%lld cap=%u table=%.1f MB scratch=%.1f MB", (long long) n_buckets, pp.cap,
+                   (double) (a->t.capacity * slot_bytes(a)) / 1e6, (double) (cursor_bytes + recs * 16) / 1e6);
             const int span = prof_begin(a, s, chunk, 2);
-            rc = launch_part(pp, pk, sms, s);
+            rc = launch_part(pp, sms, s);
             prof_end(a, s, span);
             VK_CUDA(cudaFreeAsync(scratch, s));
             if (rc != VK_OK) return rc;
