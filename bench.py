@@ -26,7 +26,7 @@ config 5.  Its `e2e` is ONE logical query over the row-range-sharded host table:
 
 Also in the line: `configs` -- one sub-record per BASELINE.json config and per kernel path that the
 headline does not exercise (C2 filter, C3 group-by, C4 sort, the north-star query on non-dense keys =
-CTA hash table instead of direct group ids, and on 1e6 groups = global table), each with ms, rows/s
+CTA hash table instead of direct group ids, on 1e6 groups = global table, on 8.4e6 groups = partitioned plan), each with ms, rows/s
 and its own roofline fraction; `verified` -- the timed result checked, outside the timed region,
 against NumPy over the regenerated rows (all 1000 counts exact, sums to 1e-6).
 
@@ -392,6 +392,17 @@ def run_configs(vb, t8, rows, st, peak) -> dict:
     rec("northstar_1e6_groups", ms, best, rows, 24, launches_of(fn), groups=int(len(state["raw"][2])), agg_path=state["path"],
         query="same query, GROUP BY i3 (1e6 groups)")
     assert len(state["raw"][2]) == 1_000_000
+    state.clear()
+    # ---- north-star with 8.4e6 groups: the table (805 MB) is beyond the L2 -> partitioned plan ----
+    k23 = ops.arith("&", t8.column("i1"), (1 << 23) - 1, st)
+    fn, state = agg_query(k23, pa.int64(), t8.column("f0"))
+    ms, best = tm.run(fn, reps=3, warm=1)
+    rec("northstar_8e6_groups", ms, best, rows, 24, launches_of(fn), groups=int(len(state["raw"][2])), agg_path=state["path"],
+        query="same query, GROUP BY (i1 & 8388607) (8.4e6 groups; read-back of 200 MB of groups included)")
+    if rows >= 200_000_000:
+        assert len(state["raw"][2]) == 1 << 23
+    state.clear()
+    del k23
     # ---- C2: SELECT * FROM t WHERE f0 > 0.5 over {i1, i2, f0, f1}, 1e8 rows ----
     n2 = min(rows, 100_000_000)
     names = ["i1", "i2", "f0", "f1"]

@@ -41,6 +41,9 @@ profile() {
   # 2e8 rows = launches of 7.2 M, 65 M and 127 M rows per aggregate (chunks grow while the table is sized): the last one
   cap agg_wide_1e6 agg_wide 5 groups1e6
   VINUM_B200_AGG_WIDE=0 cap agg_general_1e6 agg_general 5 groups1e6
+  # 8.4e6 groups: the partitioned plan's two kernels, third round of the first aggregate (all groups exist)
+  cap agg_part_scatter_8m agg_part_scatter 2 groups8m
+  cap agg_part_update_8m agg_part_update 2 groups8m
   cap filter filter_kernel 2 filter
   cap sort_pass sort_pass 10 sort
   cap sort_prepare sort_prepare8 1 sort
