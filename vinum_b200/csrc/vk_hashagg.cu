@@ -2283,8 +2283,12 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
                 a->groups_ub = groups;
                 if (sizing && (uint64_t) new_groups * 64 < new_selected) {
                     a->sizing = false;   // fewer than 1 row in 64 opened a group: the table has seen most keys
-                } else if (pos + chunk < n_rows && selected > 0) {
-                    const double left = (double) (n_rows - pos - chunk) * ((double) selected / (double) a->rows_seen);
+                } else if (selected > 0) {
+                    // rows still to come: known within this update; after its last chunk the caller may or may not send more
+                    // batches (BaseAggregate::Next is called per batch), so room is made for at most 4 x the groups so far
+                    const bool last = pos + chunk >= n_rows;
+                    const double left = last ? 3.0 * (double) groups
+                                             : (double) (n_rows - pos - chunk) * ((double) selected / (double) a->rows_seen);
                     double est = estimate_groups((double) selected, (double) groups);
                     if (est <= 0 || est > (double) groups + left) est = (double) groups + left;   // every row left a new group
                     a->est_groups = est;
