@@ -2,7 +2,7 @@
 //
 // Replaces the row-at-a-time loop of BaseAggregate::Next
 // (vinum_cpp/src/operators/aggregate/base_aggregate.cpp:23-45) and its
-// SingleNumerical / MultiNumerical / OneGroup specialisations with three kernels:
+// SingleNumerical / MultiNumerical / OneGroup specialisations with these kernels:
 //
 //   agg_fast_kernel   low-cardinality single-key path (the north-star pipeline):
 //                     persistent CTAs stream row tiles with 16-byte loads, evaluate the
@@ -10,7 +10,14 @@
 //                     open-addressing table and accumulate COUNT / SUM(f64) there; one
 //                     flush per CTA into the global table.  No row is written back.
 //   agg_general_kernel any key arity / dtype / NULLs / function: straight to the global
-//                     (L2/HBM) table with native 64-bit atomics.
+//                     (L2/HBM) table with native 64-bit atomics, one row per thread.
+//   agg_wide_kernel   the same update for single-key tables (more groups than shared memory
+//                     holds): four rows per thread, every stage's loads issued together, linear
+//                     probing in lock step across the warp.
+//   agg_part_scatter_kernel + agg_part_update_kernel
+//                     tables beyond the L2: rows are scattered into buckets that are slices of
+//                     the table, then the table is updated slice by slice (wide_update over the
+//                     records) so that the slice stays in the L2.
 //   agg_onegroup_kernel un-grouped reduction (OneGroupAggregate::Next,
 //                     one_group_aggregate.cpp:9-26): register accumulate, warp shuffle,
 //                     one atomic per CTA.
