@@ -77,7 +77,9 @@ PATH_OPTS = {
     "split_entries": {"AGG_ENTRY": 2},                             # SUM array + {tag | COUNT} array
     "general": {"AGG_NOFAST": 1},                                  # global table, four rows per thread (agg_wide_kernel)
     "general_one_row": {"AGG_NOFAST": 1, "AGG_WIDE": 0},           # agg_general_kernel
-    "partitioned": {"AGG_NOFAST": 1, "AGG_PARTITION": 2},          # scatter into hash buckets + per-bucket reduce
+    "partitioned": {"AGG_NOFAST": 1, "AGG_PARTITION": 2},          # scatter into table slices + slice-by-slice update
+    "general_hot": {"AGG_NOFAST": 1, "AGG_HOT": 2},                # global-table kernel that merges a warp's updates of one slot
+    "partitioned_hot": {"AGG_NOFAST": 1, "AGG_PARTITION": 2, "AGG_HOT": 2},
     "no_partition": {"AGG_PARTITION": 0},
 }
 
@@ -140,7 +142,7 @@ def _many_keys(kind: str, n: int, rng) -> np.ndarray:
     raise ValueError(kind)
 
 
-@pytest.mark.parametrize("path", ["auto", "general", "general_one_row", "partitioned", "no_partition"])
+@pytest.mark.parametrize("path", ["auto", "general", "general_one_row", "partitioned", "partitioned_hot", "no_partition"])
 @pytest.mark.parametrize("chunks", [1, 3])
 @pytest.mark.parametrize("kind", ["uniform_2e6", "all_distinct", "sorted_runs", "skewed_long_tail"])
 def test_group_by_more_groups_than_the_first_table_holds(vb, stream, kind, chunks, path):
@@ -155,11 +157,11 @@ def test_group_by_more_groups_than_the_first_table_holds(vb, stream, kind, chunk
     got, paths = _device_groupby(vb, stream, table, ("p", ">", 0.25), dict(AGG_LEARN_LOG2=16, **PATH_OPTS[path]), chunks=chunks)
     assert_tables_match(got, want, key_cols=["k"], rtol=FLOAT_RTOL)
     assert paths[-1] in (2, 4)
-    if path == "partitioned":
+    if path.startswith("partitioned"):
         assert paths == [4] * chunks
 
 
-@pytest.mark.parametrize("path", ["partitioned", "general", "general_one_row"])
+@pytest.mark.parametrize("path", ["partitioned", "partitioned_hot", "general", "general_hot", "general_one_row"])
 @pytest.mark.parametrize("pred_kind", ["none", "f64_cmp", "i64_cmp", "i32_cmp", "mask", "expr"])
 def test_global_table_plans_every_predicate_kind_and_cell(vb, stream, pred_kind, path):
     """The plans behind the shared-memory kernel (partitioned scatter + reduce, four rows per thread, one row per
@@ -189,7 +191,7 @@ def test_global_table_plans_every_predicate_kind_and_cell(vb, stream, pred_kind,
                 "mask": lambda: ops.Predicate.from_mask(ops.mask_and(ops.compare(d["x"], ">", 0.0, stream), ops.compare(d["q"], "<", 3, stream), stream)),
                 "expr": lambda: ops.Predicate.expr([(None, d["x"]), ("*", 2.0)], ">", [(None, d["w"]), ("/", 1e10)])}[pred_kind]()
         agg.update([d["k"]], [None, d["w"], d["a"], d["y"]], pred, stream)
-        assert agg.last_path == (4 if path == "partitioned" else 2)
+        assert agg.last_path == (4 if path.startswith("partitioned") else 2)
     keys, aggs = agg.result_arrays(stream)
     agg.close()
     got = pa.table([keys[0]] + aggs, names=["k", "c", "mn", "sa", "ay"]).sort_by("k")

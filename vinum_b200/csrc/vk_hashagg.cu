@@ -249,7 +249,7 @@ __device__ __forceinline__ void wide_select_and_keys(const GenParams& p, int64_t
 
 // Stages 2 - 4: the slot of every selected row (lock-step probing), then the accumulator updates.  `row` = row ids
 // (for the value columns and the replay list).  Must be called by all 32 lanes of a warp together.
-template <int R, bool HINTS = false>
+template <int R, bool HINTS = false, bool HOT = false>
 __device__ __forceinline__ void wide_update(const GenParams& p, bool (&sel)[R], const uint64_t (&key)[R], const bool (&plain)[R],
                                             const uint32_t (&row)[R]) {   // row ids fit 32 bits (chunks are cut accordingly)
     const GTable& t = p.table;
@@ -339,12 +339,39 @@ __device__ __forceinline__ void wide_update(const GenParams& p, bool (&sel)[R], 
             sel[j] = false;
         }
     __syncwarp();
+    // A key that many lanes of the warp hold (skewed keys): same-address reductions serialise in one L2 slice at about one
+    // lane per cycle for the whole GPU, so half the rows on one key would cost 0.2 s per 1e9 rows.  The lanes that share the
+    // slot of the LOWEST selected lane are found with one shuffle and one vote per row slot; from HOT_MIN of them on, that
+    // lane alone updates the slot for all of them (COUNT: the population count; SUM(float64): a warp butterfly).  A template
+    // parameter: the host launches this variant when the learning launch saw one key hold >= 30 % of the rows (AGG_HOT).
+    constexpr int HOT_MIN = 4;
+    unsigned hot[R];
+    int64_t hot_slot[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        hot[j] = 0;
+        hot_slot[j] = -1;
+        if (HOT) {
+            const unsigned live = __ballot_sync(0xffffffffu, sel[j]);
+            if (live) {   // warp-uniform
+                hot_slot[j] = __shfl_sync(0xffffffffu, slot[j], __ffs(live) - 1);
+                const unsigned same = __ballot_sync(0xffffffffu, sel[j] && slot[j] == hot_slot[j]);
+                if (__popc(same) >= HOT_MIN) hot[j] = same;
+            }
+        }
+    }
 #pragma unroll
     for (int j = 0; j < R; ++j)
-        if (sel[j]) {
+        if (sel[j] && !(HOT && hot[j] && slot[j] == hot_slot[j])) {
             if (HINTS) red_add_u64_hint(t.count_star + slot[j], 1ULL, keep);
             else atomicAdd(reinterpret_cast<unsigned long long*>(t.count_star + slot[j]), 1ULL);
         }
+    if (HOT) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            if (hot[j] && lane == (unsigned) (__ffs(hot[j]) - 1))
+                atomicAdd(reinterpret_cast<unsigned long long*>(t.count_star + slot[j]), (unsigned long long) __popc(hot[j]));
+    }
     for (int f = 0; f < p.n_funcs; ++f) {
         const FuncSpec spec = p.specs[f];
         if (spec.acc == ACC_NONE) continue;
@@ -362,11 +389,23 @@ __device__ __forceinline__ void wide_update(const GenParams& p, bool (&sel)[R], 
                                  : reinterpret_cast<const uint64_t*>(vc.data)[row[j]];
             }
 #pragma unroll
-            for (int j = 0; j < R; ++j)
-                if (ok[j]) {
-                    if (HINTS) red_add_f64_hint(t.acc_lo[f] + slot[j], __longlong_as_double((long long) v[j]), keep);
-                    else atomicAdd(reinterpret_cast<double*>(t.acc_lo[f] + slot[j]), __longlong_as_double((long long) v[j]));
+            for (int j = 0; j < R; ++j) {
+                double x = __longlong_as_double((long long) v[j]);
+                bool mine = ok[j];
+                if (HOT && hot[j]) {   // warp-uniform
+                    const bool member = ok[j] && slot[j] == hot_slot[j];
+                    double part = member ? x : 0.0;
+                    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                    if (member) {
+                        mine = lane == (unsigned) (__ffs(hot[j]) - 1);
+                        x = part;
+                    }
                 }
+                if (mine) {
+                    if (HINTS) red_add_f64_hint(t.acc_lo[f] + slot[j], x, keep);
+                    else atomicAdd(reinterpret_cast<double*>(t.acc_lo[f] + slot[j]), x);
+                }
+            }
             continue;
         }
 #pragma unroll
@@ -399,7 +438,7 @@ __device__ __forceinline__ void wide_update(const GenParams& p, bool (&sel)[R], 
 // gt1_find_or_insert makes a plain load a complete look-up when the key is already there), then the
 // value loads, then the fire-and-forget reductions.  Rows that meet a foreign slot probe on in lock step
 // with the other rows of the warp; an empty slot is claimed by the same CAS as in gt1_find_or_insert.
-template <int PK, int R>
+template <int PK, int R, bool HOT>
 __global__ void __launch_bounds__(256) agg_wide_kernel(const __grid_constant__ GenParams p) {
     constexpr int64_t TILE = 256 * R;
     const int64_t n_tiles = (p.n - p.row_begin + TILE - 1) / TILE;
@@ -418,13 +457,13 @@ __global__ void __launch_bounds__(256) agg_wide_kernel(const __grid_constant__ G
             n_selected += sel[j] ? 1u : 0u;
             row[j] = (uint32_t) (base + (j / 2) * 512 + (j & 1));
         }
-        wide_update<R>(p, sel, key, plain, row);
+        wide_update<R, false, HOT>(p, sel, key, plain, row);
     }
     count_selected(p, n_selected);
 }
 
 // One launch: as many CTAs as are resident at once (the tile loop is persistent).
-static int launch_wide(const GenParams& gp, int sms, cudaStream_t s) {
+static int launch_wide(const GenParams& gp, bool hot, int sms, cudaStream_t s) {
     constexpr int R = 4;
     const int64_t tiles = (gp.n - gp.row_begin + 256 * R - 1) / (256 * R);
     auto go = [&](auto kernel) -> int {
@@ -440,11 +479,11 @@ static int launch_wide(const GenParams& gp, int sms, cudaStream_t s) {
         return VK_OK;
     };
     switch (gp.pk) {
-        case PK_NONE: return go(agg_wide_kernel<PK_NONE, R>);
-        case PK_MASK: return go(agg_wide_kernel<PK_MASK, R>);
-        case PK_F64_VEC: return go(agg_wide_kernel<PK_F64_VEC, R>);
-        case PK_I64_VEC: return go(agg_wide_kernel<PK_I64_VEC, R>);
-        default: return go(agg_wide_kernel<PK_GENERIC, R>);
+        case PK_NONE: return hot ? go(agg_wide_kernel<PK_NONE, R, true>) : go(agg_wide_kernel<PK_NONE, R, false>);
+        case PK_MASK: return hot ? go(agg_wide_kernel<PK_MASK, R, true>) : go(agg_wide_kernel<PK_MASK, R, false>);
+        case PK_F64_VEC: return hot ? go(agg_wide_kernel<PK_F64_VEC, R, true>) : go(agg_wide_kernel<PK_F64_VEC, R, false>);
+        case PK_I64_VEC: return hot ? go(agg_wide_kernel<PK_I64_VEC, R, true>) : go(agg_wide_kernel<PK_I64_VEC, R, false>);
+        default: return hot ? go(agg_wide_kernel<PK_GENERIC, R, true>) : go(agg_wide_kernel<PK_GENERIC, R, false>);
     }
 }
 
@@ -506,6 +545,7 @@ __global__ void __launch_bounds__(256) agg_part_scatter_kernel(const __grid_cons
     count_selected(g, n_selected);
 }
 
+template <bool HOT>
 __global__ void __launch_bounds__(256) agg_part_update_kernel(const __grid_constant__ PartParams p) {
     constexpr int R = 4;
     constexpr uint32_t TILE = 256 * R;
@@ -545,7 +585,7 @@ __global__ void __launch_bounds__(256) agg_part_update_kernel(const __grid_const
                 row[j] = (uint32_t) rec.y;
             }
         }
-        wide_update<R, true>(g, sel, key, plain, row);
+        wide_update<R, true, HOT>(g, sel, key, plain, row);
     }
 }
 
@@ -555,7 +595,7 @@ constexpr int64_t PART_MIN_TABLE_BYTES = (int64_t) 96 << 20;
 constexpr int64_t PART_BUCKET_BYTES = (int64_t) 4 << 20;   // slice of the table one bucket updates (256 KB - 16 MB measured: no difference)
 constexpr int64_t PART_MAX_CHUNK = (int64_t) 1 << 27;    // rows per scatter + reduce round (bounds the scratch: 16 B per selected row)
 
-static int launch_part(const PartParams& pp, int sms, cudaStream_t s) {
+static int launch_part(const PartParams& pp, bool hot, int sms, cudaStream_t s) {
     auto resident = [&](auto kernel, int* per_sm) -> int {
         if (*per_sm == 0) {
             int b = 0;
@@ -583,13 +623,17 @@ static int launch_part(const PartParams& pp, int sms, cudaStream_t s) {
         default: rc = scatter(agg_part_scatter_kernel<PK_GENERIC>); break;
     }
     if (rc != VK_OK) return rc;
-    static int per_sm_update = 0;
-    rc = resident(agg_part_update_kernel, &per_sm_update);
-    if (rc != VK_OK) return rc;
-    const int64_t update_tiles = (int64_t) ((pp.cap + 1023) / 1024) << pp.log2p, cap = (int64_t) sms * per_sm_update;
-    agg_part_update_kernel<<<(unsigned) (update_tiles < cap ? update_tiles : cap), 256, 0, s>>>(pp);
-    VK_CHECK_LAUNCH("agg_part_update_kernel");
-    return VK_OK;
+    const int64_t update_tiles = (int64_t) ((pp.cap + 1023) / 1024) << pp.log2p;
+    auto update = [&](auto kernel) -> int {
+        static int per_sm = 0;
+        const int urc = resident(kernel, &per_sm);
+        if (urc != VK_OK) return urc;
+        const int64_t cap = (int64_t) sms * per_sm;
+        kernel<<<(unsigned) (update_tiles < cap ? update_tiles : cap), 256, 0, s>>>(pp);
+        VK_CHECK_LAUNCH("agg_part_update_kernel");
+        return VK_OK;
+    };
+    return hot ? update(agg_part_update_kernel<true>) : update(agg_part_update_kernel<false>);
 }
 
 // ============================================================ one-group kernel
@@ -2045,10 +2089,15 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             const int64_t lim = a->rows_seen < ((int64_t) 1 << 17) ? ((int64_t) 1 << 20) : 8 * a->rows_seen;
             if (chunk > lim) chunk = lim;
         }
+        // skewed keys on the global-table kernels: the variant that merges a warp's updates of one slot (option AGG_HOT)
+        const bool hot_keys = a->hot_policy == 2 || (a->hot_policy == 1 && a->hot_share >= 0.3);
         // many groups: scatter into buckets + reduce per bucket instead of random updates of the global table
         // (the part of the table that is touched counts, not what is allocated: groups at the load limit)
+        // (and not with one key holding a third of the rows: they would all land in ONE bucket, overflow it and come back
+        // through the replay list -- measured 245 ms against 17 for the global-table kernel with the hot-slot merge)
         const bool use_part = !fast && part_ok &&
-                              (a->part_policy == 2 || a->est_groups * (double) slot_bytes(a) / kMaxLoad > (double) PART_MIN_TABLE_BYTES);
+                              (a->part_policy == 2 ||
+                               (!hot_keys && a->est_groups * (double) slot_bytes(a) / kMaxLoad > (double) PART_MIN_TABLE_BYTES));
         if (use_part && chunk > PART_MAX_CHUNK) chunk = PART_MAX_CHUNK;
         if (use_part) {
             // any row may be deferred (its bucket full, its group not creatable): the list must hold a whole chunk
@@ -2209,7 +2258,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             VK_DBG("partitioned: buckets=%lld cap=%u table=%.1f MB scratch=%.1f MB", (long long) n_buckets, pp.cap,
                    (double) (a->t.capacity * slot_bytes(a)) / 1e6, (double) (cursor_bytes + recs * 16) / 1e6);
             const int span = prof_begin(a, s, chunk, 2);
-            rc = launch_part(pp, sms, s);
+            rc = launch_part(pp, hot_keys, sms, s);
             prof_end(a, s, span);
             VK_CUDA(cudaFreeAsync(scratch, s));
             if (rc != VK_OK) return rc;
@@ -2219,7 +2268,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
             int64_t need = (chunk + 255) / 256, capb = (int64_t) sms * 8;
             const int span = prof_begin(a, s, chunk, 2);
             // single-key tables: several rows per thread, the loads of each stage issued together
-            if (a->t.single && a->wide_rows != 0) rc = launch_wide(gp, sms, s);
+            if (a->t.single && a->wide_rows != 0) rc = launch_wide(gp, hot_keys, sms, s);
             else {
                 agg_general_kernel<<<(unsigned) (need < capb ? need : capb), 256, 0, s>>>(gp);
                 VK_CHECK_LAUNCH("agg_general_kernel");
