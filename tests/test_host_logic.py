@@ -422,3 +422,53 @@ def test_every_option_has_a_default_and_a_name():
     with vb.options(AGG_DICT=0, SORT_PREP=0):
         assert vb.get_option("AGG_DICT") == 0 and vb.get_option("SORT_PREP") == 0
     assert vb.get_option("AGG_DICT") == 1 and vb.get_option("SORT_PREP") == 4
+
+
+def test_string_rank_codes_are_order_preserving_and_keep_nulls():
+    """vinum_b200.strings: the int32 code of a row is the rank of its string among the batch's distinct values
+    (binary order, like std::string::operator< in StringMinMaxFunc, agg_funcs.h:219-261); NULL stays NULL."""
+    import pyarrow as pa
+    from vinum_b200.strings import key_matrix, rank_codes
+    values = ["pear", None, "apple", "pear", "zz", "", "Apple", "éclair", "apple pie", None]
+    codes, ordered = rank_codes(pa.array(values, type=pa.string()))
+    assert ordered.to_pylist() == sorted({v for v in values if v is not None}, key=lambda s: s.encode())
+    got = codes.to_pylist()
+    for v, c in zip(values, got):
+        assert (c is None) == (v is None)
+        if v is not None:
+            assert ordered[c].as_py() == v
+    a, b = np.array(values, dtype=object), np.array(got, dtype=object)
+    for i in range(len(values)):
+        for j in range(len(values)):
+            if values[i] is not None and values[j] is not None:
+                assert (a[i].encode() < a[j].encode()) == (b[i] < b[j])
+    codes, ordered = rank_codes(pa.array([None, None], type=pa.string()))
+    assert codes.to_pylist() == [None, None] and len(ordered) == 0
+    # group identity for the host merge: NULL == NULL, NaN payloads by their bits, -0.0 != +0.0 (as the device table)
+    m = key_matrix([pa.array([1, None, 1, None]), pa.array([float("nan"), 0.0, float("nan"), -0.0])], 4)
+    assert m.shape == (4, 4)
+    assert (m[0] == m[2]).all() and not (m[1] == m[3]).all()
+    assert key_matrix([], 3).shape == (3, 0)
+
+
+def test_pinned_result_pool_keeps_the_large_blocks():
+    """aggregate._pinned_give_back: over its budget the free list drops the SMALLEST block (pinning and unpinning a
+    400 MB block costs ~0.1 s each, and a loop of large queries asks for the same size again)."""
+    import vinum_b200.aggregate as A
+
+    class Block:
+        def __init__(self, mb):
+            self.nbytes = mb << 20
+
+    saved = list(A._PINNED_POOL)
+    try:
+        A._PINNED_POOL.clear()
+        for mb in (50, 50, 50, 400, 400, 400, 400, 400, 400):
+            A._pinned_give_back(Block(mb))
+        sizes = sorted(b.nbytes >> 20 for b in A._PINNED_POOL)
+        assert sum(sizes) << 20 <= A._PINNED_POOL_BYTES and len(sizes) <= A._PINNED_POOL_MAX
+        assert sizes.count(400) >= 4 and sizes.count(50) <= 1
+        got = A._pinned_take(300 << 20)
+        assert got.nbytes == 400 << 20 and got not in A._PINNED_POOL
+    finally:
+        A._PINNED_POOL[:] = saved
