@@ -319,6 +319,11 @@ int vk_agg_peer_merge(VkAgg* agg, VkPeer* peer, uint64_t epoch, VkStream stream)
  * (0 = none, 1 = shared-memory table, 2 = global table, 3 = one-group reduction,
  * 4 = partitioned: scatter into buckets that are slices of the global table + update slice by slice) */
 int vk_agg_last_path(VkAgg* agg);
+/* The estimate behind the sizing of the global table (host arithmetic, no device work): number of distinct keys G
+ * if `groups` distinct keys were seen among `selected_rows` rows drawn evenly, g = G (1 - exp(-n / G)); 0 when
+ * groups >= selected_rows (no upper bound).  The reference sizes nothing in advance (std::unordered_map grows,
+ * single_numerical_hash_aggregate.cpp:15-46); exported for tests. */
+double vk_agg_estimate_groups(double selected_rows, double groups);
 /* Optional per-launch kernel timing (CUDA events recorded on the launch stream, resolved
  * lazily: no extra synchronisation).  vk_agg_profile_read returns, for `path` (1/2 as
  * above), the summed kernel milliseconds, the number of launches and the rows they

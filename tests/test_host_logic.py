@@ -472,3 +472,23 @@ def test_pinned_result_pool_keeps_the_large_blocks():
         assert got.nbytes == 400 << 20 and got not in A._PINNED_POOL
     finally:
         A._PINNED_POOL[:] = saved
+
+
+def test_cardinality_estimate_behind_the_table_sizing():
+    """vk_agg_estimate_groups: from (rows that passed the predicate, groups so far) to the final number of groups under
+    even draws; the host grows the global table to 1.02 x this BEFORE the rows arrive."""
+    import vinum_b200 as vb
+    est = vb.lib.vk_agg_estimate_groups
+    rng = np.random.default_rng(3)
+    for true_groups in (1_000, 100_000, 1_000_000):
+        for share in (0.1, 0.45, 1.0, 3.0):
+            n = int(true_groups * share)
+            seen = len(np.unique(rng.integers(0, true_groups, n)))
+            got = est(float(n), float(seen))
+            if share >= 0.45 or true_groups >= 100_000:     # enough collisions for the estimate to be tight
+                assert abs(got - true_groups) / true_groups < 0.05, (true_groups, share, seen, got)
+            else:
+                assert got > seen
+    assert est(1000.0, 1000.0) == 0.0        # every row its own group: no upper bound
+    assert est(0.0, 0.0) == 0.0
+    assert est(1e9, 1000.0) == pytest.approx(1000.0, rel=1e-6)   # saturated

@@ -211,6 +211,7 @@ SIGNATURES = {
     "vk_agg_peer_send": (_int, [_p, _p, _int, _u64, _p]),
     "vk_agg_peer_merge": (_int, [_p, _p, _u64, _p]),
     "vk_agg_last_path": (_int, [_p]),
+    "vk_agg_estimate_groups": (C.c_double, [C.c_double, C.c_double]),
     "vk_agg_profile": (_int, [_p, _int]),
     "vk_agg_profile_read": (_int, [_p, _int, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "vk_sort_scratch_bytes": (_u64, [_i64]),

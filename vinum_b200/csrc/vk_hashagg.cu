@@ -1377,8 +1377,8 @@ double estimate_groups(double n, double g) {
     if (g <= 0 || n <= 0) return 0;
     if (g >= n) return 0;
     const double r = g / n;
-    double lo = 1e-9, hi = 64.0;
-    for (int it = 0; it < 60; ++it) {
+    double lo = 1e-9, hi = 2.0 / r + 64.0;   // x -> 1 / r when the keys have all been seen many times (G -> g)
+    for (int it = 0; it < 100; ++it) {
         const double x = 0.5 * (lo + hi);
         if ((1.0 - exp(-x)) / x > r) lo = x;
         else hi = x;
@@ -1823,6 +1823,7 @@ int vk_agg_destroy(VkAgg* a) {
 }
 
 int vk_agg_last_path(VkAgg* a) { return a ? a->last_path : 0; }
+double vk_agg_estimate_groups(double selected_rows, double groups) { return estimate_groups(selected_rows, groups); }
 
 int vk_agg_profile(VkAgg* a, int enable) {
     VK_REQUIRE(a, "vk_agg_profile: agg is NULL");
