@@ -1,7 +1,7 @@
 """High-cardinality GROUP BY on ONE box: whole-operator ms (create + update + packed result; `_update` = up to the end of the update's kernels) of the north-star
 query with the key folded to G groups (G beyond what the shared-memory tables hold goes to the global table),
-as chosen automatically, with the partitioned plan forced (scatter into hash buckets + per-bucket reduce in shared
-memory, option AGG_PARTITION), with the four-rows-per-thread global-table kernel and with the one-row-per-thread one.  Counts are
+as chosen automatically, with the partitioned plan forced (scatter into buckets that are slices of the table + slice-by-slice
+update, option AGG_PARTITION), with the four-rows-per-thread global-table kernel and with the one-row-per-thread one.  Counts are
 checked against np.bincount for the first setting of every G.
     python scripts/groups_probe.py [ROWS]"""
 import ctypes as C, json, os, statistics, sys

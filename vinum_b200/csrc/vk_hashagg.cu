@@ -2092,7 +2092,7 @@ int vk_agg_update(VkAgg* a, const VkPredicate* pred, int64_t n_rows, const VkCol
         }
         // skewed keys on the global-table kernels: the variant that merges a warp's updates of one slot (option AGG_HOT)
         const bool hot_keys = a->hot_policy == 2 || (a->hot_policy == 1 && a->hot_share >= 0.3);
-        // many groups: scatter into buckets + reduce per bucket instead of random updates of the global table
+        // table beyond the L2: scatter into buckets (= slices of the table) + update slice by slice instead of at random
         // (the part of the table that is touched counts, not what is allocated: groups at the load limit)
         // (and not with one key holding a third of the rows: they would all land in ONE bucket, overflow it and come back
         // through the replay list -- measured 245 ms against 17 for the global-table kernel with the hot-slot merge)
