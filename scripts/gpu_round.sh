@@ -60,6 +60,7 @@ probes() {
   run agg_ab 600 python -u scripts/agg_ab.py
   run groups 600 python -u scripts/groups_probe.py
   run skew 900 python -u scripts/skew_probe.py
+  run hot 300 python -u scripts/hot_probe.py
   run ingest 300 python -u scripts/ingest_probe.py
   run filter 120 python -u scripts/gpu_check.py filter
   run sort 120 python -u scripts/gpu_check.py sort
