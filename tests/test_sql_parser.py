@@ -108,6 +108,18 @@ def test_group_having_order_limit():
     assert q.distinct and q.limit is None and q.offset == 0     # OFFSET is only read next to LIMIT
 
 
+def test_non_reserved_keywords_are_column_names():
+    """BY, FIRST, LAST, NULLS are non-reserved in the PostgreSQL grammar the reference parses with (pglast):
+    `select first from t` names a column there; the clause keywords keep their meaning in clause position."""
+    q = P.parse_sql("select first, last + 1 as l, nulls from t where by > 2 group by first order by last desc nulls first",
+                    ["first", "last", "nulls", "by"])
+    assert [getattr(c, "name", None) for c in q.select] == ["first", None, "nulls"]
+    assert q.select[1].op == A.Op.ADDITION and q.select[1].args[0].name == "last" and q.select[1].alias == "l"
+    assert q.where.op == A.Op.GREATER_THAN and q.where.args[0].name == "by"
+    assert [g.name for g in q.group_by] == ["first"]
+    assert [o.name for o in q.order_by] == ["last"] and [s.name for s in q.sort_order] == ["DESC"]
+
+
 def test_string_literal_quotes_and_concat():
     q = parse("select city || '_' || 'it''s' from t")
     e = q.select[0]

@@ -29,6 +29,8 @@ _KEYWORDS = {"select", "distinct", "from", "where", "group", "by", "having", "or
              "offset", "and", "or", "not", "is", "null", "in", "between", "like", "as", "true", "false",
              "nulls", "first", "last"}
 
+_NON_RESERVED = {"by", "first", "last", "nulls"}
+
 _TOKEN_RE = re.compile(r"""
     (?P<ws>\s+|--[^\n]*)
   | (?P<number>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?)
@@ -340,6 +342,11 @@ class Parser:
         if t.kind == "qident":
             self._advance()
             return Column(_unquote(t))
+        if t.kind == "kw" and t.text in _NON_RESERVED:
+            # BY / FIRST / LAST / NULLS are non-reserved in PostgreSQL (the grammar pglast gives the reference,
+            # vinum/parser/parser.py): where an operand is expected they are ordinary column names
+            self._advance()
+            return Column(t.text)
         if t.kind == "ident":
             self._advance()
             if self._accept_op("("):
